@@ -1,0 +1,121 @@
+/*
+ * rdb200.h — C ABI of librdb200.so, the B200 (sm_100a) replay engine for ReverseDiff compiled tapes.
+ *
+ * The reference (JuliaDiff/ReverseDiff.jl v1.16.2, pure Julia) has no FFI; its seam for the tape-replay
+ * path is multiple dispatch on the tape object.  Each entry point below replaces one such method; the
+ * Julia shim (julia/ReverseDiffB200.jl) binds them with `ccall`.  All citations are
+ * relative to the reference tree.
+ *
+ * Conventions: every function returning `int` returns 0 on success and a negative RDB_E* code on
+ * failure; the message is available from rdb_last_error() (thread-local).  No exceptions cross the ABI.
+ * Arrays are column-major and contiguous (the reference requires IndexLinear storage, src/tracked.jl:77).
+ * The caller owns host arrays; the engine owns all device memory.  A tape handle is NOT thread-safe (the
+ * reference mutates tapes in place, src/tracked.jl:155-173); calls are synchronous on return unless
+ * stated otherwise.  There is no CPU fallback: without a CUDA device every compute entry point fails
+ * with RDB_ENODEVICE.
+ */
+#ifndef RDB200_H
+#define RDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDB_OK 0
+#define RDB_EINVAL (-1)       /* malformed program / bad argument                                 */
+#define RDB_EUNSUPPORTED (-2) /* instruction kind that cannot be lowered (e.g. @grad closures)     */
+#define RDB_ECUDA (-3)        /* CUDA runtime error                                                */
+#define RDB_ENODEVICE (-4)    /* no CUDA device: the engine has no CPU path                        */
+#define RDB_ENOMEM (-5)
+
+#define RDB_F64 0
+#define RDB_F32 1
+
+typedef struct rdb_ctx rdb_ctx;
+typedef struct rdb_tape rdb_tape;
+
+typedef struct rdb_options {
+    int32_t fuse_elementwise; /* 1 = fuse runs of adjacent elementwise instructions (default 1)     */
+    int32_t seed_block;       /* R: seed rows / Hessian columns processed per batched sweep (0=auto) */
+    int32_t use_graph;        /* 1 = replay gradient! through a captured CUDA graph (default 1)      */
+    int32_t profile;          /* 1 = record per-step CUDA-event timings for rdb_tape_stats           */
+    int32_t reserved[4];
+} rdb_options;
+
+/* ---- library / context --------------------------------------------------------------------------- */
+const char *rdb_version(void);
+const char *rdb_last_error(void);
+/* One context per process and device (one process per GPU). */
+rdb_ctx *rdb_ctx_create(int device_id);
+void rdb_ctx_destroy(rdb_ctx *);
+/* Adopt a caller stream (e.g. torch's current stream) instead of the context's own. */
+int rdb_ctx_set_stream(rdb_ctx *, void *cuda_stream);
+int rdb_ctx_synchronize(rdb_ctx *);
+
+/* ---- tape life cycle ----------------------------------------------------------------------------- */
+/* Replaces ReverseDiff.compile(t::AbstractTape) (src/api/tape.jl:146-149) and the CompiledTape it builds
+ * (:55-59,101-106).  `program` is the flat tape program of reversediff.jl_b200/program.py (= Appendix C
+ * of SURVEY.md); it is validated, CONSTs and index maps are copied to the device.  Returns NULL on
+ * failure.  Unsupported instruction kinds make the load fail (no silent fallback). */
+rdb_tape *rdb_tape_load(rdb_ctx *, const void *program, size_t nbytes, const rdb_options *opts);
+void rdb_tape_destroy(rdb_tape *);
+
+/* value!(input_hook(tape)[slot], x) (src/api/tape.jl:40-44 -> src/tracked.jl:156-163). */
+int rdb_tape_set_input(rdb_tape *, int input_slot, const void *data, int is_device);
+
+/* forward_pass!(::CompiledTape) (src/api/tape.jl:122-127; src/tape.jl:75-80). */
+int rdb_forward(rdb_tape *);
+/* seeded_reverse_pass! for a scalar output minus result extraction: pull_value!(output);
+ * unseed!(input); seed!(output); reverse_pass!(tape) (src/api/utils.jl:27-33; src/api/tape.jl:129-134). */
+int rdb_reverse_scalar_seed(rdb_tape *);
+
+/* gradient!(result, tape::CompiledGradient, input) (src/api/gradients.jl:78-82) after set_input:
+ * forward sweep + seeded reverse sweep + extract_result! (src/api/utils.jl:77-100).
+ * result_ptrs[i] receives deriv(input[i]) (NULL = skip); value_out (host, element type of the tape, may be
+ * NULL) receives value(output) as the DiffResult methods do (src/api/utils.jl:96-100). */
+int rdb_gradient(rdb_tape *, void *const *result_ptrs, int results_on_device, void *value_out);
+
+/* jacobian!(result, tape::CompiledJacobian, input) (src/api/jacobians.jl:120-124) restricted to the seed
+ * rows [row_begin,row_end) of seeded_reverse_pass! (src/api/utils.jl:44-58): one forward sweep, then the
+ * rows are replayed in blocks of `seed_block` one-hot seeds.  `result` addresses element (row_begin, 0) of
+ * a column-major (rows x length(input[slot])) matrix with leading dimension `ld` (ld = length(output) for
+ * the full matrix, src/api/utils.jl:45).  value_out (may be NULL; host or device like `result`) receives
+ * value(output) (extract_result_value!, src/api/utils.jl:60-64). */
+int rdb_jacobian(rdb_tape *, int input_slot, int64_t row_begin, int64_t row_end, void *result, int64_t ld,
+                 int result_on_device, void *value_out);
+
+/* hessian!(result, tape::CompiledHessian, input) (src/api/hessians.jl:86-90) restricted to columns
+ * [col_begin,col_end).  Mechanism differs from the reference on purpose (BASELINE.json north_star): the
+ * reference replays a scalar reverse-over-reverse tape n times (src/api/tape.jl:285-293); here the inner
+ * array tape of f is replayed forward-over-reverse with `seed_block` tangent directions per sweep.
+ * `result` addresses element (0, col_begin) of the column-major n x n matrix, leading dimension `ld`.
+ * grad_out / value_out (may be NULL) receive the gradient and primal as the DiffResult method does
+ * (src/api/hessians.jl:92-97). */
+int rdb_hessian(rdb_tape *, int64_t col_begin, int64_t col_end, void *result, int64_t ld, int result_on_device,
+                void *grad_out, void *value_out);
+
+/* Debug / parity accessors: value(x), deriv(x) of any tape buffer, copied to host. */
+int rdb_get_value(rdb_tape *, int buffer_id, void *dst_host);
+int rdb_get_deriv(rdb_tape *, int buffer_id, void *dst_host);
+int64_t rdb_buffer_size(rdb_tape *, int buffer_id);
+/* Per-step report (kernel name, time, algorithmic bytes / flops) as JSON; needs opts.profile = 1. */
+int rdb_tape_stats(rdb_tape *, char *json, size_t cap);
+/* Number of kernel launches issued by the engine on this tape since load (bench "gpu_launches"). */
+int64_t rdb_tape_launch_count(rdb_tape *);
+
+/* ---- single-kernel entry points (kernel tests and per-kernel roofline measurement) ----------------- */
+/* C <- alpha*op(A)*op(B) + beta*C, column-major device pointers; the kernel behind every `*` instruction
+ * (mul!, src/derivatives/linalg/arithmetic.jl:245-255,272-285). Asynchronous on the context stream. */
+int rdb_gemm(rdb_ctx *, int dtype, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
+             const void *A, int64_t lda, const void *B, int64_t ldb, double beta, void *C, int64_t ldc);
+/* out = a + sign*b and block-reduced sum(out) (array +/- fused with sum, arithmetic.jl:55-61 +
+ * reductions.jl:23-27); sum_out is a device scalar. */
+int rdb_add_sum(rdb_ctx *, int dtype, int64_t n, const void *a, const void *b, double sign, void *out, void *sum_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDB200_H */

@@ -1,0 +1,445 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product; imported only by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+
+CPU restatement (numpy) of ReverseDiff's compiled-tape replay semantics, instruction by
+instruction, for the opcode subset of the tape program.  All citations are relative to
+/root/reference (JuliaDiff/ReverseDiff.jl v1.16.2).
+
+PARITY PINNING.  The reference is pure Julia and no `julia` binary exists in this image, so
+the reference cannot be executed here; it also stores no golden vectors for the five
+benchmark configs ("parity unpinned" for those sizes).  The restatement is pinned instead on
+(i) every in-scope known-answer literal of the reference's tests (LinAlgTests.jl:281-282,
+compat/CompatTests.jl:5-11, the index iterables of TrackedTests.jl:641-716), committed under
+tests/golden/reference_literals.json, (ii) independent closed forms and
+(iii) central finite differences — see tests/test_oracle.py.
+
+Third-party arithmetic restated here (not under /root/reference; compat ranges only,
+Project.toml:20-36): ForwardDiff "0.10, 1" Dual arithmetic with DiffRules "1.4" derivative
+rules (tanh' = 1 - tanh², exp' = exp, log' = 1/x, sqrt' = 1/(2√x), abs2' = 2x, (a/b)' =
+(1/b, -a/b²), x^n → n·x^(n-1), …), DiffResults value+partials records, and
+LinearAlgebra.mul! → OpenBLAS gemm (here numpy → OpenBLAS).
+
+The file parses the wire format on its own (it does not import the product package), so a
+serialisation bug cannot cancel out between product and checker.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+MAGIC = 0x3030324244525052
+VERSION = 2
+MAX_ARGS, MAX_DIMS = 4, 4
+
+BUF_TA, BUF_TR, BUF_CONST = 0, 1, 2
+CLS_TA, CLS_IDX, CLS_CONST, CLS_TR = 0, 1, 2, 3
+IDX_NONE, IDX_EXPLICIT, IDX_TRANSPOSE = 0, 1, 2
+(OP_MUL, OP_ADD, OP_SUB, OP_NEG, OP_SUM, OP_MEAN, OP_NBCAST, OP_MAP, OP_BCAST,
+ OP_BCAST_ADD, OP_BCAST_SUB, OP_BCAST_MUL) = range(1, 13)
+OP_GETINDEX = 16
+ELEMENTWISE = (OP_NBCAST, OP_MAP, OP_BCAST, OP_BCAST_ADD, OP_BCAST_SUB, OP_BCAST_MUL)
+(E_CONST, E_ADD, E_SUB, E_MUL, E_DIV, E_NEG, E_POWI, E_POW, E_TANH, E_EXP, E_LOG, E_SQRT,
+ E_SIN, E_COS, E_ABS2, E_ABS, E_MAX, E_MIN, E_INV, E_SIGMOID, E_ARG) = range(1, 22)
+
+_HEADER = np.dtype([
+    ("magic", "<u8"), ("version", "<u4"), ("dtype", "<u4"),
+    ("n_buffers", "<u4"), ("n_instr", "<u4"), ("n_inputs", "<u4"), ("output_buffer", "<i4"),
+    ("off_buffers", "<u8"), ("off_inputs", "<u8"), ("off_instr", "<u8"),
+    ("off_idx", "<u8"), ("n_idx", "<u8"), ("off_expr", "<u8"), ("n_expr", "<u8"),
+    ("off_fconst", "<u8"), ("n_fconst", "<u8"), ("off_const", "<u8"), ("n_const", "<u8"),
+    ("total_bytes", "<u8")])
+_BUFFER = np.dtype([("kind", "<i4"), ("ndims", "<i4"), ("dims", "<i8", (MAX_DIMS,)),
+                    ("alias_of", "<i4"), ("pad", "<i4"), ("const_offset", "<i8")])
+_OPERAND = np.dtype([("buffer", "<i4"), ("cls", "<i4"), ("tracked", "<i4"), ("idx_kind", "<i4"),
+                     ("idx_offset", "<i8"), ("idx_len", "<i8"), ("ndims", "<i4"), ("pad", "<i4"),
+                     ("dims", "<i8", (MAX_DIMS,)), ("bound", "<i8", (MAX_DIMS,))])
+_INSTR = np.dtype([("opcode", "<i4"), ("n_in", "<i4"), ("out", "<i4"), ("n_expr_args", "<i4"),
+                   ("expr_offset", "<i8"), ("expr_len", "<i8"), ("in", _OPERAND, (MAX_ARGS,))])
+
+
+class _Operand:
+    pass
+
+
+class _Instr:
+    pass
+
+
+# ======================================================================================
+# ForwardDiff-style Dual evaluation of the scalar bytecode (vectorised over elements)
+# ======================================================================================
+def _powi(x, n):
+    if n == 0:
+        return np.ones_like(x)
+    if n < 0:
+        return 1.0 / _powi(x, -n)
+    r = x
+    for _ in range(n - 1):
+        r = r * x
+    return r
+
+
+def dual_eval(ops, fconst, args, dtype, order=1):
+    """One ``Dual{N}`` evaluation per element: value + N partials (``broadcast.jl:147-153``,
+    ``elementwise.jl:234,301``); with ``order=2`` also the N×N second partials (hyper-dual),
+    used only for the Hessian check.
+
+    Returns ``(value, [partial_p], [[second_pq]])`` with every array broadcast to the common shape.
+    """
+    n = len(args)
+    zero = np.zeros((), dtype)
+    one = np.ones((), dtype)
+    V = [np.asarray(a, dtype) for a in args]
+    D = [[one if p == q else zero for p in range(n)] for q in range(n)]   # D[reg][p]
+    H = [[[zero] * n for _ in range(n)] for _ in range(n)] if order == 2 else None
+
+    def unary(a, f0, f1, f2=None):
+        """chain rule: y = f(u): y_p = f'(u) u_p ; y_pq = f''(u) u_p u_q + f'(u) u_pq"""
+        V.append(f0)
+        D.append([f1 * D[a][p] for p in range(n)])
+        if order == 2:
+            H.append([[f2 * D[a][p] * D[a][q] + f1 * H[a][p][q] for q in range(n)] for p in range(n)])
+
+    for code, a, b, imm in ops:
+        code, a, b, imm = int(code), int(a), int(b), int(imm)
+        if code == E_CONST:
+            V.append(np.asarray(fconst[imm], dtype)); D.append([zero] * n)
+            if order == 2: H.append([[zero] * n for _ in range(n)])
+        elif code == E_ARG:
+            V.append(V[imm]); D.append(list(D[imm]))
+            if order == 2: H.append([list(r) for r in H[imm]])
+        elif code in (E_ADD, E_SUB):
+            s = one if code == E_ADD else -one
+            V.append(V[a] + V[b] if code == E_ADD else V[a] - V[b])
+            D.append([D[a][p] + s * D[b][p] for p in range(n)])
+            if order == 2: H.append([[H[a][p][q] + s * H[b][p][q] for q in range(n)] for p in range(n)])
+        elif code == E_MUL:
+            V.append(V[a] * V[b])
+            D.append([D[a][p] * V[b] + V[a] * D[b][p] for p in range(n)])
+            if order == 2:
+                H.append([[H[a][p][q] * V[b] + D[a][p] * D[b][q] + D[a][q] * D[b][p] + V[a] * H[b][p][q]
+                           for q in range(n)] for p in range(n)])
+        elif code == E_DIV:
+            # (a/b)' = (1/b, -a/b^2)
+            q0 = V[a] / V[b]
+            ib = one / V[b]
+            V.append(q0)
+            da = [(D[a][p] - q0 * D[b][p]) * ib for p in range(n)]
+            D.append(da)
+            if order == 2:
+                # y = a/b  =>  y_pq = (a_pq - y_p b_q - y_q b_p - y b_pq)/b
+                H.append([[(H[a][p][q] - da[p] * D[b][q] - da[q] * D[b][p] - q0 * H[b][p][q]) * ib
+                           for q in range(n)] for p in range(n)])
+        elif code == E_NEG:
+            unary(a, -V[a], -one, zero)
+        elif code == E_POWI:
+            x = V[a]
+            f1 = imm * _powi(x, imm - 1) if imm != 0 else zero * x
+            f2 = imm * (imm - 1) * _powi(x, imm - 2) if imm not in (0, 1) else zero * x
+            unary(a, _powi(x, imm), f1, f2)
+        elif code == E_POW:
+            # (a^b)' = (b a^(b-1), a^b log a)
+            y = V[a] ** V[b]
+            fa = V[b] * V[a] ** (V[b] - one)
+            fb = y * np.log(V[a])
+            V.append(y); D.append([fa * D[a][p] + fb * D[b][p] for p in range(n)])
+            if order == 2:
+                raise NotImplementedError("second-order pow")
+        elif code == E_TANH:
+            t = np.tanh(V[a]); f1 = one - t * t
+            unary(a, t, f1, -2 * t * f1)
+        elif code == E_EXP:
+            e = np.exp(V[a]); unary(a, e, e, e)
+        elif code == E_LOG:
+            unary(a, np.log(V[a]), one / V[a], -one / (V[a] * V[a]))
+        elif code == E_SQRT:
+            s = np.sqrt(V[a]); unary(a, s, one / (2 * s), -one / (4 * s * V[a]))
+        elif code == E_SIN:
+            unary(a, np.sin(V[a]), np.cos(V[a]), -np.sin(V[a]))
+        elif code == E_COS:
+            unary(a, np.cos(V[a]), -np.sin(V[a]), -np.cos(V[a]))
+        elif code == E_ABS2:
+            unary(a, V[a] * V[a], 2 * V[a], 2 * one)
+        elif code == E_ABS:
+            unary(a, np.abs(V[a]), np.sign(V[a]), zero)
+        elif code in (E_MAX, E_MIN):
+            pick_a = (V[a] > V[b]) if code == E_MAX else (V[a] < V[b])
+            V.append(np.where(pick_a, V[a], V[b]))
+            D.append([np.where(pick_a, D[a][p], D[b][p]) for p in range(n)])
+            if order == 2:
+                H.append([[np.where(pick_a, H[a][p][q], H[b][p][q]) for q in range(n)] for p in range(n)])
+        elif code == E_INV:
+            r = one / V[a]; unary(a, r, -r * r, 2 * r * r * r)
+        elif code == E_SIGMOID:
+            s = one / (one + np.exp(-V[a])); f1 = s * (one - s)
+            unary(a, s, f1, f1 * (one - 2 * s))
+        else:
+            raise ValueError(f"unknown scalar opcode {code}")
+    shape = np.broadcast_shapes(*[np.shape(v) for v in V[:n]], np.shape(V[-1]))
+    val = np.broadcast_to(np.asarray(V[-1], dtype), shape)
+    part = [np.broadcast_to(np.asarray(D[-1][p], dtype), shape) for p in range(n)]
+    sec = None
+    if order == 2:
+        sec = [[np.broadcast_to(np.asarray(H[-1][p][q], dtype), shape) for q in range(n)] for p in range(n)]
+    return val, part, sec
+
+
+# ======================================================================================
+# Tape
+# ======================================================================================
+class OracleTape:
+    """Buffers + instruction list, replayed like ``forward_pass!`` / ``reverse_pass!``
+    (``src/tape.jl:75-90``; compiled variant ``src/api/tape.jl:122-134``)."""
+
+    def __init__(self, program_bytes: bytes, keep_reference_copies: bool = True):
+        mv = memoryview(program_bytes)
+        h = np.frombuffer(mv, _HEADER, 1)[0]
+        assert int(h["magic"]) == MAGIC and int(h["version"]) == VERSION, "bad tape program"
+        assert int(h["total_bytes"]) == len(program_bytes), "truncated tape program"
+        self.dtype = np.dtype(np.float64 if int(h["dtype"]) == 0 else np.float32)
+        self.keep_reference_copies = keep_reference_copies
+        bufs = np.frombuffer(mv, _BUFFER, int(h["n_buffers"]), int(h["off_buffers"]))
+        self.inputs = [int(i) for i in np.frombuffer(mv, np.int32, int(h["n_inputs"]), int(h["off_inputs"]))]
+        ins = np.frombuffer(mv, _INSTR, int(h["n_instr"]), int(h["off_instr"]))
+        idx = np.frombuffer(mv, np.int64, int(h["n_idx"]), int(h["off_idx"]))
+        expr = np.frombuffer(mv, np.int32, int(h["n_expr"]), int(h["off_expr"]))
+        self.fconst = np.frombuffer(mv, np.float64, int(h["n_fconst"]), int(h["off_fconst"]))
+        coff = int(h["off_const"])
+        self.output = int(h["output_buffer"])
+        self.kind, self.dims, self.value, self.deriv = [], [], [], []
+        for b in bufs:
+            nd = int(b["ndims"]); dims = tuple(int(d) for d in b["dims"][:nd])
+            n = int(np.prod(dims)) if dims else 1
+            kind = int(b["kind"])
+            self.kind.append(kind); self.dims.append(dims)
+            al = int(b["alias_of"])
+            if al >= 0:   # reshape aliases value AND deriv (tracked.jl:402-408)
+                self.value.append(self.value[al].reshape(dims, order="F"))
+                self.deriv.append(self.deriv[al].reshape(dims, order="F"))
+            elif kind == BUF_CONST:
+                data = np.frombuffer(mv, self.dtype, n, coff + int(b["const_offset"]))
+                self.value.append(np.array(data.reshape(dims, order="F"), order="F"))
+                self.deriv.append(None)
+            else:
+                self.value.append(np.zeros(dims, self.dtype, order="F"))
+                self.deriv.append(np.zeros(dims, self.dtype, order="F"))
+        self.instrs = []
+        for rec in ins:
+            it = _Instr()
+            it.opcode, it.out = int(rec["opcode"]), int(rec["out"])
+            it.n_expr_args = int(rec["n_expr_args"])
+            it.inputs = []
+            for j in range(int(rec["n_in"])):
+                o = rec["in"][j]
+                op = _Operand()
+                op.buffer, op.cls, op.tracked = int(o["buffer"]), int(o["cls"]), bool(o["tracked"])
+                nd = int(o["ndims"])
+                op.dims = tuple(int(d) for d in o["dims"][:nd])
+                op.bound = tuple(int(x) for x in o["bound"])
+                k = int(o["idx_kind"])
+                if k == IDX_EXPLICIT:
+                    op.idx = idx[int(o["idx_offset"]): int(o["idx_offset"]) + int(o["idx_len"])]
+                elif k == IDX_TRANSPOSE:
+                    # adjoint of a (rows x cols) parent: element (i,j) -> j + i*rows   (tracked.jl:348-351)
+                    rows, cols = self.dims[op.buffer]
+                    ii = np.arange(cols, dtype=np.int64)[:, None]; jj = np.arange(rows, dtype=np.int64)[None, :]
+                    op.idx = (jj + ii * rows).reshape(-1, order="F")
+                else:
+                    op.idx = None
+                it.inputs.append(op)
+            it.expr = None
+            if int(rec["expr_len"]) > 0:
+                eo, el = int(rec["expr_offset"]), int(rec["expr_len"])
+                it.expr = expr[eo: eo + 4 * el].reshape(-1, 4)
+            it.cache = None
+            self.instrs.append(it)
+
+    # ------------------------------------------------------------------ operand accessors
+    def _val(self, op):
+        """``value(x)`` after ``pull_value!`` (``tracked.jl:178-181``).  For IDX operands the reference
+        re-gathers element by element and then densifies with ``map(value, a)`` (``tracked.jl:103``)."""
+        if op.cls == CLS_IDX:
+            flat = self.value[op.buffer].reshape(-1, order="F")
+            g = flat[op.idx]                       # pull_value!
+            if self.keep_reference_copies:
+                g = g.copy()                       # value(::Array{TrackedReal}) dense copy
+            return g.reshape(op.dims, order="F")
+        v = self.value[op.buffer]
+        return v if op.cls != CLS_TR else np.asarray(v).reshape(())
+
+    def _inc(self, op, x, sign=1.0):
+        """``increment_deriv!`` / ``decrement_deriv!`` (``propagation.jl:33-73``)."""
+        if not op.tracked:
+            return
+        d = self.deriv[op.buffer]
+        if op.cls == CLS_IDX:
+            # per element: pull_deriv!, add, push_deriv! (propagation.jl:45-50) — sequential, duplicates add
+            flat = d.reshape(-1, order="F")
+            np.add.at(flat, op.idx, sign * np.asarray(x, self.dtype).reshape(-1, order="F"))
+            self.deriv[op.buffer][...] = flat.reshape(d.shape, order="F")
+        elif op.cls == CLS_TR:
+            d[...] = d + sign * x
+        else:
+            if sign > 0:
+                d += np.asarray(x, self.dtype).reshape(d.shape, order="F")
+            else:
+                d -= np.asarray(x, self.dtype).reshape(d.shape, order="F")
+
+    def _unseed(self, b):
+        """``unseed!`` (``tracked.jl:207-213``)."""
+        self.deriv[b][...] = 0
+
+    # ----------------------------------------------------------------------- public API
+    def set_input(self, slot, x):
+        """``value!(input_hook(t)[slot], x)`` (``tracked.jl:156-163``)."""
+        b = self.inputs[slot]
+        self.value[b][...] = np.asarray(x, self.dtype).reshape(self.dims[b], order="F")
+
+    def forward(self):
+        """``forward_pass!`` in recorded order (``src/tape.jl:75-80``)."""
+        for it in self.instrs:
+            self._forward_exec(it)
+
+    def reverse(self):
+        """``reverse_pass!`` in reverse order (``src/tape.jl:85-90``)."""
+        for it in reversed(self.instrs):
+            self._reverse_exec(it)
+
+    def gradient(self, inputs):
+        """``gradient!(result, tape, input)`` (``src/api/gradients.jl:78-82``):
+        seeded_forward_pass! (``api/tape.jl:40-44``) + seeded_reverse_pass! (``api/utils.jl:27-34``)."""
+        for i, x in enumerate(inputs):
+            self.set_input(i, x)
+        self.forward()
+        for b in self.inputs:
+            self._unseed(b)                       # unseed!(input)
+        self.deriv[self.output][...] = 1          # seed!(output)
+        self.reverse()
+        val = np.asarray(self.value[self.output]).reshape(()).copy()
+        return val, [self.deriv[b].copy(order="F") for b in self.inputs]   # extract_result!
+
+    def jacobian(self, inputs, slot=0, rows=None):
+        """``jacobian!`` (``src/api/jacobians.jl:120-124``): one forward sweep then one one-hot seeded
+        reverse sweep per output element (``src/api/utils.jl:44-58``).  Result is column-major
+        ``length(output) x length(input)``."""
+        for i, x in enumerate(inputs):
+            self.set_input(i, x)
+        self.forward()
+        out_d = self.deriv[self.output]
+        m = out_d.size
+        xin = self.inputs[slot]
+        n = self.deriv[xin].size
+        rows = range(m) if rows is None else rows
+        J = np.zeros((len(rows), n), self.dtype, order="F")
+        of = out_d.reshape(-1, order="F")
+        for r, i in enumerate(rows):
+            for b in self.inputs:
+                self._unseed(b)
+            of[i] = 1                              # seed!(output, i)
+            self.deriv[self.output][...] = of.reshape(out_d.shape, order="F")
+            self.reverse()
+            J[r, :] = self.deriv[xin].reshape(-1, order="F")
+            of = self.deriv[self.output].reshape(-1, order="F")
+            of[i] = 0                              # unseed!(output, i)
+            self.deriv[self.output][...] = of.reshape(out_d.shape, order="F")
+        return self.value[self.output].copy(order="F"), J
+
+    # ------------------------------------------------------------------ instruction execs
+    def _forward_exec(self, it):
+        op = it.opcode
+        out = self.value[it.out]
+        a = it.inputs
+        if op == OP_MUL:                      # arithmetic.jl:245-255
+            va, vb = self._val(a[0]), self._val(a[1])
+            res = va @ vb                     # mul! -> BLAS gemm / gemv
+            out[...] = res.reshape(out.shape, order="F")
+        elif op == OP_ADD:                    # arithmetic.jl:55-61, plus! :7-12
+            out[...] = self._val(a[0]) + self._val(a[1])
+        elif op == OP_SUB:                    # arithmetic.jl:142-154, minus! :69-79
+            out[...] = self._val(a[0]) - self._val(a[1])
+        elif op == OP_NEG:
+            out[...] = -self._val(a[0])
+        elif op == OP_SUM:                    # reductions.jl:23-27
+            self.value[it.out][...] = np.sum(self._val(a[0]))
+        elif op == OP_MEAN:                   # reductions.jl:81-85
+            self.value[it.out][...] = np.mean(self._val(a[0]))
+        elif op in ELEMENTWISE:               # broadcast.jl:196-204 ; elementwise.jl:323-343
+            nd = len(self.dims[it.out])
+            vals = [self._val(o).reshape(tuple(o.dims) + (1,) * (nd - len(o.dims)), order="F") for o in a]
+            val, part, _ = dual_eval(it.expr, self.fconst, vals, self.dtype)
+            it.cache = [np.array(p, order="F") for p in part]          # results[I].partial[p]
+            out[...] = val
+        elif op == OP_GETINDEX:               # tracked.jl:331-340
+            flat = self.value[a[0].buffer].reshape(-1, order="F")
+            out[...] = flat[a[0].idx].reshape(out.shape, order="F")
+        else:
+            raise NotImplementedError(f"opcode {op}")
+
+    def _reverse_exec(self, it):
+        op = it.opcode
+        a = it.inputs
+        delta = self.deriv[it.out]
+        if op == OP_MUL:                      # arithmetic.jl:260-285 (generic method on materialised operands)
+            va, vb = self._val(a[0]), self._val(a[1])
+            d2 = np.asarray(delta).reshape((va.shape[0], -1) if va.ndim == 2 else delta.shape, order="F")
+            if a[0].tracked:
+                vb2 = vb.reshape(vb.shape[0], -1, order="F")
+                a_tmp = d2 @ vb2.T            # mul!(a_tmp, output_deriv, transpose(value(b)))
+                self._inc(a[0], a_tmp.reshape(a[0].dims, order="F"))
+            if a[1].tracked:
+                b_tmp = va.T @ d2             # mul!(b_tmp, transpose(value(a)), output_deriv)
+                self._inc(a[1], b_tmp.reshape(a[1].dims, order="F"))
+        elif op == OP_ADD:                    # arithmetic.jl:45-53
+            self._inc(a[0], delta); self._inc(a[1], delta)
+        elif op == OP_SUB:                    # arithmetic.jl:127-140
+            self._inc(a[0], delta); self._inc(a[1], delta, -1.0)
+        elif op == OP_NEG:
+            self._inc(a[0], delta, -1.0)
+        elif op == OP_SUM:                    # reductions.jl:15-21 ; propagation.jl:34,38-43
+            if a[0].tracked:
+                self._inc(a[0], np.full(a[0].dims, np.asarray(delta).reshape(()), self.dtype))
+        elif op == OP_MEAN:                   # reductions.jl:73-79
+            if a[0].tracked:
+                n = int(np.prod(a[0].dims))
+                self._inc(a[0], np.full(a[0].dims, (self.dtype.type(1) / self.dtype.type(n)) *
+                                        np.asarray(delta).reshape(()), self.dtype))
+        elif op in ELEMENTWISE:               # broadcast.jl:163-194 ; elementwise.jl:349-408,466-537
+            nd = len(self.dims[it.out])
+            for p, o in enumerate(a):
+                if not o.tracked:
+                    continue
+                contrib = delta * it.cache[p]                         # x[i] * getpartial(results[i], p)
+                odims = tuple(o.dims) + (1,) * (nd - len(o.dims))
+                red = contrib
+                for ax in range(nd):                                  # min(bound, I): size-1 dims collapse
+                    if odims[ax] == 1 and red.shape[ax] != 1:
+                        # sequential accumulation in column-major order (propagation.jl:90-95)
+                        red = np.add.accumulate(red, axis=ax).take([-1], axis=ax)
+                self._inc(o, red.reshape(o.dims, order="F"))
+        elif op == OP_GETINDEX:               # tracked.jl:318-329
+            d = self.deriv[a[0].buffer]
+            flat = d.reshape(-1, order="F")
+            np.add.at(flat, a[0].idx, np.asarray(delta).reshape(-1, order="F"))
+            d[...] = flat.reshape(d.shape, order="F")
+        else:
+            raise NotImplementedError(f"opcode {op}")
+        self._unseed(it.out)                  # every reverse exec ends with unseed!(output)
+
+
+# ======================================================================================
+# Hessian check (forward-over-reverse restated densely; small n only)
+# ======================================================================================
+def hessian_dense(program_bytes, x, eps=None):
+    """Hessian of a scalar tape w.r.t. input slot 0 as the Jacobian of the replayed gradient, by
+    *complex-free* central differences of ``OracleTape.gradient`` — an independent (non-AD) check used
+    next to the closed forms; O(n) replays, small n only."""
+    t = OracleTape(program_bytes)
+    x = np.asarray(x, np.float64)
+    n = x.size
+    H = np.zeros((n, n), order="F")
+    for j in range(n):
+        h = eps or 1e-6 * max(1.0, abs(x.reshape(-1, order="F")[j]))
+        xp = x.copy(order="F"); xm = x.copy(order="F")
+        xp.reshape(-1, order="F")[j] += h; xm.reshape(-1, order="F")[j] -= h
+        _, gp = t.gradient([xp]); _, gm = t.gradient([xm])
+        H[:, j] = (gp[0].reshape(-1, order="F") - gm[0].reshape(-1, order="F")) / (2 * h)
+    return H

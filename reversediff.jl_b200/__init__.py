@@ -1,0 +1,18 @@
+"""reversediff.jl_b200 — B200-native replay engine for ReverseDiff compiled tapes (host side).
+
+The directory name carries a dot (fixed by the repo layout contract), so it is imported through
+``__graft_entry__.load_package()`` (or ``tests/conftest.py``) under the module name
+``reversediff_jl_b200``.
+
+Scope: ONLY the compiled-tape replay path — ``compile`` + ``gradient!/jacobian!/hessian!(result,
+tape, input)`` — see DESIGN.md.  Recording happens on the host (``tracked.py``), replay happens in
+``csrc/librdb200.so`` (hand-written sm_100a CUDA) through the C ABI of ``include/rdb200.h``.
+"""
+from .tracked import (TrackedArray, TrackedReal, InstructionTape, ForwardOptimize, SkipOptimize,  # noqa: F401
+                      forward, skip, value, istracked, sum, mean, bcast, map_, broadcast)
+from .expr import (tanh, exp, log, sqrt, sin, cos, abs2, abs_, inv, logistic, max_, min_)          # noqa: F401
+from .api import (GradientTape, JacobianTape, HessianTape, CompiledTape, DiffResult, compile,      # noqa: F401
+                  gradient_, jacobian_, hessian_, gradient, jacobian, hessian, seeded_forward_pass)
+from . import program, expr, engine, workloads                                                    # noqa: F401
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,262 @@
+"""Tape objects and the replay API — host-side mirror of the reference's L4/L5 layers for the
+compiled-tape path only.
+
+==========================================  ===========================================================
+reference (Julia)                           here (Python spelling; Julia shim in julia/ReverseDiffB200.jl)
+==========================================  ===========================================================
+``GradientTape(f, input)``                  ``GradientTape(f, input)``            api/tape.jl:197-209
+``JacobianTape(f, input)``                  ``JacobianTape(f, input)``            api/tape.jl:226-238
+``HessianTape(f, input)``                   ``HessianTape(f, input)``             api/tape.jl:285-293
+``compile(t)``                              ``compile(t)``                        api/tape.jl:146-149
+``gradient!(result, ct, input)``            ``gradient_(result, ct, input)``      api/gradients.jl:78-82
+``jacobian!(result, ct, input)``            ``jacobian_(result, ct, input)``      api/jacobians.jl:120-124
+``hessian!(result, ct, input)``             ``hessian_(result, ct, input)``       api/hessians.jl:86-97
+``DiffResults.GradientResult`` etc.         ``DiffResult``                        api/utils.jl:91-111
+==========================================  ===========================================================
+
+Uncompiled tapes cannot be replayed here: there is deliberately no CPU path — ``compile`` lowers
+to the B200 engine or raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import program as P
+from .tracked import InstructionTape, TrackedArray, TrackedReal, value
+from . import engine as _engine
+
+
+class DiffResult:
+    """Minimal ``DiffResults.MutableDiffResult``: ``value`` plus derivative arrays."""
+
+    def __init__(self, value_, *derivs):
+        self.value = value_
+        self.derivs = list(derivs)
+
+    @property
+    def gradient(self):
+        return self.derivs[0]
+
+    @property
+    def jacobian(self):
+        return self.derivs[0]
+
+    @property
+    def hessian(self):
+        return self.derivs[1]
+
+
+class AbstractTape:
+    kind = "abstract"
+
+    def __init__(self, func, input_, dtype=None):
+        self.func = func
+        self.is_tuple = isinstance(input_, (tuple, list))
+        xs = list(input_) if self.is_tuple else [input_]
+        if dtype is None:
+            dtype = np.result_type(*[np.asarray(x).dtype for x in xs])
+            if dtype not in (np.float32, np.float64):
+                dtype = np.float64
+        self.tape = InstructionTape(dtype)
+        prog = self.tape.program
+        # GradientConfig(input): track(similar(x), D, tp) then track!(cfg.input, input)
+        # (api/Config.jl:37,45-47 ; tracked.jl:476-478)
+        self.input = []
+        for x in xs:
+            v = np.array(x, dtype=self.tape.dtype, order="F", copy=True)
+            if v.ndim == 0:
+                raise TypeError("tape inputs must be arrays")
+            b = prog.add_buffer(P.BUF_TA, v.shape)
+            prog.inputs.append(b)
+            self.input.append(TrackedArray(v, self.tape, b))
+        self.output = func(*self.input) if self.is_tuple else func(self.input[0])
+        self._check_output()
+        prog.output_buffer = self.output.buffer
+
+    def _check_output(self):
+        raise NotImplementedError
+
+    def __len__(self):
+        return len(self.tape)
+
+    # hooks (api/tape.jl:28-32)
+    def func_hook(self): return self.func
+    def input_hook(self): return tuple(self.input) if self.is_tuple else self.input[0]
+    def output_hook(self): return self.output
+
+    def program_bytes(self) -> bytes:
+        return self.tape.program.to_bytes()
+
+
+class GradientTape(AbstractTape):
+    kind = "gradient"
+
+    def _check_output(self):
+        if not isinstance(self.output, TrackedReal):
+            raise TypeError("GradientTape: f must return a tracked scalar (e.g. end in sum/mean)")
+
+
+class JacobianTape(AbstractTape):
+    kind = "jacobian"
+
+    def _check_output(self):
+        if not isinstance(self.output, TrackedArray):
+            raise TypeError("JacobianTape: f must return a tracked array")
+
+
+class HessianTape(AbstractTape):
+    """Records the *inner array tape* of ``f``.  The reference instead records a scalar
+    reverse-over-reverse program (``api/tape.jl:285-293``, ``api/Config.jl:152-156``); the engine
+    obtains the same Hessian by replaying this tape forward-over-reverse (BASELINE.json north star)."""
+    kind = "hessian"
+
+    def __init__(self, func, input_, dtype=None):
+        if isinstance(input_, (tuple, list)):
+            # api/hessians.jl:103-108
+            raise TypeError("Taking the Hessian of a function with multiple arguments is not yet supported")
+        super().__init__(func, input_, dtype)
+
+    def _check_output(self):
+        if not isinstance(self.output, TrackedReal):
+            raise TypeError("HessianTape: f must return a tracked scalar")
+
+
+class CompiledTape:
+    """``CompiledTape`` (``api/tape.jl:55-59``): here a handle on an engine-resident tape."""
+
+    def __init__(self, tape: AbstractTape, ctx=None, **options):
+        self.tape = tape
+        self.kind = tape.kind
+        self.ctx = ctx if ctx is not None else _engine.default_context()
+        self.program = tape.program_bytes()
+        self.handle = _engine.EngineTape(self.ctx, self.program, **options)
+        self.dtype = tape.tape.dtype
+
+    def __len__(self):
+        return len(self.tape)
+
+    def func_hook(self): return self.tape.func_hook()
+    def input_hook(self): return self.tape.input_hook()
+    def output_hook(self): return self.tape.output_hook()
+
+    # forward_pass!/reverse_pass! (api/tape.jl:122-134)
+    def forward_pass(self): self.handle.forward()
+    def reverse_pass(self): self.handle.reverse_scalar_seed()
+
+
+def compile(t: AbstractTape, ctx=None, **options) -> CompiledTape:  # noqa: A001 - mirrors ReverseDiff.compile
+    if isinstance(t, CompiledTape):
+        return t
+    return CompiledTape(t, ctx, **options)
+
+
+# ---------------------------------------------------------------------------------------------
+def _as_list(x, is_tuple):
+    return list(x) if is_tuple else [x]
+
+
+def _is_device(x):
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+def _need_compiled(ct, kind):
+    if not isinstance(ct, CompiledTape):
+        raise TypeError(f"{kind}! replays only compiled tapes here: call compile(tape) first "
+                        "(uncompiled replay would be a CPU path; this engine has none)")
+    if ct.kind != kind:
+        raise TypeError(f"{kind}! needs a compiled {kind.capitalize()}Tape, got a {ct.kind} tape")
+
+
+def seeded_forward_pass(ct: CompiledTape, input_):
+    """``seeded_forward_pass!`` (``api/tape.jl:40-44``)."""
+    xs = _as_list(input_, ct.tape.is_tuple)
+    if len(xs) != len(ct.tape.input):
+        raise ValueError("wrong number of inputs for this tape")
+    for i, x in enumerate(xs):
+        ct.handle.set_input(i, x, tuple(ct.tape.input[i].shape))
+    return None
+
+
+def _result_arrays(result, n):
+    """Unpack result containers the way ``extract_result!`` dispatches (``api/utils.jl:77-111``)."""
+    if isinstance(result, DiffResult):
+        return [result.derivs[0]], [result]
+    if isinstance(result, (tuple, list)):
+        arrs, drs = [], []
+        for r in result:
+            if isinstance(r, DiffResult):
+                arrs.append(r.derivs[0]); drs.append(r)
+            else:
+                arrs.append(r)
+        return arrs, drs
+    return [result], []
+
+
+def gradient_(result, ct: CompiledTape, input_):
+    """``gradient!(result, tape::CompiledGradient, input)`` (``api/gradients.jl:78-82``)."""
+    _need_compiled(ct, "gradient")
+    seeded_forward_pass(ct, input_)
+    arrs, drs = _result_arrays(result, len(ct.tape.input))
+    if len(arrs) != len(ct.tape.input):
+        raise ValueError("result does not match the tape's inputs")
+    val = ct.handle.gradient(arrs, [tuple(t.shape) for t in ct.tape.input], want_value=bool(drs))
+    for d in drs:
+        d.value = val
+    return result
+
+
+def gradient(ct: CompiledTape, input_):
+    """``gradient!(tape, input)`` (``api/gradients.jl:61-65``): allocates via construct_result."""
+    res = [np.zeros(t.shape, ct.dtype, order="F") for t in ct.tape.input]
+    out = tuple(res) if ct.tape.is_tuple else res[0]
+    return gradient_(out, ct, input_)
+
+
+def jacobian_(result, ct: CompiledTape, input_, rows=None):
+    """``jacobian!(result, tape::CompiledJacobian, input)`` (``api/jacobians.jl:120-124``).  ``rows=(b,e)``
+    restricts to a block of output-seed rows (the multi-GPU shard); ``result`` then holds ``e-b`` rows."""
+    _need_compiled(ct, "jacobian")
+    seeded_forward_pass(ct, input_)
+    m = ct.tape.output.size
+    b, e = (0, m) if rows is None else rows
+    arrs, drs = _result_arrays(result, len(ct.tape.input))
+    if len(arrs) != len(ct.tape.input):
+        raise ValueError("result does not match the tape's inputs")
+    val = None
+    for slot, arr in enumerate(arrs):    # tuple inputs: the sweep loop is repeated per input (api/utils.jl:66-71)
+        n = ct.tape.input[slot].size
+        val = ct.handle.jacobian(slot, b, e, arr, (e - b, n), want_value=bool(drs), out_shape=ct.tape.output.shape)
+    for d in drs:
+        d.value = val
+    return result
+
+
+def jacobian(ct: CompiledTape, input_):
+    m = ct.tape.output.size
+    res = [np.zeros((m, t.size), ct.dtype, order="F") for t in ct.tape.input]
+    out = tuple(res) if ct.tape.is_tuple else res[0]
+    return jacobian_(out, ct, input_)
+
+
+def hessian_(result, ct: CompiledTape, input_, cols=None):
+    """``hessian!(result, tape::CompiledHessian, input)`` (``api/hessians.jl:86-97``).  ``cols=(b,e)``
+    restricts to a block of columns (the multi-GPU shard)."""
+    _need_compiled(ct, "hessian")
+    seeded_forward_pass(ct, input_)
+    n = ct.tape.input[0].size
+    b, e = (0, n) if cols is None else cols
+    if isinstance(result, DiffResult):
+        g, val = ct.handle.hessian(b, e, result.derivs[1], (n, e - b), want_grad=True)
+        np.copyto(result.derivs[0].reshape(-1, order="F"), g) if not _is_device(result.derivs[0]) else None
+        result.value = val
+    else:
+        ct.handle.hessian(b, e, result, (n, e - b), want_grad=False)
+    return result
+
+
+def hessian(ct: CompiledTape, input_):
+    n = ct.tape.input[0].size
+    return hessian_(np.zeros((n, n), ct.dtype, order="F"), ct, input_)
+
+
+_ = value

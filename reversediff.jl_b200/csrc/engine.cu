@@ -1,0 +1,1125 @@
+// Host side of librdb200.so: tape-program loader/validator, buffer arena, forward/reverse executors, batched
+// seed sweeps for jacobian!/hessian!, and the C ABI of include/rdb200.h.
+//
+// Reference semantics followed here (all paths relative to the ReverseDiff.jl tree):
+//   pass loops              src/tape.jl:75-90, src/api/tape.jl:122-134
+//   seeding / extraction    src/api/utils.jl:27-58,77-100 ; src/tracked.jl:202-213
+//   `*`                     src/derivatives/linalg/arithmetic.jl:245-285
+//   array +/-               src/derivatives/linalg/arithmetic.jl:45-61,127-154
+//   sum / mean              src/derivatives/linalg/reductions.jl:15-27,73-85
+//   elementwise closures    src/derivatives/broadcast.jl:163-204 ; src/derivatives/elementwise.jl:323-408,466-537
+//   accumulators            src/derivatives/propagation.jl:33-108
+//   getindex                src/tracked.jl:318-340
+// Every reverse exec ends with unseed!(output) (e.g. arithmetic.jl:51,266; reductions.jl:19; broadcast.jl:174).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "program.h"
+#include "rdb200.h"
+
+using namespace rdb;
+
+// ------------------------------------------------------------------------------------------ error state
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(RDB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define OK(call)                 \
+    do {                         \
+        int rc__ = (call);       \
+        if (rc__ != RDB_OK) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ structures
+struct rdb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+};
+
+struct Buf {
+    int kind = 0, nd = 0;
+    int64_t dims[kMaxDims] = {1, 1, 1, 1};
+    int64_t size = 1;
+    int alias_of = -1;
+    void *val = nullptr;   // value(x)
+    void *der = nullptr;   // deriv(x), size x R (batched seeds)
+    void *tv = nullptr;    // value tangents  (size x K), hessian! only
+    void *td = nullptr;    // deriv tangents  (size x K), hessian! only
+    int n_consumers = 0;
+};
+
+enum OperandMode { OPM_PLAIN = 0, OPM_FOLDED_T = 1, OPM_GATHER = 2 };
+
+struct OperandPlan {
+    OperandRec rec{};
+    int mode = OPM_PLAIN;
+    int64_t size = 1;           // elements of the operand as the instruction sees it
+    int64_t rows = 1, cols = 1; // matrix view (vectors are cols == 1; row vectors rows == 1)
+    int64_t *d_map = nullptr;   // device index map (OPM_GATHER, and getindex)
+    void *dense_val = nullptr;  // densified value(a) for OPM_GATHER operands
+    void *dense_der = nullptr;  // adjoint temporary for OPM_GATHER operands
+};
+
+struct InstrPlan {
+    InstrRec rec{};
+    OperandPlan in[kMaxArgs];
+    int32_t *d_ops = nullptr;
+    void *partial[kMaxArgs] = {nullptr, nullptr, nullptr, nullptr};
+    void *second[kMaxArgs * (kMaxArgs + 1) / 2] = {nullptr};
+    bool fused_into_prev = false;   // forward: this `sum`/`mean` was produced by the previous kernel
+};
+
+struct StepStat {
+    std::string name;
+    double ms = 0, bytes = 0, flops = 0;
+    int count = 0;
+};
+
+struct rdb_tape {
+    rdb_ctx *ctx = nullptr;
+    int dtype = RDB_F64;
+    size_t es = 8;
+    std::vector<Buf> bufs;
+    std::vector<InstrPlan> instrs;
+    std::vector<int> inputs;
+    int output = -1;
+    rdb_options opts{};
+    std::vector<void *> allocs;
+    double *d_fconst = nullptr;
+    void *scratch = nullptr;       // reduction scratch
+    int64_t scratch_bytes = 0;
+    int64_t R_alloc = 0;           // deriv buffers hold size x R_alloc
+    int64_t K_alloc = 0;           // tangent buffers hold size x K_alloc
+    void *stage = nullptr;         // device staging for host results
+    int64_t stage_bytes = 0;
+    int64_t launches = 0;
+    bool second_order = false;     // partial/second arrays allocated for hessian!
+    std::vector<StepStat> stats;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool forward_valid = false;
+};
+
+static cudaStream_t S(rdb_tape *t) { return t->ctx->stream; }
+
+static int dev_alloc(rdb_tape *t, void **p, int64_t bytes) {
+    if (bytes <= 0) bytes = 8;
+    cudaError_t e = cudaMalloc(p, (size_t)bytes);
+    if (e != cudaSuccess) return fail(RDB_ENOMEM, "cudaMalloc(%lld bytes) failed: %s", (long long)bytes, cudaGetErrorString(e));
+    t->allocs.push_back(*p);
+    return RDB_OK;
+}
+static void dev_free(rdb_tape *t, void *p) {
+    if (!p) return;
+    auto it = std::find(t->allocs.begin(), t->allocs.end(), p);
+    if (it != t->allocs.end()) t->allocs.erase(it);
+    cudaFree(p);
+}
+
+// per-step profiling ----------------------------------------------------------------------------------
+struct StepTimer {
+    rdb_tape *t;
+    const char *name;
+    double bytes, flops;
+    bool on;
+    StepTimer(rdb_tape *t_, const char *n, double b, double f) : t(t_), name(n), bytes(b), flops(f), on(t_->opts.profile != 0) {
+        if (on) cudaEventRecord(t->ev0, S(t));
+    }
+    ~StepTimer() {
+        if (!on) return;
+        cudaEventRecord(t->ev1, S(t));
+        cudaEventSynchronize(t->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t->ev0, t->ev1);
+        for (auto &s : t->stats)
+            if (s.name == name) { s.ms += ms; s.bytes += bytes; s.flops += flops; s.count++; return; }
+        StepStat s; s.name = name; s.ms = ms; s.bytes = bytes; s.flops = flops; s.count = 1;
+        t->stats.push_back(s);
+    }
+};
+
+// ------------------------------------------------------------------------------------------ typed ops
+template <typename T>
+static cudaError_t gemm_t(cudaStream_t s, bool ta, bool tb, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t lda,
+                          const T *B, int64_t ldb, T beta, T *C, int64_t ldc);
+template <>
+cudaError_t gemm_t<double>(cudaStream_t s, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
+                           int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc) {
+    return gemm_f64(s, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+template <>
+cudaError_t gemm_t<float>(cudaStream_t s, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                          int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc) {
+    return gemm_f32(s, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
+#define KL(t, call)                                                                                        \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        (t)->launches++;                                                                                   \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail(RDB_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+static bool is_elementwise(int op) {
+    return op == OP_NBCAST || op == OP_MAP || op == OP_BCAST || op == OP_BCAST_ADD || op == OP_BCAST_SUB || op == OP_BCAST_MUL;
+}
+
+// A matrix operand as the GEMM sees it: stored pointer, leading dimension and whether the stored matrix is the
+// transpose of the operand (folded IDX transposes cost nothing: SURVEY.md Appendix A.1 "engine-minimal").
+template <typename T>
+struct MatRef {
+    const T *ptr;
+    int64_t ld;
+    bool stored_t;
+};
+
+template <typename T>
+static int operand_value(rdb_tape *t, OperandPlan &o, MatRef<T> &m) {
+    Buf &b = t->bufs[o.rec.buffer];
+    if (o.mode == OPM_PLAIN) { m.ptr = (const T *)b.val; m.ld = o.rows; m.stored_t = false; return RDB_OK; }
+    if (o.mode == OPM_FOLDED_T) { m.ptr = (const T *)b.val; m.ld = o.cols; m.stored_t = true; return RDB_OK; }
+    // pull_value! element by element + dense copy (tracked.jl:178-181,103) as ONE gather kernel
+    KL(t, launch_gather<T>(S(t), (T *)o.dense_val, (const T *)b.val, o.d_map, o.size));
+    m.ptr = (const T *)o.dense_val; m.ld = o.rows; m.stored_t = false;
+    return RDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+template <typename T>
+static int expr_forward(rdb_tape *t, InstrPlan &I, bool reduce, int order) {
+    Buf &out = t->bufs[I.rec.out];
+    ExprParams p{};
+    p.n_args = I.rec.n_in; p.n_ops = (int)I.rec.expr_len; p.order = order; p.reduce = reduce ? 1 : 0;
+    p.n = out.size;
+    for (int d = 0; d < kMaxDims; ++d) p.dims[d] = out.dims[d];
+    for (int a = 0; a < I.rec.n_in; ++a) {
+        OperandPlan &o = I.in[a];
+        MatRef<T> m;
+        OK(operand_value<T>(t, o, m));
+        if (m.stored_t) return fail(RDB_EUNSUPPORTED, "elementwise instruction on a transposed operand");
+        p.arg[a].ptr = m.ptr;
+        int64_t st = 1;
+        bool same = true;
+        for (int d = 0; d < kMaxDims; ++d) {
+            int64_t od = d < o.rec.ndims ? o.rec.dims[d] : 1;
+            p.arg[a].stride[d] = (od == 1 && out.dims[d] != 1) ? 0 : st;
+            if (od != out.dims[d]) same = false;
+            st *= od;
+        }
+        p.arg[a].same = same ? 1 : 0;
+        p.partial[a] = I.partial[a];
+    }
+    for (int h = 0; h < kMaxArgs * (kMaxArgs + 1) / 2; ++h) p.second[h] = I.second[h];
+    p.out = out.val; p.ops = I.d_ops; p.fconst = t->d_fconst; p.block_sums = t->scratch;
+    int np = 0;
+    for (int a = 0; a < I.rec.n_in; ++a) np += I.partial[a] ? 1 : 0;
+    StepTimer tm(t, order == 2 ? "expr_forward2" : (reduce ? "expr_forward+sum" : "expr_forward"),
+                 (double)out.size * t->es * (1 + np + 1), 0);
+    KL(t, launch_expr_forward<T>(S(t), p));
+    return RDB_OK;
+}
+
+template <typename T>
+static int forward_pass(rdb_tape *t, int order = 1) {
+    const size_t n = t->instrs.size();
+    for (size_t i = 0; i < n; ++i) {
+        InstrPlan &I = t->instrs[i];
+        Buf &out = t->bufs[I.rec.out];
+        // fusion of an elementwise producer with the `sum`/`mean` that consumes it (adjacent instructions only)
+        bool fuse_next = false;
+        if (t->opts.fuse_elementwise && i + 1 < n) {
+            InstrPlan &Nx = t->instrs[i + 1];
+            if ((Nx.rec.opcode == OP_SUM || Nx.rec.opcode == OP_MEAN) && Nx.in[0].rec.buffer == I.rec.out &&
+                Nx.in[0].mode == OPM_PLAIN &&
+                (I.rec.opcode == OP_ADD || I.rec.opcode == OP_SUB || is_elementwise(I.rec.opcode)))
+                fuse_next = true;
+        }
+        switch (I.rec.opcode) {
+            case OP_MUL: {
+                MatRef<T> A, B;
+                OK(operand_value<T>(t, I.in[0], A));
+                OK(operand_value<T>(t, I.in[1], B));
+                int64_t M = I.in[0].rows, K = I.in[0].cols, N = I.in[1].cols;
+                StepTimer tm(t, "gemm_forward", (double)(M * K + K * N + M * N) * t->es, 2.0 * M * N * K);
+                KL(t, gemm_t<T>(S(t), A.stored_t, B.stored_t, M, N, K, (T)1, A.ptr, A.ld, B.ptr, B.ld, (T)0, (T *)out.val, M));
+            } break;
+            case OP_ADD:
+            case OP_SUB: {
+                MatRef<T> A, B;
+                OK(operand_value<T>(t, I.in[0], A));
+                OK(operand_value<T>(t, I.in[1], B));
+                StepTimer tm(t, fuse_next ? "add+sum_forward" : "add_forward", 3.0 * out.size * t->es, 0);
+                KL(t, launch_add<T>(S(t), (T *)out.val, A.ptr, B.ptr, I.rec.opcode == OP_ADD ? (T)1 : (T)-1, out.size,
+                                    fuse_next ? (T *)t->scratch : nullptr));
+            } break;
+            case OP_NEG: {
+                MatRef<T> A;
+                OK(operand_value<T>(t, I.in[0], A));
+                KL(t, launch_axpy<T>(S(t), (T *)out.val, A.ptr, (T)-1, out.size, true));
+            } break;
+            case OP_SUM:
+            case OP_MEAN: {
+                T scale = I.rec.opcode == OP_MEAN ? (T)1 / (T)I.in[0].size : (T)1;
+                if (!I.fused_into_prev) {
+                    MatRef<T> A;
+                    OK(operand_value<T>(t, I.in[0], A));
+                    StepTimer tm(t, "sum_forward", (double)I.in[0].size * t->es, 0);
+                    KL(t, launch_block_sums<T>(S(t), A.ptr, I.in[0].size, (T *)t->scratch));
+                }
+                KL(t, launch_finish_sum<T>(S(t), (const T *)t->scratch, (T *)out.val, scale));
+            } break;
+            case OP_NBCAST: case OP_MAP: case OP_BCAST: case OP_BCAST_ADD: case OP_BCAST_SUB: case OP_BCAST_MUL:
+                OK(expr_forward<T>(t, I, fuse_next, order));
+                break;
+            case OP_GETINDEX: {
+                Buf &src = t->bufs[I.in[0].rec.buffer];
+                StepTimer tm(t, "getindex_forward", 2.0 * out.size * t->es + 8.0 * out.size, 0);
+                KL(t, launch_gather<T>(S(t), (T *)out.val, (const T *)src.val, I.in[0].d_map, out.size));
+            } break;
+            default:
+                return fail(RDB_EUNSUPPORTED, "opcode %d has no forward kernel", I.rec.opcode);
+        }
+        if (i + 1 < n) t->instrs[i + 1].fused_into_prev = fuse_next;
+    }
+    t->forward_valid = true;
+    return RDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ reverse
+template <typename T>
+static int unseed(rdb_tape *t, Buf &b, int64_t R) {
+    CU(cudaMemsetAsync(b.der, 0, (size_t)(b.size * R) * t->es, S(t)));
+    return RDB_OK;
+}
+
+// a.deriv += delta * value(b)'   and   b.deriv += value(a)' * delta     (arithmetic.jl:272-285), R seed columns
+template <typename T>
+static int mul_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
+    Buf &out = t->bufs[I.rec.out];
+    OperandPlan &oa = I.in[0], &ob = I.in[1];
+    const int64_t M = oa.rows, K = oa.cols, N = ob.cols;
+    MatRef<T> A, B;
+    // values are unchanged since the forward sweep: reuse the densified copies of OPM_GATHER operands
+    auto ref = [&](OperandPlan &o, MatRef<T> &m) {
+        Buf &b = t->bufs[o.rec.buffer];
+        if (o.mode == OPM_PLAIN) { m.ptr = (const T *)b.val; m.ld = o.rows; m.stored_t = false; }
+        else if (o.mode == OPM_FOLDED_T) { m.ptr = (const T *)b.val; m.ld = o.cols; m.stored_t = true; }
+        else { m.ptr = (const T *)o.dense_val; m.ld = o.rows; m.stored_t = false; }
+    };
+    ref(oa, A);
+    ref(ob, B);
+    const T *delta = (const T *)out.der;
+    if (oa.rec.tracked) {
+        Buf &ba = t->bufs[oa.rec.buffer];
+        StepTimer tm(t, "gemm_reverse_a", (double)(M * N + K * N + 2 * M * K) * t->es * R, 2.0 * M * N * K * R);
+        for (int64_t r = 0; r < R; ++r) {
+            const T *d = delta + r * M * N;
+            if (oa.mode == OPM_PLAIN) {
+                // a.deriv(MxK) += delta(MxN) * Bmat'(NxK)
+                KL(t, gemm_t<T>(S(t), false, !B.stored_t, M, K, N, (T)1, d, M, B.ptr, B.ld, (T)1, (T *)ba.der + r * ba.size, M));
+            } else if (oa.mode == OPM_FOLDED_T) {
+                // scatter-add through the transpose map == origin.deriv(KxM) += Bmat(KxN) * delta'(NxM)
+                KL(t, gemm_t<T>(S(t), B.stored_t, true, K, M, N, (T)1, B.ptr, B.ld, d, M, (T)1, (T *)ba.der + r * ba.size, K));
+            } else {
+                KL(t, gemm_t<T>(S(t), false, !B.stored_t, M, K, N, (T)1, d, M, B.ptr, B.ld, (T)0, (T *)oa.dense_der, M));
+                KL(t, launch_scatter_add<T>(S(t), (T *)ba.der + r * ba.size, ba.size, oa.d_map, (const T *)oa.dense_der, oa.size, 1));
+            }
+        }
+    }
+    if (ob.rec.tracked) {
+        Buf &bb = t->bufs[ob.rec.buffer];
+        StepTimer tm(t, "gemm_reverse_b", (double)(M * N + M * K + 2 * K * N) * t->es * R, 2.0 * M * N * K * R);
+        if (ob.mode == OPM_PLAIN) {
+            // b.deriv(K x N*R) += Amat'(KxM) * delta(M x N*R): the R seed columns ride along as extra GEMM columns
+            KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, N * R, M, (T)1, A.ptr, A.ld, delta, M, (T)1, (T *)bb.der, K));
+        } else {
+            for (int64_t r = 0; r < R; ++r) {
+                const T *d = delta + r * M * N;
+                if (ob.mode == OPM_FOLDED_T) {
+                    // origin.deriv(NxK) += delta'(NxM) * Amat(MxK)
+                    KL(t, gemm_t<T>(S(t), true, A.stored_t, N, K, M, (T)1, d, M, A.ptr, A.ld, (T)1, (T *)bb.der + r * bb.size, N));
+                } else {
+                    KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, N, M, (T)1, A.ptr, A.ld, d, M, (T)0, (T *)ob.dense_der, K));
+                    KL(t, launch_scatter_add<T>(S(t), (T *)bb.der + r * bb.size, bb.size, ob.d_map, (const T *)ob.dense_der, ob.size, 1));
+                }
+            }
+        }
+    }
+    return RDB_OK;
+}
+
+template <typename T>
+static int expr_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
+    Buf &out = t->bufs[I.rec.out];
+    const T *delta = (const T *)out.der;
+    for (int a = 0; a < I.rec.n_in; ++a) {
+        OperandPlan &o = I.in[a];
+        if (!o.rec.tracked) continue;
+        Buf &b = t->bufs[o.rec.buffer];
+        if (o.mode != OPM_PLAIN) return fail(RDB_EUNSUPPORTED, "elementwise instruction on an index-mapped operand");
+        bool same = true;
+        for (int d = 0; d < kMaxDims; ++d) {
+            int64_t od = d < o.rec.ndims ? o.rec.dims[d] : 1;
+            if (od != out.dims[d]) same = false;
+        }
+        if (same) {
+            StepTimer tm(t, "expr_reverse", 4.0 * out.size * R * t->es, 0);
+            KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[a], out.size, R, false));
+        } else {
+            int64_t d0 = o.rec.ndims >= 1 ? o.rec.dims[0] : 1;
+            bool colvec = (o.size == d0) && (d0 == out.dims[0]) && d0 > 1;
+            if (colvec) {
+                StepTimer tm(t, "expr_reverse_colreduce", 2.0 * out.size * R * t->es, 0);
+                KL(t, launch_mul_acc_colvec<T>(S(t), (T *)b.der, delta, (const T *)I.partial[a], d0, out.size / d0, R,
+                                               (T *)t->scratch, t->scratch_bytes / 8));
+                t->launches++;
+            } else {
+                int64_t dst_stride[kMaxDims], st = 1;
+                for (int d = 0; d < kMaxDims; ++d) {
+                    int64_t od = d < o.rec.ndims ? o.rec.dims[d] : 1;
+                    dst_stride[d] = (od == 1 && out.dims[d] != 1) ? 0 : st;
+                    st *= od;
+                }
+                StepTimer tm(t, "expr_reverse_generic", 3.0 * out.size * R * t->es, 0);
+                KL(t, launch_mul_acc_generic<T>(S(t), (T *)b.der, b.size, dst_stride, delta, (const T *)I.partial[a], out.dims,
+                                                out.size, R));
+            }
+        }
+    }
+    return RDB_OK;
+}
+
+template <typename T>
+static int reverse_pass(rdb_tape *t, int64_t R) {
+    for (size_t k = t->instrs.size(); k-- > 0;) {
+        InstrPlan &I = t->instrs[k];
+        Buf &out = t->bufs[I.rec.out];
+        const T *delta = (const T *)out.der;
+        switch (I.rec.opcode) {
+            case OP_MUL: OK(mul_reverse<T>(t, I, R)); break;
+            case OP_ADD:
+            case OP_SUB:
+                for (int a = 0; a < 2; ++a) {
+                    if (!I.in[a].rec.tracked) continue;
+                    Buf &b = t->bufs[I.in[a].rec.buffer];
+                    T sign = (a == 1 && I.rec.opcode == OP_SUB) ? (T)-1 : (T)1;
+                    StepTimer tm(t, "add_reverse", 3.0 * out.size * R * t->es, 0);
+                    KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, sign, out.size * R, false));
+                }
+                break;
+            case OP_NEG:
+                if (I.in[0].rec.tracked) {
+                    Buf &b = t->bufs[I.in[0].rec.buffer];
+                    KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, (T)-1, out.size * R, false));
+                }
+                break;
+            case OP_SUM:
+            case OP_MEAN:
+                if (I.in[0].rec.tracked) {
+                    Buf &b = t->bufs[I.in[0].rec.buffer];
+                    T scale = I.rec.opcode == OP_MEAN ? (T)1 / (T)I.in[0].size : (T)1;
+                    StepTimer tm(t, "sum_reverse", 2.0 * b.size * R * t->es, 0);
+                    KL(t, launch_acc_scalar<T>(S(t), (T *)b.der, b.size, R, delta, scale, false));
+                }
+                break;
+            case OP_NBCAST: case OP_MAP: case OP_BCAST: case OP_BCAST_ADD: case OP_BCAST_SUB: case OP_BCAST_MUL:
+                OK(expr_reverse<T>(t, I, R));
+                break;
+            case OP_GETINDEX:
+                if (I.in[0].rec.tracked) {
+                    Buf &b = t->bufs[I.in[0].rec.buffer];
+                    StepTimer tm(t, "getindex_reverse", 3.0 * out.size * R * t->es, 0);
+                    KL(t, launch_scatter_add<T>(S(t), (T *)b.der, b.size, I.in[0].d_map, delta, out.size, R));
+                }
+                break;
+            default:
+                return fail(RDB_EUNSUPPORTED, "opcode %d has no reverse kernel", I.rec.opcode);
+        }
+        {
+            StepTimer tm(t, "unseed", (double)out.size * R * t->es, 0);
+            OK(unseed<T>(t, out, R));
+        }
+    }
+    return RDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ allocation
+static int ensure_batch(rdb_tape *t, int64_t R) {
+    if (R <= t->R_alloc) return RDB_OK;
+    for (auto &b : t->bufs) {
+        if (b.kind == BUF_CONST || b.alias_of >= 0) continue;
+        dev_free(t, b.der);
+        b.der = nullptr;
+        OK(dev_alloc(t, &b.der, b.size * R * (int64_t)t->es));
+        CU(cudaMemsetAsync(b.der, 0, (size_t)(b.size * R) * t->es, S(t)));
+    }
+    for (auto &b : t->bufs)
+        if (b.alias_of >= 0) b.der = t->bufs[b.alias_of].der;
+    // column-reduction scratch grows with R
+    int64_t need = t->scratch_bytes;
+    for (auto &I : t->instrs)
+        if (is_elementwise(I.rec.opcode))
+            for (int a = 0; a < I.rec.n_in; ++a)
+                if (I.in[a].rec.tracked && I.in[a].size != t->bufs[I.rec.out].size)
+                    need = std::max<int64_t>(need, I.in[a].size * R * 64 * 8);
+    if (need > t->scratch_bytes) {
+        dev_free(t, t->scratch);
+        OK(dev_alloc(t, &t->scratch, need));
+        t->scratch_bytes = need;
+    }
+    t->R_alloc = R;
+    return RDB_OK;
+}
+
+static int ensure_stage(rdb_tape *t, int64_t bytes) {
+    if (bytes <= t->stage_bytes) return RDB_OK;
+    dev_free(t, t->stage);
+    t->stage = nullptr;
+    OK(dev_alloc(t, &t->stage, bytes));
+    t->stage_bytes = bytes;
+    return RDB_OK;
+}
+
+static int64_t auto_seed_block(rdb_tape *t, int64_t rows, bool tangents) {
+    if (t->opts.seed_block > 0) return std::min<int64_t>(rows, t->opts.seed_block);
+    int64_t per_seed = 0;
+    for (auto &b : t->bufs)
+        if (b.kind != BUF_CONST && b.alias_of < 0) per_seed += b.size * (int64_t)t->es * (tangents ? 2 : 1);
+    int64_t budget = 24LL << 30;   // 24 GB of the 180 GB for seed-batched adjoints
+    int64_t R = std::max<int64_t>(1, budget / std::max<int64_t>(per_seed, 1));
+    R = std::min<int64_t>(R, 8192);
+    return std::min(R, rows);
+}
+
+// ------------------------------------------------------------------------------------------ loader
+static bool is_transpose_map(const int64_t *m, int64_t r, int64_t c) {
+    // operand is r x c, origin is c x r: operand (i,j) at k = i + j*r  ->  origin index j + i*c
+    for (int64_t j = 0; j < c; ++j)
+        for (int64_t i = 0; i < r; ++i)
+            if (m[i + j * r] != j + i * c) return false;
+    return true;
+}
+static bool is_identity_map(const int64_t *m, int64_t n) {
+    for (int64_t i = 0; i < n; ++i)
+        if (m[i] != i) return false;
+    return true;
+}
+
+static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
+    if (nbytes < sizeof(Header)) return fail(RDB_EINVAL, "tape program too short");
+    Header h;
+    memcpy(&h, raw, sizeof(h));
+    if (h.magic != kMagic) return fail(RDB_EINVAL, "not a tape program (bad magic)");
+    if (h.version != kVersion) return fail(RDB_EINVAL, "tape program version %u, engine expects %u", h.version, kVersion);
+    if (h.total_bytes != nbytes) return fail(RDB_EINVAL, "tape program is truncated (%llu != %zu)", (unsigned long long)h.total_bytes, nbytes);
+    if (h.dtype != RDB_F64 && h.dtype != RDB_F32) return fail(RDB_EINVAL, "unknown dtype %u", h.dtype);
+    auto in_range = [&](uint64_t off, uint64_t bytes) { return off <= nbytes && bytes <= nbytes - off; };
+    if (!in_range(h.off_buffers, (uint64_t)h.n_buffers * sizeof(BufferRec)) || !in_range(h.off_inputs, (uint64_t)h.n_inputs * 4) ||
+        !in_range(h.off_instr, (uint64_t)h.n_instr * sizeof(InstrRec)) || !in_range(h.off_idx, h.n_idx * 8) ||
+        !in_range(h.off_expr, h.n_expr * 4) || !in_range(h.off_fconst, h.n_fconst * 8) || !in_range(h.off_const, h.n_const))
+        return fail(RDB_EINVAL, "tape program section out of range");
+    t->dtype = (int)h.dtype;
+    t->es = h.dtype == RDB_F64 ? 8 : 4;
+    const BufferRec *brec = (const BufferRec *)(raw + h.off_buffers);
+    const int32_t *inputs = (const int32_t *)(raw + h.off_inputs);
+    const InstrRec *irec = (const InstrRec *)(raw + h.off_instr);
+    const int64_t *idx = (const int64_t *)(raw + h.off_idx);
+    const int32_t *expr = (const int32_t *)(raw + h.off_expr);
+    const double *fconst = (const double *)(raw + h.off_fconst);
+    const uint8_t *consts = raw + h.off_const;
+
+    // buffers ------------------------------------------------------------------------------------------
+    t->bufs.resize(h.n_buffers);
+    for (uint32_t i = 0; i < h.n_buffers; ++i) {
+        Buf &b = t->bufs[i];
+        const BufferRec &r = brec[i];
+        if (r.ndims < 0 || r.ndims > kMaxDims) return fail(RDB_EINVAL, "buffer %u: bad ndims", i);
+        b.kind = r.kind; b.nd = r.ndims; b.alias_of = r.alias_of; b.size = 1;
+        for (int d = 0; d < kMaxDims; ++d) {
+            b.dims[d] = d < r.ndims ? r.dims[d] : 1;
+            if (b.dims[d] < 0) return fail(RDB_EINVAL, "buffer %u: negative dim", i);
+            b.size *= b.dims[d];
+        }
+        if (b.kind != BUF_TA && b.kind != BUF_TR && b.kind != BUF_CONST) return fail(RDB_EINVAL, "buffer %u: bad kind", i);
+        if (b.alias_of >= 0) {
+            if ((uint32_t)b.alias_of >= i || t->bufs[b.alias_of].size != b.size) return fail(RDB_EINVAL, "buffer %u: bad alias", i);
+            b.val = t->bufs[b.alias_of].val;   // reshape shares value AND deriv (tracked.jl:402-408)
+            continue;
+        }
+        OK(dev_alloc(t, &b.val, b.size * (int64_t)t->es));
+        if (b.kind == BUF_CONST) {
+            if (r.const_offset < 0 || !in_range(h.off_const + r.const_offset, b.size * t->es)) return fail(RDB_EINVAL, "buffer %u: const data out of range", i);
+            CU(cudaMemcpyAsync(b.val, consts + r.const_offset, (size_t)b.size * t->es, cudaMemcpyHostToDevice, S(t)));
+        } else {
+            CU(cudaMemsetAsync(b.val, 0, (size_t)b.size * t->es, S(t)));
+        }
+    }
+    for (uint32_t i = 0; i < h.n_inputs; ++i) {
+        if (inputs[i] < 0 || (uint32_t)inputs[i] >= h.n_buffers || t->bufs[inputs[i]].kind != BUF_TA) return fail(RDB_EINVAL, "bad input buffer id");
+        t->inputs.push_back(inputs[i]);
+    }
+    if (h.output_buffer < 0 || (uint32_t)h.output_buffer >= h.n_buffers) return fail(RDB_EINVAL, "bad output buffer id");
+    t->output = h.output_buffer;
+
+    if (h.n_fconst) {
+        OK(dev_alloc(t, (void **)&t->d_fconst, h.n_fconst * 8));
+        CU(cudaMemcpyAsync(t->d_fconst, fconst, h.n_fconst * 8, cudaMemcpyHostToDevice, S(t)));
+    }
+
+    // instructions ---------------------------------------------------------------------------------------
+    t->instrs.resize(h.n_instr);
+    for (uint32_t i = 0; i < h.n_instr; ++i) {
+        InstrPlan &I = t->instrs[i];
+        I.rec = irec[i];
+        const int op = I.rec.opcode;
+        if (I.rec.n_in < 1 || I.rec.n_in > kMaxArgs) return fail(RDB_EINVAL, "instruction %u: bad input count", i);
+        if (I.rec.out < 0 || (uint32_t)I.rec.out >= h.n_buffers || t->bufs[I.rec.out].kind == BUF_CONST) return fail(RDB_EINVAL, "instruction %u: bad output", i);
+        switch (op) {
+            case OP_MUL: case OP_ADD: case OP_SUB: if (I.rec.n_in != 2) return fail(RDB_EINVAL, "instruction %u: needs 2 inputs", i); break;
+            case OP_NEG: case OP_SUM: case OP_MEAN: case OP_GETINDEX: if (I.rec.n_in != 1) return fail(RDB_EINVAL, "instruction %u: needs 1 input", i); break;
+            case OP_NBCAST: case OP_MAP: case OP_BCAST: case OP_BCAST_ADD: case OP_BCAST_SUB: case OP_BCAST_MUL: break;
+            default:
+                // @grad / ChainRules closures, det, inv, cat, tracker_∇broadcast, scalar instructions, ... cannot be lowered
+                return fail(RDB_EUNSUPPORTED, "instruction %u: opcode %d cannot be replayed on the device (no CPU fallback)", i, op);
+        }
+        Buf &out = t->bufs[I.rec.out];
+        for (int a = 0; a < I.rec.n_in; ++a) {
+            OperandPlan &o = I.in[a];
+            o.rec = I.rec.in[a];
+            if (o.rec.buffer < 0 || (uint32_t)o.rec.buffer >= h.n_buffers) return fail(RDB_EINVAL, "instruction %u: bad operand buffer", i);
+            if (o.rec.ndims < 0 || o.rec.ndims > kMaxDims) return fail(RDB_EINVAL, "instruction %u: bad operand ndims", i);
+            Buf &b = t->bufs[o.rec.buffer];
+            if (o.rec.tracked && b.kind == BUF_CONST) return fail(RDB_EINVAL, "instruction %u: tracked CONST operand", i);
+            b.n_consumers++;
+            o.size = 1;
+            for (int d = 0; d < o.rec.ndims; ++d) o.size *= o.rec.dims[d];
+            o.rows = o.rec.ndims >= 1 ? o.rec.dims[0] : 1;
+            o.cols = o.rec.ndims >= 2 ? o.rec.dims[1] : 1;
+            const bool indexed = (o.rec.cls == CLS_IDX) || (op == OP_GETINDEX);
+            if (!indexed) {
+                if (o.size != b.size) return fail(RDB_EINVAL, "instruction %u: operand/buffer size mismatch", i);
+                continue;
+            }
+            if (o.rec.idx_kind == IDX_TRANSPOSE) {
+                if (b.nd != 2 || b.dims[0] != o.cols || b.dims[1] != o.rows) return fail(RDB_EINVAL, "instruction %u: transpose tag on a non-matching origin", i);
+                if (op != OP_MUL) return fail(RDB_EUNSUPPORTED, "instruction %u: transposed operand outside `*`", i);
+                o.mode = OPM_FOLDED_T;
+                continue;
+            }
+            if (o.rec.idx_kind != IDX_EXPLICIT) return fail(RDB_EINVAL, "instruction %u: indexed operand without a map", i);
+            const int64_t expect = op == OP_GETINDEX ? out.size : o.size;
+            if (o.rec.idx_offset < 0 || o.rec.idx_len != expect || (uint64_t)(o.rec.idx_offset + o.rec.idx_len) > h.n_idx)
+                return fail(RDB_EINVAL, "instruction %u: index map out of range", i);
+            const int64_t *m = idx + o.rec.idx_offset;
+            for (int64_t k = 0; k < o.rec.idx_len; ++k)
+                if (m[k] < 0 || m[k] >= b.size) return fail(RDB_EINVAL, "instruction %u: index map entry out of bounds", i);
+            if (op == OP_MUL && o.rec.ndims == 2 && b.size == o.size &&
+                ((b.nd == 2 && b.dims[0] == o.cols && b.dims[1] == o.rows) || (b.nd == 1 && o.rows == 1)) &&
+                is_transpose_map(m, o.rows, o.cols)) {
+                o.mode = OPM_FOLDED_T;     // pure transpose: folded into the GEMM operand flag
+                continue;
+            }
+            if (op == OP_MUL && b.size == o.size && is_identity_map(m, o.size)) { o.mode = OPM_PLAIN; continue; }
+            o.mode = OPM_GATHER;
+            OK(dev_alloc(t, (void **)&o.d_map, o.rec.idx_len * 8));
+            CU(cudaMemcpyAsync(o.d_map, m, (size_t)o.rec.idx_len * 8, cudaMemcpyHostToDevice, S(t)));
+            if (op == OP_MUL) {
+                OK(dev_alloc(t, &o.dense_val, o.size * (int64_t)t->es));
+                if (o.rec.tracked) OK(dev_alloc(t, &o.dense_der, o.size * (int64_t)t->es));
+            } else if (op != OP_GETINDEX) {
+                return fail(RDB_EUNSUPPORTED, "instruction %u: index-mapped operand outside `*`/getindex", i);
+            }
+        }
+        // shape checks + per-instruction caches
+        if (op == OP_MUL) {
+            if (I.in[0].cols != I.in[1].rows || out.size != I.in[0].rows * I.in[1].cols) return fail(RDB_EINVAL, "instruction %u: `*` shape mismatch", i);
+        } else if (op == OP_ADD || op == OP_SUB || op == OP_NEG) {
+            for (int a = 0; a < I.rec.n_in; ++a)
+                if (I.in[a].size != out.size || I.in[a].mode != OPM_PLAIN) return fail(RDB_EINVAL, "instruction %u: array +/- shape mismatch", i);
+        } else if (op == OP_SUM || op == OP_MEAN) {
+            if (out.size != 1 || I.in[0].mode != OPM_PLAIN) return fail(RDB_EINVAL, "instruction %u: sum/mean shape mismatch", i);
+        } else if (is_elementwise(op)) {
+            if (I.rec.expr_len < 1 || I.rec.n_expr_args != I.rec.n_in || (uint64_t)(I.rec.expr_offset + 4 * I.rec.expr_len) > h.n_expr)
+                return fail(RDB_EINVAL, "instruction %u: bad scalar expression", i);
+            if (I.rec.n_in + I.rec.expr_len > kMaxExprRegs) return fail(RDB_EUNSUPPORTED, "instruction %u: scalar expression too large", i);
+            const int32_t *ops = expr + I.rec.expr_offset;
+            for (int64_t k = 0; k < I.rec.expr_len; ++k) {
+                int code = ops[4 * k], ra = ops[4 * k + 1], rb = ops[4 * k + 2], imm = ops[4 * k + 3];
+                int reg = I.rec.n_in + (int)k;
+                if (code < E_CONST || code > E_ARG) return fail(RDB_EUNSUPPORTED, "instruction %u: scalar function %d is not on the whitelist", i, code);
+                if (code == E_CONST) { if (imm < 0 || (uint64_t)imm >= h.n_fconst) return fail(RDB_EINVAL, "instruction %u: bad literal", i); }
+                else if (code == E_ARG) { if (imm < 0 || imm >= I.rec.n_in) return fail(RDB_EINVAL, "instruction %u: bad arg ref", i); }
+                else {
+                    if (ra < 0 || ra >= reg) return fail(RDB_EINVAL, "instruction %u: bad SSA ref", i);
+                    bool binary = code == E_ADD || code == E_SUB || code == E_MUL || code == E_DIV || code == E_POW || code == E_MAX || code == E_MIN;
+                    if (binary && (rb < 0 || rb >= reg)) return fail(RDB_EINVAL, "instruction %u: bad SSA ref", i);
+                }
+            }
+            OK(dev_alloc(t, (void **)&I.d_ops, I.rec.expr_len * 16));
+            CU(cudaMemcpyAsync(I.d_ops, ops, (size_t)I.rec.expr_len * 16, cudaMemcpyHostToDevice, S(t)));
+            for (int a = 0; a < I.rec.n_in; ++a) {
+                if (I.in[a].mode != OPM_PLAIN) return fail(RDB_EUNSUPPORTED, "instruction %u: elementwise op on an index-mapped operand", i);
+                for (int d = 0; d < kMaxDims; ++d) {
+                    int64_t od = d < I.in[a].rec.ndims ? I.in[a].rec.dims[d] : 1;
+                    if (od != out.dims[d] && od != 1) return fail(RDB_EINVAL, "instruction %u: operand does not broadcast to the output", i);
+                }
+                // results[I].partial[p] (broadcast.jl:155; elementwise.jl:239): only tracked arguments are ever read back
+                if (I.in[a].rec.tracked) OK(dev_alloc(t, &I.partial[a], out.size * (int64_t)t->es));
+            }
+        } else if (op == OP_GETINDEX) {
+            if (I.in[0].mode != OPM_GATHER) return fail(RDB_EINVAL, "instruction %u: getindex without a map", i);
+        }
+    }
+    // reduction scratch: kReduceBlocks doubles for sums + column-reduction partials
+    t->scratch_bytes = std::max<int64_t>(kReduceBlocks * 8, 1 << 20);
+    for (auto &I : t->instrs)
+        if (is_elementwise(I.rec.opcode))
+            for (int a = 0; a < I.rec.n_in; ++a)
+                if (I.in[a].rec.tracked && I.in[a].size != t->bufs[I.rec.out].size)
+                    t->scratch_bytes = std::max<int64_t>(t->scratch_bytes, I.in[a].size * 4096 * 8);
+    OK(dev_alloc(t, &t->scratch, t->scratch_bytes));
+    OK(ensure_batch(t, 1));
+    CU(cudaStreamSynchronize(S(t)));
+    return RDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ gradient
+template <typename T>
+static int seed_scalar_and_reverse(rdb_tape *t) {
+    Buf &out = t->bufs[t->output];
+    if (out.size != 1) return fail(RDB_EINVAL, "gradient! needs a scalar tape output");
+    for (int b : t->inputs) OK(unseed<T>(t, t->bufs[b], 1));               // unseed!(input)
+    KL(t, launch_fill<T>(S(t), (T *)out.der, 1, (T)1));                     // seed!(output)
+    return reverse_pass<T>(t, 1);
+}
+
+template <typename T>
+static int gradient_impl(rdb_tape *t, void *const *result_ptrs, int on_device, void *value_out) {
+    OK(forward_pass<T>(t));
+    OK(seed_scalar_and_reverse<T>(t));
+    for (size_t i = 0; i < t->inputs.size(); ++i) {                          // extract_result!
+        if (!result_ptrs || !result_ptrs[i]) continue;
+        Buf &b = t->bufs[t->inputs[i]];
+        CU(cudaMemcpyAsync(result_ptrs[i], b.der, (size_t)b.size * t->es, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, S(t)));
+    }
+    if (value_out) CU(cudaMemcpyAsync(value_out, t->bufs[t->output].val, t->es, cudaMemcpyDeviceToHost, S(t)));
+    CU(cudaStreamSynchronize(S(t)));
+    return RDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ jacobian
+template <typename T>
+static int jacobian_impl(rdb_tape *t, int slot, int64_t rb, int64_t re, void *result, int64_t ld, int on_device, void *value_out) {
+    if (slot < 0 || (size_t)slot >= t->inputs.size()) return fail(RDB_EINVAL, "bad input slot");
+    Buf &out = t->bufs[t->output];
+    Buf &x = t->bufs[t->inputs[slot]];
+    const int64_t m = out.size, n = x.size;
+    if (rb < 0 || re > m || rb > re) return fail(RDB_EINVAL, "row range [%lld,%lld) outside [0,%lld)", (long long)rb, (long long)re, (long long)m);
+    const int64_t rows = re - rb;
+    if (rows > 0 && ld < rows) return fail(RDB_EINVAL, "leading dimension smaller than the row block");
+    OK(forward_pass<T>(t));
+    if (value_out) CU(cudaMemcpyAsync(value_out, out.val, (size_t)m * t->es, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, S(t)));
+    if (rows == 0) { CU(cudaStreamSynchronize(S(t))); return RDB_OK; }
+    const int64_t R = auto_seed_block(t, rows, false);
+    OK(ensure_batch(t, R));
+    T *dres = (T *)result;
+    int64_t dld = ld;
+    if (!on_device) {
+        OK(ensure_stage(t, rows * n * (int64_t)t->es));
+        dres = (T *)t->stage;
+        dld = rows;
+    }
+    for (int64_t i0 = rb; i0 < re; i0 += R) {
+        const int64_t Rb = std::min(R, re - i0);
+        for (int b : t->inputs) OK(unseed<T>(t, t->bufs[b], Rb));                      // unseed!(input)
+        KL(t, launch_seed_onehot<T>(S(t), (T *)out.der, m, Rb, i0));                    // seed!(output, i) for Rb rows
+        OK(reverse_pass<T>(t, Rb));
+        StepTimer tm(t, "rows_out", 2.0 * n * Rb * t->es, 0);
+        KL(t, launch_rows_out<T>(S(t), dres + (i0 - rb), dld, (const T *)x.der, n, Rb)); // result_matrix[i, :] = input_deriv
+    }
+    if (!on_device)
+        CU(cudaMemcpy2DAsync(result, (size_t)ld * t->es, t->stage, (size_t)rows * t->es, (size_t)rows * t->es, (size_t)n,
+                             cudaMemcpyDeviceToHost, S(t)));
+    CU(cudaStreamSynchronize(S(t)));
+    return RDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ hessian
+static int ensure_tangents(rdb_tape *t, int64_t K) {
+    if (K <= t->K_alloc) return RDB_OK;
+    for (auto &b : t->bufs) {
+        if (b.kind == BUF_CONST || b.alias_of >= 0) continue;
+        dev_free(t, b.tv); dev_free(t, b.td);
+        b.tv = b.td = nullptr;
+        OK(dev_alloc(t, &b.tv, b.size * K * (int64_t)t->es));
+        OK(dev_alloc(t, &b.td, b.size * K * (int64_t)t->es));
+        CU(cudaMemsetAsync(b.td, 0, (size_t)(b.size * K) * t->es, S(t)));
+    }
+    for (auto &b : t->bufs)
+        if (b.alias_of >= 0) { b.tv = t->bufs[b.alias_of].tv; b.td = t->bufs[b.alias_of].td; }
+    t->K_alloc = K;
+    return RDB_OK;
+}
+
+static int ensure_second_order(rdb_tape *t) {
+    if (t->second_order) return RDB_OK;
+    for (auto &I : t->instrs) {
+        const int op = I.rec.opcode;
+        if (op == OP_MUL) {
+            if (I.in[0].rec.tracked && I.in[1].rec.tracked)
+                return fail(RDB_EUNSUPPORTED, "hessian!: `*` of two tracked operands is not lowered yet");
+            for (int a = 0; a < 2; ++a)
+                if (I.in[a].mode == OPM_GATHER) return fail(RDB_EUNSUPPORTED, "hessian!: gathered `*` operand");
+            continue;
+        }
+        if (!is_elementwise(op)) continue;
+        Buf &out = t->bufs[I.rec.out];
+        const int N = I.rec.n_in;
+        for (int a = 0; a < N; ++a) {
+            if (I.in[a].size != out.size) return fail(RDB_EUNSUPPORTED, "hessian!: broadcasting elementwise instructions are not lowered yet");
+            if (!I.partial[a]) OK(dev_alloc(t, &I.partial[a], out.size * (int64_t)t->es));
+        }
+        for (int h = 0; h < N * (N + 1) / 2; ++h) OK(dev_alloc(t, &I.second[h], out.size * (int64_t)t->es));
+    }
+    t->second_order = true;
+    return RDB_OK;
+}
+
+static int tri_index(int p, int q, int N) {
+    if (p > q) std::swap(p, q);
+    return p * N - p * (p - 1) / 2 + (q - p);
+}
+
+// forward-over-reverse: value tangents forward, (adjoint, adjoint tangent) backward, K directions at a time.
+template <typename T>
+static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64_t ld, int on_device, void *grad_out, void *value_out) {
+    if (t->inputs.size() != 1) return fail(RDB_EINVAL, "Taking the Hessian of a function with multiple arguments is not yet supported");
+    Buf &out = t->bufs[t->output];
+    Buf &x = t->bufs[t->inputs[0]];
+    if (out.size != 1) return fail(RDB_EINVAL, "hessian! needs a scalar tape output");
+    const int64_t n = x.size;
+    if (cb < 0 || ce > n || cb > ce) return fail(RDB_EINVAL, "column range outside [0,n)");
+    const int64_t cols = ce - cb;
+    if (cols > 0 && ld < n) return fail(RDB_EINVAL, "leading dimension smaller than n");
+    OK(ensure_second_order(t));
+    OK(forward_pass<T>(t, 2));
+    // first-order reverse sweep: adjoints of every buffer are needed by the tangent sweep, so intermediates are
+    // kept (no unseed) until the chunk loop is done; gradient falls out for free (DiffResult method, hessians.jl:92-97)
+    if (value_out) CU(cudaMemcpyAsync(value_out, out.val, t->es, cudaMemcpyDeviceToHost, S(t)));
+    if (cols == 0 && !grad_out) { CU(cudaStreamSynchronize(S(t))); return RDB_OK; }
+    const int64_t K = std::max<int64_t>(1, auto_seed_block(t, std::max<int64_t>(cols, 1), true));
+    OK(ensure_tangents(t, K));
+    T *dres = (T *)result;
+    int64_t dld = ld;
+    if (!on_device && cols > 0) {
+        OK(ensure_stage(t, n * cols * (int64_t)t->es));
+        dres = (T *)t->stage;
+        dld = n;
+    }
+    bool first = true;
+    for (int64_t c0 = cb; c0 < ce || first; c0 += K) {
+        const int64_t Kb = cols > 0 ? std::min(K, ce - c0) : 1;
+        // ---- tangent-forward sweep
+        KL(t, launch_seed_tangent<T>(S(t), (T *)x.tv, n, Kb, c0));
+        for (auto &I : t->instrs) {
+            Buf &o = t->bufs[I.rec.out];
+            switch (I.rec.opcode) {
+                case OP_GETINDEX:
+                    KL(t, launch_gather_cols<T>(S(t), (T *)o.tv, (const T *)t->bufs[I.in[0].rec.buffer].tv, t->bufs[I.in[0].rec.buffer].size, I.in[0].d_map, o.size, Kb));
+                    break;
+                case OP_ADD: case OP_SUB: {
+                    T sign = I.rec.opcode == OP_ADD ? (T)1 : (T)-1;
+                    Buf &a = t->bufs[I.in[0].rec.buffer], &b = t->bufs[I.in[1].rec.buffer];
+                    if (I.in[0].rec.tracked) KL(t, launch_axpy<T>(S(t), (T *)o.tv, (const T *)a.tv, (T)1, o.size * Kb, true));
+                    else CU(cudaMemsetAsync(o.tv, 0, (size_t)(o.size * Kb) * t->es, S(t)));
+                    if (I.in[1].rec.tracked) KL(t, launch_axpy<T>(S(t), (T *)o.tv, (const T *)b.tv, sign, o.size * Kb, false));
+                } break;
+                case OP_NEG:
+                    KL(t, launch_axpy<T>(S(t), (T *)o.tv, (const T *)t->bufs[I.in[0].rec.buffer].tv, (T)-1, o.size * Kb, true));
+                    break;
+                case OP_SUM: case OP_MEAN: {
+                    T scale = I.rec.opcode == OP_MEAN ? (T)1 / (T)I.in[0].size : (T)1;
+                    KL(t, launch_colsum<T>(S(t), (T *)o.tv, (const T *)t->bufs[I.in[0].rec.buffer].tv, I.in[0].size, Kb, scale));
+                } break;
+                case OP_MUL: {
+                    // exactly one tracked operand (checked): tangent is linear in it
+                    OperandPlan &oa = I.in[0], &ob = I.in[1];
+                    int64_t M = oa.rows, Kd = oa.cols, N = ob.cols;
+                    if (ob.rec.tracked) {
+                        if (ob.mode != OPM_PLAIN) return fail(RDB_EUNSUPPORTED, "hessian!: transposed tracked `*` operand");
+                        Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
+                        bool st = oa.mode == OPM_FOLDED_T;
+                        KL(t, gemm_t<T>(S(t), st, false, M, N * Kb, Kd, (T)1, (const T *)a.val, st ? oa.cols : oa.rows, (const T *)b.tv, Kd, (T)0, (T *)o.tv, M));
+                    } else {
+                        if (oa.mode != OPM_PLAIN) return fail(RDB_EUNSUPPORTED, "hessian!: transposed tracked `*` operand");
+                        Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
+                        bool st = ob.mode == OPM_FOLDED_T;
+                        for (int64_t k = 0; k < Kb; ++k)
+                            KL(t, gemm_t<T>(S(t), false, st, M, N, Kd, (T)1, (const T *)a.tv + k * a.size, M, (const T *)b.val, st ? ob.cols : ob.rows, (T)0, (T *)o.tv + k * o.size, M));
+                    }
+                } break;
+                default: {   // elementwise closures
+                    const T *part[kMaxArgs], *tvs[kMaxArgs];
+                    for (int a = 0; a < I.rec.n_in; ++a) {
+                        part[a] = (const T *)I.partial[a];
+                        tvs[a] = (const T *)t->bufs[I.in[a].rec.buffer].tv;
+                        if (!I.in[a].rec.tracked) return fail(RDB_EUNSUPPORTED, "hessian!: untracked elementwise argument");
+                    }
+                    StepTimer tm(t, "tangent_forward", (double)(I.rec.n_in + 1) * o.size * Kb * t->es, 0);
+                    KL(t, launch_tangent_forward<T>(S(t), (T *)o.tv, I.rec.n_in, part, tvs, o.size, Kb));
+                }
+            }
+        }
+        // ---- reverse sweep carrying (adjoint, adjoint tangent); adjoints are recomputed per chunk (R = 1, cheap)
+        for (int b : t->inputs) { OK(unseed<T>(t, t->bufs[b], 1)); CU(cudaMemsetAsync(t->bufs[b].td, 0, (size_t)(t->bufs[b].size * Kb) * t->es, S(t))); }
+        KL(t, launch_fill<T>(S(t), (T *)out.der, 1, (T)1));
+        CU(cudaMemsetAsync(out.td, 0, (size_t)Kb * t->es, S(t)));
+        for (size_t ii = t->instrs.size(); ii-- > 0;) {
+            InstrPlan &I = t->instrs[ii];
+            Buf &o = t->bufs[I.rec.out];
+            const T *delta = (const T *)o.der, *dt = (const T *)o.td;
+            switch (I.rec.opcode) {
+                case OP_GETINDEX: {
+                    Buf &b = t->bufs[I.in[0].rec.buffer];
+                    KL(t, launch_scatter_add<T>(S(t), (T *)b.der, b.size, I.in[0].d_map, delta, o.size, 1));
+                    KL(t, launch_scatter_add<T>(S(t), (T *)b.td, b.size, I.in[0].d_map, dt, o.size, Kb));
+                } break;
+                case OP_ADD: case OP_SUB:
+                    for (int a = 0; a < 2; ++a) {
+                        if (!I.in[a].rec.tracked) continue;
+                        Buf &b = t->bufs[I.in[a].rec.buffer];
+                        T sign = (a == 1 && I.rec.opcode == OP_SUB) ? (T)-1 : (T)1;
+                        KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, sign, o.size, false));
+                        KL(t, launch_axpy<T>(S(t), (T *)b.td, dt, sign, o.size * Kb, false));
+                    }
+                    break;
+                case OP_NEG: {
+                    Buf &b = t->bufs[I.in[0].rec.buffer];
+                    KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, (T)-1, o.size, false));
+                    KL(t, launch_axpy<T>(S(t), (T *)b.td, dt, (T)-1, o.size * Kb, false));
+                } break;
+                case OP_SUM: case OP_MEAN: {
+                    Buf &b = t->bufs[I.in[0].rec.buffer];
+                    T scale = I.rec.opcode == OP_MEAN ? (T)1 / (T)I.in[0].size : (T)1;
+                    KL(t, launch_acc_scalar<T>(S(t), (T *)b.der, b.size, 1, delta, scale, false));
+                    KL(t, launch_acc_scalar<T>(S(t), (T *)b.td, b.size, Kb, dt, scale, false));
+                } break;
+                case OP_MUL: {
+                    OperandPlan &oa = I.in[0], &ob = I.in[1];
+                    int64_t M = oa.rows, Kd = oa.cols, N = ob.cols;
+                    if (ob.rec.tracked) {
+                        Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
+                        bool st = oa.mode == OPM_FOLDED_T;
+                        KL(t, gemm_t<T>(S(t), !st, false, Kd, N, M, (T)1, (const T *)a.val, st ? oa.cols : oa.rows, delta, M, (T)1, (T *)b.der, Kd));
+                        KL(t, gemm_t<T>(S(t), !st, false, Kd, N * Kb, M, (T)1, (const T *)a.val, st ? oa.cols : oa.rows, dt, M, (T)1, (T *)b.td, Kd));
+                    } else {
+                        Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
+                        bool st = ob.mode == OPM_FOLDED_T;
+                        KL(t, gemm_t<T>(S(t), false, !st, M, Kd, N, (T)1, delta, M, (const T *)b.val, st ? ob.cols : ob.rows, (T)1, (T *)a.der, M));
+                        for (int64_t k = 0; k < Kb; ++k)
+                            KL(t, gemm_t<T>(S(t), false, !st, M, Kd, N, (T)1, dt + k * o.size, M, (const T *)b.val, st ? ob.cols : ob.rows, (T)1, (T *)a.td + k * a.size, M));
+                    }
+                } break;
+                default: {
+                    const int N = I.rec.n_in;
+                    const T *tvs[kMaxArgs];
+                    for (int a = 0; a < N; ++a) tvs[a] = (const T *)t->bufs[I.in[a].rec.buffer].tv;
+                    for (int p = 0; p < N; ++p) {
+                        Buf &b = t->bufs[I.in[p].rec.buffer];
+                        const T *sec[kMaxArgs];
+                        for (int q = 0; q < N; ++q) sec[q] = (const T *)I.second[tri_index(p, q, N)];
+                        StepTimer tm(t, "tangent_reverse", (double)(N + 3) * o.size * Kb * t->es, 0);
+                        KL(t, launch_tangent_reverse<T>(S(t), (T *)b.td, dt, delta, (const T *)I.partial[p], N, sec, tvs, o.size, Kb, false));
+                        KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[p], o.size, 1, false));
+                    }
+                }
+            }
+            OK(unseed<T>(t, o, 1));
+            CU(cudaMemsetAsync(o.td, 0, (size_t)(o.size * Kb) * t->es, S(t)));
+        }
+        if (cols > 0) {
+            StepTimer tm(t, "hessian_cols_out", 2.0 * n * Kb * t->es, 0);
+            KL(t, launch_copy2d<T>(S(t), dres + (c0 - cb) * dld, dld, (const T *)x.td, n, n, Kb));   // H[:, c0:c0+Kb] = tangent of deriv(x)
+        }
+        first = false;
+        if (cols == 0) break;
+    }
+    if (grad_out) CU(cudaMemcpyAsync(grad_out, x.der, (size_t)n * t->es, cudaMemcpyDeviceToHost, S(t)));
+    if (!on_device && cols > 0)
+        CU(cudaMemcpy2DAsync(result, (size_t)ld * t->es, t->stage, (size_t)n * t->es, (size_t)n * t->es, (size_t)cols, cudaMemcpyDeviceToHost, S(t)));
+    CU(cudaStreamSynchronize(S(t)));
+    return RDB_OK;
+}
+
+// ================================================================================================ C ABI
+#define DISPATCH(t, fn, ...) ((t)->dtype == RDB_F64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+
+extern "C" {
+
+const char *rdb_version(void) { return "rdb200 0.1 (sm_100a)"; }
+const char *rdb_last_error(void) { return g_err; }
+
+rdb_ctx *rdb_ctx_create(int device_id) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        fail(RDB_ENODEVICE, "no CUDA device (%s): the B200 engine has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (device_id < 0 || device_id >= n) { fail(RDB_EINVAL, "device %d out of range (%d devices)", device_id, n); return nullptr; }
+    if (cudaSetDevice(device_id) != cudaSuccess) { fail(RDB_ECUDA, "cudaSetDevice(%d) failed", device_id); return nullptr; }
+    auto *c = new rdb_ctx();
+    c->device = device_id;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(RDB_ECUDA, "cudaStreamCreate failed"); delete c; return nullptr; }
+    return c;
+}
+void rdb_ctx_destroy(rdb_ctx *c) {
+    if (!c) return;
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+int rdb_ctx_set_stream(rdb_ctx *c, void *stream) {
+    if (!c) return fail(RDB_EINVAL, "null context");
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)stream;
+    c->own_stream = false;
+    return RDB_OK;
+}
+int rdb_ctx_synchronize(rdb_ctx *c) {
+    if (!c) return fail(RDB_EINVAL, "null context");
+    CU(cudaStreamSynchronize(c->stream));
+    return RDB_OK;
+}
+
+rdb_tape *rdb_tape_load(rdb_ctx *c, const void *program, size_t nbytes, const rdb_options *opts) {
+    if (!c || !program) { fail(RDB_EINVAL, "null argument"); return nullptr; }
+    cudaSetDevice(c->device);
+    auto *t = new rdb_tape();
+    t->ctx = c;
+    t->opts.fuse_elementwise = 1; t->opts.use_graph = 1;
+    if (opts) t->opts = *opts;
+    cudaEventCreate(&t->ev0);
+    cudaEventCreate(&t->ev1);
+    if (load_program(t, (const uint8_t *)program, nbytes) != RDB_OK) { rdb_tape_destroy(t); return nullptr; }
+    return t;
+}
+void rdb_tape_destroy(rdb_tape *t) {
+    if (!t) return;
+    if (t->ctx) cudaStreamSynchronize(t->ctx->stream);
+    for (void *p : t->allocs) cudaFree(p);
+    if (t->ev0) cudaEventDestroy(t->ev0);
+    if (t->ev1) cudaEventDestroy(t->ev1);
+    delete t;
+}
+
+int rdb_tape_set_input(rdb_tape *t, int slot, const void *data, int is_device) {
+    if (!t || !data) return fail(RDB_EINVAL, "null argument");
+    if (slot < 0 || (size_t)slot >= t->inputs.size()) return fail(RDB_EINVAL, "input slot %d out of range", slot);
+    Buf &b = t->bufs[t->inputs[slot]];
+    CU(cudaMemcpyAsync(b.val, data, (size_t)b.size * t->es, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, S(t)));
+    t->forward_valid = false;
+    return RDB_OK;
+}
+int rdb_forward(rdb_tape *t) {
+    if (!t) return fail(RDB_EINVAL, "null tape");
+    OK(DISPATCH(t, forward_pass, t, 1));
+    CU(cudaStreamSynchronize(S(t)));
+    return RDB_OK;
+}
+int rdb_reverse_scalar_seed(rdb_tape *t) {
+    if (!t) return fail(RDB_EINVAL, "null tape");
+    OK(DISPATCH(t, seed_scalar_and_reverse, t));
+    CU(cudaStreamSynchronize(S(t)));
+    return RDB_OK;
+}
+int rdb_gradient(rdb_tape *t, void *const *result_ptrs, int on_device, void *value_out) {
+    if (!t) return fail(RDB_EINVAL, "null tape");
+    return DISPATCH(t, gradient_impl, t, result_ptrs, on_device, value_out);
+}
+int rdb_jacobian(rdb_tape *t, int slot, int64_t rb, int64_t re, void *result, int64_t ld, int on_device, void *value_out) {
+    if (!t || (!result && re > rb)) return fail(RDB_EINVAL, "null argument");
+    return DISPATCH(t, jacobian_impl, t, slot, rb, re, result, ld, on_device, value_out);
+}
+int rdb_hessian(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64_t ld, int on_device, void *grad_out, void *value_out) {
+    if (!t || (!result && ce > cb)) return fail(RDB_EINVAL, "null argument");
+    return DISPATCH(t, hessian_impl, t, cb, ce, result, ld, on_device, grad_out, value_out);
+}
+int64_t rdb_buffer_size(rdb_tape *t, int b) {
+    if (!t || b < 0 || (size_t)b >= t->bufs.size()) return -1;
+    return t->bufs[b].size;
+}
+int rdb_get_value(rdb_tape *t, int b, void *dst) {
+    if (!t || !dst || b < 0 || (size_t)b >= t->bufs.size()) return fail(RDB_EINVAL, "bad buffer id");
+    CU(cudaMemcpyAsync(dst, t->bufs[b].val, (size_t)t->bufs[b].size * t->es, cudaMemcpyDeviceToHost, S(t)));
+    CU(cudaStreamSynchronize(S(t)));
+    return RDB_OK;
+}
+int rdb_get_deriv(rdb_tape *t, int b, void *dst) {
+    if (!t || !dst || b < 0 || (size_t)b >= t->bufs.size()) return fail(RDB_EINVAL, "bad buffer id");
+    if (!t->bufs[b].der) return fail(RDB_EINVAL, "buffer %d has no deriv (CONST)", b);
+    CU(cudaMemcpyAsync(dst, t->bufs[b].der, (size_t)t->bufs[b].size * t->es, cudaMemcpyDeviceToHost, S(t)));
+    CU(cudaStreamSynchronize(S(t)));
+    return RDB_OK;
+}
+int rdb_tape_stats(rdb_tape *t, char *json, size_t cap) {
+    if (!t || !json || cap < 3) return fail(RDB_EINVAL, "bad argument");
+    std::string s = "[";
+    char buf[512];
+    for (size_t i = 0; i < t->stats.size(); ++i) {
+        auto &st = t->stats[i];
+        snprintf(buf, sizeof(buf), "%s{\"step\":\"%s\",\"count\":%d,\"ms\":%.6f,\"bytes\":%.0f,\"flops\":%.0f}", i ? "," : "", st.name.c_str(), st.count, st.ms, st.bytes, st.flops);
+        s += buf;
+    }
+    s += "]";
+    if (s.size() + 1 > cap) return fail(RDB_EINVAL, "stats buffer too small");
+    memcpy(json, s.c_str(), s.size() + 1);
+    t->stats.clear();
+    return RDB_OK;
+}
+int64_t rdb_tape_launch_count(rdb_tape *t) { return t ? t->launches : -1; }
+
+int rdb_gemm(rdb_ctx *c, int dtype, int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const void *A, int64_t lda,
+             const void *B, int64_t ldb, double beta, void *C, int64_t ldc) {
+    if (!c) return fail(RDB_EINVAL, "null context");
+    cudaError_t e = dtype == RDB_F64
+                        ? gemm_f64(c->stream, ta != 0, tb != 0, m, n, k, alpha, (const double *)A, lda, (const double *)B, ldb, beta, (double *)C, ldc)
+                        : gemm_f32(c->stream, ta != 0, tb != 0, m, n, k, (float)alpha, (const float *)A, lda, (const float *)B, ldb, (float)beta, (float *)C, ldc);
+    if (e != cudaSuccess) return fail(RDB_ECUDA, "gemm launch failed: %s", cudaGetErrorString(e));
+    return RDB_OK;
+}
+
+int rdb_add_sum(rdb_ctx *c, int dtype, int64_t n, const void *a, const void *b, double sign, void *out, void *sum_out) {
+    if (!c) return fail(RDB_EINVAL, "null context");
+    static void *scratch = nullptr;
+    if (!scratch && cudaMalloc(&scratch, kReduceBlocks * 8) != cudaSuccess) return fail(RDB_ENOMEM, "scratch alloc failed");
+    cudaError_t e;
+    if (dtype == RDB_F64) {
+        e = launch_add<double>(c->stream, (double *)out, (const double *)a, (const double *)b, sign, n, (double *)scratch);
+        if (e == cudaSuccess) e = launch_finish_sum<double>(c->stream, (const double *)scratch, (double *)sum_out, 1.0);
+    } else {
+        e = launch_add<float>(c->stream, (float *)out, (const float *)a, (const float *)b, (float)sign, n, (float *)scratch);
+        if (e == cudaSuccess) e = launch_finish_sum<float>(c->stream, (const float *)scratch, (float *)sum_out, 1.f);
+    }
+    if (e != cudaSuccess) return fail(RDB_ECUDA, "add_sum launch failed: %s", cudaGetErrorString(e));
+    return RDB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,484 @@
+// GEMM kernels behind every `*` instruction of a ReverseDiff tape and its two adjoints
+// (reference: mul! in src/derivatives/linalg/arithmetic.jl:245-255 forward, :272-285 reverse).
+//
+//   C(MxN) <- alpha * op(A)(MxK) * op(B)(KxN) + beta * C,   everything column-major (Julia layout).
+//
+// FP64: tcgen05 has no f64 MMA kind, so the FP64 tensor path on sm_100a is `mma.sync ... f64` (SASS DMMA).
+//       128x128x16 CTA tile, 8 warps (2x4), 64x32 warp tile = 8x4 m8n8k4 DMMA tiles, multi-stage cp.async
+//       (LDGSTS) pipeline, padded shared-memory rows so every fragment LDS.64 is bank-conflict free.
+//       The beta=1 epilogue is what folds `increment_deriv!(a, mul!(a_tmp, ...))` (arithmetic.jl:279-284)
+//       into the GEMM: tmp = A*B is rounded to double in the accumulator, then added — same arithmetic.
+// FP32: SIMT FFMA 128x128x16 tile (8x8 per thread); FP32 accumulate.  (tcgen05 kind::tf32 needs a 3xTF32
+//       split to hold the 1e-5 bound — see DESIGN.md; not in this round.)
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "kernels.h"
+
+namespace rdb {
+
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem, bool pred) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    int sz = pred ? 16 : 0;   // src-size 0 => zero-fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem, bool pred) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    int sz = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_4(void *smem, const void *gmem, bool pred) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    int sz = pred ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ==================================================================================================
+// FP64 DMMA kernel
+// ==================================================================================================
+namespace d64 {
+constexpr int BM = 128, BN = 128, BK = 16, THREADS = 256, PAD = 4;
+constexpr int STAGES = 4;
+// tile of op(X) with R rows in the "outer" dim (m or n) and BK in k:
+//   KMAJOR (k contiguous in global):  smem [R][BK+PAD]
+//   else   (m/n contiguous in global): smem [BK][R+PAD]
+template <bool KMAJOR, int R>
+struct Tile {
+    static constexpr int STRIDE = KMAJOR ? (BK + PAD) : (R + PAD);
+    static constexpr int ELEMS = KMAJOR ? R * (BK + PAD) : BK * (R + PAD);
+    __device__ __forceinline__ static int at(int r, int k) { return KMAJOR ? r * STRIDE + k : k * STRIDE + r; }
+};
+
+// global -> shared for one k-tile.  `g` points at element (row 0, k 0) of op(X); ld is the leading dim of the
+// stored matrix.  KMAJOR: element (r,k) at g[k + r*ld]; else at g[r + k*ld].
+template <bool KMAJOR, int R, bool VEC>
+__device__ __forceinline__ void load_tile(double *s, const double *g, int64_t ld, int r0, int k0, int Rtot, int Ktot,
+                                          int tid) {
+    using TL = Tile<KMAJOR, R>;
+    if (VEC) {
+        constexpr int CHUNKS = R * BK / 2;
+#pragma unroll
+        for (int i = 0; i < CHUNKS / THREADS; ++i) {
+            int c = tid + i * THREADS;
+            if (KMAJOR) {
+                int r = c / (BK / 2), kc = (c % (BK / 2)) * 2;
+                bool p = (r0 + r < Rtot) && (k0 + kc < Ktot);
+                const double *src = p ? g + (int64_t)(k0 + kc) + (int64_t)(r0 + r) * ld : g;
+                cp_async_16(s + TL::at(r, kc), src, p);
+            } else {
+                int k = c / (R / 2), rc = (c % (R / 2)) * 2;
+                bool p = (r0 + rc < Rtot) && (k0 + k < Ktot);
+                const double *src = p ? g + (int64_t)(r0 + rc) + (int64_t)(k0 + k) * ld : g;
+                cp_async_16(s + TL::at(rc, k), src, p);
+            }
+        }
+    } else {
+        constexpr int ELEMS = R * BK;
+#pragma unroll
+        for (int i = 0; i < ELEMS / THREADS; ++i) {
+            int c = tid + i * THREADS;
+            if (KMAJOR) {
+                int r = c / BK, k = c % BK;
+                bool p = (r0 + r < Rtot) && (k0 + k < Ktot);
+                const double *src = p ? g + (int64_t)(k0 + k) + (int64_t)(r0 + r) * ld : g;
+                cp_async_8(s + TL::at(r, k), src, p);
+            } else {
+                int k = c / R, r = c % R;
+                bool p = (r0 + r < Rtot) && (k0 + k < Ktot);
+                const double *src = p ? g + (int64_t)(r0 + r) + (int64_t)(k0 + k) * ld : g;
+                cp_async_8(s + TL::at(r, k), src, p);
+            }
+        }
+    }
+}
+
+template <bool TA, bool TB>
+constexpr int smem_bytes() {
+    return STAGES * (Tile<TA, BM>::ELEMS + Tile<!TB, BN>::ELEMS) * (int)sizeof(double);
+}
+
+// op(A) is MxK.  !TA: A stored MxK (m contiguous)  -> not KMAJOR.   TA: A stored KxM (k contiguous) -> KMAJOR.
+// op(B) is KxN.  !TB: B stored KxN (k contiguous)  -> KMAJOR.       TB: B stored NxK (n contiguous) -> not KMAJOR.
+template <bool TA, bool TB, bool VEC>
+__global__ void __launch_bounds__(THREADS, 1)
+dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, int64_t lda,
+                  const double *__restrict__ B, int64_t ldb, double beta, double *__restrict__ C, int64_t ldc) {
+    extern __shared__ __align__(16) double smem[];
+    using TLA = Tile<TA, BM>;
+    using TLB = Tile<!TB, BN>;
+    double *sA = smem;
+    double *sB = smem + STAGES * TLA::ELEMS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;      // 2 x 4 warps; warp tile 64 x 32
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int KT = (K + BK - 1) / BK;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) {
+            load_tile<TA, BM, VEC>(sA + s * TLA::ELEMS, A, lda, m0, s * BK, M, K, tid);
+            load_tile<!TB, BN, VEC>(sB + s * TLB::ELEMS, B, ldb, n0, s * BK, N, K, tid);
+        }
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < KT) {
+                int s = nk % STAGES;
+                load_tile<TA, BM, VEC>(sA + s * TLA::ELEMS, A, lda, m0, nk * BK, M, K, tid);
+                load_tile<!TB, BN, VEC>(sB + s * TLB::ELEMS, B, ldb, n0, nk * BK, N, K, tid);
+            }
+            cp_async_commit();
+        }
+        const double *a_s = sA + (kt % STAGES) * TLA::ELEMS;
+        const double *b_s = sB + (kt % STAGES) * TLB::ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) af[i] = a_s[TLA::at(wm * 64 + i * 8 + g, kk + t)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = b_s[TLB::at(wn * 32 + j * 8 + g, kk + t)];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: C fragment of tile (i,j): rows m0+wm*64+i*8+g, cols n0+wn*32+j*8+2t+{0,1}
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            int col = n0 + wn * 32 + j * 8 + 2 * t + c;
+            if (col >= N) continue;
+            double *cp = C + (int64_t)col * ldc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int row = m0 + wm * 64 + i * 8 + g;
+                if (row < M) {
+                    double v = alpha * acc[i][j][c];
+                    if (beta != 0.0) v += beta * cp[row];
+                    cp[row] = v;
+                }
+            }
+        }
+    }
+}
+
+// small-problem variant: 64x64x16 tile, 4 warps (2x2), 32x32 warp tile — more CTAs for the 100x100 config
+constexpr int SBM = 64, SBN = 64, STHREADS = 128, SSTAGES = 2;
+template <bool KMAJOR, int R>
+__device__ __forceinline__ void load_tile_small(double *s, const double *g, int64_t ld, int r0, int k0, int Rtot,
+                                                int Ktot, int tid) {
+    using TL = Tile<KMAJOR, R>;
+    constexpr int ELEMS = R * BK;
+#pragma unroll
+    for (int i = 0; i < ELEMS / STHREADS; ++i) {
+        int c = tid + i * STHREADS;
+        int r, k;
+        if (KMAJOR) { r = c / BK; k = c % BK; } else { k = c / R; r = c % R; }
+        bool p = (r0 + r < Rtot) && (k0 + k < Ktot);
+        const double *src = p ? (KMAJOR ? g + (int64_t)(k0 + k) + (int64_t)(r0 + r) * ld
+                                        : g + (int64_t)(r0 + r) + (int64_t)(k0 + k) * ld)
+                              : g;
+        cp_async_8(s + TL::at(r, k), src, p);
+    }
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(STHREADS)
+dgemm_dmma_small_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, int64_t lda,
+                        const double *__restrict__ B, int64_t ldb, double beta, double *__restrict__ C, int64_t ldc) {
+    using TLA = Tile<TA, SBM>;
+    using TLB = Tile<!TB, SBN>;
+    __shared__ __align__(16) double sA[SSTAGES * TLA::ELEMS];
+    __shared__ __align__(16) double sB[SSTAGES * TLB::ELEMS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int m0 = blockIdx.x * SBM, n0 = blockIdx.y * SBN;
+    const int KT = (K + BK - 1) / BK;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < SSTAGES - 1; ++s) {
+        if (s < KT) {
+            load_tile_small<TA, SBM>(sA + s * TLA::ELEMS, A, lda, m0, s * BK, M, K, tid);
+            load_tile_small<!TB, SBN>(sB + s * TLB::ELEMS, B, ldb, n0, s * BK, N, K, tid);
+        }
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<SSTAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + SSTAGES - 1;
+            if (nk < KT) {
+                int s = nk % SSTAGES;
+                load_tile_small<TA, SBM>(sA + s * TLA::ELEMS, A, lda, m0, nk * BK, M, K, tid);
+                load_tile_small<!TB, SBN>(sB + s * TLB::ELEMS, B, ldb, n0, nk * BK, N, K, tid);
+            }
+            cp_async_commit();
+        }
+        const double *a_s = sA + (kt % SSTAGES) * TLA::ELEMS;
+        const double *b_s = sB + (kt % SSTAGES) * TLB::ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = a_s[TLA::at(wm * 32 + i * 8 + g, kk + t)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = b_s[TLB::at(wn * 32 + j * 8 + g, kk + t)];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            int col = n0 + wn * 32 + j * 8 + 2 * t + c;
+            if (col >= N) continue;
+            double *cp = C + (int64_t)col * ldc;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int row = m0 + wm * 32 + i * 8 + g;
+                if (row < M) {
+                    double v = alpha * acc[i][j][c];
+                    if (beta != 0.0) v += beta * cp[row];
+                    cp[row] = v;
+                }
+            }
+        }
+}
+
+template <bool TA, bool TB>
+static cudaError_t launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const double *A, int64_t lda,
+                          const double *B, int64_t ldb, double beta, double *C, int64_t ldc) {
+    // small problems: more, smaller CTAs
+    int64_t big_ctas = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    if (big_ctas < 64) {
+        dim3 grid((unsigned)((M + SBM - 1) / SBM), (unsigned)((N + SBN - 1) / SBN));
+        dgemm_dmma_small_kernel<TA, TB><<<grid, STHREADS, 0, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta,
+                                                                    C, ldc);
+        return cudaGetLastError();
+    }
+    // 16-byte cp.async needs even contiguous extents, even leading dims and 16B-aligned bases
+    bool vec = (lda % 2 == 0) && (ldb % 2 == 0) && (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0) &&
+               ((TA ? K : M) % 2 == 0) && ((TB ? N : K) % 2 == 0);
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
+    constexpr int smem = smem_bytes<TA, TB>();
+    cudaError_t e;
+    if (vec) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            e = cudaFuncSetAttribute(dgemm_dmma_kernel<TA, TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        dgemm_dmma_kernel<TA, TB, true><<<grid, THREADS, smem, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta,
+                                                                      C, ldc);
+    } else {
+        static bool attr_done = false;
+        if (!attr_done) {
+            e = cudaFuncSetAttribute(dgemm_dmma_kernel<TA, TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        dgemm_dmma_kernel<TA, TB, false><<<grid, THREADS, smem, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb,
+                                                                       beta, C, ldc);
+    }
+    return cudaGetLastError();
+}
+}  // namespace d64
+
+cudaError_t gemm_f64(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
+                     int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc) {
+    if (M <= 0 || N <= 0) return cudaSuccess;
+    if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return cudaErrorInvalidValue;
+    if (!ta && !tb) return d64::launch<false, false>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (!ta && tb) return d64::launch<false, true>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (ta && !tb) return d64::launch<true, false>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    return d64::launch<true, true>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
+// ==================================================================================================
+// FP32 SIMT kernel (128x128x16, 8x8 per thread).  Shared tiles are always [k][m] / [k][n].
+// ==================================================================================================
+namespace s32 {
+constexpr int BM = 128, BN = 128, BK = 16, THREADS = 256, PAD = 4, STAGES = 3;
+constexpr int STRIDE = BM + PAD;
+constexpr int TILE = BK * STRIDE;
+
+// KMAJOR: element (r,k) at g[k + r*ld]  -> 4-byte copies (transposing scatter)
+// else:   element (r,k) at g[r + k*ld]  -> 16-byte copies when VEC
+template <bool KMAJOR, bool VEC>
+__device__ __forceinline__ void load_tile(float *s, const float *g, int64_t ld, int r0, int k0, int Rtot, int Ktot,
+                                          int tid) {
+    if (!KMAJOR && VEC) {
+#pragma unroll
+        for (int i = 0; i < (BM * BK / 4) / THREADS; ++i) {
+            int c = tid + i * THREADS;
+            int k = c / (BM / 4), rc = (c % (BM / 4)) * 4;
+            bool p = (r0 + rc < Rtot) && (k0 + k < Ktot);
+            const float *src = p ? g + (int64_t)(r0 + rc) + (int64_t)(k0 + k) * ld : g;
+            cp_async_16(s + k * STRIDE + rc, src, p);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < (BM * BK) / THREADS; ++i) {
+            int c = tid + i * THREADS;
+            int r, k;
+            if (KMAJOR) { r = c / BK; k = c % BK; } else { k = c / BM; r = c % BM; }
+            bool p = (r0 + r < Rtot) && (k0 + k < Ktot);
+            const float *src = p ? (KMAJOR ? g + (int64_t)(k0 + k) + (int64_t)(r0 + r) * ld
+                                           : g + (int64_t)(r0 + r) + (int64_t)(k0 + k) * ld)
+                                 : g;
+            cp_async_4(s + k * STRIDE + r, src, p);
+        }
+    }
+}
+
+template <bool TA, bool TB, bool VEC>
+__global__ void __launch_bounds__(THREADS, 2)
+sgemm_simt_kernel(int M, int N, int K, float alpha, const float *__restrict__ A, int64_t lda,
+                  const float *__restrict__ B, int64_t ldb, float beta, float *__restrict__ C, int64_t ldc) {
+    extern __shared__ __align__(16) float smemf[];
+    float *sA = smemf, *sB = smemf + STAGES * TILE;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;   // thread owns rows tx*4..+3 and 64+tx*4..+3 ; cols ty*4..+3 and 64+ty*4..
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int KT = (K + BK - 1) / BK;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) {
+            load_tile<TA, VEC>(sA + s * TILE, A, lda, m0, s * BK, M, K, tid);
+            load_tile<!TB, VEC>(sB + s * TILE, B, ldb, n0, s * BK, N, K, tid);
+        }
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < KT) {
+                int s = nk % STAGES;
+                load_tile<TA, VEC>(sA + s * TILE, A, lda, m0, nk * BK, M, K, tid);
+                load_tile<!TB, VEC>(sB + s * TILE, B, ldb, n0, nk * BK, N, K, tid);
+            }
+            cp_async_commit();
+        }
+        const float *a_s = sA + (kt % STAGES) * TILE;
+        const float *b_s = sB + (kt % STAGES) * TILE;
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float4 a0 = *reinterpret_cast<const float4 *>(a_s + k * STRIDE + tx * 4);
+            float4 a1 = *reinterpret_cast<const float4 *>(a_s + k * STRIDE + 64 + tx * 4);
+            float4 b0 = *reinterpret_cast<const float4 *>(b_s + k * STRIDE + ty * 4);
+            float4 b1 = *reinterpret_cast<const float4 *>(b_s + k * STRIDE + 64 + ty * 4);
+            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int col = n0 + (j < 4 ? ty * 4 + j : 64 + ty * 4 + (j - 4));
+        if (col >= N) continue;
+        float *cp = C + (int64_t)col * ldc;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int row = m0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
+            if (row < M) {
+                float v = alpha * acc[i][j];
+                if (beta != 0.f) v += beta * cp[row];
+                cp[row] = v;
+            }
+        }
+    }
+}
+
+template <bool TA, bool TB>
+static cudaError_t launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t lda,
+                          const float *B, int64_t ldb, float beta, float *C, int64_t ldc) {
+    bool vec = (lda % 4 == 0) && (ldb % 4 == 0) && (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0) &&
+               (M % 4 == 0) && (N % 4 == 0);
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
+    constexpr int smem = 2 * STAGES * TILE * (int)sizeof(float);
+    cudaError_t e;
+    if (vec) {
+        static bool done = false;
+        if (!done) {
+            e = cudaFuncSetAttribute(sgemm_simt_kernel<TA, TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            done = true;
+        }
+        sgemm_simt_kernel<TA, TB, true><<<grid, THREADS, smem, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta,
+                                                                      C, ldc);
+    } else {
+        static bool done = false;
+        if (!done) {
+            e = cudaFuncSetAttribute(sgemm_simt_kernel<TA, TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            done = true;
+        }
+        sgemm_simt_kernel<TA, TB, false><<<grid, THREADS, smem, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb,
+                                                                       beta, C, ldc);
+    }
+    return cudaGetLastError();
+}
+}  // namespace s32
+
+cudaError_t gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                     int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc) {
+    if (M <= 0 || N <= 0) return cudaSuccess;
+    if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return cudaErrorInvalidValue;
+    if (!ta && !tb) return s32::launch<false, false>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (!ta && tb) return s32::launch<false, true>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (ta && !tb) return s32::launch<true, false>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    return s32::launch<true, true>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
+}  // namespace rdb

@@ -1,0 +1,844 @@
+// Elementwise / reduction / gather-scatter kernels of the replay engine: kernel families (a) and (b) of
+// BASELINE.json's north star.  All of them are HBM-bound streams: coalesced (128-bit where alignment allows),
+// grid sized in multiples of the SM count, two-pass deterministic reductions (per-block partial sums with
+// warp shuffles, then one finishing block) instead of atomics wherever the access pattern is known.
+//
+// Compiled with -fmad=false: ForwardDiff's Dual arithmetic on the CPU is not FMA-contracted, and parity with the
+// reference's partials (e.g. tanh' = 1 - t*t) is checked to 1e-12 of max|.|.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "kernels.h"
+
+namespace rdb {
+
+constexpr int kSMs = 148;
+constexpr int kThreads = 256;
+
+static inline int grid_for(int64_t n, int per_thread = 1) {
+    int64_t b = (n + (int64_t)kThreads * per_thread - 1) / ((int64_t)kThreads * per_thread);
+    int64_t cap = (int64_t)kSMs * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ------------------------------------------------------------------------------------ block reduction
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double block_sum(double v) {   // result valid in thread 0
+    __shared__ double ws[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) ws[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        v = lane < nw ? ws[lane] : 0.0;
+        v = warp_sum(v);
+    }
+    return v;
+}
+
+template <typename T> struct Vec;
+template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
+template <> struct Vec<float> { using type = float4; static constexpr int N = 4; };
+template <typename T> __device__ __forceinline__ void vec_unpack(const typename Vec<T>::type &v, T *o);
+template <> __device__ __forceinline__ void vec_unpack<double>(const double2 &v, double *o) { o[0] = v.x; o[1] = v.y; }
+template <> __device__ __forceinline__ void vec_unpack<float>(const float4 &v, float *o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+template <typename T> __device__ __forceinline__ typename Vec<T>::type vec_pack(const T *o);
+template <> __device__ __forceinline__ double2 vec_pack<double>(const double *o) { return make_double2(o[0], o[1]); }
+template <> __device__ __forceinline__ float4 vec_pack<float>(const float *o) { return make_float4(o[0], o[1], o[2], o[3]); }
+
+static inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
+
+// ------------------------------------------------------------------------------------------------ fill
+template <typename T>
+__global__ void k_fill(T *p, int64_t n, T v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += st) p[i] = v;
+}
+template <typename T>
+cudaError_t launch_fill(cudaStream_t s, T *p, int64_t n, T v) {
+    if (n <= 0) return cudaSuccess;
+    k_fill<T><<<grid_for(n, 4), kThreads, 0, s>>>(p, n, v);
+    return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------- add (+ fused block sums)
+template <typename T, bool VEC, bool REDUCE>
+__global__ void __launch_bounds__(kThreads)
+k_add(T *__restrict__ out, const T *__restrict__ a, const T *__restrict__ b, T sign, int64_t n, double *block_sums) {
+    constexpr int W = Vec<T>::N;
+    using V = typename Vec<T>::type;
+    double local = 0.0;
+    int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    if (VEC) {
+        int64_t nv = n / W;
+        const V *av = reinterpret_cast<const V *>(a), *bv = reinterpret_cast<const V *>(b);
+        V *ov = reinterpret_cast<V *>(out);
+        for (int64_t i = tid; i < nv; i += st) {
+            T x[W], y[W], z[W];
+            vec_unpack<T>(av[i], x);
+            vec_unpack<T>(bv[i], y);
+#pragma unroll
+            for (int j = 0; j < W; ++j) { z[j] = x[j] + sign * y[j]; if (REDUCE) local += (double)z[j]; }
+            ov[i] = vec_pack<T>(z);
+        }
+        for (int64_t i = nv * W + tid; i < n; i += st) {
+            T z = a[i] + sign * b[i];
+            out[i] = z;
+            if (REDUCE) local += (double)z;
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += st) {
+            T z = a[i] + sign * b[i];
+            out[i] = z;
+            if (REDUCE) local += (double)z;
+        }
+    }
+    if (REDUCE) {
+        double s = block_sum(local);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
+    }
+}
+template <typename T>
+cudaError_t launch_add(cudaStream_t s, T *out, const T *a, const T *b, T sign, int64_t n, T *block_sums_) {
+    double *bs = reinterpret_cast<double *>(block_sums_);
+    bool vec = aligned16(out) && aligned16(a) && aligned16(b);
+    int grid = bs ? kReduceBlocks : grid_for(n, Vec<T>::N * 2);
+    if (vec) {
+        if (bs) k_add<T, true, true><<<grid, kThreads, 0, s>>>(out, a, b, sign, n, bs);
+        else k_add<T, true, false><<<grid, kThreads, 0, s>>>(out, a, b, sign, n, bs);
+    } else {
+        if (bs) k_add<T, false, true><<<grid, kThreads, 0, s>>>(out, a, b, sign, n, bs);
+        else k_add<T, false, false><<<grid, kThreads, 0, s>>>(out, a, b, sign, n, bs);
+    }
+    return cudaGetLastError();
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_block_sums(const T *__restrict__ x, int64_t n, double *block_sums) {
+    constexpr int W = Vec<T>::N;
+    using V = typename Vec<T>::type;
+    double local = 0.0;
+    int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    if (VEC) {
+        int64_t nv = n / W;
+        const V *xv = reinterpret_cast<const V *>(x);
+        for (int64_t i = tid; i < nv; i += st) {
+            T e[W];
+            vec_unpack<T>(xv[i], e);
+#pragma unroll
+            for (int j = 0; j < W; ++j) local += (double)e[j];
+        }
+        for (int64_t i = nv * W + tid; i < n; i += st) local += (double)x[i];
+    } else {
+        for (int64_t i = tid; i < n; i += st) local += (double)x[i];
+    }
+    double s = block_sum(local);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
+}
+template <typename T>
+cudaError_t launch_block_sums(cudaStream_t s, const T *x, int64_t n, T *block_sums_) {
+    double *bs = reinterpret_cast<double *>(block_sums_);
+    if (aligned16(x)) k_block_sums<T, true><<<kReduceBlocks, kThreads, 0, s>>>(x, n, bs);
+    else k_block_sums<T, false><<<kReduceBlocks, kThreads, 0, s>>>(x, n, bs);
+    return cudaGetLastError();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) k_finish_sum(const double *block_sums, T *out, double scale) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < kReduceBlocks; i += blockDim.x) v += block_sums[i];
+    v = block_sum(v);
+    if (threadIdx.x == 0) out[0] = (T)(scale * v);
+}
+template <typename T>
+cudaError_t launch_finish_sum(cudaStream_t s, const T *block_sums_, T *out, T scale) {
+    k_finish_sum<T><<<1, 1024, 0, s>>>(reinterpret_cast<const double *>(block_sums_), out, (double)scale);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ axpy
+template <typename T, bool VEC, bool OVERWRITE>
+__global__ void __launch_bounds__(kThreads) k_axpy(T *__restrict__ dst, const T *__restrict__ src, T sign, int64_t n) {
+    constexpr int W = Vec<T>::N;
+    using V = typename Vec<T>::type;
+    int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    if (VEC) {
+        int64_t nv = n / W;
+        const V *sv = reinterpret_cast<const V *>(src);
+        V *dv = reinterpret_cast<V *>(dst);
+        for (int64_t i = tid; i < nv; i += st) {
+            T x[W], y[W];
+            vec_unpack<T>(sv[i], x);
+            if (OVERWRITE) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) y[j] = sign * x[j];
+            } else {
+                vec_unpack<T>(dv[i], y);
+#pragma unroll
+                for (int j = 0; j < W; ++j) y[j] = y[j] + sign * x[j];
+            }
+            dv[i] = vec_pack<T>(y);
+        }
+        for (int64_t i = nv * W + tid; i < n; i += st) dst[i] = OVERWRITE ? sign * src[i] : dst[i] + sign * src[i];
+    } else {
+        for (int64_t i = tid; i < n; i += st) dst[i] = OVERWRITE ? sign * src[i] : dst[i] + sign * src[i];
+    }
+}
+template <typename T>
+cudaError_t launch_axpy(cudaStream_t s, T *dst, const T *src, T sign, int64_t n, bool overwrite) {
+    if (n <= 0) return cudaSuccess;
+    bool vec = aligned16(dst) && aligned16(src);
+    int grid = grid_for(n, Vec<T>::N * 2);
+    if (vec) {
+        if (overwrite) k_axpy<T, true, true><<<grid, kThreads, 0, s>>>(dst, src, sign, n);
+        else k_axpy<T, true, false><<<grid, kThreads, 0, s>>>(dst, src, sign, n);
+    } else {
+        if (overwrite) k_axpy<T, false, true><<<grid, kThreads, 0, s>>>(dst, src, sign, n);
+        else k_axpy<T, false, false><<<grid, kThreads, 0, s>>>(dst, src, sign, n);
+    }
+    return cudaGetLastError();
+}
+
+template <typename T, bool OVERWRITE>
+__global__ void __launch_bounds__(kThreads)
+k_acc_scalar(T *__restrict__ dst, int64_t n, int64_t R, const T *__restrict__ delta, T scale) {
+    int64_t tot = n * R;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) {
+        T d = scale * delta[i / n];
+        dst[i] = OVERWRITE ? d : dst[i] + d;
+    }
+}
+template <typename T>
+cudaError_t launch_acc_scalar(cudaStream_t s, T *dst, int64_t n, int64_t R, const T *delta, T scale, bool overwrite) {
+    if (n * R <= 0) return cudaSuccess;
+    int grid = grid_for(n * R, 4);
+    if (overwrite) k_acc_scalar<T, true><<<grid, kThreads, 0, s>>>(dst, n, R, delta, scale);
+    else k_acc_scalar<T, false><<<grid, kThreads, 0, s>>>(dst, n, R, delta, scale);
+    return cudaGetLastError();
+}
+
+// ======================================================================================================
+// Scalar-expression interpreter: one Dual{N} (or hyper-dual) evaluation per element
+// ======================================================================================================
+template <typename T> struct M;
+template <> struct M<double> {
+    static __device__ __forceinline__ double tanh_(double x) { return tanh(x); }
+    static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+    static __device__ __forceinline__ double log_(double x) { return log(x); }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double sin_(double x) { return sin(x); }
+    static __device__ __forceinline__ double cos_(double x) { return cos(x); }
+    static __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
+    static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+};
+template <> struct M<float> {
+    static __device__ __forceinline__ float tanh_(float x) { return tanhf(x); }
+    static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+    static __device__ __forceinline__ float log_(float x) { return logf(x); }
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float sin_(float x) { return sinf(x); }
+    static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
+    static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
+    static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+};
+
+template <typename T>
+__device__ __forceinline__ T powi(T x, int n) {   // Base.literal_pow: repeated product
+    if (n == 0) return (T)1;
+    bool neg = n < 0;
+    if (neg) n = -n;
+    T r = x;
+    for (int i = 1; i < n; ++i) r = r * x;
+    return neg ? (T)1 / r : r;
+}
+
+template <int N> struct Tri { static constexpr int NH = N * (N + 1) / 2; };
+__device__ __forceinline__ int tri(int p, int q, int N) {   // p <= q packed index
+    return p * N - p * (p - 1) / 2 + (q - p);
+}
+
+template <typename T, int N, int ORDER>
+__device__ __forceinline__ void eval_expr(const int4 *__restrict__ ops, int n_ops, const double *__restrict__ fc,
+                                          const T *x, T &val, T *dout, T *hout) {
+    constexpr int NH = Tri<N>::NH;
+    T V[kMaxExprRegs];
+    T D[kMaxExprRegs][N];
+    T H[ORDER == 2 ? kMaxExprRegs : 1][NH];
+#pragma unroll
+    for (int p = 0; p < N; ++p) {
+        V[p] = x[p];
+#pragma unroll
+        for (int q = 0; q < N; ++q) D[p][q] = (p == q) ? (T)1 : (T)0;
+        if (ORDER == 2) {
+#pragma unroll
+            for (int h = 0; h < NH; ++h) H[p][h] = (T)0;
+        }
+    }
+    int r = N;
+    for (int o = 0; o < n_ops; ++o, ++r) {
+        const int4 op = ops[o];
+        const int code = op.x, a = op.y, b = op.z, imm = op.w;
+        T f0, f1 = (T)0, f2 = (T)0;
+        bool unary = true;
+        switch (code) {
+            case E_CONST: {
+                V[r] = (T)fc[imm];
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = (T)0;
+                if (ORDER == 2) {
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) H[r][h] = (T)0;
+                }
+                unary = false;
+            } break;
+            case E_ARG: {
+                V[r] = V[imm];
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = D[imm][p];
+                if (ORDER == 2) {
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) H[r][h] = H[imm][h];
+                }
+                unary = false;
+            } break;
+            case E_ADD:
+            case E_SUB: {
+                const T s = code == E_ADD ? (T)1 : (T)-1;
+                V[r] = code == E_ADD ? V[a] + V[b] : V[a] - V[b];
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = D[a][p] + s * D[b][p];
+                if (ORDER == 2) {
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) H[r][h] = H[a][h] + s * H[b][h];
+                }
+                unary = false;
+            } break;
+            case E_MUL: {
+                const T va = V[a], vb = V[b];
+                V[r] = va * vb;
+                if (ORDER == 2) {
+#pragma unroll
+                    for (int p = 0; p < N; ++p)
+#pragma unroll
+                        for (int q = p; q < N; ++q)
+                            H[r][tri(p, q, N)] = H[a][tri(p, q, N)] * vb + D[a][p] * D[b][q] + D[a][q] * D[b][p] +
+                                                 va * H[b][tri(p, q, N)];
+                }
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = D[a][p] * vb + va * D[b][p];
+                unary = false;
+            } break;
+            case E_DIV: {
+                const T q0 = V[a] / V[b], ib = (T)1 / V[b];
+                T da[N];
+#pragma unroll
+                for (int p = 0; p < N; ++p) da[p] = (D[a][p] - q0 * D[b][p]) * ib;
+                if (ORDER == 2) {
+#pragma unroll
+                    for (int p = 0; p < N; ++p)
+#pragma unroll
+                        for (int q = p; q < N; ++q)
+                            H[r][tri(p, q, N)] = (H[a][tri(p, q, N)] - da[p] * D[b][q] - da[q] * D[b][p] -
+                                                  q0 * H[b][tri(p, q, N)]) * ib;
+                }
+                V[r] = q0;
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = da[p];
+                unary = false;
+            } break;
+            case E_POW: {
+                const T y = M<T>::pow_(V[a], V[b]);
+                const T fa = V[b] * M<T>::pow_(V[a], V[b] - (T)1);
+                const T fb = y * M<T>::log_(V[a]);
+                V[r] = y;
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = fa * D[a][p] + fb * D[b][p];
+                if (ORDER == 2) {   // second-order pow is rejected at load time
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) H[r][h] = (T)0;
+                }
+                unary = false;
+            } break;
+            case E_MAX:
+            case E_MIN: {
+                const bool pick_a = code == E_MAX ? (V[a] > V[b]) : (V[a] < V[b]);
+                const int s = pick_a ? a : b;
+                V[r] = V[s];
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = D[s][p];
+                if (ORDER == 2) {
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) H[r][h] = H[s][h];
+                }
+                unary = false;
+            } break;
+            case E_NEG: f0 = -V[a]; f1 = (T)-1; f2 = (T)0; break;
+            case E_POWI: {
+                const T xx = V[a];
+                f0 = powi(xx, imm);
+                f1 = imm != 0 ? (T)imm * powi(xx, imm - 1) : (T)0;
+                if (ORDER == 2) f2 = (imm != 0 && imm != 1) ? (T)(imm * (imm - 1)) * powi(xx, imm - 2) : (T)0;
+            } break;
+            case E_TANH: { const T t = M<T>::tanh_(V[a]); f0 = t; f1 = (T)1 - t * t; f2 = (T)-2 * t * f1; } break;
+            case E_EXP: { const T e = M<T>::exp_(V[a]); f0 = e; f1 = e; f2 = e; } break;
+            case E_LOG: { f0 = M<T>::log_(V[a]); f1 = (T)1 / V[a]; f2 = (T)-1 / (V[a] * V[a]); } break;
+            case E_SQRT: { const T s = M<T>::sqrt_(V[a]); f0 = s; f1 = (T)1 / ((T)2 * s); f2 = (T)-1 / ((T)4 * s * V[a]); } break;
+            case E_SIN: { f0 = M<T>::sin_(V[a]); f1 = M<T>::cos_(V[a]); f2 = -f0; } break;
+            case E_COS: { f0 = M<T>::cos_(V[a]); f1 = -M<T>::sin_(V[a]); f2 = -f0; } break;
+            case E_ABS2: { f0 = V[a] * V[a]; f1 = (T)2 * V[a]; f2 = (T)2; } break;
+            case E_ABS: { f0 = M<T>::abs_(V[a]); f1 = V[a] > (T)0 ? (T)1 : (V[a] < (T)0 ? (T)-1 : (T)0); f2 = (T)0; } break;
+            case E_INV: { const T rr = (T)1 / V[a]; f0 = rr; f1 = -rr * rr; f2 = (T)2 * rr * rr * rr; } break;
+            case E_SIGMOID: { const T s = (T)1 / ((T)1 + M<T>::exp_(-V[a])); f0 = s; f1 = s * ((T)1 - s); f2 = f1 * ((T)1 - (T)2 * s); } break;
+            default: f0 = (T)0; break;
+        }
+        if (unary) {
+            if (ORDER == 2) {
+#pragma unroll
+                for (int p = 0; p < N; ++p)
+#pragma unroll
+                    for (int q = p; q < N; ++q)
+                        H[r][tri(p, q, N)] = f2 * D[a][p] * D[a][q] + f1 * H[a][tri(p, q, N)];
+            }
+            V[r] = f0;
+#pragma unroll
+            for (int p = 0; p < N; ++p) D[r][p] = f1 * D[a][p];
+        }
+    }
+    val = V[r - 1];
+#pragma unroll
+    for (int p = 0; p < N; ++p) dout[p] = D[r - 1][p];
+    if (ORDER == 2) {
+#pragma unroll
+        for (int h = 0; h < NH; ++h) hout[h] = H[r - 1][h];
+    }
+}
+
+template <int N>
+struct ExprDev {
+    const void *arg[N];
+    int64_t stride[N][kMaxDims];
+    int same[N];
+    void *partial[N];
+    void *second[Tri<N>::NH];
+    int64_t dims[kMaxDims];
+    int64_t n;
+    void *out;
+    const int4 *ops;
+    const double *fconst;
+    double *block_sums;
+    int n_ops;
+};
+
+template <typename T, int N, int ORDER, bool REDUCE>
+__global__ void __launch_bounds__(kThreads) k_expr_forward(const ExprDev<N> P) {
+    __shared__ int4 s_ops[kMaxExprRegs];
+    for (int i = threadIdx.x; i < P.n_ops; i += blockDim.x) s_ops[i] = P.ops[i];
+    __syncthreads();
+    double local = 0.0;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < P.n; i += st) {
+        T x[N];
+        bool need_idx = false;
+#pragma unroll
+        for (int p = 0; p < N; ++p) need_idx |= !P.same[p];
+        int64_t idx[kMaxDims] = {0, 0, 0, 0};
+        if (need_idx) {
+            int64_t rem = i;
+#pragma unroll
+            for (int d = 0; d < kMaxDims; ++d) {
+                if (P.n <= 0x7fffffffLL) { unsigned r32 = (unsigned)rem, dd = (unsigned)P.dims[d]; idx[d] = r32 % dd; rem = r32 / dd; }
+                else { idx[d] = rem % P.dims[d]; rem = rem / P.dims[d]; }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < N; ++p) {
+            int64_t off = i;
+            if (!P.same[p]) {
+                off = 0;
+#pragma unroll
+                for (int d = 0; d < kMaxDims; ++d) off += idx[d] * P.stride[p][d];
+            }
+            x[p] = reinterpret_cast<const T *>(P.arg[p])[off];
+        }
+        T val, dd[N], hh[Tri<N>::NH];
+        eval_expr<T, N, ORDER>(s_ops, P.n_ops, P.fconst, x, val, dd, hh);
+        reinterpret_cast<T *>(P.out)[i] = val;
+#pragma unroll
+        for (int p = 0; p < N; ++p)
+            if (P.partial[p]) reinterpret_cast<T *>(P.partial[p])[i] = dd[p];
+        if (ORDER == 2) {
+#pragma unroll
+            for (int h = 0; h < Tri<N>::NH; ++h)
+                if (P.second[h]) reinterpret_cast<T *>(P.second[h])[i] = hh[h];
+        }
+        if (REDUCE) local += (double)val;
+    }
+    if (REDUCE) {
+        double s = block_sum(local);
+        if (threadIdx.x == 0) P.block_sums[blockIdx.x] = s;
+    }
+}
+
+template <typename T, int N>
+static cudaError_t expr_forward_n(cudaStream_t s, const ExprParams &p) {
+    ExprDev<N> d;
+    for (int i = 0; i < N; ++i) {
+        d.arg[i] = p.arg[i].ptr;
+        d.same[i] = p.arg[i].same;
+        d.partial[i] = p.partial[i];
+        for (int k = 0; k < kMaxDims; ++k) d.stride[i][k] = p.arg[i].stride[k];
+    }
+    for (int h = 0; h < Tri<N>::NH; ++h) d.second[h] = p.order == 2 ? p.second[h] : nullptr;
+    for (int k = 0; k < kMaxDims; ++k) d.dims[k] = p.dims[k];
+    d.n = p.n; d.out = p.out; d.ops = reinterpret_cast<const int4 *>(p.ops); d.fconst = p.fconst;
+    d.block_sums = reinterpret_cast<double *>(p.block_sums); d.n_ops = p.n_ops;
+    int grid = p.reduce ? kReduceBlocks : grid_for(p.n, 2);
+    if (p.order == 2) {
+        if (p.reduce) k_expr_forward<T, N, 2, true><<<grid, kThreads, 0, s>>>(d);
+        else k_expr_forward<T, N, 2, false><<<grid, kThreads, 0, s>>>(d);
+    } else {
+        if (p.reduce) k_expr_forward<T, N, 1, true><<<grid, kThreads, 0, s>>>(d);
+        else k_expr_forward<T, N, 1, false><<<grid, kThreads, 0, s>>>(d);
+    }
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_expr_forward(cudaStream_t s, const ExprParams &p) {
+    if (p.n <= 0) return cudaSuccess;
+    switch (p.n_args) {
+        case 1: return expr_forward_n<T, 1>(s, p);
+        case 2: return expr_forward_n<T, 2>(s, p);
+        case 3: return expr_forward_n<T, 3>(s, p);
+        case 4: return expr_forward_n<T, 4>(s, p);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------- reverse: delta * partial accumulate
+template <typename T, bool OVERWRITE>
+__global__ void __launch_bounds__(kThreads)
+k_mul_acc(T *__restrict__ dst, const T *__restrict__ delta, const T *__restrict__ partial, int64_t n, int64_t R) {
+    int64_t tot = n * R;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    if (R == 1) {
+        for (; i < tot; i += st) {
+            T v = delta[i] * partial[i];
+            dst[i] = OVERWRITE ? v : dst[i] + v;
+        }
+    } else {
+        for (; i < tot; i += st) {
+            T v = delta[i] * partial[i % n];
+            dst[i] = OVERWRITE ? v : dst[i] + v;
+        }
+    }
+}
+template <typename T>
+cudaError_t launch_mul_acc(cudaStream_t s, T *dst, const T *delta, const T *partial, int64_t n, int64_t R, bool overwrite) {
+    if (n * R <= 0) return cudaSuccess;
+    int grid = grid_for(n * R, 4);
+    if (overwrite) k_mul_acc<T, true><<<grid, kThreads, 0, s>>>(dst, delta, partial, n, R);
+    else k_mul_acc<T, false><<<grid, kThreads, 0, s>>>(dst, delta, partial, n, R);
+    return cudaGetLastError();
+}
+
+// column-vector clamp: pass 1 -> scratch[(c*R + r)*d0 + i] = sum over the chunk's columns
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_colvec_partial(double *__restrict__ scratch, const T *__restrict__ delta, const T *__restrict__ partial, int64_t d0,
+                 int64_t d1, int64_t R, int64_t cols_per_chunk) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t c = blockIdx.y, r = blockIdx.z;
+    if (i >= d0) return;
+    int64_t j0 = c * cols_per_chunk, j1 = j0 + cols_per_chunk;
+    if (j1 > d1) j1 = d1;
+    const T *dl = delta + r * d0 * d1;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int64_t j = j0; j < j1; ++j) acc += (double)(dl[i + j * d0] * partial[i + j * d0]);
+    scratch[(c * R + r) * d0 + i] = acc;
+}
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_colvec_finish(T *__restrict__ dst, const double *__restrict__ scratch, int64_t d0, int64_t R, int64_t chunks) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= d0 * R) return;
+    double acc = 0.0;
+    for (int64_t c = 0; c < chunks; ++c) acc += scratch[c * R * d0 + i];
+    dst[i] = dst[i] + (T)acc;
+}
+template <typename T>
+cudaError_t launch_mul_acc_colvec(cudaStream_t s, T *dst, const T *delta, const T *partial, int64_t d0, int64_t d1, int64_t R,
+                                  T *scratch_, int64_t scratch_elems) {
+    if (d0 * d1 * R <= 0) return cudaSuccess;
+    double *scratch = reinterpret_cast<double *>(scratch_);
+    int64_t bx = (d0 + kThreads - 1) / kThreads;
+    // enough column chunks to fill the machine (~8 CTAs per SM), bounded by the scratch size
+    int64_t want = (kSMs * 8 + bx * R - 1) / (bx * R);
+    if (want < 1) want = 1;
+    if (want > d1) want = d1;
+    int64_t maxc = scratch_elems / (d0 * R);
+    if (maxc < 1) return cudaErrorMemoryAllocation;
+    if (want > maxc) want = maxc;
+    if (want > 65535) want = 65535;
+    int64_t cols = (d1 + want - 1) / want;
+    int64_t chunks = (d1 + cols - 1) / cols;
+    if (R > 65535) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)bx, (unsigned)chunks, (unsigned)R);
+    k_colvec_partial<T><<<grid, kThreads, 0, s>>>(scratch, delta, partial, d0, d1, R, cols);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_colvec_finish<T><<<(unsigned)((d0 * R + kThreads - 1) / kThreads), kThreads, 0, s>>>(dst, scratch, d0, R, chunks);
+    return cudaGetLastError();
+}
+
+struct GenericIdx {
+    int64_t dims[kMaxDims];
+    int64_t dst_stride[kMaxDims];
+};
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_mul_acc_generic(T *dst, int64_t dst_n, GenericIdx g, const T *__restrict__ delta, const T *__restrict__ partial,
+                  int64_t n, int64_t R) {
+    int64_t tot = n * R;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) {
+        int64_t r = i / n, e = i - r * n, rem = e, off = 0;
+#pragma unroll
+        for (int d = 0; d < kMaxDims; ++d) {
+            off += (rem % g.dims[d]) * g.dst_stride[d];
+            rem /= g.dims[d];
+        }
+        atomicAdd(dst + off + r * dst_n, delta[i] * partial[e]);
+    }
+}
+template <typename T>
+cudaError_t launch_mul_acc_generic(cudaStream_t s, T *dst, int64_t dst_n, const int64_t *dst_stride, const T *delta,
+                                   const T *partial, const int64_t *dims, int64_t n, int64_t R) {
+    if (n * R <= 0) return cudaSuccess;
+    GenericIdx g;
+    for (int d = 0; d < kMaxDims; ++d) { g.dims[d] = dims[d]; g.dst_stride[d] = dst_stride[d]; }
+    k_mul_acc_generic<T><<<grid_for(n * R, 2), kThreads, 0, s>>>(dst, dst_n, g, delta, partial, n, R);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ gather / scatter
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_gather_cols(T *__restrict__ out, const T *__restrict__ src, int64_t src_n, const int64_t *__restrict__ map, int64_t n, int64_t K) {
+    int64_t tot = n * K;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) {
+        int64_t c = i / n, k = i - c * n;
+        out[i] = src[map[k] + c * src_n];
+    }
+}
+template <typename T>
+cudaError_t launch_gather_cols(cudaStream_t s, T *out, const T *src, int64_t src_n, const int64_t *map, int64_t n, int64_t K) {
+    if (n * K <= 0) return cudaSuccess;
+    k_gather_cols<T><<<grid_for(n * K, 2), kThreads, 0, s>>>(out, src, src_n, map, n, K);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_gather(cudaStream_t s, T *out, const T *src, const int64_t *map, int64_t n) {
+    return launch_gather_cols<T>(s, out, src, 0, map, n, 1);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_scatter_add(T *dst, int64_t dst_n, const int64_t *__restrict__ map, const T *__restrict__ src, int64_t n, int64_t R) {
+    int64_t tot = n * R;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) {
+        int64_t r = i / n, k = i - r * n;
+        atomicAdd(dst + map[k] + r * dst_n, src[i]);
+    }
+}
+template <typename T>
+cudaError_t launch_scatter_add(cudaStream_t s, T *dst, int64_t dst_n, const int64_t *map, const T *src, int64_t n, int64_t R) {
+    if (n * R <= 0) return cudaSuccess;
+    k_scatter_add<T><<<grid_for(n * R, 2), kThreads, 0, s>>>(dst, dst_n, map, src, n, R);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ seeding / extraction
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_seed_onehot(T *der, int64_t m, int64_t R, int64_t i0) {
+    int64_t tot = m * R;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) {
+        int64_t r = i / m, e = i - r * m;
+        der[i] = (e == i0 + r) ? (T)1 : (T)0;
+    }
+}
+template <typename T>
+cudaError_t launch_seed_onehot(cudaStream_t s, T *der, int64_t m, int64_t R, int64_t i0) {
+    if (m * R <= 0) return cudaSuccess;
+    k_seed_onehot<T><<<grid_for(m * R, 4), kThreads, 0, s>>>(der, m, R, i0);
+    return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_seed_tangent(cudaStream_t s, T *tv, int64_t n, int64_t K, int64_t c0) {
+    return launch_seed_onehot<T>(s, tv, n, K, c0);
+}
+
+// result[r + j*ld] = xder[j + r*n] : 32x32 shared-memory transpose, both sides coalesced
+template <typename T>
+__global__ void __launch_bounds__(256) k_rows_out(T *__restrict__ result, int64_t ld, const T *__restrict__ xder, int64_t n, int64_t R) {
+    __shared__ T tile[32][33];
+    int64_t j0 = blockIdx.x * 32LL, r0 = blockIdx.y * 32LL;
+    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        int64_t j = j0 + tx, r = r0 + ty + k;
+        if (j < n && r < R) tile[ty + k][tx] = xder[j + r * n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        int64_t r = r0 + tx, j = j0 + ty + k;
+        if (j < n && r < R) result[r + j * ld] = tile[tx][ty + k];
+    }
+}
+template <typename T>
+cudaError_t launch_rows_out(cudaStream_t s, T *result, int64_t ld, const T *xder, int64_t n, int64_t R) {
+    if (n * R <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((R + 31) / 32));
+    k_rows_out<T><<<grid, 256, 0, s>>>(result, ld, xder, n, R);
+    return cudaGetLastError();
+}
+
+// ======================================================================================================
+// forward-over-reverse tangent sweeps (hessian!)
+// ======================================================================================================
+template <typename T, int N>
+struct TanArgs {
+    const T *partial[N];
+    const T *tv[N];
+    const T *second[N];
+};
+template <typename T, int N>
+__global__ void __launch_bounds__(kThreads) k_tangent_forward(T *__restrict__ out, TanArgs<T, N> a, int64_t n, int64_t K) {
+    int64_t tot = n * K;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) {
+        int64_t e = i % n;
+        T acc = (T)0;
+#pragma unroll
+        for (int p = 0; p < N; ++p) acc += a.partial[p][e] * a.tv[p][i];
+        out[i] = acc;
+    }
+}
+template <typename T>
+cudaError_t launch_tangent_forward(cudaStream_t s, T *tv_out, int n_args, const T *const *partial, const T *const *tv_in, int64_t n, int64_t K) {
+    if (n * K <= 0) return cudaSuccess;
+    int grid = grid_for(n * K, 2);
+#define RDB_TF(NN)                                                                     \
+    case NN: {                                                                         \
+        TanArgs<T, NN> a;                                                              \
+        for (int p = 0; p < NN; ++p) { a.partial[p] = partial[p]; a.tv[p] = tv_in[p]; a.second[p] = nullptr; } \
+        k_tangent_forward<T, NN><<<grid, kThreads, 0, s>>>(tv_out, a, n, K);           \
+    } break;
+    switch (n_args) { RDB_TF(1) RDB_TF(2) RDB_TF(3) RDB_TF(4) default: return cudaErrorInvalidValue; }
+#undef RDB_TF
+    return cudaGetLastError();
+}
+
+template <typename T, int N, bool OVERWRITE>
+__global__ void __launch_bounds__(kThreads)
+k_tangent_reverse(T *__restrict__ td, const T *__restrict__ dt, const T *__restrict__ delta, const T *__restrict__ partial_p,
+                  TanArgs<T, N> a, int64_t n, int64_t K) {
+    int64_t tot = n * K;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) {
+        int64_t e = i % n;
+        T acc = (T)0;
+#pragma unroll
+        for (int q = 0; q < N; ++q) acc += a.second[q][e] * a.tv[q][i];
+        T v = dt[i] * partial_p[e] + delta[e] * acc;
+        td[i] = OVERWRITE ? v : td[i] + v;
+    }
+}
+template <typename T>
+cudaError_t launch_tangent_reverse(cudaStream_t s, T *td_p, const T *dt, const T *delta, const T *partial_p, int n_args,
+                                   const T *const *second_pq, const T *const *tv_in, int64_t n, int64_t K, bool overwrite) {
+    if (n * K <= 0) return cudaSuccess;
+    int grid = grid_for(n * K, 2);
+#define RDB_TR(NN)                                                                                      \
+    case NN: {                                                                                          \
+        TanArgs<T, NN> a;                                                                               \
+        for (int q = 0; q < NN; ++q) { a.partial[q] = nullptr; a.tv[q] = tv_in[q]; a.second[q] = second_pq[q]; } \
+        if (overwrite) k_tangent_reverse<T, NN, true><<<grid, kThreads, 0, s>>>(td_p, dt, delta, partial_p, a, n, K); \
+        else k_tangent_reverse<T, NN, false><<<grid, kThreads, 0, s>>>(td_p, dt, delta, partial_p, a, n, K);          \
+    } break;
+    switch (n_args) { RDB_TR(1) RDB_TR(2) RDB_TR(3) RDB_TR(4) default: return cudaErrorInvalidValue; }
+#undef RDB_TR
+    return cudaGetLastError();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_colsum(T *__restrict__ out, const T *__restrict__ x, int64_t n, int64_t K, double scale) {
+    int64_t k = blockIdx.x;
+    if (k >= K) return;
+    double local = 0.0;
+    const T *col = x + k * n;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) local += (double)col[i];
+    double s = block_sum(local);
+    if (threadIdx.x == 0) out[k] = (T)(scale * s);
+}
+template <typename T>
+cudaError_t launch_colsum(cudaStream_t s, T *out, const T *x, int64_t n, int64_t K, T scale) {
+    if (K <= 0) return cudaSuccess;
+    k_colsum<T><<<(unsigned)K, kThreads, 0, s>>>(out, x, n, K, (double)scale);
+    return cudaGetLastError();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_copy2d(T *__restrict__ dst, int64_t ldd, const T *__restrict__ src, int64_t lds, int64_t n, int64_t K) {
+    int64_t tot = n * K;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) {
+        int64_t k = i / n, e = i - k * n;
+        dst[e + k * ldd] = src[e + k * lds];
+    }
+}
+template <typename T>
+cudaError_t launch_copy2d(cudaStream_t s, T *dst, int64_t ldd, const T *src, int64_t lds, int64_t n, int64_t K) {
+    if (n * K <= 0) return cudaSuccess;
+    k_copy2d<T><<<grid_for(n * K, 4), kThreads, 0, s>>>(dst, ldd, src, lds, n, K);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ explicit instantiation
+#define RDB_INST(T)                                                                                                       \
+    template cudaError_t launch_fill<T>(cudaStream_t, T *, int64_t, T);                                                   \
+    template cudaError_t launch_add<T>(cudaStream_t, T *, const T *, const T *, T, int64_t, T *);                         \
+    template cudaError_t launch_block_sums<T>(cudaStream_t, const T *, int64_t, T *);                                     \
+    template cudaError_t launch_finish_sum<T>(cudaStream_t, const T *, T *, T);                                           \
+    template cudaError_t launch_axpy<T>(cudaStream_t, T *, const T *, T, int64_t, bool);                                  \
+    template cudaError_t launch_acc_scalar<T>(cudaStream_t, T *, int64_t, int64_t, const T *, T, bool);                   \
+    template cudaError_t launch_expr_forward<T>(cudaStream_t, const ExprParams &);                                        \
+    template cudaError_t launch_mul_acc<T>(cudaStream_t, T *, const T *, const T *, int64_t, int64_t, bool);              \
+    template cudaError_t launch_mul_acc_colvec<T>(cudaStream_t, T *, const T *, const T *, int64_t, int64_t, int64_t, T *, int64_t); \
+    template cudaError_t launch_mul_acc_generic<T>(cudaStream_t, T *, int64_t, const int64_t *, const T *, const T *, const int64_t *, int64_t, int64_t); \
+    template cudaError_t launch_gather<T>(cudaStream_t, T *, const T *, const int64_t *, int64_t);                        \
+    template cudaError_t launch_scatter_add<T>(cudaStream_t, T *, int64_t, const int64_t *, const T *, int64_t, int64_t); \
+    template cudaError_t launch_seed_onehot<T>(cudaStream_t, T *, int64_t, int64_t, int64_t);                             \
+    template cudaError_t launch_rows_out<T>(cudaStream_t, T *, int64_t, const T *, int64_t, int64_t);                     \
+    template cudaError_t launch_tangent_forward<T>(cudaStream_t, T *, int, const T *const *, const T *const *, int64_t, int64_t); \
+    template cudaError_t launch_tangent_reverse<T>(cudaStream_t, T *, const T *, const T *, const T *, int, const T *const *, const T *const *, int64_t, int64_t, bool); \
+    template cudaError_t launch_gather_cols<T>(cudaStream_t, T *, const T *, int64_t, const int64_t *, int64_t, int64_t); \
+    template cudaError_t launch_seed_tangent<T>(cudaStream_t, T *, int64_t, int64_t, int64_t);                            \
+    template cudaError_t launch_colsum<T>(cudaStream_t, T *, const T *, int64_t, int64_t, T);                             \
+    template cudaError_t launch_copy2d<T>(cudaStream_t, T *, int64_t, const T *, int64_t, int64_t, int64_t);
+RDB_INST(double)
+RDB_INST(float)
+
+}  // namespace rdb

@@ -1,0 +1,86 @@
+// Kernel launchers of the replay engine (device code in gemm.cu / kernels.cu).  Everything is
+// asynchronous on the given stream and returns the launch status.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "program.h"
+
+namespace rdb {
+
+// ---- (c) dense contractions -------------------------------------------------------------------------
+cudaError_t gemm_f64(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
+                     int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc);
+cudaError_t gemm_f32(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                     int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc);
+
+// ---- (a)/(b) elementwise sweeps ---------------------------------------------------------------------
+constexpr int kReduceBlocks = 1184;   // 148 SMs x 8 resident CTAs: partial-sum slots of the two-pass reductions
+
+// Broadcast-aware argument of an elementwise instruction (bound trick of propagation.jl:25-27 expressed as
+// strides: a size-1 dimension gets stride 0).
+struct ExprArg {
+    const void *ptr;
+    int64_t stride[kMaxDims];
+    int32_t same;   // 1: same shape as the output (offset == linear index)
+    int32_t pad;
+};
+
+struct ExprParams {
+    int32_t n_args, n_ops;
+    int32_t order;                 // 1: value + first partials; 2: also second partials (Hessian)
+    int32_t reduce;                // 1: also emit per-block partial sums of the output (fused `sum`)
+    int64_t n;                     // output elements
+    int64_t dims[kMaxDims];        // output dims
+    ExprArg arg[kMaxArgs];
+    void *out;
+    void *partial[kMaxArgs];       // may be NULL (untracked argument)
+    void *second[kMaxArgs * (kMaxArgs + 1) / 2];   // (p<=q) packed, order 2 only
+    const int32_t *ops;            // device, 4 x int32 per op
+    const double *fconst;          // device
+    void *block_sums;              // kReduceBlocks partial sums when reduce == 1
+};
+
+template <typename T> cudaError_t launch_fill(cudaStream_t, T *p, int64_t n, T v);
+// out = a + sign*b   (array +/-: arithmetic.jl:7-12,69-79); if block_sums != NULL also writes per-block sums
+template <typename T> cudaError_t launch_add(cudaStream_t, T *out, const T *a, const T *b, T sign, int64_t n, T *block_sums);
+// block_sums <- per-block sums of x  (sum / mean forward, reductions.jl:23-27,81-85)
+template <typename T> cudaError_t launch_block_sums(cudaStream_t, const T *x, int64_t n, T *block_sums);
+// out[0] = scale * sum(block_sums[0..kReduceBlocks))
+template <typename T> cudaError_t launch_finish_sum(cudaStream_t, const T *block_sums, T *out, T scale);
+// dst (+)= sign*src over n elements (increment_deriv!/decrement_deriv!, propagation.jl:33-73)
+template <typename T> cudaError_t launch_axpy(cudaStream_t, T *dst, const T *src, T sign, int64_t n, bool overwrite);
+// dst[i + r*n] (+)= scale*delta[r]   (sum/mean reverse: scalar adjoint broadcast, reductions.jl:15-21,73-79)
+template <typename T> cudaError_t launch_acc_scalar(cudaStream_t, T *dst, int64_t n, int64_t R, const T *delta, T scale, bool overwrite);
+// elementwise instruction forward (broadcast.jl:196-204 ; elementwise.jl:323-343)
+template <typename T> cudaError_t launch_expr_forward(cudaStream_t, const ExprParams &p);
+// dst[i + r*n] (+)= delta[i + r*n]*partial[i]   (diffresult_increment_deriv!, propagation.jl:82-88)
+template <typename T> cudaError_t launch_mul_acc(cudaStream_t, T *dst, const T *delta, const T *partial, int64_t n, int64_t R, bool overwrite);
+// clamped accumulate into a column vector: dst[i + r*d0] += sum_j delta[i + j*d0 + r*d0*d1]*partial[i + j*d0]
+// (propagation.jl:90-96 with bound (d0,1)); scratch holds d0*R*chunks partial sums
+template <typename T> cudaError_t launch_mul_acc_colvec(cudaStream_t, T *dst, const T *delta, const T *partial, int64_t d0, int64_t d1, int64_t R, T *scratch, int64_t scratch_elems);
+// generic clamped accumulate (any broadcast pattern) with atomics
+template <typename T> cudaError_t launch_mul_acc_generic(cudaStream_t, T *dst, int64_t dst_n, const int64_t *dst_stride, const T *delta, const T *partial, const int64_t *dims, int64_t n, int64_t R);
+// out[k] = src[map[k]]      (pull_value! of IDX operands, getindex forward: tracked.jl:178-181,331-340)
+template <typename T> cudaError_t launch_gather(cudaStream_t, T *out, const T *src, const int64_t *map, int64_t n);
+// dst[map[k] + r*dst_n] += src[k + r*n]   (scatter-add: propagation.jl:45-50, tracked.jl:318-329)
+template <typename T> cudaError_t launch_scatter_add(cudaStream_t, T *dst, int64_t dst_n, const int64_t *map, const T *src, int64_t n, int64_t R);
+// der[i + r*m] = (i == i0 + r)      (seed!(output, i) for a block of R rows, api/utils.jl:50)
+template <typename T> cudaError_t launch_seed_onehot(cudaStream_t, T *der, int64_t m, int64_t R, int64_t i0);
+// result[r + j*ld] = xder[j + r*n]  (result_matrix[i, j] = input_deriv[j], api/utils.jl:52-54, for R rows at once)
+template <typename T> cudaError_t launch_rows_out(cudaStream_t, T *result, int64_t ld, const T *xder, int64_t n, int64_t R);
+
+// ---- forward-over-reverse (Hessian) tangent sweeps ---------------------------------------------------
+// tv_out[i + k*n] = sum_p partial_p[i]*tv_p[i + k*n]
+template <typename T> cudaError_t launch_tangent_forward(cudaStream_t, T *tv_out, int n_args, const T *const *partial, const T *const *tv_in, int64_t n, int64_t K);
+// td_p[i+k*n] (+)= dt[i+k*n]*partial_p[i] + delta[i]*sum_q second_pq[i]*tv_q[i+k*n]
+template <typename T> cudaError_t launch_tangent_reverse(cudaStream_t, T *td_p, const T *dt, const T *delta, const T *partial_p, int n_args, const T *const *second_pq, const T *const *tv_in, int64_t n, int64_t K, bool overwrite);
+// rows gather/scatter for getindex under tangents: out[k + c*n] = src[map[k] + c*src_n]
+template <typename T> cudaError_t launch_gather_cols(cudaStream_t, T *out, const T *src, int64_t src_n, const int64_t *map, int64_t n, int64_t K);
+// tv[i + k*n] = (i == c0 + k)
+template <typename T> cudaError_t launch_seed_tangent(cudaStream_t, T *tv, int64_t n, int64_t K, int64_t c0);
+// out[k] = sum_i x[i + k*n]   (column sums; tangent of sum)
+template <typename T> cudaError_t launch_colsum(cudaStream_t, T *out, const T *x, int64_t n, int64_t K, T scale);
+// 2-D strided copy: dst[i + k*ldd] = src[i + k*lds]
+template <typename T> cudaError_t launch_copy2d(cudaStream_t, T *dst, int64_t ldd, const T *src, int64_t lds, int64_t n, int64_t K);
+
+}  // namespace rdb

@@ -1,0 +1,262 @@
+"""ctypes binding of ``librdb200.so`` (declared in ``include/rdb200.h``).
+
+This is the Python equivalent of the ``ccall`` layer in ``julia/ReverseDiffB200.jl``.  The library
+is built in-tree by ``__graft_entry__.build()`` (``nvcc -gencode arch=compute_100a,code=sm_100a``).
+There is no fallback: a missing library or a missing CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "librdb200.so")
+
+RDB_F64, RDB_F32 = 0, 1
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _Options(C.Structure):
+    _fields_ = [("fuse_elementwise", C.c_int32), ("seed_block", C.c_int32), ("use_graph", C.c_int32),
+                ("profile", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the B200 engine has no CPU fallback)")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i32, i64, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    sig = {
+        "rdb_version": (C.c_char_p, []),
+        "rdb_last_error": (C.c_char_p, []),
+        "rdb_ctx_create": (vp, [i32]),
+        "rdb_ctx_destroy": (None, [vp]),
+        "rdb_ctx_set_stream": (i32, [vp, vp]),
+        "rdb_ctx_synchronize": (i32, [vp]),
+        "rdb_tape_load": (vp, [vp, vp, C.c_size_t, C.POINTER(_Options)]),
+        "rdb_tape_destroy": (None, [vp]),
+        "rdb_tape_set_input": (i32, [vp, i32, vp, i32]),
+        "rdb_forward": (i32, [vp]),
+        "rdb_reverse_scalar_seed": (i32, [vp]),
+        "rdb_gradient": (i32, [vp, C.POINTER(vp), i32, vp]),
+        "rdb_jacobian": (i32, [vp, i32, i64, i64, vp, i64, i32, vp]),
+        "rdb_hessian": (i32, [vp, i64, i64, vp, i64, i32, vp, vp]),
+        "rdb_get_value": (i32, [vp, i32, vp]),
+        "rdb_get_deriv": (i32, [vp, i32, vp]),
+        "rdb_buffer_size": (i64, [vp, i32]),
+        "rdb_tape_stats": (i32, [vp, C.c_char_p, C.c_size_t]),
+        "rdb_tape_launch_count": (i64, [vp]),
+        "rdb_gemm": (i32, [vp, i32, i32, i32, i64, i64, i64, f64, vp, i64, vp, i64, f64, vp, i64]),
+        "rdb_add_sum": (i32, [vp, i32, i64, vp, vp, f64, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)          # AttributeError if the library lacks a declared symbol
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "rdb_version", "rdb_last_error", "rdb_ctx_create", "rdb_ctx_destroy", "rdb_ctx_set_stream",
+    "rdb_ctx_synchronize", "rdb_tape_load", "rdb_tape_destroy", "rdb_tape_set_input", "rdb_forward",
+    "rdb_reverse_scalar_seed", "rdb_gradient", "rdb_jacobian", "rdb_hessian", "rdb_get_value", "rdb_get_deriv",
+    "rdb_buffer_size", "rdb_tape_stats", "rdb_tape_launch_count", "rdb_gemm", "rdb_add_sum",
+]
+
+
+def _check(rc):
+    if rc != 0:
+        msg = lib().rdb_last_error()
+        raise EngineError(f"librdb200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def _is_device(x):
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+class Context:
+    def __init__(self, device_id: int = 0):
+        self.device_id = device_id
+        self.ptr = lib().rdb_ctx_create(device_id)
+        if not self.ptr:
+            msg = lib().rdb_last_error()
+            raise EngineError(f"rdb_ctx_create({device_id}) failed: {msg.decode() if msg else '?'}")
+
+    def set_stream(self, cuda_stream_ptr: int):
+        _check(lib().rdb_ctx_set_stream(self.ptr, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        _check(lib().rdb_ctx_synchronize(self.ptr))
+
+    def gemm(self, dtype, ta, tb, m, n, k, alpha, A, lda, Bp, ldb, beta, Cp, ldc):
+        _check(lib().rdb_gemm(self.ptr, dtype, int(ta), int(tb), m, n, k, alpha, A, lda, Bp, ldb, beta, Cp, ldc))
+
+    def add_sum(self, dtype, n, a, b, sign, out, sum_out):
+        _check(lib().rdb_add_sum(self.ptr, dtype, n, a, b, sign, out, sum_out))
+
+    def close(self):
+        if self.ptr:
+            lib().rdb_ctx_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        dev = int(os.environ.get("LOCAL_RANK", "0"))
+        _default_ctx = Context(dev)
+    return _default_ctx
+
+
+class EngineTape:
+    def __init__(self, ctx: Context, program: bytes, fuse_elementwise=1, seed_block=0, use_graph=1, profile=0):
+        self.ctx = ctx
+        opts = _Options(int(fuse_elementwise), int(seed_block), int(use_graph), int(profile))
+        buf = (C.c_char * len(program)).from_buffer_copy(program)
+        self.ptr = lib().rdb_tape_load(ctx.ptr, buf, len(program), C.byref(opts))
+        if not self.ptr:
+            msg = lib().rdb_last_error()
+            raise EngineError(f"rdb_tape_load failed: {msg.decode() if msg else '?'}")
+        hdr = np.frombuffer(program, "<u4", 3, 8)
+        self.np_dtype = np.dtype(np.float64 if int(hdr[1]) == RDB_F64 else np.float32)
+        self._keep = []
+
+    # ------------------------------------------------------------------------------
+    def _host_in(self, x, shape):
+        a = np.asarray(x, dtype=self.np_dtype)
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError(f"input of shape {a.shape} does not match the recorded shape {tuple(shape)}")
+        return np.asfortranarray(a)
+
+    def set_input(self, slot, x, shape):
+        if _is_device(x):
+            if x.numel() != int(np.prod(shape)):
+                raise ValueError("device input has the wrong number of elements")
+            _check(lib().rdb_tape_set_input(self.ptr, slot, C.c_void_p(x.data_ptr()), 1))
+        else:
+            a = self._host_in(x, shape)
+            _check(lib().rdb_tape_set_input(self.ptr, slot, a.ctypes.data_as(C.c_void_p), 0))
+
+    def forward(self):
+        _check(lib().rdb_forward(self.ptr))
+
+    def reverse_scalar_seed(self):
+        _check(lib().rdb_reverse_scalar_seed(self.ptr))
+
+    def _out_array(self, arr, shape):
+        """Return (pointer, is_device, staging) for a result array."""
+        if arr is None:
+            return None, 0, None
+        if _is_device(arr):
+            return arr.data_ptr(), 1, None
+        if not isinstance(arr, np.ndarray) or arr.dtype != self.np_dtype:
+            raise TypeError(f"result arrays must be numpy arrays of dtype {self.np_dtype}")
+        if arr.size != int(np.prod(shape)):
+            raise ValueError("result array has the wrong size")
+        if arr.flags.f_contiguous:
+            return arr.ctypes.data, 0, None
+        st = np.empty(shape, self.np_dtype, order="F")
+        return st.ctypes.data, 0, st
+
+    def gradient(self, results, shapes, want_value=True):
+        n = len(results)
+        ptrs = (C.c_void_p * n)()
+        staged = []
+        dev = None
+        for i, (r, s) in enumerate(zip(results, shapes)):
+            p, d, st = self._out_array(r, s)
+            if p is not None:
+                dev = d if dev is None else dev
+                if d != dev:
+                    raise ValueError("results must be all host or all device arrays")
+            ptrs[i] = p
+            staged.append((r, st))
+        val = np.zeros(1, self.np_dtype)
+        _check(lib().rdb_gradient(self.ptr, ptrs, dev or 0, val.ctypes.data_as(C.c_void_p) if want_value else None))
+        for r, st in staged:
+            if st is not None:
+                r[...] = st.reshape(r.shape, order="F")
+        return val[0] if want_value else None
+
+    def jacobian(self, slot, row_begin, row_end, result, shape, want_value=False, out_shape=None, ld=None):
+        p, d, st = self._out_array(result, shape)
+        ld = (row_end - row_begin) if ld is None else ld
+        val = None
+        vp = None
+        if want_value and not d:
+            val = np.zeros(out_shape, self.np_dtype, order="F")
+            vp = val.ctypes.data_as(C.c_void_p)
+        _check(lib().rdb_jacobian(self.ptr, slot, row_begin, row_end, C.c_void_p(p), ld, d, vp))
+        if st is not None:
+            result[...] = st.reshape(result.shape, order="F")
+        return val
+
+    def hessian(self, col_begin, col_end, result, shape, want_grad=False, ld=None):
+        p, d, st = self._out_array(result, shape)
+        n = shape[0]
+        ld = n if ld is None else ld
+        g = val = None
+        gp = vp = None
+        if want_grad:
+            g = np.zeros(n, self.np_dtype); val = np.zeros(1, self.np_dtype)
+            gp, vp = g.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p)
+        _check(lib().rdb_hessian(self.ptr, col_begin, col_end, C.c_void_p(p), ld, d, gp, vp))
+        if st is not None:
+            result[...] = st.reshape(result.shape, order="F")
+        return g, (val[0] if val is not None else None)
+
+    # debug / parity accessors ---------------------------------------------------------
+    def buffer_size(self, b):
+        return int(lib().rdb_buffer_size(self.ptr, b))
+
+    def get_value(self, b, shape=None):
+        n = self.buffer_size(b)
+        out = np.zeros(n, self.np_dtype)
+        _check(lib().rdb_get_value(self.ptr, b, out.ctypes.data_as(C.c_void_p)))
+        return out if shape is None else out.reshape(shape, order="F")
+
+    def get_deriv(self, b, shape=None):
+        n = self.buffer_size(b)
+        out = np.zeros(n, self.np_dtype)
+        _check(lib().rdb_get_deriv(self.ptr, b, out.ctypes.data_as(C.c_void_p)))
+        return out if shape is None else out.reshape(shape, order="F")
+
+    def stats(self) -> str:
+        buf = C.create_string_buffer(1 << 20)
+        _check(lib().rdb_tape_stats(self.ptr, buf, len(buf)))
+        return buf.value.decode()
+
+    def launch_count(self) -> int:
+        return int(lib().rdb_tape_launch_count(self.ptr))
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            lib().rdb_tape_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,408 @@
+"""Host-side recorder: the Python mirror of the reference's record path.
+
+Recording stays on the CPU exactly as in the reference (it is a one-off); only the recorded
+instruction list is replayed on the GPU.  This module mirrors, name for name:
+
+* ``TrackedArray`` (``src/tracked.jl:70-87``) — here a handle on a *buffer id* of the tape program
+  plus the record-time value;
+* ``Adjoint`` wrappers whose ``capture`` materialises index-linked ``TrackedReal`` arrays
+  (``src/tracked.jl:223-225,348-351``; ``src/tape.jl:24-25,67-69``) — operand class IDX;
+* the instruction recorders for ``*`` (``linalg/arithmetic.jl:171-177``), array ``+``/``-``
+  (``:36-41,111-123``), ``sum``/``mean`` (``linalg/reductions.jl:8-13,66-71``), ``∇broadcast``
+  (``broadcast.jl:142-162``), ``map``/``broadcast`` of ``@forward`` closures
+  (``elementwise.jl:230-310``), infix broadcasts (``elementwise.jl:449-517``) and range
+  ``getindex`` (``tracked.jl:308-316``).
+
+Julia spellings map to Python as ``a' -> a.T``, ``a*b -> a @ b``, ``f.(x, y) -> bcast(f, x, y)``,
+``map(@forward(f), x, y) -> map_(forward(f), x, y)``, ``x[1:2:end] -> x[0::2]``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import program as P
+from . import expr as E
+
+
+COMPACT_TRANSPOSE_THRESHOLD = 1 << 20
+
+
+class InstructionTape:
+    """``InstructionTape`` (``src/tape.jl:5-7``) being recorded into a ``TapeProgram``."""
+
+    def __init__(self, dtype=np.float64):
+        dtype = np.dtype(dtype)
+        if dtype == np.float64:
+            code = P.F64
+        elif dtype == np.float32:
+            code = P.F32
+        else:
+            raise TypeError("only Float64 and Float32 tapes are supported")
+        self.dtype = dtype
+        self.program = P.TapeProgram(code)
+
+    def __len__(self):
+        return len(self.program.instrs)
+
+    def record(self, opcode, inputs, out_buffer, expr=None, n_expr_args=0):
+        """``record!`` (``src/tape.jl:9-12``)."""
+        self.program.instrs.append(P.Instr(opcode, inputs, out_buffer, expr, n_expr_args))
+
+
+class ForwardOptimize:
+    """``@forward`` (``src/macros.jl:40-74``): the wrapped scalar closure is differentiated in
+    forward mode and recorded as ONE instruction."""
+
+    def __init__(self, f):
+        self.f = f
+
+    def __call__(self, *a):
+        return self.f(*a)
+
+
+def forward(f):
+    return f if isinstance(f, ForwardOptimize) else ForwardOptimize(f)
+
+
+class SkipOptimize:
+    """``@skip`` (``src/macros.jl:140-168``): evaluate on plain values, record nothing."""
+
+    def __init__(self, f):
+        self.f = f
+
+    def __call__(self, *a):
+        return self.f(*[value(x) for x in a])
+
+
+def skip(f):
+    return SkipOptimize(f)
+
+
+class TrackedArray:
+    __slots__ = ("value", "tape", "buffer")
+    __array_ufunc__ = None      # numpy defers `ndarray @ tracked`, `ndarray + tracked` to the reflected methods
+
+    def __init__(self, value_, tape: InstructionTape, buffer: int):
+        self.value = value_
+        self.tape = tape
+        self.buffer = buffer
+
+    # -- AbstractArray interface ---------------------------------------------------------
+    @property
+    def shape(self):
+        return self.value.shape
+
+    @property
+    def ndim(self):
+        return self.value.ndim
+
+    @property
+    def size(self):
+        return self.value.size
+
+    def __len__(self):
+        return self.value.shape[0]
+
+    @property
+    def T(self):
+        return Adjoint(self)
+
+    def adjoint(self):
+        return Adjoint(self)
+
+    def transpose(self):
+        return Adjoint(self)
+
+    # -- recorded operations -------------------------------------------------------------
+    def __matmul__(self, other):
+        return record_mul(self, other)
+
+    def __rmatmul__(self, other):
+        return record_mul(other, self)
+
+    def __add__(self, other):
+        return record_plusminus(P.OP_ADD, self, other)
+
+    def __radd__(self, other):
+        return record_plusminus(P.OP_ADD, other, self)
+
+    def __sub__(self, other):
+        return record_plusminus(P.OP_SUB, self, other)
+
+    def __rsub__(self, other):
+        return record_plusminus(P.OP_SUB, other, self)
+
+    def __neg__(self):
+        tp = self.tape
+        out = _track_new(-self.value, tp)
+        tp.record(P.OP_NEG, [_capture(self, tp)], out.buffer)
+        return out
+
+    def __mul__(self, other):
+        raise TypeError("`*` between arrays is matrix multiplication in the reference: use `@`; "
+                        "for elementwise products use broadcast('*', a, b) or bcast(lambda x, y: x*y, a, b)")
+
+    def __getitem__(self, key):
+        return record_getindex(self, key)
+
+    def __setitem__(self, *a):
+        raise TypeError("TrackedArrays do not support setindex!")   # tracked.jl:390
+
+    def reshape(self, *dims):
+        """``reshape`` aliases value AND deriv (``src/tracked.jl:402-408``)."""
+        if len(dims) == 1 and isinstance(dims[0], (tuple, list)):
+            dims = tuple(dims[0])
+        v = self.value.reshape(dims, order="F")
+        root = self.buffer
+        prog = self.tape.program
+        while prog.buffers[root].alias_of >= 0:
+            root = prog.buffers[root].alias_of
+        b = prog.add_buffer(P.BUF_TA, v.shape, alias_of=root)
+        return TrackedArray(v, self.tape, b)
+
+
+class TrackedReal:
+    """Originless scalar ``TrackedReal`` (``src/tracked.jl:47-57``), e.g. the output of ``sum``."""
+
+    __slots__ = ("value", "tape", "buffer")
+
+    def __init__(self, value_, tape, buffer):
+        self.value, self.tape, self.buffer = value_, tape, buffer
+
+    shape = ()
+    ndim = 0
+    size = 1
+
+
+class Adjoint:
+    """Lazy ``Adjoint``/``Transpose`` of a tracked or plain array (real eltype: the two coincide)."""
+
+    __slots__ = ("parent",)
+    __array_ufunc__ = None
+
+    def __init__(self, parent):
+        self.parent = parent
+
+    @property
+    def shape(self):
+        s = self.parent.shape
+        return (1, s[0]) if len(s) == 1 else (s[1], s[0])
+
+    @property
+    def T(self):
+        return self.parent
+
+    def __matmul__(self, other):
+        return record_mul(self, other)
+
+    def __rmatmul__(self, other):
+        return record_mul(other, self)
+
+
+def value(x):
+    """``value`` (``src/tracked.jl:97-103``)."""
+    if isinstance(x, (TrackedArray, TrackedReal)):
+        return x.value
+    if isinstance(x, Adjoint):
+        v = value(x.parent)
+        return v.reshape(1, -1) if v.ndim == 1 else v.T
+    return x
+
+
+def istracked(x):
+    if isinstance(x, Adjoint):
+        return istracked(x.parent)
+    return isinstance(x, (TrackedArray, TrackedReal))
+
+
+def _tape_of(*xs):
+    for x in xs:
+        if isinstance(x, Adjoint):
+            x = x.parent
+        if isinstance(x, (TrackedArray, TrackedReal)):
+            return x.tape
+    raise TypeError("no tracked argument")
+
+
+def _track_new(v, tp: InstructionTape):
+    v = np.asarray(v, tp.dtype)
+    if v.ndim == 0:
+        return TrackedReal(v[()], tp, tp.program.add_buffer(P.BUF_TR, ()))
+    return TrackedArray(np.asfortranarray(v), tp, tp.program.add_buffer(P.BUF_TA, v.shape))
+
+
+def _capture(x, tp: InstructionTape, bound_to=None) -> P.Operand:
+    """``capture`` (``src/tracked.jl:223-225``): TrackedArray → itself; an array whose elements are
+    TrackedReals (the ``Adjoint`` of a tracked array) → dense index-linked copy (IDX); plain arrays →
+    frozen copy (CONST)."""
+    bound = None
+    if bound_to is not None:
+        shp = tuple(x.shape)
+        nd = len(bound_to)
+        # index_bound(x, out) = CartesianIndex(size(x,1..N_out))   (propagation.jl:25-27)
+        bound = tuple(shp[i] if i < len(shp) else 1 for i in range(nd))
+    if isinstance(x, TrackedArray):
+        return P.Operand(x.buffer, P.CLS_TA, True, x.shape, bound=bound)
+    if isinstance(x, TrackedReal):
+        return P.Operand(x.buffer, P.CLS_TR, True, (), bound=bound)
+    if isinstance(x, Adjoint):
+        par = x.parent
+        if isinstance(par, TrackedArray):
+            if par.ndim == 1:
+                m = np.arange(par.size, dtype=np.int64)          # row vector: identity map
+            elif par.size > COMPACT_TRANSPOSE_THRESHOLD:
+                # same map, shipped as a tag instead of size(a) int64 entries; loader and oracle expand it themselves
+                return P.Operand(par.buffer, P.CLS_IDX, True, x.shape, P.IDX_TRANSPOSE, None, bound=bound)
+            else:
+                m = P.transpose_map(par.shape[0], par.shape[1])
+            return P.Operand(par.buffer, P.CLS_IDX, True, x.shape, P.IDX_EXPLICIT, m, bound=bound)
+        x = value(x)                                             # plain array: frozen dense copy
+    v = np.asarray(x, tp.dtype)
+    if v.ndim == 0:
+        raise TypeError("plain Real arguments select the :tracker broadcast implementation "
+                        "(broadcast.jl:68-85), which is not lowered yet; close over the number instead")
+    b = tp.program.add_buffer(P.BUF_CONST, v.shape, const_data=np.array(v, order="F", copy=True))
+    return P.Operand(b, P.CLS_CONST, False, v.shape, bound=bound)
+
+
+# ---------------------------------------------------------------------------------------- *
+def record_mul(x, y):
+    """``record_mul`` (``linalg/arithmetic.jl:171-177``; dispatch combos ``:186-240``)."""
+    tp = _tape_of(x, y)
+    vx, vy = np.asarray(value(x)), np.asarray(value(y))
+    if vx.ndim not in (1, 2) or vy.ndim not in (1, 2):
+        raise TypeError("`*` is defined for vectors and matrices")
+    out = _track_new(vx @ vy, tp)
+    if isinstance(out, TrackedReal):
+        raise TypeError("scalar-valued `*` (row vector times vector) is not lowered; use dot/sum")
+    tp.record(P.OP_MUL, [_capture(x, tp), _capture(y, tp)], out.buffer)
+    return out
+
+
+# ------------------------------------------------------------------------------------- + / -
+def record_plusminus(opcode, x, y):
+    """``record_plus``/``record_minus`` (``linalg/arithmetic.jl:36-41,118-123``)."""
+    if isinstance(x, Adjoint) or isinstance(y, Adjoint):
+        raise TypeError("array +/- on lazy adjoints is not lowered")
+    tp = _tape_of(x, y)
+    vx, vy = np.asarray(value(x)), np.asarray(value(y))
+    if vx.shape != vy.shape:
+        raise ValueError("array +/- needs equal shapes (use broadcast('+', a, b) otherwise)")
+    out = _track_new(vx + vy if opcode == P.OP_ADD else vx - vy, tp)
+    tp.record(opcode, [_capture(x, tp), _capture(y, tp)], out.buffer)
+    return out
+
+
+# --------------------------------------------------------------------------------- reductions
+def sum(x):  # noqa: A001 - mirrors Base.sum
+    """``Base.sum(::TrackedArray)`` (``linalg/reductions.jl:8-13``)."""
+    if not isinstance(x, TrackedArray):
+        return np.sum(x)
+    tp = x.tape
+    out = _track_new(np.sum(x.value), tp)
+    tp.record(P.OP_SUM, [_capture(x, tp)], out.buffer)
+    return out
+
+
+def mean(x):
+    """``Statistics.mean(::TrackedArray)`` (``linalg/reductions.jl:66-71``)."""
+    if not isinstance(x, TrackedArray):
+        return np.mean(x)
+    tp = x.tape
+    out = _track_new(np.mean(x.value), tp)
+    tp.record(P.OP_MEAN, [_capture(x, tp)], out.buffer)
+    return out
+
+
+# ------------------------------------------------------------------------- elementwise closures
+def _bshape(shapes):
+    return np.broadcast_shapes(*shapes)
+
+
+def _record_elementwise(opcode, f, args, require_same_shape=False):
+    tp = _tape_of(*args)
+    for a in args:
+        if isinstance(a, Adjoint):
+            raise TypeError("elementwise operations on lazy adjoints are not lowered")
+        if isinstance(a, TrackedReal) or np.ndim(value(a)) == 0:
+            raise TypeError("scalar (Real/TrackedReal) broadcast arguments select the :tracker implementation "
+                            "(broadcast.jl:68-85), which is not lowered yet")
+    shapes = [tuple(np.shape(value(a))) for a in args]
+    if require_same_shape and any(s != shapes[0] for s in shapes):
+        raise ValueError("map needs equal shapes")
+    nd = max(len(s) for s in shapes)
+    # Julia broadcasting aligns LEADING dimensions (column-major), numpy aligns trailing ones
+    padded = [s + (1,) * (nd - len(s)) for s in shapes]
+    oshape = tuple(int(max(p[i] for p in padded)) for i in range(nd))
+    for p in padded:
+        for i in range(nd):
+            if p[i] not in (1, oshape[i]):
+                raise ValueError(f"arrays could not be broadcast to a common size: {shapes}")
+    ex = E.trace(f, len(args))
+    vals = [np.asarray(value(a), tp.dtype).reshape(p, order="F") for a, p in zip(args, padded)]
+    out = _track_new(np.broadcast_to(E.eval_value(ex, vals, tp.dtype), oshape), tp)
+    ops = [_capture(a, tp, bound_to=oshape) for a in args]
+    tp.record(opcode, ops, out.buffer, ex, len(args))
+    return out
+
+
+def bcast(f, *args):
+    """Fused dot-broadcast ``f.(args...)`` → ONE ``∇broadcast`` instruction
+    (``broadcast.jl:86-94,142-162``).  Partials are taken w.r.t. every array argument."""
+    if isinstance(f, ForwardOptimize):
+        f = f.f
+    return _record_elementwise(P.OP_NBCAST, f, args)
+
+
+def map_(f, *args):
+    """``map(f::ForwardOptimize, x[, y])`` (``elementwise.jl:230-310``)."""
+    if not isinstance(f, ForwardOptimize):
+        raise TypeError("map_ lowers only @forward closures (wrap with forward(f))")
+    if len(args) not in (1, 2):
+        raise TypeError("map of a @forward closure takes 1 or 2 arrays")
+    return _record_elementwise(P.OP_MAP, f.f, args, require_same_shape=True)
+
+
+_INFIX = {"+": (P.OP_BCAST_ADD, lambda a, b: a + b), "-": (P.OP_BCAST_SUB, lambda a, b: a - b),
+          "*": (P.OP_BCAST_MUL, lambda a, b: a * b)}
+
+
+def broadcast(f, *args):
+    """``broadcast(f::ForwardOptimize, x[, y])`` (``elementwise.jl:230-310``) and the built-in
+    infix instructions ``broadcast(+|-|*, x, y)`` (``elementwise.jl:449-537``)."""
+    if isinstance(f, str):
+        if f not in _INFIX or len(args) != 2:
+            raise TypeError(f"unsupported infix broadcast {f!r}")
+        op, fn = _INFIX[f]
+        return _record_elementwise(op, fn, args)
+    if not isinstance(f, ForwardOptimize):
+        raise TypeError("broadcast lowers only @forward closures or '+', '-', '*'")
+    if len(args) not in (1, 2):
+        raise TypeError("broadcast of a @forward closure takes 1 or 2 arrays")
+    return _record_elementwise(P.OP_BCAST, f.f, args)
+
+
+# ----------------------------------------------------------------------------------- getindex
+def record_getindex(t: TrackedArray, key):
+    """Range/colon ``getindex`` (``src/tracked.jl:308-316``); the index iterable
+    (``index_iterable``, ``:291-306``) is shipped as an explicit 0-based linear map."""
+    if not isinstance(key, tuple):
+        key = (key,)
+    if any(isinstance(k, (int, np.integer)) for k in key):
+        raise TypeError("scalar getindex yields an origin-linked TrackedReal (tracked.jl:348-351); "
+                        "scalar tapes are not lowered yet")
+    if not all(isinstance(k, slice) for k in key):
+        raise TypeError("only range/colon getindex is lowered")
+    lin = np.arange(t.size, dtype=np.int64).reshape(t.shape, order="F")
+    if len(key) == 1 and t.ndim > 1:
+        sub = lin.reshape(-1, order="F")[key[0]]       # linear indexing x[a:b]
+    else:
+        if len(key) != t.ndim:
+            raise IndexError("wrong number of indices")
+        sub = lin[key]
+    m = np.ascontiguousarray(sub.reshape(-1, order="F"))
+    tp = t.tape
+    out = _track_new(t.value.reshape(-1, order="F")[m].reshape(sub.shape, order="F"), tp)
+    op = P.Operand(t.buffer, P.CLS_TA, True, t.shape, P.IDX_EXPLICIT, m)
+    tp.record(P.OP_GETINDEX, [op], out.buffer)
+    return out

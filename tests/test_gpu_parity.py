@@ -1,0 +1,279 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same seeded
+inputs.  Tolerances are the north star's: 1e-12 (FP64) / 1e-5 (FP32), relative to max|.| of each result array.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-12, np.float32: 1e-5}
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def run_gradient(rd, orc, f, rec_inputs, inputs, dtype=np.float64, check_buffers=True, **opts):
+    tape = rd.GradientTape(f, tuple(rec_inputs), dtype=dtype)
+    ct = rd.compile(tape, **opts)
+    res = tuple(rd.DiffResult(0.0, np.zeros(np.shape(x), dtype, order="F")) for x in inputs)
+    rd.gradient_(res, ct, tuple(inputs))
+    ot = orc.OracleTape(tape.program_bytes())
+    val, grads = ot.gradient(list(inputs))
+    tol = TOL[dtype]
+    assert abs(float(res[0].value) - float(val)) <= tol * max(abs(float(val)), 1e-300)
+    for r, g in zip(res, grads):
+        assert relerr(r.gradient, g) < tol
+    if check_buffers:
+        # every observable buffer: values of all instruction outputs, derivs of intermediates back to zero
+        for b in range(len(ot.value)):
+            if ot.kind[b] == orc.BUF_CONST:
+                continue
+            v = ct.handle.get_value(b)
+            assert relerr(v, ot.value[b].reshape(-1, order="F")) < tol, f"value of buffer {b}"
+            d = ct.handle.get_deriv(b)
+            if b in ot.inputs:
+                assert relerr(d, ot.deriv[b].reshape(-1, order="F")) < tol
+            else:
+                assert not np.any(d), f"deriv of intermediate buffer {b} not unseeded"
+    return ct
+
+
+# ------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (3, 5, 7), (64, 64, 64), (100, 100, 100), (129, 257, 65), (512, 384, 640),
+                                   (1024, 1024, 1024), (8, 1, 300), (1030, 1026, 18)])
+def test_gemm_kernel(rd, ctx, dtype, ta, tb, m, n, k):
+    import torch
+    rng = np.random.default_rng(m * 7 + n * 3 + k)
+    A = rng.standard_normal((k, m) if ta else (m, k)).astype(dtype)
+    B = rng.standard_normal((n, k) if tb else (k, n)).astype(dtype)
+    C0 = rng.standard_normal((m, n)).astype(dtype)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    # column-major buffers on the device
+    dA = torch.from_numpy(np.ascontiguousarray(A.T)).cuda(); dB = torch.from_numpy(np.ascontiguousarray(B.T)).cuda()
+    for alpha, beta in [(1.0, 0.0), (1.0, 1.0), (-0.5, 2.0)]:
+        dC = torch.from_numpy(np.ascontiguousarray(C0.T)).cuda()
+        ctx.gemm(0 if dtype == np.float64 else 1, ta, tb, m, n, k, alpha, dA.data_ptr(), A.shape[0], dB.data_ptr(), B.shape[0],
+                 beta, dC.data_ptr(), m)
+        ctx.synchronize()
+        got = dC.cpu().numpy().T
+        opA = A.T if ta else A; opB = B.T if tb else B
+        ref = alpha * (opA.astype(np.float64) @ opB.astype(np.float64)) + beta * C0.astype(np.float64)
+        scale = np.abs(opA).astype(np.float64) @ np.abs(opB).astype(np.float64) + np.abs(C0) * abs(beta)
+        err = np.max(np.abs(got - ref) / np.maximum(scale, 1e-300))
+        assert err < (1e-14 if dtype == np.float64 else 2e-6), (alpha, beta, err)
+    _ = tdt
+
+
+def test_gemm_beta0_ignores_nan(rd, ctx):
+    import torch
+    A = torch.ones(128, 128, dtype=torch.float64, device="cuda")
+    C = torch.full((128, 128), float("nan"), dtype=torch.float64, device="cuda")
+    ctx.gemm(0, 0, 0, 128, 128, 128, 1.0, A.data_ptr(), 128, A.data_ptr(), 128, 0.0, C.data_ptr(), 128)
+    ctx.synchronize()
+    assert torch.all(C == 128.0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [1, 7, 1000, 1 << 20, (1 << 20) + 3])
+def test_add_sum_kernel(rd, ctx, dtype, n):
+    import torch
+    rng = np.random.default_rng(n)
+    a = rng.random(n).astype(dtype); b = rng.random(n).astype(dtype)
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = torch.empty_like(da); s = torch.zeros(1, dtype=da.dtype, device="cuda")
+    ctx.add_sum(0 if dtype == np.float64 else 1, n, da.data_ptr(), db.data_ptr(), 1.0, out.data_ptr(), s.data_ptr())
+    ctx.synchronize()
+    assert np.array_equal(out.cpu().numpy(), a + b)           # elementwise: bit-exact
+    ref = np.sum((a + b).astype(np.float64))
+    assert abs(float(s.item()) - ref) <= TOL[dtype] * ref
+
+
+# ------------------------------------------------------------------------------------------ the five configs (small)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [1, 2, 5, 100, 257])
+def test_cfg1_gradient(rd, orc, dtype, n):
+    rng = np.random.default_rng(1)
+    rec = (rng.random((n, n)).astype(dtype), rng.random((n, n)).astype(dtype))
+    run_gradient(rd, orc, rd.workloads.f_gradient_example, rec, rd.workloads.inputs_gradient_example(n, dtype), dtype)
+
+
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_cfg1_fusion_toggle_same_result(rd, orc, fuse):
+    rng = np.random.default_rng(1)
+    n = 65
+    rec = (rng.random((n, n)), rng.random((n, n)))
+    run_gradient(rd, orc, rd.workloads.f_gradient_example, rec, rd.workloads.inputs_gradient_example(n), fuse_elementwise=fuse)
+
+
+def test_cfg1_replay_twice_new_inputs(rd, orc):
+    """Record at one point, replay at others (GradientTests.jl:40-43); a tape is reusable."""
+    n = 33
+    rng = np.random.default_rng(1)
+    tape = rd.GradientTape(rd.workloads.f_gradient_example, (rng.random((n, n)), rng.random((n, n))))
+    ct = rd.compile(tape)
+    ot = orc.OracleTape(tape.program_bytes())
+    for seed in (2, 3, 4):
+        a, b = rd.workloads.inputs_gradient_example(n, seed=seed)
+        ga, gb = rd.gradient(ct, (a, b))
+        _, (oa, ob) = ot.gradient([a, b])
+        assert relerr(ga, oa) < 1e-12 and relerr(gb, ob) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(7, 5, 4, 9), (64, 48, 32, 200), (128, 128, 128, 1024)])
+def test_cfg3_mlp(rd, orc, dtype, shape):
+    d, h, o, N = shape
+    X, rec = rd.workloads.inputs_mlp(d, h, o, N, dtype, seed=1)
+    _, ws = rd.workloads.inputs_mlp(d, h, o, N, dtype, seed=2)
+    run_gradient(rd, orc, rd.workloads.make_f_mlp(X), rec, ws, dtype)
+
+
+@pytest.mark.parametrize("n,block", [(12, 0), (12, 5), (200, 64), (256, 0)])
+def test_cfg4_jacobian(rd, orc, n, block):
+    A, B, x0 = rd.workloads.inputs_jacobian(n, seed=1)
+    tape = rd.JacobianTape(rd.workloads.make_f_jacobian(A, B), x0)
+    ct = rd.compile(tape, seed_block=block)
+    _, _, x = rd.workloads.inputs_jacobian(n, seed=2)
+    res = rd.DiffResult(None, np.zeros((n, n), order="F"))
+    rd.jacobian_(res, ct, x)
+    y, J = orc.OracleTape(tape.program_bytes()).jacobian([x])
+    assert relerr(res.jacobian, J) < 1e-12
+    assert relerr(res.value, y) < 1e-12
+    # a shard of rows (the multi-GPU partition) equals the same rows of the full matrix
+    part = np.zeros((5, n), order="F")
+    rd.jacobian_(part, ct, x, rows=(3, 8))
+    assert np.array_equal(part, res.jacobian[3:8, :])
+
+
+@pytest.mark.parametrize("n,block", [(2, 0), (10, 0), (10, 3), (64, 16), (1000, 0)])
+def test_cfg5_hessian(rd, orc, n, block):
+    x0 = rd.workloads.inputs_rosenbrock(n, seed=1)
+    tape = rd.HessianTape(rd.workloads.f_rosenbrock, x0)
+    ct = rd.compile(tape, seed_block=block)
+    x = rd.workloads.inputs_rosenbrock(n, seed=2)
+    H = np.full((n, n), np.nan, order="F")
+    g = np.zeros(n)
+    res = rd.DiffResult(0.0, g, H)
+    rd.hessian_(res, ct, x)
+    o, e = x[0::2], x[1::2]
+    Hcf = np.zeros((n, n))
+    idx = np.arange(n // 2)
+    Hcf[2 * idx, 2 * idx] = 1200 * o ** 2 - 400 * e + 2
+    Hcf[2 * idx, 2 * idx + 1] = Hcf[2 * idx + 1, 2 * idx] = -400 * o
+    Hcf[2 * idx + 1, 2 * idx + 1] = 200
+    assert relerr(H, Hcf) < 1e-12
+    assert np.all(H[Hcf == 0] == 0.0)                           # structural zeros exact
+    val, (og,) = orc.OracleTape(tape.program_bytes()).gradient([x])
+    assert relerr(g, og) < 1e-12 and abs(res.value - val) < 1e-12 * abs(val)
+    if n >= 10:
+        part = np.zeros((n, 4), order="F")
+        rd.hessian_(part, ct, x, cols=(3, 7))
+        assert np.array_equal(part, H[:, 3:7])
+
+
+def test_hessian_general_tape_vs_fd(rd, orc):
+    """A tape with `*` by constants, +, elementwise closures: forward-over-reverse vs finite differences of the oracle."""
+    rng = np.random.default_rng(5)
+    n = 9
+    A = rng.random((n, n)) / n
+    f = lambda x: rd.sum(rd.map_(rd.forward(lambda u, v: rd.tanh(u) * v + u * u * rd.exp(-v)), A @ x + x, x))
+    tape = rd.HessianTape(f, rng.random(n))
+    ct = rd.compile(tape)
+    x = rng.random(n)
+    H = rd.hessian(ct, x)
+    Hfd = orc.hessian_dense(tape.program_bytes(), x)
+    assert np.max(np.abs(H - Hfd)) < 1e-6 * max(1.0, np.max(np.abs(Hfd)))
+    assert np.max(np.abs(H - H.T)) < 1e-12 * np.max(np.abs(H))
+
+
+# ------------------------------------------------------------------------------------------ per-instruction
+def _cases(rd):
+    from test_oracle import CASES
+    return CASES
+
+
+@pytest.mark.parametrize("name", ["a*b", "a'*b", "a*b'", "a'*b'", "a+b", "a-b", "-a", "bcast*", "bcast-", "map", "nbcast_fns",
+                                  "getindex", "reshape"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_instruction(rd, orc, name, dtype):
+    rng = np.random.default_rng(11)
+    for shp in [(3, 3), (40, 40)]:
+        if name in ("reshape",) and shp != (3, 3):
+            continue
+        rec = (rng.random(shp).astype(dtype), rng.random(shp).astype(dtype))
+        ins = (np.asfortranarray(rng.random(shp).astype(dtype)), np.asfortranarray(rng.random(shp).astype(dtype)))
+        run_gradient(rd, orc, _cases(rd)[name](rd), rec, ins, dtype)
+
+
+def test_broadcast_patterns(rd, orc):
+    rng = np.random.default_rng(3)
+    W, b, r = rng.random((40, 60)), rng.random(40), rng.random((1, 60))
+    f = lambda W_, b_, r_: rd.sum(rd.bcast(lambda x, y, z: rd.tanh(x + y) * z, W_, b_, r_))
+    run_gradient(rd, orc, f, (W, b, r), (np.asfortranarray(rng.random((40, 60))), rng.random(40), np.asfortranarray(rng.random((1, 60)))))
+
+
+def test_general_index_map_gather_scatter(rd, orc):
+    """An IDX operand that is NOT a pure transpose (row-vector adjoint of a vector times a matrix exercises the
+    folded path; a hand-built permuted map exercises gather + scatter-add)."""
+    P = rd.program
+    rng = np.random.default_rng(9)
+    n = 6
+    a0, b0 = rng.random((n, n)), rng.random((n, n))
+    tape = rd.GradientTape(lambda a, b: rd.sum(a.T @ b), (a0, b0))
+    op = tape.tape.program.instrs[0].inputs[0]
+    perm = rng.permutation(n * n).astype(np.int64)
+    perm[0] = perm[1]                                   # a duplicate: both elements must add
+    op.idx_map = perm
+    ct = rd.compile(tape)
+    a, b = np.asfortranarray(rng.random((n, n))), np.asfortranarray(rng.random((n, n)))
+    ga, gb = rd.gradient(ct, (a, b))
+    _, (oa, ob) = orc.OracleTape(tape.program_bytes()).gradient([a, b])
+    assert relerr(ga, oa) < 1e-12 and relerr(gb, ob) < 1e-12
+    _ = P
+
+
+def test_loader_rejects_bad_programs(rd, ctx):
+    tape = rd.GradientTape(lambda v: rd.sum(v + v), np.ones(3))
+    raw = bytearray(tape.program_bytes())
+    with pytest.raises(rd.engine.EngineError):
+        rd.engine.EngineTape(ctx, bytes(raw[:-8]))                        # truncated
+    bad = bytearray(raw); bad[0] ^= 0xFF
+    with pytest.raises(rd.engine.EngineError):
+        rd.engine.EngineTape(ctx, bytes(bad))                             # bad magic
+    prog = rd.program.TapeProgram.from_bytes(bytes(raw))
+    prog.instrs[0].opcode = 99                                            # e.g. an @grad closure instruction
+    with pytest.raises(rd.engine.EngineError, match="cannot be replayed"):
+        rd.engine.EngineTape(ctx, prog.to_bytes())
+
+
+def test_input_shape_errors(rd):
+    tape = rd.GradientTape(lambda v: rd.sum(v + v), np.ones(3))
+    ct = rd.compile(tape)
+    with pytest.raises(ValueError):
+        rd.gradient_(np.zeros(3), ct, np.ones(4))
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_cfg2_full_size_closed_form(rd):
+    """4096x4096 FP64: the oracle needs ~3 s of DGEMM per eval, so the full-size check uses the size-independent
+    closed form — O(n^2), shares no GEMM with the engine."""
+    n = 4096
+    rng = np.random.default_rng(1)
+    tape = rd.GradientTape(rd.workloads.f_gradient_example, (rng.random((8, 8)), rng.random((8, 8))))
+    _ = tape
+    a0 = np.asfortranarray(rng.random((n, n))); b0 = np.asfortranarray(rng.random((n, n)))
+    tape = rd.GradientTape(rd.workloads.f_gradient_example, (a0, b0))
+    ct = rd.compile(tape)
+    a, b = rd.workloads.inputs_gradient_example(n)
+    ga, gb = np.zeros((n, n), order="F"), np.zeros((n, n), order="F")
+    res = (rd.DiffResult(0.0, ga), rd.DiffResult(0.0, gb))
+    rd.gradient_(res, ct, (a, b))
+    one = np.ones(n)
+    val = (a @ one) @ (b @ one) + (a.T @ one) @ (b.T @ one)
+    assert abs(res[0].value - val) < 1e-12 * abs(val)
+    assert relerr(ga, b.sum(1)[:, None] + b.sum(0)[None, :]) < 1e-12
+    assert relerr(gb, a.sum(1)[:, None] + a.sum(0)[None, :]) < 1e-12
