@@ -52,7 +52,13 @@ struct rdb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    int refs = 1;          // the handle itself + one per live tape: destruction order is the caller's business
 };
+static void ctx_release(rdb_ctx *c) {
+    if (!c || --c->refs > 0) return;
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
 
 struct Buf {
     int kind = 0, nd = 0;
@@ -991,11 +997,7 @@ rdb_ctx *rdb_ctx_create(int device_id) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(RDB_ECUDA, "cudaStreamCreate failed"); delete c; return nullptr; }
     return c;
 }
-void rdb_ctx_destroy(rdb_ctx *c) {
-    if (!c) return;
-    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
-    delete c;
-}
+void rdb_ctx_destroy(rdb_ctx *c) { ctx_release(c); }
 int rdb_ctx_set_stream(rdb_ctx *c, void *stream) {
     if (!c) return fail(RDB_EINVAL, "null context");
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -1014,6 +1016,7 @@ rdb_tape *rdb_tape_load(rdb_ctx *c, const void *program, size_t nbytes, const rd
     cudaSetDevice(c->device);
     auto *t = new rdb_tape();
     t->ctx = c;
+    c->refs++;
     t->opts.fuse_elementwise = 1; t->opts.use_graph = 1;
     if (opts) t->opts = *opts;
     cudaEventCreate(&t->ev0);
@@ -1027,6 +1030,7 @@ void rdb_tape_destroy(rdb_tape *t) {
     for (void *p : t->allocs) cudaFree(p);
     if (t->ev0) cudaEventDestroy(t->ev0);
     if (t->ev1) cudaEventDestroy(t->ev1);
+    ctx_release(t->ctx);
     delete t;
 }
 
