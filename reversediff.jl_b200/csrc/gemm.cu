@@ -60,48 +60,51 @@ struct Tile {
     __device__ __forceinline__ static int at(int r, int k) { return KMAJOR ? r * STRIDE + k : k * STRIDE + r; }
 };
 
-// global -> shared for one k-tile.  `g` points at element (row 0, k 0) of op(X); ld is the leading dim of the
-// stored matrix.  KMAJOR: element (r,k) at g[k + r*ld]; else at g[r + k*ld].
+// Per-thread copy plan for one operand tile: global pointers, shared offsets and row predicates are computed ONCE;
+// a k-tile then costs one compare + one cp.async + one pointer bump per 16-byte chunk (ncu on the first version showed
+// ~150 integer instructions per thread per k-tile in front of the DMMAs, issued right after the barrier).
+// `g` points at element (row 0, k 0) of op(X).  KMAJOR: element (r,k) at g[k + r*ld]; else at g[r + k*ld].
 template <bool KMAJOR, int R, bool VEC>
-__device__ __forceinline__ void load_tile(double *s, const double *g, int64_t ld, int r0, int k0, int Rtot, int Ktot,
-                                          int tid) {
+struct TileLoader {
     using TL = Tile<KMAJOR, R>;
-    if (VEC) {
-        constexpr int CHUNKS = R * BK / 2;
+    static constexpr int PER = VEC ? (R * BK / 2) / THREADS : (R * BK) / THREADS;
+    const double *ptr[PER];
+    const double *base;
+    int soff[PER];
+    int kofs[PER];
+    unsigned rowok;
+    int64_t kstep;
+    __device__ __forceinline__ void init(const double *g, int64_t ld, int r0, int Rtot, int tid) {
+        base = g;
+        rowok = 0;
+        kstep = KMAJOR ? (int64_t)BK : (int64_t)BK * ld;
 #pragma unroll
-        for (int i = 0; i < CHUNKS / THREADS; ++i) {
-            int c = tid + i * THREADS;
-            if (KMAJOR) {
-                int r = c / (BK / 2), kc = (c % (BK / 2)) * 2;
-                bool p = (r0 + r < Rtot) && (k0 + kc < Ktot);
-                const double *src = p ? g + (int64_t)(k0 + kc) + (int64_t)(r0 + r) * ld : g;
-                cp_async_16(s + TL::at(r, kc), src, p);
+        for (int i = 0; i < PER; ++i) {
+            int c = tid + i * THREADS, r, k;
+            if (VEC) {
+                if (KMAJOR) { r = c / (BK / 2); k = (c % (BK / 2)) * 2; } else { k = c / (R / 2); r = (c % (R / 2)) * 2; }
             } else {
-                int k = c / (R / 2), rc = (c % (R / 2)) * 2;
-                bool p = (r0 + rc < Rtot) && (k0 + k < Ktot);
-                const double *src = p ? g + (int64_t)(r0 + rc) + (int64_t)(k0 + k) * ld : g;
-                cp_async_16(s + TL::at(rc, k), src, p);
+                if (KMAJOR) { r = c / BK; k = c % BK; } else { k = c / R; r = c % R; }
             }
-        }
-    } else {
-        constexpr int ELEMS = R * BK;
-#pragma unroll
-        for (int i = 0; i < ELEMS / THREADS; ++i) {
-            int c = tid + i * THREADS;
-            if (KMAJOR) {
-                int r = c / BK, k = c % BK;
-                bool p = (r0 + r < Rtot) && (k0 + k < Ktot);
-                const double *src = p ? g + (int64_t)(k0 + k) + (int64_t)(r0 + r) * ld : g;
-                cp_async_8(s + TL::at(r, k), src, p);
-            } else {
-                int k = c / R, r = c % R;
-                bool p = (r0 + r < Rtot) && (k0 + k < Ktot);
-                const double *src = p ? g + (int64_t)(r0 + r) + (int64_t)(k0 + k) * ld : g;
-                cp_async_8(s + TL::at(r, k), src, p);
-            }
+            bool ok = r0 + r < Rtot;
+            int rr = ok ? r0 + r : 0;
+            ptr[i] = KMAJOR ? g + (int64_t)k + (int64_t)rr * ld : g + (int64_t)rr + (int64_t)k * ld;
+            soff[i] = TL::at(r, k);
+            kofs[i] = k;
+            rowok |= (ok ? 1u : 0u) << i;
         }
     }
-}
+    // copy k-tile number `kt` (k0 = kt*BK) into stage buffer s, then advance the pointers to the next k-tile
+    __device__ __forceinline__ void issue(double *s, int k0, int Ktot) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            bool p = ((rowok >> i) & 1u) && (k0 + kofs[i] < Ktot);
+            const double *src = p ? ptr[i] : base;
+            if (VEC) cp_async_16(s + soff[i], src, p); else cp_async_8(s + soff[i], src, p);
+            ptr[i] += kstep;
+        }
+    }
+};
 
 template <bool TA, bool TB>
 constexpr int smem_bytes() {
@@ -126,6 +129,11 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int KT = (K + BK - 1) / BK;
 
+    TileLoader<TA, BM, VEC> la;
+    TileLoader<!TB, BN, VEC> lb;
+    la.init(A, lda, m0, M, tid);
+    lb.init(B, ldb, n0, N, tid);
+
     double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -135,38 +143,50 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < KT) {
-            load_tile<TA, BM, VEC>(sA + s * TLA::ELEMS, A, lda, m0, s * BK, M, K, tid);
-            load_tile<!TB, BN, VEC>(sB + s * TLB::ELEMS, B, ldb, n0, s * BK, N, K, tid);
+            la.issue(sA + s * TLA::ELEMS, s * BK, K);
+            lb.issue(sB + s * TLB::ELEMS, s * BK, K);
         }
         cp_async_commit();
     }
 
+    // fragment base offsets (loop invariant)
+    const int a_off = TLA::at(wm * 64 + g, t);
+    const int b_off = TLB::at(wn * 32 + g, t);
+    constexpr int A_ROW8 = TA ? 8 * TLA::STRIDE : 8;      // +8 rows of op(A)
+    constexpr int B_ROW8 = !TB ? 8 * TLB::STRIDE : 8;
+    constexpr int A_K4 = TA ? 4 : 4 * TLA::STRIDE;        // +4 in k
+    constexpr int B_K4 = !TB ? 4 : 4 * TLB::STRIDE;
+
+    int stage = 0;
     for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {
-            int nk = kt + STAGES - 1;
-            if (nk < KT) {
-                int s = nk % STAGES;
-                load_tile<TA, BM, VEC>(sA + s * TLA::ELEMS, A, lda, m0, nk * BK, M, K, tid);
-                load_tile<!TB, BN, VEC>(sB + s * TLB::ELEMS, B, ldb, n0, nk * BK, N, K, tid);
+        const double *a_s = sA + stage * TLA::ELEMS + a_off;
+        const double *b_s = sB + stage * TLB::ELEMS + b_off;
+        double af[8], bf[4];
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) af[i] = a_s[i * A_ROW8 + kk * A_K4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = b_s[j * B_ROW8 + kk * B_K4];
+            if (kk == 1) {
+                // refill the stage consumed in the previous iteration; issued behind the first DMMA batch so the tensor
+                // pipe already has work queued while the copies are set up
+                int nk = kt + STAGES - 1;
+                if (nk < KT) {
+                    int ns = stage == 0 ? STAGES - 1 : stage - 1;
+                    la.issue(sA + ns * TLA::ELEMS, nk * BK, K);
+                    lb.issue(sB + ns * TLB::ELEMS, nk * BK, K);
+                }
+                cp_async_commit();
             }
-            cp_async_commit();
-        }
-        const double *a_s = sA + (kt % STAGES) * TLA::ELEMS;
-        const double *b_s = sB + (kt % STAGES) * TLB::ELEMS;
-#pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
-            double af[8], bf[4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) af[i] = a_s[TLA::at(wm * 64 + i * 8 + g, kk + t)];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = b_s[TLB::at(wn * 32 + j * 8 + g, kk + t)];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
+        stage = stage + 1 == STAGES ? 0 : stage + 1;
     }
     cp_async_wait<0>();
 
