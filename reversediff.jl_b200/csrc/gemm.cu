@@ -12,6 +12,7 @@
 //       split to hold the 1e-5 bound — see DESIGN.md; not in this round.)
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include "kernels.h"
 
 namespace rdb {
@@ -64,9 +65,10 @@ struct Tile {
 // a k-tile then costs one compare + one cp.async + one pointer bump per 16-byte chunk (ncu on the first version showed
 // ~150 integer instructions per thread per k-tile in front of the DMMAs, issued right after the barrier).
 // `g` points at element (row 0, k 0) of op(X).  KMAJOR: element (r,k) at g[k + r*ld]; else at g[r + k*ld].
-template <bool KMAJOR, int R, bool VEC>
+template <bool KMAJOR, int R, bool VEC, int NTHREADS>
 struct TileLoader {
     using TL = Tile<KMAJOR, R>;
+    static constexpr int THREADS = NTHREADS;
     static constexpr int PER = VEC ? (R * BK / 2) / THREADS : (R * BK) / THREADS;
     const double *ptr[PER];
     const double *base;
@@ -106,18 +108,27 @@ struct TileLoader {
     }
 };
 
-template <bool TA, bool TB>
+// NWN = warps along N: 4 -> 128x128 tile, 256 threads, 4 stages, 1 CTA/SM; 2 -> 128x64 tile, 128 threads, 3 stages,
+// 2 CTAs/SM (two independently progressing CTAs hide each other's barrier and fixed-latency stalls).
+template <int NWN> struct Cfg {
+    static constexpr int BN_ = 32 * NWN;
+    static constexpr int THREADS_ = 64 * NWN;
+    static constexpr int STAGES_ = NWN == 4 ? 4 : 3;
+    static constexpr int MINB = NWN == 4 ? 1 : 2;
+};
+template <bool TA, bool TB, int NWN>
 constexpr int smem_bytes() {
-    return STAGES * (Tile<TA, BM>::ELEMS + Tile<!TB, BN>::ELEMS) * (int)sizeof(double);
+    return Cfg<NWN>::STAGES_ * (Tile<TA, BM>::ELEMS + Tile<!TB, Cfg<NWN>::BN_>::ELEMS) * (int)sizeof(double);
 }
 
 // op(A) is MxK.  !TA: A stored MxK (m contiguous)  -> not KMAJOR.   TA: A stored KxM (k contiguous) -> KMAJOR.
 // op(B) is KxN.  !TB: B stored KxN (k contiguous)  -> KMAJOR.       TB: B stored NxK (n contiguous) -> not KMAJOR.
-template <bool TA, bool TB, bool VEC>
-__global__ void __launch_bounds__(THREADS, 1)
+template <bool TA, bool TB, bool VEC, int NWN>
+__global__ void __launch_bounds__(Cfg<NWN>::THREADS_, Cfg<NWN>::MINB)
 dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, int64_t lda,
                   const double *__restrict__ B, int64_t ldb, double beta, double *__restrict__ C, int64_t ldc) {
     extern __shared__ __align__(16) double smem[];
+    constexpr int BN = Cfg<NWN>::BN_, THREADS = Cfg<NWN>::THREADS_, STAGES = Cfg<NWN>::STAGES_;
     using TLA = Tile<TA, BM>;
     using TLB = Tile<!TB, BN>;
     double *sA = smem;
@@ -125,12 +136,12 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;      // 2 x 4 warps; warp tile 64 x 32
+    const int wm = warp / NWN, wn = warp % NWN;   // 2 x NWN warps; warp tile 64 x 32
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int KT = (K + BK - 1) / BK;
 
-    TileLoader<TA, BM, VEC> la;
-    TileLoader<!TB, BN, VEC> lb;
+    TileLoader<TA, BM, VEC, THREADS> la;
+    TileLoader<!TB, BN, VEC, THREADS> lb;
     la.init(A, lda, m0, M, tid);
     lb.init(B, ldb, n0, N, tid);
 
@@ -304,6 +315,31 @@ dgemm_dmma_small_kernel(int M, int N, int K, double alpha, const double *__restr
         }
 }
 
+template <bool TA, bool TB, bool VEC, int NWN>
+static cudaError_t launch_cfg(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const double *A, int64_t lda,
+                              const double *B, int64_t ldb, double beta, double *C, int64_t ldc) {
+    constexpr int smem = smem_bytes<TA, TB, NWN>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_kernel<TA, TB, VEC, NWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + Cfg<NWN>::BN_ - 1) / Cfg<NWN>::BN_));
+    dgemm_dmma_kernel<TA, TB, VEC, NWN><<<grid, Cfg<NWN>::THREADS_, smem, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb,
+                                                                               beta, C, ldc);
+    return cudaGetLastError();
+}
+
+static int gemm_cfg() {
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char *e = getenv("RDB_GEMM_CFG");
+        cfg = e ? atoi(e) : 1;
+    }
+    return cfg;
+}
+
 template <bool TA, bool TB>
 static cudaError_t launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const double *A, int64_t lda,
                           const double *B, int64_t ldb, double beta, double *C, int64_t ldc) {
@@ -318,29 +354,12 @@ static cudaError_t launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, doub
     // 16-byte cp.async needs even contiguous extents, even leading dims and 16B-aligned bases
     bool vec = (lda % 2 == 0) && (ldb % 2 == 0) && (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0) &&
                ((TA ? K : M) % 2 == 0) && ((TB ? N : K) % 2 == 0);
-    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
-    constexpr int smem = smem_bytes<TA, TB>();
-    cudaError_t e;
-    if (vec) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            e = cudaFuncSetAttribute(dgemm_dmma_kernel<TA, TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return e;
-            attr_done = true;
-        }
-        dgemm_dmma_kernel<TA, TB, true><<<grid, THREADS, smem, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta,
-                                                                      C, ldc);
-    } else {
-        static bool attr_done = false;
-        if (!attr_done) {
-            e = cudaFuncSetAttribute(dgemm_dmma_kernel<TA, TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (e != cudaSuccess) return e;
-            attr_done = true;
-        }
-        dgemm_dmma_kernel<TA, TB, false><<<grid, THREADS, smem, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb,
-                                                                       beta, C, ldc);
+    if (gemm_cfg() == 0) {
+        if (vec) return launch_cfg<TA, TB, true, 4>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+        return launch_cfg<TA, TB, false, 4>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
     }
-    return cudaGetLastError();
+    if (vec) return launch_cfg<TA, TB, true, 2>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    return launch_cfg<TA, TB, false, 2>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 }  // namespace d64
 
