@@ -344,7 +344,7 @@ def sharded_legs(args, torch, dist, rd, ctx, rank, world):
     _, _, x = rd.workloads.inputs_jacobian(n, seed=2)
     x_d = torch.from_numpy(x).cuda()
     rows = n // world
-    rb, re = rank * rows, (rank + 1) * rows if rank < world - 1 else n
+    rb, re = rd.shard_range(n, world, rank)
     J_d = torch.empty((re - rb) * n, dtype=torch.float64, device="cuda")
 
     def step():
@@ -366,7 +366,7 @@ def sharded_legs(args, torch, dist, rd, ctx, rank, world):
     ct = rd.compile(tape, ctx=ctx)
     x_d = torch.from_numpy(rd.workloads.inputs_rosenbrock(n, seed=2)).cuda()
     cols = n // world
-    cb, ce = rank * cols, (rank + 1) * cols if rank < world - 1 else n
+    cb, ce = rd.shard_range(n, world, rank)
     H_d = torch.empty(n * (ce - cb), dtype=torch.float64, device="cuda")
 
     def hstep():

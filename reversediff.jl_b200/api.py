@@ -254,6 +254,12 @@ def hessian_(result, ct: CompiledTape, input_, cols=None):
     return result
 
 
+def shard_range(n: int, world: int, rank: int):
+    """Contiguous block of output-seed rows (jacobian!) or Hessian columns owned by `rank` of `world`."""
+    per = n // world
+    return rank * per, ((rank + 1) * per if rank < world - 1 else n)
+
+
 def hessian(ct: CompiledTape, input_):
     n = ct.tape.input[0].size
     return hessian_(np.zeros((n, n), ct.dtype, order="F"), ct, input_)
