@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--jac-n", type=int, default=8192)
     ap.add_argument("--hess-n", type=int, default=16384)
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--skip-extra", action="store_true", help="skip the jacobian!/hessian! legs at N>1")
+    ap.add_argument("--skip-extra", action="store_true", help="skip the jacobian!/hessian! legs")
     return ap.parse_args()
 
 
@@ -306,7 +306,7 @@ def main():
                          f"{cores} BLAS threads of {os.cpu_count()} host cores"}
 
     extra = {}
-    if world > 1 and not args.skip_extra:
+    if not args.skip_extra:
         extra = sharded_legs(args, torch, dist, rd, ctx, rank, world)
 
     if rank == 0:
@@ -350,7 +350,7 @@ def sharded_legs(args, torch, dist, rd, ctx, rank, world):
     def step():
         rd.jacobian_(J_d, ct, x_d, rows=(rb, re))
     ms = timed_steps(torch, dist, world, step, 3, 2)
-    full = torch.empty(world * rows * n, dtype=torch.float64, device="cuda") if n % world == 0 else None
+    full = torch.empty(world * rows * n, dtype=torch.float64, device="cuda") if (n % world == 0 and world > 1) else None
     gather_ms = None
     if full is not None:
         torch.cuda.synchronize(); dist.barrier()
