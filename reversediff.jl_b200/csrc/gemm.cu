@@ -367,6 +367,12 @@ cudaError_t gemm_f64(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, in
                      int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc) {
     if (M <= 0 || N <= 0) return cudaSuccess;
     if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return cudaErrorInvalidValue;
+    static int use_ozaki = -1;
+    if (use_ozaki < 0) { const char *e = getenv("RDB_F64_GEMM"); use_ozaki = (e && e[0] == 'o') ? 1 : 0; }
+    if (use_ozaki) {
+        cudaError_t e = gemm_f64_ozaki(st, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, ozaki_default_slices());
+        if (e != cudaErrorNotSupported) return e;
+    }
     if (!ta && !tb) return d64::launch<false, false>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
     if (!ta && tb) return d64::launch<false, true>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
     if (ta && !tb) return d64::launch<true, false>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
@@ -514,6 +520,12 @@ cudaError_t gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, in
                      int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc) {
     if (M <= 0 || N <= 0) return cudaSuccess;
     if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return cudaErrorInvalidValue;
+    static int force_simt = -1;
+    if (force_simt < 0) { const char *e = getenv("RDB_F32_GEMM"); force_simt = (e && e[0] == 's') ? 1 : 0; }
+    if (!force_simt) {
+        cudaError_t e = gemm_f32_umma(st, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);   // 3xTF32 on tcgen05
+        if (e != cudaErrorNotSupported) return e;
+    }
     if (!ta && !tb) return s32::launch<false, false>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
     if (!ta && tb) return s32::launch<false, true>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
     if (ta && !tb) return s32::launch<true, false>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);

@@ -13,6 +13,16 @@ cudaError_t gemm_f64(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N, int64
 cudaError_t gemm_f32(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
                      int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc);
 
+// TMA-fed tcgen05 path (umma.cu): FP32 via 3xTF32; returns cudaErrorNotSupported for problems too small to pay off
+bool umma_available();
+cudaError_t gemm_f32_umma(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                          int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc);
+
+// FP64 through exact int8 slices on the tcgen05 INT8 pipe (Ozaki scheme); cudaErrorNotSupported when not applicable
+int ozaki_default_slices();
+cudaError_t gemm_f64_ozaki(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
+                           int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices);
+
 // ---- (a)/(b) elementwise sweeps ---------------------------------------------------------------------
 constexpr int kReduceBlocks = 1184;   // 148 SMs x 8 resident CTAs: partial-sum slots of the two-pass reductions
 

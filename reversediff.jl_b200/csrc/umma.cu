@@ -1,0 +1,621 @@
+// TMA-fed tcgen05 GEMM (sm_100a): the tensor-core path behind `*` instructions and their adjoints
+// (reference: mul! in src/derivatives/linalg/arithmetic.jl:245-255,272-285).
+//
+// One generic kernel: D(128 x 256 tile, TMEM accumulator) = sum over a list of K-segments of A_seg * B_seg^T, where every
+// operand slice is a K-major [rows][Kp] matrix reached through a 3-D TMA tensor map (k, row, slice).
+//   * warp 0 : TMA producer  (cp.async.bulk.tensor.3d, 128B swizzle, mbarrier complete_tx)
+//   * warp 1 : TMEM allocator + single-thread tcgen05.mma issuer (smem descriptors, tcgen05.commit -> mbarrier)
+//   * warps 2-5 : epilogue (tcgen05.ld 32x32b -> registers -> alpha/beta -> coalesced column-major stores)
+// Two instantiations:
+//   kind::tf32  FP32 tapes.  1xTF32 (10-bit mantissa) cannot hold the 1e-5 bound, so operands are split hi = RN_tf32(a),
+//               lo = a - hi and three segments (lo*hi, hi*lo, hi*hi) accumulate in one FP32 TMEM accumulator ("3xTF32").
+//   kind::i8    FP64 tapes, Ozaki-style exact slicing: each FP64 operand row is scaled by a power of two and cut into
+//               signed 7-bit slices; slice products accumulate EXACTLY in int32 TMEM accumulators; the epilogue rescales
+//               into the FP64 result.  tcgen05 has no f64 kind — this is how the FP64 GEMMs reach the tcgen05 pipe.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include "kernels.h"
+
+namespace rdb {
+namespace umma {
+
+constexpr int BM = 128, BN = 256, BKB = 128;          // tile rows / cols / K-bytes per stage (= one 128B swizzle atom)
+constexpr int STAGES = 4;
+constexpr int A_STAGE = BM * BKB, B_STAGE = BN * BKB;  // 16 KB + 32 KB
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 256;
+constexpr int MAX_SEG = 8;
+constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum Kind { KIND_TF32 = 0, KIND_I8 = 1 };
+
+struct Segs {
+    int n;
+    int sa[MAX_SEG], sb[MAX_SEG];
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == KIND_TF32) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+            "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+            "r"(accumulate)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms of 1024 B (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);         // start address      bits [0,14)
+    d |= (uint64_t)0 << 16;                          // leading byte offs  bits [16,30)  (one atom along K)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset bits [32,46)
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // layout type: SWIZZLE_128B
+    return d;
+}
+template <int KIND>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+    // c_format [4,6): 1 = F32, 2 = S32 ; a/b_format [7,10)/[10,13): TF32 = 2, signed int8 = 1 ; a/b major bits 15/16 = 0 (K-major)
+    // n_dim [17,23) = N >> 3 ; m_dim [24,29) = M >> 4
+    return (KIND == KIND_TF32 ? (1u << 4) | (2u << 7) | (2u << 10) : (2u << 4) | (1u << 7) | (1u << 10)) |
+           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------ epilogues
+struct EpiF32 {           // C = alpha*acc + beta*C   (FP32, column-major)
+    float *C;
+    int64_t ldc;
+    float alpha, beta;
+    using prev_t = float;
+    __device__ __forceinline__ float load(int row, int col) const { return beta != 0.f ? C[row + (int64_t)col * ldc] : 0.f; }
+    __device__ __forceinline__ void store(int row, int col, uint32_t raw, float prev) const {
+        C[row + (int64_t)col * ldc] = alpha * __uint_as_float(raw) + beta * prev;
+    }
+};
+// ------------------------------------------------------------------------------------------ the kernel
+template <int KIND, typename Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                 Segs segs, Epi epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // SWIZZLE_128B needs 1024B alignment
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + STAGES * A_STAGE;
+    uint64_t *full = (uint64_t *)(smem + STAGES * (A_STAGE + B_STAGE));
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_ptr = (uint32_t *)(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    constexpr int ELEMS = KIND == KIND_TF32 ? BKB / 4 : BKB;      // K elements per stage
+    constexpr int KSTEP = KIND == KIND_TF32 ? 8 : 32;              // K elements per tcgen05.mma (32 bytes)
+    const int kblocks = (K + ELEMS - 1) / ELEMS;
+    const int total = segs.n * kblocks;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < total; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], A_STAGE + B_STAGE);
+                const int seg = it / kblocks, kb = it - seg * kblocks;
+                tma_load_3d(sA + s * A_STAGE, &tmA, &full[s], kb * ELEMS, m0, segs.sa[seg]);
+                tma_load_3d(sB + s * B_STAGE, &tmB, &full[s], kb * ELEMS, n0, segs.sb[seg]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc<KIND>();
+            for (int it = 0; it < total; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t ad = make_smem_desc(smem_u32(sA + s * A_STAGE));
+                const uint64_t bd = make_smem_desc(smem_u32(sB + s * B_STAGE));
+#pragma unroll
+                for (int k = 0; k < ELEMS / KSTEP; ++k) {
+                    // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                    tc_mma<KIND>(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                tc_commit(&empty[s]);            // frees the smem stage when these MMAs retire
+            }
+            tc_commit(tmem_full);                // accumulator complete
+        }
+    } else {
+        // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+        const int q = warp & 3;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (row < M) {
+                // all 32 loads of the old C are issued before the first store (a load->store->load chain cost ~0.4 ms per GEMM)
+                typename Epi::prev_t prev[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = n0 + c0 + j;
+                    if (col < N) prev[j] = epi.load(row, col);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = n0 + c0 + j;
+                    if (col < N) epi.store(row, col, v[j], prev[j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// [slices][rows][Kp] K-major operand, element size es; box = (BKB/es, box_rows, 1), 128B swizzle
+static bool make_map(CUtensorMap *map, CUtensorMapDataType dt, int es, void *base, int64_t Kp, int64_t rows, int slices, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)slices};
+    cuuint64_t strides[2] = {(cuuint64_t)Kp * es, (cuuint64_t)Kp * es * rows};
+    cuuint32_t box[3] = {(cuuint32_t)(BKB / es), (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// grow-only device workspace (one device per process)
+static void *g_ws = nullptr;
+static size_t g_ws_bytes = 0;
+static void *workspace(size_t bytes) {
+    if (bytes > g_ws_bytes) {
+        if (g_ws) cudaFree(g_ws);
+        g_ws = nullptr;
+        g_ws_bytes = 0;
+        if (cudaMalloc(&g_ws, bytes) != cudaSuccess) return nullptr;
+        g_ws_bytes = bytes;
+    }
+    return g_ws;
+}
+
+// ------------------------------------------------------------------------------------------ 3xTF32 operand split
+// dst[0] = hi = RN_tf32(x), dst[1] = lo = x - hi, both [rows][Kp] with k contiguous (zero padded to Kp).
+// KMAJOR source: element (r,k) at src[k + r*ld]; otherwise at src[r + k*ld] (transposed through shared memory).
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+template <bool KMAJOR>
+__global__ void __launch_bounds__(256) k_split_tf32(float *__restrict__ dst, const float *__restrict__ src, int64_t ld, int rows,
+                                                    int K, int Kp) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    const int64_t plane = (int64_t)rows * Kp;
+    if (KMAJOR) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            int r = r0 + ty + i, k = k0 + tx;
+            if (r < rows && k < Kp) {
+                float x = k < K ? src[k + (int64_t)r * ld] : 0.f;
+                float hi = tf32_rn(x);
+                dst[(int64_t)r * Kp + k] = hi;
+                dst[plane + (int64_t)r * Kp + k] = x - hi;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            int k = k0 + ty + i, r = r0 + tx;
+            tile[ty + i][tx] = (r < rows && k < K) ? src[r + (int64_t)k * ld] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            int r = r0 + ty + i, k = k0 + tx;
+            if (r < rows && k < Kp) {
+                float x = tile[tx][ty + i];
+                float hi = tf32_rn(x);
+                dst[(int64_t)r * Kp + k] = hi;
+                dst[plane + (int64_t)r * Kp + k] = x - hi;
+            }
+        }
+    }
+}
+
+
+// ==================================================================================================
+// FP64 on the tcgen05 INT8 pipe: Ozaki-style error-free slicing
+// ==================================================================================================
+// op(A)(i,k) = 2^ea[i] * sum_p qa_p(i,k) 2^(-7(p+1)) + O(2^(ea[i]-7s-1)),  qa_p in [-64,64] (signed 7-bit slices), same for
+// the columns of op(B).  Slice products are summed EXACTLY in int32 (K*(d+1)*2^12 < 2^31), grouped by d = p+q:
+//     C(i,j) = 2^(ea[i]+eb[j]) * sum_d 2^(-7(d+2)) * D_d(i,j),   D_d = sum_{p+q=d} Qa_p * Qb_q^T   (int32)
+// Groups are processed from the smallest magnitude (d = s-1) to the largest (d = 0); each group is one accumulation chain in
+// one of two TMEM buffers, and the epilogue of group d (FP64 read-modify-write of the C tile, L2 resident) overlaps the MMAs of
+// the next group.  Only pairs with p+q <= s-1 are formed: the dropped ones are below the slicing truncation.
+constexpr int OZ_MAX_SLICES = 10;
+
+// ---- pass 1: per-row binary exponent e = ilogb(max_k |x|) + 2  (so |x| 2^-e <= 0.5), stored as int; scale 2^e as double
+template <bool KMAJOR>
+__global__ void __launch_bounds__(256) k_row_exponent(const double *__restrict__ src, int64_t ld, int rows, int K, int *__restrict__ e_out,
+                                                      double *__restrict__ scale_out) {
+    if (KMAJOR) {                               // one warp per row, k contiguous
+        int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+        if (r >= rows) return;
+        const double *p = src + (int64_t)r * ld;
+        double mx = 0.0;
+        for (int k = lane; k < K; k += 32) mx = fmax(mx, fabs(p[k]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) {
+            int e = mx > 0.0 ? ilogb(mx) + 2 : 0;
+            e_out[r] = e;
+            scale_out[r] = scalbn(1.0, e);
+        }
+    } else {                                    // one thread per row, rows contiguous: coalesced over threads
+        int r = blockIdx.x * 256 + threadIdx.x;
+        if (r >= rows) return;
+        double mx = 0.0;
+        for (int k = 0; k < K; ++k) mx = fmax(mx, fabs(src[r + (int64_t)k * ld]));
+        int e = mx > 0.0 ? ilogb(mx) + 2 : 0;
+        e_out[r] = e;
+        scale_out[r] = scalbn(1.0, e);
+    }
+}
+
+// ---- pass 2: slices.  dst is [s][rows][Kp] int8, k contiguous.  Block = 32 rows x 128 k; thread = 1 row x 4 consecutive k per
+// iteration, so every slice store is one packed 32-bit word and a warp writes 128 contiguous bytes of one row.
+template <bool KMAJOR>
+__global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, const double *__restrict__ src, int64_t ld, int rows, int K,
+                                                  int Kp, int nslices, const int *__restrict__ e_in) {
+    __shared__ double tile[KMAJOR ? 1 : 128][KMAJOR ? 1 : 33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 128;
+    if (!KMAJOR) {
+        // tile[k][r] <- src[(r0+r) + (k0+k)*ld], lanes along r (coalesced)
+        for (int k = w; k < 128; k += 8) {
+            int r = r0 + lane, kk = k0 + k;
+            tile[k][lane] = (r < rows && kk < K) ? src[r + (int64_t)kk * ld] : 0.0;
+        }
+        __syncthreads();
+    }
+    const int64_t plane = (int64_t)rows * Kp;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const int rl = w + 8 * i, r = r0 + rl, k = k0 + 4 * lane;
+        if (r >= rows || k >= Kp) continue;
+        const int e = e_in[r];
+        double x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double v;
+            if (KMAJOR) v = (k + j < K) ? src[(int64_t)r * ld + k + j] : 0.0;
+            else v = tile[4 * lane + j][rl];
+            x[j] = scalbn(v, -e);                                  // |x| <= 0.5, exact
+        }
+        for (int sidx = 0; sidx < nslices; ++sidx) {
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double t = x[j] * 128.0;                           // exact
+                double q = rint(t);                                // |q| <= 64
+                x[j] = t - q;                                      // exact remainder in [-0.5, 0.5]
+                packed |= ((uint32_t)(uint8_t)(int8_t)(int)q) << (8 * j);
+            }
+            *reinterpret_cast<uint32_t *>(dst + sidx * plane + (int64_t)r * Kp + k) = packed;
+        }
+    }
+}
+
+struct OzParams {
+    double *C;
+    int64_t ldc;
+    double alpha, beta;
+    const double *sa, *sb;      // 2^ea[row], 2^eb[col]
+    int nslices;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+umma_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, OzParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + STAGES * A_STAGE;
+    uint64_t *full = (uint64_t *)(smem + STAGES * (A_STAGE + B_STAGE));
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;      // [2]
+    uint64_t *tmem_empty = tmem_full + 2;      // [2]
+    uint32_t *tmem_ptr = (uint32_t *)(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kblocks = (K + BKB - 1) / BKB;
+    const int S = P.nslices;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int d = S - 1; d >= 0; --d)
+                for (int p = 0; p <= d; ++p)
+                    for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_expect_tx(&full[s], A_STAGE + B_STAGE);
+                        tma_load_3d(sA + s * A_STAGE, &tmA, &full[s], kb * BKB, m0, p);
+                        tma_load_3d(sB + s * B_STAGE, &tmB, &full[s], kb * BKB, n0, d - p);
+                    }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc<KIND_I8>();
+            int it = 0, gi = 0;
+            for (int d = S - 1; d >= 0; --d, ++gi) {
+                const int buf = gi & 1;
+                mbar_wait(&tmem_empty[buf], ((gi >> 1) & 1) ^ 1);          // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                const int iters = (d + 1) * kblocks;
+                for (int j = 0; j < iters; ++j, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint64_t ad = make_smem_desc(smem_u32(sA + s * A_STAGE));
+                    const uint64_t bd = make_smem_desc(smem_u32(sB + s * B_STAGE));
+#pragma unroll
+                    for (int k = 0; k < BKB / 32; ++k) tc_mma<KIND_I8>(acc, ad + 2 * k, bd + 2 * k, idesc, (j > 0 || k > 0) ? 1u : 0u);
+                    tc_commit(&empty[s]);
+                }
+                tc_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        const double sa = row < M ? P.sa[row] : 0.0;
+        int gi = 0;
+        for (int d = S - 1; d >= 0; --d, ++gi) {
+            const int buf = gi & 1;
+            mbar_wait(&tmem_full[buf], (gi >> 1) & 1);
+            tc_fence_after();
+            const double rs = P.alpha * sa * scalbn(1.0, -7 * (d + 2));     // alpha * 2^(ea[row] - 7(d+2))
+            const bool first = gi == 0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+                if (row < M) {
+                    double prev[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = n0 + c0 + j;
+                        prev[j] = 0.0;
+                        if (col < N && !(first && P.beta == 0.0)) prev[j] = P.C[row + (int64_t)col * P.ldc];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = n0 + c0 + j;
+                        if (col < N) {
+                            double t = (double)(int)v[j] * rs * P.sb[col];
+                            P.C[row + (int64_t)col * P.ldc] = (first ? P.beta * prev[j] : prev[j]) + t;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+}  // namespace umma
+
+bool umma_available() { return umma::encode_fn() != nullptr; }
+
+// C(MxN) <- alpha*op(A)*op(B) + beta*C in FP32 via 3xTF32 on tcgen05.  Returns cudaErrorNotSupported when the problem is
+// too small to be worth it (caller uses the SIMT kernel).
+cudaError_t gemm_f32_umma(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                          int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc) {
+    using namespace umma;
+    if (M < 128 || N < 128 || K < 32 || !umma_available()) return cudaErrorNotSupported;
+    const int64_t Kp = (K + 3) & ~3LL;                       // 16-byte rows for TMA
+    const size_t a_bytes = (size_t)2 * M * Kp * 4, b_bytes = (size_t)2 * N * Kp * 4;
+    uint8_t *ws = (uint8_t *)workspace(((a_bytes + 255) & ~(size_t)255) + b_bytes);
+    if (!ws) return cudaErrorMemoryAllocation;
+    float *As = (float *)ws, *Bs = (float *)(ws + ((a_bytes + 255) & ~(size_t)255));
+    // op(A) is MxK: ta => stored KxM (k contiguous per row m) => KMAJOR source.  op(B)^T rows are n: !tb => stored KxN => KMAJOR.
+    dim3 ga((unsigned)((Kp + 31) / 32), (unsigned)((M + 31) / 32)), gb((unsigned)((Kp + 31) / 32), (unsigned)((N + 31) / 32));
+    if (ta) k_split_tf32<true><<<ga, 256, 0, st>>>(As, A, lda, (int)M, (int)K, (int)Kp);
+    else k_split_tf32<false><<<ga, 256, 0, st>>>(As, A, lda, (int)M, (int)K, (int)Kp);
+    if (!tb) k_split_tf32<true><<<gb, 256, 0, st>>>(Bs, B, ldb, (int)N, (int)K, (int)Kp);
+    else k_split_tf32<false><<<gb, 256, 0, st>>>(Bs, B, ldb, (int)N, (int)K, (int)Kp);
+    CUtensorMap mA, mB;
+    if (!make_map(&mA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, As, Kp, M, 2, BM) ||
+        !make_map(&mB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Bs, Kp, N, 2, BN))
+        return cudaErrorInvalidValue;
+    Segs segs;
+    segs.n = 3;                      // small terms first: lo*hi, hi*lo, then hi*hi
+    segs.sa[0] = 1; segs.sb[0] = 0;
+    segs.sa[1] = 0; segs.sb[1] = 1;
+    segs.sa[2] = 0; segs.sb[2] = 0;
+    EpiF32 epi{C, ldc, alpha, beta};
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<KIND_TF32, EpiF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
+    umma_gemm_kernel<KIND_TF32, EpiF32><<<grid, THREADS, SMEM_BYTES, st>>>(mA, mB, (int)M, (int)N, (int)Kp, segs, epi);
+    return cudaGetLastError();
+}
+
+
+int ozaki_default_slices() {
+    static int n = -1;
+    if (n < 0) {
+        const char *e = getenv("RDB_OZAKI_SLICES");
+        n = e ? atoi(e) : 8;
+        if (n < 2) n = 2;
+        if (n > umma::OZ_MAX_SLICES) n = umma::OZ_MAX_SLICES;
+    }
+    return n;
+}
+
+// C(MxN) <- alpha*op(A)*op(B) + beta*C in FP64 through exact int8 slices on tcgen05 (see the comment block above).
+cudaError_t gemm_f64_ozaki(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
+                           int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices) {
+    using namespace umma;
+    // int32 exactness: (d+1)*K*2^12 < 2^31 for d <= nslices-1
+    if (M < 256 || N < 256 || K < 256 || K * (int64_t)nslices > (1 << 19) - 1 || !umma_available()) return cudaErrorNotSupported;
+    const int64_t Kp = (K + 15) & ~15LL;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t a_bytes = al((size_t)nslices * M * Kp), b_bytes = al((size_t)nslices * N * Kp);
+    const size_t ea_bytes = al(M * 4), eb_bytes = al(N * 4), sa_bytes = al(M * 8), sb_bytes = al(N * 8);
+    uint8_t *ws = (uint8_t *)workspace(a_bytes + b_bytes + ea_bytes + eb_bytes + sa_bytes + sb_bytes);
+    if (!ws) return cudaErrorMemoryAllocation;
+    int8_t *As = (int8_t *)ws, *Bs = (int8_t *)(ws + a_bytes);
+    int *ea = (int *)(ws + a_bytes + b_bytes), *eb = (int *)(ws + a_bytes + b_bytes + ea_bytes);
+    double *sa = (double *)(ws + a_bytes + b_bytes + ea_bytes + eb_bytes);
+    double *sb = (double *)(ws + a_bytes + b_bytes + ea_bytes + eb_bytes + sa_bytes);
+    // rows of op(A) are m: ta => stored KxM, k contiguous per m => KMAJOR.  rows of op(B)^T are n: !tb => stored KxN => KMAJOR.
+    if (ta) k_row_exponent<true><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(A, lda, (int)M, (int)K, ea, sa);
+    else k_row_exponent<false><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(A, lda, (int)M, (int)K, ea, sa);
+    if (!tb) k_row_exponent<true><<<(unsigned)((N + 7) / 8), 256, 0, st>>>(B, ldb, (int)N, (int)K, eb, sb);
+    else k_row_exponent<false><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(B, ldb, (int)N, (int)K, eb, sb);
+    dim3 ga((unsigned)((Kp + 127) / 128), (unsigned)((M + 31) / 32)), gb((unsigned)((Kp + 127) / 128), (unsigned)((N + 31) / 32));
+    if (ta) k_slice_i8<true><<<ga, 256, 0, st>>>(As, A, lda, (int)M, (int)K, (int)Kp, nslices, ea);
+    else k_slice_i8<false><<<ga, 256, 0, st>>>(As, A, lda, (int)M, (int)K, (int)Kp, nslices, ea);
+    if (!tb) k_slice_i8<true><<<gb, 256, 0, st>>>(Bs, B, ldb, (int)N, (int)K, (int)Kp, nslices, eb);
+    else k_slice_i8<false><<<gb, 256, 0, st>>>(Bs, B, ldb, (int)N, (int)K, (int)Kp, nslices, eb);
+    CUtensorMap mA, mB;
+    if (!make_map(&mA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM) ||
+        !make_map(&mB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN))
+        return cudaErrorInvalidValue;
+    OzParams P{C, ldc, alpha, beta, sa, sb, nslices};
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(umma_ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
+    umma_ozaki_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mA, mB, (int)M, (int)N, (int)Kp, P);
+    return cudaGetLastError();
+}
+
+}  // namespace rdb

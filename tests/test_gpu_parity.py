@@ -1,6 +1,8 @@
 """GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same seeded
 inputs.  Tolerances are the north star's: 1e-12 (FP64) / 1e-5 (FP32), relative to max|.| of each result array.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -66,7 +68,9 @@ def test_gemm_kernel(rd, ctx, dtype, ta, tb, m, n, k):
         ref = alpha * (opA.astype(np.float64) @ opB.astype(np.float64)) + beta * C0.astype(np.float64)
         scale = np.abs(opA).astype(np.float64) @ np.abs(opB).astype(np.float64) + np.abs(C0) * abs(beta)
         err = np.max(np.abs(got - ref) / np.maximum(scale, 1e-300))
-        assert err < (1e-14 if dtype == np.float64 else 2e-6), (alpha, beta, err)
+        # RDB_F64_GEMM=ozaki routes large FP64 GEMMs through exact int8 slices on tcgen05: truncation 2^-7s instead of 2^-53
+        f64_tol = 2e-13 if os.environ.get("RDB_F64_GEMM", "").startswith("o") else 1e-14
+        assert err < (f64_tol if dtype == np.float64 else 2e-6), (alpha, beta, err)
     _ = tdt
 
 
