@@ -241,15 +241,17 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 // [slices][rows][Kp] K-major operand, element size es; box = (BKB/es, box_rows, 1), 128B swizzle
-static bool make_map(CUtensorMap *map, CUtensorMapDataType dt, int es, void *base, int64_t Kp, int64_t rows, int slices, int box_rows) {
+static bool make_map(CUtensorMap *map, CUtensorMapDataType dt, int es, void *base, int64_t Kp, int64_t rows, int slices, int box_rows,
+                     int box_k_bytes = BKB, int box_slices = 1) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)slices};
     cuuint64_t strides[2] = {(cuuint64_t)Kp * es, (cuuint64_t)Kp * es * rows};
-    cuuint32_t box[3] = {(cuuint32_t)(BKB / es), (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)(box_k_bytes / es), (cuuint32_t)box_rows, (cuuint32_t)box_slices};
     cuuint32_t estr[3] = {1, 1, 1};
-    return fn(map, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return fn(map, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              box_k_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // grow-only device workspace (one device per process)
@@ -324,10 +326,11 @@ __global__ void __launch_bounds__(256) k_split_tf32(float *__restrict__ dst, con
 // the next group.  Only pairs with p+q <= s-1 are formed: the dropped ones are below the slicing truncation.
 constexpr int OZ_MAX_SLICES = 10;
 
-// ---- pass 1: per-row binary exponent e = ilogb(max_k |x|) + 2  (so |x| 2^-e <= 0.5), stored as int; scale 2^e as double
+// ---- pass 1: per-row max |x| (bit pattern of a non-negative double orders like an unsigned integer), then the binary
+// exponent e = ilogb(max) + 2 (so |x| 2^-e <= 0.5) and the scale 2^e
 template <bool KMAJOR>
-__global__ void __launch_bounds__(256) k_row_exponent(const double *__restrict__ src, int64_t ld, int rows, int K, int *__restrict__ e_out,
-                                                      double *__restrict__ scale_out) {
+__global__ void __launch_bounds__(256) k_row_absmax(const double *__restrict__ src, int64_t ld, int rows, int K,
+                                                    unsigned long long *__restrict__ mx_bits) {
     if (KMAJOR) {                               // one warp per row, k contiguous
         int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
         if (r >= rows) return;
@@ -336,20 +339,25 @@ __global__ void __launch_bounds__(256) k_row_exponent(const double *__restrict__
         for (int k = lane; k < K; k += 32) mx = fmax(mx, fabs(p[k]));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) {
-            int e = mx > 0.0 ? ilogb(mx) + 2 : 0;
-            e_out[r] = e;
-            scale_out[r] = scalbn(1.0, e);
-        }
-    } else {                                    // one thread per row, rows contiguous: coalesced over threads
+        if (lane == 0) mx_bits[r] = (unsigned long long)__double_as_longlong(mx);
+    } else {                                    // threads along rows (coalesced), blockIdx.y splits K into chunks of 64
         int r = blockIdx.x * 256 + threadIdx.x;
         if (r >= rows) return;
+        int k0 = blockIdx.y * 64, k1 = min(K, k0 + 64);
         double mx = 0.0;
-        for (int k = 0; k < K; ++k) mx = fmax(mx, fabs(src[r + (int64_t)k * ld]));
-        int e = mx > 0.0 ? ilogb(mx) + 2 : 0;
-        e_out[r] = e;
-        scale_out[r] = scalbn(1.0, e);
+#pragma unroll 8
+        for (int k = k0; k < k1; ++k) mx = fmax(mx, fabs(src[r + (int64_t)k * ld]));
+        atomicMax(mx_bits + r, (unsigned long long)__double_as_longlong(mx));
     }
+}
+__global__ void __launch_bounds__(256) k_row_exponent(const unsigned long long *__restrict__ mx_bits, int rows, int *__restrict__ e_out,
+                                                      double *__restrict__ scale_out) {
+    int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= rows) return;
+    double mx = __longlong_as_double((long long)mx_bits[r]);
+    int e = (mx > 0.0 && isfinite(mx)) ? ilogb(mx) + 2 : 0;
+    e_out[r] = e;
+    scale_out[r] = scalbn(1.0, e);
 }
 
 // ---- pass 2: slices.  dst is [s][rows][Kp] int8, k contiguous.  Block = 32 rows x 128 k; thread = 1 row x 4 consecutive k per
@@ -522,6 +530,145 @@ umma_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+
+// --------------------------------------------------------------------------------------------------
+// Second generation: every loaded slice is reused for ALL of its pairs.  Tile 128 x 64, one TMEM accumulator per slice-sum d
+// (S x 64 columns <= 512), K-blocks of 64 bytes (64B swizzle).  One stage = all S slices of the A tile and of the B tile for one
+// K-block (S*(8 KB + 4 KB)); the MMA thread then issues the S(S+1)/2 pair products on it.  L2->SM traffic per MAC drops 2.25x
+// against the pair-at-a-time kernel above (which ncu/timing showed L2-bound), and the FP64 result is assembled in registers and
+// written ONCE instead of read-modify-written per group.
+namespace oz2 {
+constexpr int BM2 = 128, BN2 = 64, BKB2 = 64, STAGES2 = 2;
+constexpr int A_SLICE = BM2 * BKB2, B_SLICE = BN2 * BKB2;      // 8 KB, 4 KB
+__host__ __device__ constexpr int stage_bytes(int S) { return S * (A_SLICE + B_SLICE); }
+__host__ __device__ constexpr int smem_bytes(int S) { return STAGES2 * stage_bytes(S) + 1024 + 256; }
+
+// K-major, 64B-swizzled tile: rows of 64 bytes, 8-row atoms of 512 B
+__device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(512 >> 4) << 32;                 // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                          // descriptor version
+    d |= (uint64_t)4 << 61;                          // layout type: SWIZZLE_64B
+    return d;
+}
+__device__ __forceinline__ constexpr uint32_t make_idesc_i8(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
+}
+
+template <int S>
+__global__ void __launch_bounds__(THREADS, 1)
+umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, OzParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int STAGE = stage_bytes(S);
+    uint64_t *full = (uint64_t *)(smem + STAGES2 * STAGE);
+    uint64_t *empty = full + STAGES2;
+    uint64_t *tmem_full = empty + STAGES2;
+    uint32_t *tmem_ptr = (uint32_t *)(tmem_full + 1);
+    constexpr int TCOLS = S * BN2 <= 32 ? 32 : S * BN2 <= 64 ? 64 : S * BN2 <= 128 ? 128 : S * BN2 <= 256 ? 256 : 512;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM2, n0 = blockIdx.y * BN2;
+    const int kblocks = (K + BKB2 - 1) / BKB2;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % STAGES2;
+                const uint32_t ph = (kb / STAGES2) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], STAGE);
+                // one 3-D box per operand: (64 bytes of k) x rows x all S slices
+                tma_load_3d(smem + s * STAGE, &tmA, &full[s], kb * BKB2, m0, 0);
+                tma_load_3d(smem + s * STAGE + S * A_SLICE, &tmB, &full[s], kb * BKB2, n0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % STAGES2;
+                const uint32_t ph = (kb / STAGES2) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(smem + s * STAGE), b0 = a0 + S * A_SLICE;
+                // For a fixed A slice p the partner slices q = 0..S-1-p are CONTIGUOUS rows of the B stage ([slice][64 rows]) and
+                // their accumulators d = p+q are CONTIGUOUS TMEM column blocks, so up to four pairs go out as ONE MMA with
+                // N = 64*(#q) <= 256: A is read from shared memory once per four pairs (N=64 MMAs were smem-read bound).
+#pragma unroll
+                for (int p = 0; p < S; ++p) {
+                    const uint64_t ad = make_desc64(a0 + p * A_SLICE);
+#pragma unroll
+                    for (int q0 = 0; q0 < S - p; q0 += 4) {
+                        const int nq = (S - p - q0) < 4 ? (S - p - q0) : 4;
+                        const uint64_t bd = make_desc64(b0 + q0 * B_SLICE);
+                        const uint32_t acc = tmem_base + (uint32_t)((p + q0) * BN2);
+                        const uint32_t idesc = make_idesc_i8(nq * BN2);
+#pragma unroll
+                        for (int k = 0; k < BKB2 / 32; ++k)
+                            tc_mma<KIND_I8>(acc, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || p > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(&empty[s]);
+            }
+            tc_commit(tmem_full);
+        }
+    } else {
+        const int q4 = warp & 3;
+        const int row = m0 + q4 * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const double rs = row < M ? P.alpha * P.sa[row] : 0.0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN2; c0 += 32) {
+            double sum[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[j] = 0.0;
+#pragma unroll 1
+            for (int d = S - 1; d >= 0; --d) {                          // smallest terms first
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(d * BN2 + c0), v);
+                const double w = scalbn(1.0, -7 * (d + 2));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[j] += (double)(int)v[j] * w;      // exact products, FP64 adds
+            }
+            if (row < M) {
+                double prev[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = n0 + c0 + j;
+                    prev[j] = (col < N && P.beta != 0.0) ? P.C[row + (int64_t)col * P.ldc] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = n0 + c0 + j;
+                    if (col < N) P.C[row + (int64_t)col * P.ldc] = P.beta * prev[j] + sum[j] * (rs * P.sb[col]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
+    }
+}
+}  // namespace oz2
+
 }  // namespace umma
 
 bool umma_available() { return umma::encode_fn() != nullptr; }
@@ -593,20 +740,51 @@ cudaError_t gemm_f64_ozaki(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t
     double *sa = (double *)(ws + a_bytes + b_bytes + ea_bytes + eb_bytes);
     double *sb = (double *)(ws + a_bytes + b_bytes + ea_bytes + eb_bytes + sa_bytes);
     // rows of op(A) are m: ta => stored KxM, k contiguous per m => KMAJOR.  rows of op(B)^T are n: !tb => stored KxN => KMAJOR.
-    if (ta) k_row_exponent<true><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(A, lda, (int)M, (int)K, ea, sa);
-    else k_row_exponent<false><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(A, lda, (int)M, (int)K, ea, sa);
-    if (!tb) k_row_exponent<true><<<(unsigned)((N + 7) / 8), 256, 0, st>>>(B, ldb, (int)N, (int)K, eb, sb);
-    else k_row_exponent<false><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(B, ldb, (int)N, (int)K, eb, sb);
+    unsigned long long *mxa = (unsigned long long *)sa, *mxb = (unsigned long long *)sb;    // scale arrays double as max scratch
+    if (ta) k_row_absmax<true><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(A, lda, (int)M, (int)K, mxa);
+    else {
+        cudaMemsetAsync(mxa, 0, M * 8, st);
+        k_row_absmax<false><<<dim3((unsigned)((M + 255) / 256), (unsigned)((K + 63) / 64)), 256, 0, st>>>(A, lda, (int)M, (int)K, mxa);
+    }
+    if (!tb) k_row_absmax<true><<<(unsigned)((N + 7) / 8), 256, 0, st>>>(B, ldb, (int)N, (int)K, mxb);
+    else {
+        cudaMemsetAsync(mxb, 0, N * 8, st);
+        k_row_absmax<false><<<dim3((unsigned)((N + 255) / 256), (unsigned)((K + 63) / 64)), 256, 0, st>>>(B, ldb, (int)N, (int)K, mxb);
+    }
+    k_row_exponent<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(mxa, (int)M, ea, sa);
+    k_row_exponent<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(mxb, (int)N, eb, sb);
     dim3 ga((unsigned)((Kp + 127) / 128), (unsigned)((M + 31) / 32)), gb((unsigned)((Kp + 127) / 128), (unsigned)((N + 31) / 32));
     if (ta) k_slice_i8<true><<<ga, 256, 0, st>>>(As, A, lda, (int)M, (int)K, (int)Kp, nslices, ea);
     else k_slice_i8<false><<<ga, 256, 0, st>>>(As, A, lda, (int)M, (int)K, (int)Kp, nslices, ea);
     if (!tb) k_slice_i8<true><<<gb, 256, 0, st>>>(Bs, B, ldb, (int)N, (int)K, (int)Kp, nslices, eb);
     else k_slice_i8<false><<<gb, 256, 0, st>>>(Bs, B, ldb, (int)N, (int)K, (int)Kp, nslices, eb);
     CUtensorMap mA, mB;
+    OzParams P{C, ldc, alpha, beta, sa, sb, nslices};
+    static int gen = -1;
+    if (gen < 0) { const char *e = getenv("RDB_OZAKI_GEN"); gen = e ? atoi(e) : 2; }
+    if (gen == 2 && nslices <= 8) {
+        using namespace oz2;
+        if (!make_map(&mA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, BKB2, nslices) ||
+            !make_map(&mB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2, BKB2, nslices))
+            return cudaErrorInvalidValue;
+        dim3 grid2((unsigned)((M + BM2 - 1) / BM2), (unsigned)((N + BN2 - 1) / BN2));
+#define RDB_OZ2(SS)                                                                                                        \
+    case SS: {                                                                                                             \
+        static bool attr2 = false;                                                                                         \
+        if (!attr2) {                                                                                                      \
+            cudaError_t e = cudaFuncSetAttribute(umma_ozaki2_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(SS)); \
+            if (e != cudaSuccess) return e;                                                                                \
+            attr2 = true;                                                                                                  \
+        }                                                                                                                  \
+        umma_ozaki2_kernel<SS><<<grid2, THREADS, smem_bytes(SS), st>>>(mA, mB, (int)M, (int)N, (int)Kp, P);               \
+    } break;
+        switch (nslices) { RDB_OZ2(2) RDB_OZ2(3) RDB_OZ2(4) RDB_OZ2(5) RDB_OZ2(6) RDB_OZ2(7) RDB_OZ2(8) default: return cudaErrorInvalidValue; }
+#undef RDB_OZ2
+        return cudaGetLastError();
+    }
     if (!make_map(&mA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM) ||
         !make_map(&mB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN))
         return cudaErrorInvalidValue;
-    OzParams P{C, ldc, alpha, beta, sa, sb, nslices};
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(umma_ozaki_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
