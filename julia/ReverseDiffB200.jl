@@ -21,9 +21,12 @@ struct RdbOptions
     seed_block::Int32
     use_graph::Int32
     profile::Int32
-    reserved::NTuple{4,Int32}
+    gemm_f64_mode::Int32
+    ozaki_slices::Int32
+    reserved::NTuple{2,Int32}
 end
-RdbOptions(; fuse=1, seed_block=0, graph=1, profile=0) = RdbOptions(fuse, seed_block, graph, profile, (0, 0, 0, 0))
+RdbOptions(; fuse=1, seed_block=0, graph=1, profile=0, gemm_f64_mode=0, ozaki_slices=0) =
+    RdbOptions(fuse, seed_block, graph, profile, gemm_f64_mode, ozaki_slices, (0, 0))
 
 last_error() = unsafe_string(ccall((:rdb_last_error, LIB), Cstring, ()))
 check(rc) = rc == 0 ? nothing : error("librdb200: ", last_error())

@@ -53,6 +53,7 @@ struct rdb_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     int refs = 1;          // the handle itself + one per live tape: destruction order is the caller's business
+    int gemm_f64_mode = 0, ozaki_slices = 0;   // for rdb_gemm on this context
 };
 static void ctx_release(rdb_ctx *c) {
     if (!c || --c->refs > 0) return;
@@ -162,13 +163,14 @@ struct StepTimer {
 };
 
 // ------------------------------------------------------------------------------------------ typed ops
+static thread_local int g_f64_mode = 0, g_f64_slices = 0;   // set from the tape's options around each API call
 template <typename T>
 static cudaError_t gemm_t(cudaStream_t s, bool ta, bool tb, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t lda,
                           const T *B, int64_t ldb, T beta, T *C, int64_t ldc);
 template <>
 cudaError_t gemm_t<double>(cudaStream_t s, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
                            int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc) {
-    return gemm_f64(s, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    return gemm_f64(s, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, g_f64_mode, g_f64_slices);
 }
 template <>
 cudaError_t gemm_t<float>(cudaStream_t s, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
@@ -976,7 +978,9 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
 }
 
 // ================================================================================================ C ABI
-#define DISPATCH(t, fn, ...) ((t)->dtype == RDB_F64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+#define DISPATCH(t, fn, ...) \
+    (g_f64_mode = (t)->opts.gemm_f64_mode, g_f64_slices = (t)->opts.ozaki_slices, \
+     (t)->dtype == RDB_F64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
 
 extern "C" {
 
@@ -1003,6 +1007,13 @@ int rdb_ctx_set_stream(rdb_ctx *c, void *stream) {
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     c->stream = (cudaStream_t)stream;
     c->own_stream = false;
+    return RDB_OK;
+}
+int rdb_ctx_set_gemm_f64_mode(rdb_ctx *c, int mode, int slices) {
+    if (!c) return fail(RDB_EINVAL, "null context");
+    if (mode < 0 || mode > 2 || slices < 0 || slices > 8) return fail(RDB_EINVAL, "bad gemm_f64_mode/slices");
+    c->gemm_f64_mode = mode;
+    c->ozaki_slices = slices;
     return RDB_OK;
 }
 int rdb_ctx_synchronize(rdb_ctx *c) {
@@ -1104,7 +1115,8 @@ int rdb_gemm(rdb_ctx *c, int dtype, int ta, int tb, int64_t m, int64_t n, int64_
              const void *B, int64_t ldb, double beta, void *C, int64_t ldc) {
     if (!c) return fail(RDB_EINVAL, "null context");
     cudaError_t e = dtype == RDB_F64
-                        ? gemm_f64(c->stream, ta != 0, tb != 0, m, n, k, alpha, (const double *)A, lda, (const double *)B, ldb, beta, (double *)C, ldc)
+                        ? gemm_f64(c->stream, ta != 0, tb != 0, m, n, k, alpha, (const double *)A, lda, (const double *)B, ldb, beta, (double *)C, ldc,
+                                   c->gemm_f64_mode, c->ozaki_slices)
                         : gemm_f32(c->stream, ta != 0, tb != 0, m, n, k, (float)alpha, (const float *)A, lda, (const float *)B, ldb, (float)beta, (float *)C, ldc);
     if (e != cudaSuccess) return fail(RDB_ECUDA, "gemm launch failed: %s", cudaGetErrorString(e));
     return RDB_OK;

@@ -363,14 +363,17 @@ static cudaError_t launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, doub
 }
 }  // namespace d64
 
+// mode: 0 = auto (exact int8 slices on tcgen05 when the shape is eligible, DMMA otherwise), 1 = DMMA only, 2 = same as auto.
+// RDB_F64_GEMM=dmma|ozaki overrides (experiments / A-B timing).
 cudaError_t gemm_f64(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
-                     int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc) {
+                     int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int mode, int slices) {
     if (M <= 0 || N <= 0) return cudaSuccess;
     if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return cudaErrorInvalidValue;
-    static int use_ozaki = -1;
-    if (use_ozaki < 0) { const char *e = getenv("RDB_F64_GEMM"); use_ozaki = (e && e[0] == 'o') ? 1 : 0; }
-    if (use_ozaki) {
-        cudaError_t e = gemm_f64_ozaki(st, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, ozaki_default_slices());
+    static int env_mode = -1;
+    if (env_mode < 0) { const char *e = getenv("RDB_F64_GEMM"); env_mode = !e ? 0 : (e[0] == 'd' ? 1 : (e[0] == 'o' ? 2 : 0)); }
+    if (env_mode) mode = env_mode;
+    if (mode != 1) {
+        cudaError_t e = gemm_f64_ozaki(st, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, slices > 0 ? slices : ozaki_default_slices());
         if (e != cudaErrorNotSupported) return e;
     }
     if (!ta && !tb) return d64::launch<false, false>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);

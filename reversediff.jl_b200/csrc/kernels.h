@@ -9,7 +9,7 @@ namespace rdb {
 
 // ---- (c) dense contractions -------------------------------------------------------------------------
 cudaError_t gemm_f64(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
-                     int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc);
+                     int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int mode = 0, int slices = 0);
 cudaError_t gemm_f32(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
                      int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc);
 

@@ -250,7 +250,8 @@ static bool make_map(CUtensorMap *map, CUtensorMapDataType dt, int es, void *bas
     cuuint32_t box[3] = {(cuuint32_t)(box_k_bytes / es), (cuuint32_t)box_rows, (cuuint32_t)box_slices};
     cuuint32_t estr[3] = {1, 1, 1};
     return fn(map, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              box_k_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              box_k_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_k_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -538,30 +539,33 @@ umma_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // against the pair-at-a-time kernel above (which ncu/timing showed L2-bound), and the FP64 result is assembled in registers and
 // written ONCE instead of read-modify-written per group.
 namespace oz2 {
-constexpr int BM2 = 128, BN2 = 64, BKB2 = 64, STAGES2 = 2;
-constexpr int A_SLICE = BM2 * BKB2, B_SLICE = BN2 * BKB2;      // 8 KB, 4 KB
-__host__ __device__ constexpr int stage_bytes(int S) { return S * (A_SLICE + B_SLICE); }
-__host__ __device__ constexpr int smem_bytes(int S) { return STAGES2 * stage_bytes(S) + 1024 + 256; }
+constexpr int BM2 = 128, BN2 = 64;
+// KB = K bytes per stage: 64 (64B swizzle, 2 stages at S = 8) or 32 (32B swizzle, 4 stages: a deeper ring hides the TMA latency
+// that a 2-deep ring of 96 KB stages exposed)
+__host__ __device__ constexpr int stages_for(int KB) { return KB == 64 ? 2 : 4; }
+__host__ __device__ constexpr int stage_bytes(int S, int KB) { return S * (BM2 + BN2) * KB; }
+__host__ __device__ constexpr int smem_bytes(int S, int KB) { return stages_for(KB) * stage_bytes(S, KB) + 1024 + 256; }
 
-// K-major, 64B-swizzled tile: rows of 64 bytes, 8-row atoms of 512 B
-__device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
+// K-major swizzled tile with rows of KB bytes: 8-row atoms of 8*KB bytes (SBO); layout type 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+template <int KB>
+__device__ __forceinline__ uint64_t make_desc_kb(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(512 >> 4) << 32;                 // stride byte offset between 8-row groups
+    d |= (uint64_t)((8 * KB) >> 4) << 32;            // stride byte offset between 8-row groups
     d |= (uint64_t)1 << 46;                          // descriptor version
-    d |= (uint64_t)4 << 61;                          // layout type: SWIZZLE_64B
+    d |= (uint64_t)(KB == 64 ? 4 : 6) << 61;
     return d;
 }
 __device__ __forceinline__ constexpr uint32_t make_idesc_i8(int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
 }
 
-template <int S>
+template <int S, int KB>
 __global__ void __launch_bounds__(THREADS, 1)
 umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, OzParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr int STAGE = stage_bytes(S);
+    constexpr int STAGE = stage_bytes(S, KB), STAGES2 = stages_for(KB), BKB2 = KB, A_SLICE = BM2 * KB, B_SLICE = BN2 * KB;
     uint64_t *full = (uint64_t *)(smem + STAGES2 * STAGE);
     uint64_t *empty = full + STAGES2;
     uint64_t *tmem_full = empty + STAGES2;
@@ -611,11 +615,11 @@ umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 // N = 64*(#q) <= 256: A is read from shared memory once per four pairs (N=64 MMAs were smem-read bound).
 #pragma unroll
                 for (int p = 0; p < S; ++p) {
-                    const uint64_t ad = make_desc64(a0 + p * A_SLICE);
+                    const uint64_t ad = make_desc_kb<KB>(a0 + p * A_SLICE);
 #pragma unroll
                     for (int q0 = 0; q0 < S - p; q0 += 4) {
                         const int nq = (S - p - q0) < 4 ? (S - p - q0) : 4;
-                        const uint64_t bd = make_desc64(b0 + q0 * B_SLICE);
+                        const uint64_t bd = make_desc_kb<KB>(b0 + q0 * B_SLICE);
                         const uint32_t acc = tmem_base + (uint32_t)((p + q0) * BN2);
                         const uint32_t idesc = make_idesc_i8(nq * BN2);
 #pragma unroll
@@ -764,19 +768,23 @@ cudaError_t gemm_f64_ozaki(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t
     if (gen < 0) { const char *e = getenv("RDB_OZAKI_GEN"); gen = e ? atoi(e) : 2; }
     if (gen == 2 && nslices <= 8) {
         using namespace oz2;
-        if (!make_map(&mA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, BKB2, nslices) ||
-            !make_map(&mB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2, BKB2, nslices))
+        static int kbytes = -1;
+        if (kbytes < 0) { const char *e = getenv("RDB_OZAKI_KB"); kbytes = (e && atoi(e) == 32) ? 32 : 64; }
+        if (!make_map(&mA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, kbytes, nslices) ||
+            !make_map(&mB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2, kbytes, nslices))
             return cudaErrorInvalidValue;
         dim3 grid2((unsigned)((M + BM2 - 1) / BM2), (unsigned)((N + BN2 - 1) / BN2));
 #define RDB_OZ2(SS)                                                                                                        \
     case SS: {                                                                                                             \
         static bool attr2 = false;                                                                                         \
         if (!attr2) {                                                                                                      \
-            cudaError_t e = cudaFuncSetAttribute(umma_ozaki2_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(SS)); \
+            cudaError_t e = cudaFuncSetAttribute(umma_ozaki2_kernel<SS, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(SS, 64)); \
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_ozaki2_kernel<SS, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(SS, 32)); \
             if (e != cudaSuccess) return e;                                                                                \
             attr2 = true;                                                                                                  \
         }                                                                                                                  \
-        umma_ozaki2_kernel<SS><<<grid2, THREADS, smem_bytes(SS), st>>>(mA, mB, (int)M, (int)N, (int)Kp, P);               \
+        if (kbytes == 64) umma_ozaki2_kernel<SS, 64><<<grid2, THREADS, smem_bytes(SS, 64), st>>>(mA, mB, (int)M, (int)N, (int)Kp, P); \
+        else umma_ozaki2_kernel<SS, 32><<<grid2, THREADS, smem_bytes(SS, 32), st>>>(mA, mB, (int)M, (int)N, (int)Kp, P);   \
     } break;
         switch (nslices) { RDB_OZ2(2) RDB_OZ2(3) RDB_OZ2(4) RDB_OZ2(5) RDB_OZ2(6) RDB_OZ2(7) RDB_OZ2(8) default: return cudaErrorInvalidValue; }
 #undef RDB_OZ2

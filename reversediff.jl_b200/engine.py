@@ -23,7 +23,7 @@ class EngineError(RuntimeError):
 
 class _Options(C.Structure):
     _fields_ = [("fuse_elementwise", C.c_int32), ("seed_block", C.c_int32), ("use_graph", C.c_int32),
-                ("profile", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("profile", C.c_int32), ("gemm_f64_mode", C.c_int32), ("ozaki_slices", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 _lib = None
@@ -45,6 +45,7 @@ def lib():
         "rdb_ctx_destroy": (None, [vp]),
         "rdb_ctx_set_stream": (i32, [vp, vp]),
         "rdb_ctx_synchronize": (i32, [vp]),
+        "rdb_ctx_set_gemm_f64_mode": (i32, [vp, i32, i32]),
         "rdb_tape_load": (vp, [vp, vp, C.c_size_t, C.POINTER(_Options)]),
         "rdb_tape_destroy": (None, [vp]),
         "rdb_tape_set_input": (i32, [vp, i32, vp, i32]),
@@ -70,7 +71,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "rdb_version", "rdb_last_error", "rdb_ctx_create", "rdb_ctx_destroy", "rdb_ctx_set_stream",
-    "rdb_ctx_synchronize", "rdb_tape_load", "rdb_tape_destroy", "rdb_tape_set_input", "rdb_forward",
+    "rdb_ctx_synchronize", "rdb_ctx_set_gemm_f64_mode", "rdb_tape_load", "rdb_tape_destroy", "rdb_tape_set_input", "rdb_forward",
     "rdb_reverse_scalar_seed", "rdb_gradient", "rdb_jacobian", "rdb_hessian", "rdb_get_value", "rdb_get_deriv",
     "rdb_buffer_size", "rdb_tape_stats", "rdb_tape_launch_count", "rdb_gemm", "rdb_add_sum",
 ]
@@ -99,6 +100,9 @@ class Context:
 
     def synchronize(self):
         _check(lib().rdb_ctx_synchronize(self.ptr))
+
+    def set_gemm_f64_mode(self, mode: int, slices: int = 0):
+        _check(lib().rdb_ctx_set_gemm_f64_mode(self.ptr, mode, slices))
 
     def gemm(self, dtype, ta, tb, m, n, k, alpha, A, lda, Bp, ldb, beta, Cp, ldc):
         _check(lib().rdb_gemm(self.ptr, dtype, int(ta), int(tb), m, n, k, alpha, A, lda, Bp, ldb, beta, Cp, ldc))
@@ -130,9 +134,10 @@ def default_context() -> Context:
 
 
 class EngineTape:
-    def __init__(self, ctx: Context, program: bytes, fuse_elementwise=1, seed_block=0, use_graph=1, profile=0):
+    def __init__(self, ctx: Context, program: bytes, fuse_elementwise=1, seed_block=0, use_graph=1, profile=0,
+                 gemm_f64_mode=0, ozaki_slices=0):
         self.ctx = ctx
-        opts = _Options(int(fuse_elementwise), int(seed_block), int(use_graph), int(profile))
+        opts = _Options(int(fuse_elementwise), int(seed_block), int(use_graph), int(profile), int(gemm_f64_mode), int(ozaki_slices))
         buf = (C.c_char * len(program)).from_buffer_copy(program)
         self.ptr = lib().rdb_tape_load(ctx.ptr, buf, len(program), C.byref(opts))
         if not self.ptr:
