@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--jac-n", type=int, default=8192)
     ap.add_argument("--hess-n", type=int, default=16384)
+    ap.add_argument("--gemm", default="auto", choices=["auto", "dmma"],
+                    help="FP64 `*` kernels: auto = exact int8 slices on tcgen05 where eligible (default), dmma = DMMA only")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extra", action="store_true", help="skip the jacobian!/hessian! legs")
     return ap.parse_args()
@@ -209,7 +211,8 @@ def main():
     rng = np.random.default_rng(1)
     a0 = np.asfortranarray(rng.random((n, n)).astype(npdt)); b0 = np.asfortranarray(rng.random((n, n)).astype(npdt))
     tape = rd.GradientTape(rd.workloads.f_gradient_example, (a0, b0))
-    ct = rd.compile(tape, ctx=ctx)
+    mode = 1 if args.gemm == "dmma" else 0
+    ct = rd.compile(tape, ctx=ctx, gemm_f64_mode=mode)
     a, b = rd.workloads.inputs_gradient_example(n, npdt)
 
     # ---- device-resident leg ---------------------------------------------------------------------
@@ -258,33 +261,64 @@ def main():
     assert np.max(np.abs(ga_h - ga)) <= tol * np.max(np.abs(ga))
 
     # ---- roofline of the dominant kernel: per-launch CUDA events inside the engine --------------------
-    ctp = rd.compile(tape, ctx=ctx, profile=1)
-    for _ in range(2):
-        rd.gradient_((ga_d, gb_d), ctp, (a_d, b_d))
-    ctp.handle.stats()
-    reps = 3
-    for _ in range(reps):
-        rd.gradient_((ga_d, gb_d), ctp, (a_d, b_d))
-    stats = json.loads(ctp.handle.stats())
+    def gemm_stats(m):
+        ctp = rd.compile(tape, ctx=ctx, profile=1, gemm_f64_mode=m)
+        for _ in range(2):
+            rd.gradient_((ga_d, gb_d), ctp, (a_d, b_d))
+        ctp.handle.stats()
+        reps_ = 3
+        for _ in range(reps_):
+            rd.gradient_((ga_d, gb_d), ctp, (a_d, b_d))
+        st = json.loads(ctp.handle.stats())
+        del ctp
+        return st, reps_
+    stats, reps = gemm_stats(mode)
     g_ms = sum(s["ms"] for s in stats if s["step"].startswith("gemm"))
     g_fl = sum(s["flops"] for s in stats if s["step"].startswith("gemm"))
     g_cnt = sum(s["count"] for s in stats if s["step"].startswith("gemm"))
     tot_ms = sum(s["ms"] for s in stats)
-    achieved = g_fl / (g_ms * 1e-3) / 1e12
+    fp_equiv = g_fl / (g_ms * 1e-3) / 1e12                    # FP64/FP32-equivalent TFLOP/s of the `*` instructions
     ew = [s for s in stats if not s["step"].startswith("gemm")]
     ew_bytes = sum(s["bytes"] for s in ew); ew_ms = sum(s["ms"] for s in ew)
-    peak = measure_blas_peak(torch, n, tdt)
+    blas_peak = measure_blas_peak(torch, n, tdt)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    bf16_peak = peaks.get("bf16_tflops", 1590.0)
+    peak_tag = "MEASURED_PEAKS.json bf16_tflops" if "bf16_tflops" in peaks else "fallback 1590 TFLOP/s bf16"
+    slices = 8
+    if args.dtype == "f64" and mode == 0:
+        # tcgen05 kind::i8 path: every FP64 GEMM is S(S+1)/2 = 36 exact int8 slice products of the same shape
+        ops_per_flop = slices * (slices + 1) / 2
+        kernel = "oz2::umma_ozaki2_kernel<8,64> (TMA + tcgen05.mma kind::i8, int32 TMEM accumulators) + k_slice_i8/k_row_absmax"
+        unit, pipe_peak = "TOP/s (int8)", 2.0 * bf16_peak
+        peak_src = f"2 x {peak_tag} (int8 issues at twice the bf16 rate; no int8 figure is measured on this pool; nominal dense 4500)"
+        traffic = 2.03e9 + 0.13e9       # dram__bytes_read+write per launch, ncu --set full (profiles/prof_ozaki2_r1.txt)
+    elif args.dtype == "f64":
+        ops_per_flop = 1.0
+        kernel = "d64::dgemm_dmma_kernel (mma.sync m8n8k4 f64 = SASS DMMA.8x8x4)"
+        unit, pipe_peak = "TFLOP/s (fp64)", blas_peak
+        peak_src = "cuBLAS DGEMM measured in this run (MEASURED_PEAKS.json holds no FP64 figure)"
+        traffic = 1.10e9 + 0.12e9       # profiles/prof_dgemm_r1a.txt
+    else:
+        ops_per_flop = 3.0
+        kernel = "umma::umma_gemm_kernel<tf32> (TMA + tcgen05.mma kind::tf32, 3xTF32 split) + k_split_tf32"
+        unit, pipe_peak = "TFLOP/s (tf32)", 0.5 * bf16_peak
+        peak_src = f"0.5 x {peak_tag} (tf32 issues at half the bf16 rate)"
+        traffic = None
+    achieved = fp_equiv * ops_per_flop
     roofline = {
-        "bound": "tensor", "kernel": "dgemm_dmma_kernel (DMMA m8n8k4)" if args.dtype == "f64" else "sgemm_simt_kernel",
-        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-        "peak_source": f"cuBLAS {'D' if args.dtype == 'f64' else 'S'}GEMM {n}^3 measured in this run (best of 6, CUDA events); "
-                       "MEASURED_PEAKS.json holds no FP64/FP32 GEMM figure",
+        "bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": pipe_peak, "unit": unit, "frac": achieved / pipe_peak,
+        "traffic": traffic, "peak_source": peak_src,
+        "note": "achieved = tensor-pipe operations actually issued (algorithmic 2mnk x ops_per_flop) / CUDA-event time of the `*` "
+                "steps INCLUDING their operand slicing passes",
+        "ops_per_algorithmic_flop": ops_per_flop,
+        "fp_equivalent": {"achieved_tflops": fp_equiv, "cublas_gemm_tflops_same_run": blas_peak, "ratio_vs_cublas": fp_equiv / blas_peak,
+                          "what": f"algorithmic 2mnk flops of the six {n}^3 `*` instructions / their time, next to cuBLAS "
+                                  f"{'D' if args.dtype == 'f64' else 'S'}GEMM {n}^3 (best of 6)"},
         "algorithmic_flops_per_launch": 2.0 * n ** 3, "launches_per_step": g_cnt // reps,
         "avg_launch_ms": g_ms / max(g_cnt, 1), "gemm_share_of_step": g_ms / tot_ms,
         "elementwise": {"bound": "hbm", "achieved": ew_bytes / (ew_ms * 1e-3) / 1e9 if ew_ms > 0 else None, "peak": hbm_peak,
@@ -293,7 +327,12 @@ def main():
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
         "steps": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in s.items()} for s in stats],
     }
-    del ctp
+    if args.dtype == "f64" and mode == 0:
+        # the DMMA kernel on the same tape, same run, for context
+        st1, r1 = gemm_stats(1)
+        d_ms = sum(s["ms"] for s in st1 if s["step"].startswith("gemm")); d_fl = sum(s["flops"] for s in st1 if s["step"].startswith("gemm"))
+        roofline["dmma_path_same_run"] = {"gemm_tflops": d_fl / (d_ms * 1e-3) / 1e12, "frac_of_cublas_dgemm": d_fl / (d_ms * 1e-3) / 1e12 / blas_peak,
+                                          "ms_per_eval_all_steps": sum(s["ms"] for s in st1) / r1}
 
     # ---- CPU baseline (rank 0, N=1): reference-equivalent replay on the host cores ---------------------
     cpu = None
@@ -315,7 +354,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"compiled-tape gradient! of sum(a'*b + a*b') at {n}x{n} {args.dtype} (BASELINE configs[1])",
-                       "n": n, "tape": "*(IDX a', b) ; *(a, IDX b') ; + ; sum", "flops_per_eval": 12.0 * n ** 3,
+                       "n": n, "tape": "*(IDX a', b) ; *(a, IDX b') ; + ; sum", "flops_per_eval": 12.0 * n ** 3, "gemm_kernels": args.gemm,
                        "l2": "working set (8 x %d MB) larger than the 126 MB L2" % (n * n * es // 2 ** 20),
                        "multi_gpu": "replicas only (a scalar function's gradient does not shard)" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": 2 * n * n * es, "d2h_bytes_per_step": 2 * n * n * es + es,

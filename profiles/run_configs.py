@@ -1,0 +1,139 @@
+#!/usr/bin/env python
+"""Measure all five BASELINE.json configs on one B200 (device-resident inputs, CUDA events, 3 warm-ups) and print one JSON
+object per config.  Used for profiles/README.md; the headline contract lives in bench.py."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+rd = graft.load_package()
+ctx = rd.engine.Context(0)
+ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+
+def timeit(step, steps=5, warm=3):
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def stats_of(tape, run, **opts):
+    ctp = rd.compile(tape, ctx=ctx, profile=1, **opts)
+    run(ctp); run(ctp)
+    ctp.handle.stats()
+    run(ctp)
+    return json.loads(ctp.handle.stats())
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x).T if np.ndim(x) == 2 else x)).cuda()
+
+
+out = []
+which = sys.argv[1:] or ["1", "2", "2f32", "3", "4", "5"]
+
+if "1" in which:   # cfg 1: 100x100 FP64 (README: 429.65 us per gradient! on unstated CPU hardware)
+    n = 100
+    rng = np.random.default_rng(1)
+    tape = rd.GradientTape(rd.workloads.f_gradient_example, (rng.random((n, n)), rng.random((n, n))))
+    ct = rd.compile(tape, ctx=ctx)
+    a, b = rd.workloads.inputs_gradient_example(n)
+    ad, bd = dev(a), dev(b); ga, gb = torch.empty(n * n, dtype=torch.float64, device="cuda"), torch.empty(n * n, dtype=torch.float64, device="cuda")
+    ms = timeit(lambda: rd.gradient_((ga, gb), ct, (ad, bd)), 200, 20)
+    gh, gbh = np.zeros((n, n), order="F"), np.zeros((n, n), order="F")
+    ms_h = timeit(lambda: rd.gradient_((gh, gbh), ct, (a, b)), 200, 20)
+    out.append({"cfg": 1, "what": "gradient! 100x100 f64", "us_per_eval_device": ms * 1e3, "us_per_eval_host_arrays": ms_h * 1e3,
+                "evals_per_s_host_arrays": 1e3 / ms_h, "readme_cpu_us": 429.65})
+
+for key, dt, tdt in (("2", np.float64, torch.float64), ("2f32", np.float32, torch.float32)):
+    if key in which:
+        n = 4096
+        rng = np.random.default_rng(1)
+        tape = rd.GradientTape(rd.workloads.f_gradient_example, (rng.random((n, n)).astype(dt), rng.random((n, n)).astype(dt)))
+        ct = rd.compile(tape, ctx=ctx)
+        a, b = rd.workloads.inputs_gradient_example(n, dt)
+        ad, bd = dev(a), dev(b); ga, gb = torch.empty(n * n, dtype=tdt, device="cuda"), torch.empty(n * n, dtype=tdt, device="cuda")
+        ms = timeit(lambda: rd.gradient_((ga, gb), ct, (ad, bd)))
+        out.append({"cfg": key, "what": f"gradient! 4096x4096 {np.dtype(dt).name}", "ms_per_eval": ms, "evals_per_s": 1e3 / ms,
+                    "tflops_equiv": 12 * n ** 3 / ms / 1e9, "steps": stats_of(tape, lambda c: rd.gradient_((ga, gb), c, (ad, bd)))})
+        del ct
+
+if "3" in which:   # cfg 3: MLP, X 1024 x 65536 frozen in the tape
+    d = h = o = 1024; N = 65536
+    X, rec = rd.workloads.inputs_mlp(d, h, o, N, seed=1)
+    tape = rd.GradientTape(rd.workloads.make_f_mlp(X), rec)
+    ct = rd.compile(tape, ctx=ctx)
+    _, ws = rd.workloads.inputs_mlp(d, h, o, N, seed=2)
+    wd = [dev(w) for w in ws]
+    gs = [torch.empty(w.size, dtype=torch.float64, device="cuda") for w in ws]
+    ms = timeit(lambda: rd.gradient_(tuple(gs), ct, tuple(wd)), 3, 2)
+    # parity at full size: standard backprop in torch fp64 (independent of the engine)
+    Xd = torch.from_numpy(X).cuda(); W1, b1, W2, b2 = [torch.from_numpy(np.asarray(w)).cuda() for w in ws]
+    H = torch.tanh(W1 @ Xd + b1[:, None]); Y = torch.tanh(W2 @ H + b2[:, None])
+    dZ2 = 1 - Y * Y; dZ1 = (W2.T @ dZ2) * (1 - H * H)
+    refs = [dZ1 @ Xd.T, dZ1.sum(1), dZ2 @ H.T, dZ2.sum(1)]
+    errs = []
+    for g, r, w in zip(gs, refs, ws):
+        gg = g.reshape(w.shape[::-1]).T if w.ndim == 2 else g
+        errs.append(float((gg - r).abs().max() / r.abs().max()))
+    S = h * N
+    out.append({"cfg": 3, "what": "gradient! MLP sum(tanh.(W2*tanh.(W1*X .+ b1) .+ b2)), X 1024x65536 f64", "ms_per_eval": ms, "evals_per_s": 1e3 / ms,
+                "gemm_flops": 10.0 * 1024 ** 2 * N, "elementwise_bytes_algorithmic": 14 * S * 8, "max_rel_err_vs_torch_backprop": max(errs),
+                "steps": stats_of(tape, lambda c: rd.gradient_(tuple(gs), c, tuple(wd)))})
+    del ct, Xd, H, Y, dZ2, dZ1
+
+if "4" in which:   # cfg 4: jacobian! 8192 -> 8192
+    n = 8192
+    A, B, x0 = rd.workloads.inputs_jacobian(n, seed=1)
+    tape = rd.JacobianTape(rd.workloads.make_f_jacobian(A, B), x0)
+    ct = rd.compile(tape, ctx=ctx)
+    _, _, x = rd.workloads.inputs_jacobian(n, seed=2)
+    xd = dev(x); J = torch.empty(n * n, dtype=torch.float64, device="cuda")
+    ms = timeit(lambda: rd.jacobian_(J, ct, xd), 3, 2)
+    Ad, Bd, xt = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), torch.from_numpy(x).cuda()
+    s = Ad @ xt + xt; v = Bd @ xt; t = torch.tanh(v)
+    Jcf = t[:, None] * (Ad + torch.eye(n, dtype=torch.float64, device="cuda")) + (s * (1 - t * t))[:, None] * Bd
+    Jg = J.reshape(n, n).T          # column-major (rows = outputs) viewed row-major
+    err = float((Jg - Jcf).abs().max() / Jcf.abs().max())
+    out.append({"cfg": 4, "what": "jacobian! f(x)=(A*x+x).*tanh.(B*x), R^8192->R^8192 f64", "ms_per_jacobian": ms, "rows_per_s": n / ms * 1e3,
+                "gemm_flops": 4.0 * n ** 3, "tflops_equiv": 4.0 * n ** 3 / ms / 1e9, "max_rel_err_vs_closed_form": err,
+                "steps": stats_of(tape, lambda c: rd.jacobian_(J, c, xd))})
+    del ct, Ad, Bd, Jcf
+
+if "5" in which:   # cfg 5: hessian! extended Rosenbrock n = 16384
+    n = 16384
+    tape = rd.HessianTape(rd.workloads.f_rosenbrock, rd.workloads.inputs_rosenbrock(n, seed=1))
+    ct = rd.compile(tape, ctx=ctx)
+    x = rd.workloads.inputs_rosenbrock(n, seed=2)
+    xd = dev(x); H = torch.empty(n * n, dtype=torch.float64, device="cuda")
+    ms = timeit(lambda: rd.hessian_(H, ct, xd), 3, 2)
+    Hm = H.reshape(n, n)
+    xt = torch.from_numpy(x).cuda(); oo, ee = xt[0::2], xt[1::2]
+    idx = torch.arange(n // 2, device="cuda")
+    Hcf = torch.zeros(n, n, dtype=torch.float64, device="cuda")
+    Hcf[2 * idx, 2 * idx] = 1200 * oo ** 2 - 400 * ee + 2
+    Hcf[2 * idx, 2 * idx + 1] = -400 * oo; Hcf[2 * idx + 1, 2 * idx] = -400 * oo
+    Hcf[2 * idx + 1, 2 * idx + 1] = 200
+    err = float((Hm - Hcf).abs().max() / Hcf.abs().max())
+    zeros_exact = bool((Hm[Hcf == 0] == 0).all())
+    out.append({"cfg": 5, "what": "hessian! extended Rosenbrock n=16384 f64 (forward-over-reverse)", "ms_per_hessian": ms, "rows_per_s": n / ms * 1e3,
+                "result_bytes": n * n * 8, "result_write_GBps": n * n * 8 / ms / 1e6, "max_rel_err_vs_closed_form": err,
+                "structural_zeros_exact": zeros_exact, "steps": stats_of(tape, lambda c: rd.hessian_(H, c, xd))})
+
+for o in out:
+    print(json.dumps(o))
+_ = time

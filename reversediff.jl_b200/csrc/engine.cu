@@ -167,15 +167,20 @@ static thread_local int g_f64_mode = 0, g_f64_slices = 0;   // set from the tape
 template <typename T>
 static cudaError_t gemm_t(cudaStream_t s, bool ta, bool tb, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t lda,
                           const T *B, int64_t ldb, T beta, T *C, int64_t ldc);
+static thread_local int64_t g_extra_launches = 0;           // kernels behind gemm calls beyond the one KL() counts
 template <>
 cudaError_t gemm_t<double>(cudaStream_t s, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
                            int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc) {
-    return gemm_f64(s, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, g_f64_mode, g_f64_slices);
+    cudaError_t e = gemm_f64(s, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, g_f64_mode, g_f64_slices);
+    g_extra_launches += g_gemm_launches - 1;
+    return e;
 }
 template <>
 cudaError_t gemm_t<float>(cudaStream_t s, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
                           int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc) {
-    return gemm_f32(s, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    cudaError_t e = gemm_f32(s, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    g_extra_launches += g_gemm_launches - 1;
+    return e;
 }
 
 #define KL(t, call)                                                                                        \
@@ -978,9 +983,14 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
 }
 
 // ================================================================================================ C ABI
+static int fold_launches(rdb_tape *t, int rc) {
+    t->launches += g_extra_launches;
+    g_extra_launches = 0;
+    return rc;
+}
 #define DISPATCH(t, fn, ...) \
-    (g_f64_mode = (t)->opts.gemm_f64_mode, g_f64_slices = (t)->opts.ozaki_slices, \
-     (t)->dtype == RDB_F64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__))
+    (g_f64_mode = (t)->opts.gemm_f64_mode, g_f64_slices = (t)->opts.ozaki_slices, g_extra_launches = 0, \
+     fold_launches((t), (t)->dtype == RDB_F64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__)))
 
 extern "C" {
 
@@ -1110,6 +1120,7 @@ int rdb_tape_stats(rdb_tape *t, char *json, size_t cap) {
     return RDB_OK;
 }
 int64_t rdb_tape_launch_count(rdb_tape *t) { return t ? t->launches : -1; }
+
 
 int rdb_gemm(rdb_ctx *c, int dtype, int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const void *A, int64_t lda,
              const void *B, int64_t ldb, double beta, void *C, int64_t ldc) {

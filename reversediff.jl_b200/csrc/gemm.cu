@@ -17,6 +17,8 @@
 
 namespace rdb {
 
+thread_local int g_gemm_launches = 0;
+
 // --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async_16(void *smem, const void *gmem, bool pred) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -367,8 +369,10 @@ static cudaError_t launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, doub
 // RDB_F64_GEMM=dmma|ozaki overrides (experiments / A-B timing).
 cudaError_t gemm_f64(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
                      int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int mode, int slices) {
+    g_gemm_launches = 0;
     if (M <= 0 || N <= 0) return cudaSuccess;
     if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return cudaErrorInvalidValue;
+    g_gemm_launches = 1;
     static int env_mode = -1;
     if (env_mode < 0) { const char *e = getenv("RDB_F64_GEMM"); env_mode = !e ? 0 : (e[0] == 'd' ? 1 : (e[0] == 'o' ? 2 : 0)); }
     if (env_mode) mode = env_mode;
@@ -521,8 +525,10 @@ static cudaError_t launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, floa
 
 cudaError_t gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
                      int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc) {
+    g_gemm_launches = 0;
     if (M <= 0 || N <= 0) return cudaSuccess;
     if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return cudaErrorInvalidValue;
+    g_gemm_launches = 1;
     static int force_simt = -1;
     if (force_simt < 0) { const char *e = getenv("RDB_F32_GEMM"); force_simt = (e && e[0] == 's') ? 1 : 0; }
     if (!force_simt) {

@@ -7,6 +7,9 @@
 
 namespace rdb {
 
+// kernels launched by the most recent gemm_f64/gemm_f32 call on this thread (slicing passes + MMA kernel), for launch accounting
+extern thread_local int g_gemm_launches;
+
 // ---- (c) dense contractions -------------------------------------------------------------------------
 cudaError_t gemm_f64(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
                      int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int mode = 0, int slices = 0);

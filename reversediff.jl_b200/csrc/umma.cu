@@ -712,6 +712,7 @@ cudaError_t gemm_f32_umma(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t 
     }
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
     umma_gemm_kernel<KIND_TF32, EpiF32><<<grid, THREADS, SMEM_BYTES, st>>>(mA, mB, (int)M, (int)N, (int)Kp, segs, epi);
+    g_gemm_launches = 3;
     return cudaGetLastError();
 }
 
@@ -727,12 +728,40 @@ int ozaki_default_slices() {
     return n;
 }
 
+// One K-chunk of the sliced product (K*nslices < 2^19 keeps every int32 accumulation chain exact).
+static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
+                               int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices);
+
 // C(MxN) <- alpha*op(A)*op(B) + beta*C in FP64 through exact int8 slices on tcgen05 (see the comment block above).
+// Long contractions are cut into K-chunks (each sliced with its own row/column scales, accumulated into C with beta = 1): this
+// keeps int32 exact and gives small-MxN / huge-K adjoints (dW = dZ * X', K = 65536 in the MLP config) enough tiles per wave.
 cudaError_t gemm_f64_ozaki(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
                            int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices) {
+    if (M < 256 || N < 256 || K < 256 || !umma_available()) return cudaErrorNotSupported;
+    const int64_t kmax = (((1 << 19) - 1) / nslices) & ~127LL;
+    int64_t chunks = (K + kmax - 1) / kmax;
+    const int64_t tiles = ((M + 127) / 128) * ((N + 63) / 64);
+    while (tiles < 592 && K / (chunks * 2) >= 8192) chunks *= 2;        // want >= 4 waves of 148 tiles; chunks are serialised
+    chunks = 1 > chunks ? 1 : chunks;
+    const int64_t kc = (((K + chunks - 1) / chunks) + 127) & ~127LL;
+    int launches = 0;
+    for (int64_t k0 = 0, c = 0; k0 < K; k0 += kc, ++c) {
+        const int64_t kk = K - k0 < kc ? K - k0 : kc;
+        const double *Ac = ta ? A + k0 : A + k0 * lda;                   // op(A)(:, k0:) : stored KxM (ta) or MxK
+        const double *Bc = tb ? B + k0 * ldb : B + k0;                   // op(B)(k0:, :) : stored NxK (tb) or KxN
+        cudaError_t e = ozaki_chunk(st, ta, tb, M, N, kk, alpha, Ac, lda, Bc, ldb, c == 0 ? beta : 1.0, C, ldc, nslices);
+        if (e != cudaSuccess) return e;
+        launches += 7;      // 2 x absmax, 2 x exponent, 2 x slice, 1 x tcgen05 kernel
+    }
+    g_gemm_launches = launches;
+    return cudaSuccess;
+}
+
+static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
+                               int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices) {
     using namespace umma;
     // int32 exactness: (d+1)*K*2^12 < 2^31 for d <= nslices-1
-    if (M < 256 || N < 256 || K < 256 || K * (int64_t)nslices > (1 << 19) - 1 || !umma_available()) return cudaErrorNotSupported;
+    if (K * (int64_t)nslices > (1 << 19) - 1) return cudaErrorInvalidValue;
     const int64_t Kp = (K + 15) & ~15LL;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t a_bytes = al((size_t)nslices * M * Kp), b_bytes = al((size_t)nslices * N * Kp);
