@@ -822,11 +822,21 @@ static int tri_index(int p, int q, int N) {
 }
 
 // forward-over-reverse: value tangents forward, (adjoint, adjoint tangent) backward, K directions at a time.
+//
+// Traffic is everything here (the result alone is n*n*E bytes), so the sweep is planned:
+//  * value tangents are computed only for buffers whose tangent some nonlinear instruction will read (liveness);
+//  * the tangent of `getindex(input)` is written directly as a one-hot selector of the index map — the n x K seed block of
+//    the input itself is only materialised if a non-getindex instruction consumes it;
+//  * adjoint tangents carry a "known zero" flag per buffer and sweep: a zero tangent is never read, the first accumulation
+//    into a buffer overwrites instead of memset + read-modify-write (the reference's unseed!/increment pattern with the zero
+//    state tracked on the host);
+//  * the adjoint tangent of the input IS the result block H[:, c0:c0+K] (column-major, ld = n): it is accumulated in place.
 template <typename T>
 static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64_t ld, int on_device, void *grad_out, void *value_out) {
     if (t->inputs.size() != 1) return fail(RDB_EINVAL, "Taking the Hessian of a function with multiple arguments is not yet supported");
     Buf &out = t->bufs[t->output];
-    Buf &x = t->bufs[t->inputs[0]];
+    const int xid = t->inputs[0];
+    Buf &x = t->bufs[xid];
     if (out.size != 1) return fail(RDB_EINVAL, "hessian! needs a scalar tape output");
     const int64_t n = x.size;
     if (cb < 0 || ce > n || cb > ce) return fail(RDB_EINVAL, "column range outside [0,n)");
@@ -834,8 +844,6 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
     if (cols > 0 && ld < n) return fail(RDB_EINVAL, "leading dimension smaller than n");
     OK(ensure_second_order(t));
     OK(forward_pass<T>(t, 2));
-    // first-order reverse sweep: adjoints of every buffer are needed by the tangent sweep, so intermediates are
-    // kept (no unseed) until the chunk loop is done; gradient falls out for free (DiffResult method, hessians.jl:92-97)
     if (value_out) CU(cudaMemcpyAsync(value_out, out.val, t->es, cudaMemcpyDeviceToHost, S(t)));
     if (cols == 0 && !grad_out) { CU(cudaStreamSynchronize(S(t))); return RDB_OK; }
     const int64_t K = std::max<int64_t>(1, auto_seed_block(t, std::max<int64_t>(cols, 1), true));
@@ -847,17 +855,49 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
         dres = (T *)t->stage;
         dld = n;
     }
+    const size_t nb = t->bufs.size();
+    auto root = [&](int b) { while (t->bufs[b].alias_of >= 0) b = t->bufs[b].alias_of; return b; };
+
+    // ---- liveness of value tangents (backward over the tape)
+    std::vector<char> need_tv(nb, 0);
+    for (size_t ii = t->instrs.size(); ii-- > 0;) {
+        InstrPlan &I = t->instrs[ii];
+        const bool nonlinear = is_elementwise(I.rec.opcode);
+        for (int a = 0; a < I.rec.n_in; ++a) {
+            if (!I.in[a].rec.tracked) continue;
+            if (nonlinear || need_tv[root(I.rec.out)]) need_tv[root(I.in[a].rec.buffer)] = 1;
+        }
+    }
+    // the input's own n x K seed block is needed only by consumers other than getindex
+    bool need_x_tv = false;
+    for (auto &I : t->instrs)
+        for (int a = 0; a < I.rec.n_in; ++a)
+            if (root(I.in[a].rec.buffer) == root(xid) && I.rec.opcode != OP_GETINDEX && (is_elementwise(I.rec.opcode) || need_tv[root(I.rec.out)]))
+                need_x_tv = true;
+
+    void *const x_td_own = x.td;
     bool first = true;
     for (int64_t c0 = cb; c0 < ce || first; c0 += K) {
         const int64_t Kb = cols > 0 ? std::min(K, ce - c0) : 1;
+        // accumulate the input's adjoint tangent straight into the result block when its leading dimension is n
+        const bool in_place = cols > 0 && dld == n;
+        if (in_place) x.td = dres + (c0 - cb) * dld;
+        for (auto &b : t->bufs) if (b.alias_of >= 0) b.td = t->bufs[b.alias_of].td;
+
         // ---- tangent-forward sweep
-        KL(t, launch_seed_tangent<T>(S(t), (T *)x.tv, n, Kb, c0));
+        if (need_x_tv) KL(t, launch_seed_tangent<T>(S(t), (T *)x.tv, n, Kb, c0));
         for (auto &I : t->instrs) {
             Buf &o = t->bufs[I.rec.out];
+            if (!need_tv[root(I.rec.out)]) continue;
             switch (I.rec.opcode) {
-                case OP_GETINDEX:
-                    KL(t, launch_gather_cols<T>(S(t), (T *)o.tv, (const T *)t->bufs[I.in[0].rec.buffer].tv, t->bufs[I.in[0].rec.buffer].size, I.in[0].d_map, o.size, Kb));
-                    break;
+                case OP_GETINDEX: {
+                    Buf &src = t->bufs[I.in[0].rec.buffer];
+                    StepTimer tm(t, "tangent_getindex", 1.0 * o.size * Kb * t->es, 0);
+                    if (root(I.in[0].rec.buffer) == root(xid))
+                        KL(t, launch_seed_gather<T>(S(t), (T *)o.tv, I.in[0].d_map, o.size, Kb, c0));
+                    else
+                        KL(t, launch_gather_cols<T>(S(t), (T *)o.tv, (const T *)src.tv, src.size, I.in[0].d_map, o.size, Kb));
+                } break;
                 case OP_ADD: case OP_SUB: {
                     T sign = I.rec.opcode == OP_ADD ? (T)1 : (T)-1;
                     Buf &a = t->bufs[I.in[0].rec.buffer], &b = t->bufs[I.in[1].rec.buffer];
@@ -901,54 +941,72 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                 }
             }
         }
-        // ---- reverse sweep carrying (adjoint, adjoint tangent); adjoints are recomputed per chunk (R = 1, cheap)
-        for (int b : t->inputs) { OK(unseed<T>(t, t->bufs[b], 1)); CU(cudaMemsetAsync(t->bufs[b].td, 0, (size_t)(t->bufs[b].size * Kb) * t->es, S(t))); }
+        // ---- reverse sweep carrying (adjoint, adjoint tangent); first-order adjoints are recomputed per chunk (size n, cheap)
+        std::vector<char> td_zero(nb, 1);               // per ROOT buffer: adjoint tangent is (logically) zero
+        for (int b : t->inputs) OK(unseed<T>(t, t->bufs[b], 1));
         KL(t, launch_fill<T>(S(t), (T *)out.der, 1, (T)1));
-        CU(cudaMemsetAsync(out.td, 0, (size_t)Kb * t->es, S(t)));
         for (size_t ii = t->instrs.size(); ii-- > 0;) {
             InstrPlan &I = t->instrs[ii];
             Buf &o = t->bufs[I.rec.out];
-            const T *delta = (const T *)o.der, *dt = (const T *)o.td;
+            const T *delta = (const T *)o.der;
+            const bool dt_zero = td_zero[root(I.rec.out)];
+            const T *dt = dt_zero ? nullptr : (const T *)o.td;
             switch (I.rec.opcode) {
                 case OP_GETINDEX: {
+                    const int rb = root(I.in[0].rec.buffer);
                     Buf &b = t->bufs[I.in[0].rec.buffer];
                     KL(t, launch_scatter_add<T>(S(t), (T *)b.der, b.size, I.in[0].d_map, delta, o.size, 1));
-                    KL(t, launch_scatter_add<T>(S(t), (T *)b.td, b.size, I.in[0].d_map, dt, o.size, Kb));
+                    if (!dt_zero) {
+                        if (td_zero[rb]) { CU(cudaMemsetAsync(b.td, 0, (size_t)(b.size * Kb) * t->es, S(t))); td_zero[rb] = 0; }
+                        StepTimer tm(t, "tangent_getindex_reverse", 3.0 * o.size * Kb * t->es, 0);
+                        KL(t, launch_scatter_add<T>(S(t), (T *)b.td, b.size, I.in[0].d_map, dt, o.size, Kb));
+                    }
                 } break;
                 case OP_ADD: case OP_SUB:
                     for (int a = 0; a < 2; ++a) {
                         if (!I.in[a].rec.tracked) continue;
+                        const int rb = root(I.in[a].rec.buffer);
                         Buf &b = t->bufs[I.in[a].rec.buffer];
                         T sign = (a == 1 && I.rec.opcode == OP_SUB) ? (T)-1 : (T)1;
                         KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, sign, o.size, false));
-                        KL(t, launch_axpy<T>(S(t), (T *)b.td, dt, sign, o.size * Kb, false));
+                        if (!dt_zero) { KL(t, launch_axpy<T>(S(t), (T *)b.td, dt, sign, o.size * Kb, td_zero[rb] != 0)); td_zero[rb] = 0; }
                     }
                     break;
                 case OP_NEG: {
+                    const int rb = root(I.in[0].rec.buffer);
                     Buf &b = t->bufs[I.in[0].rec.buffer];
                     KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, (T)-1, o.size, false));
-                    KL(t, launch_axpy<T>(S(t), (T *)b.td, dt, (T)-1, o.size * Kb, false));
+                    if (!dt_zero) { KL(t, launch_axpy<T>(S(t), (T *)b.td, dt, (T)-1, o.size * Kb, td_zero[rb] != 0)); td_zero[rb] = 0; }
                 } break;
                 case OP_SUM: case OP_MEAN: {
+                    const int rb = root(I.in[0].rec.buffer);
                     Buf &b = t->bufs[I.in[0].rec.buffer];
                     T scale = I.rec.opcode == OP_MEAN ? (T)1 / (T)I.in[0].size : (T)1;
                     KL(t, launch_acc_scalar<T>(S(t), (T *)b.der, b.size, 1, delta, scale, false));
-                    KL(t, launch_acc_scalar<T>(S(t), (T *)b.td, b.size, Kb, dt, scale, false));
+                    if (!dt_zero) { KL(t, launch_acc_scalar<T>(S(t), (T *)b.td, b.size, Kb, dt, scale, td_zero[rb] != 0)); td_zero[rb] = 0; }
                 } break;
                 case OP_MUL: {
                     OperandPlan &oa = I.in[0], &ob = I.in[1];
                     int64_t M = oa.rows, Kd = oa.cols, N = ob.cols;
                     if (ob.rec.tracked) {
+                        const int rb = root(ob.rec.buffer);
                         Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
                         bool st = oa.mode == OPM_FOLDED_T;
                         KL(t, gemm_t<T>(S(t), !st, false, Kd, N, M, (T)1, (const T *)a.val, st ? oa.cols : oa.rows, delta, M, (T)1, (T *)b.der, Kd));
-                        KL(t, gemm_t<T>(S(t), !st, false, Kd, N * Kb, M, (T)1, (const T *)a.val, st ? oa.cols : oa.rows, dt, M, (T)1, (T *)b.td, Kd));
+                        if (!dt_zero) {
+                            KL(t, gemm_t<T>(S(t), !st, false, Kd, N * Kb, M, (T)1, (const T *)a.val, st ? oa.cols : oa.rows, dt, M, td_zero[rb] ? (T)0 : (T)1, (T *)b.td, Kd));
+                            td_zero[rb] = 0;
+                        }
                     } else {
+                        const int rb = root(oa.rec.buffer);
                         Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
                         bool st = ob.mode == OPM_FOLDED_T;
                         KL(t, gemm_t<T>(S(t), false, !st, M, Kd, N, (T)1, delta, M, (const T *)b.val, st ? ob.cols : ob.rows, (T)1, (T *)a.der, M));
-                        for (int64_t k = 0; k < Kb; ++k)
-                            KL(t, gemm_t<T>(S(t), false, !st, M, Kd, N, (T)1, dt + k * o.size, M, (const T *)b.val, st ? ob.cols : ob.rows, (T)1, (T *)a.td + k * a.size, M));
+                        if (!dt_zero) {
+                            for (int64_t k = 0; k < Kb; ++k)
+                                KL(t, gemm_t<T>(S(t), false, !st, M, Kd, N, (T)1, dt + k * o.size, M, (const T *)b.val, st ? ob.cols : ob.rows, td_zero[rb] ? (T)0 : (T)1, (T *)a.td + k * a.size, M));
+                            td_zero[rb] = 0;
+                        }
                     }
                 } break;
                 default: {
@@ -956,25 +1014,34 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                     const T *tvs[kMaxArgs];
                     for (int a = 0; a < N; ++a) tvs[a] = (const T *)t->bufs[I.in[a].rec.buffer].tv;
                     for (int p = 0; p < N; ++p) {
+                        const int rb = root(I.in[p].rec.buffer);
                         Buf &b = t->bufs[I.in[p].rec.buffer];
                         const T *sec[kMaxArgs];
                         for (int q = 0; q < N; ++q) sec[q] = (const T *)I.second[tri_index(p, q, N)];
-                        StepTimer tm(t, "tangent_reverse", (double)(N + 3) * o.size * Kb * t->es, 0);
-                        KL(t, launch_tangent_reverse<T>(S(t), (T *)b.td, dt, delta, (const T *)I.partial[p], N, sec, tvs, o.size, Kb, false));
+                        StepTimer tm(t, "tangent_reverse", (double)(N + (dt ? 2 : 1) + (td_zero[rb] ? 0 : 1)) * o.size * Kb * t->es, 0);
+                        KL(t, launch_tangent_reverse<T>(S(t), (T *)b.td, dt, delta, (const T *)I.partial[p], N, sec, tvs, o.size, Kb, td_zero[rb] != 0));
+                        td_zero[rb] = 0;
                         KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[p], o.size, 1, false));
                     }
                 }
             }
             OK(unseed<T>(t, o, 1));
-            CU(cudaMemsetAsync(o.td, 0, (size_t)(o.size * Kb) * t->es, S(t)));
         }
         if (cols > 0) {
-            StepTimer tm(t, "hessian_cols_out", 2.0 * n * Kb * t->es, 0);
-            KL(t, launch_copy2d<T>(S(t), dres + (c0 - cb) * dld, dld, (const T *)x.td, n, n, Kb));   // H[:, c0:c0+Kb] = tangent of deriv(x)
+            if (td_zero[root(xid)]) {          // f does not depend on x through any second-order path: exact zeros
+                if (in_place) CU(cudaMemsetAsync(x.td, 0, (size_t)(n * Kb) * t->es, S(t)));
+                else CU(cudaMemsetAsync(x_td_own, 0, (size_t)(n * Kb) * t->es, S(t)));
+            }
+            if (!in_place) {
+                StepTimer tm(t, "hessian_cols_out", 2.0 * n * Kb * t->es, 0);
+                KL(t, launch_copy2d<T>(S(t), dres + (c0 - cb) * dld, dld, (const T *)x.td, n, n, Kb));   // H[:, c0:c0+Kb] = tangent of deriv(x)
+            }
         }
         first = false;
         if (cols == 0) break;
     }
+    x.td = x_td_own;
+    for (auto &b : t->bufs) if (b.alias_of >= 0) b.td = t->bufs[b.alias_of].td;
     if (grad_out) CU(cudaMemcpyAsync(grad_out, x.der, (size_t)n * t->es, cudaMemcpyDeviceToHost, S(t)));
     if (!on_device && cols > 0)
         CU(cudaMemcpy2DAsync(result, (size_t)ld * t->es, t->stage, (size_t)n * t->es, (size_t)n * t->es, (size_t)cols, cudaMemcpyDeviceToHost, S(t)));

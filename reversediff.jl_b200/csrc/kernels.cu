@@ -685,6 +685,21 @@ cudaError_t launch_seed_onehot(cudaStream_t s, T *der, int64_t m, int64_t R, int
     return cudaGetLastError();
 }
 template <typename T>
+__global__ void __launch_bounds__(kThreads) k_seed_gather(T *__restrict__ tv, const int64_t *__restrict__ map, int64_t n, int64_t K, int64_t c0) {
+    int64_t tot = n * K;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) {
+        int64_t c = i / n, k = i - c * n;
+        tv[i] = (map[k] == c0 + c) ? (T)1 : (T)0;
+    }
+}
+template <typename T>
+cudaError_t launch_seed_gather(cudaStream_t s, T *tv, const int64_t *map, int64_t n, int64_t K, int64_t c0) {
+    if (n * K <= 0) return cudaSuccess;
+    k_seed_gather<T><<<grid_for(n * K, 4), kThreads, 0, s>>>(tv, map, n, K, c0);
+    return cudaGetLastError();
+}
+template <typename T>
 cudaError_t launch_seed_tangent(cudaStream_t s, T *tv, int64_t n, int64_t K, int64_t c0) {
     return launch_seed_onehot<T>(s, tv, n, K, c0);
 }
@@ -762,7 +777,8 @@ k_tangent_reverse(T *__restrict__ td, const T *__restrict__ dt, const T *__restr
         T acc = (T)0;
 #pragma unroll
         for (int q = 0; q < N; ++q) acc += a.second[q][e] * a.tv[q][i];
-        T v = dt[i] * partial_p[e] + delta[e] * acc;
+        T v = delta[e] * acc;
+        if (dt) v += dt[i] * partial_p[e];          // dt == nullptr: the output's adjoint tangent is known to be zero
         td[i] = OVERWRITE ? v : td[i] + v;
     }
 }
@@ -836,6 +852,7 @@ cudaError_t launch_copy2d(cudaStream_t s, T *dst, int64_t ldd, const T *src, int
     template cudaError_t launch_tangent_reverse<T>(cudaStream_t, T *, const T *, const T *, const T *, int, const T *const *, const T *const *, int64_t, int64_t, bool); \
     template cudaError_t launch_gather_cols<T>(cudaStream_t, T *, const T *, int64_t, const int64_t *, int64_t, int64_t); \
     template cudaError_t launch_seed_tangent<T>(cudaStream_t, T *, int64_t, int64_t, int64_t);                            \
+    template cudaError_t launch_seed_gather<T>(cudaStream_t, T *, const int64_t *, int64_t, int64_t, int64_t);            \
     template cudaError_t launch_colsum<T>(cudaStream_t, T *, const T *, int64_t, int64_t, T);                             \
     template cudaError_t launch_copy2d<T>(cudaStream_t, T *, int64_t, const T *, int64_t, int64_t, int64_t);
 RDB_INST(double)
