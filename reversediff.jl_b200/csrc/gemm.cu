@@ -365,6 +365,105 @@ static cudaError_t launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, doub
 }
 }  // namespace d64
 
+
+// ==================================================================================================
+// GEMV: `*` with a vector operand (forward sweep of the jacobian! config: u = A*x, v = B*x).  HBM-bound (the matrix is read
+// once); a 128x64-tile GEMM kernel with one useful column wasted ~8x that.
+//   trans:   y(cols) = alpha * A' * x(rows) + beta*y   one warp per column, lanes stride the contiguous column, shuffle reduce
+//   notrans: y(rows) = alpha * A  * x(cols) + beta*y   threads along rows (coalesced), K split over blockIdx.y, deterministic
+//                                                      two-pass reduction through a scratch buffer (no atomics)
+// ==================================================================================================
+namespace gv {
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_t_kernel(int rows, int cols, double alpha, const T *__restrict__ A, int64_t lda,
+                                                     const T *__restrict__ x, int64_t incx, double beta, T *__restrict__ y, int64_t incy) {
+    int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= cols) return;
+    const T *col = A + (int64_t)j * lda;
+    double acc = 0.0;
+    for (int i = lane; i < rows; i += 32) acc += (double)col[i] * (double)x[(int64_t)i * incx];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        double v = alpha * acc;
+        if (beta != 0.0) v += beta * (double)y[(int64_t)j * incy];
+        y[(int64_t)j * incy] = (T)v;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_n_partial(int rows, int cols, const T *__restrict__ A, int64_t lda, const T *__restrict__ x,
+                                                      int64_t incx, double *__restrict__ part, int kchunk) {
+    int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= rows) return;
+    int k0 = blockIdx.y * kchunk, k1 = min(cols, k0 + kchunk);
+    double acc = 0.0;
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) acc += (double)A[r + (int64_t)k * lda] * (double)x[(int64_t)k * incx];
+    part[(int64_t)blockIdx.y * rows + r] = acc;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_n_finish(int rows, int chunks, double alpha, const double *__restrict__ part, double beta,
+                                                     T *__restrict__ y, int64_t incy) {
+    int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= rows) return;
+    double acc = 0.0;
+    for (int c = 0; c < chunks; ++c) acc += part[(int64_t)c * rows + r];
+    double v = alpha * acc;
+    if (beta != 0.0) v += beta * (double)y[(int64_t)r * incy];
+    y[(int64_t)r * incy] = (T)v;
+}
+static double *g_scratch = nullptr;
+static size_t g_scratch_elems = 0;
+template <typename T>
+static cudaError_t gemv(cudaStream_t st, bool trans, int64_t rows, int64_t cols, double alpha, const T *A, int64_t lda, const T *x,
+                        int64_t incx, double beta, T *y, int64_t incy) {
+    if (trans) {
+        gemv_t_kernel<T><<<(unsigned)((cols + 7) / 8), 256, 0, st>>>((int)rows, (int)cols, alpha, A, lda, x, incx, beta, y, incy);
+        g_gemm_launches = 1;
+        return cudaGetLastError();
+    }
+    int64_t bx = (rows + 255) / 256;
+    int64_t chunks = (148 * 8 + bx - 1) / bx;                 // ~8 CTAs per SM
+    if (chunks > (cols + 31) / 32) chunks = (cols + 31) / 32;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 65535) chunks = 65535;
+    int kchunk = (int)((cols + chunks - 1) / chunks);
+    chunks = (cols + kchunk - 1) / kchunk;
+    size_t need = (size_t)chunks * rows;
+    if (need > g_scratch_elems) {
+        if (g_scratch) cudaFree(g_scratch);
+        g_scratch = nullptr; g_scratch_elems = 0;
+        if (cudaMalloc(&g_scratch, need * sizeof(double)) != cudaSuccess) return cudaErrorMemoryAllocation;
+        g_scratch_elems = need;
+    }
+    gemv_n_partial<T><<<dim3((unsigned)bx, (unsigned)chunks), 256, 0, st>>>((int)rows, (int)cols, A, lda, x, incx, g_scratch, kchunk);
+    gemv_n_finish<T><<<(unsigned)bx, 256, 0, st>>>((int)rows, (int)chunks, alpha, g_scratch, beta, y, incy);
+    g_gemm_launches = 2;
+    return cudaGetLastError();
+}
+// C(MxN) = alpha*op(A)*op(B) + beta*C with N == 1 or M == 1, expressed as a GEMV.  Returns false if not applicable.
+template <typename T>
+static bool try_gemv(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const T *A, int64_t lda,
+                     const T *B, int64_t ldb, double beta, T *C, int64_t ldc, cudaError_t *err) {
+    if (K < 1 || (M < 64 && N < 64)) return false;
+    if (N == 1 && M > 1) {
+        // y(M) = op(A) * b ;  op(B) is Kx1: stored Kx1 (contiguous) or 1xK with leading dim ldb
+        const int64_t incb = tb ? ldb : 1;
+        *err = ta ? gemv<T>(st, true, K, M, alpha, A, lda, B, incb, beta, C, 1)       // A stored KxM: y = A' b
+                  : gemv<T>(st, false, M, K, alpha, A, lda, B, incb, beta, C, 1);     // A stored MxK: y = A b
+        return true;
+    }
+    if (M == 1 && N > 1) {
+        // c(N) = op(B)' * a ;  op(A) is 1xK: stored 1xK (stride lda) or Kx1 (contiguous)
+        const int64_t inca = ta ? 1 : lda;
+        *err = tb ? gemv<T>(st, false, N, K, alpha, B, ldb, A, inca, beta, C, ldc)    // B stored NxK: c = B a
+                  : gemv<T>(st, true, K, N, alpha, B, ldb, A, inca, beta, C, ldc);    // B stored KxN: c = B' a
+        return true;
+    }
+    return false;
+}
+}  // namespace gv
+
 // mode: 0 = auto (exact int8 slices on tcgen05 when the shape is eligible, DMMA otherwise), 1 = DMMA only, 2 = same as auto.
 // RDB_F64_GEMM=dmma|ozaki overrides (experiments / A-B timing).
 cudaError_t gemm_f64(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
@@ -373,6 +472,10 @@ cudaError_t gemm_f64(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, in
     if (M <= 0 || N <= 0) return cudaSuccess;
     if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return cudaErrorInvalidValue;
     g_gemm_launches = 1;
+    {
+        cudaError_t ge;
+        if (gv::try_gemv<double>(st, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, &ge)) return ge;
+    }
     static int env_mode = -1;
     if (env_mode < 0) { const char *e = getenv("RDB_F64_GEMM"); env_mode = !e ? 0 : (e[0] == 'd' ? 1 : (e[0] == 'o' ? 2 : 0)); }
     if (env_mode) mode = env_mode;
@@ -529,6 +632,10 @@ cudaError_t gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, in
     if (M <= 0 || N <= 0) return cudaSuccess;
     if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return cudaErrorInvalidValue;
     g_gemm_launches = 1;
+    {
+        cudaError_t ge;
+        if (gv::try_gemv<float>(st, ta, tb, M, N, K, (double)alpha, A, lda, B, ldb, (double)beta, C, ldc, &ge)) return ge;
+    }
     static int force_simt = -1;
     if (force_simt < 0) { const char *e = getenv("RDB_F32_GEMM"); force_simt = (e && e[0] == 's') ? 1 : 0; }
     if (!force_simt) {

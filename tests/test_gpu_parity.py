@@ -48,7 +48,8 @@ def run_gradient(rd, orc, f, rec_inputs, inputs, dtype=np.float64, check_buffers
 @pytest.mark.parametrize("dtype,mode", [(np.float64, 0), (np.float64, 1), (np.float32, 0)])
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("m,n,k", [(1, 1, 1), (3, 5, 7), (64, 64, 64), (100, 100, 100), (129, 257, 65), (512, 384, 640),
-                                   (1024, 1024, 1024), (8, 1, 300), (1030, 1026, 18), (300, 270, 1000), (257, 2049, 263)])
+                                   (1024, 1024, 1024), (8, 1, 300), (1030, 1026, 18), (300, 270, 1000), (257, 2049, 263),
+                                   (300, 1, 200), (1, 300, 200), (4097, 1, 513), (1, 2000, 77)])
 def test_gemm_kernel(rd, ctx, dtype, mode, ta, tb, m, n, k):
     """mode 0 = auto: FP64 shapes >= 256^3 go through exact int8 slices on tcgen05 (truncation 2^-56 of the row/column
     maxima instead of 2^-53 rounding), FP32 shapes >= 128 through 3xTF32 on tcgen05; mode 1 = DMMA only."""
