@@ -71,6 +71,7 @@ struct Buf {
     void *tv = nullptr;    // value tangents  (size x K), hessian! only
     void *td = nullptr;    // deriv tangents  (size x K), hessian! only
     int n_consumers = 0;
+    uint32_t version = 1;  // bumped whenever value(x) is rewritten: identifies sliced-operand cache entries
 };
 
 enum OperandMode { OPM_PLAIN = 0, OPM_FOLDED_T = 1, OPM_GATHER = 2 };
@@ -100,7 +101,9 @@ struct StepStat {
     int count = 0;
 };
 
+static uint32_t g_next_tape_uid = 1;
 struct rdb_tape {
+    uint32_t uid = g_next_tape_uid++;
     rdb_ctx *ctx = nullptr;
     int dtype = RDB_F64;
     size_t es = 8;
@@ -191,6 +194,17 @@ cudaError_t gemm_t<float>(cudaStream_t s, bool ta, bool tb, int64_t M, int64_t N
             return fail(RDB_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
+// identity of value(buffer) for the sliced-operand cache (kernels.h: g_tag_a/g_tag_b); never 0
+static uint64_t value_tag(rdb_tape *t, int b) {
+    while (t->bufs[b].alias_of >= 0) b = t->bufs[b].alias_of;
+    return ((uint64_t)(t->uid & 0xFFFF) << 48) | ((uint64_t)((b + 1) & 0xFFFF) << 32) | (uint64_t)t->bufs[b].version;
+}
+static void bump_version(rdb_tape *t, int b) {
+    while (t->bufs[b].alias_of >= 0) b = t->bufs[b].alias_of;
+    t->bufs[b].version++;
+}
+static uint64_t operand_tag(rdb_tape *t, const OperandPlan &o) { return o.mode == OPM_GATHER ? 0 : value_tag(t, o.rec.buffer); }
+
 static bool is_elementwise(int op) {
     return op == OP_NBCAST || op == OP_MAP || op == OP_BCAST || op == OP_BCAST_ADD || op == OP_BCAST_SUB || op == OP_BCAST_MUL;
 }
@@ -256,6 +270,7 @@ static int forward_pass(rdb_tape *t, int order = 1) {
     for (size_t i = 0; i < n; ++i) {
         InstrPlan &I = t->instrs[i];
         Buf &out = t->bufs[I.rec.out];
+        bump_version(t, I.rec.out);
         // fusion of an elementwise producer with the `sum`/`mean` that consumes it (adjacent instructions only)
         bool fuse_next = false;
         if (t->opts.fuse_elementwise && i + 1 < n) {
@@ -272,6 +287,7 @@ static int forward_pass(rdb_tape *t, int order = 1) {
                 OK(operand_value<T>(t, I.in[1], B));
                 int64_t M = I.in[0].rows, K = I.in[0].cols, N = I.in[1].cols;
                 StepTimer tm(t, "gemm_forward", (double)(M * K + K * N + M * N) * t->es, 2.0 * M * N * K);
+                g_tag_a = operand_tag(t, I.in[0]); g_tag_b = operand_tag(t, I.in[1]);
                 KL(t, gemm_t<T>(S(t), A.stored_t, B.stored_t, M, N, K, (T)1, A.ptr, A.ld, B.ptr, B.ld, (T)0, (T *)out.val, M));
             } break;
             case OP_ADD:
@@ -347,11 +363,14 @@ static int mul_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
             const T *d = delta + r * M * N;
             if (oa.mode == OPM_PLAIN) {
                 // a.deriv(MxK) += delta(MxN) * Bmat'(NxK)
+                g_tag_b = operand_tag(t, ob);
                 KL(t, gemm_t<T>(S(t), false, !B.stored_t, M, K, N, (T)1, d, M, B.ptr, B.ld, (T)1, (T *)ba.der + r * ba.size, M));
             } else if (oa.mode == OPM_FOLDED_T) {
                 // scatter-add through the transpose map == origin.deriv(KxM) += Bmat(KxN) * delta'(NxM)
+                g_tag_a = operand_tag(t, ob);
                 KL(t, gemm_t<T>(S(t), B.stored_t, true, K, M, N, (T)1, B.ptr, B.ld, d, M, (T)1, (T *)ba.der + r * ba.size, K));
             } else {
+                g_tag_b = operand_tag(t, ob);
                 KL(t, gemm_t<T>(S(t), false, !B.stored_t, M, K, N, (T)1, d, M, B.ptr, B.ld, (T)0, (T *)oa.dense_der, M));
                 KL(t, launch_scatter_add<T>(S(t), (T *)ba.der + r * ba.size, ba.size, oa.d_map, (const T *)oa.dense_der, oa.size, 1));
             }
@@ -362,12 +381,14 @@ static int mul_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
         StepTimer tm(t, "gemm_reverse_b", (double)(M * N + M * K + 2 * K * N) * t->es * R, 2.0 * M * N * K * R);
         if (ob.mode == OPM_PLAIN) {
             // b.deriv(K x N*R) += Amat'(KxM) * delta(M x N*R): the R seed columns ride along as extra GEMM columns
+            g_tag_a = operand_tag(t, oa);
             KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, N * R, M, (T)1, A.ptr, A.ld, delta, M, (T)1, (T *)bb.der, K));
         } else {
             for (int64_t r = 0; r < R; ++r) {
                 const T *d = delta + r * M * N;
                 if (ob.mode == OPM_FOLDED_T) {
                     // origin.deriv(NxK) += delta'(NxM) * Amat(MxK)
+                    g_tag_b = operand_tag(t, oa);
                     KL(t, gemm_t<T>(S(t), true, A.stored_t, N, K, M, (T)1, d, M, A.ptr, A.ld, (T)1, (T *)bb.der + r * bb.size, N));
                 } else {
                     KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, N, M, (T)1, A.ptr, A.ld, d, M, (T)0, (T *)ob.dense_der, K));
@@ -1127,6 +1148,7 @@ int rdb_tape_set_input(rdb_tape *t, int slot, const void *data, int is_device) {
     if (slot < 0 || (size_t)slot >= t->inputs.size()) return fail(RDB_EINVAL, "input slot %d out of range", slot);
     Buf &b = t->bufs[t->inputs[slot]];
     CU(cudaMemcpyAsync(b.val, data, (size_t)b.size * t->es, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, S(t)));
+    bump_version(t, t->inputs[slot]);
     t->forward_valid = false;
     return RDB_OK;
 }

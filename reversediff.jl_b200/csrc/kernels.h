@@ -21,10 +21,16 @@ bool umma_available();
 cudaError_t gemm_f32_umma(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
                           int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc);
 
+// Operand identity hints for the slice cache of the int8 path: a non-zero tag says "this operand's contents are identified by
+// (tag, pointer, shape)"; the engine derives it from (tape uid, buffer id, value version).  0 = do not cache (adjoints).
+// Consumed (reset to 0) by the next gemm_f64 call on this thread.
+extern thread_local uint64_t g_tag_a, g_tag_b;
+
 // FP64 through exact int8 slices on the tcgen05 INT8 pipe (Ozaki scheme); cudaErrorNotSupported when not applicable
 int ozaki_default_slices();
 cudaError_t gemm_f64_ozaki(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
-                           int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices);
+                           int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices,
+                           uint64_t tag_a = 0, uint64_t tag_b = 0);
 
 // ---- (a)/(b) elementwise sweeps ---------------------------------------------------------------------
 constexpr int kReduceBlocks = 1184;   // 148 SMs x 8 resident CTAs: partial-sum slots of the two-pass reductions

@@ -17,9 +17,11 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include "kernels.h"
 
 namespace rdb {
+thread_local uint64_t g_tag_a = 0, g_tag_b = 0;
 namespace umma {
 
 constexpr int BM = 128, BN = 256, BKB = 128;          // tile rows / cols / K-bytes per stage (= one 128B swizzle atom)
@@ -730,13 +732,16 @@ int ozaki_default_slices() {
 
 // One K-chunk of the sliced product (K*nslices < 2^19 keeps every int32 accumulation chain exact).
 static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
-                               int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices);
+                               int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices,
+                               uint64_t tag_a, uint64_t tag_b);
+static thread_local int g_chunk_launches = 0;
 
 // C(MxN) <- alpha*op(A)*op(B) + beta*C in FP64 through exact int8 slices on tcgen05 (see the comment block above).
 // Long contractions are cut into K-chunks (each sliced with its own row/column scales, accumulated into C with beta = 1): this
 // keeps int32 exact and gives small-MxN / huge-K adjoints (dW = dZ * X', K = 65536 in the MLP config) enough tiles per wave.
 cudaError_t gemm_f64_ozaki(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
-                           int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices) {
+                           int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices,
+                           uint64_t tag_a, uint64_t tag_b) {
     if (M < 256 || N < 256 || K < 256 || !umma_available()) return cudaErrorNotSupported;
     const int64_t kmax = (((1 << 19) - 1) / nslices) & ~127LL;
     int64_t chunks = (K + kmax - 1) / kmax;
@@ -749,48 +754,121 @@ cudaError_t gemm_f64_ozaki(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t
         const int64_t kk = K - k0 < kc ? K - k0 : kc;
         const double *Ac = ta ? A + k0 : A + k0 * lda;                   // op(A)(:, k0:) : stored KxM (ta) or MxK
         const double *Bc = tb ? B + k0 * ldb : B + k0;                   // op(B)(k0:, :) : stored NxK (tb) or KxN
-        cudaError_t e = ozaki_chunk(st, ta, tb, M, N, kk, alpha, Ac, lda, Bc, ldb, c == 0 ? beta : 1.0, C, ldc, nslices);
+        cudaError_t e = ozaki_chunk(st, ta, tb, M, N, kk, alpha, Ac, lda, Bc, ldb, c == 0 ? beta : 1.0, C, ldc, nslices, tag_a, tag_b);
         if (e != cudaSuccess) return e;
-        launches += 7;      // 2 x absmax, 2 x exponent, 2 x slice, 1 x tcgen05 kernel
+        launches += g_chunk_launches;      // per uncached operand: absmax, exponent, slice; + 1 tcgen05 kernel
     }
     g_gemm_launches = launches;
     return cudaSuccess;
 }
 
+// ---- sliced-operand cache: CONST matrices (frozen by `capture`) and value buffers are sliced once per content version and
+// reused by every `*` instruction / adjoint / seed block that reads them (the jacobian! config re-reads A and B for every block).
+struct SliceEntry {
+    uint64_t tag;
+    const void *ptr;
+    int64_t ld, rows, K;
+    bool kmajor;
+    int ns;
+    int8_t *q;
+    double *sc;
+    size_t bytes;
+    uint64_t last_use;
+};
+static std::vector<SliceEntry> g_cache;
+static uint64_t g_use = 0;
+static size_t g_cache_bytes = 0;
+static size_t cache_cap() {
+    static size_t cap = 0;
+    if (!cap) { const char *e = getenv("RDB_SLICE_CACHE_MB"); cap = (size_t)(e ? atoll(e) : 8192) << 20; }
+    return cap;
+}
+
+static void slice_operand(cudaStream_t st, const double *src, int64_t ld, int64_t rows, int64_t K, int64_t Kp, bool kmajor, int ns,
+                          int8_t *q, int *e, double *sc) {
+    using namespace umma;
+    unsigned long long *mx = (unsigned long long *)sc;                  // scale array doubles as max scratch
+    if (kmajor) k_row_absmax<true><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(src, ld, (int)rows, (int)K, mx);
+    else {
+        cudaMemsetAsync(mx, 0, rows * 8, st);
+        k_row_absmax<false><<<dim3((unsigned)((rows + 255) / 256), (unsigned)((K + 63) / 64)), 256, 0, st>>>(src, ld, (int)rows, (int)K, mx);
+    }
+    k_row_exponent<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(mx, (int)rows, e, sc);
+    dim3 g((unsigned)((Kp + 127) / 128), (unsigned)((rows + 31) / 32));
+    if (kmajor) k_slice_i8<true><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, e);
+    else k_slice_i8<false><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, e);
+}
+
+// returns the slices/scales of one operand; launches = kernels issued (0 on a cache hit)
+static cudaError_t prepare_operand(cudaStream_t st, uint64_t tag, const double *src, int64_t ld, int64_t rows, int64_t K, int64_t Kp,
+                                   bool kmajor, int ns, int8_t *ws_q, int *ws_e, double *ws_sc, int8_t **q, double **sc, int *launches) {
+    if (!tag) {
+        slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc);
+        *q = ws_q; *sc = ws_sc; *launches = 3;
+        return cudaSuccess;
+    }
+    SliceEntry *slot = nullptr;
+    for (auto &en : g_cache)
+        if (en.ptr == src && en.ld == ld && en.rows == rows && en.K == K && en.kmajor == kmajor && en.ns == ns) { slot = &en; break; }
+    if (slot && slot->tag == tag) {
+        slot->last_use = ++g_use;
+        *q = slot->q; *sc = slot->sc; *launches = 0;
+        return cudaSuccess;
+    }
+    if (!slot) {
+        const size_t bytes = (size_t)ns * rows * Kp + (size_t)rows * 8 + 512;
+        while (!g_cache.empty() && g_cache_bytes + bytes > cache_cap()) {          // evict least recently used
+            size_t lru = 0;
+            for (size_t i = 1; i < g_cache.size(); ++i) if (g_cache[i].last_use < g_cache[lru].last_use) lru = i;
+            cudaFree(g_cache[lru].q);
+            g_cache_bytes -= g_cache[lru].bytes;
+            g_cache.erase(g_cache.begin() + lru);
+        }
+        if (bytes > cache_cap()) {                                                  // too big to cache
+            slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc);
+            *q = ws_q; *sc = ws_sc; *launches = 3;
+            return cudaSuccess;
+        }
+        SliceEntry en{};
+        if (cudaMalloc((void **)&en.q, bytes) != cudaSuccess) { cudaGetLastError(); slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc); *q = ws_q; *sc = ws_sc; *launches = 3; return cudaSuccess; }
+        en.sc = (double *)(en.q + (((size_t)ns * rows * Kp + 255) & ~(size_t)255));
+        en.ptr = src; en.ld = ld; en.rows = rows; en.K = K; en.kmajor = kmajor; en.ns = ns; en.bytes = bytes;
+        g_cache_bytes += bytes;
+        g_cache.push_back(en);
+        slot = &g_cache.back();
+    }
+    slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, slot->q, ws_e, slot->sc);    // (re)fill in place: same buffers, new version
+    slot->tag = tag;
+    slot->last_use = ++g_use;
+    *q = slot->q; *sc = slot->sc; *launches = 3;
+    return cudaSuccess;
+}
+
 static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
-                               int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices) {
+                               int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices,
+                               uint64_t tag_a, uint64_t tag_b) {
     using namespace umma;
     // int32 exactness: (d+1)*K*2^12 < 2^31 for d <= nslices-1
     if (K * (int64_t)nslices > (1 << 19) - 1) return cudaErrorInvalidValue;
     const int64_t Kp = (K + 15) & ~15LL;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t a_bytes = al((size_t)nslices * M * Kp), b_bytes = al((size_t)nslices * N * Kp);
+    const size_t a_bytes = tag_a ? 0 : al((size_t)nslices * M * Kp), b_bytes = tag_b ? 0 : al((size_t)nslices * N * Kp);
     const size_t ea_bytes = al(M * 4), eb_bytes = al(N * 4), sa_bytes = al(M * 8), sb_bytes = al(N * 8);
     uint8_t *ws = (uint8_t *)workspace(a_bytes + b_bytes + ea_bytes + eb_bytes + sa_bytes + sb_bytes);
     if (!ws) return cudaErrorMemoryAllocation;
-    int8_t *As = (int8_t *)ws, *Bs = (int8_t *)(ws + a_bytes);
+    int8_t *ws_a = (int8_t *)ws, *ws_b = (int8_t *)(ws + a_bytes);
     int *ea = (int *)(ws + a_bytes + b_bytes), *eb = (int *)(ws + a_bytes + b_bytes + ea_bytes);
-    double *sa = (double *)(ws + a_bytes + b_bytes + ea_bytes + eb_bytes);
-    double *sb = (double *)(ws + a_bytes + b_bytes + ea_bytes + eb_bytes + sa_bytes);
+    double *ws_sa = (double *)(ws + a_bytes + b_bytes + ea_bytes + eb_bytes);
+    double *ws_sb = (double *)(ws + a_bytes + b_bytes + ea_bytes + eb_bytes + sa_bytes);
     // rows of op(A) are m: ta => stored KxM, k contiguous per m => KMAJOR.  rows of op(B)^T are n: !tb => stored KxN => KMAJOR.
-    unsigned long long *mxa = (unsigned long long *)sa, *mxb = (unsigned long long *)sb;    // scale arrays double as max scratch
-    if (ta) k_row_absmax<true><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(A, lda, (int)M, (int)K, mxa);
-    else {
-        cudaMemsetAsync(mxa, 0, M * 8, st);
-        k_row_absmax<false><<<dim3((unsigned)((M + 255) / 256), (unsigned)((K + 63) / 64)), 256, 0, st>>>(A, lda, (int)M, (int)K, mxa);
-    }
-    if (!tb) k_row_absmax<true><<<(unsigned)((N + 7) / 8), 256, 0, st>>>(B, ldb, (int)N, (int)K, mxb);
-    else {
-        cudaMemsetAsync(mxb, 0, N * 8, st);
-        k_row_absmax<false><<<dim3((unsigned)((N + 255) / 256), (unsigned)((K + 63) / 64)), 256, 0, st>>>(B, ldb, (int)N, (int)K, mxb);
-    }
-    k_row_exponent<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(mxa, (int)M, ea, sa);
-    k_row_exponent<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(mxb, (int)N, eb, sb);
-    dim3 ga((unsigned)((Kp + 127) / 128), (unsigned)((M + 31) / 32)), gb((unsigned)((Kp + 127) / 128), (unsigned)((N + 31) / 32));
-    if (ta) k_slice_i8<true><<<ga, 256, 0, st>>>(As, A, lda, (int)M, (int)K, (int)Kp, nslices, ea);
-    else k_slice_i8<false><<<ga, 256, 0, st>>>(As, A, lda, (int)M, (int)K, (int)Kp, nslices, ea);
-    if (!tb) k_slice_i8<true><<<gb, 256, 0, st>>>(Bs, B, ldb, (int)N, (int)K, (int)Kp, nslices, eb);
-    else k_slice_i8<false><<<gb, 256, 0, st>>>(Bs, B, ldb, (int)N, (int)K, (int)Kp, nslices, eb);
+    int8_t *As, *Bs;
+    double *sa, *sb;
+    int la = 0, lb = 0;
+    cudaError_t pe = prepare_operand(st, tag_a, A, lda, M, K, Kp, ta, nslices, ws_a, ea, ws_sa, &As, &sa, &la);
+    if (pe != cudaSuccess) return pe;
+    pe = prepare_operand(st, tag_b, B, ldb, N, K, Kp, !tb, nslices, ws_b, eb, ws_sb, &Bs, &sb, &lb);
+    if (pe != cudaSuccess) return pe;
+    g_chunk_launches = la + lb + 1;
     CUtensorMap mA, mB;
     OzParams P{C, ldc, alpha, beta, sa, sb, nslices};
     static int gen = -1;
