@@ -35,8 +35,9 @@ CLS_TA, CLS_IDX, CLS_CONST, CLS_TR = 0, 1, 2, 3
 IDX_NONE, IDX_EXPLICIT, IDX_TRANSPOSE = 0, 1, 2
 (OP_MUL, OP_ADD, OP_SUB, OP_NEG, OP_SUM, OP_MEAN, OP_NBCAST, OP_MAP, OP_BCAST,
  OP_BCAST_ADD, OP_BCAST_SUB, OP_BCAST_MUL) = range(1, 13)
-OP_GETINDEX = 16
-ELEMENTWISE = (OP_NBCAST, OP_MAP, OP_BCAST, OP_BCAST_ADD, OP_BCAST_SUB, OP_BCAST_MUL)
+OP_BCAST_DIV, OP_BCAST_LDIV, OP_BCAST_POW, OP_GETINDEX, OP_DOT, OP_SUMDIMS, OP_TRACKER_BCAST, OP_GETINDEX_GENERIC = range(13, 21)
+ELEMENTWISE = (OP_NBCAST, OP_MAP, OP_BCAST, OP_BCAST_ADD, OP_BCAST_SUB, OP_BCAST_MUL, OP_BCAST_DIV, OP_BCAST_LDIV, OP_BCAST_POW,
+               OP_TRACKER_BCAST)
 (E_CONST, E_ADD, E_SUB, E_MUL, E_DIV, E_NEG, E_POWI, E_POW, E_TANH, E_EXP, E_LOG, E_SQRT,
  E_SIN, E_COS, E_ABS2, E_ABS, E_MAX, E_MIN, E_INV, E_SIGMOID, E_ARG) = range(1, 22)
 
@@ -368,9 +369,15 @@ class OracleTape:
             val, part, _ = dual_eval(it.expr, self.fconst, vals, self.dtype)
             it.cache = [np.array(p, order="F") for p in part]          # results[I].partial[p]
             out[...] = val
-        elif op == OP_GETINDEX:               # tracked.jl:331-340
+        elif op in (OP_GETINDEX, OP_GETINDEX_GENERIC):   # tracked.jl:331-340,377-388
             flat = self.value[a[0].buffer].reshape(-1, order="F")
             out[...] = flat[a[0].idx].reshape(out.shape, order="F")
+        elif op == OP_DOT:                    # reductions.jl:106-112
+            self.value[it.out][...] = np.dot(self._val(a[0]).reshape(-1, order="F"), self._val(a[1]).reshape(-1, order="F"))
+        elif op == OP_SUMDIMS:                # reductions.jl:57-60
+            x = self._val(a[0])
+            axes = tuple(d for d in range(x.ndim) if out.shape[d] == 1 and x.shape[d] != 1)
+            out[...] = np.sum(x, axis=axes, keepdims=True)
         else:
             raise NotImplementedError(f"opcode {op}")
 
@@ -408,6 +415,9 @@ class OracleTape:
                 if not o.tracked:
                     continue
                 contrib = delta * it.cache[p]                         # x[i] * getpartial(results[i], p)
+                if o.cls == CLS_TR:                                   # sequential scalar accumulation (propagation.jl:98-108)
+                    self._inc(o, np.add.accumulate(contrib.reshape(-1, order="F"))[-1])
+                    continue
                 odims = tuple(o.dims) + (1,) * (nd - len(o.dims))
                 red = contrib
                 for ax in range(nd):                                  # min(bound, I): size-1 dims collapse
@@ -415,7 +425,16 @@ class OracleTape:
                         # sequential accumulation in column-major order (propagation.jl:90-95)
                         red = np.add.accumulate(red, axis=ax).take([-1], axis=ax)
                 self._inc(o, red.reshape(o.dims, order="F"))
-        elif op == OP_GETINDEX:               # tracked.jl:318-329
+        elif op == OP_DOT:                    # reductions.jl:114-131
+            dl = np.asarray(delta).reshape(())
+            if a[0].tracked:
+                self._inc(a[0], dl * self._val(a[1]).reshape(a[0].dims, order="F"))
+            if a[1].tracked:
+                self._inc(a[1], dl * self._val(a[0]).reshape(a[1].dims, order="F"))
+        elif op == OP_SUMDIMS:                # reductions.jl:48-55 ; propagation.jl:217-223
+            if a[0].tracked:
+                self._inc(a[0], np.broadcast_to(delta, a[0].dims))
+        elif op in (OP_GETINDEX, OP_GETINDEX_GENERIC):   # tracked.jl:318-329,363-376
             d = self.deriv[a[0].buffer]
             flat = d.reshape(-1, order="F")
             np.add.at(flat, a[0].idx, np.asarray(delta).reshape(-1, order="F"))

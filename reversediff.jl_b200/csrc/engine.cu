@@ -206,8 +206,10 @@ static void bump_version(rdb_tape *t, int b) {
 static uint64_t operand_tag(rdb_tape *t, const OperandPlan &o) { return o.mode == OPM_GATHER ? 0 : value_tag(t, o.rec.buffer); }
 
 static bool is_elementwise(int op) {
-    return op == OP_NBCAST || op == OP_MAP || op == OP_BCAST || op == OP_BCAST_ADD || op == OP_BCAST_SUB || op == OP_BCAST_MUL;
+    return op == OP_NBCAST || op == OP_MAP || op == OP_BCAST || op == OP_BCAST_ADD || op == OP_BCAST_SUB || op == OP_BCAST_MUL ||
+           op == OP_BCAST_DIV || op == OP_BCAST_LDIV || op == OP_BCAST_POW || op == OP_TRACKER_BCAST;
 }
+static bool is_getindex(int op) { return op == OP_GETINDEX || op == OP_GETINDEX_GENERIC; }
 
 // A matrix operand as the GEMM sees it: stored pointer, leading dimension and whether the stored matrix is the
 // transpose of the operand (folded IDX transposes cost nothing: SURVEY.md Appendix A.1 "engine-minimal").
@@ -316,9 +318,34 @@ static int forward_pass(rdb_tape *t, int order = 1) {
                 KL(t, launch_finish_sum<T>(S(t), (const T *)t->scratch, (T *)out.val, scale));
             } break;
             case OP_NBCAST: case OP_MAP: case OP_BCAST: case OP_BCAST_ADD: case OP_BCAST_SUB: case OP_BCAST_MUL:
+            case OP_BCAST_DIV: case OP_BCAST_LDIV: case OP_BCAST_POW: case OP_TRACKER_BCAST:
                 OK(expr_forward<T>(t, I, fuse_next, order));
                 break;
-            case OP_GETINDEX: {
+            case OP_DOT: {
+                MatRef<T> A, B;
+                OK(operand_value<T>(t, I.in[0], A));
+                OK(operand_value<T>(t, I.in[1], B));
+                StepTimer tm(t, "dot_forward", 2.0 * I.in[0].size * t->es, 0);
+                KL(t, launch_dot_block_sums<T>(S(t), A.ptr, B.ptr, I.in[0].size, (T *)t->scratch));
+                KL(t, launch_finish_sum<T>(S(t), (const T *)t->scratch, (T *)out.val, (T)1));
+            } break;
+            case OP_SUMDIMS: {
+                Buf &src = t->bufs[I.in[0].rec.buffer];
+                const int64_t d0 = src.dims[0], d1 = src.size / src.dims[0];
+                StepTimer tm(t, "sumdims_forward", (double)src.size * t->es, 0);
+                if (out.size == 1) {
+                    KL(t, launch_block_sums<T>(S(t), (const T *)src.val, src.size, (T *)t->scratch));
+                    KL(t, launch_finish_sum<T>(S(t), (const T *)t->scratch, (T *)out.val, (T)1));
+                } else if (out.dims[0] == 1 && out.size == d1) {            // sum(x, dims=1): column sums
+                    KL(t, launch_colsum<T>(S(t), (T *)out.val, (const T *)src.val, d0, d1, (T)1));
+                } else if (out.dims[0] == d0 && out.size == d0) {           // sum over every trailing dimension: row sums
+                    CU(cudaMemsetAsync(out.val, 0, (size_t)out.size * t->es, S(t)));
+                    KL(t, launch_mul_acc_colvec<T>(S(t), (T *)out.val, (const T *)src.val, (const T *)nullptr, d0, d1, 1, (T *)t->scratch, t->scratch_bytes / 8));
+                } else {
+                    return fail(RDB_EUNSUPPORTED, "sum over this combination of dimensions is not lowered");
+                }
+            } break;
+            case OP_GETINDEX: case OP_GETINDEX_GENERIC: {
                 Buf &src = t->bufs[I.in[0].rec.buffer];
                 StepTimer tm(t, "getindex_forward", 2.0 * out.size * t->es + 8.0 * out.size, 0);
                 KL(t, launch_gather<T>(S(t), (T *)out.val, (const T *)src.val, I.in[0].d_map, out.size));
@@ -417,6 +444,13 @@ static int expr_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
         if (same) {
             StepTimer tm(t, "expr_reverse", 4.0 * out.size * R * t->es, 0);
             KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[a], out.size, R, false));
+        } else if (o.size == 1) {
+            // scalar (TrackedReal) argument: input_deriv += sum_i x[i]*partial[i]   (propagation.jl:98-108; unbroadcast(::Number) = sum)
+            StepTimer tm(t, "expr_reverse_scalar", 2.0 * out.size * R * t->es, 0);
+            for (int64_t r = 0; r < R; ++r) {
+                KL(t, launch_dot_block_sums<T>(S(t), delta + r * out.size, (const T *)I.partial[a], out.size, (T *)t->scratch));
+                KL(t, launch_finish_sum<T>(S(t), (const T *)t->scratch, (T *)b.der + r, (T)1, true));
+            }
         } else {
             int64_t d0 = o.rec.ndims >= 1 ? o.rec.dims[0] : 1;
             bool colvec = (o.size == d0) && (d0 == out.dims[0]) && d0 > 1;
@@ -475,9 +509,28 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                 }
                 break;
             case OP_NBCAST: case OP_MAP: case OP_BCAST: case OP_BCAST_ADD: case OP_BCAST_SUB: case OP_BCAST_MUL:
+            case OP_BCAST_DIV: case OP_BCAST_LDIV: case OP_BCAST_POW: case OP_TRACKER_BCAST:
                 OK(expr_reverse<T>(t, I, R));
                 break;
-            case OP_GETINDEX:
+            case OP_DOT:
+                for (int a = 0; a < 2; ++a) {
+                    if (!I.in[a].rec.tracked) continue;
+                    Buf &b = t->bufs[I.in[a].rec.buffer];
+                    Buf &other = t->bufs[I.in[1 - a].rec.buffer];
+                    StepTimer tm(t, "dot_reverse", 3.0 * b.size * R * t->es, 0);
+                    KL(t, launch_scal_acc<T>(S(t), (T *)b.der, (const T *)other.val, delta, b.size, R));
+                }
+                break;
+            case OP_SUMDIMS:
+                if (I.in[0].rec.tracked) {
+                    Buf &b = t->bufs[I.in[0].rec.buffer];
+                    int64_t dstride[kMaxDims], st = 1;
+                    for (int d = 0; d < kMaxDims; ++d) { dstride[d] = (out.dims[d] == 1 && b.dims[d] != 1) ? 0 : st; st *= out.dims[d]; }
+                    StepTimer tm(t, "sumdims_reverse", 2.0 * b.size * R * t->es, 0);
+                    KL(t, launch_bcast_acc<T>(S(t), (T *)b.der, b.dims, dstride, delta, b.size, R, out.size));
+                }
+                break;
+            case OP_GETINDEX: case OP_GETINDEX_GENERIC:
                 if (I.in[0].rec.tracked) {
                     Buf &b = t->bufs[I.in[0].rec.buffer];
                     StepTimer tm(t, "getindex_reverse", 3.0 * out.size * R * t->es, 0);
@@ -627,9 +680,12 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
         if (I.rec.n_in < 1 || I.rec.n_in > kMaxArgs) return fail(RDB_EINVAL, "instruction %u: bad input count", i);
         if (I.rec.out < 0 || (uint32_t)I.rec.out >= h.n_buffers || t->bufs[I.rec.out].kind == BUF_CONST) return fail(RDB_EINVAL, "instruction %u: bad output", i);
         switch (op) {
-            case OP_MUL: case OP_ADD: case OP_SUB: if (I.rec.n_in != 2) return fail(RDB_EINVAL, "instruction %u: needs 2 inputs", i); break;
-            case OP_NEG: case OP_SUM: case OP_MEAN: case OP_GETINDEX: if (I.rec.n_in != 1) return fail(RDB_EINVAL, "instruction %u: needs 1 input", i); break;
-            case OP_NBCAST: case OP_MAP: case OP_BCAST: case OP_BCAST_ADD: case OP_BCAST_SUB: case OP_BCAST_MUL: break;
+            case OP_MUL: case OP_ADD: case OP_SUB: case OP_DOT: if (I.rec.n_in != 2) return fail(RDB_EINVAL, "instruction %u: needs 2 inputs", i); break;
+            case OP_NEG: case OP_SUM: case OP_MEAN: case OP_GETINDEX: case OP_GETINDEX_GENERIC: case OP_SUMDIMS:
+                if (I.rec.n_in != 1) return fail(RDB_EINVAL, "instruction %u: needs 1 input", i);
+                break;
+            case OP_NBCAST: case OP_MAP: case OP_BCAST: case OP_BCAST_ADD: case OP_BCAST_SUB: case OP_BCAST_MUL:
+            case OP_BCAST_DIV: case OP_BCAST_LDIV: case OP_BCAST_POW: case OP_TRACKER_BCAST: break;
             default:
                 // @grad / ChainRules closures, det, inv, cat, tracker_∇broadcast, scalar instructions, ... cannot be lowered
                 return fail(RDB_EUNSUPPORTED, "instruction %u: opcode %d cannot be replayed on the device (no CPU fallback)", i, op);
@@ -647,7 +703,7 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
             for (int d = 0; d < o.rec.ndims; ++d) o.size *= o.rec.dims[d];
             o.rows = o.rec.ndims >= 1 ? o.rec.dims[0] : 1;
             o.cols = o.rec.ndims >= 2 ? o.rec.dims[1] : 1;
-            const bool indexed = (o.rec.cls == CLS_IDX) || (op == OP_GETINDEX);
+            const bool indexed = (o.rec.cls == CLS_IDX) || is_getindex(op);
             if (!indexed) {
                 if (o.size != b.size) return fail(RDB_EINVAL, "instruction %u: operand/buffer size mismatch", i);
                 continue;
@@ -659,7 +715,7 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
                 continue;
             }
             if (o.rec.idx_kind != IDX_EXPLICIT) return fail(RDB_EINVAL, "instruction %u: indexed operand without a map", i);
-            const int64_t expect = op == OP_GETINDEX ? out.size : o.size;
+            const int64_t expect = is_getindex(op) ? out.size : o.size;
             if (o.rec.idx_offset < 0 || o.rec.idx_len != expect || (uint64_t)(o.rec.idx_offset + o.rec.idx_len) > h.n_idx)
                 return fail(RDB_EINVAL, "instruction %u: index map out of range", i);
             const int64_t *m = idx + o.rec.idx_offset;
@@ -678,7 +734,7 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
             if (op == OP_MUL) {
                 OK(dev_alloc(t, &o.dense_val, o.size * (int64_t)t->es));
                 if (o.rec.tracked) OK(dev_alloc(t, &o.dense_der, o.size * (int64_t)t->es));
-            } else if (op != OP_GETINDEX) {
+            } else if (!is_getindex(op)) {
                 return fail(RDB_EUNSUPPORTED, "instruction %u: index-mapped operand outside `*`/getindex", i);
             }
         }
@@ -718,8 +774,16 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
                 // results[I].partial[p] (broadcast.jl:155; elementwise.jl:239): only tracked arguments are ever read back
                 if (I.in[a].rec.tracked) OK(dev_alloc(t, &I.partial[a], out.size * (int64_t)t->es));
             }
-        } else if (op == OP_GETINDEX) {
+        } else if (is_getindex(op)) {
             if (I.in[0].mode != OPM_GATHER) return fail(RDB_EINVAL, "instruction %u: getindex without a map", i);
+        } else if (op == OP_DOT) {
+            if (out.size != 1 || I.in[0].size != I.in[1].size || I.in[0].mode != OPM_PLAIN || I.in[1].mode != OPM_PLAIN)
+                return fail(RDB_EINVAL, "instruction %u: dot shape mismatch", i);
+        } else if (op == OP_SUMDIMS) {
+            Buf &src = t->bufs[I.in[0].rec.buffer];
+            if (I.in[0].mode != OPM_PLAIN) return fail(RDB_EINVAL, "instruction %u: sum! on an index-mapped operand", i);
+            for (int d = 0; d < kMaxDims; ++d)
+                if (out.dims[d] != src.dims[d] && out.dims[d] != 1) return fail(RDB_EINVAL, "instruction %u: sum! shape mismatch", i);
         }
     }
     // reduction scratch: kReduceBlocks doubles for sums + column-reduction partials
@@ -817,6 +881,8 @@ static int ensure_second_order(rdb_tape *t) {
     if (t->second_order) return RDB_OK;
     for (auto &I : t->instrs) {
         const int op = I.rec.opcode;
+        if (!(op == OP_MUL || op == OP_ADD || op == OP_SUB || op == OP_NEG || op == OP_SUM || op == OP_MEAN || is_getindex(op) || is_elementwise(op)))
+            return fail(RDB_EUNSUPPORTED, "hessian!: opcode %d has no forward-over-reverse rule yet", op);
         if (op == OP_MUL) {
             if (I.in[0].rec.tracked && I.in[1].rec.tracked)
                 return fail(RDB_EUNSUPPORTED, "hessian!: `*` of two tracked operands is not lowered yet");
@@ -893,7 +959,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
     bool need_x_tv = false;
     for (auto &I : t->instrs)
         for (int a = 0; a < I.rec.n_in; ++a)
-            if (root(I.in[a].rec.buffer) == root(xid) && I.rec.opcode != OP_GETINDEX && (is_elementwise(I.rec.opcode) || need_tv[root(I.rec.out)]))
+            if (root(I.in[a].rec.buffer) == root(xid) && !is_getindex(I.rec.opcode) && (is_elementwise(I.rec.opcode) || need_tv[root(I.rec.out)]))
                 need_x_tv = true;
 
     void *const x_td_own = x.td;
@@ -911,7 +977,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
             Buf &o = t->bufs[I.rec.out];
             if (!need_tv[root(I.rec.out)]) continue;
             switch (I.rec.opcode) {
-                case OP_GETINDEX: {
+                case OP_GETINDEX: case OP_GETINDEX_GENERIC: {
                     Buf &src = t->bufs[I.in[0].rec.buffer];
                     StepTimer tm(t, "tangent_getindex", 1.0 * o.size * Kb * t->es, 0);
                     if (root(I.in[0].rec.buffer) == root(xid))
@@ -973,7 +1039,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
             const bool dt_zero = td_zero[root(I.rec.out)];
             const T *dt = dt_zero ? nullptr : (const T *)o.td;
             switch (I.rec.opcode) {
-                case OP_GETINDEX: {
+                case OP_GETINDEX: case OP_GETINDEX_GENERIC: {
                     const int rb = root(I.in[0].rec.buffer);
                     Buf &b = t->bufs[I.in[0].rec.buffer];
                     KL(t, launch_scatter_add<T>(S(t), (T *)b.der, b.size, I.in[0].d_map, delta, o.size, 1));

@@ -151,15 +151,44 @@ cudaError_t launch_block_sums(cudaStream_t s, const T *x, int64_t n, T *block_su
 }
 
 template <typename T>
-__global__ void __launch_bounds__(1024) k_finish_sum(const double *block_sums, T *out, double scale) {
+__global__ void __launch_bounds__(1024) k_finish_sum(const double *block_sums, T *out, double scale, int accumulate) {
     double v = 0.0;
     for (int i = threadIdx.x; i < kReduceBlocks; i += blockDim.x) v += block_sums[i];
     v = block_sum(v);
-    if (threadIdx.x == 0) out[0] = (T)(scale * v);
+    if (threadIdx.x == 0) out[0] = accumulate ? (T)((double)out[0] + scale * v) : (T)(scale * v);
 }
 template <typename T>
-cudaError_t launch_finish_sum(cudaStream_t s, const T *block_sums_, T *out, T scale) {
-    k_finish_sum<T><<<1, 1024, 0, s>>>(reinterpret_cast<const double *>(block_sums_), out, (double)scale);
+cudaError_t launch_finish_sum(cudaStream_t s, const T *block_sums_, T *out, T scale, bool accumulate) {
+    k_finish_sum<T><<<1, 1024, 0, s>>>(reinterpret_cast<const double *>(block_sums_), out, (double)scale, accumulate ? 1 : 0);
+    return cudaGetLastError();
+}
+
+// block_sums <- per-block sums of a[i]*b[i]   (dot forward, reductions.jl:106-112; scalar-argument adjoints, propagation.jl:98-108)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_dot_block_sums(const T *__restrict__ a, const T *__restrict__ b, int64_t n, double *block_sums) {
+    double local = 0.0;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += st) local += (double)(a[i] * b[i]);
+    double s = block_sum(local);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
+}
+template <typename T>
+cudaError_t launch_dot_block_sums(cudaStream_t s, const T *a, const T *b, int64_t n, T *block_sums_) {
+    k_dot_block_sums<T><<<kReduceBlocks, kThreads, 0, s>>>(a, b, n, reinterpret_cast<double *>(block_sums_));
+    return cudaGetLastError();
+}
+
+// dst[i + r*n] += delta[r]*src[i]     (dot reverse: lmul!(output_deriv, tmp); increment_deriv!, reductions.jl:114-131)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_scal_acc(T *__restrict__ dst, const T *__restrict__ src, const T *__restrict__ delta, int64_t n, int64_t R) {
+    int64_t tot = n * R;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) { int64_t r = i / n; dst[i] = dst[i] + delta[r] * src[i - r * n]; }
+}
+template <typename T>
+cudaError_t launch_scal_acc(cudaStream_t s, T *dst, const T *src, const T *delta, int64_t n, int64_t R) {
+    if (n * R <= 0) return cudaSuccess;
+    k_scal_acc<T><<<grid_for(n * R, 4), kThreads, 0, s>>>(dst, src, delta, n, R);
     return cudaGetLastError();
 }
 
@@ -562,7 +591,8 @@ k_colvec_partial(double *__restrict__ scratch, const T *__restrict__ delta, cons
     const T *dl = delta + r * d0 * d1;
     double acc = 0.0;
 #pragma unroll 4
-    for (int64_t j = j0; j < j1; ++j) acc += (double)(dl[i + j * d0] * partial[i + j * d0]);
+    if (partial) { for (int64_t j = j0; j < j1; ++j) acc += (double)(dl[i + j * d0] * partial[i + j * d0]); }
+    else { for (int64_t j = j0; j < j1; ++j) acc += (double)dl[i + j * d0]; }
     scratch[(c * R + r) * d0 + i] = acc;
 }
 template <typename T>
@@ -626,6 +656,31 @@ cudaError_t launch_mul_acc_generic(cudaStream_t s, T *dst, int64_t dst_n, const 
     GenericIdx g;
     for (int d = 0; d < kMaxDims; ++d) { g.dims[d] = dims[d]; g.dst_stride[d] = dst_stride[d]; }
     k_mul_acc_generic<T><<<grid_for(n * R, 2), kThreads, 0, s>>>(dst, dst_n, g, delta, partial, n, R);
+    return cudaGetLastError();
+}
+
+// dst[i + r*n] += delta[clamp(i) + r*delta_n]   (reduction_increment_deriv!, propagation.jl:217-223: the adjoint of sum over dims)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_bcast_acc(T *__restrict__ dst, GenericIdx g, const T *__restrict__ delta, int64_t n, int64_t R, int64_t delta_n) {
+    int64_t tot = n * R;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) {
+        int64_t r = i / n, e = i - r * n, rem = e, off = 0;
+#pragma unroll
+        for (int d = 0; d < kMaxDims; ++d) {
+            off += (rem % g.dims[d]) * g.dst_stride[d];
+            rem /= g.dims[d];
+        }
+        dst[i] = dst[i] + delta[off + r * delta_n];
+    }
+}
+template <typename T>
+cudaError_t launch_bcast_acc(cudaStream_t s, T *dst, const int64_t *dims, const int64_t *delta_stride, const T *delta, int64_t n, int64_t R, int64_t delta_n) {
+    if (n * R <= 0) return cudaSuccess;
+    GenericIdx g;
+    for (int d = 0; d < kMaxDims; ++d) { g.dims[d] = dims[d]; g.dst_stride[d] = delta_stride[d]; }
+    k_bcast_acc<T><<<grid_for(n * R, 2), kThreads, 0, s>>>(dst, g, delta, n, R, delta_n);
     return cudaGetLastError();
 }
 
@@ -837,7 +892,10 @@ cudaError_t launch_copy2d(cudaStream_t s, T *dst, int64_t ldd, const T *src, int
     template cudaError_t launch_fill<T>(cudaStream_t, T *, int64_t, T);                                                   \
     template cudaError_t launch_add<T>(cudaStream_t, T *, const T *, const T *, T, int64_t, T *);                         \
     template cudaError_t launch_block_sums<T>(cudaStream_t, const T *, int64_t, T *);                                     \
-    template cudaError_t launch_finish_sum<T>(cudaStream_t, const T *, T *, T);                                           \
+    template cudaError_t launch_finish_sum<T>(cudaStream_t, const T *, T *, T, bool);                                     \
+    template cudaError_t launch_dot_block_sums<T>(cudaStream_t, const T *, const T *, int64_t, T *);                      \
+    template cudaError_t launch_scal_acc<T>(cudaStream_t, T *, const T *, const T *, int64_t, int64_t);                   \
+    template cudaError_t launch_bcast_acc<T>(cudaStream_t, T *, const int64_t *, const int64_t *, const T *, int64_t, int64_t, int64_t); \
     template cudaError_t launch_axpy<T>(cudaStream_t, T *, const T *, T, int64_t, bool);                                  \
     template cudaError_t launch_acc_scalar<T>(cudaStream_t, T *, int64_t, int64_t, const T *, T, bool);                   \
     template cudaError_t launch_expr_forward<T>(cudaStream_t, const ExprParams &);                                        \

@@ -65,7 +65,13 @@ template <typename T> cudaError_t launch_add(cudaStream_t, T *out, const T *a, c
 // block_sums <- per-block sums of x  (sum / mean forward, reductions.jl:23-27,81-85)
 template <typename T> cudaError_t launch_block_sums(cudaStream_t, const T *x, int64_t n, T *block_sums);
 // out[0] = scale * sum(block_sums[0..kReduceBlocks))
-template <typename T> cudaError_t launch_finish_sum(cudaStream_t, const T *block_sums, T *out, T scale);
+template <typename T> cudaError_t launch_finish_sum(cudaStream_t, const T *block_sums, T *out, T scale, bool accumulate = false);
+// block_sums <- per-block sums of a[i]*b[i]
+template <typename T> cudaError_t launch_dot_block_sums(cudaStream_t, const T *a, const T *b, int64_t n, T *block_sums);
+// dst[i + r*n] += delta[r]*src[i]
+template <typename T> cudaError_t launch_scal_acc(cudaStream_t, T *dst, const T *src, const T *delta, int64_t n, int64_t R);
+// dst[i + r*n] += delta[clamp(i) + r*delta_n], clamp given by per-dimension strides of delta (0 on reduced dims)
+template <typename T> cudaError_t launch_bcast_acc(cudaStream_t, T *dst, const int64_t *dims, const int64_t *delta_stride, const T *delta, int64_t n, int64_t R, int64_t delta_n);
 // dst (+)= sign*src over n elements (increment_deriv!/decrement_deriv!, propagation.jl:33-73)
 template <typename T> cudaError_t launch_axpy(cudaStream_t, T *dst, const T *src, T sign, int64_t n, bool overwrite);
 // dst[i + r*n] (+)= scale*delta[r]   (sum/mean reverse: scalar adjoint broadcast, reductions.jl:15-21,73-79)

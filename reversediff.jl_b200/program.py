@@ -54,12 +54,20 @@ OP_BCAST = 9      # broadcast(@forward f, ...)  elementwise.jl:230-310
 OP_BCAST_ADD = 10  # (broadcast,+)  elementwise.jl:449-455
 OP_BCAST_SUB = 11  # (broadcast,-)  elementwise.jl:480-486
 OP_BCAST_MUL = 12  # (broadcast,*)  elementwise.jl:511-517
+OP_BCAST_DIV = 13  # (broadcast,/)  elementwise.jl:555-563
+OP_BCAST_LDIV = 14  # (broadcast,\\) elementwise.jl:594-602
+OP_BCAST_POW = 15  # (broadcast,^)  elementwise.jl:651-659
 OP_GETINDEX = 16  # getindex       tracked.jl:308-316
+OP_DOT = 17       # dot            linalg/reductions.jl:91-104
+OP_SUMDIMS = 18   # sum!/sum(x,dims) linalg/reductions.jl:32-46
+OP_TRACKER_BCAST = 19  # tracker_∇broadcast (a plain Real or TrackedReal among the args)  broadcast.jl:229-238
+OP_GETINDEX_GENERIC = 20  # (getindex, Val(:generic)): integer-vector indices  tracked.jl:352-362
 OP_NAMES = {
     OP_MUL: "*", OP_ADD: "+", OP_SUB: "-", OP_NEG: "neg", OP_SUM: "sum", OP_MEAN: "mean",
     OP_NBCAST: "∇broadcast", OP_MAP: "map", OP_BCAST: "broadcast",
     OP_BCAST_ADD: "(broadcast,+)", OP_BCAST_SUB: "(broadcast,-)", OP_BCAST_MUL: "(broadcast,*)",
-    OP_GETINDEX: "getindex",
+    OP_GETINDEX: "getindex", OP_BCAST_DIV: "(broadcast,/)", OP_BCAST_LDIV: "(broadcast,\\)", OP_BCAST_POW: "(broadcast,^)",
+    OP_DOT: "dot", OP_SUMDIMS: "sum!", OP_TRACKER_BCAST: "tracker_∇broadcast", OP_GETINDEX_GENERIC: "(getindex,:generic)",
 }
 
 # scalar-expression bytecode: SSA, 4 x int32 per op = (code, a, b, imm) -----------------

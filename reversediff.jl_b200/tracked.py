@@ -294,10 +294,13 @@ def record_plusminus(opcode, x, y):
 
 
 # --------------------------------------------------------------------------------- reductions
-def sum(x):  # noqa: A001 - mirrors Base.sum
-    """``Base.sum(::TrackedArray)`` (``linalg/reductions.jl:8-13``)."""
+def sum(x, dims=None):  # noqa: A001 - mirrors Base.sum
+    """``Base.sum(::TrackedArray)`` (``linalg/reductions.jl:8-13``); ``sum(x, dims)`` records a ``sum!`` instruction
+    (``:39-46``).  ``dims`` is 1-based like Julia's."""
     if not isinstance(x, TrackedArray):
-        return np.sum(x)
+        return np.sum(x) if dims is None else np.sum(x, axis=tuple(d - 1 for d in np.atleast_1d(dims)), keepdims=True)
+    if dims is not None:
+        return record_sum_dims(x, dims)
     tp = x.tape
     out = _track_new(np.sum(x.value), tp)
     tp.record(P.OP_SUM, [_capture(x, tp)], out.buffer)
@@ -314,6 +317,30 @@ def mean(x):
     return out
 
 
+def record_sum_dims(x, dims):
+    dims = tuple(int(d) for d in np.atleast_1d(dims))
+    if any(d < 1 or d > x.ndim for d in dims):
+        raise ValueError("sum: dims out of range")
+    tp = x.tape
+    out = _track_new(np.sum(x.value, axis=tuple(d - 1 for d in dims), keepdims=True), tp)
+    # cache = index_bound(out, x)   (reductions.jl:43)
+    tp.record(P.OP_SUMDIMS, [P.Operand(x.buffer, P.CLS_TA, True, x.shape, bound=out.shape)], out.buffer)
+    return out
+
+
+def dot(x, y):
+    """``LinearAlgebra.dot`` (``linalg/reductions.jl:91-104``)."""
+    if isinstance(x, Adjoint) or isinstance(y, Adjoint):
+        raise TypeError("dot of lazy adjoints is not lowered")
+    tp = _tape_of(x, y)
+    vx, vy = np.asarray(value(x)), np.asarray(value(y))
+    if vx.size != vy.size:
+        raise ValueError("dot needs equal lengths")
+    out = _track_new(np.dot(vx.reshape(-1, order="F"), vy.reshape(-1, order="F")), tp)
+    tp.record(P.OP_DOT, [_capture(x, tp), _capture(y, tp)], out.buffer)
+    return out
+
+
 # ------------------------------------------------------------------------- elementwise closures
 def _bshape(shapes):
     return np.broadcast_shapes(*shapes)
@@ -324,9 +351,9 @@ def _record_elementwise(opcode, f, args, require_same_shape=False):
     for a in args:
         if isinstance(a, Adjoint):
             raise TypeError("elementwise operations on lazy adjoints are not lowered")
-        if isinstance(a, TrackedReal) or np.ndim(value(a)) == 0:
-            raise TypeError("scalar (Real/TrackedReal) broadcast arguments select the :tracker implementation "
-                            "(broadcast.jl:68-85), which is not lowered yet")
+        if (isinstance(a, TrackedReal) or np.ndim(value(a)) == 0) and opcode != P.OP_TRACKER_BCAST:
+            raise TypeError("scalar (Real/TrackedReal) arguments are only valid in dot-broadcasts (the :tracker implementation, "
+                            "broadcast.jl:68-85)")
     shapes = [tuple(np.shape(value(a))) for a in args]
     if require_same_shape and any(s != shapes[0] for s in shapes):
         raise ValueError("map needs equal shapes")
@@ -351,7 +378,26 @@ def bcast(f, *args):
     (``broadcast.jl:86-94,142-162``).  Partials are taken w.r.t. every array argument."""
     if isinstance(f, ForwardOptimize):
         f = f.f
+    # get_implementation (broadcast.jl:68-85): any plain Real / TrackedReal argument selects tracker_∇broadcast
+    if any(isinstance(a, TrackedReal) or np.ndim(value(a)) == 0 for a in args):
+        return _record_tracker_bcast(f, args)
     return _record_elementwise(P.OP_NBCAST, f, args)
+
+
+def _record_tracker_bcast(f, args):
+    """``tracker_∇broadcast`` (``broadcast.jl:229-260``).  Plain ``Real`` arguments carry no adjoint (``dual(x, p) = x`` only for
+    non-Reals... a plain Real IS dualised but its adjoint is discarded by ``_add_to_deriv!``), so they are closed over as literals;
+    ``TrackedReal`` arguments stay operands (class TR) whose adjoint is the full reduction ``unbroadcast(::Number, Δ) = sum(Δ)``."""
+    live, slots = [], []
+    for a in args:
+        if isinstance(a, (TrackedArray, TrackedReal)) or np.ndim(value(a)) > 0:
+            slots.append(len(live)); live.append(a)
+        else:
+            slots.append(float(a))
+
+    def g(*xs):
+        return f(*[xs[s] if isinstance(s, int) else s for s in slots])
+    return _record_elementwise(P.OP_TRACKER_BCAST, g, live)
 
 
 def map_(f, *args):
@@ -364,19 +410,20 @@ def map_(f, *args):
 
 
 _INFIX = {"+": (P.OP_BCAST_ADD, lambda a, b: a + b), "-": (P.OP_BCAST_SUB, lambda a, b: a - b),
-          "*": (P.OP_BCAST_MUL, lambda a, b: a * b)}
+          "*": (P.OP_BCAST_MUL, lambda a, b: a * b), "/": (P.OP_BCAST_DIV, lambda a, b: a / b),
+          "\\": (P.OP_BCAST_LDIV, lambda a, b: b / a), "^": (P.OP_BCAST_POW, lambda a, b: a ** b)}
 
 
 def broadcast(f, *args):
     """``broadcast(f::ForwardOptimize, x[, y])`` (``elementwise.jl:230-310``) and the built-in
-    infix instructions ``broadcast(+|-|*, x, y)`` (``elementwise.jl:449-537``)."""
+    infix instructions ``broadcast(+|-|*|/|\\|^, x, y)`` (``elementwise.jl:449-685``)."""
     if isinstance(f, str):
         if f not in _INFIX or len(args) != 2:
             raise TypeError(f"unsupported infix broadcast {f!r}")
         op, fn = _INFIX[f]
         return _record_elementwise(op, fn, args)
     if not isinstance(f, ForwardOptimize):
-        raise TypeError("broadcast lowers only @forward closures or '+', '-', '*'")
+        raise TypeError("broadcast lowers only @forward closures or '+', '-', '*', '/', '\\\\', '^'")
     if len(args) not in (1, 2):
         raise TypeError("broadcast of a @forward closure takes 1 or 2 arrays")
     return _record_elementwise(P.OP_BCAST, f.f, args)
@@ -388,21 +435,29 @@ def record_getindex(t: TrackedArray, key):
     (``index_iterable``, ``:291-306``) is shipped as an explicit 0-based linear map."""
     if not isinstance(key, tuple):
         key = (key,)
-    if any(isinstance(k, (int, np.integer)) for k in key):
+    if all(isinstance(k, (int, np.integer)) for k in key):
         raise TypeError("scalar getindex yields an origin-linked TrackedReal (tracked.jl:348-351); "
                         "scalar tapes are not lowered yet")
-    if not all(isinstance(k, slice) for k in key):
-        raise TypeError("only range/colon getindex is lowered")
+    generic = not all(isinstance(k, slice) for k in key)
+    if generic:
+        # (getindex, Val(:generic)): Integer / Colon / integer-vector per dimension (tracked.jl:352-362)
+        key = tuple(np.asarray(k, dtype=np.int64) if isinstance(k, (list, np.ndarray)) else k for k in key)
+        if not all(isinstance(k, (slice, int, np.integer, np.ndarray)) for k in key):
+            raise TypeError("unsupported index type")
     lin = np.arange(t.size, dtype=np.int64).reshape(t.shape, order="F")
     if len(key) == 1 and t.ndim > 1:
         sub = lin.reshape(-1, order="F")[key[0]]       # linear indexing x[a:b]
     else:
         if len(key) != t.ndim:
             raise IndexError("wrong number of indices")
-        sub = lin[key]
+        if generic:                                    # Julia indexes the outer product of the per-dimension index sets
+            sub = lin[np.ix_(*[np.arange(t.shape[d])[k] if isinstance(k, slice) else np.atleast_1d(k) for d, k in enumerate(key)])]
+            sub = sub.reshape([n for n, k in zip(sub.shape, key) if not isinstance(k, (int, np.integer))], order="F")
+        else:
+            sub = lin[key]
     m = np.ascontiguousarray(sub.reshape(-1, order="F"))
     tp = t.tape
     out = _track_new(t.value.reshape(-1, order="F")[m].reshape(sub.shape, order="F"), tp)
     op = P.Operand(t.buffer, P.CLS_TA, True, t.shape, P.IDX_EXPLICIT, m)
-    tp.record(P.OP_GETINDEX, [op], out.buffer)
+    tp.record(P.OP_GETINDEX_GENERIC if generic else P.OP_GETINDEX, [op], out.buffer)
     return out

@@ -226,7 +226,8 @@ def _cases(rd):
 
 
 @pytest.mark.parametrize("name", ["a*b", "a'*b", "a*b'", "a'*b'", "a+b", "a-b", "-a", "bcast*", "bcast-", "map", "nbcast_fns",
-                                  "getindex", "reshape"])
+                                  "getindex", "reshape", "bcast/", "bcast\\", "bcast^", "dot", "sum_dims1", "sum_dims2", "tracker_real",
+                                  "tracker_trackedreal", "getindex_generic"])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_instruction(rd, orc, name, dtype):
     rng = np.random.default_rng(11)

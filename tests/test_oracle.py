@@ -170,6 +170,15 @@ CASES = {
     "nbcast_fns": lambda rd: (lambda a, b: rd.sum(rd.bcast(lambda x, y: rd.log(x + 1.5) * rd.sqrt(y + 0.5) + rd.logistic(x) - rd.cos(y) ** 3, a, b))),
     "getindex": lambda rd: (lambda a, b: rd.sum(a[0:2, :] @ b[:, 1:3])),
     "reshape": lambda rd: (lambda a, b: rd.sum(a.reshape(9) + b.reshape(9))),
+    "bcast/": lambda rd: (lambda a, b: rd.sum(rd.broadcast("/", a, rd.bcast(lambda y: y + 1.0, b)))),
+    "bcast\\": lambda rd: (lambda a, b: rd.sum(rd.broadcast("\\", rd.bcast(lambda y: y + 1.0, a), b))),
+    "bcast^": lambda rd: (lambda a, b: rd.sum(rd.broadcast("^", rd.bcast(lambda y: y + 0.5, a), b))),
+    "dot": lambda rd: (lambda a, b: rd.dot(a, b)),
+    "sum_dims1": lambda rd: (lambda a, b: rd.dot(rd.sum(a, dims=1), rd.sum(b, dims=1))),
+    "sum_dims2": lambda rd: (lambda a, b: rd.sum(rd.broadcast("*", rd.sum(a, dims=2), b))),
+    "tracker_real": lambda rd: (lambda a, b: rd.sum(rd.bcast(lambda u, c, v: u * c + rd.tanh(v), a, 2.5, b))),
+    "tracker_trackedreal": lambda rd: (lambda a, b: rd.sum(rd.bcast(lambda u, s: u * s, a, rd.sum(b)))),
+    "getindex_generic": lambda rd: (lambda a, b: rd.sum(a[[0, 2, 2], :] @ b[:, [1, 2]])),
 }
 
 
@@ -227,7 +236,7 @@ def test_capture_freezes_constants(rd, orc):
 def test_recorder_rejections(rd):
     x = np.ones(3)
     with pytest.raises(TypeError):
-        rd.GradientTape(lambda v: rd.sum(rd.bcast(lambda a, b: a * b, v, 2.0)), x)     # plain Real arg -> :tracker
+        rd.GradientTape(lambda v: rd.sum(rd.map_(rd.forward(lambda a, b: a * b), v, 2.0)), x)   # map needs arrays
     with pytest.raises(TypeError):
         rd.GradientTape(lambda v: v[0], x)                                            # scalar getindex
     with pytest.raises(TypeError):
