@@ -204,6 +204,37 @@ def test_cfg5_hessian(rd, orc, n, block):
         assert np.array_equal(part, H[:, 3:7])
 
 
+def test_hessian_vs_reference_algorithm(rd):
+    """Forward-over-reverse on the array tape (engine) against the reference's reverse-over-reverse on a scalar tape
+    (oracle/scalar_tape.py, literal restatement of api/tape.jl:285-293): same Hessian to 1e-12."""
+    from oracle import scalar_tape as st
+    from test_oracle import _rosen_scalar
+    n = 16
+    x = rd.workloads.inputs_rosenbrock(n, seed=2)
+    ct = rd.compile(rd.HessianTape(rd.workloads.f_rosenbrock, rd.workloads.inputs_rosenbrock(n, seed=1)))
+    H = rd.hessian(ct, x)
+    _, _, Href = st.hessian_reverse_over_reverse(_rosen_scalar, x)
+    assert relerr(H, np.array(Href)) < 1e-12
+    # a tape with `*` by a constant matrix, +, and a two-argument closure of tanh/exp
+    rng = np.random.default_rng(5)
+    m = 7
+    A = rng.random((m, m)) / m
+    f = lambda v: rd.sum(rd.map_(rd.forward(lambda u, w: rd.tanh(u) * w + u * u * rd.exp(-w)), A @ v + v, v))
+
+    def f_scalar(v):
+        s = 0.0
+        for i in range(m):
+            u = v[i]
+            for j in range(m):
+                u = u + float(A[i, j]) * v[j]
+            s = s + (st.tanh(u) * v[i] + u * u * st.exp(-v[i]))
+        return s
+    x = rng.random(m)
+    H = rd.hessian(rd.compile(rd.HessianTape(f, rng.random(m))), x)
+    _, _, Href = st.hessian_reverse_over_reverse(f_scalar, x)
+    assert relerr(H, np.array(Href)) < 1e-12
+
+
 def test_hessian_general_tape_vs_fd(rd, orc):
     """A tape with `*` by constants, +, elementwise closures: forward-over-reverse vs finite differences of the oracle."""
     rng = np.random.default_rng(5)

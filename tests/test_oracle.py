@@ -256,3 +256,32 @@ def test_uncompiled_replay_is_refused(rd):
     tape = rd.GradientTape(lambda v: rd.sum(v + v), np.ones(3))
     with pytest.raises(TypeError):
         rd.gradient_(np.zeros(3), tape, np.ones(3))
+
+
+# ------------------------------------------------------------------ the reference's own Hessian algorithm (reverse-over-reverse)
+def _rosen_scalar(v):
+    s = 0.0
+    for i in range(0, len(v), 2):
+        o, e = v[i], v[i + 1]
+        s = s + (100.0 * (e - o ** 2) ** 2 + (1.0 - o) ** 2)
+    return s
+
+
+def test_scalar_tape_reverse_over_reverse_rosenbrock(rd, orc):
+    """oracle/scalar_tape.py restates HessianTape literally (api/tape.jl:285-293); pin it on the closed form and on the
+    array-tape oracle's gradient."""
+    from oracle import scalar_tape as st
+    n = 12
+    x = rd.workloads.inputs_rosenbrock(n, seed=2)
+    val, g, H = st.hessian_reverse_over_reverse(_rosen_scalar, x)
+    H = np.array(H)
+    o, e = x[0::2], x[1::2]
+    Hcf = np.zeros((n, n)); idx = np.arange(n // 2)
+    Hcf[2 * idx, 2 * idx] = 1200 * o ** 2 - 400 * e + 2
+    Hcf[2 * idx, 2 * idx + 1] = Hcf[2 * idx + 1, 2 * idx] = -400 * o
+    Hcf[2 * idx + 1, 2 * idx + 1] = 200
+    assert relerr(H, Hcf) < 1e-14
+    assert np.all(H[Hcf == 0] == 0.0)
+    tape = rd.HessianTape(rd.workloads.f_rosenbrock, x)
+    oval, (og,) = orc.OracleTape(tape.program_bytes()).gradient([x])
+    assert relerr(g, og) < 1e-14 and abs(val - oval) < 1e-13 * abs(oval)
