@@ -54,9 +54,11 @@ struct rdb_ctx {
     bool own_stream = true;
     int refs = 1;          // the handle itself + one per live tape: destruction order is the caller's business
     int gemm_f64_mode = 0, ozaki_slices = 0;   // for rdb_gemm on this context
+    cudaStream_t copy_stream = nullptr;        // device->host result copies that overlap the tail of the reverse sweep
 };
 static void ctx_release(rdb_ctx *c) {
     if (!c || --c->refs > 0) return;
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -125,6 +127,16 @@ struct rdb_tape {
     std::vector<StepStat> stats;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool forward_valid = false;
+    // early result extraction (gradient! with host results): deriv(input) is copied out as soon as its last accumulation of
+    // the reverse sweep has been issued, overlapping the remaining instructions
+    struct Early {
+        bool enabled = false;
+        std::vector<int> remaining;          // per buffer: accumulations still to come in this sweep
+        std::vector<void *> dst;             // per buffer: host destination (nullptr = none)
+        std::vector<char> issued;
+        cudaEvent_t ev[kMaxArgs * 2] = {nullptr};
+        int n_ev = 0;
+    } early;
 };
 
 static cudaStream_t S(rdb_tape *t) { return t->ctx->stream; }
@@ -360,6 +372,24 @@ static int forward_pass(rdb_tape *t, int order = 1) {
 }
 
 // ------------------------------------------------------------------------------------------ reverse
+// called after every accumulation into deriv(buffer): when it was the last one of this sweep for a tape input whose result is
+// wanted on the host, start the D2H copy on the copy stream right away
+static int acc_done(rdb_tape *t, int b) {
+    if (!t->early.enabled) return RDB_OK;
+    while (t->bufs[b].alias_of >= 0) b = t->bufs[b].alias_of;
+    if (!t->early.dst[b] || t->early.issued[b]) return RDB_OK;
+    if (--t->early.remaining[b] > 0) return RDB_OK;
+    if (t->early.n_ev >= kMaxArgs * 2) return RDB_OK;
+    cudaEvent_t &ev = t->early.ev[t->early.n_ev];
+    if (!ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    t->early.n_ev++;
+    CU(cudaEventRecord(ev, S(t)));
+    CU(cudaStreamWaitEvent(t->ctx->copy_stream, ev, 0));
+    CU(cudaMemcpyAsync(t->early.dst[b], t->bufs[b].der, (size_t)t->bufs[b].size * t->es, cudaMemcpyDeviceToHost, t->ctx->copy_stream));
+    t->early.issued[b] = 1;
+    return RDB_OK;
+}
+
 template <typename T>
 static int unseed(rdb_tape *t, Buf &b, int64_t R) {
     CU(cudaMemsetAsync(b.der, 0, (size_t)(b.size * R) * t->es, S(t)));
@@ -402,6 +432,7 @@ static int mul_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
                 KL(t, launch_scatter_add<T>(S(t), (T *)ba.der + r * ba.size, ba.size, oa.d_map, (const T *)oa.dense_der, oa.size, 1));
             }
         }
+        OK(acc_done(t, oa.rec.buffer));
     }
     if (ob.rec.tracked) {
         Buf &bb = t->bufs[ob.rec.buffer];
@@ -423,6 +454,7 @@ static int mul_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
                 }
             }
         }
+        OK(acc_done(t, ob.rec.buffer));
     }
     return RDB_OK;
 }
@@ -471,6 +503,7 @@ static int expr_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
                                                 out.size, R));
             }
         }
+        OK(acc_done(t, o.rec.buffer));
     }
     return RDB_OK;
 }
@@ -491,12 +524,14 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                     T sign = (a == 1 && I.rec.opcode == OP_SUB) ? (T)-1 : (T)1;
                     StepTimer tm(t, "add_reverse", 3.0 * out.size * R * t->es, 0);
                     KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, sign, out.size * R, false));
+                    OK(acc_done(t, I.in[a].rec.buffer));
                 }
                 break;
             case OP_NEG:
                 if (I.in[0].rec.tracked) {
                     Buf &b = t->bufs[I.in[0].rec.buffer];
                     KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, (T)-1, out.size * R, false));
+                    OK(acc_done(t, I.in[0].rec.buffer));
                 }
                 break;
             case OP_SUM:
@@ -506,6 +541,7 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                     T scale = I.rec.opcode == OP_MEAN ? (T)1 / (T)I.in[0].size : (T)1;
                     StepTimer tm(t, "sum_reverse", 2.0 * b.size * R * t->es, 0);
                     KL(t, launch_acc_scalar<T>(S(t), (T *)b.der, b.size, R, delta, scale, false));
+                    OK(acc_done(t, I.in[0].rec.buffer));
                 }
                 break;
             case OP_NBCAST: case OP_MAP: case OP_BCAST: case OP_BCAST_ADD: case OP_BCAST_SUB: case OP_BCAST_MUL:
@@ -519,6 +555,7 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                     Buf &other = t->bufs[I.in[1 - a].rec.buffer];
                     StepTimer tm(t, "dot_reverse", 3.0 * b.size * R * t->es, 0);
                     KL(t, launch_scal_acc<T>(S(t), (T *)b.der, (const T *)other.val, delta, b.size, R));
+                    OK(acc_done(t, I.in[a].rec.buffer));
                 }
                 break;
             case OP_SUMDIMS:
@@ -528,6 +565,7 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                     for (int d = 0; d < kMaxDims; ++d) { dstride[d] = (out.dims[d] == 1 && b.dims[d] != 1) ? 0 : st; st *= out.dims[d]; }
                     StepTimer tm(t, "sumdims_reverse", 2.0 * b.size * R * t->es, 0);
                     KL(t, launch_bcast_acc<T>(S(t), (T *)b.der, b.dims, dstride, delta, b.size, R, out.size));
+                    OK(acc_done(t, I.in[0].rec.buffer));
                 }
                 break;
             case OP_GETINDEX: case OP_GETINDEX_GENERIC:
@@ -535,6 +573,7 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                     Buf &b = t->bufs[I.in[0].rec.buffer];
                     StepTimer tm(t, "getindex_reverse", 3.0 * out.size * R * t->es, 0);
                     KL(t, launch_scatter_add<T>(S(t), (T *)b.der, b.size, I.in[0].d_map, delta, out.size, R));
+                    OK(acc_done(t, I.in[0].rec.buffer));
                 }
                 break;
             default:
@@ -812,14 +851,41 @@ static int seed_scalar_and_reverse(rdb_tape *t) {
 template <typename T>
 static int gradient_impl(rdb_tape *t, void *const *result_ptrs, int on_device, void *value_out) {
     OK(forward_pass<T>(t));
-    OK(seed_scalar_and_reverse<T>(t));
-    for (size_t i = 0; i < t->inputs.size(); ++i) {                          // extract_result!
+    if (value_out) CU(cudaMemcpyAsync(value_out, t->bufs[t->output].val, t->es, cudaMemcpyDeviceToHost, S(t)));
+    // host results: plan the early copies (extract_result!, api/utils.jl:77-100, overlapped with the rest of the sweep)
+    auto &E = t->early;
+    E.enabled = false;
+    if (!on_device && result_ptrs) {
+        if (!t->ctx->copy_stream) CU(cudaStreamCreateWithFlags(&t->ctx->copy_stream, cudaStreamNonBlocking));
+        E.remaining.assign(t->bufs.size(), 0);
+        E.dst.assign(t->bufs.size(), nullptr);
+        E.issued.assign(t->bufs.size(), 0);
+        E.n_ev = 0;
+        auto root = [&](int b) { while (t->bufs[b].alias_of >= 0) b = t->bufs[b].alias_of; return b; };
+        for (auto &I : t->instrs)
+            for (int a = 0; a < I.rec.n_in; ++a)
+                if (I.in[a].rec.tracked) E.remaining[root(I.in[a].rec.buffer)]++;
+        bool distinct = true;
+        for (size_t i = 0; i < t->inputs.size(); ++i) {
+            int r = root(t->inputs[i]);
+            if (result_ptrs[i] && E.dst[r]) distinct = false;      // two result slots alias one buffer: keep the plain path
+            if (result_ptrs[i]) E.dst[r] = result_ptrs[i];
+        }
+        E.enabled = distinct;
+    }
+    int rc = seed_scalar_and_reverse<T>(t);
+    E.enabled = false;
+    OK(rc);
+    for (size_t i = 0; i < t->inputs.size(); ++i) {                          // extract_result! for whatever was not copied early
         if (!result_ptrs || !result_ptrs[i]) continue;
+        int r = t->inputs[i];
+        while (t->bufs[r].alias_of >= 0) r = t->bufs[r].alias_of;
+        if (!on_device && !E.issued.empty() && E.issued[r] && E.dst[r] == result_ptrs[i]) continue;
         Buf &b = t->bufs[t->inputs[i]];
         CU(cudaMemcpyAsync(result_ptrs[i], b.der, (size_t)b.size * t->es, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, S(t)));
     }
-    if (value_out) CU(cudaMemcpyAsync(value_out, t->bufs[t->output].val, t->es, cudaMemcpyDeviceToHost, S(t)));
     CU(cudaStreamSynchronize(S(t)));
+    if (t->ctx->copy_stream) CU(cudaStreamSynchronize(t->ctx->copy_stream));
     return RDB_OK;
 }
 
