@@ -127,6 +127,9 @@ struct rdb_tape {
     std::vector<StepStat> stats;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool forward_valid = false;
+    // whole-sweep CUDA graph for launch-bound tapes (the 100x100 config is ~25 launches of a few microseconds each)
+    cudaGraphExec_t gexec = nullptr;
+    int graph_state = 0;           // 0 = first call runs eagerly (warms every lazy allocation), 1 = capture next, 2 = ready, -1 = off
     // early result extraction (gradient! with host results): deriv(input) is copied out as soon as its last accumulation of
     // the reverse sweep has been issued, overlapping the remaining instructions
     struct Early {
@@ -848,8 +851,55 @@ static int seed_scalar_and_reverse(rdb_tape *t) {
     return reverse_pass<T>(t, 1);
 }
 
+static bool graph_eligible(rdb_tape *t) {
+    if (!t->opts.use_graph || t->opts.profile || S(t) == nullptr) return false;     // the legacy default stream cannot be captured
+    int64_t elems = 0;
+    for (auto &b : t->bufs) elems += b.size;
+    return elems <= (1 << 20);                                                       // launch-bound tapes only
+}
+
+// forward sweep + seeded reverse sweep as ONE graph launch; returns 1 if the graph ran, 0 if the caller must run eagerly
+template <typename T>
+static int graph_sweep(rdb_tape *t) {
+    if (t->graph_state == 2) {
+        CU(cudaGraphLaunch(t->gexec, S(t)));
+        t->launches += 1;
+        return 1;
+    }
+    if (t->graph_state == 0) { t->graph_state = 1; return 0; }
+    if (t->graph_state != 1) return 0;
+    t->graph_state = -1;
+    if (cudaStreamBeginCapture(S(t), cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int rc = forward_pass<T>(t);
+    if (rc == RDB_OK) rc = seed_scalar_and_reverse<T>(t);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(S(t), &g);
+    if (rc != RDB_OK || e != cudaSuccess || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); return 0; }
+    e = cudaGraphInstantiate(&t->gexec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { cudaGetLastError(); t->gexec = nullptr; return 0; }
+    t->graph_state = 2;
+    CU(cudaGraphLaunch(t->gexec, S(t)));
+    t->launches += 1;
+    return 1;
+}
+
 template <typename T>
 static int gradient_impl(rdb_tape *t, void *const *result_ptrs, int on_device, void *value_out) {
+    if (graph_eligible(t)) {
+        int ran = graph_sweep<T>(t);
+        if (ran < 0) return ran;
+        if (ran == 1) {
+            for (size_t i = 0; i < t->inputs.size(); ++i) {
+                if (!result_ptrs || !result_ptrs[i]) continue;
+                Buf &b = t->bufs[t->inputs[i]];
+                CU(cudaMemcpyAsync(result_ptrs[i], b.der, (size_t)b.size * t->es, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, S(t)));
+            }
+            if (value_out) CU(cudaMemcpyAsync(value_out, t->bufs[t->output].val, t->es, cudaMemcpyDeviceToHost, S(t)));
+            CU(cudaStreamSynchronize(S(t)));
+            return RDB_OK;
+        }
+    }
     OK(forward_pass<T>(t));
     if (value_out) CU(cudaMemcpyAsync(value_out, t->bufs[t->output].val, t->es, cudaMemcpyDeviceToHost, S(t)));
     // host results: plan the early copies (extract_result!, api/utils.jl:77-100, overlapped with the rest of the sweep)
@@ -1271,6 +1321,8 @@ void rdb_tape_destroy(rdb_tape *t) {
     for (void *p : t->allocs) cudaFree(p);
     if (t->ev0) cudaEventDestroy(t->ev0);
     if (t->ev1) cudaEventDestroy(t->ev1);
+    if (t->gexec) cudaGraphExecDestroy(t->gexec);
+    for (auto &e : t->early.ev) if (e) cudaEventDestroy(e);
     ctx_release(t->ctx);
     delete t;
 }
