@@ -1061,22 +1061,47 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
     const size_t nb = t->bufs.size();
     auto root = [&](int b) { while (t->bufs[b].alias_of >= 0) b = t->bufs[b].alias_of; return b; };
 
-    // ---- liveness of value tangents (backward over the tape)
-    std::vector<char> need_tv(nb, 0);
-    for (size_t ii = t->instrs.size(); ii-- > 0;) {
+    // ---- static plan (backward over the tape, mirrors the sweep): which adjoint tangents can be non-zero, which elementwise
+    // instructions can take the sparse path (all arguments are getindex views of the input, incoming adjoint tangent zero),
+    // and which value tangents somebody will actually read
+    const size_t ni = t->instrs.size();
+    std::vector<int> producer(nb, -1);
+    for (size_t ii = 0; ii < ni; ++ii) producer[root(t->instrs[ii].rec.out)] = (int)ii;
+    std::vector<char> td_nz(nb, 0), sparse_ok(ni, 0), need_tv(nb, 0);
+    for (size_t ii = ni; ii-- > 0;) {
         InstrPlan &I = t->instrs[ii];
-        const bool nonlinear = is_elementwise(I.rec.opcode);
+        const bool dtz = !td_nz[root(I.rec.out)];
+        if (is_elementwise(I.rec.opcode)) {
+            bool views = dtz;
+            for (int a = 0; a < I.rec.n_in && views; ++a) {
+                int pr = producer[root(I.in[a].rec.buffer)];
+                views = I.in[a].rec.tracked && pr >= 0 && is_getindex(t->instrs[pr].rec.opcode) &&
+                        root(t->instrs[pr].in[0].rec.buffer) == root(xid);
+            }
+            sparse_ok[ii] = views;
+            if (views) td_nz[root(xid)] = 1;
+            else for (int a = 0; a < I.rec.n_in; ++a) if (I.in[a].rec.tracked) td_nz[root(I.in[a].rec.buffer)] = 1;
+        } else if (!dtz) {
+            for (int a = 0; a < I.rec.n_in; ++a) if (I.in[a].rec.tracked) td_nz[root(I.in[a].rec.buffer)] = 1;
+        }
+    }
+    for (size_t ii = ni; ii-- > 0;) {
+        InstrPlan &I = t->instrs[ii];
+        const bool nonlinear = is_elementwise(I.rec.opcode) && !sparse_ok[ii];
         for (int a = 0; a < I.rec.n_in; ++a) {
             if (!I.in[a].rec.tracked) continue;
-            if (nonlinear || need_tv[root(I.rec.out)]) need_tv[root(I.in[a].rec.buffer)] = 1;
+            if (nonlinear || (!is_elementwise(I.rec.opcode) && need_tv[root(I.rec.out)])) need_tv[root(I.in[a].rec.buffer)] = 1;
         }
     }
     // the input's own n x K seed block is needed only by consumers other than getindex
     bool need_x_tv = false;
-    for (auto &I : t->instrs)
+    for (size_t ii = 0; ii < ni; ++ii) {
+        InstrPlan &I = t->instrs[ii];
         for (int a = 0; a < I.rec.n_in; ++a)
-            if (root(I.in[a].rec.buffer) == root(xid) && !is_getindex(I.rec.opcode) && (is_elementwise(I.rec.opcode) || need_tv[root(I.rec.out)]))
+            if (root(I.in[a].rec.buffer) == root(xid) && !is_getindex(I.rec.opcode) &&
+                ((is_elementwise(I.rec.opcode) && !sparse_ok[ii]) || (!is_elementwise(I.rec.opcode) && need_tv[root(I.rec.out)])))
                 need_x_tv = true;
+    }
 
     void *const x_td_own = x.td;
     bool first = true;
@@ -1214,6 +1239,22 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                 } break;
                 default: {
                     const int N = I.rec.n_in;
+                    if (sparse_ok[ii]) {
+                        // every argument is a getindex view of the seeded input and no adjoint tangent flows in
+                        const int rx = root(xid);
+                        if (td_zero[rx]) { CU(cudaMemsetAsync(x.td, 0, (size_t)(n * Kb) * t->es, S(t))); td_zero[rx] = 0; }
+                        const int64_t *maps[kMaxArgs];
+                        const T *sec[kMaxArgs * kMaxArgs];
+                        for (int p = 0; p < N; ++p) {
+                            maps[p] = t->instrs[producer[root(I.in[p].rec.buffer)]].in[0].d_map;
+                            for (int q = 0; q < N; ++q) sec[p * N + q] = (const T *)I.second[tri_index(p, q, N)];
+                        }
+                        StepTimer tm(t, "tangent_reverse_sparse", (double)n * Kb * t->es, 0);
+                        KL(t, launch_tangent_reverse_sparse<T>(S(t), (T *)x.td, n, Kb, c0, delta, N, maps, sec, o.size));
+                        for (int p = 0; p < N; ++p)
+                            KL(t, launch_mul_acc<T>(S(t), (T *)t->bufs[I.in[p].rec.buffer].der, delta, (const T *)I.partial[p], o.size, 1, false));
+                        break;
+                    }
                     const T *tvs[kMaxArgs];
                     for (int a = 0; a < N; ++a) tvs[a] = (const T *)t->bufs[I.in[a].rec.buffer].tv;
                     for (int p = 0; p < N; ++p) {

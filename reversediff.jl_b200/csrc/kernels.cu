@@ -854,6 +854,41 @@ cudaError_t launch_tangent_reverse(cudaStream_t s, T *td_p, const T *dt, const T
     return cudaGetLastError();
 }
 
+// Sparse second-order term for an elementwise instruction whose arguments are all `getindex` views of the seeded input: the value
+// tangent of argument q is the one-hot selector (map_q[i] == c0 + k), so
+//   td_x[map_p[i] + k*n_x] += delta[i] * second_pq[i]   only at k = map_q[i] - c0.
+// One thread per (i, p, q): O(n N^2) work instead of O(n K N) — the dense result block is just memset + these scattered adds.
+template <typename T>
+struct SparseArgs {
+    const int64_t *map[kMaxArgs];
+    const T *second[kMaxArgs][kMaxArgs];
+};
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_tangent_reverse_sparse(T *td_x, int64_t n_x, int64_t K, int64_t c0, const T *__restrict__ delta, SparseArgs<T> a, int64_t n, int N) {
+    int64_t tot = n * N * N;
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; t < tot; t += st) {
+        int64_t i = t % n;
+        int pq = (int)(t / n), p = pq / N, q = pq % N;
+        int64_t k = a.map[q][i] - c0;
+        if (k < 0 || k >= K) continue;
+        atomicAdd(td_x + a.map[p][i] + k * n_x, delta[i] * a.second[p][q][i]);
+    }
+}
+template <typename T>
+cudaError_t launch_tangent_reverse_sparse(cudaStream_t s, T *td_x, int64_t n_x, int64_t K, int64_t c0, const T *delta, int n_args,
+                                          const int64_t *const *maps, const T *const *second_pq, int64_t n) {
+    if (n <= 0) return cudaSuccess;
+    SparseArgs<T> a;
+    for (int p = 0; p < n_args; ++p) {
+        a.map[p] = maps[p];
+        for (int q = 0; q < n_args; ++q) a.second[p][q] = second_pq[p * n_args + q];
+    }
+    k_tangent_reverse_sparse<T><<<grid_for(n * n_args * n_args, 1), kThreads, 0, s>>>(td_x, n_x, K, c0, delta, a, n, n_args);
+    return cudaGetLastError();
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_colsum(T *__restrict__ out, const T *__restrict__ x, int64_t n, int64_t K, double scale) {
     int64_t k = blockIdx.x;
@@ -909,6 +944,7 @@ cudaError_t launch_copy2d(cudaStream_t s, T *dst, int64_t ldd, const T *src, int
     template cudaError_t launch_tangent_forward<T>(cudaStream_t, T *, int, const T *const *, const T *const *, int64_t, int64_t); \
     template cudaError_t launch_tangent_reverse<T>(cudaStream_t, T *, const T *, const T *, const T *, int, const T *const *, const T *const *, int64_t, int64_t, bool); \
     template cudaError_t launch_gather_cols<T>(cudaStream_t, T *, const T *, int64_t, const int64_t *, int64_t, int64_t); \
+    template cudaError_t launch_tangent_reverse_sparse<T>(cudaStream_t, T *, int64_t, int64_t, int64_t, const T *, int, const int64_t *const *, const T *const *, int64_t); \
     template cudaError_t launch_seed_tangent<T>(cudaStream_t, T *, int64_t, int64_t, int64_t);                            \
     template cudaError_t launch_seed_gather<T>(cudaStream_t, T *, const int64_t *, int64_t, int64_t, int64_t);            \
     template cudaError_t launch_colsum<T>(cudaStream_t, T *, const T *, int64_t, int64_t, T);                             \

@@ -99,6 +99,8 @@ template <typename T> cudaError_t launch_rows_out(cudaStream_t, T *result, int64
 template <typename T> cudaError_t launch_tangent_forward(cudaStream_t, T *tv_out, int n_args, const T *const *partial, const T *const *tv_in, int64_t n, int64_t K);
 // td_p[i+k*n] (+)= dt[i+k*n]*partial_p[i] + delta[i]*sum_q second_pq[i]*tv_q[i+k*n]   (dt may be NULL = known zero)
 template <typename T> cudaError_t launch_tangent_reverse(cudaStream_t, T *td_p, const T *dt, const T *delta, const T *partial_p, int n_args, const T *const *second_pq, const T *const *tv_in, int64_t n, int64_t K, bool overwrite);
+// all arguments are getindex views of the seeded input: td_x[map_p[i] + k*n_x] += delta[i]*second_pq[i] at k = map_q[i] - c0
+template <typename T> cudaError_t launch_tangent_reverse_sparse(cudaStream_t, T *td_x, int64_t n_x, int64_t K, int64_t c0, const T *delta, int n_args, const int64_t *const *maps, const T *const *second_pq /* [p*n_args+q] */, int64_t n);
 // rows gather/scatter for getindex under tangents: out[k + c*n] = src[map[k] + c*src_n]
 template <typename T> cudaError_t launch_gather_cols(cudaStream_t, T *out, const T *src, int64_t src_n, const int64_t *map, int64_t n, int64_t K);
 // tangent of getindex applied to the seeded tape input: tv[k + c*n] = (map[k] == c0 + c)
