@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(256) k_split_tf32(float *__restrict__ dst, con
 // Groups are processed from the smallest magnitude (d = s-1) to the largest (d = 0); each group is one accumulation chain in
 // one of two TMEM buffers, and the epilogue of group d (FP64 read-modify-write of the C tile, L2 resident) overlaps the MMAs of
 // the next group.  Only pairs with p+q <= s-1 are formed: the dropped ones are below the slicing truncation.
-constexpr int OZ_MAX_SLICES = 10;
+constexpr int OZ_MAX_SLICES = 8;    // 7*8 = 56 fixed-point bits fit an int64 with headroom; 8 x 64 TMEM columns = 512
 
 // ---- pass 1: per-row max |x| (bit pattern of a non-negative double orders like an unsigned integer), then the binary
 // exponent e = ilogb(max) + 2 (so |x| 2^-e <= 0.5) and the scale 2^e
@@ -388,27 +388,50 @@ __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, cons
         __syncthreads();
     }
     const int64_t plane = (int64_t)rows * Kp;
-#pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-        const int rl = w + 8 * i, r = r0 + rl, k = k0 + 4 * lane;
-        if (r >= rows || k >= Kp) continue;
-        const int e = e_in[r];
-        double x[4];
+    const int k = k0 + 4 * lane;
+    // fixed point: X = rint(v * 2^(7S - e)), |X| <= 2^(7S-1); balanced base-128 digits q_j in [-64, 63] from the least significant
+    // end (d = X & 127; X >>= 7; if d >= 64: d -= 128, X += 1) so that v 2^-e = sum_j q_j 2^(-7(j+1)) + O(2^(-7S-1)).
+    // All four rows of a thread are loaded before any digit work so four 32-byte loads are in flight per thread.
+    long long X[4][4];
+    bool ok[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            double v;
-            if (KMAJOR) v = (k + j < K) ? src[(int64_t)r * ld + k + j] : 0.0;
-            else v = tile[4 * lane + j][rl];
-            x[j] = scalbn(v, -e);                                  // |x| <= 0.5, exact
+    for (int i = 0; i < 4; ++i) {
+        const int rl = w + 8 * i, r = r0 + rl;
+        ok[i] = r < rows && k < Kp;
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        int e = 0;
+        if (ok[i]) {
+            e = e_in[r];
+            if (KMAJOR) {
+                const double *p = src + (int64_t)r * ld + k;
+                if (k + 3 < K && ((((uintptr_t)p) & 15) == 0)) {
+                    double2 lo = *reinterpret_cast<const double2 *>(p), hi = *reinterpret_cast<const double2 *>(p + 2);
+                    v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = (k + j < K) ? p[j] : 0.0;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = tile[4 * lane + j][rl];
+            }
         }
-        for (int sidx = 0; sidx < nslices; ++sidx) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) X[i][j] = __double2ll_rn(scalbn(v[j], 7 * nslices - e));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (!ok[i]) continue;
+        const int r = r0 + w + 8 * i;
+        for (int sidx = nslices - 1; sidx >= 0; --sidx) {
             uint32_t packed = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                double t = x[j] * 128.0;                           // exact
-                double q = rint(t);                                // |q| <= 64
-                x[j] = t - q;                                      // exact remainder in [-0.5, 0.5]
-                packed |= ((uint32_t)(uint8_t)(int8_t)(int)q) << (8 * j);
+                int d = (int)(X[i][j] & 127);
+                X[i][j] >>= 7;
+                if (sidx > 0 && d >= 64) { d -= 128; X[i][j] += 1; }
+                if (sidx == 0) d = (int)((X[i][j] << 7) | d);          // most significant digit keeps the sign: |d| <= 64
+                packed |= ((uint32_t)(uint8_t)(int8_t)d) << (8 * j);
             }
             *reinterpret_cast<uint32_t *>(dst + sidx * plane + (int64_t)r * Kp + k) = packed;
         }
