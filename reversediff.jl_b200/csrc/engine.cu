@@ -95,6 +95,9 @@ struct InstrPlan {
     void *partial[kMaxArgs] = {nullptr, nullptr, nullptr, nullptr};
     void *second[kMaxArgs * (kMaxArgs + 1) / 2] = {nullptr};
     bool fused_into_prev = false;   // forward: this `sum`/`mean` was produced by the previous kernel
+    std::vector<int32_t> h_ops;     // host copy of the scalar program (NVRTC specialisation)
+    void *jit_fn[2] = {nullptr, nullptr};   // [reduce]
+    bool jit_tried[2] = {false, false};
 };
 
 struct StepStat {
@@ -116,6 +119,7 @@ struct rdb_tape {
     rdb_options opts{};
     std::vector<void *> allocs;
     double *d_fconst = nullptr;
+    std::vector<double> h_fconst;
     void *scratch = nullptr;       // reduction scratch
     int64_t scratch_bytes = 0;
     int64_t R_alloc = 0;           // deriv buffers hold size x R_alloc
@@ -277,6 +281,17 @@ static int expr_forward(rdb_tape *t, InstrPlan &I, bool reduce, int order) {
     for (int a = 0; a < I.rec.n_in; ++a) np += I.partial[a] ? 1 : 0;
     StepTimer tm(t, order == 2 ? "expr_forward2" : (reduce ? "expr_forward+sum" : "expr_forward"),
                  (double)out.size * t->es * (1 + np + 1), 0);
+    if (order == 1 && out.size > 0) {
+        const int ri = reduce ? 1 : 0;
+        if (!I.jit_tried[ri]) {
+            I.jit_tried[ri] = true;
+            I.jit_fn[ri] = jit_expr_kernel(p, I.h_ops.data(), t->h_fconst.data(), sizeof(T) == 4, reduce);
+        }
+        if (I.jit_fn[ri]) {
+            KL(t, jit_expr_launch(S(t), I.jit_fn[ri], p, reduce));
+            return RDB_OK;
+        }
+    }
     KL(t, launch_expr_forward<T>(S(t), p));
     return RDB_OK;
 }
@@ -708,6 +723,7 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
     if (h.output_buffer < 0 || (uint32_t)h.output_buffer >= h.n_buffers) return fail(RDB_EINVAL, "bad output buffer id");
     t->output = h.output_buffer;
 
+    t->h_fconst.assign(fconst, fconst + h.n_fconst);
     if (h.n_fconst) {
         OK(dev_alloc(t, (void **)&t->d_fconst, h.n_fconst * 8));
         CU(cudaMemcpyAsync(t->d_fconst, fconst, h.n_fconst * 8, cudaMemcpyHostToDevice, S(t)));
@@ -805,6 +821,7 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
                     if (binary && (rb < 0 || rb >= reg)) return fail(RDB_EINVAL, "instruction %u: bad SSA ref", i);
                 }
             }
+            I.h_ops.assign(ops, ops + 4 * I.rec.expr_len);
             OK(dev_alloc(t, (void **)&I.d_ops, I.rec.expr_len * 16));
             CU(cudaMemcpyAsync(I.d_ops, ops, (size_t)I.rec.expr_len * 16, cudaMemcpyHostToDevice, S(t)));
             for (int a = 0; a < I.rec.n_in; ++a) {

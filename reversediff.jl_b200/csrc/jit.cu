@@ -1,0 +1,313 @@
+// NVRTC specialisation of elementwise instructions (kernel family a).
+//
+// The bytecode interpreter in kernels.cu keeps its SSA registers in local memory and dispatches every scalar op through a switch;
+// with FP64 tanh on top it ran the MLP config's `∇broadcast` forward sweeps at ~1.4 TB/s.  At rdb_tape_load the same straight-line
+// program is emitted as CUDA C — one Dual{N} evaluation per element in exactly the interpreter's arithmetic order, shapes and
+// broadcast strides baked in as literals, partials of untracked arguments never computed — compiled for sm_100a with NVRTC
+// (--fmad=false, like kernels.cu) and launched through the driver API.  No NVRTC at run time (dlopen fails) => the interpreter
+// stays in use; both paths are covered by the same parity tests (RDB_JIT=0 forces the interpreter).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace rdb {
+namespace jit {
+
+// ---- NVRTC through dlopen (no link-time dependency) ---------------------------------------------------------
+typedef int nvrtcResult;
+typedef struct _nvrtcProgram *nvrtcProgram;
+struct Nvrtc {
+    nvrtcResult (*createProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *);
+    nvrtcResult (*compileProgram)(nvrtcProgram, int, const char *const *);
+    nvrtcResult (*getCUBINSize)(nvrtcProgram, size_t *);
+    nvrtcResult (*getCUBIN)(nvrtcProgram, char *);
+    nvrtcResult (*getProgramLogSize)(nvrtcProgram, size_t *);
+    nvrtcResult (*getProgramLog)(nvrtcProgram, char *);
+    nvrtcResult (*destroyProgram)(nvrtcProgram *);
+    bool ok = false;
+};
+static Nvrtc &nvrtc() {
+    static Nvrtc n;
+    static bool tried = false;
+    if (tried) return n;
+    tried = true;
+    const char *e = getenv("RDB_JIT");
+    if (e && e[0] == '0') return n;
+    const char *names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    void *h = nullptr;
+    for (const char *nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_LOCAL); if (h) break; }
+    if (!h) return n;
+#define RDB_SYM(field, sym) n.field = (decltype(n.field))dlsym(h, sym); if (!n.field) return n;
+    RDB_SYM(createProgram, "nvrtcCreateProgram")
+    RDB_SYM(compileProgram, "nvrtcCompileProgram")
+    RDB_SYM(getCUBINSize, "nvrtcGetCUBINSize")
+    RDB_SYM(getCUBIN, "nvrtcGetCUBIN")
+    RDB_SYM(getProgramLogSize, "nvrtcGetProgramLogSize")
+    RDB_SYM(getProgramLog, "nvrtcGetProgramLog")
+    RDB_SYM(destroyProgram, "nvrtcDestroyProgram")
+#undef RDB_SYM
+    n.ok = true;
+    return n;
+}
+
+// ---- driver API through cudaGetDriverEntryPoint ---------------------------------------------------------------
+struct Drv {
+    CUresult (*moduleLoadData)(CUmodule *, const void *);
+    CUresult (*moduleGetFunction)(CUfunction *, CUmodule, const char *);
+    CUresult (*launchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
+    bool ok = false;
+};
+static Drv &drv() {
+    static Drv d;
+    static bool tried = false;
+    if (tried) return d;
+    tried = true;
+    cudaDriverEntryPointQueryResult q;
+    void *p = nullptr;
+#define RDB_DRV(field, name)                                                                                               \
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return d; \
+    d.field = (decltype(d.field))p;
+    RDB_DRV(moduleLoadData, "cuModuleLoadData")
+    RDB_DRV(moduleGetFunction, "cuModuleGetFunction")
+    RDB_DRV(launchKernel, "cuLaunchKernel")
+#undef RDB_DRV
+    d.ok = true;
+    return d;
+}
+
+// ---- code generation ----------------------------------------------------------------------------------------------
+static std::string lit(double c, bool f32) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), f32 ? "%.9gf" : "%.17g", c);
+    std::string s(buf);
+    if (s.find_first_of(".en") == std::string::npos && !f32) s += ".0";          // integer-valued: keep it a double literal
+    if (f32 && s.find_first_of(".e") == std::string::npos) s.insert(s.size() - 1, ".0");
+    if (s.find("inf") != std::string::npos || s.find("nan") != std::string::npos) return "";   // not expressible: no JIT
+    return "(" + s + ")";
+}
+
+struct Gen {
+    std::ostringstream o;
+    int N;
+    bool f32;
+    std::string V(int r) { return "v" + std::to_string(r); }
+    std::string D(int r, int p) { return "d" + std::to_string(r) + "_" + std::to_string(p); }
+    std::string one() { return f32 ? "1.0f" : "1.0"; }
+    std::string zero() { return f32 ? "0.0f" : "0.0"; }
+    std::string fn(const char *name) { return std::string(name) + (f32 ? "f" : ""); }
+    void unary(int r, int a, const std::string &f0, const std::string &f1) {
+        o << "    const T f0_" << r << " = " << f0 << ";\n    const T f1_" << r << " = " << f1 << ";\n";
+        o << "    const T " << V(r) << " = f0_" << r << ";\n";
+        for (int p = 0; p < N; ++p) o << "    const T " << D(r, p) << " = f1_" << r << " * " << D(a, p) << ";\n";
+    }
+};
+
+// returns "" when the program cannot be specialised
+static std::string generate(const ExprParams &P, const int32_t *ops, const double *fconst, bool f32, bool reduce) {
+    Gen g;
+    g.N = P.n_args;
+    g.f32 = f32;
+    const int N = P.n_args;
+    auto &o = g.o;
+    o << "typedef " << (f32 ? "float" : "double") << " T;\n";
+    o << "__device__ __forceinline__ T powi_(T x, int n) { if (n == 0) return (T)1; bool neg = n < 0; if (neg) n = -n; T r = x; "
+         "for (int i = 1; i < n; ++i) r = r * x; return neg ? (T)1 / r : r; }\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(256) expr_k(";
+    for (int a = 0; a < N; ++a) o << "const T* __restrict__ a" << a << ", ";
+    o << "T* __restrict__ out";
+    for (int a = 0; a < N; ++a) if (P.partial[a]) o << ", T* __restrict__ p" << a;
+    o << ", double* __restrict__ bsums) {\n";
+    o << "  double local = 0.0;\n";
+    const bool small = P.n <= 0x7fffffffLL;
+    o << "  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < " << P.n << "LL; i += gridDim.x * 256LL) {\n";
+    for (int a = 0; a < N; ++a) {
+        if (P.arg[a].same) { o << "    const T v" << a << " = a" << a << "[i];\n"; continue; }
+        // broadcast clamp (propagation.jl:25-27) as literal strides
+        o << "    T v" << a << ";\n    {\n";
+        if (small) o << "      unsigned rem = (unsigned)i; unsigned off = 0u;\n";
+        else o << "      long long rem = i; long long off = 0;\n";
+        for (int d = 0; d < kMaxDims; ++d) {
+            const long long dim = P.dims[d], st = P.arg[a].stride[d];
+            if (dim == 1) continue;
+            const char *sfx = small ? "u" : "LL";
+            if (st != 0) o << "      off += (rem % " << dim << sfx << ") * " << st << sfx << ";\n";
+            o << "      rem /= " << dim << sfx << ";\n";
+        }
+        o << "      v" << a << " = a" << a << "[off];\n    }\n";
+    }
+    for (int a = 0; a < N; ++a)
+        for (int p = 0; p < N; ++p) o << "    const T " << g.D(a, p) << " = " << (a == p ? g.one() : g.zero()) << ";\n";
+    int r = N;
+    for (int k = 0; k < P.n_ops; ++k, ++r) {
+        const int code = ops[4 * k], a = ops[4 * k + 1], b = ops[4 * k + 2], imm = ops[4 * k + 3];
+        switch (code) {
+            case E_CONST: {
+                std::string c = lit(fconst[imm], f32);
+                if (c.empty()) return "";
+                o << "    const T " << g.V(r) << " = (T)" << c << ";\n";
+                for (int p = 0; p < N; ++p) o << "    const T " << g.D(r, p) << " = " << g.zero() << ";\n";
+            } break;
+            case E_ARG:
+                o << "    const T " << g.V(r) << " = " << g.V(imm) << ";\n";
+                for (int p = 0; p < N; ++p) o << "    const T " << g.D(r, p) << " = " << g.D(imm, p) << ";\n";
+                break;
+            case E_ADD: case E_SUB: {
+                const char *op = code == E_ADD ? " + " : " - ";
+                o << "    const T " << g.V(r) << " = " << g.V(a) << op << g.V(b) << ";\n";
+                for (int p = 0; p < N; ++p) o << "    const T " << g.D(r, p) << " = " << g.D(a, p) << op << g.D(b, p) << ";\n";
+            } break;
+            case E_MUL:
+                o << "    const T " << g.V(r) << " = " << g.V(a) << " * " << g.V(b) << ";\n";
+                for (int p = 0; p < N; ++p)
+                    o << "    const T " << g.D(r, p) << " = " << g.D(a, p) << " * " << g.V(b) << " + " << g.V(a) << " * " << g.D(b, p) << ";\n";
+                break;
+            case E_DIV:
+                o << "    const T " << g.V(r) << " = " << g.V(a) << " / " << g.V(b) << ";\n";
+                o << "    const T ib_" << r << " = " << g.one() << " / " << g.V(b) << ";\n";
+                for (int p = 0; p < N; ++p)
+                    o << "    const T " << g.D(r, p) << " = (" << g.D(a, p) << " - " << g.V(r) << " * " << g.D(b, p) << ") * ib_" << r << ";\n";
+                break;
+            case E_POW:
+                o << "    const T " << g.V(r) << " = " << g.fn("pow") << "(" << g.V(a) << ", " << g.V(b) << ");\n";
+                o << "    const T fa_" << r << " = " << g.V(b) << " * " << g.fn("pow") << "(" << g.V(a) << ", " << g.V(b) << " - " << g.one() << ");\n";
+                o << "    const T fb_" << r << " = " << g.V(r) << " * " << g.fn("log") << "(" << g.V(a) << ");\n";
+                for (int p = 0; p < N; ++p)
+                    o << "    const T " << g.D(r, p) << " = fa_" << r << " * " << g.D(a, p) << " + fb_" << r << " * " << g.D(b, p) << ";\n";
+                break;
+            case E_MAX: case E_MIN:
+                o << "    const bool pk_" << r << " = " << g.V(a) << (code == E_MAX ? " > " : " < ") << g.V(b) << ";\n";
+                o << "    const T " << g.V(r) << " = pk_" << r << " ? " << g.V(a) << " : " << g.V(b) << ";\n";
+                for (int p = 0; p < N; ++p)
+                    o << "    const T " << g.D(r, p) << " = pk_" << r << " ? " << g.D(a, p) << " : " << g.D(b, p) << ";\n";
+                break;
+            case E_NEG: g.unary(r, a, "-" + g.V(a), "-" + g.one()); break;
+            case E_POWI:
+                g.unary(r, a, "powi_(" + g.V(a) + ", " + std::to_string(imm) + ")",
+                        imm != 0 ? "(T)" + std::to_string(imm) + " * powi_(" + g.V(a) + ", " + std::to_string(imm - 1) + ")" : g.zero());
+                break;
+            case E_TANH:
+                o << "    const T t_" << r << " = " << g.fn("tanh") << "(" << g.V(a) << ");\n";
+                g.unary(r, a, "t_" + std::to_string(r), g.one() + " - t_" + std::to_string(r) + " * t_" + std::to_string(r));
+                break;
+            case E_EXP:
+                o << "    const T t_" << r << " = " << g.fn("exp") << "(" << g.V(a) << ");\n";
+                g.unary(r, a, "t_" + std::to_string(r), "t_" + std::to_string(r));
+                break;
+            case E_LOG: g.unary(r, a, g.fn("log") + "(" + g.V(a) + ")", g.one() + " / " + g.V(a)); break;
+            case E_SQRT:
+                o << "    const T t_" << r << " = " << g.fn("sqrt") << "(" << g.V(a) << ");\n";
+                g.unary(r, a, "t_" + std::to_string(r), g.one() + " / ((T)2 * t_" + std::to_string(r) + ")");
+                break;
+            case E_SIN: g.unary(r, a, g.fn("sin") + "(" + g.V(a) + ")", g.fn("cos") + "(" + g.V(a) + ")"); break;
+            case E_COS: g.unary(r, a, g.fn("cos") + "(" + g.V(a) + ")", "-" + g.fn("sin") + "(" + g.V(a) + ")"); break;
+            case E_ABS2: g.unary(r, a, g.V(a) + " * " + g.V(a), "(T)2 * " + g.V(a)); break;
+            case E_ABS:
+                g.unary(r, a, g.fn("fabs") + "(" + g.V(a) + ")",
+                        g.V(a) + " > " + g.zero() + " ? " + g.one() + " : (" + g.V(a) + " < " + g.zero() + " ? -" + g.one() + " : " + g.zero() + ")");
+                break;
+            case E_INV:
+                o << "    const T t_" << r << " = " << g.one() << " / " << g.V(a) << ";\n";
+                g.unary(r, a, "t_" + std::to_string(r), "-t_" + std::to_string(r) + " * t_" + std::to_string(r));
+                break;
+            case E_SIGMOID:
+                o << "    const T t_" << r << " = " << g.one() << " / (" << g.one() << " + " << g.fn("exp") << "(-" << g.V(a) << "));\n";
+                g.unary(r, a, "t_" + std::to_string(r), "t_" + std::to_string(r) + " * (" + g.one() + " - t_" + std::to_string(r) + ")");
+                break;
+            default: return "";
+        }
+    }
+    o << "    out[i] = " << g.V(r - 1) << ";\n";
+    for (int a = 0; a < N; ++a) if (P.partial[a]) o << "    p" << a << "[i] = " << g.D(r - 1, a) << ";\n";
+    if (reduce) o << "    local += (double)" << g.V(r - 1) << ";\n";
+    o << "  }\n";
+    if (reduce) {
+        o << "  __shared__ double ws[8];\n"
+             "  for (int s = 16; s > 0; s >>= 1) local += __shfl_xor_sync(0xffffffffu, local, s);\n"
+             "  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = local;\n"
+             "  __syncthreads();\n"
+             "  if (threadIdx.x < 32) {\n"
+             "    double v = threadIdx.x < 8 ? ws[threadIdx.x] : 0.0;\n"
+             "    for (int s = 4; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);\n"
+             "    if (threadIdx.x == 0) bsums[blockIdx.x] = v;\n"
+             "  }\n";
+    }
+    o << "}\n";
+    return o.str();
+}
+
+static std::map<std::string, CUfunction> g_cache;
+
+static CUfunction compile(const std::string &src) {
+    auto it = g_cache.find(src);
+    if (it != g_cache.end()) return it->second;
+    g_cache[src] = nullptr;
+    Nvrtc &n = nvrtc();
+    Drv &d = drv();
+    if (!n.ok || (!d.ok && !getenv("RDB_JIT_DUMP"))) return nullptr;
+    nvrtcProgram prog = nullptr;
+    if (n.createProgram(&prog, src.c_str(), "rdb_expr.cu", 0, nullptr, nullptr) != 0) return nullptr;
+    const char *opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "-default-device", "--std=c++17"};
+    nvrtcResult rc = n.compileProgram(prog, 4, opts);
+    if (getenv("RDB_JIT_DUMP")) fprintf(stderr, "[rdb jit] NVRTC rc=%d for\n%s\n", rc, src.c_str());
+    if (rc != 0) {
+        if (getenv("RDB_JIT_VERBOSE")) {
+            size_t ls = 0;
+            n.getProgramLogSize(prog, &ls);
+            std::vector<char> log(ls + 1, 0);
+            n.getProgramLog(prog, log.data());
+            fprintf(stderr, "[rdb jit] NVRTC failed (%d):\n%s\n---- source ----\n%s\n", rc, log.data(), src.c_str());
+        }
+        n.destroyProgram(&prog);
+        return nullptr;
+    }
+    size_t sz = 0;
+    if (n.getCUBINSize(prog, &sz) != 0 || sz == 0) { n.destroyProgram(&prog); return nullptr; }
+    std::vector<char> cubin(sz);
+    n.getCUBIN(prog, cubin.data());
+    n.destroyProgram(&prog);
+    CUmodule mod = nullptr;
+    CUfunction fn = nullptr;
+    if (!d.ok) return nullptr;
+    if (d.moduleLoadData(&mod, cubin.data()) != CUDA_SUCCESS) return nullptr;
+    if (d.moduleGetFunction(&fn, mod, "expr_k") != CUDA_SUCCESS) return nullptr;
+    g_cache[src] = fn;
+    return fn;
+}
+
+}  // namespace jit
+
+// Build (or fetch) the specialised kernel for one elementwise instruction; nullptr => use the interpreter.
+void *jit_expr_kernel(const ExprParams &p, const int32_t *host_ops, const double *host_fconst, bool f32, bool reduce) {
+    if (p.order != 1) return nullptr;
+    std::string src = jit::generate(p, host_ops, host_fconst, f32, reduce);
+    if (src.empty()) return nullptr;
+    return (void *)jit::compile(src);
+}
+
+cudaError_t jit_expr_launch(cudaStream_t st, void *fn, const ExprParams &p, bool reduce) {
+    void *args[2 * kMaxArgs + 3];
+    const void *a[kMaxArgs];
+    void *pp[kMaxArgs];
+    void *out = p.out, *bs = p.block_sums;
+    int n = 0;
+    for (int i = 0; i < p.n_args; ++i) { a[i] = p.arg[i].ptr; args[n++] = &a[i]; }
+    args[n++] = &out;
+    for (int i = 0; i < p.n_args; ++i) if (p.partial[i]) { pp[i] = p.partial[i]; args[n++] = &pp[i]; }
+    args[n++] = &bs;
+    int64_t blocks = reduce ? kReduceBlocks : (p.n + 511) / 512;
+    if (!reduce && blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    CUresult r = jit::drv().launchKernel((CUfunction)fn, (unsigned)blocks, 1, 1, 256, 1, 1, 0, (CUstream)st, args, nullptr);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorLaunchFailure;
+}
+
+}  // namespace rdb

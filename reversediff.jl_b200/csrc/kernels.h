@@ -59,6 +59,11 @@ struct ExprParams {
     void *block_sums;              // kReduceBlocks partial sums when reduce == 1
 };
 
+// NVRTC-specialised elementwise forward kernel (jit.cu); jit_expr_kernel returns nullptr when NVRTC is unavailable or the
+// program cannot be specialised (the interpreter launch_expr_forward is used then)
+void *jit_expr_kernel(const ExprParams &p, const int32_t *host_ops, const double *host_fconst, bool f32, bool reduce);
+cudaError_t jit_expr_launch(cudaStream_t, void *fn, const ExprParams &p, bool reduce);
+
 template <typename T> cudaError_t launch_fill(cudaStream_t, T *p, int64_t n, T v);
 // out = a + sign*b   (array +/-: arithmetic.jl:7-12,69-79); if block_sums != NULL also writes per-block sums
 template <typename T> cudaError_t launch_add(cudaStream_t, T *out, const T *a, const T *b, T sign, int64_t n, T *block_sums);
