@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--jac-n", type=int, default=8192)
     ap.add_argument("--hess-n", type=int, default=16384)
+    ap.add_argument("--hess-large-n", type=int, default=65536,
+                    help="second hessian! leg: at n=16384 one B200 writes the whole 2.1 GB Hessian in ~0.45 ms, too little work to "
+                         "shard 8 ways; n=65536 (34 GB) shows the scaling of the same code path (0 = skip)")
     ap.add_argument("--gemm", default="auto", choices=["auto", "dmma"],
                     help="FP64 `*` kernels: auto = exact int8 slices on tcgen05 where eligible (default), dmma = DMMA only")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -400,19 +403,29 @@ def sharded_legs(args, torch, dist, rd, ctx, rank, world):
                        "rows_per_rank": rows, "result": "left sharded in device memory", "allgather_ms": gather_ms}
     del ct, J_d, full
     # ---- hessian!: extended Rosenbrock, column chunks
-    n = args.hess_n
-    tape = rd.HessianTape(rd.workloads.f_rosenbrock, rd.workloads.inputs_rosenbrock(n, seed=1))
-    ct = rd.compile(tape, ctx=ctx)
-    x_d = torch.from_numpy(rd.workloads.inputs_rosenbrock(n, seed=2)).cuda()
-    cols = n // world
-    cb, ce = rd.shard_range(n, world, rank)
-    H_d = torch.empty(n * (ce - cb), dtype=torch.float64, device="cuda")
+    for key, n in (("hessian", args.hess_n), ("hessian_large", args.hess_large_n)):
+        if n <= 0:
+            continue
+        cols = n // world
+        cb, ce = rd.shard_range(n, world, rank)
+        need = n * (ce - cb) * 8
+        free, _total = torch.cuda.mem_get_info()
+        if need * 1.5 + (40 << 30) > free:
+            out[key] = {"skipped": f"needs {need / 2**30:.1f} GiB result + tangent workspace, {free / 2**30:.1f} GiB free"}
+            continue
+        tape = rd.HessianTape(rd.workloads.f_rosenbrock, rd.workloads.inputs_rosenbrock(n, seed=1))
+        ct = rd.compile(tape, ctx=ctx)
+        x_d = torch.from_numpy(rd.workloads.inputs_rosenbrock(n, seed=2)).cuda()
+        H_d = torch.empty(n * (ce - cb), dtype=torch.float64, device="cuda")
 
-    def hstep():
-        rd.hessian_(H_d, ct, x_d, cols=(cb, ce))
-    ms = timed_steps(torch, dist, world, hstep, 3, 2)
-    out["hessian"] = {"metric": "hessian! rows/s", "value": n * 3 / (ms * 1e-3), "unit": "rows/s", "n": n, "ms_per_hessian": ms / 3,
-                      "cols_per_rank": cols, "result": "left sharded in device memory"}
+        def hstep():
+            rd.hessian_(H_d, ct, x_d, cols=(cb, ce))
+        ms = timed_steps(torch, dist, world, hstep, 3, 2)
+        out[key] = {"metric": "hessian! rows/s", "value": n * 3 / (ms * 1e-3), "unit": "rows/s", "n": n, "ms_per_hessian": ms / 3,
+                    "cols_per_rank": cols, "result": "left sharded in device memory",
+                    "result_write_GBps_per_gpu": n * (ce - cb) * 8 / (ms / 3 * 1e-3) / 1e9}
+        del ct, H_d, x_d
+        torch.cuda.empty_cache()
     return out
 
 
