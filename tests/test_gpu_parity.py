@@ -270,6 +270,48 @@ def test_instruction(rd, orc, name, dtype):
         run_gradient(rd, orc, _cases(rd)[name](rd), rec, ins, dtype)
 
 
+SHAPE_CASES = {
+    # rectangular and vector products, the combinations LinAlgTests.jl:210-278 walks through on 3x3 / length-3 inputs
+    "rect a*b": ((3, 5), (5, 2), lambda rd: lambda a, b: rd.sum(a @ b)),
+    "rect a'*b": ((5, 3), (5, 2), lambda rd: lambda a, b: rd.sum(a.T @ b)),
+    "rect a*b'": ((3, 5), (2, 5), lambda rd: lambda a, b: rd.sum(a @ b.T)),
+    "mat*vec": ((4, 6), (6,), lambda rd: lambda a, x: rd.sum(a @ x)),
+    "mat'*vec": ((6, 4), (6,), lambda rd: lambda a, x: rd.sum(a.T @ x)),
+    "vec'*mat": ((6, 4), (6,), lambda rd: lambda a, x: rd.sum(x.T @ a)),
+    "outer x*y'": ((5,), (7,), lambda rd: lambda x, y: rd.sum(rd.bcast(lambda u: u * u, x.reshape(5, 1) @ y.T))),
+    "1x1": ((1, 1), (1, 1), lambda rd: lambda a, b: rd.sum(a.T @ b + a @ b.T)),
+    "big mat*vec": ((300, 200), (200,), lambda rd: lambda a, x: rd.sum(rd.bcast(lambda u: rd.tanh(u * 0.01), a @ x))),
+    "big vec'*mat": ((300, 200), (300,), lambda rd: lambda a, x: rd.mean(x.T @ a)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SHAPE_CASES))
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_shapes(rd, orc, name, dtype):
+    sa, sb, mk = SHAPE_CASES[name]
+    rng = np.random.default_rng(21)
+    rec = (rng.random(sa).astype(dtype), rng.random(sb).astype(dtype))
+    ins = tuple(np.asfortranarray(rng.random(s).astype(dtype)) for s in (sa, sb))
+    run_gradient(rd, orc, mk(rd), rec, ins, dtype)
+
+
+def test_tuple_input_jacobian_and_diffresult(rd, orc):
+    """jacobian! with a tuple of inputs repeats the seed loop per input (api/utils.jl:66-71)."""
+    rng = np.random.default_rng(8)
+    n = 9
+    A = rng.random((n, n))
+    f = lambda x, y: rd.bcast(lambda u, v: u * rd.tanh(v), A @ x + y, y)
+    x0, y0 = rng.random(n), rng.random(n)
+    tape = rd.JacobianTape(f, (x0, y0))
+    ct = rd.compile(tape)
+    x, y = rng.random(n), rng.random(n)
+    Jx, Jy = rd.jacobian(ct, (x, y))
+    ot = orc.OracleTape(tape.program_bytes())
+    _, Jx_o = ot.jacobian([x, y], slot=0)
+    _, Jy_o = ot.jacobian([x, y], slot=1)
+    assert relerr(Jx, Jx_o) < 1e-12 and relerr(Jy, Jy_o) < 1e-12
+
+
 def test_broadcast_patterns(rd, orc):
     rng = np.random.default_rng(3)
     W, b, r = rng.random((40, 60)), rng.random(40), rng.random((1, 60))
