@@ -704,6 +704,145 @@ umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
     }
 }
+
+// --------------------------------------------------------------------------------------------------
+// Cluster variant: CL CTAs with the same m-block and adjacent n-blocks form a thread-block cluster and SHARE the A stage.
+// Each CTA fetches S/CL of the A slices and TMA-multicasts them into every CTA of the cluster; B stays private.  The single-CTA
+// kernel moves 96 KB per stage from L2 and ncu/timing showed it bound there (~8 TB/s aggregate L2->SM); with CL = 2 the per-CTA
+// L2 traffic drops to 64 KB, with CL = 4 to 48 KB.  A stage may be refilled only when ALL CTAs of the cluster have consumed it,
+// so tcgen05.commit arrives (multicast) on the empty barrier of every CTA and those barriers count CL arrivals.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+
+template <int S, int CL>
+__global__ void __launch_bounds__(THREADS, 1)
+umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, OzParams P) {
+    static_assert(S % CL == 0, "slices must divide evenly over the cluster");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int KB = 64, STAGE = stage_bytes(S, KB), STAGES2 = stages_for(KB), A_SLICE = BM2 * KB, B_SLICE = BN2 * KB;
+    constexpr int SL = S / CL;                                    // A slices fetched by each CTA
+    constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
+    uint64_t *full = (uint64_t *)(smem + STAGES2 * STAGE);
+    uint64_t *empty = full + STAGES2;
+    uint64_t *tmem_full = empty + STAGES2;
+    uint32_t *tmem_ptr = (uint32_t *)(tmem_full + 1);
+    constexpr int TCOLS = S * BN2 <= 32 ? 32 : S * BN2 <= 64 ? 64 : S * BN2 <= 128 ? 128 : S * BN2 <= 256 ? 256 : 512;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const int m0 = blockIdx.x * BM2, n0 = blockIdx.y * BN2;
+    const int kblocks = (K + KB - 1) / KB;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                           // every CTA's barriers are initialised before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % STAGES2;
+                const uint32_t ph = (kb / STAGES2) & 1;
+                mbar_wait(&empty[s], ph ^ 1);                     // all CL consumers released this stage (in every CTA)
+                mbar_expect_tx(&full[s], STAGE);                  // bytes landing in MY smem: S A-slices (CL multicasts) + my B slices
+                tma_load_3d_mc(smem + s * STAGE + crank * SL * A_SLICE, &tmAmc, &full[s], kb * KB, m0, crank * SL, MASK);
+                tma_load_3d(smem + s * STAGE + S * A_SLICE, &tmB, &full[s], kb * KB, n0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % STAGES2;
+                const uint32_t ph = (kb / STAGES2) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(smem + s * STAGE), b0 = a0 + S * A_SLICE;
+#pragma unroll
+                for (int p = 0; p < S; ++p) {
+                    const uint64_t ad = make_desc_kb<KB>(a0 + p * A_SLICE);
+#pragma unroll
+                    for (int q0 = 0; q0 < S - p; q0 += 4) {
+                        const int nq = (S - p - q0) < 4 ? (S - p - q0) : 4;
+                        const uint64_t bd = make_desc_kb<KB>(b0 + q0 * B_SLICE);
+                        const uint32_t acc = tmem_base + (uint32_t)((p + q0) * BN2);
+                        const uint32_t idesc = make_idesc_i8(nq * BN2);
+#pragma unroll
+                        for (int k = 0; k < KB / 32; ++k)
+                            tc_mma<KIND_I8>(acc, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || p > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit_mc(&empty[s], MASK);                    // arrives on empty[s] of every CTA in the cluster
+            }
+            tc_commit(tmem_full);
+        }
+    } else {
+        const int q4 = warp & 3;
+        const int row = m0 + q4 * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const double rs = row < M ? P.alpha * P.sa[row] : 0.0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN2; c0 += 32) {
+            double sum[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[j] = 0.0;
+#pragma unroll 1
+            for (int d = S - 1; d >= 0; --d) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(d * BN2 + c0), v);
+                const double w = scalbn(1.0, -7 * (d + 2));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[j] += (double)(int)v[j] * w;
+            }
+            if (row < M) {
+                double prev[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = n0 + c0 + j;
+                    prev[j] = (col < N && P.beta != 0.0) ? P.C[row + (int64_t)col * P.ldc] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = n0 + c0 + j;
+                    if (col < N) P.C[row + (int64_t)col * P.ldc] = P.beta * prev[j] + sum[j] * (rs * P.sb[col]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                           // no CTA exits while a peer may still multicast into it
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
+    }
+}
 }  // namespace oz2
 
 }  // namespace umma
@@ -912,6 +1051,29 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
             !make_map(&mB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2, kbytes, nslices))
             return cudaErrorInvalidValue;
         dim3 grid2((unsigned)((M + BM2 - 1) / BM2), (unsigned)((N + BN2 - 1) / BN2));
+        static int cl = -1;
+        if (cl < 0) { const char *e = getenv("RDB_OZAKI_CLUSTER"); cl = e ? atoi(e) : 2; if (cl != 1 && cl != 2 && cl != 4) cl = 1; }
+        if (nslices == 8 && kbytes == 64 && cl > 1 && grid2.y % cl == 0) {
+            // cluster of `cl` CTAs along n sharing the A stage through TMA multicast
+            CUtensorMap mAmc;
+            if (!make_map(&mAmc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, kbytes, nslices / cl)) return cudaErrorInvalidValue;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid2; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes(8, 64); cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)cl; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            static bool attrc = false;
+            if (!attrc) {
+                cudaError_t e = cudaFuncSetAttribute(umma_ozaki2c_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(8, 64));
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_ozaki2c_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(8, 64));
+                if (e != cudaSuccess) return e;
+                attrc = true;
+            }
+            int Mi = (int)M, Ni = (int)N, Ki = (int)Kp;
+            if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 2>, mAmc, mB, Mi, Ni, Ki, P);
+            return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 4>, mAmc, mB, Mi, Ni, Ki, P);
+        }
 #define RDB_OZ2(SS)                                                                                                        \
     case SS: {                                                                                                             \
         static bool attr2 = false;                                                                                         \
