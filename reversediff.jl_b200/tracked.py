@@ -433,6 +433,14 @@ def broadcast(f, *args):
 def record_getindex(t: TrackedArray, key):
     """Range/colon ``getindex`` (``src/tracked.jl:308-316``); the index iterable
     (``index_iterable``, ``:291-306``) is shipped as an explicit 0-based linear map."""
+    if isinstance(key, list) and key and all(isinstance(k, tuple) for k in key):
+        # getindex(t, inds::AbstractArray{<:CartesianIndex}) (tracked.jl:342-347): 0-based index tuples here
+        lin = np.arange(t.size, dtype=np.int64).reshape(t.shape, order="F")
+        m = np.asarray([lin[k] for k in key], dtype=np.int64)
+        tp = t.tape
+        out = _track_new(t.value.reshape(-1, order="F")[m], tp)
+        tp.record(P.OP_GETINDEX, [P.Operand(t.buffer, P.CLS_TA, True, t.shape, P.IDX_EXPLICIT, m)], out.buffer)
+        return out
     if not isinstance(key, tuple):
         key = (key,)
     if all(isinstance(k, (int, np.integer)) for k in key):

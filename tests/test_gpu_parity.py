@@ -258,7 +258,7 @@ def _cases(rd):
 
 @pytest.mark.parametrize("name", ["a*b", "a'*b", "a*b'", "a'*b'", "a+b", "a-b", "-a", "bcast*", "bcast-", "map", "nbcast_fns",
                                   "getindex", "reshape", "bcast/", "bcast\\", "bcast^", "dot", "sum_dims1", "sum_dims2", "tracker_real",
-                                  "tracker_trackedreal", "getindex_generic"])
+                                  "tracker_trackedreal", "getindex_generic", "getindex_cartesian"])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_instruction(rd, orc, name, dtype):
     rng = np.random.default_rng(11)
@@ -293,6 +293,28 @@ def test_shapes(rd, orc, name, dtype):
     rec = (rng.random(sa).astype(dtype), rng.random(sb).astype(dtype))
     ins = tuple(np.asfortranarray(rng.random(s).astype(dtype)) for s in (sa, sb))
     run_gradient(rd, orc, mk(rd), rec, ins, dtype)
+
+
+def test_jacobian_through_every_reduction_kind(rd, orc):
+    """Batched seed rows (R > 1) through dot / sum(x,dims) / scalar-argument broadcasts / getindex adjoints."""
+    rng = np.random.default_rng(12)
+    n = 6
+    A = rng.random((n, n))
+
+    def f(x):
+        X = A @ x.reshape(n, 1) @ x.reshape(1, n)                     # n x n, tracked on both sides
+        rows = rd.sum(X, dims=2)                                      # n x 1
+        s = rd.dot(x, x)                                              # TrackedReal
+        y = rd.bcast(lambda u, c: rd.tanh(u) * c, rows.reshape(n), s) # tracker_∇broadcast with a TrackedReal argument
+        return rd.broadcast("/", y, rd.bcast(lambda v: v + 2.0, x[[5, 4, 3, 2, 1, 0]]))
+    x0 = rng.random(n)
+    tape = rd.JacobianTape(f, x0)
+    x = rng.random(n)
+    for block in (0, 4):
+        ct = rd.compile(tape, seed_block=block)
+        J = rd.jacobian(ct, x)
+        y, Jo = orc.OracleTape(tape.program_bytes()).jacobian([x])
+        assert relerr(J, Jo) < 1e-12
 
 
 def test_tuple_input_jacobian_and_diffresult(rd, orc):

@@ -178,6 +178,7 @@ CASES = {
     "sum_dims2": lambda rd: (lambda a, b: rd.sum(rd.broadcast("*", rd.sum(a, dims=2), b))),
     "tracker_real": lambda rd: (lambda a, b: rd.sum(rd.bcast(lambda u, c, v: u * c + rd.tanh(v), a, 2.5, b))),
     "tracker_trackedreal": lambda rd: (lambda a, b: rd.sum(rd.bcast(lambda u, s: u * s, a, rd.sum(b)))),
+    "getindex_cartesian": lambda rd: (lambda a, b: rd.dot(a[[(0, 0), (2, 1), (1, 2), (2, 1)]], b[[(1, 1), (0, 2), (2, 2), (0, 0)]])),
     "getindex_generic": lambda rd: (lambda a, b: rd.sum(a[[0, 2, 2], :] @ b[:, [1, 2]])),
 }
 
