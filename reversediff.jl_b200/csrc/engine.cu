@@ -38,8 +38,10 @@ static int fail(int code, const char *fmt, ...) {
 #define CU(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e__ = (call);                                                                        \
-        if (e__ != cudaSuccess)                                                                          \
+        if (e__ != cudaSuccess) {                                                                        \
+            cudaGetLastError(); /* do not leave a stale error for the next, unrelated call */             \
             return fail(RDB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                                \
     } while (0)
 #define OK(call)                 \
     do {                         \
@@ -131,6 +133,11 @@ struct rdb_tape {
     std::vector<StepStat> stats;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool forward_valid = false;
+    // deriv zero-state, per ROOT buffer: dz[b] != 0 means deriv(b) is LOGICALLY zero while its storage may hold anything.
+    // unseed! (every reverse exec ends with one, tracked.jl:207-213) only sets the flag; the next accumulation into the buffer
+    // overwrites (beta = 0, plain store) instead of memset + read-modify-write; anything that cannot overwrite (scatter, atomics)
+    // and every reader outside the sweep (extract_result!, rdb_get_deriv, hessian!) materialises the zeros first.
+    std::vector<char> dz;
     // whole-sweep CUDA graph for launch-bound tapes (the 100x100 config is ~25 launches of a few microseconds each)
     cudaGraphExec_t gexec = nullptr;
     int graph_state = 0;           // 0 = first call runs eagerly (warms every lazy allocation), 1 = capture next, 2 = ready, -1 = off
@@ -413,6 +420,28 @@ static int unseed(rdb_tape *t, Buf &b, int64_t R) {
     CU(cudaMemsetAsync(b.der, 0, (size_t)(b.size * R) * t->es, S(t)));
     return RDB_OK;
 }
+static int droot(rdb_tape *t, int b) {
+    while (t->bufs[b].alias_of >= 0) b = t->bufs[b].alias_of;
+    return b;
+}
+// logical unseed!: no memory traffic
+static void dclear(rdb_tape *t, int b) { t->dz[droot(t, b)] = 1; }
+// before a full-coverage accumulation: returns true if it must OVERWRITE (buffer was logically zero); marks the buffer live
+static bool dtake(rdb_tape *t, int b) {
+    const int r = droot(t, b);
+    const bool ow = t->dz[r] != 0;
+    t->dz[r] = 0;
+    return ow;
+}
+// before a partial / atomic accumulation, or any read from outside the sweep: make the storage really zero
+static int dmaterialize(rdb_tape *t, int b, int64_t R, bool mark_live) {
+    const int r = droot(t, b);
+    if (t->dz[r] && t->bufs[r].der) {
+        CU(cudaMemsetAsync(t->bufs[r].der, 0, (size_t)(t->bufs[r].size * R) * t->es, S(t)));
+        if (mark_live) t->dz[r] = 0;
+    }
+    return RDB_OK;
+}
 
 // a.deriv += delta * value(b)'   and   b.deriv += value(a)' * delta     (arithmetic.jl:272-285), R seed columns
 template <typename T>
@@ -434,16 +463,18 @@ static int mul_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
     if (oa.rec.tracked) {
         Buf &ba = t->bufs[oa.rec.buffer];
         StepTimer tm(t, "gemm_reverse_a", (double)(M * N + K * N + 2 * M * K) * t->es * R, 2.0 * M * N * K * R);
+        if (oa.mode == OPM_GATHER) OK(dmaterialize(t, oa.rec.buffer, R, true));
+        const T beta_a = (oa.mode != OPM_GATHER && dtake(t, oa.rec.buffer)) ? (T)0 : (T)1;
         for (int64_t r = 0; r < R; ++r) {
             const T *d = delta + r * M * N;
             if (oa.mode == OPM_PLAIN) {
                 // a.deriv(MxK) += delta(MxN) * Bmat'(NxK)
                 g_tag_b = operand_tag(t, ob);
-                KL(t, gemm_t<T>(S(t), false, !B.stored_t, M, K, N, (T)1, d, M, B.ptr, B.ld, (T)1, (T *)ba.der + r * ba.size, M));
+                KL(t, gemm_t<T>(S(t), false, !B.stored_t, M, K, N, (T)1, d, M, B.ptr, B.ld, beta_a, (T *)ba.der + r * ba.size, M));
             } else if (oa.mode == OPM_FOLDED_T) {
                 // scatter-add through the transpose map == origin.deriv(KxM) += Bmat(KxN) * delta'(NxM)
                 g_tag_a = operand_tag(t, ob);
-                KL(t, gemm_t<T>(S(t), B.stored_t, true, K, M, N, (T)1, B.ptr, B.ld, d, M, (T)1, (T *)ba.der + r * ba.size, K));
+                KL(t, gemm_t<T>(S(t), B.stored_t, true, K, M, N, (T)1, B.ptr, B.ld, d, M, beta_a, (T *)ba.der + r * ba.size, K));
             } else {
                 g_tag_b = operand_tag(t, ob);
                 KL(t, gemm_t<T>(S(t), false, !B.stored_t, M, K, N, (T)1, d, M, B.ptr, B.ld, (T)0, (T *)oa.dense_der, M));
@@ -455,17 +486,19 @@ static int mul_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
     if (ob.rec.tracked) {
         Buf &bb = t->bufs[ob.rec.buffer];
         StepTimer tm(t, "gemm_reverse_b", (double)(M * N + M * K + 2 * K * N) * t->es * R, 2.0 * M * N * K * R);
+        if (ob.mode == OPM_GATHER) OK(dmaterialize(t, ob.rec.buffer, R, true));
+        const T beta_b = (ob.mode != OPM_GATHER && dtake(t, ob.rec.buffer)) ? (T)0 : (T)1;
         if (ob.mode == OPM_PLAIN) {
             // b.deriv(K x N*R) += Amat'(KxM) * delta(M x N*R): the R seed columns ride along as extra GEMM columns
             g_tag_a = operand_tag(t, oa);
-            KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, N * R, M, (T)1, A.ptr, A.ld, delta, M, (T)1, (T *)bb.der, K));
+            KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, N * R, M, (T)1, A.ptr, A.ld, delta, M, beta_b, (T *)bb.der, K));
         } else {
             for (int64_t r = 0; r < R; ++r) {
                 const T *d = delta + r * M * N;
                 if (ob.mode == OPM_FOLDED_T) {
                     // origin.deriv(NxK) += delta'(NxM) * Amat(MxK)
                     g_tag_b = operand_tag(t, oa);
-                    KL(t, gemm_t<T>(S(t), true, A.stored_t, N, K, M, (T)1, d, M, A.ptr, A.ld, (T)1, (T *)bb.der + r * bb.size, N));
+                    KL(t, gemm_t<T>(S(t), true, A.stored_t, N, K, M, (T)1, d, M, A.ptr, A.ld, beta_b, (T *)bb.der + r * bb.size, N));
                 } else {
                     KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, N, M, (T)1, A.ptr, A.ld, d, M, (T)0, (T *)ob.dense_der, K));
                     KL(t, launch_scatter_add<T>(S(t), (T *)bb.der + r * bb.size, bb.size, ob.d_map, (const T *)ob.dense_der, ob.size, 1));
@@ -493,13 +526,14 @@ static int expr_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
         }
         if (same) {
             StepTimer tm(t, "expr_reverse", 4.0 * out.size * R * t->es, 0);
-            KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[a], out.size, R, false));
+            KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[a], out.size, R, dtake(t, o.rec.buffer)));
         } else if (o.size == 1) {
             // scalar (TrackedReal) argument: input_deriv += sum_i x[i]*partial[i]   (propagation.jl:98-108; unbroadcast(::Number) = sum)
             StepTimer tm(t, "expr_reverse_scalar", 2.0 * out.size * R * t->es, 0);
+            const bool ow = dtake(t, o.rec.buffer);
             for (int64_t r = 0; r < R; ++r) {
                 KL(t, launch_dot_block_sums<T>(S(t), delta + r * out.size, (const T *)I.partial[a], out.size, (T *)t->scratch));
-                KL(t, launch_finish_sum<T>(S(t), (const T *)t->scratch, (T *)b.der + r, (T)1, true));
+                KL(t, launch_finish_sum<T>(S(t), (const T *)t->scratch, (T *)b.der + r, (T)1, !ow));
             }
         } else {
             int64_t d0 = o.rec.ndims >= 1 ? o.rec.dims[0] : 1;
@@ -507,7 +541,7 @@ static int expr_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
             if (colvec) {
                 StepTimer tm(t, "expr_reverse_colreduce", 2.0 * out.size * R * t->es, 0);
                 KL(t, launch_mul_acc_colvec<T>(S(t), (T *)b.der, delta, (const T *)I.partial[a], d0, out.size / d0, R,
-                                               (T *)t->scratch, t->scratch_bytes / 8));
+                                               (T *)t->scratch, t->scratch_bytes / 8, dtake(t, o.rec.buffer)));
                 t->launches++;
             } else {
                 int64_t dst_stride[kMaxDims], st = 1;
@@ -517,6 +551,7 @@ static int expr_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
                     st *= od;
                 }
                 StepTimer tm(t, "expr_reverse_generic", 3.0 * out.size * R * t->es, 0);
+                OK(dmaterialize(t, o.rec.buffer, R, true));
                 KL(t, launch_mul_acc_generic<T>(S(t), (T *)b.der, b.size, dst_stride, delta, (const T *)I.partial[a], out.dims,
                                                 out.size, R));
             }
@@ -532,6 +567,7 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
         InstrPlan &I = t->instrs[k];
         Buf &out = t->bufs[I.rec.out];
         const T *delta = (const T *)out.der;
+        if (t->dz[droot(t, I.rec.out)]) continue;        // no adjoint reached this output: every increment would add zero
         switch (I.rec.opcode) {
             case OP_MUL: OK(mul_reverse<T>(t, I, R)); break;
             case OP_ADD:
@@ -541,14 +577,14 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                     Buf &b = t->bufs[I.in[a].rec.buffer];
                     T sign = (a == 1 && I.rec.opcode == OP_SUB) ? (T)-1 : (T)1;
                     StepTimer tm(t, "add_reverse", 3.0 * out.size * R * t->es, 0);
-                    KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, sign, out.size * R, false));
+                    KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, sign, out.size * R, dtake(t, I.in[a].rec.buffer)));
                     OK(acc_done(t, I.in[a].rec.buffer));
                 }
                 break;
             case OP_NEG:
                 if (I.in[0].rec.tracked) {
                     Buf &b = t->bufs[I.in[0].rec.buffer];
-                    KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, (T)-1, out.size * R, false));
+                    KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, (T)-1, out.size * R, dtake(t, I.in[0].rec.buffer)));
                     OK(acc_done(t, I.in[0].rec.buffer));
                 }
                 break;
@@ -558,7 +594,7 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                     Buf &b = t->bufs[I.in[0].rec.buffer];
                     T scale = I.rec.opcode == OP_MEAN ? (T)1 / (T)I.in[0].size : (T)1;
                     StepTimer tm(t, "sum_reverse", 2.0 * b.size * R * t->es, 0);
-                    KL(t, launch_acc_scalar<T>(S(t), (T *)b.der, b.size, R, delta, scale, false));
+                    KL(t, launch_acc_scalar<T>(S(t), (T *)b.der, b.size, R, delta, scale, dtake(t, I.in[0].rec.buffer)));
                     OK(acc_done(t, I.in[0].rec.buffer));
                 }
                 break;
@@ -572,7 +608,7 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                     Buf &b = t->bufs[I.in[a].rec.buffer];
                     Buf &other = t->bufs[I.in[1 - a].rec.buffer];
                     StepTimer tm(t, "dot_reverse", 3.0 * b.size * R * t->es, 0);
-                    KL(t, launch_scal_acc<T>(S(t), (T *)b.der, (const T *)other.val, delta, b.size, R));
+                    KL(t, launch_scal_acc<T>(S(t), (T *)b.der, (const T *)other.val, delta, b.size, R, dtake(t, I.in[a].rec.buffer)));
                     OK(acc_done(t, I.in[a].rec.buffer));
                 }
                 break;
@@ -582,7 +618,7 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                     int64_t dstride[kMaxDims], st = 1;
                     for (int d = 0; d < kMaxDims; ++d) { dstride[d] = (out.dims[d] == 1 && b.dims[d] != 1) ? 0 : st; st *= out.dims[d]; }
                     StepTimer tm(t, "sumdims_reverse", 2.0 * b.size * R * t->es, 0);
-                    KL(t, launch_bcast_acc<T>(S(t), (T *)b.der, b.dims, dstride, delta, b.size, R, out.size));
+                    KL(t, launch_bcast_acc<T>(S(t), (T *)b.der, b.dims, dstride, delta, b.size, R, out.size, dtake(t, I.in[0].rec.buffer)));
                     OK(acc_done(t, I.in[0].rec.buffer));
                 }
                 break;
@@ -590,6 +626,7 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                 if (I.in[0].rec.tracked) {
                     Buf &b = t->bufs[I.in[0].rec.buffer];
                     StepTimer tm(t, "getindex_reverse", 3.0 * out.size * R * t->es, 0);
+                    OK(dmaterialize(t, I.in[0].rec.buffer, R, true));
                     KL(t, launch_scatter_add<T>(S(t), (T *)b.der, b.size, I.in[0].d_map, delta, out.size, R));
                     OK(acc_done(t, I.in[0].rec.buffer));
                 }
@@ -597,10 +634,7 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
             default:
                 return fail(RDB_EUNSUPPORTED, "opcode %d has no reverse kernel", I.rec.opcode);
         }
-        {
-            StepTimer tm(t, "unseed", (double)out.size * R * t->es, 0);
-            OK(unseed<T>(t, out, R));
-        }
+        dclear(t, I.rec.out);                              // unseed!(output)
     }
     return RDB_OK;
 }
@@ -853,6 +887,7 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
                 if (I.in[a].rec.tracked && I.in[a].size != t->bufs[I.rec.out].size)
                     t->scratch_bytes = std::max<int64_t>(t->scratch_bytes, I.in[a].size * 4096 * 8);
     OK(dev_alloc(t, &t->scratch, t->scratch_bytes));
+    t->dz.assign(t->bufs.size(), 1);
     OK(ensure_batch(t, 1));
     CU(cudaStreamSynchronize(S(t)));
     return RDB_OK;
@@ -863,8 +898,9 @@ template <typename T>
 static int seed_scalar_and_reverse(rdb_tape *t) {
     Buf &out = t->bufs[t->output];
     if (out.size != 1) return fail(RDB_EINVAL, "gradient! needs a scalar tape output");
-    for (int b : t->inputs) OK(unseed<T>(t, t->bufs[b], 1));               // unseed!(input)
+    for (size_t b = 0; b < t->bufs.size(); ++b) t->dz[droot(t, (int)b)] = 1;   // unseed!(input); intermediates are zero by invariant
     KL(t, launch_fill<T>(S(t), (T *)out.der, 1, (T)1));                     // seed!(output)
+    t->dz[droot(t, t->output)] = 0;
     return reverse_pass<T>(t, 1);
 }
 
@@ -910,6 +946,7 @@ static int gradient_impl(rdb_tape *t, void *const *result_ptrs, int on_device, v
             for (size_t i = 0; i < t->inputs.size(); ++i) {
                 if (!result_ptrs || !result_ptrs[i]) continue;
                 Buf &b = t->bufs[t->inputs[i]];
+                OK(dmaterialize(t, t->inputs[i], 1, false));
                 CU(cudaMemcpyAsync(result_ptrs[i], b.der, (size_t)b.size * t->es, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, S(t)));
             }
             if (value_out) CU(cudaMemcpyAsync(value_out, t->bufs[t->output].val, t->es, cudaMemcpyDeviceToHost, S(t)));
@@ -949,6 +986,7 @@ static int gradient_impl(rdb_tape *t, void *const *result_ptrs, int on_device, v
         while (t->bufs[r].alias_of >= 0) r = t->bufs[r].alias_of;
         if (!on_device && !E.issued.empty() && E.issued[r] && E.dst[r] == result_ptrs[i]) continue;
         Buf &b = t->bufs[t->inputs[i]];
+        OK(dmaterialize(t, t->inputs[i], 1, false));
         CU(cudaMemcpyAsync(result_ptrs[i], b.der, (size_t)b.size * t->es, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, S(t)));
     }
     CU(cudaStreamSynchronize(S(t)));
@@ -980,9 +1018,11 @@ static int jacobian_impl(rdb_tape *t, int slot, int64_t rb, int64_t re, void *re
     }
     for (int64_t i0 = rb; i0 < re; i0 += R) {
         const int64_t Rb = std::min(R, re - i0);
-        for (int b : t->inputs) OK(unseed<T>(t, t->bufs[b], Rb));                      // unseed!(input)
+        for (size_t b = 0; b < t->bufs.size(); ++b) t->dz[droot(t, (int)b)] = 1;       // unseed!(input)
         KL(t, launch_seed_onehot<T>(S(t), (T *)out.der, m, Rb, i0));                    // seed!(output, i) for Rb rows
+        t->dz[droot(t, t->output)] = 0;
         OK(reverse_pass<T>(t, Rb));
+        OK(dmaterialize(t, t->inputs[slot], Rb, false));
         StepTimer tm(t, "rows_out", 2.0 * n * Rb * t->es, 0);
         KL(t, launch_rows_out<T>(S(t), dres + (i0 - rb), dld, (const T *)x.der, n, Rb)); // result_matrix[i, :] = input_deriv
     }
@@ -1063,6 +1103,8 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
     const int64_t cols = ce - cb;
     if (cols > 0 && ld < n) return fail(RDB_EINVAL, "leading dimension smaller than n");
     OK(ensure_second_order(t));
+    // this sweep keeps the reference's physical unseed!/increment pattern for the (size-n) first-order adjoints
+    for (size_t b = 0; b < t->bufs.size(); ++b) OK(dmaterialize(t, (int)b, 1, false));
     OK(forward_pass<T>(t, 2));
     if (value_out) CU(cudaMemcpyAsync(value_out, out.val, t->es, cudaMemcpyDeviceToHost, S(t)));
     if (cols == 0 && !grad_out) { CU(cudaStreamSynchronize(S(t))); return RDB_OK; }
@@ -1303,6 +1345,8 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
     }
     x.td = x_td_own;
     for (auto &b : t->bufs) if (b.alias_of >= 0) b.td = t->bufs[b.alias_of].td;
+    for (size_t b = 0; b < t->bufs.size(); ++b) t->dz[droot(t, (int)b)] = 1;   // intermediates were physically unseeded
+    t->dz[droot(t, xid)] = 0;                                                   // deriv(x) holds the gradient
     if (grad_out) CU(cudaMemcpyAsync(grad_out, x.der, (size_t)n * t->es, cudaMemcpyDeviceToHost, S(t)));
     if (!on_device && cols > 0)
         CU(cudaMemcpy2DAsync(result, (size_t)ld * t->es, t->stage, (size_t)n * t->es, (size_t)n * t->es, (size_t)cols, cudaMemcpyDeviceToHost, S(t)));
@@ -1431,6 +1475,7 @@ int rdb_get_value(rdb_tape *t, int b, void *dst) {
 int rdb_get_deriv(rdb_tape *t, int b, void *dst) {
     if (!t || !dst || b < 0 || (size_t)b >= t->bufs.size()) return fail(RDB_EINVAL, "bad buffer id");
     if (!t->bufs[b].der) return fail(RDB_EINVAL, "buffer %d has no deriv (CONST)", b);
+    OK(dmaterialize(t, b, std::max<int64_t>(t->R_alloc, 1), false));
     CU(cudaMemcpyAsync(dst, t->bufs[b].der, (size_t)t->bufs[b].size * t->es, cudaMemcpyDeviceToHost, S(t)));
     CU(cudaStreamSynchronize(S(t)));
     return RDB_OK;

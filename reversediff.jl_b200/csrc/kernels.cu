@@ -180,15 +180,15 @@ cudaError_t launch_dot_block_sums(cudaStream_t s, const T *a, const T *b, int64_
 
 // dst[i + r*n] += delta[r]*src[i]     (dot reverse: lmul!(output_deriv, tmp); increment_deriv!, reductions.jl:114-131)
 template <typename T>
-__global__ void __launch_bounds__(kThreads) k_scal_acc(T *__restrict__ dst, const T *__restrict__ src, const T *__restrict__ delta, int64_t n, int64_t R) {
+__global__ void __launch_bounds__(kThreads) k_scal_acc(T *__restrict__ dst, const T *__restrict__ src, const T *__restrict__ delta, int64_t n, int64_t R, int overwrite) {
     int64_t tot = n * R;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
-    for (; i < tot; i += st) { int64_t r = i / n; dst[i] = dst[i] + delta[r] * src[i - r * n]; }
+    for (; i < tot; i += st) { int64_t r = i / n; T v = delta[r] * src[i - r * n]; dst[i] = overwrite ? v : dst[i] + v; }
 }
 template <typename T>
-cudaError_t launch_scal_acc(cudaStream_t s, T *dst, const T *src, const T *delta, int64_t n, int64_t R) {
+cudaError_t launch_scal_acc(cudaStream_t s, T *dst, const T *src, const T *delta, int64_t n, int64_t R, bool overwrite) {
     if (n * R <= 0) return cudaSuccess;
-    k_scal_acc<T><<<grid_for(n * R, 4), kThreads, 0, s>>>(dst, src, delta, n, R);
+    k_scal_acc<T><<<grid_for(n * R, 4), kThreads, 0, s>>>(dst, src, delta, n, R, overwrite ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -597,16 +597,16 @@ k_colvec_partial(double *__restrict__ scratch, const T *__restrict__ delta, cons
 }
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-k_colvec_finish(T *__restrict__ dst, const double *__restrict__ scratch, int64_t d0, int64_t R, int64_t chunks) {
+k_colvec_finish(T *__restrict__ dst, const double *__restrict__ scratch, int64_t d0, int64_t R, int64_t chunks, int overwrite) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= d0 * R) return;
     double acc = 0.0;
     for (int64_t c = 0; c < chunks; ++c) acc += scratch[c * R * d0 + i];
-    dst[i] = dst[i] + (T)acc;
+    dst[i] = overwrite ? (T)acc : dst[i] + (T)acc;
 }
 template <typename T>
 cudaError_t launch_mul_acc_colvec(cudaStream_t s, T *dst, const T *delta, const T *partial, int64_t d0, int64_t d1, int64_t R,
-                                  T *scratch_, int64_t scratch_elems) {
+                                  T *scratch_, int64_t scratch_elems, bool overwrite) {
     if (d0 * d1 * R <= 0) return cudaSuccess;
     double *scratch = reinterpret_cast<double *>(scratch_);
     int64_t bx = (d0 + kThreads - 1) / kThreads;
@@ -625,7 +625,7 @@ cudaError_t launch_mul_acc_colvec(cudaStream_t s, T *dst, const T *delta, const 
     k_colvec_partial<T><<<grid, kThreads, 0, s>>>(scratch, delta, partial, d0, d1, R, cols);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k_colvec_finish<T><<<(unsigned)((d0 * R + kThreads - 1) / kThreads), kThreads, 0, s>>>(dst, scratch, d0, R, chunks);
+    k_colvec_finish<T><<<(unsigned)((d0 * R + kThreads - 1) / kThreads), kThreads, 0, s>>>(dst, scratch, d0, R, chunks, overwrite ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -662,7 +662,7 @@ cudaError_t launch_mul_acc_generic(cudaStream_t s, T *dst, int64_t dst_n, const 
 // dst[i + r*n] += delta[clamp(i) + r*delta_n]   (reduction_increment_deriv!, propagation.jl:217-223: the adjoint of sum over dims)
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-k_bcast_acc(T *__restrict__ dst, GenericIdx g, const T *__restrict__ delta, int64_t n, int64_t R, int64_t delta_n) {
+k_bcast_acc(T *__restrict__ dst, GenericIdx g, const T *__restrict__ delta, int64_t n, int64_t R, int64_t delta_n, int overwrite) {
     int64_t tot = n * R;
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
     for (; i < tot; i += st) {
@@ -672,15 +672,15 @@ k_bcast_acc(T *__restrict__ dst, GenericIdx g, const T *__restrict__ delta, int6
             off += (rem % g.dims[d]) * g.dst_stride[d];
             rem /= g.dims[d];
         }
-        dst[i] = dst[i] + delta[off + r * delta_n];
+        dst[i] = overwrite ? delta[off + r * delta_n] : dst[i] + delta[off + r * delta_n];
     }
 }
 template <typename T>
-cudaError_t launch_bcast_acc(cudaStream_t s, T *dst, const int64_t *dims, const int64_t *delta_stride, const T *delta, int64_t n, int64_t R, int64_t delta_n) {
+cudaError_t launch_bcast_acc(cudaStream_t s, T *dst, const int64_t *dims, const int64_t *delta_stride, const T *delta, int64_t n, int64_t R, int64_t delta_n, bool overwrite) {
     if (n * R <= 0) return cudaSuccess;
     GenericIdx g;
     for (int d = 0; d < kMaxDims; ++d) { g.dims[d] = dims[d]; g.dst_stride[d] = delta_stride[d]; }
-    k_bcast_acc<T><<<grid_for(n * R, 2), kThreads, 0, s>>>(dst, g, delta, n, R, delta_n);
+    k_bcast_acc<T><<<grid_for(n * R, 2), kThreads, 0, s>>>(dst, g, delta, n, R, delta_n, overwrite ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -929,13 +929,13 @@ cudaError_t launch_copy2d(cudaStream_t s, T *dst, int64_t ldd, const T *src, int
     template cudaError_t launch_block_sums<T>(cudaStream_t, const T *, int64_t, T *);                                     \
     template cudaError_t launch_finish_sum<T>(cudaStream_t, const T *, T *, T, bool);                                     \
     template cudaError_t launch_dot_block_sums<T>(cudaStream_t, const T *, const T *, int64_t, T *);                      \
-    template cudaError_t launch_scal_acc<T>(cudaStream_t, T *, const T *, const T *, int64_t, int64_t);                   \
-    template cudaError_t launch_bcast_acc<T>(cudaStream_t, T *, const int64_t *, const int64_t *, const T *, int64_t, int64_t, int64_t); \
+    template cudaError_t launch_scal_acc<T>(cudaStream_t, T *, const T *, const T *, int64_t, int64_t, bool);             \
+    template cudaError_t launch_bcast_acc<T>(cudaStream_t, T *, const int64_t *, const int64_t *, const T *, int64_t, int64_t, int64_t, bool); \
     template cudaError_t launch_axpy<T>(cudaStream_t, T *, const T *, T, int64_t, bool);                                  \
     template cudaError_t launch_acc_scalar<T>(cudaStream_t, T *, int64_t, int64_t, const T *, T, bool);                   \
     template cudaError_t launch_expr_forward<T>(cudaStream_t, const ExprParams &);                                        \
     template cudaError_t launch_mul_acc<T>(cudaStream_t, T *, const T *, const T *, int64_t, int64_t, bool);              \
-    template cudaError_t launch_mul_acc_colvec<T>(cudaStream_t, T *, const T *, const T *, int64_t, int64_t, int64_t, T *, int64_t); \
+    template cudaError_t launch_mul_acc_colvec<T>(cudaStream_t, T *, const T *, const T *, int64_t, int64_t, int64_t, T *, int64_t, bool); \
     template cudaError_t launch_mul_acc_generic<T>(cudaStream_t, T *, int64_t, const int64_t *, const T *, const T *, const int64_t *, int64_t, int64_t); \
     template cudaError_t launch_gather<T>(cudaStream_t, T *, const T *, const int64_t *, int64_t);                        \
     template cudaError_t launch_scatter_add<T>(cudaStream_t, T *, int64_t, const int64_t *, const T *, int64_t, int64_t); \

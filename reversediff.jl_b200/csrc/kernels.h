@@ -74,9 +74,9 @@ template <typename T> cudaError_t launch_finish_sum(cudaStream_t, const T *block
 // block_sums <- per-block sums of a[i]*b[i]
 template <typename T> cudaError_t launch_dot_block_sums(cudaStream_t, const T *a, const T *b, int64_t n, T *block_sums);
 // dst[i + r*n] += delta[r]*src[i]
-template <typename T> cudaError_t launch_scal_acc(cudaStream_t, T *dst, const T *src, const T *delta, int64_t n, int64_t R);
+template <typename T> cudaError_t launch_scal_acc(cudaStream_t, T *dst, const T *src, const T *delta, int64_t n, int64_t R, bool overwrite = false);
 // dst[i + r*n] += delta[clamp(i) + r*delta_n], clamp given by per-dimension strides of delta (0 on reduced dims)
-template <typename T> cudaError_t launch_bcast_acc(cudaStream_t, T *dst, const int64_t *dims, const int64_t *delta_stride, const T *delta, int64_t n, int64_t R, int64_t delta_n);
+template <typename T> cudaError_t launch_bcast_acc(cudaStream_t, T *dst, const int64_t *dims, const int64_t *delta_stride, const T *delta, int64_t n, int64_t R, int64_t delta_n, bool overwrite = false);
 // dst (+)= sign*src over n elements (increment_deriv!/decrement_deriv!, propagation.jl:33-73)
 template <typename T> cudaError_t launch_axpy(cudaStream_t, T *dst, const T *src, T sign, int64_t n, bool overwrite);
 // dst[i + r*n] (+)= scale*delta[r]   (sum/mean reverse: scalar adjoint broadcast, reductions.jl:15-21,73-79)
@@ -87,7 +87,7 @@ template <typename T> cudaError_t launch_expr_forward(cudaStream_t, const ExprPa
 template <typename T> cudaError_t launch_mul_acc(cudaStream_t, T *dst, const T *delta, const T *partial, int64_t n, int64_t R, bool overwrite);
 // clamped accumulate into a column vector: dst[i + r*d0] += sum_j delta[i + j*d0 + r*d0*d1]*partial[i + j*d0]
 // (propagation.jl:90-96 with bound (d0,1)); scratch holds d0*R*chunks partial sums
-template <typename T> cudaError_t launch_mul_acc_colvec(cudaStream_t, T *dst, const T *delta, const T *partial, int64_t d0, int64_t d1, int64_t R, T *scratch, int64_t scratch_elems);
+template <typename T> cudaError_t launch_mul_acc_colvec(cudaStream_t, T *dst, const T *delta, const T *partial, int64_t d0, int64_t d1, int64_t R, T *scratch, int64_t scratch_elems, bool overwrite = false);
 // generic clamped accumulate (any broadcast pattern) with atomics
 template <typename T> cudaError_t launch_mul_acc_generic(cudaStream_t, T *dst, int64_t dst_n, const int64_t *dst_stride, const T *delta, const T *partial, const int64_t *dims, int64_t n, int64_t R);
 // out[k] = src[map[k]]      (pull_value! of IDX operands, getindex forward: tracked.jl:178-181,331-340)
