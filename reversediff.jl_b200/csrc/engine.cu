@@ -460,11 +460,56 @@ static int mul_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
     ref(oa, A);
     ref(ob, B);
     const T *delta = (const T *)out.der;
+    // When a GEMM is the LAST accumulation into a tape input whose result goes to the host (gradient!), it is cut into column
+    // panels of the result and each finished panel starts its D2H copy while the next one computes.
+    auto &E = t->early;
+    auto want_panels = [&](int buffer, int64_t rows, int64_t cols) -> int {
+        const int rb = droot(t, buffer);
+        if (E.enabled && R == 1 && E.dst[rb] && !E.issued[rb] && E.remaining[rb] == 1 && cols >= 2048 &&
+            rows * cols * (int64_t)t->es >= (32 << 20) && E.n_ev + 4 <= kMaxArgs * 2)
+            return 4;
+        return 1;
+    };
+    auto panel_copy = [&](int buffer, int64_t first_elem, int64_t n_elems) -> int {
+        const int rb = droot(t, buffer);
+        cudaEvent_t &ev = E.ev[E.n_ev];
+        if (!ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        E.n_ev++;
+        CU(cudaEventRecord(ev, S(t)));
+        CU(cudaStreamWaitEvent(t->ctx->copy_stream, ev, 0));
+        CU(cudaMemcpyAsync((char *)E.dst[rb] + (size_t)first_elem * t->es, (char *)t->bufs[rb].der + (size_t)first_elem * t->es,
+                           (size_t)n_elems * t->es, cudaMemcpyDeviceToHost, t->ctx->copy_stream));
+        return RDB_OK;
+    };
+    auto panels_done = [&](int buffer) { const int rb = droot(t, buffer); E.issued[rb] = 1; E.remaining[rb] = 0; };
     if (oa.rec.tracked) {
         Buf &ba = t->bufs[oa.rec.buffer];
         StepTimer tm(t, "gemm_reverse_a", (double)(M * N + K * N + 2 * M * K) * t->es * R, 2.0 * M * N * K * R);
         if (oa.mode == OPM_GATHER) OK(dmaterialize(t, oa.rec.buffer, R, true));
         const T beta_a = (oa.mode != OPM_GATHER && dtake(t, oa.rec.buffer)) ? (T)0 : (T)1;
+        const int pa = oa.mode == OPM_PLAIN ? want_panels(oa.rec.buffer, M, K) : (oa.mode == OPM_FOLDED_T ? want_panels(oa.rec.buffer, K, M) : 1);
+        if (pa > 1) {
+            if (oa.mode == OPM_PLAIN) {
+                // column panels [k0,k1) of a.deriv(MxK) = delta(MxN) * Bmat'(N x k-panel)
+                const int64_t pk = ((K + pa - 1) / pa + 63) & ~63LL;
+                for (int64_t k0 = 0; k0 < K; k0 += pk) {
+                    const int64_t kn = std::min<int64_t>(pk, K - k0);
+                    const T *bp = B.stored_t ? B.ptr + k0 * B.ld : B.ptr + k0;
+                    KL(t, gemm_t<T>(S(t), false, !B.stored_t, M, kn, N, (T)1, delta, M, bp, B.ld, beta_a, (T *)ba.der + k0 * M, M));
+                    OK(panel_copy(oa.rec.buffer, k0 * M, kn * M));
+                }
+            } else {
+                // column panels [m0,m1) of origin.deriv(KxM) = Bmat(KxN) * delta'(N x m-panel)
+                const int64_t pm = ((M + pa - 1) / pa + 63) & ~63LL;
+                for (int64_t m0 = 0; m0 < M; m0 += pm) {
+                    const int64_t mn = std::min<int64_t>(pm, M - m0);
+                    g_tag_a = operand_tag(t, ob);
+                    KL(t, gemm_t<T>(S(t), B.stored_t, true, K, mn, N, (T)1, B.ptr, B.ld, delta + m0, M, beta_a, (T *)ba.der + m0 * K, K));
+                    OK(panel_copy(oa.rec.buffer, m0 * K, mn * K));
+                }
+            }
+            panels_done(oa.rec.buffer);
+        } else
         for (int64_t r = 0; r < R; ++r) {
             const T *d = delta + r * M * N;
             if (oa.mode == OPM_PLAIN) {
@@ -490,8 +535,20 @@ static int mul_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
         const T beta_b = (ob.mode != OPM_GATHER && dtake(t, ob.rec.buffer)) ? (T)0 : (T)1;
         if (ob.mode == OPM_PLAIN) {
             // b.deriv(K x N*R) += Amat'(KxM) * delta(M x N*R): the R seed columns ride along as extra GEMM columns
-            g_tag_a = operand_tag(t, oa);
-            KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, N * R, M, (T)1, A.ptr, A.ld, delta, M, beta_b, (T *)bb.der, K));
+            const int panels = want_panels(ob.rec.buffer, K, N);
+            if (panels == 1) {
+                g_tag_a = operand_tag(t, oa);
+                KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, N * R, M, (T)1, A.ptr, A.ld, delta, M, beta_b, (T *)bb.der, K));
+            } else {
+                const int64_t pn = ((N + panels - 1) / panels + 63) & ~63LL;
+                for (int64_t j0 = 0; j0 < N; j0 += pn) {
+                    const int64_t jn = std::min<int64_t>(pn, N - j0);
+                    g_tag_a = operand_tag(t, oa);
+                    KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, jn, M, (T)1, A.ptr, A.ld, delta + j0 * M, M, beta_b, (T *)bb.der + j0 * K, K));
+                    OK(panel_copy(ob.rec.buffer, j0 * K, jn * K));
+                }
+                panels_done(ob.rec.buffer);
+            }
         } else {
             for (int64_t r = 0; r < R; ++r) {
                 const T *d = delta + r * M * N;
