@@ -237,8 +237,11 @@ class OracleTape:
                 op.dims = tuple(int(d) for d in o["dims"][:nd])
                 op.bound = tuple(int(x) for x in o["bound"])
                 k = int(o["idx_kind"])
+                op.unique = True
                 if k == IDX_EXPLICIT:
                     op.idx = idx[int(o["idx_offset"]): int(o["idx_offset"]) + int(o["idx_len"])]
+                    # duplicates must each add once (sequential semantics); without duplicates a vectorised += is the same thing
+                    op.unique = np.unique(op.idx).size == op.idx.size
                 elif k == IDX_TRANSPOSE:
                     # adjoint of a (rows x cols) parent: element (i,j) -> j + i*rows   (tracked.jl:348-351)
                     rows, cols = self.dims[op.buffer]
@@ -275,7 +278,11 @@ class OracleTape:
         if op.cls == CLS_IDX:
             # per element: pull_deriv!, add, push_deriv! (propagation.jl:45-50) — sequential, duplicates add
             flat = d.reshape(-1, order="F")
-            np.add.at(flat, op.idx, sign * np.asarray(x, self.dtype).reshape(-1, order="F"))
+            upd = sign * np.asarray(x, self.dtype).reshape(-1, order="F")
+            if op.unique:
+                flat[op.idx] += upd
+            else:
+                np.add.at(flat, op.idx, upd)
             self.deriv[op.buffer][...] = flat.reshape(d.shape, order="F")
         elif op.cls == CLS_TR:
             d[...] = d + sign * x
@@ -437,7 +444,10 @@ class OracleTape:
         elif op in (OP_GETINDEX, OP_GETINDEX_GENERIC):   # tracked.jl:318-329,363-376
             d = self.deriv[a[0].buffer]
             flat = d.reshape(-1, order="F")
-            np.add.at(flat, a[0].idx, np.asarray(delta).reshape(-1, order="F"))
+            if a[0].unique:
+                flat[a[0].idx] += np.asarray(delta).reshape(-1, order="F")
+            else:
+                np.add.at(flat, a[0].idx, np.asarray(delta).reshape(-1, order="F"))
             d[...] = flat.reshape(d.shape, order="F")
         else:
             raise NotImplementedError(f"opcode {op}")
