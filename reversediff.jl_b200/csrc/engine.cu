@@ -582,8 +582,9 @@ static int expr_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
             if (od != out.dims[d]) same = false;
         }
         if (same) {
-            StepTimer tm(t, "expr_reverse", 4.0 * out.size * R * t->es, 0);
-            KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[a], out.size, R, dtake(t, o.rec.buffer)));
+            const bool ow = dtake(t, o.rec.buffer);
+            StepTimer tm(t, "expr_reverse", ((ow ? 2.0 : 3.0) * R + 1.0) * out.size * t->es, 0);
+            KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[a], out.size, R, ow));
         } else if (o.size == 1) {
             // scalar (TrackedReal) argument: input_deriv += sum_i x[i]*partial[i]   (propagation.jl:98-108; unbroadcast(::Number) = sum)
             StepTimer tm(t, "expr_reverse_scalar", 2.0 * out.size * R * t->es, 0);
@@ -633,8 +634,9 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                     if (!I.in[a].rec.tracked) continue;
                     Buf &b = t->bufs[I.in[a].rec.buffer];
                     T sign = (a == 1 && I.rec.opcode == OP_SUB) ? (T)-1 : (T)1;
-                    StepTimer tm(t, "add_reverse", 3.0 * out.size * R * t->es, 0);
-                    KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, sign, out.size * R, dtake(t, I.in[a].rec.buffer)));
+                    const bool ow = dtake(t, I.in[a].rec.buffer);
+                    StepTimer tm(t, "add_reverse", (ow ? 2.0 : 3.0) * out.size * R * t->es, 0);
+                    KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, sign, out.size * R, ow));
                     OK(acc_done(t, I.in[a].rec.buffer));
                 }
                 break;
@@ -650,8 +652,9 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                 if (I.in[0].rec.tracked) {
                     Buf &b = t->bufs[I.in[0].rec.buffer];
                     T scale = I.rec.opcode == OP_MEAN ? (T)1 / (T)I.in[0].size : (T)1;
-                    StepTimer tm(t, "sum_reverse", 2.0 * b.size * R * t->es, 0);
-                    KL(t, launch_acc_scalar<T>(S(t), (T *)b.der, b.size, R, delta, scale, dtake(t, I.in[0].rec.buffer)));
+                    const bool ow = dtake(t, I.in[0].rec.buffer);
+                    StepTimer tm(t, "sum_reverse", (ow ? 1.0 : 2.0) * b.size * R * t->es, 0);
+                    KL(t, launch_acc_scalar<T>(S(t), (T *)b.der, b.size, R, delta, scale, ow));
                     OK(acc_done(t, I.in[0].rec.buffer));
                 }
                 break;
