@@ -296,16 +296,17 @@ def main():
     if args.dtype == "f64" and mode == 0:
         # tcgen05 kind::i8 path: every FP64 GEMM is S(S+1)/2 = 36 exact int8 slice products of the same shape
         ops_per_flop = slices * (slices + 1) / 2
-        kernel = "oz2::umma_ozaki2_kernel<8,64> (TMA + tcgen05.mma kind::i8, int32 TMEM accumulators) + k_slice_i8/k_row_absmax"
+        kernel = ("oz2::umma_ozaki2c_kernel<8,2> (TMA multicast in 2-CTA clusters + tcgen05.mma kind::i8, int32 TMEM accumulators) "
+                  "+ k_slice_i8/k_row_absmax")
         unit, pipe_peak = "TOP/s (int8)", 2.0 * bf16_peak
         peak_src = f"2 x {peak_tag} (int8 issues at twice the bf16 rate; no int8 figure is measured on this pool; nominal dense 4500)"
-        traffic = 2.03e9 + 0.13e9       # dram__bytes_read+write per launch, ncu --set full (profiles/prof_ozaki2_r1.txt)
+        traffic = 2.058e9 + 0.130e9     # dram__bytes_read+write per 4096^3 launch, ncu --set full (profiles/prof_ozaki2c_r1.txt)
     elif args.dtype == "f64":
         ops_per_flop = 1.0
         kernel = "d64::dgemm_dmma_kernel (mma.sync m8n8k4 f64 = SASS DMMA.8x8x4)"
         unit, pipe_peak = "TFLOP/s (fp64)", blas_peak
         peak_src = "cuBLAS DGEMM measured in this run (MEASURED_PEAKS.json holds no FP64 figure)"
-        traffic = 1.10e9 + 0.12e9       # profiles/prof_dgemm_r1a.txt
+        traffic = 1.084e9 + 0.121e9     # profiles/prof_dgemm_r1.txt
     else:
         ops_per_flop = 3.0
         kernel = "umma::umma_gemm_kernel<tf32> (TMA + tcgen05.mma kind::tf32, 3xTF32 split) + k_split_tf32"
