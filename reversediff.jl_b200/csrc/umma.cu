@@ -347,7 +347,8 @@ __global__ void __launch_bounds__(256) k_row_absmax(const double *__restrict__ s
         if (r >= rows) return;
         const double *p = src + (int64_t)r * ld;
         double mx = 0.0;
-        for (int k = lane; k < K; k += 32) mx = fmax(mx, fabs(p[k]));
+        // NaN/Inf anywhere in the row poisons the row: fmax() would silently drop a NaN, so non-finite elements count as +Inf
+        for (int k = lane; k < K; k += 32) { double v = fabs(p[k]); mx = fmax(mx, v <= 1.7976931348623157e308 ? v : __longlong_as_double(0x7FF0000000000000LL)); }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if (lane == 0) mx_bits[r] = (unsigned long long)__double_as_longlong(mx);
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(256) k_row_absmax(const double *__restrict__ s
         int k0 = blockIdx.y * 64, k1 = min(K, k0 + 64);
         double mx = 0.0;
 #pragma unroll 8
-        for (int k = k0; k < k1; ++k) mx = fmax(mx, fabs(src[r + (int64_t)k * ld]));
+        for (int k = k0; k < k1; ++k) { double v = fabs(src[r + (int64_t)k * ld]); mx = fmax(mx, v <= 1.7976931348623157e308 ? v : __longlong_as_double(0x7FF0000000000000LL)); }
         atomicMax(mx_bits + r, (unsigned long long)__double_as_longlong(mx));
     }
 }
@@ -366,9 +367,11 @@ __global__ void __launch_bounds__(256) k_row_exponent(const unsigned long long *
     int r = blockIdx.x * 256 + threadIdx.x;
     if (r >= rows) return;
     double mx = __longlong_as_double((long long)mx_bits[r]);
-    int e = (mx > 0.0 && isfinite(mx)) ? ilogb(mx) + 2 : 0;
+    const bool finite = isfinite(mx);
+    int e = (mx > 0.0 && finite) ? ilogb(mx) + 2 : 0;
     e_out[r] = e;
-    scale_out[r] = scalbn(1.0, e);
+    // a row/column holding NaN or Inf gets a NaN scale: every output it touches becomes NaN, as DGEMM would propagate it
+    scale_out[r] = finite ? scalbn(1.0, e) : __longlong_as_double(0x7FF8000000000000LL);
 }
 
 // ---- pass 2: slices.  dst is [s][rows][Kp] int8, k contiguous.  Block = 32 rows x 128 k; thread = 1 row x 4 consecutive k per
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, cons
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) X[i][j] = __double2ll_rn(scalbn(v[j], 7 * nslices - e));
+        for (int j = 0; j < 4; ++j) X[i][j] = isfinite(v[j]) ? __double2ll_rn(scalbn(v[j], 7 * nslices - e)) : 0LL;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

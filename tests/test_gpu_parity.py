@@ -78,6 +78,25 @@ def test_gemm_kernel(rd, ctx, dtype, mode, ta, tb, m, n, k):
     _ = tdt
 
 
+def test_gemm_int8_path_propagates_nonfinite(rd, ctx):
+    """NaN / Inf in an operand row must poison the outputs it touches on the sliced tcgen05 path too (DGEMM semantics)."""
+    import torch
+    n = 512
+    A = torch.rand(n, n, dtype=torch.float64, device="cuda"); B = torch.rand(n, n, dtype=torch.float64, device="cuda")
+    A[7, 100] = float("nan")            # column-major view: element (row 100, col 7) of the stored matrix
+    B[300, 5] = float("inf")            # element (row 5, col 300)
+    C = torch.zeros(n, n, dtype=torch.float64, device="cuda")
+    ctx.set_gemm_f64_mode(0)
+    ctx.gemm(0, 0, 0, n, n, n, 1.0, A.data_ptr(), n, B.data_ptr(), n, 0.0, C.data_ptr(), n)
+    ctx.synchronize()
+    Cm = C.cpu().numpy().T               # back to (row, col)
+    assert np.all(~np.isfinite(Cm[100, :]))      # row 100 of op(A) holds the NaN
+    assert np.all(~np.isfinite(Cm[:, 300]))      # column 300 of op(B) holds the Inf
+    mask = np.ones((n, n), bool); mask[100, :] = False; mask[:, 300] = False
+    ref = (A.cpu().numpy().T @ B.cpu().numpy().T)
+    assert np.all(np.isfinite(Cm[mask])) and np.max(np.abs(Cm[mask] - ref[mask])) < 1e-11
+
+
 def test_gemm_beta0_ignores_nan(rd, ctx):
     import torch
     A = torch.ones(128, 128, dtype=torch.float64, device="cuda")
