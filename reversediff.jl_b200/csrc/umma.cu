@@ -447,6 +447,7 @@ struct OzParams {
     double alpha, beta;
     const double *sa, *sb;      // 2^ea[row], 2^eb[col]
     int nslices;
+    int group_m;                // tile rasterisation group (see raster())
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -596,6 +597,19 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_i8(int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
 }
 
+// Tile rasterisation: CTAs are dispatched in linear block order (x fastest).  With x = m-tile a wave of 148 CTAs touched every
+// m-tile, i.e. ALL slices of A (134 MB at 4096^2) per wave, and ncu showed A re-read from DRAM once per wave (2.06 GB per launch for
+// 0.27 GB of operands).  Remap so that consecutive (cluster) ids walk GROUP_M m-tiles x all n-tiles: a wave then works on
+// ~GROUP_M m-tiles of A plus a few n-tiles of B, which stay in the 126 MB L2 for the waves that follow.
+__device__ __forceinline__ void raster(int cid, int tiles_m, int tiles_n, int GROUP_M, int &m_tile, int &n_tile) {
+    const int per_group = GROUP_M * tiles_n;
+    const int group = cid / per_group, first_m = group * GROUP_M;
+    const int gsz = min(GROUP_M, tiles_m - first_m);
+    const int in_group = cid - group * per_group;
+    m_tile = first_m + in_group % gsz;
+    n_tile = in_group / gsz;
+}
+
 template <int S, int KB>
 __global__ void __launch_bounds__(THREADS, 1)
 umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, OzParams P) {
@@ -609,7 +623,9 @@ umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     constexpr int TCOLS = S * BN2 <= 32 ? 32 : S * BN2 <= 64 ? 64 : S * BN2 <= 128 ? 128 : S * BN2 <= 256 ? 256 : 512;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM2, n0 = blockIdx.y * BN2;
+    int m_tile, n_tile;
+    raster((int)(blockIdx.x + gridDim.x * blockIdx.y), (int)gridDim.x, (int)gridDim.y, P.group_m, m_tile, n_tile);
+    const int m0 = m_tile * BM2, n0 = n_tile * BN2;
     const int kblocks = (K + BKB2 - 1) / BKB2;
 
     if (warp == 0 && lane == 0) {
@@ -750,7 +766,9 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
-    const int m0 = blockIdx.x * BM2, n0 = blockIdx.y * BN2;
+    int m_tile, n_group;
+    raster((int)(blockIdx.x + gridDim.x * (blockIdx.y / CL)), (int)gridDim.x, (int)(gridDim.y / CL), P.group_m, m_tile, n_group);
+    const int m0 = m_tile * BM2, n0 = (n_group * CL + (int)crank) * BN2;
     const int kblocks = (K + KB - 1) / KB;
 
     if (warp == 0 && lane == 0) {
@@ -1043,7 +1061,9 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     if (pe != cudaSuccess) return pe;
     g_chunk_launches = la + lb + 1;
     CUtensorMap mA, mB;
-    OzParams P{C, ldc, alpha, beta, sa, sb, nslices};
+    static int group_m = -1;
+    if (group_m < 0) { const char *e = getenv("RDB_OZAKI_GROUP_M"); group_m = e ? atoi(e) : 8; if (group_m < 1) group_m = 1 << 20; }
+    OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m};
     static int gen = -1;
     if (gen < 0) { const char *e = getenv("RDB_OZAKI_GEN"); gen = e ? atoi(e) : 2; }
     if (gen == 2 && nslices <= 8) {
