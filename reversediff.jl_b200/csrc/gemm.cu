@@ -127,6 +127,14 @@ constexpr int smem_bytes() {
 
 // op(A) is MxK.  !TA: A stored MxK (m contiguous)  -> not KMAJOR.   TA: A stored KxM (k contiguous) -> KMAJOR.
 // op(B) is KxN.  !TB: B stored KxN (k contiguous)  -> KMAJOR.       TB: B stored NxK (n contiguous) -> not KMAJOR.
+// Grouped tile order (see umma.cu raster()): consecutive CTAs walk 8 m-tiles x all n-tiles so a wave's A panel stays in L2.
+__device__ __forceinline__ void raster8(int &m_tile, int &n_tile) {
+    const int cid = blockIdx.x + gridDim.x * blockIdx.y, tiles_m = gridDim.x, tiles_n = gridDim.y;
+    const int per_group = 8 * tiles_n, group = cid / per_group, first_m = group * 8;
+    const int gsz = min(8, tiles_m - first_m), in_group = cid - group * per_group;
+    m_tile = first_m + in_group % gsz;
+    n_tile = in_group / gsz;
+}
 template <bool TA, bool TB, bool VEC, int NWN>
 __global__ void __launch_bounds__(Cfg<NWN>::THREADS_, Cfg<NWN>::MINB)
 dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, int64_t lda,
@@ -141,7 +149,9 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp / NWN, wn = warp % NWN;   // 2 x NWN warps; warp tile 64 x 32
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    int m_tile, n_tile;
+    raster8(m_tile, n_tile);
+    const int m0 = m_tile * BM, n0 = n_tile * BN;
     const int KT = (K + BK - 1) / BK;
 
     TileLoader<TA, BM, VEC, THREADS> la;

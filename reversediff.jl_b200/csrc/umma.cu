@@ -130,6 +130,19 @@ struct EpiF32 {           // C = alpha*acc + beta*C   (FP32, column-major)
     }
 };
 // ------------------------------------------------------------------------------------------ the kernel
+// Tile rasterisation: CTAs are dispatched in linear block order (x fastest).  With x = m-tile a wave of 148 CTAs touched every
+// m-tile, i.e. ALL slices of A (134 MB at 4096^2) per wave, and ncu showed A re-read from DRAM once per wave (2.06 GB per launch for
+// 0.27 GB of operands).  Remap so that consecutive (cluster) ids walk GROUP_M m-tiles x all n-tiles: a wave then works on
+// ~GROUP_M m-tiles of A plus a few n-tiles of B, which stay in the 126 MB L2 for the waves that follow.
+__device__ __forceinline__ void raster(int cid, int tiles_m, int tiles_n, int GROUP_M, int &m_tile, int &n_tile) {
+    const int per_group = GROUP_M * tiles_n;
+    const int group = cid / per_group, first_m = group * GROUP_M;
+    const int gsz = min(GROUP_M, tiles_m - first_m);
+    const int in_group = cid - group * per_group;
+    m_tile = first_m + in_group % gsz;
+    n_tile = in_group / gsz;
+}
+
 template <int KIND, typename Epi>
 __global__ void __launch_bounds__(THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
@@ -144,7 +157,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t *tmem_ptr = (uint32_t *)(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    int m_tile, n_tile;
+    raster((int)(blockIdx.x + gridDim.x * blockIdx.y), (int)gridDim.x, (int)gridDim.y, 8, m_tile, n_tile);
+    const int m0 = m_tile * BM, n0 = n_tile * BN;
     constexpr int ELEMS = KIND == KIND_TF32 ? BKB / 4 : BKB;      // K elements per stage
     constexpr int KSTEP = KIND == KIND_TF32 ? 8 : 32;              // K elements per tcgen05.mma (32 bytes)
     const int kblocks = (K + ELEMS - 1) / ELEMS;
@@ -595,19 +610,6 @@ __device__ __forceinline__ uint64_t make_desc_kb(uint32_t saddr) {
 }
 __device__ __forceinline__ constexpr uint32_t make_idesc_i8(int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
-}
-
-// Tile rasterisation: CTAs are dispatched in linear block order (x fastest).  With x = m-tile a wave of 148 CTAs touched every
-// m-tile, i.e. ALL slices of A (134 MB at 4096^2) per wave, and ncu showed A re-read from DRAM once per wave (2.06 GB per launch for
-// 0.27 GB of operands).  Remap so that consecutive (cluster) ids walk GROUP_M m-tiles x all n-tiles: a wave then works on
-// ~GROUP_M m-tiles of A plus a few n-tiles of B, which stay in the 126 MB L2 for the waves that follow.
-__device__ __forceinline__ void raster(int cid, int tiles_m, int tiles_n, int GROUP_M, int &m_tile, int &n_tile) {
-    const int per_group = GROUP_M * tiles_n;
-    const int group = cid / per_group, first_m = group * GROUP_M;
-    const int gsz = min(GROUP_M, tiles_m - first_m);
-    const int in_group = cid - group * per_group;
-    m_tile = first_m + in_group % gsz;
-    n_tile = in_group / gsz;
 }
 
 template <int S, int KB>
