@@ -36,6 +36,8 @@ IDX_NONE, IDX_EXPLICIT, IDX_TRANSPOSE = 0, 1, 2
 (OP_MUL, OP_ADD, OP_SUB, OP_NEG, OP_SUM, OP_MEAN, OP_NBCAST, OP_MAP, OP_BCAST,
  OP_BCAST_ADD, OP_BCAST_SUB, OP_BCAST_MUL) = range(1, 13)
 OP_BCAST_DIV, OP_BCAST_LDIV, OP_BCAST_POW, OP_GETINDEX, OP_DOT, OP_SUMDIMS, OP_TRACKER_BCAST, OP_GETINDEX_GENERIC = range(13, 21)
+OP_SCALAR_BLOCK = 21
+SP_POOL, SP_LITERAL, SP_NONE = -1, -2, -3
 ELEMENTWISE = (OP_NBCAST, OP_MAP, OP_BCAST, OP_BCAST_ADD, OP_BCAST_SUB, OP_BCAST_MUL, OP_BCAST_DIV, OP_BCAST_LDIV, OP_BCAST_POW,
                OP_TRACKER_BCAST)
 (E_CONST, E_ADD, E_SUB, E_MUL, E_DIV, E_NEG, E_POWI, E_POW, E_TANH, E_EXP, E_LOG, E_SQRT,
@@ -255,6 +257,8 @@ class OracleTape:
                 eo, el = int(rec["expr_offset"]), int(rec["expr_len"])
                 it.expr = expr[eo: eo + 4 * el].reshape(-1, 4)
             it.cache = None
+            if it.opcode == OP_SCALAR_BLOCK:
+                it.block = _ScalarBlock(it.inputs[0].idx, expr)
             self.instrs.append(it)
 
     # ------------------------------------------------------------------ operand accessors
@@ -385,6 +389,8 @@ class OracleTape:
             x = self._val(a[0])
             axes = tuple(d for d in range(x.ndim) if out.shape[d] == 1 and x.shape[d] != 1)
             out[...] = np.sum(x, axis=axes, keepdims=True)
+        elif op == OP_SCALAR_BLOCK:
+            self._scalar_forward(it.block)
         else:
             raise NotImplementedError(f"opcode {op}")
 
@@ -392,6 +398,9 @@ class OracleTape:
         op = it.opcode
         a = it.inputs
         delta = self.deriv[it.out]
+        if op == OP_SCALAR_BLOCK:
+            self._scalar_reverse(it.block)
+            return
         if op == OP_MUL:                      # arithmetic.jl:260-285 (generic method on materialised operands)
             va, vb = self._val(a[0]), self._val(a[1])
             d2 = np.asarray(delta).reshape((va.shape[0], -1) if va.ndim == 2 else delta.shape, order="F")
@@ -452,6 +461,123 @@ class OracleTape:
         else:
             raise NotImplementedError(f"opcode {op}")
         self._unseed(it.out)                  # every reverse exec ends with unseed!(output)
+
+
+    # ------------------------------------------------------------------ scalar instructions
+    def _flat(self, arrs, b):
+        """Column-major flat VIEW of a buffer (buffers are allocated order='F', so this never copies)."""
+        f = arrs[b].reshape(-1, order="F")
+        assert f.size == 0 or np.shares_memory(f, arrs[b])
+        return f
+
+    def _scalar_forward(self, blk):
+        """``scalar_forward_exec!`` for every instruction of the run, in tape order (``scalars.jl:80-123``): pull the input
+        values (``pull_value!``: an origin-linked TrackedReal re-reads ``origin.value[index]``, ``tracked.jl:178-181``),
+        one ``ForwardDiff.derivative!`` / ``gradient!`` evaluation, store the value and cache the partials."""
+        if blk.run_c(self, forward=True):
+            return
+        dt = self.dtype.type
+        val = blk.val = np.zeros(blk.n, self.dtype)
+        pa = blk.pa = np.zeros(blk.n, self.dtype)
+        pb = blk.pb = np.zeros(blk.n, self.dtype)
+        flats = [self._flat(self.value, b) for b in blk.refbufs]
+
+        def get(space, idx):
+            if space == SP_POOL: return val[idx]
+            if space == SP_LITERAL: return dt(self.fconst[idx])
+            if space == SP_NONE: return None
+            return flats[space][idx]
+        for i in range(blk.n):
+            args = [v for v in (get(blk.a_space[i], blk.a_idx[i]), get(blk.b_space[i], blk.b_idx[i])) if v is not None]
+            eo, el, na = blk.exprs[blk.expr_id[i]]
+            v, part, _ = dual_eval(blk.expr_words[eo: eo + 4 * el].reshape(-1, 4), self.fconst, args, self.dtype)
+            val[i] = v
+            if na >= 1: pa[i] = part[0]
+            if na >= 2: pb[i] = part[1]
+        for slot, r, e in blk.exports:            # the slot IS the buffer element for everything outside the run
+            flats[r][e] = val[slot]
+
+    def _scalar_reverse(self, blk):
+        """``scalar_reverse_exec!`` in reverse tape order (``scalars.jl:52-74``): ``increment_deriv!(input, deriv(output) *
+        partial)`` — for an origin-linked TrackedReal that is pull_deriv!, add, push_deriv! on ``origin.deriv[index]``
+        (``propagation.jl:33-36``, ``tracked.jl:186-197``) — then ``unseed!(output)``."""
+        dflats = [self._flat(self.deriv, b) for b in blk.refbufs]
+        der = blk.der = np.zeros(blk.n, self.dtype)
+        for slot, r, e in blk.exports:            # adjoints that later instructions pushed into the exported slots
+            der[slot] = der[slot] + dflats[r][e]
+            dflats[r][e] = 0                      # (one TrackedReal, one deriv field: it now lives in der[slot])
+        if blk.run_c(self, forward=False):
+            return
+        for i in range(blk.n - 1, -1, -1):
+            d = der[i]
+            for space, idx, p in ((blk.a_space[i], blk.a_idx[i], blk.pa[i]), (blk.b_space[i], blk.b_idx[i], blk.pb[i])):
+                if space == SP_POOL:
+                    der[idx] = der[idx] + d * p
+                elif space >= 0:
+                    dflats[space][idx] = dflats[space][idx] + d * p
+            der[i] = 0                            # unseed!(output)
+
+
+class _ScalarBlock:
+    """Parsed payload of an OP_SCALAR_BLOCK entry (layout: reversediff.jl_b200/program.py ``ScalarBlock``)."""
+
+    use_c = True
+
+    def __init__(self, w, expr_words):
+        w = np.asarray(w, np.int64)
+        n, nref, nexp, nex = (int(v) for v in w[:4])
+        o = 4
+        self.n = n
+        self.refbufs = [int(v) for v in w[o:o + nref]]; o += nref
+        self.exprs = [tuple(int(v) for v in row) for row in w[o:o + 3 * nex].reshape(-1, 3)]; o += 3 * nex
+        self.exports = [tuple(int(v) for v in row) for row in w[o:o + 3 * nexp].reshape(-1, 3)]; o += 3 * nexp
+        body = np.ascontiguousarray(w[o:o + 5 * n].reshape(-1, 5))
+        self.body = body
+        self.expr_id, self.a_space, self.a_idx, self.b_space, self.b_idx = (body[:, k].tolist() for k in range(5))
+        self.expr_words = np.ascontiguousarray(expr_words, np.int32)
+        self.expr_table = np.ascontiguousarray(np.asarray(self.exprs, np.int64).reshape(-1, 3))
+
+    def run_c(self, tape, forward):
+        """Same loops in C (oracle/scalar_block.c) when the helper library has been built — identical statements, used so
+        that the CPU baseline is not a Python-interpreter benchmark.  Returns False when unavailable (pure-Python loops run)."""
+        lib = _scalar_lib() if self.use_c else None
+        if lib is None or tape.dtype != np.float64:
+            return False
+        import ctypes as C
+        nref = len(self.refbufs)
+        arrs = tape.value if forward else tape.deriv
+        ptrs = (C.c_void_p * max(nref, 1))(*[tape._flat(arrs, b).ctypes.data for b in self.refbufs])
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        if forward:
+            self.val = np.zeros(self.n); self.pa = np.zeros(self.n); self.pb = np.zeros(self.n)
+            rc = lib.scalar_block_forward(C.c_int64(self.n), P(self.body), P(self.expr_table), P(self.expr_words), P(tape.fconst),
+                                          ptrs, P(self.val), P(self.pa), P(self.pb))
+            if rc != 0:
+                raise ValueError(f"scalar_block_forward: unknown scalar opcode {rc}")
+            flats = [tape._flat(tape.value, b) for b in self.refbufs]
+            for slot, r, e in self.exports:
+                flats[r][e] = self.val[slot]
+        else:
+            lib.scalar_block_reverse(C.c_int64(self.n), P(self.body), ptrs, P(self.der), P(self.pa), P(self.pb))
+        return True
+
+
+_SCALAR_LIB = [False]
+
+
+def _scalar_lib():
+    if _SCALAR_LIB[0] is False:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libscalar_block.so")
+        try:
+            lib = ctypes.CDLL(path)
+            lib.scalar_block_forward.restype = ctypes.c_int
+            lib.scalar_block_reverse.restype = ctypes.c_int
+            _SCALAR_LIB[0] = lib
+        except OSError:
+            _SCALAR_LIB[0] = None
+    return _SCALAR_LIB[0]
 
 
 # ======================================================================================

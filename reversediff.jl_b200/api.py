@@ -22,7 +22,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import program as P
-from .tracked import InstructionTape, TrackedArray, TrackedReal, value
+from .tracked import InstructionTape, TrackedArray, TrackedReal, value, scalar_buffer, collect
 from . import engine as _engine
 
 
@@ -70,8 +70,10 @@ class AbstractTape:
             prog.inputs.append(b)
             self.input.append(TrackedArray(v, self.tape, b))
         self.output = func(*self.input) if self.is_tuple else func(self.input[0])
+        if isinstance(self.output, (list, tuple)) or (isinstance(self.output, np.ndarray) and self.output.dtype == object):
+            self.output = collect(self.output, self.tape)       # Array{TrackedReal} output (api/utils.jl:44-58 seeds it elementwise)
         self._check_output()
-        prog.output_buffer = self.output.buffer
+        prog.output_buffer = scalar_buffer(self.output) if isinstance(self.output, TrackedReal) else self.output.buffer
 
     def _check_output(self):
         raise NotImplementedError

@@ -97,6 +97,7 @@ struct InstrPlan {
     void *partial[kMaxArgs] = {nullptr, nullptr, nullptr, nullptr};
     void *second[kMaxArgs * (kMaxArgs + 1) / 2] = {nullptr};
     bool fused_into_prev = false;   // forward: this `sum`/`mean` was produced by the previous kernel
+    std::unique_ptr<ScalarBlock> blk;   // OP_SCALAR_BLOCK: planner output + device tables (scalar.cu)
     std::vector<int32_t> h_ops;     // host copy of the scalar program (NVRTC specialisation)
     void *jit_fn[2] = {nullptr, nullptr};   // [reduce]
     bool jit_tried[2] = {false, false};
@@ -387,6 +388,17 @@ static int forward_pass(rdb_tape *t, int order = 1) {
                 StepTimer tm(t, "getindex_forward", 2.0 * out.size * t->es + 8.0 * out.size, 0);
                 KL(t, launch_gather<T>(S(t), (T *)out.val, (const T *)src.val, I.in[0].d_map, out.size));
             } break;
+            case OP_SCALAR_BLOCK: {
+                // scalar_forward_exec! for the whole run (scalars.jl:80-123), level-parallel
+                ScalarBlock &B = *I.blk;
+                if (order != 1) return fail(RDB_EUNSUPPORTED, "second-order sweep over scalar instructions");
+                for (int k = 0; k < B.n_ref; ++k)
+                    if (B.ref_has_export[k]) bump_version(t, B.refbufs[k]);
+                StepTimer tm(t, "scalar_forward", (double)(B.n_leaf + 3 * B.n + B.n_edges) * t->es + 16.0 * B.n, 0);
+                int nl = 0;
+                KL(t, scalar_block_forward<T>(S(t), B, t->d_fconst, &nl));
+                t->launches += nl - 1;
+            } break;
             default:
                 return fail(RDB_EUNSUPPORTED, "opcode %d has no forward kernel", I.rec.opcode);
         }
@@ -619,10 +631,34 @@ static int expr_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
     return RDB_OK;
 }
 
+// scalar_reverse_exec! for a whole run of scalar instructions (scalars.jl:52-74), R seeds at once
+template <typename T>
+static int scalar_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
+    ScalarBlock &B = *I.blk;
+    bool reached = false;
+    for (int k = 0; k < B.n_ref; ++k)
+        if (B.ref_has_export[k] && !t->dz[droot(t, B.refbufs[k])]) reached = true;
+    if (!reached) return RDB_OK;                           // no adjoint reached any exported slot: every increment would add zero
+    for (int k = 0; k < B.n_ref; ++k)                      // the kernels touch single elements: the storage must hold real zeros
+        OK(dmaterialize(t, B.refbufs[k], R, true));
+    {
+        StepTimer tm(t, "scalar_reverse", (double)(B.n + B.n_edges + 2 * B.n_leaf) * R * t->es, 0);
+        int nl = 0;
+        KL(t, scalar_block_reverse<T>(S(t), B, R, &nl));
+        t->launches += nl - 1;
+    }
+    for (int k = 0; k < B.n_ref; ++k) {
+        if (B.ref_has_export[k] && !B.ref_has_leaf[k] && B.ref_export_count[k] == t->bufs[B.refbufs[k]].size) dclear(t, B.refbufs[k]);
+        if (B.ref_has_leaf[k]) OK(acc_done(t, B.refbufs[k]));
+    }
+    return RDB_OK;
+}
+
 template <typename T>
 static int reverse_pass(rdb_tape *t, int64_t R) {
     for (size_t k = t->instrs.size(); k-- > 0;) {
         InstrPlan &I = t->instrs[k];
+        if (I.rec.opcode == OP_SCALAR_BLOCK) { OK(scalar_reverse<T>(t, I, R)); continue; }
         Buf &out = t->bufs[I.rec.out];
         const T *delta = (const T *)out.der;
         if (t->dz[droot(t, I.rec.out)]) continue;        // no adjoint reached this output: every increment would add zero
@@ -711,6 +747,19 @@ static int ensure_batch(rdb_tape *t, int64_t R) {
     }
     for (auto &b : t->bufs)
         if (b.alias_of >= 0) b.der = t->bufs[b.alias_of].der;
+    for (auto &I : t->instrs) {
+        if (!I.blk) continue;
+        ScalarBlock &B = *I.blk;
+        if (scalar_block_ensure_R(B, R, t->es) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(RDB_ENOMEM, "scalar block: cannot allocate %lld x %lld adjoints", (long long)B.n, (long long)R);
+        }
+        for (int k = 0; k < B.n_ref; ++k) {
+            Buf &b = t->bufs[B.refbufs[k]];
+            B.h_ext_val[k] = b.val; B.h_ext_der[k] = b.der; B.h_ext_size[k] = b.size;
+        }
+        CU(scalar_block_upload_ext(B, S(t)));
+    }
     // column-reduction scratch grows with R
     int64_t need = t->scratch_bytes;
     for (auto &I : t->instrs)
@@ -741,6 +790,8 @@ static int64_t auto_seed_block(rdb_tape *t, int64_t rows, bool tangents) {
     int64_t per_seed = 0;
     for (auto &b : t->bufs)
         if (b.kind != BUF_CONST && b.alias_of < 0) per_seed += b.size * (int64_t)t->es * (tangents ? 2 : 1);
+    for (auto &I : t->instrs)
+        if (I.blk) per_seed += I.blk->n * (int64_t)t->es;
     int64_t budget = 24LL << 30;   // 24 GB of the 180 GB for seed-batched adjoints
     int64_t R = std::max<int64_t>(1, budget / std::max<int64_t>(per_seed, 1));
     R = std::min<int64_t>(R, 8192);
@@ -838,8 +889,9 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
                 break;
             case OP_NBCAST: case OP_MAP: case OP_BCAST: case OP_BCAST_ADD: case OP_BCAST_SUB: case OP_BCAST_MUL:
             case OP_BCAST_DIV: case OP_BCAST_LDIV: case OP_BCAST_POW: case OP_TRACKER_BCAST: break;
+            case OP_SCALAR_BLOCK: if (I.rec.n_in != 1) return fail(RDB_EINVAL, "instruction %u: scalar block carries one payload operand", i); break;
             default:
-                // @grad / ChainRules closures, det, inv, cat, tracker_∇broadcast, scalar instructions, ... cannot be lowered
+                // @grad / ChainRules closures, det, inv, cat, ... cannot be lowered
                 return fail(RDB_EUNSUPPORTED, "instruction %u: opcode %d cannot be replayed on the device (no CPU fallback)", i, op);
         }
         Buf &out = t->bufs[I.rec.out];
@@ -937,6 +989,16 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
             if (I.in[0].mode != OPM_PLAIN) return fail(RDB_EINVAL, "instruction %u: sum! on an index-mapped operand", i);
             for (int d = 0; d < kMaxDims; ++d)
                 if (out.dims[d] != src.dims[d] && out.dims[d] != 1) return fail(RDB_EINVAL, "instruction %u: sum! shape mismatch", i);
+        } else if (op == OP_SCALAR_BLOCK) {
+            const OperandRec &o = I.rec.in[0];
+            if (o.idx_kind != IDX_EXPLICIT || o.idx_offset < 0 || o.idx_len < 0 || (uint64_t)(o.idx_offset + o.idx_len) > h.n_idx)
+                return fail(RDB_EINVAL, "instruction %u: scalar block payload out of range", i);
+            std::vector<int64_t> sizes(h.n_buffers);
+            for (uint32_t b = 0; b < h.n_buffers; ++b) sizes[b] = t->bufs[b].kind == BUF_CONST ? -1 : t->bufs[b].size;
+            I.blk.reset(new ScalarBlock());
+            std::string err = scalar_block_build(*I.blk, idx + o.idx_offset, o.idx_len, expr, h.n_expr, h.n_fconst, sizes, t->es, S(t));
+            if (!err.empty())
+                return fail(err.find("whitelist") != std::string::npos ? RDB_EUNSUPPORTED : RDB_EINVAL, "instruction %u: %s", i, err.c_str());
         }
     }
     // reduction scratch: kReduceBlocks doubles for sums + column-reduction partials
@@ -1026,9 +1088,13 @@ static int gradient_impl(rdb_tape *t, void *const *result_ptrs, int on_device, v
         E.issued.assign(t->bufs.size(), 0);
         E.n_ev = 0;
         auto root = [&](int b) { while (t->bufs[b].alias_of >= 0) b = t->bufs[b].alias_of; return b; };
-        for (auto &I : t->instrs)
+        for (auto &I : t->instrs) {
             for (int a = 0; a < I.rec.n_in; ++a)
                 if (I.in[a].rec.tracked) E.remaining[root(I.in[a].rec.buffer)]++;
+            if (I.blk)
+                for (int k = 0; k < I.blk->n_ref; ++k)
+                    if (I.blk->ref_has_leaf[k]) E.remaining[root(I.blk->refbufs[k])]++;
+        }
         bool distinct = true;
         for (size_t i = 0; i < t->inputs.size(); ++i) {
             int r = root(t->inputs[i]);
@@ -1162,6 +1228,9 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
     if (cb < 0 || ce > n || cb > ce) return fail(RDB_EINVAL, "column range outside [0,n)");
     const int64_t cols = ce - cb;
     if (cols > 0 && ld < n) return fail(RDB_EINVAL, "leading dimension smaller than n");
+    for (auto &I : t->instrs)
+        if (I.blk) return fail(RDB_EUNSUPPORTED, "hessian!: the forward-over-reverse sweep does not cover scalar instructions; "
+                                                 "record the reference's reverse-over-reverse tape instead (HessianTape(..., mode=\"reverse\"))");
     OK(ensure_second_order(t));
     // this sweep keeps the reference's physical unseed!/increment pattern for the (size-n) first-order adjoints
     for (size_t b = 0; b < t->bufs.size(); ++b) OK(dmaterialize(t, (int)b, 1, false));
@@ -1481,6 +1550,7 @@ void rdb_tape_destroy(rdb_tape *t) {
     if (!t) return;
     if (t->ctx) cudaStreamSynchronize(t->ctx->stream);
     for (void *p : t->allocs) cudaFree(p);
+    for (auto &I : t->instrs) if (I.blk) scalar_block_free(*I.blk);
     if (t->ev0) cudaEventDestroy(t->ev0);
     if (t->ev1) cudaEventDestroy(t->ev1);
     if (t->gexec) cudaGraphExecDestroy(t->gexec);

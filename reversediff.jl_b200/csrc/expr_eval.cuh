@@ -1,0 +1,204 @@
+// Dual-number evaluation of the scalar-expression bytecode (program.h ExprOp): one ForwardDiff Dual{N} evaluation per call
+// (value + N partials; ORDER == 2 also the packed second partials).  Shared by the elementwise sweeps (kernels.cu) and the
+// scalar-instruction blocks (scalar.cu).  Compile the including file with -fmad=false (see kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "program.h"
+
+namespace rdb {
+
+template <typename T> struct M;
+template <> struct M<double> {
+    static __device__ __forceinline__ double tanh_(double x) { return tanh(x); }
+    static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+    static __device__ __forceinline__ double log_(double x) { return log(x); }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double sin_(double x) { return sin(x); }
+    static __device__ __forceinline__ double cos_(double x) { return cos(x); }
+    static __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
+    static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+};
+template <> struct M<float> {
+    static __device__ __forceinline__ float tanh_(float x) { return tanhf(x); }
+    static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+    static __device__ __forceinline__ float log_(float x) { return logf(x); }
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float sin_(float x) { return sinf(x); }
+    static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
+    static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
+    static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+};
+
+template <typename T>
+__device__ __forceinline__ T powi(T x, int n) {   // Base.literal_pow: repeated product
+    if (n == 0) return (T)1;
+    bool neg = n < 0;
+    if (neg) n = -n;
+    T r = x;
+    for (int i = 1; i < n; ++i) r = r * x;
+    return neg ? (T)1 / r : r;
+}
+
+template <int N> struct Tri { static constexpr int NH = N * (N + 1) / 2; };
+__device__ __forceinline__ int tri(int p, int q, int N) {   // p <= q packed index
+    return p * N - p * (p - 1) / 2 + (q - p);
+}
+
+template <typename T, int N, int ORDER>
+__device__ __forceinline__ void eval_expr(const int4 *__restrict__ ops, int n_ops, const double *__restrict__ fc,
+                                          const T *x, T &val, T *dout, T *hout, int r0 = N) {
+    constexpr int NH = Tri<N>::NH;
+    T V[kMaxExprRegs];
+    T D[kMaxExprRegs][N];
+    T H[ORDER == 2 ? kMaxExprRegs : 1][NH];
+#pragma unroll
+    for (int p = 0; p < N; ++p) {
+        V[p] = x[p];
+#pragma unroll
+        for (int q = 0; q < N; ++q) D[p][q] = (p == q) ? (T)1 : (T)0;
+        if (ORDER == 2) {
+#pragma unroll
+            for (int h = 0; h < NH; ++h) H[p][h] = (T)0;
+        }
+    }
+    int r = r0;     // op j writes register r0 + j: r0 = the expression's own argument count (<= N)
+    for (int o = 0; o < n_ops; ++o, ++r) {
+        const int4 op = ops[o];
+        const int code = op.x, a = op.y, b = op.z, imm = op.w;
+        T f0, f1 = (T)0, f2 = (T)0;
+        bool unary = true;
+        switch (code) {
+            case E_CONST: {
+                V[r] = (T)fc[imm];
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = (T)0;
+                if (ORDER == 2) {
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) H[r][h] = (T)0;
+                }
+                unary = false;
+            } break;
+            case E_ARG: {
+                V[r] = V[imm];
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = D[imm][p];
+                if (ORDER == 2) {
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) H[r][h] = H[imm][h];
+                }
+                unary = false;
+            } break;
+            case E_ADD:
+            case E_SUB: {
+                const T s = code == E_ADD ? (T)1 : (T)-1;
+                V[r] = code == E_ADD ? V[a] + V[b] : V[a] - V[b];
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = D[a][p] + s * D[b][p];
+                if (ORDER == 2) {
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) H[r][h] = H[a][h] + s * H[b][h];
+                }
+                unary = false;
+            } break;
+            case E_MUL: {
+                const T va = V[a], vb = V[b];
+                V[r] = va * vb;
+                if (ORDER == 2) {
+#pragma unroll
+                    for (int p = 0; p < N; ++p)
+#pragma unroll
+                        for (int q = p; q < N; ++q)
+                            H[r][tri(p, q, N)] = H[a][tri(p, q, N)] * vb + D[a][p] * D[b][q] + D[a][q] * D[b][p] +
+                                                 va * H[b][tri(p, q, N)];
+                }
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = D[a][p] * vb + va * D[b][p];
+                unary = false;
+            } break;
+            case E_DIV: {
+                const T q0 = V[a] / V[b], ib = (T)1 / V[b];
+                T da[N];
+#pragma unroll
+                for (int p = 0; p < N; ++p) da[p] = (D[a][p] - q0 * D[b][p]) * ib;
+                if (ORDER == 2) {
+#pragma unroll
+                    for (int p = 0; p < N; ++p)
+#pragma unroll
+                        for (int q = p; q < N; ++q)
+                            H[r][tri(p, q, N)] = (H[a][tri(p, q, N)] - da[p] * D[b][q] - da[q] * D[b][p] -
+                                                  q0 * H[b][tri(p, q, N)]) * ib;
+                }
+                V[r] = q0;
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = da[p];
+                unary = false;
+            } break;
+            case E_POW: {
+                const T y = M<T>::pow_(V[a], V[b]);
+                const T fa = V[b] * M<T>::pow_(V[a], V[b] - (T)1);
+                const T fb = y * M<T>::log_(V[a]);
+                V[r] = y;
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = fa * D[a][p] + fb * D[b][p];
+                if (ORDER == 2) {   // second-order pow is rejected at load time
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) H[r][h] = (T)0;
+                }
+                unary = false;
+            } break;
+            case E_MAX:
+            case E_MIN: {
+                const bool pick_a = code == E_MAX ? (V[a] > V[b]) : (V[a] < V[b]);
+                const int s = pick_a ? a : b;
+                V[r] = V[s];
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = D[s][p];
+                if (ORDER == 2) {
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) H[r][h] = H[s][h];
+                }
+                unary = false;
+            } break;
+            case E_NEG: f0 = -V[a]; f1 = (T)-1; f2 = (T)0; break;
+            case E_POWI: {
+                const T xx = V[a];
+                f0 = powi(xx, imm);
+                f1 = imm != 0 ? (T)imm * powi(xx, imm - 1) : (T)0;
+                if (ORDER == 2) f2 = (imm != 0 && imm != 1) ? (T)(imm * (imm - 1)) * powi(xx, imm - 2) : (T)0;
+            } break;
+            case E_TANH: { const T t = M<T>::tanh_(V[a]); f0 = t; f1 = (T)1 - t * t; f2 = (T)-2 * t * f1; } break;
+            case E_EXP: { const T e = M<T>::exp_(V[a]); f0 = e; f1 = e; f2 = e; } break;
+            case E_LOG: { f0 = M<T>::log_(V[a]); f1 = (T)1 / V[a]; f2 = (T)-1 / (V[a] * V[a]); } break;
+            case E_SQRT: { const T s = M<T>::sqrt_(V[a]); f0 = s; f1 = (T)1 / ((T)2 * s); f2 = (T)-1 / ((T)4 * s * V[a]); } break;
+            case E_SIN: { f0 = M<T>::sin_(V[a]); f1 = M<T>::cos_(V[a]); f2 = -f0; } break;
+            case E_COS: { f0 = M<T>::cos_(V[a]); f1 = -M<T>::sin_(V[a]); f2 = -f0; } break;
+            case E_ABS2: { f0 = V[a] * V[a]; f1 = (T)2 * V[a]; f2 = (T)2; } break;
+            case E_ABS: { f0 = M<T>::abs_(V[a]); f1 = V[a] > (T)0 ? (T)1 : (V[a] < (T)0 ? (T)-1 : (T)0); f2 = (T)0; } break;
+            case E_INV: { const T rr = (T)1 / V[a]; f0 = rr; f1 = -rr * rr; f2 = (T)2 * rr * rr * rr; } break;
+            case E_SIGMOID: { const T s = (T)1 / ((T)1 + M<T>::exp_(-V[a])); f0 = s; f1 = s * ((T)1 - s); f2 = f1 * ((T)1 - (T)2 * s); } break;
+            default: f0 = (T)0; break;
+        }
+        if (unary) {
+            if (ORDER == 2) {
+#pragma unroll
+                for (int p = 0; p < N; ++p)
+#pragma unroll
+                    for (int q = p; q < N; ++q)
+                        H[r][tri(p, q, N)] = f2 * D[a][p] * D[a][q] + f1 * H[a][tri(p, q, N)];
+            }
+            V[r] = f0;
+#pragma unroll
+            for (int p = 0; p < N; ++p) D[r][p] = f1 * D[a][p];
+        }
+    }
+    val = V[r - 1];
+#pragma unroll
+    for (int p = 0; p < N; ++p) dout[p] = D[r - 1][p];
+    if (ORDER == 2) {
+#pragma unroll
+        for (int h = 0; h < NH; ++h) hout[h] = H[r - 1][h];
+    }
+}
+
+}  // namespace rdb

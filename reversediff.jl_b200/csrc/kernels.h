@@ -118,3 +118,55 @@ template <typename T> cudaError_t launch_colsum(cudaStream_t, T *out, const T *x
 template <typename T> cudaError_t launch_copy2d(cudaStream_t, T *dst, int64_t ldd, const T *src, int64_t lds, int64_t n, int64_t K);
 
 }  // namespace rdb
+
+// ---- scalar-instruction blocks (scalar.cu) ------------------------------------------------------------
+// A maximal run of consecutive ScalarInstructions (tape.jl:30-45; derivatives/scalars.jl:52-123) replayed as one unit.
+// Host planner + device tables; wire layout in program.py (ScalarBlock).
+#include <string>
+#include <vector>
+namespace rdb {
+
+struct ScalarSeg { int lv0, lv1, grid; };     // a launch: levels [lv0, lv1) — one wide level on many CTAs, or a run of narrow levels on ONE CTA
+
+struct ScalarBlock {
+    int64_t n = 0, n_leaf = 0, n_edges = 0, n_exports = 0, n_rslots = 0;
+    int n_ref = 0, n_flevels = 0, n_rlevels = 0;
+    std::vector<int32_t> refbufs;               // tape buffer ids referenced (leaf origins and export targets)
+    std::vector<char> ref_has_leaf, ref_has_export;
+    std::vector<int64_t> ref_export_count;      // elements of the buffer this block exports into
+    std::vector<ScalarSeg> fsegs, rsegs;        // forward / single-seed reverse launch plans
+    std::vector<void *> h_ext_val, h_ext_der;   // per ref: base pointers of value(buffer) / deriv(buffer) (engine-owned)
+    std::vector<int64_t> h_ext_size;
+    int64_t R_alloc = 0;
+    // device tables (owned; freed by scalar_block_free)
+    void *d_tables = nullptr;                   // one allocation holding everything below except the pools
+    int4 *d_finstr = nullptr;                   // level-sorted: (instr, a_code, b_code, expr)   a/b: >= 0 slot, < -1 literal, INT_MIN none
+    int64_t *d_flevel_off = nullptr;
+    int4 *d_ops = nullptr;                      // concatenated bytecode of the block's scalar functions
+    int4 *d_exprs = nullptr;                    // (offset, n_ops, n_args, 0)
+    int32_t *d_epos = nullptr;                  // 2n: where forward stores partial (i, a|b) in the reverse edge array, or -1
+    int32_t *d_leaf_ord = nullptr; int64_t *d_leaf_elem = nullptr;
+    int32_t *d_exp_slot = nullptr, *d_exp_ord = nullptr; int64_t *d_exp_elem = nullptr;
+    int32_t *d_rslot = nullptr;                 // reverse-level-sorted slots: >= 0 instruction output, < 0 leaf ~l
+    int64_t *d_reoff = nullptr;                 // n_rslots + 1 edge offsets
+    int32_t *d_esrc = nullptr;                  // consumer instruction of every edge, reference accumulation order
+    int64_t *d_rlevel_off = nullptr;
+    int64_t *d_xoff = nullptr; int32_t *d_xord = nullptr; int64_t *d_xelem = nullptr;   // exports of instruction i (CSR over i)
+    void **d_ext_val = nullptr, **d_ext_der = nullptr; int64_t *d_ext_size = nullptr;
+    void *d_val = nullptr;                      // T[n_leaf + n] slot values
+    void *d_epart = nullptr;                    // T[n_edges] partials in reverse edge order
+    void *d_der = nullptr;                      // T[n * R] adjoints of instruction outputs, [i*R + r]
+};
+
+// Parse + validate + plan.  buf_size[b] < 0 marks a buffer that cannot be referenced (CONST).  Returns "" or an error text.
+std::string scalar_block_build(ScalarBlock &B, const int64_t *payload, int64_t len, const int32_t *expr, uint64_t n_expr,
+                               uint64_t n_fconst, const std::vector<int64_t> &buf_size, size_t es, cudaStream_t s);
+void scalar_block_free(ScalarBlock &B);
+cudaError_t scalar_block_upload_ext(ScalarBlock &B, cudaStream_t s);
+cudaError_t scalar_block_ensure_R(ScalarBlock &B, int64_t R, size_t es);
+// forward: pull leaf values, evaluate level by level, mirror exports; returns the number of kernel launches in *launches
+template <typename T> cudaError_t scalar_block_forward(cudaStream_t, ScalarBlock &B, const double *fconst, int *launches);
+// reverse for R seeds (deriv layout of tape buffers: [elem + r*size])
+template <typename T> cudaError_t scalar_block_reverse(cudaStream_t, ScalarBlock &B, int64_t R, int *launches);
+
+}  // namespace rdb

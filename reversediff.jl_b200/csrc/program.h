@@ -19,6 +19,7 @@ enum Opcode : int32_t {
     OP_MUL = 1, OP_ADD = 2, OP_SUB = 3, OP_NEG = 4, OP_SUM = 5, OP_MEAN = 6, OP_NBCAST = 7, OP_MAP = 8,
     OP_BCAST = 9, OP_BCAST_ADD = 10, OP_BCAST_SUB = 11, OP_BCAST_MUL = 12, OP_BCAST_DIV = 13, OP_BCAST_LDIV = 14, OP_BCAST_POW = 15,
     OP_GETINDEX = 16, OP_DOT = 17, OP_SUMDIMS = 18, OP_TRACKER_BCAST = 19, OP_GETINDEX_GENERIC = 20,
+    OP_SCALAR_BLOCK = 21,   // a run of ScalarInstructions; payload layout in program.py (ScalarBlock)
 };
 
 enum ExprOp : int32_t {

@@ -1,0 +1,462 @@
+// Scalar-instruction blocks: a maximal run of consecutive ScalarInstructions (reference src/tape.jl:30-45) replayed as one unit.
+//
+// Reference semantics (src/derivatives/scalars.jl):
+//   forward  :80-123  per instruction, in tape order: pull_value!(inputs); ONE ForwardDiff.derivative!/gradient! evaluation of the
+//                     scalar function; value!(output); cache[] = partial(s)
+//   reverse  :52-74   per instruction, in REVERSE tape order: increment_deriv!(a, deriv(output)*a_partial) [then b]; unseed!(output)
+// A TrackedReal obtained by scalar getindex carries no instruction: its value/deriv are pulled from / pushed to origin[index]
+// (src/tracked.jl:178-197,348-351).
+//
+// B200 mapping.  The CPU runs these loops one instruction at a time; a tape of 1e5-1e6 scalar instructions has no other
+// parallelism for ONE seed than its dataflow, and R independent seeds for jacobian!/hessian!.  So the planner (host, at load)
+//   * levelises the forward dataflow: instructions of one level are evaluated in parallel (values do not depend on the order);
+//   * turns the reverse loop into its PULL form: the adjoint of slot s is  init(s) + sum over the instructions c that consume s,
+//     in DESCENDING tape order (operand a before b), of deriv(out_c)*partial_c — exactly the sequence of increments the
+//     reference applies to s.deriv, so every sum is built in the reference's order, but each adjoint is written ONCE, by one
+//     thread, with no read-modify-write, no atomics and no unseed! traffic (a slot is final before anyone reads it);
+//   * levelises that pull graph too.  With R >= 16 seeds a warp's lanes are 32 seeds (adjoints laid out [slot][seed]: every
+//     load/store is one coalesced 256-byte line), a CTA's warps take the slots of a level, and a CTA only ever needs
+//     __syncthreads between levels because seeds never interact.  Algorithmic traffic per (instruction, seed): one 8-byte
+//     write + one 8-byte read per operand edge (~24 B for a binary instruction) against 48 B for the push form.
+//   * partials are stored by the forward sweep directly in reverse-edge order, so the reverse sweep streams them.
+// Compiled with -fmad=false (parity of deriv*partial + accumulate with the uncontracted CPU arithmetic).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <climits>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include "kernels.h"
+#include "expr_eval.cuh"
+
+namespace rdb {
+
+namespace {
+constexpr int kFwdThreads = 512;
+constexpr int kWideLevel = 8192;      // a level at least this wide gets a grid of its own
+constexpr int kNone = INT_MIN;
+
+struct FwdP {
+    const int4 *finstr; const int64_t *level_off; const int4 *ops; const int4 *exprs; const int32_t *epos;
+    const double *fconst; void *val; void *epart; int64_t n_leaf; int lv0, lv1;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kFwdThreads) k_scalar_forward(const FwdP P) {
+    T *val = reinterpret_cast<T *>(P.val);
+    T *epart = reinterpret_cast<T *>(P.epart);
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    for (int lv = P.lv0; lv < P.lv1; ++lv) {
+        const int64_t j0 = P.level_off[lv], j1 = P.level_off[lv + 1];
+        for (int64_t j = j0 + tid; j < j1; j += nt) {
+            const int4 I = P.finstr[j];
+            const int4 E = P.exprs[I.w];
+            T x[2];
+            x[0] = I.y >= 0 ? val[I.y] : (I.y == kNone ? (T)0 : (T)P.fconst[-2 - I.y]);     // pull_value!(a)
+            x[1] = I.z >= 0 ? val[I.z] : (I.z == kNone ? (T)0 : (T)P.fconst[-2 - I.z]);     // pull_value!(b)
+            T v, d[2], h[1];
+            eval_expr<T, 2, 1>(P.ops + E.x, E.y, P.fconst, x, v, d, h, E.z);
+            val[P.n_leaf + I.x] = v;                                                        // value!(output, ...)
+            const int ea = P.epos[2 * (int64_t)I.x], eb = P.epos[2 * (int64_t)I.x + 1];
+            if (ea >= 0) epart[ea] = d[0];                                                  // cache[] = partials
+            if (eb >= 0) epart[eb] = d[1];
+        }
+        if (lv + 1 < P.lv1) __syncthreads();      // multi-level launches run on ONE CTA
+    }
+}
+
+template <typename T>
+__global__ void k_scalar_pull(T *val, const int32_t *leaf_ord, const int64_t *leaf_elem, void *const *ext_val, int64_t n_leaf) {
+    int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (l < n_leaf) val[l] = reinterpret_cast<const T *>(ext_val[leaf_ord[l]])[leaf_elem[l]];
+}
+template <typename T>
+__global__ void k_scalar_export(const T *val, const int32_t *slot, const int32_t *ord, const int64_t *elem, void *const *ext_val,
+                                int64_t n_leaf, int64_t n_exp) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n_exp) reinterpret_cast<T *>(ext_val[ord[k]])[elem[k]] = val[n_leaf + slot[k]];
+}
+
+struct RevP {
+    const int32_t *rslot; const int64_t *reoff; const int32_t *esrc; const void *epart; const int64_t *rlevel_off;
+    const int64_t *xoff; const int32_t *xord; const int64_t *xelem;
+    const int32_t *leaf_ord; const int64_t *leaf_elem;
+    void *const *ext_der; const int64_t *ext_size;
+    void *der; int64_t R; int lv0, lv1;
+};
+
+// R >= 16: lanes are seeds.  grid.x = ceil(R/32); a CTA owns 32 seeds and walks every level.
+template <typename T>
+__global__ void __launch_bounds__(256) k_scalar_reverse_seeds(const RevP P) {
+    T *der = reinterpret_cast<T *>(P.der);
+    const T *epart = reinterpret_cast<const T *>(P.epart);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int64_t R = P.R, r = blockIdx.x * 32LL + lane;
+    const bool active = r < R;
+    for (int lv = P.lv0; lv < P.lv1; ++lv) {
+        const int64_t j0 = P.rlevel_off[lv], j1 = P.rlevel_off[lv + 1];
+        for (int64_t j = j0 + warp; j < j1; j += W) {
+            const int s = P.rslot[j];
+            const int64_t e0 = P.reoff[j], e1 = P.reoff[j + 1];
+            T acc = (T)0;
+            T *dst;
+            if (s >= 0) {
+                // adjoints that instructions AFTER the block pushed into an exported slot (one TrackedReal, one deriv field)
+                for (int64_t x = P.xoff[s]; x < P.xoff[s + 1]; ++x) {
+                    const int o = P.xord[x];
+                    T *p = reinterpret_cast<T *>(P.ext_der[o]) + P.xelem[x] + r * P.ext_size[o];
+                    if (active) { acc = acc + *p; *p = (T)0; }                             // ... and unseed!(output)
+                }
+                dst = der + (int64_t)s * R + r;
+            } else {
+                const int l = ~s, o = P.leaf_ord[l];
+                dst = reinterpret_cast<T *>(P.ext_der[o]) + P.leaf_elem[l] + r * P.ext_size[o];   // origin.deriv[index]: pull_deriv!
+                if (active) acc = *dst;
+            }
+            for (int64_t e = e0; e < e1; e += 32) {
+                const int cnt = (int)min((int64_t)32, e1 - e);
+                const int src_l = lane < cnt ? P.esrc[e + lane] : 0;
+                const T part_l = lane < cnt ? epart[e + lane] : (T)0;
+#pragma unroll 4
+                for (int k = 0; k < cnt; ++k) {
+                    const int c = __shfl_sync(0xffffffffu, src_l, k);
+                    const T p = __shfl_sync(0xffffffffu, part_l, k);
+                    if (active) acc = acc + der[(int64_t)c * R + r] * p;                    // increment_deriv!(s, deriv(out_c) * partial)
+                }
+            }
+            if (active) *dst = acc;                                                         // push_deriv! / the slot's final adjoint
+        }
+        if (lv + 1 < P.lv1) __syncthreads();
+    }
+}
+
+// R < 16 (gradient!: R = 1): threads are slots of a level; multi-level launches run on ONE CTA.
+template <typename T>
+__global__ void __launch_bounds__(kFwdThreads) k_scalar_reverse_slots(const RevP P) {
+    T *der = reinterpret_cast<T *>(P.der);
+    const T *epart = reinterpret_cast<const T *>(P.epart);
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    const int64_t R = P.R;
+    for (int lv = P.lv0; lv < P.lv1; ++lv) {
+        const int64_t j0 = P.rlevel_off[lv], j1 = P.rlevel_off[lv + 1];
+        for (int64_t j = j0 + tid; j < j1; j += nt) {
+            const int s = P.rslot[j];
+            const int64_t e0 = P.reoff[j], e1 = P.reoff[j + 1];
+            for (int64_t r = 0; r < R; ++r) {
+                T acc = (T)0;
+                T *dst;
+                if (s >= 0) {
+                    for (int64_t x = P.xoff[s]; x < P.xoff[s + 1]; ++x) {
+                        const int o = P.xord[x];
+                        T *p = reinterpret_cast<T *>(P.ext_der[o]) + P.xelem[x] + r * P.ext_size[o];
+                        acc = acc + *p; *p = (T)0;
+                    }
+                    dst = der + (int64_t)s * R + r;
+                } else {
+                    const int l = ~s, o = P.leaf_ord[l];
+                    dst = reinterpret_cast<T *>(P.ext_der[o]) + P.leaf_elem[l] + r * P.ext_size[o];
+                    acc = *dst;
+                }
+                for (int64_t e = e0; e < e1; ++e) acc = acc + der[(int64_t)P.esrc[e] * R + r] * epart[e];
+                *dst = acc;
+            }
+        }
+        if (lv + 1 < P.lv1) __syncthreads();
+    }
+}
+
+// levels -> launches: a wide level alone on a full grid, runs of narrow levels on one CTA (block-level barrier between levels)
+std::vector<ScalarSeg> plan_segments(const std::vector<int64_t> &off) {
+    std::vector<ScalarSeg> segs;
+    const int nl = (int)off.size() - 1;
+    int lv = 0;
+    while (lv < nl) {
+        const int64_t w = off[lv + 1] - off[lv];
+        if (w >= kWideLevel) {
+            int grid = (int)std::min<int64_t>((w + kFwdThreads - 1) / kFwdThreads, 148 * 4);
+            segs.push_back({lv, lv + 1, grid});
+            ++lv;
+        } else {
+            int e = lv;
+            while (e < nl && off[e + 1] - off[e] < kWideLevel) ++e;
+            segs.push_back({lv, e, 1});
+            lv = e;
+        }
+    }
+    return segs;
+}
+
+template <typename U>
+U *carve(uint8_t *&p, size_t count) {
+    U *r = reinterpret_cast<U *>(p);
+    p += (count * sizeof(U) + 15) & ~size_t(15);
+    return r;
+}
+}  // namespace
+
+std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, const int32_t *expr, uint64_t n_expr, uint64_t n_fconst,
+                               const std::vector<int64_t> &buf_size, size_t es, cudaStream_t s) {
+    if (len < 4) return "scalar block: payload too short";
+    const int64_t n = w[0], nref = w[1], nexp = w[2], nex = w[3];
+    if (n < 0 || nref < 0 || nexp < 0 || nex < 0 || n > INT_MAX / 4 || nref > 1 << 20) return "scalar block: bad header";
+    if (4 + nref + 3 * nex + 3 * nexp + 5 * n != len) return "scalar block: payload length mismatch";
+    const int64_t *refs = w + 4, *etab = refs + nref, *xtab = etab + 3 * nex, *body = xtab + 3 * nexp;
+    B.n = n; B.n_ref = (int)nref; B.n_exports = nexp;
+    B.refbufs.resize(nref); B.ref_has_leaf.assign(nref, 0); B.ref_has_export.assign(nref, 0); B.ref_export_count.assign(nref, 0);
+    for (int64_t k = 0; k < nref; ++k) {
+        if (refs[k] < 0 || (size_t)refs[k] >= buf_size.size() || buf_size[refs[k]] < 0) return "scalar block: bad referenced buffer";
+        B.refbufs[k] = (int32_t)refs[k];
+    }
+    // scalar functions --------------------------------------------------------------------------------------------------
+    std::vector<int4> h_ops, h_exprs(nex);
+    for (int64_t k = 0; k < nex; ++k) {
+        const int64_t eo = etab[3 * k], el = etab[3 * k + 1], na = etab[3 * k + 2];
+        if (eo < 0 || el < 1 || na < 0 || na > 2 || (uint64_t)(eo + 4 * el) > n_expr) return "scalar block: bad scalar function";
+        if (na + el > kMaxExprRegs) return "scalar block: scalar function too large";
+        h_exprs[k] = make_int4((int)h_ops.size(), (int)el, (int)na, 0);
+        for (int64_t o = 0; o < el; ++o) {
+            const int32_t *q = expr + eo + 4 * o;
+            const int code = q[0], ra = q[1], rb = q[2], imm = q[3], reg = (int)(na + o);
+            if (code < E_CONST || code > E_ARG) return "scalar block: scalar function is not on the whitelist";
+            if (code == E_CONST) { if (imm < 0 || (uint64_t)imm >= n_fconst) return "scalar block: bad literal"; }
+            else if (code == E_ARG) { if (imm < 0 || imm >= na) return "scalar block: bad arg ref"; }
+            else {
+                if (ra < 0 || ra >= reg) return "scalar block: bad SSA ref";
+                const bool binary = code == E_ADD || code == E_SUB || code == E_MUL || code == E_DIV || code == E_POW || code == E_MAX || code == E_MIN;
+                if (binary && (rb < 0 || rb >= reg)) return "scalar block: bad SSA ref";
+            }
+            h_ops.push_back(make_int4(code, ra, rb, imm));
+        }
+    }
+    // operands: leaves (unique (buffer, element) pairs = one TrackedReal-with-origin each), literals, pool slots ---------------
+    std::map<std::pair<int, int64_t>, int> leaf_id;
+    std::vector<int32_t> leaf_ord; std::vector<int64_t> leaf_elem;
+    std::vector<int> code_a(n), code_b(n);        // >= 0: pool slot i; <= -2-...: see below; kNone
+    std::vector<int> kind_a(n), kind_b(n);        // 0 none, 1 pool, 2 leaf, 3 literal
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t *I = body + 5 * i;
+        if (I[0] < 0 || I[0] >= nex) return "scalar block: bad scalar-function id";
+        int nargs = 0;
+        for (int k = 0; k < 2; ++k) {
+            const int64_t sp = I[1 + 2 * k], ix = I[2 + 2 * k];
+            int kind, code;
+            if (sp == -3) { kind = 0; code = kNone; }
+            else if (sp == -1) { if (ix < 0 || ix >= i) return "scalar block: operand refers to a later instruction"; kind = 1; code = (int)ix; ++nargs; }
+            else if (sp == -2) { if (ix < 0 || (uint64_t)ix >= n_fconst) return "scalar block: bad literal operand"; kind = 3; code = (int)ix; ++nargs; }
+            else if (sp >= 0 && sp < nref) {
+                if (ix < 0 || ix >= buf_size[B.refbufs[sp]]) return "scalar block: operand element out of bounds";
+                auto key = std::make_pair((int)sp, ix);
+                auto it = leaf_id.find(key);
+                if (it == leaf_id.end()) {
+                    it = leaf_id.emplace(key, (int)leaf_ord.size()).first;
+                    leaf_ord.push_back((int32_t)sp); leaf_elem.push_back(ix);
+                    B.ref_has_leaf[sp] = 1;
+                }
+                kind = 2; code = it->second; ++nargs;
+            } else return "scalar block: bad operand space";
+            (k == 0 ? kind_a : kind_b)[i] = kind;
+            (k == 0 ? code_a : code_b)[i] = code;
+        }
+        if (kind_a[i] == 0 && kind_b[i] != 0) return "scalar block: second operand without a first";
+        if (nargs != h_exprs[I[0]].z) return "scalar block: operand count does not match the scalar function";
+    }
+    const int64_t nl = (int64_t)leaf_ord.size();
+    B.n_leaf = nl;
+    if (nl + n > INT_MAX / 2) return "scalar block: too many slots";
+    // exports ------------------------------------------------------------------------------------------------------------
+    std::vector<int64_t> xoff(n + 1, 0);
+    for (int64_t k = 0; k < nexp; ++k) {
+        const int64_t sl = xtab[3 * k], ro = xtab[3 * k + 1], el = xtab[3 * k + 2];
+        if (sl < 0 || sl >= n || ro < 0 || ro >= nref || el < 0 || el >= buf_size[B.refbufs[ro]]) return "scalar block: bad export";
+        if (leaf_id.count(std::make_pair((int)ro, el))) return "scalar block: export target is also read as an operand";
+        xoff[sl + 1]++;
+        B.ref_has_export[ro] = 1; B.ref_export_count[ro]++;
+    }
+    for (int64_t i = 0; i < n; ++i) xoff[i + 1] += xoff[i];
+    std::vector<int32_t> xord(nexp), exp_slot(nexp), exp_ord(nexp); std::vector<int64_t> xelem(nexp), exp_elem(nexp);
+    {
+        std::vector<int64_t> fill(xoff.begin(), xoff.end() - 1);
+        for (int64_t k = 0; k < nexp; ++k) {
+            const int64_t sl = xtab[3 * k], at = fill[sl]++;
+            xord[at] = (int32_t)xtab[3 * k + 1]; xelem[at] = xtab[3 * k + 2];
+            exp_slot[k] = (int32_t)sl; exp_ord[k] = (int32_t)xtab[3 * k + 1]; exp_elem[k] = xtab[3 * k + 2];
+        }
+    }
+    // forward levels --------------------------------------------------------------------------------------------------------
+    std::vector<int> lf(n);
+    int nfl = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        int l = 0;
+        if (kind_a[i] == 1) l = std::max(l, lf[code_a[i]] + 1);
+        if (kind_b[i] == 1) l = std::max(l, lf[code_b[i]] + 1);
+        lf[i] = l; nfl = std::max(nfl, l + 1);
+    }
+    std::vector<int64_t> flevel_off(nfl + 1, 0);
+    for (int64_t i = 0; i < n; ++i) flevel_off[lf[i] + 1]++;
+    for (int l = 0; l < nfl; ++l) flevel_off[l + 1] += flevel_off[l];
+    // reverse (pull) graph: slot ids  [0, n) instruction outputs, [n, n + nl) leaves ---------------------------------------------
+    const int64_t ns = n + nl;
+    std::vector<int> lr(ns, 0);
+    std::vector<int64_t> ecount(ns, 0);
+    auto slot_of = [&](int kind, int code) -> int64_t { return kind == 1 ? code : (kind == 2 ? n + code : -1); };
+    for (int64_t i = n - 1; i >= 0; --i) {
+        for (int k = 0; k < 2; ++k) {
+            const int64_t sl = slot_of(k == 0 ? kind_a[i] : kind_b[i], k == 0 ? code_a[i] : code_b[i]);
+            if (sl < 0) continue;
+            lr[sl] = std::max(lr[sl], lr[i] + 1);
+            ecount[sl]++;
+        }
+    }
+    int nrl = 0;
+    for (int64_t sl = 0; sl < ns; ++sl) nrl = std::max(nrl, lr[sl] + 1);
+    std::vector<int64_t> rlevel_off(nrl + 1, 0);
+    for (int64_t sl = 0; sl < ns; ++sl) rlevel_off[lr[sl] + 1]++;
+    for (int l = 0; l < nrl; ++l) rlevel_off[l + 1] += rlevel_off[l];
+    std::vector<int32_t> rslot(ns);
+    std::vector<int64_t> rpos(ns);
+    {
+        std::vector<int64_t> fill(rlevel_off.begin(), rlevel_off.end() - 1);
+        for (int64_t sl = 0; sl < ns; ++sl) {
+            const int64_t at = fill[lr[sl]]++;
+            rpos[sl] = at;
+            rslot[at] = sl < n ? (int32_t)sl : ~(int32_t)(sl - n);
+        }
+    }
+    std::vector<int64_t> reoff(ns + 1, 0);
+    for (int64_t sl = 0; sl < ns; ++sl) reoff[rpos[sl] + 1] = ecount[sl];
+    for (int64_t j = 0; j < ns; ++j) reoff[j + 1] += reoff[j];
+    const int64_t ne = reoff[ns];
+    if (ne > INT_MAX) return "scalar block: too many operand edges";
+    B.n_edges = ne; B.n_rslots = ns;
+    std::vector<int32_t> esrc(ne), epos(2 * n, -1);
+    {
+        std::vector<int64_t> fill(ns);
+        for (int64_t sl = 0; sl < ns; ++sl) fill[sl] = reoff[rpos[sl]];
+        for (int64_t i = n - 1; i >= 0; --i) {         // reverse tape order, a before b: the order of the reference's increments
+            for (int k = 0; k < 2; ++k) {
+                const int64_t sl = slot_of(k == 0 ? kind_a[i] : kind_b[i], k == 0 ? code_a[i] : code_b[i]);
+                if (sl < 0) continue;
+                const int64_t at = fill[sl]++;
+                esrc[at] = (int32_t)i;
+                epos[2 * i + k] = (int32_t)at;
+            }
+        }
+    }
+    // forward instruction table, level-sorted ------------------------------------------------------------------------------------
+    std::vector<int4> finstr(n);
+    {
+        std::vector<int64_t> fill(flevel_off.begin(), flevel_off.end() - 1);
+        auto enc = [&](int kind, int code) -> int {
+            if (kind == 0) return kNone;
+            if (kind == 1) return (int)(nl + code);     // value slots: leaves first, then instruction outputs
+            if (kind == 2) return code;
+            return -2 - code;                           // literal: fconst[code]
+        };
+        for (int64_t i = 0; i < n; ++i)
+            finstr[fill[lf[i]]++] = make_int4((int)i, enc(kind_a[i], code_a[i]), enc(kind_b[i], code_b[i]), (int)body[5 * i]);
+    }
+    B.n_flevels = nfl; B.n_rlevels = nrl;
+    B.fsegs = plan_segments(flevel_off);
+    B.rsegs = plan_segments(rlevel_off);
+    // device tables: one allocation ------------------------------------------------------------------------------------------------
+    auto pad = [](size_t b) { return (b + 15) & ~size_t(15); };
+    size_t bytes = pad(n * 16) + pad((nfl + 1) * 8) + pad(h_ops.size() * 16) + pad(nex * 16) + pad(2 * n * 4) + pad(nl * 4) + pad(nl * 8) +
+                   pad(nexp * 4) * 2 + pad(nexp * 8) + pad(ns * 4) + pad((ns + 1) * 8) + pad(ne * 4) + pad((nrl + 1) * 8) + pad((n + 1) * 8) +
+                   pad(nexp * 4) + pad(nexp * 8) + pad(nref * 8) * 3 + 256;
+    std::vector<uint8_t> host(bytes, 0);
+    if (cudaMalloc(&B.d_tables, bytes) != cudaSuccess) { cudaGetLastError(); return "scalar block: out of device memory (tables)"; }
+    uint8_t *hp = host.data();
+    auto put = [&](auto *&dptr, const auto &vec) {
+        using U = typename std::remove_reference<decltype(vec[0])>::type;
+        using V = typename std::remove_const<U>::type;
+        uint8_t *before = hp;
+        V *dst = carve<V>(hp, vec.size());
+        if (!vec.empty()) memcpy(dst, vec.data(), vec.size() * sizeof(V));
+        dptr = reinterpret_cast<typename std::remove_reference<decltype(dptr)>::type>((uint8_t *)B.d_tables + (before - host.data()));
+    };
+    put(B.d_finstr, finstr); put(B.d_flevel_off, flevel_off); put(B.d_ops, h_ops); put(B.d_exprs, h_exprs); put(B.d_epos, epos);
+    put(B.d_leaf_ord, leaf_ord); put(B.d_leaf_elem, leaf_elem);
+    put(B.d_exp_slot, exp_slot); put(B.d_exp_ord, exp_ord); put(B.d_exp_elem, exp_elem);
+    put(B.d_rslot, rslot); put(B.d_reoff, reoff); put(B.d_esrc, esrc); put(B.d_rlevel_off, rlevel_off);
+    put(B.d_xoff, xoff); put(B.d_xord, xord); put(B.d_xelem, xelem);
+    std::vector<void *> nulls(nref, nullptr); std::vector<int64_t> zeros(nref, 0);
+    put(B.d_ext_val, nulls); put(B.d_ext_der, nulls); put(B.d_ext_size, zeros);
+    if ((size_t)(hp - host.data()) > bytes) return "scalar block: internal table overflow";
+    if (cudaMemcpyAsync(B.d_tables, host.data(), bytes, cudaMemcpyHostToDevice, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+        cudaGetLastError(); return "scalar block: table upload failed";
+    }
+    if (cudaMalloc(&B.d_val, std::max<size_t>((size_t)(nl + n) * es, 16)) != cudaSuccess ||
+        cudaMalloc(&B.d_epart, std::max<size_t>((size_t)ne * es, 16)) != cudaSuccess) { cudaGetLastError(); return "scalar block: out of device memory (pools)"; }
+    B.h_ext_val.assign(nref, nullptr); B.h_ext_der.assign(nref, nullptr); B.h_ext_size.assign(nref, 0);
+    return "";
+}
+
+void scalar_block_free(ScalarBlock &B) {
+    cudaFree(B.d_tables); cudaFree(B.d_val); cudaFree(B.d_epart); cudaFree(B.d_der);
+    B.d_tables = B.d_val = B.d_epart = B.d_der = nullptr;
+}
+
+cudaError_t scalar_block_upload_ext(ScalarBlock &B, cudaStream_t s) {
+    if (B.n_ref == 0) return cudaSuccess;
+    cudaError_t e = cudaMemcpyAsync(B.d_ext_val, B.h_ext_val.data(), B.n_ref * sizeof(void *), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(B.d_ext_der, B.h_ext_der.data(), B.n_ref * sizeof(void *), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(B.d_ext_size, B.h_ext_size.data(), B.n_ref * sizeof(int64_t), cudaMemcpyHostToDevice, s);
+    return e;
+}
+
+cudaError_t scalar_block_ensure_R(ScalarBlock &B, int64_t R, size_t es) {
+    if (R <= B.R_alloc) return cudaSuccess;
+    cudaFree(B.d_der);
+    B.d_der = nullptr;
+    cudaError_t e = cudaMalloc(&B.d_der, std::max<size_t>((size_t)B.n * R * es, 16));
+    if (e == cudaSuccess) B.R_alloc = R;
+    return e;
+}
+
+template <typename T>
+cudaError_t scalar_block_forward(cudaStream_t s, ScalarBlock &B, const double *fconst, int *launches) {
+    int nl = 0;
+    if (B.n_leaf > 0) {
+        k_scalar_pull<T><<<(unsigned)((B.n_leaf + 255) / 256), 256, 0, s>>>((T *)B.d_val, B.d_leaf_ord, B.d_leaf_elem, B.d_ext_val, B.n_leaf);
+        ++nl;
+    }
+    FwdP P{B.d_finstr, B.d_flevel_off, B.d_ops, B.d_exprs, B.d_epos, fconst, B.d_val, B.d_epart, B.n_leaf, 0, 0};
+    for (const ScalarSeg &g : B.fsegs) {
+        P.lv0 = g.lv0; P.lv1 = g.lv1;
+        k_scalar_forward<T><<<g.grid, kFwdThreads, 0, s>>>(P);
+        ++nl;
+    }
+    if (B.n_exports > 0) {
+        k_scalar_export<T><<<(unsigned)((B.n_exports + 255) / 256), 256, 0, s>>>((const T *)B.d_val, B.d_exp_slot, B.d_exp_ord, B.d_exp_elem,
+                                                                                 B.d_ext_val, B.n_leaf, B.n_exports);
+        ++nl;
+    }
+    if (launches) *launches = nl;
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t scalar_block_reverse(cudaStream_t s, ScalarBlock &B, int64_t R, int *launches) {
+    RevP P{B.d_rslot, B.d_reoff, B.d_esrc, B.d_epart, B.d_rlevel_off, B.d_xoff, B.d_xord, B.d_xelem, B.d_leaf_ord, B.d_leaf_elem,
+           B.d_ext_der, B.d_ext_size, B.d_der, R, 0, B.n_rlevels};
+    int nl = 0;
+    if (R >= 16) {
+        k_scalar_reverse_seeds<T><<<(unsigned)((R + 31) / 32), 256, 0, s>>>(P);
+        ++nl;
+    } else {
+        for (const ScalarSeg &g : B.rsegs) {
+            P.lv0 = g.lv0; P.lv1 = g.lv1;
+            k_scalar_reverse_slots<T><<<g.grid, kFwdThreads, 0, s>>>(P);
+            ++nl;
+        }
+    }
+    if (launches) *launches = nl;
+    return cudaGetLastError();
+}
+
+template cudaError_t scalar_block_forward<double>(cudaStream_t, ScalarBlock &, const double *, int *);
+template cudaError_t scalar_block_forward<float>(cudaStream_t, ScalarBlock &, const double *, int *);
+template cudaError_t scalar_block_reverse<double>(cudaStream_t, ScalarBlock &, int64_t, int *);
+template cudaError_t scalar_block_reverse<float>(cudaStream_t, ScalarBlock &, int64_t, int *);
+
+}  // namespace rdb

@@ -89,6 +89,8 @@ def _unary(code, npf):
     def f(x):
         if isinstance(x, Sym):
             return x.tr.emit(code, x.reg)
+        if hasattr(x, "_scalar_unary"):          # TrackedReal: DiffRules unary function -> one ScalarInstruction (scalars.jl:11-12)
+            return x._scalar_unary(code)
         return npf(x)
     return f
 
@@ -111,6 +113,9 @@ def _binary(code, npf):
             return x._bin(code, y)
         if isinstance(y, Sym):
             return y._bin(code, x, True)
+        if hasattr(x, "_scalar_unary") or hasattr(y, "_scalar_unary"):
+            from .tracked import _scalar_binary
+            return _scalar_binary(code, x, y)
         return npf(x, y)
     return f
 

@@ -62,13 +62,23 @@ OP_DOT = 17       # dot            linalg/reductions.jl:91-104
 OP_SUMDIMS = 18   # sum!/sum(x,dims) linalg/reductions.jl:32-46
 OP_TRACKER_BCAST = 19  # tracker_∇broadcast (a plain Real or TrackedReal among the args)  broadcast.jl:229-238
 OP_GETINDEX_GENERIC = 20  # (getindex, Val(:generic)): integer-vector indices  tracked.jl:352-362
+OP_SCALAR_BLOCK = 21  # a run of consecutive ScalarInstructions (tape.jl:30-45; derivatives/scalars.jl:52-123), see ScalarBlock
 OP_NAMES = {
     OP_MUL: "*", OP_ADD: "+", OP_SUB: "-", OP_NEG: "neg", OP_SUM: "sum", OP_MEAN: "mean",
     OP_NBCAST: "∇broadcast", OP_MAP: "map", OP_BCAST: "broadcast",
     OP_BCAST_ADD: "(broadcast,+)", OP_BCAST_SUB: "(broadcast,-)", OP_BCAST_MUL: "(broadcast,*)",
     OP_GETINDEX: "getindex", OP_BCAST_DIV: "(broadcast,/)", OP_BCAST_LDIV: "(broadcast,\\)", OP_BCAST_POW: "(broadcast,^)",
     OP_DOT: "dot", OP_SUMDIMS: "sum!", OP_TRACKER_BCAST: "tracker_∇broadcast", OP_GETINDEX_GENERIC: "(getindex,:generic)",
+    OP_SCALAR_BLOCK: "scalar-block",
 }
+
+# operand spaces of a scalar instruction (ScalarBlock payload)
+SP_POOL = -1      # TrackedReal created by an earlier instruction of the SAME block: idx = its instruction number
+SP_LITERAL = -2   # untracked Real (capture(::Real), tape.jl:24): idx = index into the fconst pool
+SP_NONE = -3      # absent second input of a unary instruction
+# space >= 0: ordinal into the block's referenced-buffer list; idx = 0-based linear element of that buffer.  This is a
+# TrackedReal WITH an origin (tracked.jl:348-351: scalar getindex records nothing, value/deriv are pulled from / pushed to
+# origin[index], tracked.jl:178-197), or a TrackedReal produced by an array instruction / exported by another block.
 
 # scalar-expression bytecode: SSA, 4 x int32 per op = (code, a, b, imm) -----------------
 # registers 0..N-1 are the N arguments; op j writes register N+j; the last op is the result.
@@ -147,14 +157,115 @@ class Operand:
 
 
 class Instr:
-    __slots__ = ("opcode", "inputs", "out", "expr", "n_expr_args")
+    __slots__ = ("opcode", "inputs", "out", "expr", "n_expr_args", "scalar")
 
-    def __init__(self, opcode, inputs, out, expr=None, n_expr_args=0):
+    def __init__(self, opcode, inputs, out, expr=None, n_expr_args=0, scalar=None):
         self.opcode = int(opcode)
         self.inputs = list(inputs)
         self.out = int(out)
         self.expr = expr                  # (ops: int32[n,4], fconsts: float64[]) or None
         self.n_expr_args = int(n_expr_args)
+        self.scalar = scalar              # ScalarBlock for OP_SCALAR_BLOCK
+
+
+class ScalarBlock:
+    """A maximal run of consecutive ``ScalarInstruction``s (``src/tape.jl:30-45``), shipped as ONE tape entry.
+
+    Instruction ``i`` of the block is ``(func = exprs[expr_id[i]], input = (a, b), output = pool slot i)``; every scalar
+    instruction creates exactly one new ``TrackedReal`` (``macros.jl:84-131``), so slot == instruction number.  A slot that
+    anything OUTSIDE the block reads (the tape output, an operand of a later array instruction or of a later block) is
+    *exported*: mirrored into element ``elem`` of a tape buffer, whose deriv carries the adjoint back into the block.
+
+    Wire form (int64 words in the idx section, referenced by ``in[0].idx_offset/idx_len``)::
+
+        n_instr, n_refbufs, n_exports, n_exprs,
+        refbufs[n_refbufs],                                  buffer ids; operand spaces / export targets index this table
+        exprs[n_exprs]     x (expr_offset, expr_len, n_args),
+        exports[n_exports] x (slot, ref_ordinal, elem),
+        instrs[n_instr]    x (expr_id, a_space, a_idx, b_space, b_idx)
+    """
+
+    def __init__(self, token_buffer=-1):
+        self.token_buffer = int(token_buffer)     # the tape entry's nominal `out` (a block has many outputs: its exports)
+        self.spill_buffer = -1                    # BUF_TA that collects slots read by LATER blocks; sized by finalize()
+        self.n_spill = 0
+        self.expr_id, self.a_space, self.a_idx, self.b_space, self.b_idx = [], [], [], [], []
+        self.exprs = []           # (ops int32[n,4], fconsts float64[], n_args)
+        self._expr_key = {}
+        self.refbufs, self._ref_ord = [], {}
+        self.literals, self._lit_ord = [], {}     # block-local literal pool (re-based into fconst on the wire)
+        self.exports = []                         # (slot, ref_ordinal, elem)
+        self.export_of = {}                       # slot -> (buffer, elem) of its first export
+
+    def __len__(self):
+        return len(self.expr_id)
+
+    def expr(self, ops, fconsts, n_args) -> int:
+        ops = np.ascontiguousarray(ops, np.int32).reshape(-1, 4)
+        fconsts = np.ascontiguousarray(fconsts, np.float64)
+        key = (ops.tobytes(), fconsts.tobytes(), int(n_args))
+        k = self._expr_key.get(key)
+        if k is None:
+            k = self._expr_key[key] = len(self.exprs)
+            self.exprs.append((ops, fconsts, int(n_args)))
+        return k
+
+    def ref(self, buffer: int) -> int:
+        k = self._ref_ord.get(buffer)
+        if k is None:
+            k = self._ref_ord[buffer] = len(self.refbufs)
+            self.refbufs.append(int(buffer))
+        return k
+
+    def literal(self, v: float) -> int:
+        v = float(v)
+        key = np.float64(v).tobytes()        # bit pattern: keeps -0.0 and NaN payloads apart
+        k = self._lit_ord.get(key)
+        if k is None:
+            k = self._lit_ord[key] = len(self.literals)
+            self.literals.append(v)
+        return k
+
+    def export(self, slot: int, buffer: int, elem: int):
+        self.exports.append((int(slot), self.ref(buffer), int(elem)))
+        self.export_of.setdefault(int(slot), (int(buffer), int(elem)))
+
+    def push(self, expr_id, a, b) -> int:
+        self.expr_id.append(expr_id)
+        self.a_space.append(a[0]); self.a_idx.append(a[1])
+        self.b_space.append(b[0]); self.b_idx.append(b[1])
+        return len(self.expr_id) - 1
+
+    @staticmethod
+    def from_payload(w, expr, fconst, token_buffer) -> "ScalarBlock":
+        """Inverse of the wire form; literals come back as indices into a block-local pool again."""
+        w = np.asarray(w, np.int64)
+        n, nref, nexp, nex = (int(v) for v in w[:4])
+        blk = ScalarBlock(token_buffer)
+        o = 4
+        blk.refbufs = [int(v) for v in w[o:o + nref]]; o += nref
+        blk._ref_ord = {b: k for k, b in enumerate(blk.refbufs)}
+        table = w[o:o + 3 * nex].reshape(-1, 3); o += 3 * nex
+        for eo, el, na in table:
+            ops = np.asarray(expr[int(eo): int(eo) + 4 * int(el)], np.int32).reshape(-1, 4).copy()
+            local = []
+            for row in ops:
+                if row[0] == E_CONST:
+                    local.append(float(fconst[row[3]]))
+                    row[3] = len(local) - 1
+            blk.exprs.append((ops, np.asarray(local, np.float64), int(na)))
+        for s_, r_, e_ in w[o:o + 3 * nexp].reshape(-1, 3):
+            blk.exports.append((int(s_), int(r_), int(e_)))
+            blk.export_of.setdefault(int(s_), (blk.refbufs[int(r_)], int(e_)))
+        o += 3 * nexp
+        body = w[o:o + 5 * n].reshape(-1, 5).copy()
+        for sp, ix in ((1, 2), (3, 4)):
+            for r in np.nonzero(body[:, sp] == SP_LITERAL)[0]:
+                body[r, ix] = blk.literal(float(fconst[body[r, ix]]))
+        blk.expr_id = body[:, 0].tolist()
+        blk.a_space, blk.a_idx = body[:, 1].tolist(), body[:, 2].tolist()
+        blk.b_space, blk.b_idx = body[:, 3].tolist(), body[:, 4].tolist()
+        return blk
 
 
 class Buffer:
@@ -192,7 +303,15 @@ class TapeProgram:
         return len(self.buffers) - 1
 
     # -------------------------------------------------------------------------- serialise
+    def finalize(self):
+        """Fix the sizes that are only known once recording is over: a scalar block's spill buffer has one element per
+        slot read by a later block, and such reads keep being added while recording goes on."""
+        for it in self.instrs:
+            if it.scalar is not None and it.scalar.spill_buffer >= 0:
+                self.buffers[it.scalar.spill_buffer].dims = (max(1, it.scalar.n_spill),)
+
     def to_bytes(self) -> bytes:
+        self.finalize()
         npdt = NP_DTYPE[self.dtype]
         nb, ni, nin = len(self.buffers), len(self.instrs), len(self.inputs)
         bufs = np.zeros(nb, BUFFER_DTYPE)
@@ -225,6 +344,36 @@ class TapeProgram:
             rec["n_expr_args"] = it.n_expr_args
             if len(it.inputs) > MAX_ARGS:
                 raise ValueError(f"instructions with more than {MAX_ARGS} inputs are not supported")
+            if it.scalar is not None:
+                blk = it.scalar
+                table = np.zeros((len(blk.exprs), 3), np.int64)
+                for k, (ops, fc, na) in enumerate(blk.exprs):
+                    ops = ops.copy()
+                    for row in ops:
+                        if row[0] == E_CONST:
+                            row[3] += fconst_off
+                    table[k] = (expr_off, ops.shape[0], na)
+                    expr_chunks.append(ops.reshape(-1))
+                    expr_off += ops.shape[0] * 4
+                    fconst_chunks.append(fc)
+                    fconst_off += len(fc)
+                lit_base = fconst_off
+                fconst_chunks.append(np.asarray(blk.literals, np.float64))
+                fconst_off += len(blk.literals)
+                n = len(blk)
+                body = np.empty((n, 5), np.int64)
+                body[:, 0] = blk.expr_id
+                body[:, 1], body[:, 2] = blk.a_space, blk.a_idx
+                body[:, 3], body[:, 4] = blk.b_space, blk.b_idx
+                for sp, ix in ((1, 2), (3, 4)):
+                    lit = body[:, sp] == SP_LITERAL
+                    body[lit, ix] += lit_base
+                payload = np.concatenate([
+                    np.asarray([n, len(blk.refbufs), len(blk.exports), len(blk.exprs)], np.int64),
+                    np.asarray(blk.refbufs, np.int64), table.reshape(-1),
+                    np.asarray(blk.exports, np.int64).reshape(-1), body.reshape(-1)])
+                it.inputs = [Operand(it.out, CLS_TR, False, (), IDX_EXPLICIT, payload)]
+                rec["n_in"] = 1
             if it.expr is not None:
                 ops, fc = it.expr
                 ops = np.asarray(ops, np.int32).reshape(-1, 4).copy()
@@ -345,7 +494,10 @@ class TapeProgram:
                         local.append(float(fconst[row[3]]))
                         row[3] = len(local) - 1
                 ex = (ops, np.asarray(local, np.float64))
-            p.instrs.append(Instr(int(rec["opcode"]), ops_in, int(rec["out"]), ex, int(rec["n_expr_args"])))
+            blk = None
+            if int(rec["opcode"]) == OP_SCALAR_BLOCK:
+                blk = ScalarBlock.from_payload(ops_in[0].idx_map, expr, fconst, int(rec["out"]))
+            p.instrs.append(Instr(int(rec["opcode"]), ops_in, int(rec["out"]), ex, int(rec["n_expr_args"]), blk))
         _ = es
         return p
 

@@ -48,6 +48,17 @@ class InstructionTape:
         """``record!`` (``src/tape.jl:9-12``)."""
         self.program.instrs.append(P.Instr(opcode, inputs, out_buffer, expr, n_expr_args))
 
+    def scalar_block(self) -> "P.ScalarBlock":
+        """The block that the next ``ScalarInstruction`` (``src/tape.jl:30-45``) is appended to: consecutive scalar
+        instructions share one tape entry, any array instruction in between starts a new one (tape order is kept)."""
+        ins = self.program.instrs
+        if ins and ins[-1].scalar is not None:
+            return ins[-1].scalar
+        token = self.program.add_buffer(P.BUF_TR, ())
+        blk = P.ScalarBlock(token)
+        ins.append(P.Instr(P.OP_SCALAR_BLOCK, [], token, scalar=blk))
+        return blk
+
 
 class ForwardOptimize:
     """``@forward`` (``src/macros.jl:40-74``): the wrapped scalar closure is differentiated in
@@ -57,6 +68,10 @@ class ForwardOptimize:
         self.f = f
 
     def __call__(self, *a):
+        # (self::ForwardOptimize)(t::TrackedReal) / (a, b) with at least one TrackedReal (macros.jl:84-131): ONE instruction
+        if len(a) in (1, 2) and any(isinstance(x, TrackedReal) for x in a) and \
+                all(isinstance(x, TrackedReal) or np.ndim(x) == 0 for x in a):
+            return record_scalar(E.trace(self.f, len(a)), *a)
         return self.f(*a)
 
 
@@ -162,16 +177,163 @@ class TrackedArray:
 
 
 class TrackedReal:
-    """Originless scalar ``TrackedReal`` (``src/tracked.jl:47-57``), e.g. the output of ``sum``."""
+    """``TrackedReal`` (``src/tracked.jl:47-57``).  Three flavours, as in the reference:
 
-    __slots__ = ("value", "tape", "buffer")
+    * output of an array instruction (``sum``, ``dot``...): owns the size-1 buffer ``buffer``;
+    * scalar ``getindex`` of a TrackedArray (``tracked.jl:348-351``): NO instruction, value/deriv live in
+      ``origin[index]`` — here ``(buffer, index)`` with ``index`` the 0-based linear element;
+    * output of a ``ScalarInstruction`` (``macros.jl:84-131``): slot ``slot`` of scalar block ``block``.
+    """
 
-    def __init__(self, value_, tape, buffer):
-        self.value, self.tape, self.buffer = value_, tape, buffer
+    __slots__ = ("value", "tape", "buffer", "index", "block", "slot")
+    __array_ufunc__ = None
+    __array_priority__ = 1000
+
+    def __init__(self, value_, tape, buffer=-1, index=0, block=None, slot=-1):
+        self.value, self.tape, self.buffer, self.index, self.block, self.slot = value_, tape, buffer, index, block, slot
 
     shape = ()
     ndim = 0
     size = 1
+
+    # DiffRules binary functions (derivatives/scalars.jl:5-22): one ScalarInstruction each
+    def __add__(self, o): return _scalar_binary(P.E_ADD, self, o)
+    def __radd__(self, o): return _scalar_binary(P.E_ADD, o, self)
+    def __sub__(self, o): return _scalar_binary(P.E_SUB, self, o)
+    def __rsub__(self, o): return _scalar_binary(P.E_SUB, o, self)
+    def __mul__(self, o): return _scalar_binary(P.E_MUL, self, o)
+    def __rmul__(self, o): return _scalar_binary(P.E_MUL, o, self)
+    def __truediv__(self, o): return _scalar_binary(P.E_DIV, self, o)
+    def __rtruediv__(self, o): return _scalar_binary(P.E_DIV, o, self)
+    def __neg__(self): return self._scalar_unary(P.E_NEG)
+    def __pos__(self): return self
+
+    def __pow__(self, o):
+        if isinstance(o, (int, np.integer)) and not isinstance(o, bool):
+            # x^2 lowers to literal_pow -> ^(t::TrackedReal, 2::Int) (binary ForwardOptimize with a Real exponent)
+            ops = np.asarray([(P.E_POWI, 0, 0, int(o))], np.int32)
+            return record_scalar((ops, np.zeros(0)), self)
+        return _scalar_binary(P.E_POW, self, o)
+
+    def __rpow__(self, o): return _scalar_binary(P.E_POW, o, self)
+
+    def _scalar_unary(self, code):
+        return record_scalar((np.asarray([(code, 0, 0, 0)], np.int32), np.zeros(0)), self)
+
+    # SkipOptimize'd predicates (derivatives/scalars.jl:24-46): evaluated on values, nothing recorded — which is why a
+    # compiled tape freezes the branch taken at record time (docs/src/api.md:39-44)
+    def __lt__(self, o): return self.value < value(o)
+    def __le__(self, o): return self.value <= value(o)
+    def __gt__(self, o): return self.value > value(o)
+    def __ge__(self, o): return self.value >= value(o)
+    def __eq__(self, o): return self.value == value(o)
+    def __ne__(self, o): return self.value != value(o)
+    __hash__ = object.__hash__
+
+    def __float__(self):
+        return float(self.value)
+
+
+def _root_buffer(prog, b):
+    while prog.buffers[b].alias_of >= 0:
+        b = prog.buffers[b].alias_of
+    return b
+
+
+def _slot_buffer(t: "TrackedReal", want_whole=False):
+    """``(buffer, elem)`` through which readers outside ``t.block`` see the slot; exports it on first use.  ``want_whole``
+    asks for a size-1 buffer of its own (operand class TR of an array instruction, or the tape output)."""
+    blk, prog = t.block, t.tape.program
+    hit = blk.export_of.get(t.slot)
+    if hit is not None and (not want_whole or prog.buffers[hit[0]].kind == P.BUF_TR):
+        return hit
+    if want_whole:
+        b = prog.add_buffer(P.BUF_TR, ())
+        blk.export(t.slot, b, 0)
+        if hit is None:
+            return b, 0
+        blk.export_of[t.slot] = hit       # keep the first export as the canonical one for scalar readers
+        return b, 0
+    if blk.spill_buffer < 0:
+        blk.spill_buffer = prog.add_buffer(P.BUF_TA, (1,))
+    k = blk.n_spill
+    blk.n_spill += 1
+    blk.export(t.slot, blk.spill_buffer, k)
+    return blk.spill_buffer, k
+
+
+def _scalar_operand(blk, x, tp):
+    if isinstance(x, TrackedReal):
+        if x.tape is not tp:
+            raise ValueError("TrackedReal from a different tape")
+        if x.block is blk:
+            return (P.SP_POOL, x.slot)
+        if x.block is not None:
+            b, k = _slot_buffer(x)
+            return (blk.ref(b), k)
+        return (blk.ref(_root_buffer(tp.program, x.buffer)), int(x.index))
+    if isinstance(x, (TrackedArray, Adjoint)) or np.ndim(x) != 0:
+        raise TypeError("scalar instructions take TrackedReal / Real arguments")
+    return (P.SP_LITERAL, blk.literal(float(x)))            # capture(::Real) (tape.jl:24): frozen by value
+
+
+def record_scalar(expr, a, b=None):
+    """One ``ScalarInstruction`` (``macros.jl:84-131``): ``expr`` is the traced scalar function of 1 or 2 arguments; value and
+    partials are re-evaluated from it on every forward replay (``scalars.jl:80-123``)."""
+    args = [a] if b is None else [a, b]
+    tp = _tape_of(*[x for x in args if isinstance(x, TrackedReal)])
+    blk = tp.scalar_block()
+    ops, fc = expr
+    eid = blk.expr(ops, fc, len(args))
+    oa = _scalar_operand(blk, a, tp)
+    ob = (P.SP_NONE, 0) if b is None else _scalar_operand(blk, b, tp)
+    v = E.eval_value((np.asarray(ops, np.int32).reshape(-1, 4), fc), [np.asarray(value(x), tp.dtype) for x in args], tp.dtype)
+    slot = blk.push(eid, oa, ob)
+    return TrackedReal(v[()], tp, -1, 0, blk, slot)
+
+
+def _scalar_binary(code, a, b):
+    return record_scalar((np.asarray([(code, 0, 1, 0)], np.int32), np.zeros(0)), a, b)
+
+
+def _scalar_const(tp, c):
+    """A block slot holding a literal (not an instruction of the reference: used to materialise plain Reals in ``collect``)."""
+    blk = tp.scalar_block()
+    eid = blk.expr(np.asarray([(P.E_CONST, 0, 0, 0)], np.int32), np.asarray([float(c)]), 0)
+    slot = blk.push(eid, (P.SP_NONE, 0), (P.SP_NONE, 0))
+    return TrackedReal(np.asarray(c, tp.dtype)[()], tp, -1, 0, blk, slot)
+
+
+def _scalar_identity(t: "TrackedReal"):
+    return record_scalar((np.asarray([(P.E_ARG, 0, 0, 0)], np.int32), np.zeros(0)), t)
+
+
+def scalar_buffer(t: "TrackedReal") -> int:
+    """Size-1 buffer that carries ``t`` (operand class TR of array instructions; ``output_hook`` of a GradientTape)."""
+    prog = t.tape.program
+    if t.block is None:
+        if prog.buffers[t.buffer].kind == P.BUF_TR and prog.buffers[t.buffer].size == 1:
+            return t.buffer
+        t = _scalar_identity(t)       # element of an array: route it through a slot of its own
+    return _slot_buffer(t, want_whole=True)[0]
+
+
+def collect(xs, tape=None):
+    """``[t1, t2, ...]`` — an ``Array{TrackedReal}`` used as a tape OUTPUT (``seed!(output, i)`` works on any array of
+    tracked scalars, ``api/utils.jl:44-58``): element ``k`` of a fresh buffer mirrors ``xs[k]``."""
+    xs = list(np.asarray(xs, dtype=object).reshape(-1, order="F")) if not isinstance(xs, (list, tuple)) else list(xs)
+    tp = tape if tape is not None else _tape_of(*[x for x in xs if isinstance(x, TrackedReal)])
+    prog = tp.program
+    buf = prog.add_buffer(P.BUF_TA, (len(xs),))
+    vals = np.zeros(len(xs), tp.dtype)
+    for k, x in enumerate(xs):
+        if not isinstance(x, TrackedReal):
+            x = _scalar_const(tp, x)
+        elif x.block is None:
+            x = _scalar_identity(x)
+        x.block.export(x.slot, buf, k)
+        vals[k] = x.value
+    return TrackedArray(vals, tp, buf)
 
 
 class Adjoint:
@@ -244,7 +406,7 @@ def _capture(x, tp: InstructionTape, bound_to=None) -> P.Operand:
     if isinstance(x, TrackedArray):
         return P.Operand(x.buffer, P.CLS_TA, True, x.shape, bound=bound)
     if isinstance(x, TrackedReal):
-        return P.Operand(x.buffer, P.CLS_TR, True, (), bound=bound)
+        return P.Operand(scalar_buffer(x), P.CLS_TR, True, (), bound=bound)
     if isinstance(x, Adjoint):
         par = x.parent
         if isinstance(par, TrackedArray):
@@ -444,8 +606,16 @@ def record_getindex(t: TrackedArray, key):
     if not isinstance(key, tuple):
         key = (key,)
     if all(isinstance(k, (int, np.integer)) for k in key):
-        raise TypeError("scalar getindex yields an origin-linked TrackedReal (tracked.jl:348-351); "
-                        "scalar tapes are not lowered yet")
+        # scalar getindex (tracked.jl:348-351): TrackedReal(value[i], deriv[i], tape, index, origin) — no instruction
+        if len(key) == 1:
+            lin = int(key[0]) + (t.size if key[0] < 0 else 0)
+            if not 0 <= lin < t.size:
+                raise IndexError("index out of range")
+        else:
+            if len(key) != t.ndim:
+                raise IndexError("wrong number of indices")
+            lin = int(np.ravel_multi_index(tuple(int(k) % d for k, d in zip(key, t.shape)), t.shape, order="F"))
+        return TrackedReal(t.value.reshape(-1, order="F")[lin], t.tape, t.buffer, lin)
     generic = not all(isinstance(k, slice) for k in key)
     if generic:
         # (getindex, Val(:generic)): Integer / Colon / integer-vector per dimension (tracked.jl:352-362)

@@ -1,0 +1,280 @@
+"""Scalar-instruction tapes (``ScalarInstruction``, reference ``src/derivatives/scalars.jl:52-123``,
+``src/macros.jl:84-131``; scalar ``getindex`` ``src/tracked.jl:348-351``).
+
+CPU part: the recorder, the wire format and the oracle's sequential loops (pure Python and the C helper) against closed forms
+and finite differences.  GPU part (``-m gpu``): the level-parallel device replay through the C ABI against the oracle.
+"""
+import numpy as np
+import pytest
+
+TOL = {np.float64: 1e-12, np.float32: 1e-5}
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+# ------------------------------------------------------------------------------------------ workloads
+def rosenbrock_loop(x):
+    """``benchmark/benchmark.jl:60-76`` spelled with scalar indexing: every operation is one ScalarInstruction."""
+    acc = 0.0
+    for i in range(x.size // 2):
+        o, e = x[2 * i], x[2 * i + 1]
+        acc = acc + (100.0 * (e - o ** 2) ** 2 + (1.0 - o) ** 2)
+    return acc
+
+
+def make_ackley(rd):
+    def ackley(x):
+        """``benchmark/benchmark.jl:84-95``."""
+        a, b, c = 20.0, -0.2, 2.0 * np.pi
+        n = x.size
+        s1 = 0.0
+        s2 = 0.0
+        for i in range(n):
+            s1 = s1 + x[i] ** 2
+            s2 = s2 + rd.cos(c * x[i])
+        return -a * rd.exp(b * rd.sqrt(s1 / n)) - rd.exp(s2 / n) + a + np.e
+    return ackley
+
+
+def ackley_np(x):
+    a, b, c = 20.0, -0.2, 2.0 * np.pi
+    n = x.size
+    return -a * np.exp(b * np.sqrt(np.sum(x * x) / n)) - np.exp(np.sum(np.cos(c * x)) / n) + a + np.e
+
+
+def make_mixed(rd):
+    def mixed(x, w):
+        """Array and scalar instructions interleaved: two scalar blocks around array instructions, a TrackedReal produced by an
+        array instruction consumed by scalar ones, block slots consumed by a tracker broadcast and by a later block."""
+        s = rd.sum(x)                                  # array instruction -> TrackedReal
+        y = s * x[0] + rd.tanh(x[1]) / w[2]            # block 1
+        z = rd.bcast(lambda v, c: v * c, w, y)         # tracker_∇broadcast with a block slot as the scalar argument
+        t = rd.sum(z)
+        u = (t - y) * x[0] * x[0]                      # block 2: reads a slot of block 1, the same leaf twice
+        return u * u + rd.forward(lambda p, q: p * rd.exp(q) - q)(y, x[3])
+    return mixed
+
+
+def mixed_np(x, w):
+    s = np.sum(x)
+    y = s * x[0] + np.tanh(x[1]) / w[2]
+    t = np.sum(w * y)
+    u = (t - y) * x[0] * x[0]
+    return u * u + (y * np.exp(x[3]) - x[3])
+
+
+def fd_grad(f, xs, k, h=1e-6):
+    g = np.zeros(xs[k].size)
+    for i in range(xs[k].size):
+        xp = [v.copy() for v in xs]; xm = [v.copy() for v in xs]
+        xp[k][i] += h; xm[k][i] -= h
+        g[i] = (f(*xp) - f(*xm)) / (2 * h)
+    return g
+
+
+def make_vecfun(rd):
+    def vecfun(x):
+        """R^n -> R^n, written element by element; returned as an Array{TrackedReal}."""
+        n = x.size
+        out = []
+        for i in range(n):
+            a, b = x[i], x[(i + 1) % n]
+            out.append(a * rd.sin(b) + b / (1.0 + a ** 2))
+        out[1] = x[1]            # a tape input element passed straight through
+        out[2] = 3.0             # a plain number
+        return out
+    return vecfun
+
+
+def vecfun_jac(x):
+    n = x.size
+    J = np.zeros((n, n))
+    for i in range(n):
+        j = (i + 1) % n
+        a, b = x[i], x[j]
+        J[i, i] += np.sin(b) - b * 2 * a / (1.0 + a * a) ** 2
+        J[i, j] += a * np.cos(b) + 1.0 / (1.0 + a * a)
+    J[1, :] = 0; J[1, 1] = 1
+    J[2, :] = 0
+    return J
+
+
+# ------------------------------------------------------------------------------------------ CPU: recorder + oracle
+def test_recorder_one_block_no_getindex_instructions(rd):
+    x0 = np.random.default_rng(1).random(8)
+    tape = rd.GradientTape(rosenbrock_loop, x0)
+    assert len(tape) == 1                                            # one maximal run of scalar instructions
+    blk = tape.tape.program.instrs[0].scalar
+    assert len(blk) == 4 * 8                                          # o^2, e-., (.)^2, 100*., 1-o, (.)^2, +, acc+ per pair
+    assert blk.refbufs[0] == tape.tape.program.inputs[0]
+    raw = tape.program_bytes()
+    assert rd.program.TapeProgram.from_bytes(raw).to_bytes() == raw   # wire round trip
+
+
+@pytest.mark.parametrize("use_c", [False, True])
+def test_oracle_rosenbrock_closed_form(rd, orc, use_c):
+    n = 64
+    x0 = np.random.default_rng(1).random(n); x = np.random.default_rng(2).random(n)
+    tape = rd.GradientTape(rosenbrock_loop, x0)
+    orc._ScalarBlock.use_c = use_c
+    try:
+        if use_c:
+            assert orc._scalar_lib() is not None, "oracle/libscalar_block.so not built (run __graft_entry__.build())"
+        val, (g,) = orc.OracleTape(tape.program_bytes()).gradient([x])
+    finally:
+        orc._ScalarBlock.use_c = True
+    o, e = x[0::2], x[1::2]
+    ref = np.zeros(n); ref[0::2] = -400 * o * (e - o * o) - 2 * (1 - o); ref[1::2] = 200 * (e - o * o)
+    assert abs(val - np.sum(100 * (e - o * o) ** 2 + (1 - o) ** 2)) < 1e-12 * abs(val)
+    assert relerr(g, ref) < 1e-13
+
+
+def test_oracle_c_and_python_loops_agree(rd, orc):
+    """Same statements in both: bit-identical for pure arithmetic; within an ulp or two where libm and numpy differ (exp, tanh)."""
+    x0 = np.random.default_rng(1).random(16); w0 = np.random.default_rng(3).random(5)
+    x = np.random.default_rng(2).random(16); w = np.random.default_rng(4).random(5)
+    for f, rec, inp, exact in ((make_mixed(rd), (x0, w0), [x, w], False), (rosenbrock_loop, x0, [x], True)):
+        tape = rd.GradientTape(f, rec)
+        res = []
+        for use_c in (False, True):
+            orc._ScalarBlock.use_c = use_c
+            try:
+                res.append(orc.OracleTape(tape.program_bytes()).gradient(inp))
+            finally:
+                orc._ScalarBlock.use_c = True
+        if exact:
+            assert res[0][0] == res[1][0]
+        for a, b in zip(res[0][1], res[1][1]):
+            assert np.array_equal(a, b) if exact else relerr(a, b) < 1e-14
+
+
+def test_oracle_mixed_and_ackley_finite_differences(rd, orc):
+    x0 = np.random.default_rng(1).random(16); w0 = np.random.default_rng(3).random(5)
+    x = np.random.default_rng(2).random(16); w = np.random.default_rng(4).random(5)
+    tape = rd.GradientTape(make_mixed(rd), (x0, w0))
+    assert [i.opcode for i in tape.tape.program.instrs].count(rd.program.OP_SCALAR_BLOCK) == 2
+    val, (gx, gw) = orc.OracleTape(tape.program_bytes()).gradient([x, w])
+    assert abs(val - mixed_np(x, w)) < 1e-12 * abs(val)
+    assert relerr(gx, fd_grad(mixed_np, [x, w], 0)) < 1e-6
+    assert relerr(gw, fd_grad(mixed_np, [x, w], 1)) < 1e-6
+    tape = rd.GradientTape(make_ackley(rd), x0)
+    val, (g,) = orc.OracleTape(tape.program_bytes()).gradient([x])
+    assert abs(val - ackley_np(x)) < 1e-12 * abs(val)
+    assert relerr(g, fd_grad(ackley_np, [x], 0)) < 1e-6
+
+
+def test_oracle_jacobian_of_tracked_real_array(rd, orc):
+    n = 12
+    x0 = np.random.default_rng(1).random(n); x = np.random.default_rng(2).random(n)
+    tape = rd.JacobianTape(make_vecfun(rd), x0)
+    val, J = orc.OracleTape(tape.program_bytes()).jacobian([x])
+    assert relerr(J, vecfun_jac(x)) < 1e-13
+    assert val[2] == 3.0 and val[1] == x[1]
+
+
+def test_compiled_tape_freezes_branches(rd, orc):
+    """Predicates on TrackedReals are evaluated at record time only (SkipOptimize, scalars.jl:24-46; docs/src/api.md:39-44)."""
+    f = lambda x: x[0] * 2.0 if x[0] > 0.5 else x[0] * 3.0
+    tape = rd.GradientTape(f, np.array([0.9, 0.0]))
+    _, (g,) = orc.OracleTape(tape.program_bytes()).gradient([np.array([0.1, 0.0])])
+    assert g[0] == 2.0
+
+
+# ------------------------------------------------------------------------------------------ GPU parity
+def _check_all_buffers(ct, ot, orc, tol):
+    for b in range(len(ot.value)):
+        if ot.kind[b] == orc.BUF_CONST:
+            continue
+        assert relerr(ct.handle.get_value(b), ot.value[b].reshape(-1, order="F")) < tol, f"value of buffer {b}"
+        d = ct.handle.get_deriv(b); od = ot.deriv[b].reshape(-1, order="F")
+        if np.any(od):
+            assert relerr(d, od) < tol
+        else:
+            assert not np.any(d), f"deriv of buffer {b} not unseeded"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [2, 8, 1024, 40000])
+def test_gpu_gradient_rosenbrock_loop(rd, orc, dtype, n):
+    x0 = np.random.default_rng(1).random(n).astype(dtype); x = np.random.default_rng(2).random(n).astype(dtype)
+    tape = rd.GradientTape(rosenbrock_loop, x0, dtype=dtype)
+    ct = rd.compile(tape)
+    for rep in range(3):       # replays: eager, graph capture, graph launch for small tapes
+        res = rd.DiffResult(0.0, np.zeros(n, dtype))
+        rd.gradient_(res, ct, x)
+        ot = orc.OracleTape(tape.program_bytes())
+        val, (g,) = ot.gradient([x])
+        assert abs(float(res.value) - float(val)) <= TOL[dtype] * abs(float(val))
+        assert relerr(res.gradient, g) < TOL[dtype]
+    if dtype == np.float64:
+        o, e = x[0::2], x[1::2]
+        ref = np.zeros(n); ref[0::2] = -400 * o * (e - o * o) - 2 * (1 - o); ref[1::2] = 200 * (e - o * o)
+        assert relerr(res.gradient, ref) < 1e-12
+        if n <= 1024:
+            assert np.array_equal(res.gradient, g)      # same operations in the same order, no contraction: bit-identical
+
+
+@pytest.mark.gpu
+def test_gpu_gradient_mixed_blocks(rd, orc):
+    x0 = np.random.default_rng(1).random(16); w0 = np.random.default_rng(3).random(5)
+    x = np.random.default_rng(2).random(16); w = np.random.default_rng(4).random(5)
+    tape = rd.GradientTape(make_mixed(rd), (x0, w0))
+    for use_graph in (0, 1):
+        ct = rd.compile(tape, use_graph=use_graph)
+        for rep in range(3):
+            res = (rd.DiffResult(0.0, np.zeros(16)), rd.DiffResult(0.0, np.zeros(5)))
+            rd.gradient_(res, ct, (x, w))
+            ot = orc.OracleTape(tape.program_bytes())
+            val, (gx, gw) = ot.gradient([x, w])
+            assert abs(res[0].value - val) <= 1e-12 * abs(val)
+            assert relerr(res[0].gradient, gx) < 1e-12 and relerr(res[1].gradient, gw) < 1e-12
+        if not use_graph:
+            _check_all_buffers(ct, ot, orc, 1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_gradient_ackley(rd, orc):
+    n = 3000
+    x0 = np.random.default_rng(1).random(n); x = np.random.default_rng(2).random(n)
+    tape = rd.GradientTape(make_ackley(rd), x0)
+    ct = rd.compile(tape)
+    res = rd.DiffResult(0.0, np.zeros(n))
+    rd.gradient_(res, ct, x)
+    val, (g,) = orc.OracleTape(tape.program_bytes()).gradient([x])
+    assert abs(res.value - val) <= 1e-12 * abs(val)
+    assert relerr(res.gradient, g) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,seed_block", [(5, 0), (12, 0), (40, 0), (100, 0), (100, 16), (100, 33), (300, 7)])
+def test_gpu_jacobian_of_tracked_real_array(rd, orc, n, seed_block):
+    """R < 16 runs the slot-parallel kernel, R >= 16 the seed-lane kernel (lanes = seeds); seed_block forces ragged blocks."""
+    x0 = np.random.default_rng(1).random(n); x = np.random.default_rng(2).random(n)
+    tape = rd.JacobianTape(make_vecfun(rd), x0)
+    ct = rd.compile(tape, seed_block=seed_block)
+    J = np.zeros((n, n), order="F")
+    res = rd.DiffResult(np.zeros(n), J)
+    rd.jacobian_(res, ct, x)
+    ot = orc.OracleTape(tape.program_bytes())
+    val, Jo = ot.jacobian([x])
+    assert relerr(J, Jo) < 1e-12 and relerr(J, vecfun_jac(x)) < 1e-12
+    assert relerr(res.value, val) < 1e-12
+    # row shard (multi-GPU unit of work)
+    Jb = np.zeros((n - n // 2, n), order="F")
+    rd.jacobian_(Jb, ct, x, rows=(n // 2, n))
+    assert np.array_equal(Jb, J[n // 2:, :])
+
+
+@pytest.mark.gpu
+def test_gpu_rejects_bad_scalar_block(rd, ctx):
+    P = rd.program
+    tape = rd.GradientTape(rosenbrock_loop, np.random.default_rng(1).random(4))
+    blk = tape.tape.program.instrs[0].scalar
+    blk.a_idx[3] = 10 ** 6                        # operand refers to a slot that does not exist yet
+    blk.a_space[3] = P.SP_POOL
+    with pytest.raises(Exception):
+        rd.compile(tape)
