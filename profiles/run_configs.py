@@ -144,6 +144,60 @@ if "5" in which:   # cfg 5: hessian! extended Rosenbrock n = 16384
                 "result_bytes": n * n * 8, "result_write_GBps": n * n * 8 / ms / 1e6, "max_rel_err_vs_closed_form": err,
                 "structural_zeros_exact": zeros_exact, "steps": stats_of(tape, lambda c: rd.hessian_(H, c, xd))})
 
+if "scalar" in which:   # §8 row a13: scalar-instruction tapes (the reference's own HessianTape; loop-written gradients)
+    orc = graft.load_oracle()
+
+    def rosen_H(xt, n):
+        oo, ee = xt[0::2], xt[1::2]
+        idx = torch.arange(n // 2, device="cuda")
+        Hcf = torch.zeros(n, n, dtype=torch.float64, device="cuda")
+        Hcf[2 * idx, 2 * idx] = 1200 * oo ** 2 - 400 * ee + 2
+        Hcf[2 * idx, 2 * idx + 1] = -400 * oo; Hcf[2 * idx + 1, 2 * idx] = -400 * oo
+        Hcf[2 * idx + 1, 2 * idx + 1] = 200
+        return Hcf
+    for n in [int(v) for v in os.environ.get("SCALAR_HESS_N", "1024,4096").split(",")]:
+        t0 = time.perf_counter()
+        tape = rd.HessianTape(rd.workloads.f_rosenbrock_loop, rd.workloads.inputs_rosenbrock(n, seed=1), mode="reverse")
+        rec_s = time.perf_counter() - t0
+        blk = tape.tape.program.instrs[0].scalar
+        ct = rd.compile(tape, ctx=ctx)
+        x = rd.workloads.inputs_rosenbrock(n, seed=2)
+        xd = dev(x); H = torch.empty(n * n, dtype=torch.float64, device="cuda")
+        ms = timeit(lambda: rd.hessian_(H, ct, xd), 3, 2)
+        Hm = H.reshape(n, n).T
+        Hcf = rosen_H(torch.from_numpy(x).cuda(), n)
+        err = float((Hm - Hcf).abs().max() / Hcf.abs().max())
+        zeros_exact = bool((Hm[Hcf == 0] == 0).all())
+        # CPU: the same tape through the oracle's C loops (one forward sweep + one reverse sweep per row), a sample of rows
+        ot = orc.OracleTape(tape.program_bytes())
+        rows = min(n, 256)
+        t0 = time.perf_counter(); ot.jacobian([x], rows=range(rows)); cpu_s = time.perf_counter() - t0
+        out.append({"cfg": "5-literal", "what": f"hessian! extended Rosenbrock n={n} f64 on the reference's reverse-over-reverse scalar tape",
+                    "scalar_instructions": len(blk), "record_s": rec_s, "ms_per_hessian": ms, "rows_per_s": n / ms * 1e3,
+                    "max_rel_err_vs_closed_form": err, "structural_zeros_exact": zeros_exact,
+                    "cpu_port_rows_per_s": rows / cpu_s, "cpu_sample": f"{rows} rows, oracle/scalar_block.c loops, 1 thread",
+                    "steps": stats_of(tape, lambda c: rd.hessian_(H, c, xd))})
+        del ct, H
+    for name, f, n in (("rosenbrock_loop", rd.workloads.f_rosenbrock_loop, 16384), ("ackley_loop", rd.workloads.f_ackley_loop, 16384)):
+        tape = rd.GradientTape(f, rd.workloads.inputs_rosenbrock(n, seed=1))
+        blk = tape.tape.program.instrs[0].scalar
+        x = rd.workloads.inputs_rosenbrock(n, seed=2)
+        xd = dev(x); g = torch.empty(n, dtype=torch.float64, device="cuda")
+        res = {}
+        for label, ug in (("graph", 1), ("eager", 0)):
+            ctg = rd.compile(tape, ctx=rd.engine.Context(0) if ug else ctx, use_graph=ug)
+            res["ms_per_eval_" + label] = timeit(lambda: rd.gradient_(g, ctg, xd), 5, 3)
+        ot = orc.OracleTape(tape.program_bytes())
+        ot.gradient([x])
+        t0 = time.perf_counter()
+        for _ in range(5):
+            _, (go,) = ot.gradient([x])
+        cpu_ms = (time.perf_counter() - t0) / 5 * 1e3
+        err = float(np.max(np.abs(g.cpu().numpy() - go)) / np.max(np.abs(go)))
+        out.append({"cfg": "scalar-gradient", "what": f"gradient! of {name} n={n} f64 (one seed: only dataflow parallelism)",
+                    "scalar_instructions": len(blk), **res, "cpu_port_ms_per_eval": cpu_ms, "max_rel_err_vs_oracle": err,
+                    "steps": stats_of(tape, lambda c: rd.gradient_(g, c, xd))})
+
 for o in out:
     print(json.dumps(o))
 _ = time

@@ -107,16 +107,43 @@ class JacobianTape(AbstractTape):
 
 
 class HessianTape(AbstractTape):
-    """Records the *inner array tape* of ``f``.  The reference instead records a scalar
-    reverse-over-reverse program (``api/tape.jl:285-293``, ``api/Config.jl:152-156``); the engine
-    obtains the same Hessian by replaying this tape forward-over-reverse (BASELINE.json north star)."""
+    """``HessianTape(f, input)`` (``api/tape.jl:285-293``).  Two recordings of the same Hessian:
+
+    ``mode="forward"`` (default) records the *inner array tape* of ``f``; the engine replays it forward-over-reverse in Dual
+    chunks (BASELINE.json north star) — NOT the reference's mechanism, same result.
+
+    ``mode="reverse"`` records what the reference records: the OUTER scalar tape of a reverse-over-reverse sweep
+    (``api/Config.jl:152-156``; see ``nested.py``), i.e. the program ``x -> grad f(x)``; ``hessian!`` is then literally
+    ``seeded_reverse_pass!(result, output::Vector, input, tape)`` (``api/utils.jl:44-58``): one one-hot seeded reverse sweep of
+    that scalar tape per gradient component, R of them per device sweep."""
     kind = "hessian"
 
-    def __init__(self, func, input_, dtype=None):
+    def __init__(self, func, input_, dtype=None, mode="forward"):
         if isinstance(input_, (tuple, list)):
             # api/hessians.jl:103-108
             raise TypeError("Taking the Hessian of a function with multiple arguments is not yet supported")
-        super().__init__(func, input_, dtype)
+        if mode not in ("forward", "reverse"):
+            raise ValueError("mode must be 'forward' (forward-over-reverse on the array tape) or 'reverse' (the reference's "
+                             "reverse-over-reverse scalar tape)")
+        self.mode = mode
+        if mode == "forward":
+            super().__init__(func, input_, dtype)
+            return
+        from .nested import record_gradient_program
+        self.func = func
+        self.is_tuple = False
+        v = np.array(input_, dtype=np.float64 if dtype is None else dtype, order="F", copy=True)
+        if v.dtype not in (np.float32, np.float64):
+            v = v.astype(np.float64)
+        self.tape = InstructionTape(v.dtype)                     # jtp: the tape that is kept (api/tape.jl:288)
+        prog = self.tape.program
+        b = prog.add_buffer(P.BUF_TA, v.shape)
+        prog.inputs.append(b)
+        self.input = [TrackedArray(v, self.tape, b)]             # jcfg.input
+        y, grad = record_gradient_program(func, self.input[0])   # GradientTape(f, ht.input, gcfg) + seeded_reverse_pass!
+        self.primal = y.value                                    # f(x) as an outer-tape scalar
+        self.output = collect(grad, self.tape)                   # ht.output: the gradient, an array of outer-tape scalars
+        prog.output_buffer = self.output.buffer
 
     def _check_output(self):
         if not isinstance(self.output, TrackedReal):
@@ -240,12 +267,28 @@ def jacobian(ct: CompiledTape, input_):
     return jacobian_(out, ct, input_)
 
 
-def hessian_(result, ct: CompiledTape, input_, cols=None):
-    """``hessian!(result, tape::CompiledHessian, input)`` (``api/hessians.jl:86-97``).  ``cols=(b,e)``
-    restricts to a block of columns (the multi-GPU shard)."""
+def hessian_(result, ct: CompiledTape, input_, cols=None, rows=None):
+    """``hessian!(result, tape::CompiledHessian, input)`` (``api/hessians.jl:86-97``).  ``cols=(b,e)`` restricts a forward-mode
+    tape to a block of columns, ``rows=(b,e)`` a reverse-mode (reference-style) tape to a block of gradient components — the
+    multi-GPU shards; ``result`` then holds ``n x (e-b)`` resp. ``(e-b) x n``."""
     _need_compiled(ct, "hessian")
     seeded_forward_pass(ct, input_)
     n = ct.tape.input[0].size
+    if getattr(ct.tape, "mode", "forward") == "reverse":
+        if cols is not None:
+            raise ValueError("a reverse-mode HessianTape shards by rows (gradient components): pass rows=(b, e)")
+        b, e = (0, n) if rows is None else rows
+        if isinstance(result, DiffResult):
+            # seeded_reverse_pass!(DiffResult(gradient(result), hessian(result)), tape); value!(result, f(input))  (hessians.jl:92-97)
+            g = ct.handle.jacobian(0, b, e, result.derivs[1], (e - b, n), want_value=True, out_shape=(n,))
+            if not _is_device(result.derivs[0]):
+                np.copyto(result.derivs[0].reshape(-1, order="F"), np.asarray(g).reshape(-1, order="F"))
+            result.value = ct.tape.func(np.asarray(input_))
+        else:
+            ct.handle.jacobian(0, b, e, result, (e - b, n), want_value=False, out_shape=(n,))
+        return result
+    if rows is not None:
+        raise ValueError("a forward-mode HessianTape shards by columns: pass cols=(b, e)")
     b, e = (0, n) if cols is None else cols
     if isinstance(result, DiffResult):
         g, val = ct.handle.hessian(b, e, result.derivs[1], (n, e - b), want_grad=True)

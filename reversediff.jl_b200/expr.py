@@ -113,9 +113,9 @@ def _binary(code, npf):
             return x._bin(code, y)
         if isinstance(y, Sym):
             return y._bin(code, x, True)
-        if hasattr(x, "_scalar_unary") or hasattr(y, "_scalar_unary"):
-            from .tracked import _scalar_binary
-            return _scalar_binary(code, x, y)
+        for z in (x, y):                         # TrackedReal (or its nested wrapper): one binary ScalarInstruction
+            if hasattr(z, "_scalar_binary_code"):
+                return z._scalar_binary_code(code, x, y)
         return npf(x, y)
     return f
 

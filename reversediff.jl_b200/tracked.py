@@ -220,6 +220,10 @@ class TrackedReal:
     def _scalar_unary(self, code):
         return record_scalar((np.asarray([(code, 0, 0, 0)], np.int32), np.zeros(0)), self)
 
+    @staticmethod
+    def _scalar_binary_code(code, a, b):
+        return _scalar_binary(code, a, b)
+
     # SkipOptimize'd predicates (derivatives/scalars.jl:24-46): evaluated on values, nothing recorded — which is why a
     # compiled tape freezes the branch taken at record time (docs/src/api.md:39-44)
     def __lt__(self, o): return self.value < value(o)
@@ -459,6 +463,8 @@ def record_plusminus(opcode, x, y):
 def sum(x, dims=None):  # noqa: A001 - mirrors Base.sum
     """``Base.sum(::TrackedArray)`` (``linalg/reductions.jl:8-13``); ``sum(x, dims)`` records a ``sum!`` instruction
     (``:39-46``).  ``dims`` is 1-based like Julia's."""
+    if hasattr(x, "_inner_sum") and dims is None:
+        return x._inner_sum()          # Array{TrackedReal{TrackedReal}}: generic scalar fold (nested.py)
     if not isinstance(x, TrackedArray):
         return np.sum(x) if dims is None else np.sum(x, axis=tuple(d - 1 for d in np.atleast_1d(dims)), keepdims=True)
     if dims is not None:

@@ -67,3 +67,25 @@ def f_rosenbrock(x):
 
 def inputs_rosenbrock(n, dtype=np.float64, seed=2):
     return np.random.default_rng(seed).random(n).astype(dtype)
+
+
+# cfg 5 as the reference itself would record it through scalar indexing (benchmark/benchmark.jl:60-76 is a loop over x[i]):
+# every operation is one ScalarInstruction (macros.jl:84-131); scalar getindex records nothing (tracked.jl:348-351)
+def f_rosenbrock_loop(x):
+    acc = 0.0
+    for i in range(x.size // 2):
+        o, e = x[2 * i], x[2 * i + 1]
+        acc = acc + (100.0 * (e - o ** 2) ** 2 + (1.0 - o) ** 2)
+    return acc
+
+
+# benchmark/benchmark.jl:84-95
+def f_ackley_loop(x):
+    a, b, c = 20.0, -0.2, 2.0 * np.pi
+    n = x.size
+    s1 = 0.0
+    s2 = 0.0
+    for i in range(n):
+        s1 = s1 + x[i] ** 2
+        s2 = s2 + E.cos(c * x[i])
+    return -a * E.exp(b * E.sqrt(s1 / n)) - E.exp(s2 / n) + a + np.e

@@ -278,3 +278,78 @@ def test_gpu_rejects_bad_scalar_block(rd, ctx):
     blk.a_space[3] = P.SP_POOL
     with pytest.raises(Exception):
         rd.compile(tape)
+
+
+# ------------------------------------------------------------------------------------------ the reference's HessianTape
+def rosenbrock_hessian(x):
+    n = x.size
+    H = np.zeros((n, n))
+    o, e = x[0::2], x[1::2]
+    i = np.arange(0, n, 2)
+    H[i, i] = 1200 * o * o - 400 * e + 2
+    H[i, i + 1] = H[i + 1, i] = -400 * o
+    H[i + 1, i + 1] = 200
+    return H
+
+
+def test_oracle_reverse_over_reverse_hessian_tape(rd, orc):
+    """mode="reverse" records the reference's own Hessian program (api/tape.jl:285-293): the Jacobian of the recorded gradient
+    tape must equal the closed form and the independent literal restatement in oracle/scalar_tape.py."""
+    import oracle.scalar_tape as st
+    n = 8
+    x0 = np.random.default_rng(1).random(n); x = np.random.default_rng(2).random(n)
+    tape = rd.HessianTape(rosenbrock_loop, x0, mode="reverse")
+    assert all(i.opcode == rd.program.OP_SCALAR_BLOCK for i in tape.tape.program.instrs)
+    g, H = orc.OracleTape(tape.program_bytes()).jacobian([x])
+    assert relerr(H, rosenbrock_hessian(x)) < 1e-13
+    assert np.all(H[rosenbrock_hessian(x) == 0] == 0)                 # structural zeros exact
+    _, g2, H2 = st.hessian_reverse_over_reverse(lambda v: rosenbrock_loop(np.asarray(v, dtype=object)), list(x))
+    assert relerr(H, np.array(H2)) < 1e-13 and relerr(g, np.array(g2)) < 1e-13
+
+
+def test_oracle_reverse_hessian_ackley_matches_forward_mode_oracle(rd, orc):
+    n = 6
+    x0 = np.random.default_rng(1).random(n); x = np.random.default_rng(2).random(n)
+    tape = rd.HessianTape(make_ackley(rd), x0, mode="reverse")
+    g, H = orc.OracleTape(tape.program_bytes()).jacobian([x])
+    gt = rd.GradientTape(make_ackley(rd), x0)
+    Hfd = orc.hessian_dense(gt.program_bytes(), x)
+    assert relerr(H, Hfd) < 1e-6 and relerr(H, H.T) < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [2, 8, 64, 512])
+def test_gpu_reverse_over_reverse_hessian(rd, orc, n):
+    x0 = np.random.default_rng(1).random(n); x = np.random.default_rng(2).random(n)
+    tape = rd.HessianTape(rosenbrock_loop, x0, mode="reverse")
+    ct = rd.compile(tape)
+    H = np.zeros((n, n), order="F")
+    res = rd.DiffResult(0.0, np.zeros(n), H)
+    rd.hessian_(res, ct, x)
+    Href = rosenbrock_hessian(x)
+    assert relerr(H, Href) < 1e-12
+    assert np.all(H[Href == 0] == 0)
+    o, e = x[0::2], x[1::2]
+    gref = np.zeros(n); gref[0::2] = -400 * o * (e - o * o) - 2 * (1 - o); gref[1::2] = 200 * (e - o * o)
+    assert relerr(res.gradient, gref) < 1e-12
+    assert abs(res.value - np.sum(100 * (e - o * o) ** 2 + (1 - o) ** 2)) < 1e-12 * abs(res.value)
+    if n <= 64:
+        _, Ho = orc.OracleTape(tape.program_bytes()).jacobian([x])
+        assert relerr(H, Ho) < 1e-12
+    # the north star's mechanism on the array tape gives the same matrix
+    ft = rd.HessianTape(lambda v: rd.sum(rd.map_(rd.forward(lambda o_, e_: 100.0 * (e_ - o_ ** 2) ** 2 + (1.0 - o_) ** 2), v[0::2], v[1::2])), x0)
+    Hf = np.zeros((n, n), order="F")
+    rd.hessian_(Hf, rd.compile(ft), x)
+    assert relerr(H, Hf) < 1e-12
+    # row shard
+    Hb = np.zeros((n - n // 2, n), order="F")
+    rd.hessian_(Hb, ct, x, rows=(n // 2, n))
+    assert np.array_equal(Hb, H[n // 2:, :])
+
+
+@pytest.mark.gpu
+def test_gpu_forward_mode_hessian_rejects_scalar_tapes(rd):
+    tape = rd.HessianTape(rosenbrock_loop, np.random.default_rng(1).random(4))      # mode="forward" on a scalar-instruction tape
+    ct = rd.compile(tape)
+    with pytest.raises(Exception, match="scalar instructions"):
+        rd.hessian_(np.zeros((4, 4), order="F"), ct, np.ones(4))
