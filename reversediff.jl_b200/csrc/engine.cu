@@ -639,12 +639,15 @@ static int scalar_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
     for (int k = 0; k < B.n_ref; ++k)
         if (B.ref_has_export[k] && !t->dz[droot(t, B.refbufs[k])]) reached = true;
     if (!reached) return RDB_OK;                           // no adjoint reached any exported slot: every increment would add zero
+    bool leaves_zero = true;                               // pull_deriv! of a logically zero origin loads zeros: skip the loads
+    for (int k = 0; k < B.n_ref; ++k)
+        if (B.ref_has_leaf[k] && !t->dz[droot(t, B.refbufs[k])]) leaves_zero = false;
     for (int k = 0; k < B.n_ref; ++k)                      // the kernels touch single elements: the storage must hold real zeros
         OK(dmaterialize(t, B.refbufs[k], R, true));
     {
         StepTimer tm(t, "scalar_reverse", (double)(B.n + B.n_edges + 2 * B.n_leaf) * R * t->es, 0);
         int nl = 0;
-        KL(t, scalar_block_reverse<T>(S(t), B, R, &nl));
+        KL(t, scalar_block_reverse<T>(S(t), B, R, leaves_zero, &nl));
         t->launches += nl - 1;
     }
     for (int k = 0; k < B.n_ref; ++k) {
@@ -791,7 +794,7 @@ static int64_t auto_seed_block(rdb_tape *t, int64_t rows, bool tangents) {
     for (auto &b : t->bufs)
         if (b.kind != BUF_CONST && b.alias_of < 0) per_seed += b.size * (int64_t)t->es * (tangents ? 2 : 1);
     for (auto &I : t->instrs)
-        if (I.blk) per_seed += I.blk->n * (int64_t)t->es;
+        if (I.blk) per_seed += (I.blk->n_grow + 1) * (int64_t)t->es;
     int64_t budget = 24LL << 30;   // 24 GB of the 180 GB for seed-batched adjoints
     int64_t R = std::max<int64_t>(1, budget / std::max<int64_t>(per_seed, 1));
     R = std::min<int64_t>(R, 8192);

@@ -131,6 +131,10 @@ struct ScalarSeg { int lv0, lv1, grid; };     // a launch: levels [lv0, lv1) —
 struct ScalarBlock {
     int64_t n = 0, n_leaf = 0, n_edges = 0, n_exports = 0, n_rslots = 0;
     int n_ref = 0, n_flevels = 0, n_rlevels = 0;
+    // many-seed reverse sweep (tape-order streaming plan, scalar.cu): schedule blocks of 32 positions, adjoint rows that must
+    // live in global memory (read >= 2 blocks after they are produced), and planner statistics
+    int64_t n_sblocks = 0, n_grow = 0, n_near = 0, n_staged = 0, n_direct = 0;
+    size_t der_bytes = 0;
     std::vector<int32_t> refbufs;               // tape buffer ids referenced (leaf origins and export targets)
     std::vector<char> ref_has_leaf, ref_has_export;
     std::vector<int64_t> ref_export_count;      // elements of the buffer this block exports into
@@ -155,7 +159,10 @@ struct ScalarBlock {
     void **d_ext_val = nullptr, **d_ext_der = nullptr; int64_t *d_ext_size = nullptr;
     void *d_val = nullptr;                      // T[n_leaf + n] slot values
     void *d_epart = nullptr;                    // T[n_edges] partials in reverse edge order
-    void *d_der = nullptr;                      // T[n * R] adjoints of instruction outputs, [i*R + r]
+    int4 *d_recA = nullptr, *d_recB = nullptr, *d_recC = nullptr;   // per schedule position (scalar.cu, "streaming plan")
+    int2 *d_pf = nullptr;                       // per schedule block: what to prefetch into the staging buffer
+    int32_t *d_tsrc = nullptr;                  // operand codes of every edge for the streaming kernel (same order as d_esrc)
+    void *d_der = nullptr;                      // adjoints of instruction outputs: T[n x R] at [i*R + r] (R < 16), T[n_grow x R] (R >= 16)
 };
 
 // Parse + validate + plan.  buf_size[b] < 0 marks a buffer that cannot be referenced (CONST).  Returns "" or an error text.
@@ -167,6 +174,7 @@ cudaError_t scalar_block_ensure_R(ScalarBlock &B, int64_t R, size_t es);
 // forward: pull leaf values, evaluate level by level, mirror exports; returns the number of kernel launches in *launches
 template <typename T> cudaError_t scalar_block_forward(cudaStream_t, ScalarBlock &B, const double *fconst, int *launches);
 // reverse for R seeds (deriv layout of tape buffers: [elem + r*size])
-template <typename T> cudaError_t scalar_block_reverse(cudaStream_t, ScalarBlock &B, int64_t R, int *launches);
+// leaves_zero: every leaf origin's deriv is logically zero on entry (pull_deriv! would load zeros)
+template <typename T> cudaError_t scalar_block_reverse(cudaStream_t, ScalarBlock &B, int64_t R, bool leaves_zero, int *launches);
 
 }  // namespace rdb

@@ -85,48 +85,134 @@ struct RevP {
     void *der; int64_t R; int lv0, lv1;
 };
 
-// R >= 16: lanes are seeds.  grid.x = ceil(R/32); a CTA owns 32 seeds and walks every level.
+// ---- R >= 16: the streaming kernel.  Lanes are seeds; ONE warp owns 32 seeds for the whole sweep and walks the slots in the
+// reference's own order (reverse tape order; a leaf right after its last consumer).  Seeds never interact and a lane only ever
+// reads adjoints it wrote itself, so there is NO synchronisation at all - not between CTAs, not between warps.  What is left
+// is latency, and the host plan (scalar_block_build) removes it statically, per block of 32 schedule positions:
+//   * an adjoint produced in the same or the previous block is read from a 64-entry shared-memory ring (ring[pos & 63][lane]);
+//   * an adjoint produced earlier ("far") lives in global memory ([row][seed], only slots with a far reader get a row) and is
+//     brought into a shared-memory staging buffer by cp.async one block AHEAD of its use, as are the adjoints that later
+//     instructions pushed into exported slots; the copy overlaps the 32 steps of the running block;
+//   * the records of the next block (one per lane, coalesced) and their partials are loaded at the same time.
+// A step therefore costs a shared-memory round trip plus its arithmetic, whatever the dataflow looks like.
+constexpr int kBlk = 32;              // schedule positions per block (= lanes that load one record each)
+constexpr int kStageF = 32;           // staged operands per block
+constexpr int kRing = 64;             // two blocks of adjoints
+constexpr int kInl = 4;               // edges held in the record; the rest loop over tsrc/epart
+constexpr unsigned kSrcDirect = 0u, kSrcRing = 1u, kSrcStage = 2u;
+inline int src_code(unsigned kind, unsigned payload) { return (int)((kind << 30) | payload); }
+
+struct StreamP {
+    const int4 *recA, *recB, *recC; const int2 *pf; const int32_t *tsrc; const void *epart;
+    const int64_t *xoff; const int32_t *xord; const int64_t *xelem;
+    void *const *ext_der; const int64_t *ext_size;
+    void *der; int64_t R; int64_t n_blocks; int leaves_zero;
+};
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// record of schedule position q:
+//   A = (slot: >= 0 instruction output, < 0 leaf ~l, kNone padding; source of edge 0; source of edge 1; edge count | flags << 24)
+//       flags: 1 = the slot has exports, 2 = its (single) export is staged
+//   B = (first edge in tsrc/epart; instruction: global row or -1 | leaf: ordinal of the origin buffer;
+//        instruction: staging entry of the export | leaf: element, low word; leaf: element, high word)
+//   C = (source of edge 2, source of edge 3, 0, 0)
+//   sources: kind << 30 | payload - kSrcRing: ring entry, kSrcStage: staging entry, kSrcDirect: global row
 template <typename T>
-__global__ void __launch_bounds__(256) k_scalar_reverse_seeds(const RevP P) {
-    T *der = reinterpret_cast<T *>(P.der);
-    const T *epart = reinterpret_cast<const T *>(P.epart);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+__global__ void __launch_bounds__(32) k_scalar_reverse_stream(const StreamP P) {
+    __shared__ __align__(16) T ring[kRing][32];
+    __shared__ __align__(16) T stage[2][kStageF][32];
+    __shared__ __align__(16) T spart[2][kBlk][kInl];
+    __shared__ int4 sA[2][kBlk], sB[2][kBlk], sC[2][kBlk];
+    __shared__ int2 spf[2][kStageF];
+    const int lane = threadIdx.x;
     const int64_t R = P.R, r = blockIdx.x * 32LL + lane;
     const bool active = r < R;
-    for (int lv = P.lv0; lv < P.lv1; ++lv) {
-        const int64_t j0 = P.rlevel_off[lv], j1 = P.rlevel_off[lv + 1];
-        for (int64_t j = j0 + warp; j < j1; j += W) {
-            const int s = P.rslot[j];
-            const int64_t e0 = P.reoff[j], e1 = P.reoff[j + 1];
-            T acc = (T)0;
-            T *dst;
-            if (s >= 0) {
-                // adjoints that instructions AFTER the block pushed into an exported slot (one TrackedReal, one deriv field)
-                for (int64_t x = P.xoff[s]; x < P.xoff[s + 1]; ++x) {
-                    const int o = P.xord[x];
-                    T *p = reinterpret_cast<T *>(P.ext_der[o]) + P.xelem[x] + r * P.ext_size[o];
-                    if (active) { acc = acc + *p; *p = (T)0; }                             // ... and unseed!(output)
-                }
-                dst = der + (int64_t)s * R + r;
-            } else {
-                const int l = ~s, o = P.leaf_ord[l];
-                dst = reinterpret_cast<T *>(P.ext_der[o]) + P.leaf_elem[l] + r * P.ext_size[o];   // origin.deriv[index]: pull_deriv!
-                if (active) acc = *dst;
-            }
-            for (int64_t e = e0; e < e1; e += 32) {
-                const int cnt = (int)min((int64_t)32, e1 - e);
-                const int src_l = lane < cnt ? P.esrc[e + lane] : 0;
-                const T part_l = lane < cnt ? epart[e + lane] : (T)0;
-#pragma unroll 4
-                for (int k = 0; k < cnt; ++k) {
-                    const int c = __shfl_sync(0xffffffffu, src_l, k);
-                    const T p = __shfl_sync(0xffffffffu, part_l, k);
-                    if (active) acc = acc + der[(int64_t)c * R + r] * p;                    // increment_deriv!(s, deriv(out_c) * partial)
-                }
-            }
-            if (active) *dst = acc;                                                         // push_deriv! / the slot's final adjoint
+    const int64_t rr = active ? r : 0;                 // idle lanes of a ragged last warp follow seed 0 and never store
+    T *der = reinterpret_cast<T *>(P.der);
+    const T *epart = reinterpret_cast<const T *>(P.epart);
+
+    auto load_block = [&](int64_t b, int buf) {
+        const int64_t q = b * kBlk + lane;
+        const int4 A = P.recA[q], Bq = P.recB[q];
+        sA[buf][lane] = A; sB[buf][lane] = Bq; sC[buf][lane] = P.recC[q];
+        const int ne = A.w & 0xffffff;
+#pragma unroll
+        for (int k = 0; k < kInl; ++k) spart[buf][lane][k] = k < ne ? epart[Bq.x + k] : (T)0;
+        spf[buf][lane] = P.pf[b * kStageF + lane];
+        __syncwarp();
+        for (int f = 0; f < kStageF; ++f) {
+            const int2 e = spf[buf][f];
+            if (e.x == -1) break;
+            const T *src = e.x == -2 ? der + (int64_t)e.y * R + rr
+                                     : reinterpret_cast<const T *>(P.ext_der[e.x]) + e.y + rr * P.ext_size[e.x];
+            cp_async_small<sizeof(T)>(&stage[buf][f][lane], src);
         }
-        if (lv + 1 < P.lv1) __syncthreads();
+        cp_async_commit();
+    };
+
+    if (P.n_blocks > 0) load_block(0, 0);
+    cp_async_wait_all();
+    __syncwarp();
+    for (int64_t b = 0; b < P.n_blocks; ++b) {
+        const int cur = (int)(b & 1);
+        if (b + 1 < P.n_blocks) load_block(b + 1, cur ^ 1);
+        auto rd = [&](int c) -> T {
+            const unsigned kind = (unsigned)c >> 30, pl = (unsigned)c & 0x3fffffffu;
+            if (kind == kSrcRing) return ring[pl][lane];
+            if (kind == kSrcStage) return stage[cur][pl][lane];
+            return der[(int64_t)pl * R + rr];
+        };
+#pragma unroll 2
+        for (int k = 0; k < kBlk; ++k) {
+            const int4 A = sA[cur][k];
+            if (A.x == kNone) break;                   // padding only follows the last slot
+            const int4 Bq = sB[cur][k];
+            const int ne = A.w & 0xffffff, fl = (int)((unsigned)A.w >> 24);
+            T acc = (T)0;
+            T *dst = nullptr;
+            if (A.x >= 0) {
+                if (fl & 1) {
+                    // adjoints that instructions AFTER the block pushed into an exported slot (one TrackedReal, one deriv field)
+                    if (fl & 2) {
+                        const int2 e = spf[cur][Bq.z];
+                        acc = acc + stage[cur][Bq.z][lane];
+                        if (active) (reinterpret_cast<T *>(P.ext_der[e.x]) + e.y)[r * P.ext_size[e.x]] = (T)0;   // unseed!(output)
+                    } else {
+                        for (int64_t x = P.xoff[A.x]; x < P.xoff[A.x + 1]; ++x) {
+                            const int o = P.xord[x];
+                            T *p = reinterpret_cast<T *>(P.ext_der[o]) + P.xelem[x] + rr * P.ext_size[o];
+                            acc = acc + *p;
+                            if (active) *p = (T)0;
+                        }
+                    }
+                }
+                if (Bq.y >= 0) dst = der + (int64_t)Bq.y * R + rr;
+            } else {
+                const int64_t elem = (int64_t)(unsigned)Bq.z | ((int64_t)Bq.w << 32);
+                dst = reinterpret_cast<T *>(P.ext_der[Bq.y]) + elem + rr * P.ext_size[Bq.y];   // origin.deriv[index]
+                if (!P.leaves_zero) acc = *dst;                                                  // pull_deriv!
+            }
+            // increment_deriv!(slot, deriv(out_c) * partial) for every consumer c, in the reference's order
+            if (ne > 0) acc = acc + rd(A.y) * spart[cur][k][0];
+            if (ne > 1) acc = acc + rd(A.z) * spart[cur][k][1];
+            if (ne > 2) {
+                const int4 C = sC[cur][k];
+                acc = acc + rd(C.x) * spart[cur][k][2];
+                if (ne > 3) acc = acc + rd(C.y) * spart[cur][k][3];
+#pragma unroll 4
+                for (int e = kInl; e < ne; ++e) acc = acc + rd(P.tsrc[Bq.x + e]) * epart[Bq.x + e];
+            }
+            ring[(b * kBlk + k) & (kRing - 1)][lane] = acc;
+            if (dst && active) *dst = acc;             // the slot's final adjoint (push_deriv! for a leaf)
+        }
+        cp_async_wait_all();
+        __syncwarp();
     }
 }
 
@@ -342,6 +428,76 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
             }
         }
     }
+    // streaming plan for the many-seed reverse kernel (k_scalar_reverse_stream) -------------------------------------------------
+    // schedule: instructions in reverse tape order, every leaf right after its lowest consumer (all its increments are in by then)
+    const int64_t nblk = (ns + kBlk - 1) / kBlk, npos = nblk * kBlk;
+    std::vector<int4> recA(npos, make_int4(kNone, 0, 0, 0)), recB(npos, make_int4(0, -1, 0, 0)), recC(npos, make_int4(0, 0, 0, 0));
+    std::vector<int2> pf(nblk * kStageF, make_int2(-1, 0));
+    std::vector<int32_t> tsrc(ne, 0);
+    B.n_sblocks = nblk; B.n_grow = 0; B.n_near = B.n_staged = B.n_direct = 0;
+    {
+        std::vector<int64_t> lowc(nl, -1), lhead(n + 1, 0);
+        for (int64_t i = 0; i < n; ++i) {
+            if (kind_a[i] == 2 && lowc[code_a[i]] < 0) lowc[code_a[i]] = i;
+            if (kind_b[i] == 2 && lowc[code_b[i]] < 0) lowc[code_b[i]] = i;
+        }
+        for (int64_t l = 0; l < nl; ++l) lhead[lowc[l] + 1]++;
+        for (int64_t i = 0; i < n; ++i) lhead[i + 1] += lhead[i];
+        std::vector<int64_t> lsorted(nl), fill(lhead.begin(), lhead.end() - 1);
+        for (int64_t l = 0; l < nl; ++l) lsorted[fill[lowc[l]]++] = l;
+        std::vector<int64_t> order;
+        order.reserve(ns);
+        std::vector<int64_t> qpos(ns);
+        for (int64_t i = n - 1; i >= 0; --i) {
+            qpos[i] = (int64_t)order.size(); order.push_back(i);
+            for (int64_t x = lhead[i]; x < lhead[i + 1]; ++x) { qpos[n + lsorted[x]] = (int64_t)order.size(); order.push_back(n + lsorted[x]); }
+        }
+        // pass 1: which instruction outputs are read two or more blocks after they are produced -> they need a global row
+        std::vector<int32_t> grow(n, -1);
+        for (int64_t q = 0; q < ns; ++q) {
+            const int64_t sl = order[q], e0 = reoff[rpos[sl]];
+            for (int64_t k = 0; k < ecount[sl]; ++k) {
+                const int c = esrc[e0 + k];
+                if (q / kBlk - qpos[c] / kBlk > 1 && grow[c] < 0) grow[c] = 0;
+            }
+        }
+        for (int64_t i = 0; i < n; ++i) if (grow[i] == 0) grow[i] = (int32_t)B.n_grow++;
+        // pass 2: records, operand codes, staging lists
+        std::vector<int> nstage(nblk, 0);
+        for (int64_t q = 0; q < ns; ++q) {
+            const int64_t sl = order[q], e0 = reoff[rpos[sl]], cnt = ecount[sl], blk = q / kBlk;
+            if (cnt >= (1 << 24)) return "scalar block: a slot has too many consumers";
+            int inl[kInl] = {0, 0, 0, 0};
+            for (int64_t k = 0; k < cnt; ++k) {
+                const int c = esrc[e0 + k];
+                int code;
+                if (blk - qpos[c] / kBlk <= 1) { code = src_code(kSrcRing, (unsigned)(qpos[c] & (kRing - 1))); B.n_near++; }
+                else if (k < kInl && nstage[blk] < kStageF) {
+                    const int f = nstage[blk]++;
+                    pf[blk * kStageF + f] = make_int2(-2, grow[c]);
+                    code = src_code(kSrcStage, (unsigned)f); B.n_staged++;
+                } else { code = src_code(kSrcDirect, (unsigned)grow[c]); B.n_direct++; }
+                tsrc[e0 + k] = code;
+                if (k < kInl) inl[k] = code;
+            }
+            int flags = 0, xstage = 0;
+            if (sl < n && xoff[sl + 1] > xoff[sl]) {
+                flags |= 1;
+                if (xoff[sl + 1] - xoff[sl] == 1 && xelem[xoff[sl]] < INT_MAX && nstage[blk] < kStageF) {
+                    xstage = nstage[blk]++;
+                    pf[blk * kStageF + xstage] = make_int2(xord[xoff[sl]], (int)xelem[xoff[sl]]);
+                    flags |= 2;
+                }
+            }
+            recA[q] = make_int4(sl < n ? (int)sl : ~(int)(sl - n), inl[0], inl[1], (int)cnt | (flags << 24));
+            if (sl < n) recB[q] = make_int4((int)e0, grow[sl], xstage, 0);
+            else {
+                const int64_t l = sl - n;
+                recB[q] = make_int4((int)e0, leaf_ord[l], (int)(uint32_t)(leaf_elem[l] & 0xffffffffLL), (int)(leaf_elem[l] >> 32));
+            }
+            recC[q] = make_int4(inl[2], inl[3], 0, 0);
+        }
+    }
     // forward instruction table, level-sorted ------------------------------------------------------------------------------------
     std::vector<int4> finstr(n);
     {
@@ -362,7 +518,7 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
     auto pad = [](size_t b) { return (b + 15) & ~size_t(15); };
     size_t bytes = pad(n * 16) + pad((nfl + 1) * 8) + pad(h_ops.size() * 16) + pad(nex * 16) + pad(2 * n * 4) + pad(nl * 4) + pad(nl * 8) +
                    pad(nexp * 4) * 2 + pad(nexp * 8) + pad(ns * 4) + pad((ns + 1) * 8) + pad(ne * 4) + pad((nrl + 1) * 8) + pad((n + 1) * 8) +
-                   pad(nexp * 4) + pad(nexp * 8) + pad(nref * 8) * 3 + 256;
+                   pad(nexp * 4) + pad(nexp * 8) + pad(nref * 8) * 3 + pad(npos * 16) * 3 + pad(nblk * kStageF * 8) + pad(ne * 4) + 512;
     std::vector<uint8_t> host(bytes, 0);
     if (cudaMalloc(&B.d_tables, bytes) != cudaSuccess) { cudaGetLastError(); return "scalar block: out of device memory (tables)"; }
     uint8_t *hp = host.data();
@@ -379,6 +535,7 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
     put(B.d_exp_slot, exp_slot); put(B.d_exp_ord, exp_ord); put(B.d_exp_elem, exp_elem);
     put(B.d_rslot, rslot); put(B.d_reoff, reoff); put(B.d_esrc, esrc); put(B.d_rlevel_off, rlevel_off);
     put(B.d_xoff, xoff); put(B.d_xord, xord); put(B.d_xelem, xelem);
+    put(B.d_recA, recA); put(B.d_recB, recB); put(B.d_recC, recC); put(B.d_pf, pf); put(B.d_tsrc, tsrc);
     std::vector<void *> nulls(nref, nullptr); std::vector<int64_t> zeros(nref, 0);
     put(B.d_ext_val, nulls); put(B.d_ext_der, nulls); put(B.d_ext_size, zeros);
     if ((size_t)(hp - host.data()) > bytes) return "scalar block: internal table overflow";
@@ -394,6 +551,7 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
 void scalar_block_free(ScalarBlock &B) {
     cudaFree(B.d_tables); cudaFree(B.d_val); cudaFree(B.d_epart); cudaFree(B.d_der);
     B.d_tables = B.d_val = B.d_epart = B.d_der = nullptr;
+    B.der_bytes = 0;
 }
 
 cudaError_t scalar_block_upload_ext(ScalarBlock &B, cudaStream_t s) {
@@ -405,12 +563,19 @@ cudaError_t scalar_block_upload_ext(ScalarBlock &B, cudaStream_t s) {
 }
 
 cudaError_t scalar_block_ensure_R(ScalarBlock &B, int64_t R, size_t es) {
-    if (R <= B.R_alloc) return cudaSuccess;
-    cudaFree(B.d_der);
-    B.d_der = nullptr;
-    cudaError_t e = cudaMalloc(&B.d_der, std::max<size_t>((size_t)B.n * R * es, 16));
-    if (e == cudaSuccess) B.R_alloc = R;
-    return e;
+    // R < 16: the slot-lane kernel indexes adjoints by instruction ([i*R + r]); R >= 16: the streaming kernel only keeps the rows
+    // that are read from global memory ([row*R + r])
+    const int64_t few = std::min<int64_t>(R, 15);
+    const size_t need = std::max<size_t>(std::max<size_t>((size_t)B.n * few, R >= 16 ? (size_t)B.n_grow * R : 0) * es, 16);
+    if (need > B.der_bytes) {
+        cudaFree(B.d_der);
+        B.d_der = nullptr; B.der_bytes = 0;
+        cudaError_t e = cudaMalloc(&B.d_der, need);
+        if (e != cudaSuccess) return e;
+        B.der_bytes = need;
+    }
+    B.R_alloc = std::max(B.R_alloc, R);
+    return cudaSuccess;
 }
 
 template <typename T>
@@ -436,14 +601,16 @@ cudaError_t scalar_block_forward(cudaStream_t s, ScalarBlock &B, const double *f
 }
 
 template <typename T>
-cudaError_t scalar_block_reverse(cudaStream_t s, ScalarBlock &B, int64_t R, int *launches) {
-    RevP P{B.d_rslot, B.d_reoff, B.d_esrc, B.d_epart, B.d_rlevel_off, B.d_xoff, B.d_xord, B.d_xelem, B.d_leaf_ord, B.d_leaf_elem,
-           B.d_ext_der, B.d_ext_size, B.d_der, R, 0, B.n_rlevels};
+cudaError_t scalar_block_reverse(cudaStream_t s, ScalarBlock &B, int64_t R, bool leaves_zero, int *launches) {
     int nl = 0;
     if (R >= 16) {
-        k_scalar_reverse_seeds<T><<<(unsigned)((R + 31) / 32), 256, 0, s>>>(P);
+        StreamP P{B.d_recA, B.d_recB, B.d_recC, B.d_pf, B.d_tsrc, B.d_epart, B.d_xoff, B.d_xord, B.d_xelem,
+                  B.d_ext_der, B.d_ext_size, B.d_der, R, B.n_sblocks, leaves_zero ? 1 : 0};
+        k_scalar_reverse_stream<T><<<(unsigned)((R + 31) / 32), 32, 0, s>>>(P);
         ++nl;
     } else {
+        RevP P{B.d_rslot, B.d_reoff, B.d_esrc, B.d_epart, B.d_rlevel_off, B.d_xoff, B.d_xord, B.d_xelem, B.d_leaf_ord, B.d_leaf_elem,
+               B.d_ext_der, B.d_ext_size, B.d_der, R, 0, B.n_rlevels};
         for (const ScalarSeg &g : B.rsegs) {
             P.lv0 = g.lv0; P.lv1 = g.lv1;
             k_scalar_reverse_slots<T><<<g.grid, kFwdThreads, 0, s>>>(P);
@@ -456,7 +623,7 @@ cudaError_t scalar_block_reverse(cudaStream_t s, ScalarBlock &B, int64_t R, int 
 
 template cudaError_t scalar_block_forward<double>(cudaStream_t, ScalarBlock &, const double *, int *);
 template cudaError_t scalar_block_forward<float>(cudaStream_t, ScalarBlock &, const double *, int *);
-template cudaError_t scalar_block_reverse<double>(cudaStream_t, ScalarBlock &, int64_t, int *);
-template cudaError_t scalar_block_reverse<float>(cudaStream_t, ScalarBlock &, int64_t, int *);
+template cudaError_t scalar_block_reverse<double>(cudaStream_t, ScalarBlock &, int64_t, bool, int *);
+template cudaError_t scalar_block_reverse<float>(cudaStream_t, ScalarBlock &, int64_t, bool, int *);
 
 }  // namespace rdb

@@ -269,6 +269,66 @@ def test_gpu_jacobian_of_tracked_real_array(rd, orc, n, seed_block):
     assert np.array_equal(Jb, J[n // 2:, :])
 
 
+def make_hubfun(rd):
+    def hubfun(x):
+        """R^n -> R^n with everything the streaming reverse kernel plans around: two hub slots consumed by every output (fan-out far
+        beyond the four in-record edges, read hundreds of schedule positions after they are produced), a running chain, values
+        produced early and consumed late, one slot exported to two outputs."""
+        n = x.size
+        hub = x[0] * x[1] + rd.exp(x[2] * 0.5)         # hub slot
+        early = [rd.sin(x[i]) * hub for i in range(n)]  # produced first ...
+        acc = x[3] * 1.0
+        out = []
+        for i in range(n):
+            acc = acc * 0.9 + x[i] * hub               # chain through the whole tape
+            out.append(early[n - 1 - i] * acc + x[(i + 5) % n] / (1.5 + rd.cos(hub)))   # ... consumed last-to-first
+        out[4] = out[7]                                # one TrackedReal in two output elements
+        return out
+    return hubfun
+
+
+def hubfun_np(x):
+    n = x.size
+    hub = x[0] * x[1] + np.exp(x[2] * 0.5)
+    early = np.sin(x) * hub
+    acc = x[3] * 1.0
+    out = np.zeros(n)
+    for i in range(n):
+        acc = acc * 0.9 + x[i] * hub
+        out[i] = early[n - 1 - i] * acc + x[(i + 5) % n] / (1.5 + np.cos(hub))
+    out[4] = out[7]
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,seed_block", [(24, 0), (100, 0), (100, 37), (333, 0), (333, 64)])
+def test_gpu_jacobian_hub_chain_long_range(rd, orc, dtype, n, seed_block):
+    """Seed-lane streaming kernel (R >= 16): ring / staged / direct operand sources, staged and looped exports, ragged warps."""
+    x0 = np.random.default_rng(1).random(n).astype(dtype); x = np.random.default_rng(2).random(n).astype(dtype)
+    tape = rd.JacobianTape(make_hubfun(rd), x0)
+    ct = rd.compile(tape, seed_block=seed_block)
+    J = np.zeros((n, n), dtype=dtype, order="F")
+    res = rd.DiffResult(np.zeros(n, dtype=dtype), J)
+    rd.jacobian_(res, ct, x)
+    val, Jo = orc.OracleTape(tape.program_bytes()).jacobian([x])
+    assert relerr(res.value, val) < TOL[dtype]
+    assert relerr(J, Jo) < TOL[dtype]
+    if dtype is np.float64:
+        assert relerr(res.value, hubfun_np(x)) < 1e-12
+        h = 1e-6
+        for j in (0, 2, 3, n - 1):                       # central differences on a few columns
+            xp = x.copy(); xm = x.copy(); xp[j] += h; xm[j] -= h
+            assert relerr(J[:, j], (hubfun_np(xp) - hubfun_np(xm)) / (2 * h)) < 1e-6
+    # a second sweep on the same compiled tape (ring / staging state must not leak) and a row shard
+    J2 = np.zeros((n, n), dtype=dtype, order="F")
+    rd.jacobian_(J2, ct, x)
+    assert np.array_equal(J2, J)
+    Jb = np.zeros((n - n // 3, n), dtype=dtype, order="F")
+    rd.jacobian_(Jb, ct, x, rows=(n // 3, n))
+    assert np.array_equal(Jb, J[n // 3:, :])
+
+
 @pytest.mark.gpu
 def test_gpu_rejects_bad_scalar_block(rd, ctx):
     P = rd.program
