@@ -797,7 +797,11 @@ static int64_t auto_seed_block(rdb_tape *t, int64_t rows, bool tangents) {
         if (I.blk) per_seed += (I.blk->n_grow + 1) * (int64_t)t->es;
     int64_t budget = 24LL << 30;   // 24 GB of the 180 GB for seed-batched adjoints
     int64_t R = std::max<int64_t>(1, budget / std::max<int64_t>(per_seed, 1));
-    R = std::min<int64_t>(R, 8192);
+    // scalar-instruction tapes: the streaming reverse kernel costs the same for any number of seeds up to ~19k (one warp per 32
+    // seeds, 4 x 148 schedulers), so take them all at once; array tapes: GEMM batches of 8192 columns are already at peak
+    bool scalar_only = !t->instrs.empty();
+    for (auto &I : t->instrs) if (!I.blk) scalar_only = false;
+    R = std::min<int64_t>(R, scalar_only ? 32768 : 8192);
     return std::min(R, rows);
 }
 

@@ -159,7 +159,7 @@ struct ScalarBlock {
     void **d_ext_val = nullptr, **d_ext_der = nullptr; int64_t *d_ext_size = nullptr;
     void *d_val = nullptr;                      // T[n_leaf + n] slot values
     void *d_epart = nullptr;                    // T[n_edges] partials in reverse edge order
-    int4 *d_recA = nullptr, *d_recB = nullptr, *d_recC = nullptr;   // per schedule position (scalar.cu, "streaming plan")
+    int4 *d_recA = nullptr, *d_recB = nullptr, *d_recC = nullptr, *d_recD = nullptr;   // per schedule position (scalar.cu, "streaming plan")
     int2 *d_pf = nullptr;                       // per schedule block: what to prefetch into the staging buffer
     int32_t *d_tsrc = nullptr;                  // operand codes of every edge for the streaming kernel (same order as d_esrc)
     void *d_der = nullptr;                      // adjoints of instruction outputs: T[n x R] at [i*R + r] (R < 16), T[n_grow x R] (R >= 16)

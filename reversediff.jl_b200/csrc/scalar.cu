@@ -24,6 +24,8 @@
 #include <algorithm>
 #include <climits>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include "kernels.h"
@@ -89,21 +91,27 @@ struct RevP {
 // reference's own order (reverse tape order; a leaf right after its last consumer).  Seeds never interact and a lane only ever
 // reads adjoints it wrote itself, so there is NO synchronisation at all - not between CTAs, not between warps.  What is left
 // is latency, and the host plan (scalar_block_build) removes it statically, per block of 32 schedule positions:
-//   * an adjoint produced in the same or the previous block is read from a 64-entry shared-memory ring (ring[pos & 63][lane]);
+//   * the adjoint produced by the step right before is forwarded in a register;
+//   * an adjoint produced in the same or the previous block is read from a 64-entry shared-memory ring (row = position & 63);
 //   * an adjoint produced earlier ("far") lives in global memory ([row][seed], only slots with a far reader get a row) and is
 //     brought into a shared-memory staging buffer by cp.async one block AHEAD of its use, as are the adjoints that later
 //     instructions pushed into exported slots; the copy overlaps the 32 steps of the running block;
-//   * the records of the next block (one per lane, coalesced) and their partials are loaded at the same time.
-// A step therefore costs a shared-memory round trip plus its arithmetic, whatever the dataflow looks like.
+//   * the records of the next block (one per lane, coalesced) and their partials are loaded at the same time;
+//   * the step loop is software-pipelined by hand: the record of step k+2 and the shared-memory operands of step k+1 are
+//     loaded while step k computes (the plan guarantees they do not depend on step k except through the forwarded register).
+// A step with at most two consumers, no exports and no leaf (the bulk of any scalar tape) is ~25 branch-free instructions; the
+// rest takes one uniform branch into a general path.
 constexpr int kBlk = 32;              // schedule positions per block (= lanes that load one record each)
 constexpr int kStageF = 32;           // staged operands per block
 constexpr int kRing = 64;             // two blocks of adjoints
-constexpr int kInl = 4;               // edges held in the record; the rest loop over tsrc/epart
-constexpr unsigned kSrcDirect = 0u, kSrcRing = 1u, kSrcStage = 2u;
+constexpr int kInl = 4;               // edges whose partials are staged with the record; the rest loop over tsrc/epart
+constexpr unsigned kSrcDirect = 0u, kSrcSmem = 1u, kSrcPrev = 3u;
 inline int src_code(unsigned kind, unsigned payload) { return (int)((kind << 30) | payload); }
+constexpr int kM_E0 = 1, kM_E1 = 2, kM_Prev0 = 4, kM_Prev1 = 8, kM_Rare = 16, kM_Dir0 = 64, kM_Dir1 = 128, kM_Exp = 256,
+              kM_ExpStaged = 512, kM_Leaf = 1024;
 
 struct StreamP {
-    const int4 *recA, *recB, *recC; const int2 *pf; const int32_t *tsrc; const void *epart;
+    const int4 *recA, *recB, *recC, *recD; const int2 *pf; const int32_t *tsrc; const void *epart;
     const int64_t *xoff; const int32_t *xord; const int64_t *xelem;
     void *const *ext_der; const int64_t *ext_size;
     void *der; int64_t R; int64_t n_blocks; int leaves_zero;
@@ -116,19 +124,17 @@ __device__ __forceinline__ void cp_async_small(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// record of schedule position q:
-//   A = (slot: >= 0 instruction output, < 0 leaf ~l, kNone padding; source of edge 0; source of edge 1; edge count | flags << 24)
-//       flags: 1 = the slot has exports, 2 = its (single) export is staged
-//   B = (first edge in tsrc/epart; instruction: global row or -1 | leaf: ordinal of the origin buffer;
-//        instruction: staging entry of the export | leaf: element, low word; leaf: element, high word)
-//   C = (source of edge 2, source of edge 3, 0, 0)
-//   sources: kind << 30 | payload - kSrcRing: ring entry, kSrcStage: staging entry, kSrcDirect: global row
+// record of schedule position q (shared-memory rows: [0, 64) ring, [64, 96) staging buffer of even blocks, [96, 128) of odd blocks):
+//   A = (byte offset of the row holding the adjoint of edge 0's consumer; same for edge 1; kM_* flags; global row of this slot or -1)
+//   B = (first edge in tsrc/epart; number of edges; instruction id (exports); staging entry of the export)
+//   C = (source of edge 2; source of edge 3; global row read by edge 0 if kM_Dir0; by edge 1 if kM_Dir1)
+//   D = leaf: (ordinal of the origin buffer; element, low word; element, high word; 0)
+//   sources: kind << 30 | payload - kSrcSmem: shared-memory row, kSrcDirect: global row, kSrcPrev: the previous step's adjoint
 template <typename T>
 __global__ void __launch_bounds__(32) k_scalar_reverse_stream(const StreamP P) {
-    __shared__ __align__(16) T ring[kRing][32];
-    __shared__ __align__(16) T stage[2][kStageF][32];
-    __shared__ __align__(16) T spart[2][kBlk][kInl];
-    __shared__ int4 sA[2][kBlk], sB[2][kBlk], sC[2][kBlk];
+    __shared__ __align__(16) T comb[kRing + 2 * kStageF][32];
+    __shared__ __align__(16) T spart[2][kBlk + 2][kInl];
+    __shared__ int4 sA[2][kBlk + 2], sB[2][kBlk], sC[2][kBlk], sD[2][kBlk];
     __shared__ int2 spf[2][kStageF];
     const int lane = threadIdx.x;
     const int64_t R = P.R, r = blockIdx.x * 32LL + lane;
@@ -136,14 +142,17 @@ __global__ void __launch_bounds__(32) k_scalar_reverse_stream(const StreamP P) {
     const int64_t rr = active ? r : 0;                 // idle lanes of a ragged last warp follow seed 0 and never store
     T *der = reinterpret_cast<T *>(P.der);
     const T *epart = reinterpret_cast<const T *>(P.epart);
+    if (lane < 2) {                                    // the two records the pipeline reads past the end of a block
+        sA[0][kBlk + lane] = sA[1][kBlk + lane] = make_int4(0, 0, 0, -1);
+        for (int k = 0; k < kInl; ++k) spart[0][kBlk + lane][k] = spart[1][kBlk + lane][k] = (T)0;
+    }
 
     auto load_block = [&](int64_t b, int buf) {
         const int64_t q = b * kBlk + lane;
-        const int4 A = P.recA[q], Bq = P.recB[q];
-        sA[buf][lane] = A; sB[buf][lane] = Bq; sC[buf][lane] = P.recC[q];
-        const int ne = A.w & 0xffffff;
+        const int4 Bq = P.recB[q];
+        sA[buf][lane] = P.recA[q]; sB[buf][lane] = Bq; sC[buf][lane] = P.recC[q]; sD[buf][lane] = P.recD[q];
 #pragma unroll
-        for (int k = 0; k < kInl; ++k) spart[buf][lane][k] = k < ne ? epart[Bq.x + k] : (T)0;
+        for (int k = 0; k < kInl; ++k) spart[buf][lane][k] = k < Bq.y ? epart[Bq.x + k] : (T)0;
         spf[buf][lane] = P.pf[b * kStageF + lane];
         __syncwarp();
         for (int f = 0; f < kStageF; ++f) {
@@ -151,7 +160,7 @@ __global__ void __launch_bounds__(32) k_scalar_reverse_stream(const StreamP P) {
             if (e.x == -1) break;
             const T *src = e.x == -2 ? der + (int64_t)e.y * R + rr
                                      : reinterpret_cast<const T *>(P.ext_der[e.x]) + e.y + rr * P.ext_size[e.x];
-            cp_async_small<sizeof(T)>(&stage[buf][f][lane], src);
+            cp_async_small<sizeof(T)>(&comb[kRing + buf * kStageF + f][lane], src);
         }
         cp_async_commit();
     };
@@ -159,32 +168,45 @@ __global__ void __launch_bounds__(32) k_scalar_reverse_stream(const StreamP P) {
     if (P.n_blocks > 0) load_block(0, 0);
     cp_async_wait_all();
     __syncwarp();
+    const char *base = reinterpret_cast<const char *>(&comb[0][lane]);
+    T prev = (T)0;
     for (int64_t b = 0; b < P.n_blocks; ++b) {
         const int cur = (int)(b & 1);
         if (b + 1 < P.n_blocks) load_block(b + 1, cur ^ 1);
         auto rd = [&](int c) -> T {
             const unsigned kind = (unsigned)c >> 30, pl = (unsigned)c & 0x3fffffffu;
-            if (kind == kSrcRing) return ring[pl][lane];
-            if (kind == kSrcStage) return stage[cur][pl][lane];
+            if (kind == kSrcSmem) return comb[pl][lane];
+            if (kind == kSrcPrev) return prev;
             return der[(int64_t)pl * R + rr];
         };
-#pragma unroll 2
+        int4 r0 = sA[cur][0], r1 = sA[cur][1];
+        T p00 = spart[cur][0][0], p01 = spart[cur][0][1], p10 = spart[cur][1][0], p11 = spart[cur][1][1];
+        T v00 = *reinterpret_cast<const T *>(base + r0.x), v01 = *reinterpret_cast<const T *>(base + r0.y);
+        T *ringrow = &comb[cur * kBlk][lane];
+#pragma unroll 4
         for (int k = 0; k < kBlk; ++k) {
-            const int4 A = sA[cur][k];
-            if (A.x == kNone) break;                   // padding only follows the last slot
-            const int4 Bq = sB[cur][k];
-            const int ne = A.w & 0xffffff, fl = (int)((unsigned)A.w >> 24);
+            const int4 r2 = sA[cur][k + 2];
+            const T p20 = spart[cur][k + 2][0], p21 = spart[cur][k + 2][1];
+            const T v10 = *reinterpret_cast<const T *>(base + r1.x), v11 = *reinterpret_cast<const T *>(base + r1.y);
+            const int meta = r0.z;
+            T x0 = (meta & kM_Prev0) ? prev : v00, x1 = (meta & kM_Prev1) ? prev : v01;
             T acc = (T)0;
-            T *dst = nullptr;
-            if (A.x >= 0) {
-                if (fl & 1) {
+            if (meta & kM_Rare) {
+                const int4 Bq = sB[cur][k], C = sC[cur][k];
+                T *dst = nullptr;
+                if (meta & kM_Leaf) {
+                    const int4 D = sD[cur][k];
+                    const int64_t elem = (int64_t)(unsigned)D.y | ((int64_t)D.z << 32);
+                    dst = reinterpret_cast<T *>(P.ext_der[D.x]) + elem + rr * P.ext_size[D.x];      // origin.deriv[index]
+                    if (!P.leaves_zero) acc = *dst;                                                  // pull_deriv!
+                } else if (meta & kM_Exp) {
                     // adjoints that instructions AFTER the block pushed into an exported slot (one TrackedReal, one deriv field)
-                    if (fl & 2) {
-                        const int2 e = spf[cur][Bq.z];
-                        acc = acc + stage[cur][Bq.z][lane];
+                    if (meta & kM_ExpStaged) {
+                        const int2 e = spf[cur][Bq.w];
+                        acc = acc + comb[kRing + cur * kStageF + Bq.w][lane];
                         if (active) (reinterpret_cast<T *>(P.ext_der[e.x]) + e.y)[r * P.ext_size[e.x]] = (T)0;   // unseed!(output)
                     } else {
-                        for (int64_t x = P.xoff[A.x]; x < P.xoff[A.x + 1]; ++x) {
+                        for (int64_t x = P.xoff[Bq.z]; x < P.xoff[Bq.z + 1]; ++x) {
                             const int o = P.xord[x];
                             T *p = reinterpret_cast<T *>(P.ext_der[o]) + P.xelem[x] + rr * P.ext_size[o];
                             acc = acc + *p;
@@ -192,24 +214,28 @@ __global__ void __launch_bounds__(32) k_scalar_reverse_stream(const StreamP P) {
                         }
                     }
                 }
-                if (Bq.y >= 0) dst = der + (int64_t)Bq.y * R + rr;
-            } else {
-                const int64_t elem = (int64_t)(unsigned)Bq.z | ((int64_t)Bq.w << 32);
-                dst = reinterpret_cast<T *>(P.ext_der[Bq.y]) + elem + rr * P.ext_size[Bq.y];   // origin.deriv[index]
-                if (!P.leaves_zero) acc = *dst;                                                  // pull_deriv!
-            }
-            // increment_deriv!(slot, deriv(out_c) * partial) for every consumer c, in the reference's order
-            if (ne > 0) acc = acc + rd(A.y) * spart[cur][k][0];
-            if (ne > 1) acc = acc + rd(A.z) * spart[cur][k][1];
-            if (ne > 2) {
-                const int4 C = sC[cur][k];
-                acc = acc + rd(C.x) * spart[cur][k][2];
-                if (ne > 3) acc = acc + rd(C.y) * spart[cur][k][3];
+                if (meta & kM_Dir0) x0 = der[(int64_t)C.z * R + rr];
+                if (meta & kM_Dir1) x1 = der[(int64_t)C.w * R + rr];
+                // increment_deriv!(slot, deriv(out_c) * partial) for every consumer c, in the reference's order
+                if (meta & kM_E0) acc = acc + x0 * p00;
+                if (meta & kM_E1) acc = acc + x1 * p01;
+                const int ne = Bq.y;
+                if (ne > 2) {
+                    acc = acc + rd(C.x) * spart[cur][k][2];
+                    if (ne > 3) acc = acc + rd(C.y) * spart[cur][k][3];
 #pragma unroll 4
-                for (int e = kInl; e < ne; ++e) acc = acc + rd(P.tsrc[Bq.x + e]) * epart[Bq.x + e];
+                    for (int e = kInl; e < ne; ++e) acc = acc + rd(P.tsrc[Bq.x + e]) * epart[Bq.x + e];
+                }
+                if (dst && active) *dst = acc;                                                       // push_deriv!
+            } else {
+                const T t0 = x0 * p00, t1 = x1 * p01;
+                acc = (meta & kM_E0) ? acc + t0 : acc;
+                acc = (meta & kM_E1) ? acc + t1 : acc;
             }
-            ring[(b * kBlk + k) & (kRing - 1)][lane] = acc;
-            if (dst && active) *dst = acc;             // the slot's final adjoint (push_deriv! for a leaf)
+            ringrow[k * 32] = acc;
+            if (r0.w >= 0 && active) der[(int64_t)r0.w * R + r] = acc;                                // a far reader will want it
+            prev = acc;
+            r0 = r1; r1 = r2; p00 = p10; p01 = p11; p10 = p20; p11 = p21; v00 = v10; v01 = v11;
         }
         cp_async_wait_all();
         __syncwarp();
@@ -431,7 +457,8 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
     // streaming plan for the many-seed reverse kernel (k_scalar_reverse_stream) -------------------------------------------------
     // schedule: instructions in reverse tape order, every leaf right after its lowest consumer (all its increments are in by then)
     const int64_t nblk = (ns + kBlk - 1) / kBlk, npos = nblk * kBlk;
-    std::vector<int4> recA(npos, make_int4(kNone, 0, 0, 0)), recB(npos, make_int4(0, -1, 0, 0)), recC(npos, make_int4(0, 0, 0, 0));
+    std::vector<int4> recA(npos, make_int4(0, 0, 0, -1)), recB(npos, make_int4(0, 0, 0, 0)), recC(npos, make_int4(0, 0, 0, 0)),
+        recD(npos, make_int4(0, 0, 0, 0));
     std::vector<int2> pf(nblk * kStageF, make_int2(-1, 0));
     std::vector<int32_t> tsrc(ne, 0);
     B.n_sblocks = nblk; B.n_grow = 0; B.n_near = B.n_staged = B.n_direct = 0;
@@ -462,41 +489,55 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
             }
         }
         for (int64_t i = 0; i < n; ++i) if (grow[i] == 0) grow[i] = (int32_t)B.n_grow++;
-        // pass 2: records, operand codes, staging lists
+        // pass 2: records, operand sources, staging lists
+        const int rowbytes = 32 * (int)es;
         std::vector<int> nstage(nblk, 0);
         for (int64_t q = 0; q < ns; ++q) {
             const int64_t sl = order[q], e0 = reoff[rpos[sl]], cnt = ecount[sl], blk = q / kBlk;
-            if (cnt >= (1 << 24)) return "scalar block: a slot has too many consumers";
-            int inl[kInl] = {0, 0, 0, 0};
+            if (cnt > INT_MAX / 2) return "scalar block: a slot has too many consumers";
+            int meta = 0, off[2] = {0, 0}, dir[2] = {0, 0}, src23[2] = {0, 0};
             for (int64_t k = 0; k < cnt; ++k) {
                 const int c = esrc[e0 + k];
+                const int64_t qc = qpos[c];
                 int code;
-                if (blk - qpos[c] / kBlk <= 1) { code = src_code(kSrcRing, (unsigned)(qpos[c] & (kRing - 1))); B.n_near++; }
+                if (q - qc == 1) { code = src_code(kSrcPrev, 0); B.n_near++; }
+                else if (blk - qc / kBlk <= 1) { code = src_code(kSrcSmem, (unsigned)(qc & (kRing - 1))); B.n_near++; }
                 else if (k < kInl && nstage[blk] < kStageF) {
                     const int f = nstage[blk]++;
                     pf[blk * kStageF + f] = make_int2(-2, grow[c]);
-                    code = src_code(kSrcStage, (unsigned)f); B.n_staged++;
+                    code = src_code(kSrcSmem, (unsigned)(kRing + (blk & 1) * kStageF + f)); B.n_staged++;
                 } else { code = src_code(kSrcDirect, (unsigned)grow[c]); B.n_direct++; }
                 tsrc[e0 + k] = code;
-                if (k < kInl) inl[k] = code;
+                const unsigned kind = (unsigned)code >> 30, pl = (unsigned)code & 0x3fffffffu;
+                if (k < 2) {
+                    meta |= k == 0 ? kM_E0 : kM_E1;
+                    if (kind == kSrcPrev) meta |= k == 0 ? kM_Prev0 : kM_Prev1;
+                    else if (kind == kSrcSmem) off[k] = (int)pl * rowbytes;
+                    else { meta |= (k == 0 ? kM_Dir0 : kM_Dir1) | kM_Rare; dir[k] = (int)pl; }
+                } else if (k < kInl) src23[k - 2] = code;
             }
-            int flags = 0, xstage = 0;
+            if (cnt > 2) meta |= kM_Rare;
+            int xstage = 0;
             if (sl < n && xoff[sl + 1] > xoff[sl]) {
-                flags |= 1;
+                meta |= kM_Exp | kM_Rare;
                 if (xoff[sl + 1] - xoff[sl] == 1 && xelem[xoff[sl]] < INT_MAX && nstage[blk] < kStageF) {
                     xstage = nstage[blk]++;
                     pf[blk * kStageF + xstage] = make_int2(xord[xoff[sl]], (int)xelem[xoff[sl]]);
-                    flags |= 2;
+                    meta |= kM_ExpStaged;
                 }
             }
-            recA[q] = make_int4(sl < n ? (int)sl : ~(int)(sl - n), inl[0], inl[1], (int)cnt | (flags << 24));
-            if (sl < n) recB[q] = make_int4((int)e0, grow[sl], xstage, 0);
-            else {
+            if (sl >= n) {
                 const int64_t l = sl - n;
-                recB[q] = make_int4((int)e0, leaf_ord[l], (int)(uint32_t)(leaf_elem[l] & 0xffffffffLL), (int)(leaf_elem[l] >> 32));
+                meta |= kM_Leaf | kM_Rare;
+                recD[q] = make_int4(leaf_ord[l], (int)(uint32_t)(leaf_elem[l] & 0xffffffffLL), (int)(leaf_elem[l] >> 32), 0);
             }
-            recC[q] = make_int4(inl[2], inl[3], 0, 0);
+            recA[q] = make_int4(off[0], off[1], meta, sl < n ? grow[sl] : -1);
+            recB[q] = make_int4((int)e0, (int)cnt, sl < n ? (int)sl : 0, xstage);
+            recC[q] = make_int4(src23[0], src23[1], dir[0], dir[1]);
         }
+        if (getenv("RDB_SCALAR_DEBUG"))
+            fprintf(stderr, "[rdb scalar] n=%lld leaves=%lld edges=%lld blocks=%lld global_rows=%lld near=%lld staged=%lld direct=%lld\n", (long long)n,
+                    (long long)nl, (long long)ne, (long long)nblk, (long long)B.n_grow, (long long)B.n_near, (long long)B.n_staged, (long long)B.n_direct);
     }
     // forward instruction table, level-sorted ------------------------------------------------------------------------------------
     std::vector<int4> finstr(n);
@@ -518,7 +559,7 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
     auto pad = [](size_t b) { return (b + 15) & ~size_t(15); };
     size_t bytes = pad(n * 16) + pad((nfl + 1) * 8) + pad(h_ops.size() * 16) + pad(nex * 16) + pad(2 * n * 4) + pad(nl * 4) + pad(nl * 8) +
                    pad(nexp * 4) * 2 + pad(nexp * 8) + pad(ns * 4) + pad((ns + 1) * 8) + pad(ne * 4) + pad((nrl + 1) * 8) + pad((n + 1) * 8) +
-                   pad(nexp * 4) + pad(nexp * 8) + pad(nref * 8) * 3 + pad(npos * 16) * 3 + pad(nblk * kStageF * 8) + pad(ne * 4) + 512;
+                   pad(nexp * 4) + pad(nexp * 8) + pad(nref * 8) * 3 + pad(npos * 16) * 4 + pad(nblk * kStageF * 8) + pad(ne * 4) + 512;
     std::vector<uint8_t> host(bytes, 0);
     if (cudaMalloc(&B.d_tables, bytes) != cudaSuccess) { cudaGetLastError(); return "scalar block: out of device memory (tables)"; }
     uint8_t *hp = host.data();
@@ -535,7 +576,7 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
     put(B.d_exp_slot, exp_slot); put(B.d_exp_ord, exp_ord); put(B.d_exp_elem, exp_elem);
     put(B.d_rslot, rslot); put(B.d_reoff, reoff); put(B.d_esrc, esrc); put(B.d_rlevel_off, rlevel_off);
     put(B.d_xoff, xoff); put(B.d_xord, xord); put(B.d_xelem, xelem);
-    put(B.d_recA, recA); put(B.d_recB, recB); put(B.d_recC, recC); put(B.d_pf, pf); put(B.d_tsrc, tsrc);
+    put(B.d_recA, recA); put(B.d_recB, recB); put(B.d_recC, recC); put(B.d_recD, recD); put(B.d_pf, pf); put(B.d_tsrc, tsrc);
     std::vector<void *> nulls(nref, nullptr); std::vector<int64_t> zeros(nref, 0);
     put(B.d_ext_val, nulls); put(B.d_ext_der, nulls); put(B.d_ext_size, zeros);
     if ((size_t)(hp - host.data()) > bytes) return "scalar block: internal table overflow";
@@ -604,7 +645,7 @@ template <typename T>
 cudaError_t scalar_block_reverse(cudaStream_t s, ScalarBlock &B, int64_t R, bool leaves_zero, int *launches) {
     int nl = 0;
     if (R >= 16) {
-        StreamP P{B.d_recA, B.d_recB, B.d_recC, B.d_pf, B.d_tsrc, B.d_epart, B.d_xoff, B.d_xord, B.d_xelem,
+        StreamP P{B.d_recA, B.d_recB, B.d_recC, B.d_recD, B.d_pf, B.d_tsrc, B.d_epart, B.d_xoff, B.d_xord, B.d_xelem,
                   B.d_ext_der, B.d_ext_size, B.d_der, R, B.n_sblocks, leaves_zero ? 1 : 0};
         k_scalar_reverse_stream<T><<<(unsigned)((R + 31) / 32), 32, 0, s>>>(P);
         ++nl;
