@@ -309,12 +309,13 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     bf16_peak = peaks.get("bf16_tflops", 1590.0)
     peak_tag = "MEASURED_PEAKS.json bf16_tflops" if "bf16_tflops" in peaks else "fallback 1590 TFLOP/s bf16"
-    slices = 8
+    obits = 7 if os.environ.get("RDB_OZAKI_BITS", "8") == "7" else 8        # librdb200's default: 8-bit digits, 7 slices
+    slices = int(os.environ.get("RDB_OZAKI_SLICES", "7" if obits == 8 else "8"))
     if args.dtype == "f64" and mode == 0:
-        # tcgen05 kind::i8 path: every FP64 GEMM is S(S+1)/2 = 36 exact int8 slice products of the same shape
+        # tcgen05 kind::i8 path: every FP64 GEMM is S(S+1)/2 exact int8 slice products of the same shape (28 at S = 7 x 8 bits)
         ops_per_flop = slices * (slices + 1) / 2
-        kernel = ("oz2::umma_ozaki2c_kernel<8,2> (TMA multicast in 2-CTA clusters + tcgen05.mma kind::i8, int32 TMEM accumulators) "
-                  "+ k_slice_i8/k_row_absmax")
+        kernel = (f"oz2::umma_ozaki2c_kernel<{slices},2> (TMA multicast in 2-CTA clusters + tcgen05.mma kind::i8, int32 TMEM accumulators; "
+                  f"{slices} slices of {obits} bits) + k_slice_i8/k_row_absmax")
         unit = "TOP/s (int8)"
         i8 = measure_int8_peak(torch)
         # denominator: the int8 pipe issues at twice the bf16 rate, so 2 x the driver-measured bf16 burst; the cuBLASLt int8 GEMM

@@ -377,13 +377,15 @@ __global__ void __launch_bounds__(256) k_row_absmax(const double *__restrict__ s
         atomicMax(mx_bits + r, (unsigned long long)__double_as_longlong(mx));
     }
 }
-__global__ void __launch_bounds__(256) k_row_exponent(const unsigned long long *__restrict__ mx_bits, int rows, int *__restrict__ e_out,
+__global__ void __launch_bounds__(256) k_row_exponent(const unsigned long long *__restrict__ mx_bits, int rows, int bits, int *__restrict__ e_out,
                                                       double *__restrict__ scale_out) {
     int r = blockIdx.x * 256 + threadIdx.x;
     if (r >= rows) return;
     double mx = __longlong_as_double((long long)mx_bits[r]);
     const bool finite = isfinite(mx);
-    int e = (mx > 0.0 && finite) ? ilogb(mx) + 2 : 0;
+    // 7-bit digits: |x| 2^-e < 1/2, leading digit <= 64.  8-bit digits: one more bit of headroom (|x| 2^-e < 1/4) so that the
+    // leading digit plus the carry from below (<= 65) stays inside int8
+    int e = (mx > 0.0 && finite) ? ilogb(mx) + (bits == 8 ? 3 : 2) : 0;
     e_out[r] = e;
     // a row/column holding NaN or Inf gets a NaN scale: every output it touches becomes NaN, as DGEMM would propagate it
     scale_out[r] = finite ? scalbn(1.0, e) : __longlong_as_double(0x7FF8000000000000LL);
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(256) k_row_exponent(const unsigned long long *
 // iteration, so every slice store is one packed 32-bit word and a warp writes 128 contiguous bytes of one row.
 template <bool KMAJOR>
 __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, const double *__restrict__ src, int64_t ld, int rows, int K,
-                                                  int Kp, int nslices, const int *__restrict__ e_in) {
+                                                  int Kp, int nslices, int bits, const int *__restrict__ e_in) {
     __shared__ double tile[KMAJOR ? 1 : 128][KMAJOR ? 1 : 33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 128;
@@ -407,11 +409,13 @@ __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, cons
     }
     const int64_t plane = (int64_t)rows * Kp;
     const int k = k0 + 4 * lane;
-    // fixed point: X = rint(v * 2^(7S - e)), |X| <= 2^(7S-1); balanced base-128 digits q_j in [-64, 63] from the least significant
-    // end (d = X & 127; X >>= 7; if d >= 64: d -= 128, X += 1) so that v 2^-e = sum_j q_j 2^(-7(j+1)) + O(2^(-7S-1)).
+    // fixed point, b = bits per digit (8: the full int8 range; 7: the first-generation layout): X = rint(v * 2^(bS - e)),
+    // |X| <= 2^(bS-1); balanced base-2^b digits q_j in [-2^(b-1), 2^(b-1) - 1] from the least significant end
+    // (d = X & (2^b - 1); X >>= b; if d >= 2^(b-1): d -= 2^b, X += 1) so that v 2^-e = sum_j q_j 2^(-b(j+1)) + O(2^(-bS-1)).
     // All four rows of a thread are loaded before any digit work so four 32-byte loads are in flight per thread.
     long long X[4][4];
     bool ok[4];
+    const int radix = 1 << bits, half = radix >> 1;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int rl = w + 8 * i, r = r0 + rl;
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, cons
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) X[i][j] = isfinite(v[j]) ? __double2ll_rn(scalbn(v[j], 7 * nslices - e)) : 0LL;
+        for (int j = 0; j < 4; ++j) X[i][j] = isfinite(v[j]) ? __double2ll_rn(scalbn(v[j], bits * nslices - e)) : 0LL;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -445,10 +449,10 @@ __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, cons
             uint32_t packed = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                int d = (int)(X[i][j] & 127);
-                X[i][j] >>= 7;
-                if (sidx > 0 && d >= 64) { d -= 128; X[i][j] += 1; }
-                if (sidx == 0) d = (int)((X[i][j] << 7) | d);          // most significant digit keeps the sign: |d| <= 64
+                int d = (int)(X[i][j] & (long long)(radix - 1));
+                X[i][j] >>= bits;
+                if (sidx > 0 && d >= half) { d -= radix; X[i][j] += 1; }
+                if (sidx == 0) d = (int)((X[i][j] << bits) | d);       // most significant digit keeps the sign: |d| <= 2^(b-2) + 1
                 packed |= ((uint32_t)(uint8_t)(int8_t)d) << (8 * j);
             }
             *reinterpret_cast<uint32_t *>(dst + sidx * plane + (int64_t)r * Kp + k) = packed;
@@ -463,6 +467,7 @@ struct OzParams {
     const double *sa, *sb;      // 2^ea[row], 2^eb[col]
     int nslices;
     int group_m;                // tile rasterisation group (see raster())
+    int bits;                   // bits per digit: slice pair (p, q) weighs 2^(-bits (p + q + 2))
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -547,7 +552,7 @@ umma_ozaki_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int buf = gi & 1;
             mbar_wait(&tmem_full[buf], (gi >> 1) & 1);
             tc_fence_after();
-            const double rs = P.alpha * sa * scalbn(1.0, -7 * (d + 2));     // alpha * 2^(ea[row] - 7(d+2))
+            const double rs = P.alpha * sa * scalbn(1.0, -P.bits * (d + 2));     // alpha * 2^(ea[row] - bits(d+2))
             const bool first = gi == 0;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -597,6 +602,7 @@ constexpr int BM2 = 128, BN2 = 64;
 __host__ __device__ constexpr int stages_for(int KB) { return KB == 64 ? 2 : 4; }
 __host__ __device__ constexpr int stage_bytes(int S, int KB) { return S * (BM2 + BN2) * KB; }
 __host__ __device__ constexpr int smem_bytes(int S, int KB) { return stages_for(KB) * stage_bytes(S, KB) + 1024 + 256; }
+__host__ __device__ constexpr int smem_bytes_cluster(int S, int CL) { return 2 * (((S + CL - 1) / CL) * CL * BM2 * 64 + S * BN2 * 64) + 1024 + 256; }
 
 // K-major swizzled tile with rows of KB bytes: 8-row atoms of 8*KB bytes (SBO); layout type 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
 template <int KB>
@@ -700,7 +706,7 @@ umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int d = S - 1; d >= 0; --d) {                          // smallest terms first
                 uint32_t v[32];
                 tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(d * BN2 + c0), v);
-                const double w = scalbn(1.0, -7 * (d + 2));
+                const double w = scalbn(1.0, -P.bits * (d + 2));
 #pragma unroll
                 for (int j = 0; j < 32; ++j) sum[j] += (double)(int)v[j] * w;      // exact products, FP64 adds
             }
@@ -754,11 +760,12 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask) {
 template <int S, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, OzParams P) {
-    static_assert(S % CL == 0, "slices must divide evenly over the cluster");
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr int KB = 64, STAGE = stage_bytes(S, KB), STAGES2 = stages_for(KB), A_SLICE = BM2 * KB, B_SLICE = BN2 * KB;
-    constexpr int SL = S / CL;                                    // A slices fetched by each CTA
+    constexpr int KB = 64, STAGES2 = stages_for(KB), A_SLICE = BM2 * KB, B_SLICE = BN2 * KB;
+    constexpr int SL = (S + CL - 1) / CL;                         // A slices fetched by each CTA; the stage holds SL*CL slots: the
+    constexpr int SA = SL * CL;                                   // last box may reach past slice S-1 (TMA zero-fills, counts bytes)
+    constexpr int STAGE = SA * A_SLICE + S * B_SLICE;
     constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
     uint64_t *full = (uint64_t *)(smem + STAGES2 * STAGE);
     uint64_t *empty = full + STAGES2;
@@ -796,7 +803,7 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
                 mbar_wait(&empty[s], ph ^ 1);                     // all CL consumers released this stage (in every CTA)
                 mbar_expect_tx(&full[s], STAGE);                  // bytes landing in MY smem: S A-slices (CL multicasts) + my B slices
                 tma_load_3d_mc(smem + s * STAGE + crank * SL * A_SLICE, &tmAmc, &full[s], kb * KB, m0, crank * SL, MASK);
-                tma_load_3d(smem + s * STAGE + S * A_SLICE, &tmB, &full[s], kb * KB, n0, 0);
+                tma_load_3d(smem + s * STAGE + SA * A_SLICE, &tmB, &full[s], kb * KB, n0, 0);
             }
         }
     } else if (warp == 1) {
@@ -806,7 +813,7 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
                 const uint32_t ph = (kb / STAGES2) & 1;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t a0 = smem_u32(smem + s * STAGE), b0 = a0 + S * A_SLICE;
+                const uint32_t a0 = smem_u32(smem + s * STAGE), b0 = a0 + SA * A_SLICE;
 #pragma unroll
                 for (int p = 0; p < S; ++p) {
                     const uint64_t ad = make_desc_kb<KB>(a0 + p * A_SLICE);
@@ -840,7 +847,7 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
             for (int d = S - 1; d >= 0; --d) {
                 uint32_t v[32];
                 tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(d * BN2 + c0), v);
-                const double w = scalbn(1.0, -7 * (d + 2));
+                const double w = scalbn(1.0, -P.bits * (d + 2));
 #pragma unroll
                 for (int j = 0; j < 32; ++j) sum[j] += (double)(int)v[j] * w;
             }
@@ -912,11 +919,18 @@ cudaError_t gemm_f32_umma(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t 
 }
 
 
+// bits per int8 digit: 8 (default) uses the whole int8 range, so 7 slices carry the 56 fixed-point bits that took 8 slices of 7
+// bits - 28 slice products instead of 36 for the same truncation bound; int32 accumulators stay exact for K*S < 2^17
+int ozaki_bits() {
+    static int b = -1;
+    if (b < 0) { const char *e = getenv("RDB_OZAKI_BITS"); b = (e && atoi(e) == 7) ? 7 : 8; }
+    return b;
+}
 int ozaki_default_slices() {
     static int n = -1;
     if (n < 0) {
         const char *e = getenv("RDB_OZAKI_SLICES");
-        n = e ? atoi(e) : 8;
+        n = e ? atoi(e) : (ozaki_bits() == 8 ? 7 : 8);
         if (n < 2) n = 2;
         if (n > umma::OZ_MAX_SLICES) n = umma::OZ_MAX_SLICES;
     }
@@ -936,7 +950,7 @@ cudaError_t gemm_f64_ozaki(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t
                            int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices,
                            uint64_t tag_a, uint64_t tag_b) {
     if (M < 256 || N < 256 || K < 256 || !umma_available()) return cudaErrorNotSupported;
-    const int64_t kmax = (((1 << 19) - 1) / nslices) & ~127LL;
+    const int64_t kmax = (((1 << (33 - 2 * ozaki_bits())) - 1) / nslices) & ~127LL;      // int32 exactness, see ozaki_chunk
     int64_t chunks = (K + kmax - 1) / kmax;
     const int64_t tiles = ((M + 127) / 128) * ((N + 63) / 64);
     while (tiles < 592 && K / (chunks * 2) >= 8192) chunks *= 2;        // want >= 4 waves of 148 tiles; chunks are serialised
@@ -962,7 +976,7 @@ struct SliceEntry {
     const void *ptr;
     int64_t ld, rows, K;
     bool kmajor;
-    int ns;
+    int ns, bits;
     int8_t *q;
     double *sc;
     size_t bytes;
@@ -977,8 +991,10 @@ static size_t cache_cap() {
     return cap;
 }
 
+int ozaki_bits();
 static void slice_operand(cudaStream_t st, const double *src, int64_t ld, int64_t rows, int64_t K, int64_t Kp, bool kmajor, int ns,
                           int8_t *q, int *e, double *sc) {
+    const int bits = ozaki_bits();
     using namespace umma;
     unsigned long long *mx = (unsigned long long *)sc;                  // scale array doubles as max scratch
     if (kmajor) k_row_absmax<true><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(src, ld, (int)rows, (int)K, mx);
@@ -986,10 +1002,10 @@ static void slice_operand(cudaStream_t st, const double *src, int64_t ld, int64_
         cudaMemsetAsync(mx, 0, rows * 8, st);
         k_row_absmax<false><<<dim3((unsigned)((rows + 255) / 256), (unsigned)((K + 63) / 64)), 256, 0, st>>>(src, ld, (int)rows, (int)K, mx);
     }
-    k_row_exponent<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(mx, (int)rows, e, sc);
+    k_row_exponent<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(mx, (int)rows, bits, e, sc);
     dim3 g((unsigned)((Kp + 127) / 128), (unsigned)((rows + 31) / 32));
-    if (kmajor) k_slice_i8<true><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, e);
-    else k_slice_i8<false><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, e);
+    if (kmajor) k_slice_i8<true><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e);
+    else k_slice_i8<false><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e);
 }
 
 // returns the slices/scales of one operand; launches = kernels issued (0 on a cache hit)
@@ -1002,7 +1018,7 @@ static cudaError_t prepare_operand(cudaStream_t st, uint64_t tag, const double *
     }
     SliceEntry *slot = nullptr;
     for (auto &en : g_cache)
-        if (en.ptr == src && en.ld == ld && en.rows == rows && en.K == K && en.kmajor == kmajor && en.ns == ns) { slot = &en; break; }
+        if (en.ptr == src && en.ld == ld && en.rows == rows && en.K == K && en.kmajor == kmajor && en.ns == ns && en.bits == ozaki_bits()) { slot = &en; break; }
     if (slot && slot->tag == tag) {
         slot->last_use = ++g_use;
         *q = slot->q; *sc = slot->sc; *launches = 0;
@@ -1025,7 +1041,7 @@ static cudaError_t prepare_operand(cudaStream_t st, uint64_t tag, const double *
         SliceEntry en{};
         if (cudaMalloc((void **)&en.q, bytes) != cudaSuccess) { cudaGetLastError(); slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc); *q = ws_q; *sc = ws_sc; *launches = 3; return cudaSuccess; }
         en.sc = (double *)(en.q + (((size_t)ns * rows * Kp + 255) & ~(size_t)255));
-        en.ptr = src; en.ld = ld; en.rows = rows; en.K = K; en.kmajor = kmajor; en.ns = ns; en.bytes = bytes;
+        en.ptr = src; en.ld = ld; en.rows = rows; en.K = K; en.kmajor = kmajor; en.ns = ns; en.bits = ozaki_bits(); en.bytes = bytes;
         g_cache_bytes += bytes;
         g_cache.push_back(en);
         slot = &g_cache.back();
@@ -1041,8 +1057,8 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
                                int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices,
                                uint64_t tag_a, uint64_t tag_b) {
     using namespace umma;
-    // int32 exactness: (d+1)*K*2^12 < 2^31 for d <= nslices-1
-    if (K * (int64_t)nslices > (1 << 19) - 1) return cudaErrorInvalidValue;
+    // int32 exactness: (d+1)*K*2^(2(bits-1)) < 2^31 for d <= nslices-1
+    if (K * (int64_t)nslices > (1 << (33 - 2 * ozaki_bits())) - 1) return cudaErrorInvalidValue;
     const int64_t Kp = (K + 15) & ~15LL;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t a_bytes = tag_a ? 0 : al((size_t)nslices * M * Kp), b_bytes = tag_b ? 0 : al((size_t)nslices * N * Kp);
@@ -1065,7 +1081,7 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     CUtensorMap mA, mB;
     static int group_m = -1;
     if (group_m < 0) { const char *e = getenv("RDB_OZAKI_GROUP_M"); group_m = e ? atoi(e) : 8; if (group_m < 1) group_m = 1 << 20; }
-    OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m};
+    OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m, ozaki_bits()};
     static int gen = -1;
     if (gen < 0) { const char *e = getenv("RDB_OZAKI_GEN"); gen = e ? atoi(e) : 2; }
     if (gen == 2 && nslices <= 8) {
@@ -1078,26 +1094,32 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
         dim3 grid2((unsigned)((M + BM2 - 1) / BM2), (unsigned)((N + BN2 - 1) / BN2));
         static int cl = -1;
         if (cl < 0) { const char *e = getenv("RDB_OZAKI_CLUSTER"); cl = e ? atoi(e) : 2; if (cl != 1 && cl != 2 && cl != 4) cl = 1; }
-        if (nslices == 8 && kbytes == 64 && cl > 1 && grid2.y % cl == 0) {
+        if ((nslices == 8 || nslices == 7) && kbytes == 64 && cl > 1 && grid2.y % cl == 0) {
             // cluster of `cl` CTAs along n sharing the A stage through TMA multicast
             CUtensorMap mAmc;
-            if (!make_map(&mAmc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, kbytes, nslices / cl)) return cudaErrorInvalidValue;
+            if (!make_map(&mAmc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, kbytes, (nslices + cl - 1) / cl)) return cudaErrorInvalidValue;
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = grid2; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes(8, 64); cfg.stream = st;
+            cfg.gridDim = grid2; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes_cluster(nslices, cl); cfg.stream = st;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)cl; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             static bool attrc = false;
             if (!attrc) {
-                cudaError_t e = cudaFuncSetAttribute(umma_ozaki2c_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(8, 64));
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_ozaki2c_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(8, 64));
+                cudaError_t e = cudaFuncSetAttribute(umma_ozaki2c_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_cluster(8, 2));
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_ozaki2c_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_cluster(8, 4));
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_ozaki2c_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_cluster(7, 2));
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(umma_ozaki2c_kernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_cluster(7, 4));
                 if (e != cudaSuccess) return e;
                 attrc = true;
             }
             int Mi = (int)M, Ni = (int)N, Ki = (int)Kp;
-            if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 2>, mAmc, mB, Mi, Ni, Ki, P);
-            return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 4>, mAmc, mB, Mi, Ni, Ki, P);
+            if (nslices == 8) {
+                if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 2>, mAmc, mB, Mi, Ni, Ki, P);
+                return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 4>, mAmc, mB, Mi, Ni, Ki, P);
+            }
+            if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<7, 2>, mAmc, mB, Mi, Ni, Ki, P);
+            return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<7, 4>, mAmc, mB, Mi, Ni, Ki, P);
         }
 #define RDB_OZ2(SS)                                                                                                        \
     case SS: {                                                                                                             \
