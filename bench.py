@@ -279,6 +279,8 @@ def main():
     e2e_steps = max(3, args.steps // 2)
     e2e_val = world * e2e_steps / (ms_e2e * 1e-3)
     assert np.max(np.abs(ga_h - ga)) <= tol * np.max(np.abs(ga))
+    gb_ref = a64.sum(1)[:, None] + a64.sum(0)[None, :]
+    assert np.max(np.abs(gb_h - gb_ref)) <= tol * np.max(np.abs(gb_ref))
 
     # ---- roofline of the dominant kernel: per-launch CUDA events inside the engine --------------------
     def gemm_stats(m):

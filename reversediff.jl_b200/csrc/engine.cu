@@ -101,6 +101,7 @@ struct InstrPlan {
     std::vector<int32_t> h_ops;     // host copy of the scalar program (NVRTC specialisation)
     void *jit_fn[2] = {nullptr, nullptr};   // [reduce]
     bool jit_tried[2] = {false, false};
+    bool rev_done[2] = {false, false};   // `*`: this operand's adjoint was already accumulated in this sweep (paired panels, mul_reverse)
 };
 
 struct StepStat {
@@ -455,29 +456,119 @@ static int dmaterialize(rdb_tape *t, int b, int64_t R, bool mark_live) {
     return RDB_OK;
 }
 
+// ---- `*` adjoints by column panels of the accumulated buffer (single seed) -------------------------------------------------
+// mul_operand_ref: the GEMM view of a `*` operand's value (values are unchanged since the forward sweep: the densified copies of
+// OPM_GATHER operands are reused)
+template <typename T>
+static void mul_operand_ref(rdb_tape *t, OperandPlan &o, MatRef<T> &m) {
+    Buf &b = t->bufs[o.rec.buffer];
+    if (o.mode == OPM_PLAIN) { m.ptr = (const T *)b.val; m.ld = o.rows; m.stored_t = false; }
+    else if (o.mode == OPM_FOLDED_T) { m.ptr = (const T *)b.val; m.ld = o.cols; m.stored_t = true; }
+    else { m.ptr = (const T *)o.dense_val; m.ld = o.rows; m.stored_t = false; }
+}
+static uint64_t g_delta_serial = 0;
+static uint64_t new_delta_tag() { return (1ull << 63) | (++g_delta_serial & 0x7FFFFFFFFFFFFFFFull); }
+
+// shape of the buffer an operand's adjoint lands in (the operand itself, or the origin of a folded transpose)
+static void mul_root_shape(const OperandPlan &o, int64_t &rows, int64_t &cols) {
+    if (o.mode == OPM_FOLDED_T) { rows = o.cols; cols = o.rows; } else { rows = o.rows; cols = o.cols; }
+}
+
+// columns [c0, c0 + nc) of deriv(root of operand `side`) (+)= this instruction's contribution; dtag identifies the content of
+// deriv(output) for the sliced-operand cache (the same delta is an operand of every panel)
+template <typename T>
+static int mul_acc_cols(rdb_tape *t, InstrPlan &I, int side, int64_t c0, int64_t nc, T beta, uint64_t dtag) {
+    OperandPlan &oa = I.in[0], &ob = I.in[1];
+    const int64_t M = oa.rows, K = oa.cols, N = ob.cols;
+    MatRef<T> A, B;
+    mul_operand_ref<T>(t, oa, A);
+    mul_operand_ref<T>(t, ob, B);
+    const T *delta = (const T *)t->bufs[I.rec.out].der;
+    if (side == 0) {
+        T *dst = (T *)t->bufs[oa.rec.buffer].der;
+        if (oa.mode == OPM_PLAIN) {
+            // a.deriv(MxK)[:, c0:] = delta(MxN) * Bmat'(N x k-panel)
+            const T *bp = B.stored_t ? B.ptr + c0 * B.ld : B.ptr + c0;
+            g_tag_a = dtag;
+            if (c0 == 0 && nc == K) g_tag_b = operand_tag(t, ob);
+            KL(t, gemm_t<T>(S(t), false, !B.stored_t, M, nc, N, (T)1, delta, M, bp, B.ld, beta, dst + c0 * M, M));
+        } else {
+            // origin.deriv(KxM)[:, c0:] = Bmat(KxN) * delta'(N x m-panel)
+            g_tag_a = operand_tag(t, ob);
+            if (c0 == 0 && nc == M) g_tag_b = dtag;
+            KL(t, gemm_t<T>(S(t), B.stored_t, true, K, nc, N, (T)1, B.ptr, B.ld, delta + c0, M, beta, dst + c0 * K, K));
+        }
+    } else {
+        T *dst = (T *)t->bufs[ob.rec.buffer].der;
+        if (ob.mode == OPM_PLAIN) {
+            // b.deriv(KxN)[:, c0:] = Amat'(KxM) * delta(M x n-panel)
+            g_tag_a = operand_tag(t, oa);
+            if (c0 == 0 && nc == N) g_tag_b = dtag;
+            KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, nc, M, (T)1, A.ptr, A.ld, delta + c0 * M, M, beta, dst + c0 * K, K));
+        } else {
+            // origin.deriv(NxK)[:, c0:] = delta'(NxM) * Amat(M x k-panel)
+            const T *ap = A.stored_t ? A.ptr + c0 : A.ptr + c0 * A.ld;
+            g_tag_a = dtag;
+            if (c0 == 0 && nc == K) g_tag_b = operand_tag(t, oa);
+            KL(t, gemm_t<T>(S(t), true, A.stored_t, N, nc, M, (T)1, delta, M, ap, A.ld, beta, dst + c0 * N, N));
+        }
+    }
+    return RDB_OK;
+}
+
+// The other accumulation into the same tape input that a pair of column-panelled GEMMs can be built with: the next `*`
+// instruction (lower tape index) whose operand is rooted at `root`, provided running its adjoint NOW is the same computation as
+// running it at its own turn: deriv(its output) must be final (no instruction in between, this one included, consumes that
+// output) and reached.  Returns the instruction index and sets `side`, or -1.
+static int find_mul_partner(rdb_tape *t, int k, int root, int64_t rows, int64_t cols, int &side) {
+    for (int j = k - 1; j >= 0; --j) {
+        InstrPlan &J = t->instrs[j];
+        if (J.blk) {
+            for (int r = 0; r < J.blk->n_ref; ++r) if (droot(t, J.blk->refbufs[r]) == root) return -1;
+            continue;
+        }
+        for (int a = 0; a < J.rec.n_in; ++a) {
+            OperandPlan &o = J.in[a];
+            if (!o.rec.tracked || droot(t, o.rec.buffer) != root) continue;
+            if (J.rec.opcode != OP_MUL || a > 1 || o.mode == OPM_GATHER || J.rev_done[a]) return -1;
+            int64_t r2, c2;
+            mul_root_shape(o, r2, c2);
+            if (r2 != rows || c2 != cols) return -1;
+            const int oj = droot(t, J.rec.out);
+            if (t->dz[oj]) return -1;
+            for (int i = j + 1; i <= k; ++i) {
+                InstrPlan &X = t->instrs[i];
+                if (X.blk) { for (int r = 0; r < X.blk->n_ref; ++r) if (droot(t, X.blk->refbufs[r]) == oj) return -1; continue; }
+                for (int b = 0; b < X.rec.n_in; ++b) if (droot(t, X.in[b].rec.buffer) == oj) return -1;
+                if (droot(t, X.rec.out) == oj) return -1;
+            }
+            side = a;
+            return j;
+        }
+    }
+    return -1;
+}
+
 // a.deriv += delta * value(b)'   and   b.deriv += value(a)' * delta     (arithmetic.jl:272-285), R seed columns
 template <typename T>
-static int mul_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
+static int mul_reverse(rdb_tape *t, int k, int64_t R) {
+    InstrPlan &I = t->instrs[k];
     Buf &out = t->bufs[I.rec.out];
     OperandPlan &oa = I.in[0], &ob = I.in[1];
     const int64_t M = oa.rows, K = oa.cols, N = ob.cols;
     MatRef<T> A, B;
-    // values are unchanged since the forward sweep: reuse the densified copies of OPM_GATHER operands
-    auto ref = [&](OperandPlan &o, MatRef<T> &m) {
-        Buf &b = t->bufs[o.rec.buffer];
-        if (o.mode == OPM_PLAIN) { m.ptr = (const T *)b.val; m.ld = o.rows; m.stored_t = false; }
-        else if (o.mode == OPM_FOLDED_T) { m.ptr = (const T *)b.val; m.ld = o.cols; m.stored_t = true; }
-        else { m.ptr = (const T *)o.dense_val; m.ld = o.rows; m.stored_t = false; }
-    };
-    ref(oa, A);
-    ref(ob, B);
+    mul_operand_ref<T>(t, oa, A);
+    mul_operand_ref<T>(t, ob, B);
     const T *delta = (const T *)out.der;
-    // When a GEMM is the LAST accumulation into a tape input whose result goes to the host (gradient!), it is cut into column
-    // panels of the result and each finished panel starts its D2H copy while the next one computes.
+    // gradient! with host results: when a GEMM is the LAST accumulation into a tape input, it is cut into column panels of the
+    // result and each finished panel starts its D2H copy while the next one computes.  When TWO `*` accumulations are left and
+    // the other one can run now (find_mul_partner), both are cut into the same panels and interleaved, so the input's adjoint
+    // is final - and on its way to the host - panel by panel while the rest of the sweep still computes.
     auto &E = t->early;
-    auto want_panels = [&](int buffer, int64_t rows, int64_t cols) -> int {
+    const uint64_t dtag = new_delta_tag();
+    auto panel_count = [&](int buffer, int64_t rows, int64_t cols, int remaining) -> int {
         const int rb = droot(t, buffer);
-        if (E.enabled && R == 1 && E.dst[rb] && !E.issued[rb] && E.remaining[rb] == 1 && cols >= 2048 &&
+        if (E.enabled && R == 1 && E.dst[rb] && !E.issued[rb] && E.remaining[rb] == remaining && cols >= 2048 &&
             rows * cols * (int64_t)t->es >= (32 << 20) && E.n_ev + 4 <= kMaxArgs * 2)
             return 4;
         return 1;
@@ -493,35 +584,64 @@ static int mul_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
                            (size_t)n_elems * t->es, cudaMemcpyDeviceToHost, t->ctx->copy_stream));
         return RDB_OK;
     };
-    auto panels_done = [&](int buffer) { const int rb = droot(t, buffer); E.issued[rb] = 1; E.remaining[rb] = 0; };
-    if (oa.rec.tracked) {
+    // returns 1 if the accumulation was done by panels (alone or paired), 0 if the caller runs the plain GEMM
+    auto by_panels = [&](int side, T beta) -> int {
+        OperandPlan &o = I.in[side];
+        if (o.mode == OPM_GATHER) return 0;
+        int64_t rows, cols;
+        mul_root_shape(o, rows, cols);
+        const int root = droot(t, o.rec.buffer);
+        int pj = -1, ps = 0;
+        uint64_t ptag = 0;
+        if (panel_count(o.rec.buffer, rows, cols, 2) > 1) {
+            pj = find_mul_partner(t, k, root, rows, cols, ps);
+            if (pj < 0) return 0;
+            ptag = new_delta_tag();
+        } else if (panel_count(o.rec.buffer, rows, cols, 1) == 1) return 0;
+        // panel widths in 64-column tiles, chosen so that every panel's 128x64 tile count fills whole waves of the 148 SMs
+        // (a 4096^2 GEMM is 13.8 waves; four equal panels would be 4 x 3.46 -> 16)
+        int64_t width[4] = {0, 0, 0, 0};
+        {
+            const int64_t rt = (rows + 127) / 128, C = (cols + 63) / 64;
+            auto waves = [&](int64_t x) { return (rt * x + 147) / 148; };
+            int64_t best = -1;
+            for (int P = 3; P <= 4; ++P) {
+                const int64_t mid = C / P;
+                for (int64_t x1 = std::max<int64_t>(1, mid - 6); x1 <= mid + 6; ++x1)
+                    for (int64_t x2 = std::max<int64_t>(1, mid - 6); x2 <= mid + 6; ++x2)
+                        for (int64_t x3 = (P == 4 ? std::max<int64_t>(1, mid - 6) : 0); x3 <= (P == 4 ? mid + 6 : 0); ++x3) {
+                            const int64_t last = C - x1 - x2 - x3;
+                            if (last < 1 || last > mid + 6) continue;
+                            // total waves, then the smallest last panel (its D2H copy is the tail of the call)
+                            const int64_t cost = (waves(x1) + waves(x2) + (x3 ? waves(x3) : 0) + waves(last)) * 4096 + last;
+                            if (best < 0 || cost < best) { best = cost; width[0] = x1; width[1] = x2; width[2] = x3 ? x3 : last; width[3] = x3 ? last : 0; }
+                        }
+            }
+            if (best < 0) { const int64_t q = (C + 3) / 4; width[0] = width[1] = width[2] = q; width[3] = C > 3 * q ? C - 3 * q : 0; }
+        }
+        int64_t c0 = 0;
+        for (int pi = 0; pi < 4 && c0 < cols; ++pi) {
+            if (width[pi] <= 0) continue;
+            const int64_t nc = std::min<int64_t>(width[pi] * 64, cols - c0);
+            OK(mul_acc_cols<T>(t, I, side, c0, nc, beta, dtag));
+            if (pj >= 0) OK(mul_acc_cols<T>(t, t->instrs[pj], ps, c0, nc, (T)1, ptag));
+            OK(panel_copy(o.rec.buffer, c0 * rows, nc * rows));
+            c0 += nc;
+        }
+        if (c0 < cols) return fail(RDB_EINVAL, "internal: column panels do not cover the buffer");
+        if (pj >= 0) t->instrs[pj].rev_done[ps] = true;
+        E.issued[root] = 1; E.remaining[root] = 0;
+        return 1;
+    };
+    if (oa.rec.tracked && I.rev_done[0]) I.rev_done[0] = false;          // accumulated earlier in this sweep as the partner of a pair
+    else if (oa.rec.tracked) {
         Buf &ba = t->bufs[oa.rec.buffer];
         StepTimer tm(t, "gemm_reverse_a", (double)(M * N + K * N + 2 * M * K) * t->es * R, 2.0 * M * N * K * R);
         if (oa.mode == OPM_GATHER) OK(dmaterialize(t, oa.rec.buffer, R, true));
         const T beta_a = (oa.mode != OPM_GATHER && dtake(t, oa.rec.buffer)) ? (T)0 : (T)1;
-        const int pa = oa.mode == OPM_PLAIN ? want_panels(oa.rec.buffer, M, K) : (oa.mode == OPM_FOLDED_T ? want_panels(oa.rec.buffer, K, M) : 1);
-        if (pa > 1) {
-            if (oa.mode == OPM_PLAIN) {
-                // column panels [k0,k1) of a.deriv(MxK) = delta(MxN) * Bmat'(N x k-panel)
-                const int64_t pk = ((K + pa - 1) / pa + 63) & ~63LL;
-                for (int64_t k0 = 0; k0 < K; k0 += pk) {
-                    const int64_t kn = std::min<int64_t>(pk, K - k0);
-                    const T *bp = B.stored_t ? B.ptr + k0 * B.ld : B.ptr + k0;
-                    KL(t, gemm_t<T>(S(t), false, !B.stored_t, M, kn, N, (T)1, delta, M, bp, B.ld, beta_a, (T *)ba.der + k0 * M, M));
-                    OK(panel_copy(oa.rec.buffer, k0 * M, kn * M));
-                }
-            } else {
-                // column panels [m0,m1) of origin.deriv(KxM) = Bmat(KxN) * delta'(N x m-panel)
-                const int64_t pm = ((M + pa - 1) / pa + 63) & ~63LL;
-                for (int64_t m0 = 0; m0 < M; m0 += pm) {
-                    const int64_t mn = std::min<int64_t>(pm, M - m0);
-                    g_tag_a = operand_tag(t, ob);
-                    KL(t, gemm_t<T>(S(t), B.stored_t, true, K, mn, N, (T)1, B.ptr, B.ld, delta + m0, M, beta_a, (T *)ba.der + m0 * K, K));
-                    OK(panel_copy(oa.rec.buffer, m0 * K, mn * K));
-                }
-            }
-            panels_done(oa.rec.buffer);
-        } else
+        const int done = by_panels(0, beta_a);
+        if (done < 0) return done;
+        if (!done)
         for (int64_t r = 0; r < R; ++r) {
             const T *d = delta + r * M * N;
             if (oa.mode == OPM_PLAIN) {
@@ -540,27 +660,19 @@ static int mul_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
         }
         OK(acc_done(t, oa.rec.buffer));
     }
-    if (ob.rec.tracked) {
+    if (ob.rec.tracked && I.rev_done[1]) I.rev_done[1] = false;
+    else if (ob.rec.tracked) {
         Buf &bb = t->bufs[ob.rec.buffer];
         StepTimer tm(t, "gemm_reverse_b", (double)(M * N + M * K + 2 * K * N) * t->es * R, 2.0 * M * N * K * R);
         if (ob.mode == OPM_GATHER) OK(dmaterialize(t, ob.rec.buffer, R, true));
         const T beta_b = (ob.mode != OPM_GATHER && dtake(t, ob.rec.buffer)) ? (T)0 : (T)1;
-        if (ob.mode == OPM_PLAIN) {
+        const int done = by_panels(1, beta_b);
+        if (done < 0) return done;
+        if (done) {
+        } else if (ob.mode == OPM_PLAIN) {
             // b.deriv(K x N*R) += Amat'(KxM) * delta(M x N*R): the R seed columns ride along as extra GEMM columns
-            const int panels = want_panels(ob.rec.buffer, K, N);
-            if (panels == 1) {
-                g_tag_a = operand_tag(t, oa);
-                KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, N * R, M, (T)1, A.ptr, A.ld, delta, M, beta_b, (T *)bb.der, K));
-            } else {
-                const int64_t pn = ((N + panels - 1) / panels + 63) & ~63LL;
-                for (int64_t j0 = 0; j0 < N; j0 += pn) {
-                    const int64_t jn = std::min<int64_t>(pn, N - j0);
-                    g_tag_a = operand_tag(t, oa);
-                    KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, jn, M, (T)1, A.ptr, A.ld, delta + j0 * M, M, beta_b, (T *)bb.der + j0 * K, K));
-                    OK(panel_copy(ob.rec.buffer, j0 * K, jn * K));
-                }
-                panels_done(ob.rec.buffer);
-            }
+            g_tag_a = operand_tag(t, oa);
+            KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, N * R, M, (T)1, A.ptr, A.ld, delta, M, beta_b, (T *)bb.der, K));
         } else {
             for (int64_t r = 0; r < R; ++r) {
                 const T *d = delta + r * M * N;
@@ -659,6 +771,7 @@ static int scalar_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
 
 template <typename T>
 static int reverse_pass(rdb_tape *t, int64_t R) {
+    for (auto &I : t->instrs) I.rev_done[0] = I.rev_done[1] = false;
     for (size_t k = t->instrs.size(); k-- > 0;) {
         InstrPlan &I = t->instrs[k];
         if (I.rec.opcode == OP_SCALAR_BLOCK) { OK(scalar_reverse<T>(t, I, R)); continue; }
@@ -666,7 +779,7 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
         const T *delta = (const T *)out.der;
         if (t->dz[droot(t, I.rec.out)]) continue;        // no adjoint reached this output: every increment would add zero
         switch (I.rec.opcode) {
-            case OP_MUL: OK(mul_reverse<T>(t, I, R)); break;
+            case OP_MUL: OK(mul_reverse<T>(t, (int)k, R)); break;
             case OP_ADD:
             case OP_SUB:
                 for (int a = 0; a < 2; ++a) {
