@@ -57,10 +57,12 @@ struct rdb_ctx {
     int refs = 1;          // the handle itself + one per live tape: destruction order is the caller's business
     int gemm_f64_mode = 0, ozaki_slices = 0;   // for rdb_gemm on this context
     cudaStream_t copy_stream = nullptr;        // device->host result copies that overlap the tail of the reverse sweep
+    cudaStream_t upload_stream = nullptr;      // host->device input copies in column panels (rdb_tape_set_input), see settle_uploads
 };
 static void ctx_release(rdb_ctx *c) {
     if (!c || --c->refs > 0) return;
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->upload_stream) cudaStreamDestroy(c->upload_stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -76,6 +78,10 @@ struct Buf {
     void *td = nullptr;    // deriv tangents  (size x K), hessian! only
     int n_consumers = 0;
     uint32_t version = 1;  // bumped whenever value(x) is rewritten: identifies sliced-operand cache entries
+    // a large host input still arriving on the upload stream in column panels [up_c0[i], up_c0[i+1]): event i = panel i landed
+    cudaEvent_t up_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t up_c0[5] = {0, 0, 0, 0, 0};
+    int up_n = 0;
 };
 
 enum OperandMode { OPM_PLAIN = 0, OPM_FOLDED_T = 1, OPM_GATHER = 2 };
@@ -135,6 +141,7 @@ struct rdb_tape {
     std::vector<StepStat> stats;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool forward_valid = false;
+    int last_upload = -1;          // buffer of the most recent panelled upload (the one worth consuming panel by panel)
     // deriv zero-state, per ROOT buffer: dz[b] != 0 means deriv(b) is LOGICALLY zero while its storage may hold anything.
     // unseed! (every reverse exec ends with one, tracked.jl:207-213) only sets the flag; the next accumulation into the buffer
     // overwrites (beta = 0, plain store) instead of memset + read-modify-write; anything that cannot overwrite (scatter, atomics)
@@ -260,6 +267,9 @@ static int operand_value(rdb_tape *t, OperandPlan &o, MatRef<T> &m) {
 }
 
 // ------------------------------------------------------------------------------------------ forward
+static void plan_col_panels(int64_t rows, int64_t cols, int64_t width[4]);
+static int settle_uploads(rdb_tape *t, int keep);
+static int droot(rdb_tape *t, int b);
 template <typename T>
 static int expr_forward(rdb_tape *t, InstrPlan &I, bool reduce, int order) {
     Buf &out = t->bufs[I.rec.out];
@@ -308,6 +318,25 @@ static int expr_forward(rdb_tape *t, InstrPlan &I, bool reduce, int order) {
 template <typename T>
 static int forward_pass(rdb_tape *t, int order = 1) {
     const size_t n = t->instrs.size();
+    // An input that is still arriving in column panels (rdb_tape_set_input) is consumed panel by panel when its first reader
+    // is a `*` that has it as the plain right operand: out[:, panel] = op(A) * b[:, panel] starts as soon as the panel has
+    // landed, so the GEMM hides behind the upload.  Every other pending input is waited for here.
+    int streamed = -1, streamed_at = -1;
+    if (order == 1 && t->last_upload >= 0 && t->bufs[t->last_upload].up_n > 0) {
+        const int cand = t->last_upload;
+        for (size_t i = 0; i < n && streamed_at < 0; ++i) {
+            InstrPlan &I = t->instrs[i];
+            bool reads = false;
+            if (I.blk) { for (int r = 0; r < I.blk->n_ref; ++r) reads |= droot(t, I.blk->refbufs[r]) == cand; }
+            else for (int a = 0; a < I.rec.n_in; ++a) reads |= droot(t, I.in[a].rec.buffer) == cand;
+            if (!reads) continue;
+            streamed_at = (int)i;
+            if (!I.blk && I.rec.opcode == OP_MUL && I.in[1].rec.buffer == cand && I.in[1].mode == OPM_PLAIN &&
+                droot(t, I.in[0].rec.buffer) != cand && I.in[1].cols == t->bufs[cand].up_c0[t->bufs[cand].up_n])
+                streamed = cand;
+        }
+    }
+    OK(settle_uploads(t, streamed));
     for (size_t i = 0; i < n; ++i) {
         InstrPlan &I = t->instrs[i];
         Buf &out = t->bufs[I.rec.out];
@@ -328,6 +357,17 @@ static int forward_pass(rdb_tape *t, int order = 1) {
                 OK(operand_value<T>(t, I.in[1], B));
                 int64_t M = I.in[0].rows, K = I.in[0].cols, N = I.in[1].cols;
                 StepTimer tm(t, "gemm_forward", (double)(M * K + K * N + M * N) * t->es, 2.0 * M * N * K);
+                if (streamed >= 0 && (int)i == streamed_at) {
+                    Buf &bi = t->bufs[streamed];
+                    for (int p = 0; p < bi.up_n; ++p) {
+                        const int64_t c0 = bi.up_c0[p], nc = bi.up_c0[p + 1] - c0;
+                        CU(cudaStreamWaitEvent(S(t), bi.up_ev[p], 0));
+                        g_tag_a = operand_tag(t, I.in[0]);
+                        KL(t, gemm_t<T>(S(t), A.stored_t, false, M, nc, K, (T)1, A.ptr, A.ld, B.ptr + c0 * B.ld, B.ld, (T)0, (T *)out.val + c0 * M, M));
+                    }
+                    bi.up_n = 0;
+                    break;
+                }
                 g_tag_a = operand_tag(t, I.in[0]); g_tag_b = operand_tag(t, I.in[1]);
                 KL(t, gemm_t<T>(S(t), A.stored_t, B.stored_t, M, N, K, (T)1, A.ptr, A.ld, B.ptr, B.ld, (T)0, (T *)out.val, M));
             } break;
@@ -452,6 +492,43 @@ static int dmaterialize(rdb_tape *t, int b, int64_t R, bool mark_live) {
     if (t->dz[r] && t->bufs[r].der) {
         CU(cudaMemsetAsync(t->bufs[r].der, 0, (size_t)(t->bufs[r].size * R) * t->es, S(t)));
         if (mark_live) t->dz[r] = 0;
+    }
+    return RDB_OK;
+}
+
+// Column panels, in 64-column tiles, chosen so that every panel's 128x64 GEMM tile count fills whole waves of the 148 SMs
+// (a 4096^2 GEMM is 13.8 waves; four equal panels would be 4 x 3.46 -> 16).  width[i] = columns of panel i (0 = unused).
+static void plan_col_panels(int64_t rows, int64_t cols, int64_t width[4]) {
+    const int64_t rt = (rows + 127) / 128, C = (cols + 63) / 64;
+    auto waves = [&](int64_t x) { return (rt * x + 147) / 148; };
+    int64_t best = -1;
+    width[0] = width[1] = width[2] = width[3] = 0;
+    for (int P = 3; P <= 4; ++P) {
+        const int64_t mid = C / P;
+        for (int64_t x1 = std::max<int64_t>(1, mid - 6); x1 <= mid + 6; ++x1)
+            for (int64_t x2 = std::max<int64_t>(1, mid - 6); x2 <= mid + 6; ++x2)
+                for (int64_t x3 = (P == 4 ? std::max<int64_t>(1, mid - 6) : 0); x3 <= (P == 4 ? mid + 6 : 0); ++x3) {
+                    const int64_t last = C - x1 - x2 - x3;
+                    if (last < 1 || last > mid + 6) continue;
+                    // total waves, then the smallest last panel (its copy is the tail of the call)
+                    const int64_t cost = (waves(x1) + waves(x2) + (x3 ? waves(x3) : 0) + waves(last)) * 4096 + last;
+                    if (best < 0 || cost < best) { best = cost; width[0] = x1; width[1] = x2; width[2] = x3 ? x3 : last; width[3] = x3 ? last : 0; }
+                }
+    }
+    if (best < 0) { const int64_t q = (C + 3) / 4; width[0] = width[1] = width[2] = q; width[3] = C > 3 * q ? C - 3 * q : 0; }
+    int64_t c0 = 0;
+    for (int i = 0; i < 4; ++i) { width[i] = std::max<int64_t>(0, std::min<int64_t>(width[i] * 64, cols - c0)); c0 += width[i]; }
+    if (c0 < cols) width[3] += cols - c0;
+}
+
+// Inputs uploaded in panels (rdb_tape_set_input): make the main stream wait for them.  `keep` is left pending (its consumer
+// waits panel by panel).
+static int settle_uploads(rdb_tape *t, int keep) {
+    for (size_t b = 0; b < t->bufs.size(); ++b) {
+        Buf &B = t->bufs[b];
+        if (B.up_n == 0 || (int)b == keep) continue;
+        CU(cudaStreamWaitEvent(S(t), B.up_ev[B.up_n - 1], 0));     // panels arrive in order on one stream
+        B.up_n = 0;
     }
     return RDB_OK;
 }
@@ -598,31 +675,12 @@ static int mul_reverse(rdb_tape *t, int k, int64_t R) {
             if (pj < 0) return 0;
             ptag = new_delta_tag();
         } else if (panel_count(o.rec.buffer, rows, cols, 1) == 1) return 0;
-        // panel widths in 64-column tiles, chosen so that every panel's 128x64 tile count fills whole waves of the 148 SMs
-        // (a 4096^2 GEMM is 13.8 waves; four equal panels would be 4 x 3.46 -> 16)
-        int64_t width[4] = {0, 0, 0, 0};
-        {
-            const int64_t rt = (rows + 127) / 128, C = (cols + 63) / 64;
-            auto waves = [&](int64_t x) { return (rt * x + 147) / 148; };
-            int64_t best = -1;
-            for (int P = 3; P <= 4; ++P) {
-                const int64_t mid = C / P;
-                for (int64_t x1 = std::max<int64_t>(1, mid - 6); x1 <= mid + 6; ++x1)
-                    for (int64_t x2 = std::max<int64_t>(1, mid - 6); x2 <= mid + 6; ++x2)
-                        for (int64_t x3 = (P == 4 ? std::max<int64_t>(1, mid - 6) : 0); x3 <= (P == 4 ? mid + 6 : 0); ++x3) {
-                            const int64_t last = C - x1 - x2 - x3;
-                            if (last < 1 || last > mid + 6) continue;
-                            // total waves, then the smallest last panel (its D2H copy is the tail of the call)
-                            const int64_t cost = (waves(x1) + waves(x2) + (x3 ? waves(x3) : 0) + waves(last)) * 4096 + last;
-                            if (best < 0 || cost < best) { best = cost; width[0] = x1; width[1] = x2; width[2] = x3 ? x3 : last; width[3] = x3 ? last : 0; }
-                        }
-            }
-            if (best < 0) { const int64_t q = (C + 3) / 4; width[0] = width[1] = width[2] = q; width[3] = C > 3 * q ? C - 3 * q : 0; }
-        }
+        int64_t width[4];
+        plan_col_panels(rows, cols, width);
         int64_t c0 = 0;
         for (int pi = 0; pi < 4 && c0 < cols; ++pi) {
             if (width[pi] <= 0) continue;
-            const int64_t nc = std::min<int64_t>(width[pi] * 64, cols - c0);
+            const int64_t nc = width[pi];
             OK(mul_acc_cols<T>(t, I, side, c0, nc, beta, dtag));
             if (pj >= 0) OK(mul_acc_cols<T>(t, t->instrs[pj], ps, c0, nc, (T)1, ptag));
             OK(panel_copy(o.rec.buffer, c0 * rows, nc * rows));
@@ -1675,6 +1733,8 @@ void rdb_tape_destroy(rdb_tape *t) {
     if (t->ev1) cudaEventDestroy(t->ev1);
     if (t->gexec) cudaGraphExecDestroy(t->gexec);
     for (auto &e : t->early.ev) if (e) cudaEventDestroy(e);
+    if (t->ctx && t->ctx->upload_stream) cudaStreamSynchronize(t->ctx->upload_stream);
+    for (auto &b : t->bufs) for (auto &e : b.up_ev) if (e) cudaEventDestroy(e);
     ctx_release(t->ctx);
     delete t;
 }
@@ -1683,7 +1743,31 @@ int rdb_tape_set_input(rdb_tape *t, int slot, const void *data, int is_device) {
     if (!t || !data) return fail(RDB_EINVAL, "null argument");
     if (slot < 0 || (size_t)slot >= t->inputs.size()) return fail(RDB_EINVAL, "input slot %d out of range", slot);
     Buf &b = t->bufs[t->inputs[slot]];
-    CU(cudaMemcpyAsync(b.val, data, (size_t)b.size * t->es, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, S(t)));
+    static const bool stream_inputs = [] { const char *e = getenv("RDB_STREAM_INPUTS"); return !(e && e[0] == '0'); }();
+    const bool matrix = b.nd == 2 && b.dims[0] * b.dims[1] == b.size && b.alias_of < 0;
+    if (!is_device && stream_inputs && matrix && b.dims[1] >= 2048 && b.size * (int64_t)t->es >= (32 << 20)) {
+        // value!(input, x) as column panels on the upload stream; the forward sweep waits per panel or for all (forward_pass)
+        rdb_ctx *c = t->ctx;
+        if (!c->upload_stream) CU(cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking));
+        int64_t width[4];
+        plan_col_panels(b.dims[0], b.dims[1], width);
+        b.up_n = 0;
+        int64_t c0 = 0;
+        for (int p = 0; p < 4; ++p) {
+            if (width[p] <= 0) continue;
+            const size_t off = (size_t)c0 * b.dims[0] * t->es, nb = (size_t)width[p] * b.dims[0] * t->es;
+            CU(cudaMemcpyAsync((char *)b.val + off, (const char *)data + off, nb, cudaMemcpyHostToDevice, c->upload_stream));
+            if (!b.up_ev[b.up_n]) CU(cudaEventCreateWithFlags(&b.up_ev[b.up_n], cudaEventDisableTiming));
+            CU(cudaEventRecord(b.up_ev[b.up_n], c->upload_stream));
+            b.up_c0[b.up_n] = c0;
+            c0 += width[p];
+            b.up_c0[++b.up_n] = c0;
+        }
+        t->last_upload = t->inputs[slot];
+    } else {
+        if (b.up_n > 0) { CU(cudaStreamWaitEvent(S(t), b.up_ev[b.up_n - 1], 0)); b.up_n = 0; }
+        CU(cudaMemcpyAsync(b.val, data, (size_t)b.size * t->es, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, S(t)));
+    }
     bump_version(t, t->inputs[slot]);
     t->forward_valid = false;
     return RDB_OK;
@@ -1696,6 +1780,7 @@ int rdb_forward(rdb_tape *t) {
 }
 int rdb_reverse_scalar_seed(rdb_tape *t) {
     if (!t) return fail(RDB_EINVAL, "null tape");
+    OK(settle_uploads(t, -1));
     OK(DISPATCH(t, seed_scalar_and_reverse, t));
     CU(cudaStreamSynchronize(S(t)));
     return RDB_OK;
@@ -1718,6 +1803,7 @@ int64_t rdb_buffer_size(rdb_tape *t, int b) {
 }
 int rdb_get_value(rdb_tape *t, int b, void *dst) {
     if (!t || !dst || b < 0 || (size_t)b >= t->bufs.size()) return fail(RDB_EINVAL, "bad buffer id");
+    OK(settle_uploads(t, -1));
     CU(cudaMemcpyAsync(dst, t->bufs[b].val, (size_t)t->bufs[b].size * t->es, cudaMemcpyDeviceToHost, S(t)));
     CU(cudaStreamSynchronize(S(t)));
     return RDB_OK;
