@@ -326,7 +326,7 @@ def main():
         peak_src = (f"2 x {peak_tag} (kind::i8 issues at twice the bf16 rate; nominal dense 4500); cuBLASLt int8 GEMM 8192^3 "
                     f"(torch._int_mm) measured in this run = {i8:.0f}" if i8 else
                     f"2 x {peak_tag} (kind::i8 issues at twice the bf16 rate; nominal dense 4500); torch._int_mm unavailable")
-        traffic = 1.056e9 + 0.1285e9    # dram__bytes_read+write per 4096^3 launch, ncu --set full (profiles/prof_ozaki2c_r1b.txt)
+        traffic = 1.0387e9 + 0.1262e9   # dram__bytes_read+write per 4096^3 launch, ncu --set full (profiles/prof_ozaki2c_r1c.txt)
     elif args.dtype == "f64":
         ops_per_flop = 1.0
         kernel = "d64::dgemm_dmma_kernel (mma.sync m8n8k4 f64 = SASS DMMA.8x8x4)"

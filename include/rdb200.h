@@ -44,7 +44,7 @@ typedef struct rdb_options {
     int32_t profile;          /* 1 = record per-step CUDA-event timings for rdb_tape_stats           */
     int32_t gemm_f64_mode;    /* FP64 `*` kernels: 0 = auto (exact int8 slices on tcgen05 when eligible,
                                  DMMA otherwise), 1 = DMMA only                                        */
-    int32_t ozaki_slices;     /* 7-bit slices per FP64 operand for the tcgen05 path (0 = default 8)   */
+    int32_t ozaki_slices;     /* int8 slices per FP64 operand for the tcgen05 path (0 = default: 7 of 8 bits) */
     int32_t reserved[2];
 } rdb_options;
 
@@ -58,7 +58,7 @@ void rdb_ctx_destroy(rdb_ctx *);
 int rdb_ctx_set_stream(rdb_ctx *, void *cuda_stream);
 int rdb_ctx_synchronize(rdb_ctx *);
 /* FP64 kernel selection for rdb_gemm on this context (tapes carry their own in rdb_options): mode 0 = auto,
- * 1 = DMMA only; slices = 7-bit slices per operand of the tcgen05 int8 path (0 = default 8, at most 8). */
+ * 1 = DMMA only; slices = int8 slices per operand of the tcgen05 int8 path (0 = default: 7 slices of 8 bits, at most 8). */
 int rdb_ctx_set_gemm_f64_mode(rdb_ctx *, int mode, int slices);
 
 /* ---- tape life cycle ----------------------------------------------------------------------------- */
