@@ -238,22 +238,51 @@ cudaError_t launch_axpy(cudaStream_t s, T *dst, const T *src, T sign, int64_t n,
     return cudaGetLastError();
 }
 
-template <typename T, bool OVERWRITE>
+// blockIdx.y = seed r; 128-bit stores when a seed's row is 16-byte aligned (no per-element division, one broadcast load)
+template <typename T, bool OVERWRITE, bool VEC>
 __global__ void __launch_bounds__(kThreads)
-k_acc_scalar(T *__restrict__ dst, int64_t n, int64_t R, const T *__restrict__ delta, T scale) {
-    int64_t tot = n * R;
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
-    for (; i < tot; i += st) {
-        T d = scale * delta[i / n];
-        dst[i] = OVERWRITE ? d : dst[i] + d;
+k_acc_scalar(T *__restrict__ dst, int64_t n, const T *__restrict__ delta, T scale) {
+    const int64_t r = blockIdx.y;
+    const T d = scale * delta[r];
+    T *p = dst + r * n;
+    const int64_t st = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (VEC) {
+        constexpr int NV = Vec<T>::N;
+        using V = typename Vec<T>::type;
+        V *pv = reinterpret_cast<V *>(p);
+        T dv[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) dv[k] = d;
+        const V fillv = vec_pack<T>(dv);
+        for (const int64_t nv = n / NV; i < nv; i += st) {
+            if (OVERWRITE) pv[i] = fillv;
+            else {
+                T o[NV];
+                vec_unpack<T>(pv[i], o);
+#pragma unroll
+                for (int k = 0; k < NV; ++k) o[k] = o[k] + d;
+                pv[i] = vec_pack<T>(o);
+            }
+        }
+    } else {
+        for (; i < n; i += st) p[i] = OVERWRITE ? d : p[i] + d;
     }
 }
 template <typename T>
 cudaError_t launch_acc_scalar(cudaStream_t s, T *dst, int64_t n, int64_t R, const T *delta, T scale, bool overwrite) {
     if (n * R <= 0) return cudaSuccess;
-    int grid = grid_for(n * R, 4);
-    if (overwrite) k_acc_scalar<T, true><<<grid, kThreads, 0, s>>>(dst, n, R, delta, scale);
-    else k_acc_scalar<T, false><<<grid, kThreads, 0, s>>>(dst, n, R, delta, scale);
+    if (R > 65535) return cudaErrorInvalidValue;
+    constexpr int NV = Vec<T>::N;
+    const bool vec = n % NV == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    const int64_t work = vec ? n / NV : n;
+    int64_t gx = (work + kThreads * 4 - 1) / (kThreads * 4);
+    const int64_t capx = std::max<int64_t>(1, ((int64_t)kSMs * 16 + R - 1) / R);
+    if (gx > capx) gx = capx;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)R);
+    if (overwrite) { if (vec) k_acc_scalar<T, true, true><<<grid, kThreads, 0, s>>>(dst, n, delta, scale); else k_acc_scalar<T, true, false><<<grid, kThreads, 0, s>>>(dst, n, delta, scale); }
+    else { if (vec) k_acc_scalar<T, false, true><<<grid, kThreads, 0, s>>>(dst, n, delta, scale); else k_acc_scalar<T, false, false><<<grid, kThreads, 0, s>>>(dst, n, delta, scale); }
     return cudaGetLastError();
 }
 
