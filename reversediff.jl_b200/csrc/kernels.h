@@ -135,6 +135,9 @@ struct ScalarBlock {
     // live in global memory (read >= 2 blocks after they are produced), and planner statistics
     int64_t n_sblocks = 0, n_grow = 0, n_near = 0, n_staged = 0, n_direct = 0;
     size_t der_bytes = 0;
+    // bundle ("VLIW") plans for deep graphs: forward, and reverse with R < 16 seeds (scalar.cu)
+    int64_t n_fbundles = 0, n_rbundles = 0, n_lit = 0;
+    bool fwd_bundles = false, rev_bundles = false;
     std::vector<int32_t> refbufs;               // tape buffer ids referenced (leaf origins and export targets)
     std::vector<char> ref_has_leaf, ref_has_export;
     std::vector<int64_t> ref_export_count;      // elements of the buffer this block exports into
@@ -161,6 +164,8 @@ struct ScalarBlock {
     void *d_epart = nullptr;                    // T[n_edges] partials in reverse edge order
     int4 *d_recA = nullptr, *d_recB = nullptr, *d_recC = nullptr, *d_recD = nullptr;   // per schedule position (scalar.cu, "streaming plan")
     int2 *d_pf = nullptr;                       // per schedule block: what to prefetch into the staging buffer
+    int4 *d_vfA = nullptr, *d_vfB = nullptr, *d_vfC = nullptr, *d_vrA = nullptr, *d_vrB = nullptr;   // bundle records
+    int32_t *d_vsrc = nullptr;                  // bundle reverse: operand sources of every edge (same order as d_esrc)
     int32_t *d_tsrc = nullptr;                  // operand codes of every edge for the streaming kernel (same order as d_esrc)
     void *d_der = nullptr;                      // adjoints of instruction outputs: T[n x R] at [i*R + r] (R < 16), T[n_grow x R] (R >= 16)
 };

@@ -68,9 +68,11 @@ __global__ void __launch_bounds__(kFwdThreads) k_scalar_forward(const FwdP P) {
 }
 
 template <typename T>
-__global__ void k_scalar_pull(T *val, const int32_t *leaf_ord, const int64_t *leaf_elem, void *const *ext_val, int64_t n_leaf) {
+__global__ void k_scalar_pull(T *val, const int32_t *leaf_ord, const int64_t *leaf_elem, void *const *ext_val, int64_t n_leaf,
+                              int64_t n_instr, const double *fconst, int64_t n_lit) {
     int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (l < n_leaf) val[l] = reinterpret_cast<const T *>(ext_val[leaf_ord[l]])[leaf_elem[l]];
+    else if (l < n_leaf + n_lit) val[n_instr + l] = (T)fconst[l - n_leaf];      // literal pool behind the slots (bundle kernels)
 }
 template <typename T>
 __global__ void k_scalar_export(const T *val, const int32_t *slot, const int32_t *ord, const int64_t *elem, void *const *ext_val,
@@ -277,6 +279,203 @@ __global__ void __launch_bounds__(kFwdThreads) k_scalar_reverse_slots(const RevP
     }
 }
 
+// =================================================================================================== bundle ("VLIW") kernels
+// One seed has no parallelism but the tape's dataflow, and a scalar tape is full of long dependent chains (acc += term: one level
+// per link), so the level-parallel kernels above pay a block barrier plus an L2 round trip per link.  For deep graphs the host
+// list-schedules the dataflow into BUNDLES of up to 32 mutually independent slots (critical path first: a chain link goes out
+// every bundle while the other lanes work ahead on independent terms) and ONE warp executes bundle after bundle: lanes are the
+// slots of a bundle, __syncwarp() is the only synchronisation, values of the last 64 bundles sit in a shared-memory ring, the
+// records of bundle t+2 and the global operands of bundle t+1 (leaves, literals, far values, partials) load while bundle t
+// computes.  A chain link costs a shared-memory round trip plus its arithmetic.
+constexpr int kVRing = 64;            // bundles whose results stay in the ring
+constexpr unsigned kVGlobal = 0u, kVRingSrc = 1u, kVLiteral = 2u, kVNone = 3u;
+constexpr int kVEmpty = INT_MIN;
+
+// One scalar function evaluation = one ForwardDiff Dual{2} evaluation (scalars.jl:96-116).  Single-operation functions (what
+// the DiffRules overloads record: +, -, *, /, ^, sin, ...) take a register-only path with the SAME formulas, in the same order,
+// as the bytecode interpreter of expr_eval.cuh applied to unit partials; @forward closures run the interpreter.
+template <typename T>
+__device__ __forceinline__ void eval_scalar(const int4 *__restrict__ ops, int e_off, int n_ops, int n_args, const int4 op,
+                                            const double *__restrict__ fc, const T *x, T &v, T *d) {
+    if (n_ops != 1) {
+        T h[1];
+        eval_expr<T, 2, 1>(ops + e_off, n_ops, fc, x, v, d, h, n_args);
+        return;
+    }
+    const int code = op.x, a = op.y & 1, b = op.z & 1, imm = op.w;
+    const T xa = x[a], xb = x[b];
+    const T da0 = a == 0 ? (T)1 : (T)0, da1 = a == 1 ? (T)1 : (T)0, db0 = b == 0 ? (T)1 : (T)0, db1 = b == 1 ? (T)1 : (T)0;
+    T f0 = (T)0, f1 = (T)0;
+    switch (code) {
+        case E_CONST: v = (T)fc[imm]; d[0] = d[1] = (T)0; return;
+        case E_ARG: v = x[imm & 1]; d[0] = (imm & 1) == 0 ? (T)1 : (T)0; d[1] = (imm & 1) == 1 ? (T)1 : (T)0; return;
+        case E_ADD: v = xa + xb; d[0] = da0 + (T)1 * db0; d[1] = da1 + (T)1 * db1; return;
+        case E_SUB: v = xa - xb; d[0] = da0 + (T)-1 * db0; d[1] = da1 + (T)-1 * db1; return;
+        case E_MUL: v = xa * xb; d[0] = da0 * xb + xa * db0; d[1] = da1 * xb + xa * db1; return;
+        case E_DIV: { const T q = xa / xb, ib = (T)1 / xb; v = q; d[0] = (da0 - q * db0) * ib; d[1] = (da1 - q * db1) * ib; } return;
+        case E_POW: { const T y = M<T>::pow_(xa, xb), fa = xb * M<T>::pow_(xa, xb - (T)1), fb = y * M<T>::log_(xa);
+                      v = y; d[0] = fa * da0 + fb * db0; d[1] = fa * da1 + fb * db1; } return;
+        case E_MAX: case E_MIN: { const bool pa = code == E_MAX ? (xa > xb) : (xa < xb); v = pa ? xa : xb; d[0] = pa ? da0 : db0; d[1] = pa ? da1 : db1; } return;
+        case E_NEG: f0 = -xa; f1 = (T)-1; break;
+        case E_POWI: f0 = powi(xa, imm); f1 = imm != 0 ? (T)imm * powi(xa, imm - 1) : (T)0; break;
+        case E_TANH: { const T t = M<T>::tanh_(xa); f0 = t; f1 = (T)1 - t * t; } break;
+        case E_EXP: { const T e = M<T>::exp_(xa); f0 = e; f1 = e; } break;
+        case E_LOG: f0 = M<T>::log_(xa); f1 = (T)1 / xa; break;
+        case E_SQRT: { const T q = M<T>::sqrt_(xa); f0 = q; f1 = (T)1 / ((T)2 * q); } break;
+        case E_SIN: f0 = M<T>::sin_(xa); f1 = M<T>::cos_(xa); break;
+        case E_COS: f0 = M<T>::cos_(xa); f1 = -M<T>::sin_(xa); break;
+        default: {                                   // anything else: the interpreter is the definition
+            T h[1];
+            eval_expr<T, 2, 1>(ops + e_off, n_ops, fc, x, v, d, h, n_args);
+            return;
+        }
+    }
+    v = f0; d[0] = f1 * da0; d[1] = f1 * da1;
+}
+
+// forward record of (bundle, lane):  A = (instruction or kVEmpty, source a, source b, 0)   sources: kind << 30 | payload -
+//   kVGlobal: index into val[] (a leaf, a literal - the pool is appended to val[] - or an instruction output older than the
+//   ring), kVRingSrc: ring entry
+//   B = (where partial a goes in epart or -1, same for b, bytecode offset, n_ops | n_args << 16)     C = the first bytecode operation
+// Software pipeline, one cp.async group per bundle: records travel kVRecAhead bundles ahead into a shared-memory ring of
+// kVRecSlots, the global operands of a bundle kVOpAhead bundles ahead (their addresses come from the record, which has landed by
+// then); wait_group keeps the last kVOpAhead - 1 groups in flight.
+constexpr int kVRecAhead = 12, kVRecSlots = 16, kVOpAhead = 6, kVOpSlots = 8;
+struct VFwdP {
+    const int4 *recA, *recB, *recC; const int4 *ops; const double *fconst; void *val; void *epart; int64_t n_leaf; int64_t n_bundles;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_keep() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T>
+__global__ void __launch_bounds__(32) k_scalar_forward_bundles(const VFwdP P) {
+    __shared__ __align__(16) T ring[kVRing * 32];
+    __shared__ int4 srec[kVRecSlots][3][32];
+    __shared__ __align__(16) T sop[kVOpSlots][2][32];
+    const int lane = threadIdx.x;
+    T *val = reinterpret_cast<T *>(P.val);
+    T *epart = reinterpret_cast<T *>(P.epart);
+    const int64_t T_ = P.n_bundles;
+    for (int64_t t = -kVRecAhead; t < T_; ++t) {
+        cp_async_wait_keep<kVOpAhead - 1>();                       // groups of iterations <= t - kVOpAhead have landed
+        int4 A0 = make_int4(kVEmpty, 0, 0, 0), B0 = A0, C0 = A0;
+        if (t >= 0) { A0 = srec[t & (kVRecSlots - 1)][0][lane]; B0 = srec[t & (kVRecSlots - 1)][1][lane]; C0 = srec[t & (kVRecSlots - 1)][2][lane]; }
+        {                                                          // records of bundle t + kVRecAhead (tables are padded)
+            const int64_t tr = t + kVRecAhead, q = tr * 32 + lane;
+            const int sl = (int)(tr & (kVRecSlots - 1));
+            cp_async16(&srec[sl][0][lane], P.recA + q); cp_async16(&srec[sl][1][lane], P.recB + q); cp_async16(&srec[sl][2][lane], P.recC + q);
+        }
+        const int64_t to = t + kVOpAhead;
+        if (to >= 0 && to < T_) {                                  // pull_value! of bundle t + kVOpAhead: leaves, literals, old slots
+            const int4 A = srec[to & (kVRecSlots - 1)][0][lane];
+            if (A.x != kVEmpty) {
+                if (((unsigned)A.y >> 30) == kVGlobal) cp_async_small<sizeof(T)>(&sop[to & (kVOpSlots - 1)][0][lane], val + (A.y & 0x3fffffff));
+                if (((unsigned)A.z >> 30) == kVGlobal) cp_async_small<sizeof(T)>(&sop[to & (kVOpSlots - 1)][1][lane], val + (A.z & 0x3fffffff));
+            }
+        }
+        cp_async_commit();
+        if (A0.x != kVEmpty) {
+            T x[2], v, d[2];
+            const unsigned ka = (unsigned)A0.y >> 30, kb = (unsigned)A0.z >> 30;
+            x[0] = ka == kVRingSrc ? ring[A0.y & 0x3fffffff] : (ka == kVGlobal ? sop[t & (kVOpSlots - 1)][0][lane] : (T)0);
+            x[1] = kb == kVRingSrc ? ring[A0.z & 0x3fffffff] : (kb == kVGlobal ? sop[t & (kVOpSlots - 1)][1][lane] : (T)0);
+            eval_scalar<T>(P.ops, B0.z, B0.w & 0xffff, B0.w >> 16, C0, P.fconst, x, v, d);
+            val[P.n_leaf + A0.x] = v;                                       // value!(output, ...)
+            ring[(int)(t & (kVRing - 1)) * 32 + lane] = v;
+            if (B0.x >= 0) epart[B0.x] = d[0];                              // cache[] = partials, where the reverse sweep reads them
+            if (B0.y >= 0) epart[B0.y] = d[1];
+        }
+        __syncwarp();
+    }
+    cp_async_wait_all();
+}
+
+// reverse record of (bundle, lane):  A = (slot: >= 0 instruction output, < 0 leaf ~l, kVEmpty; source of edge 0; source of edge 1;
+//   number of edges | has-exports << 24)   sources: kVGlobal: consumer instruction (adjoint at der[c*R + r]), kVRingSrc: ring entry
+//   B = (first edge in vsrc/epart; leaf: ordinal of the origin buffer; leaf: element, low word; high word)
+struct VRevP {
+    const int4 *recA, *recB; const int32_t *vsrc; const void *epart;
+    const int64_t *xoff; const int32_t *xord; const int64_t *xelem;
+    void *const *ext_der; const int64_t *ext_size;
+    void *der; int64_t R; int64_t n_bundles; int leaves_zero;
+};
+
+// grid.x = seeds (R < 16): one warp per seed, the seeds share nothing.  Same pipeline as the forward kernel; the staged operands
+// of a bundle are its two partials, the adjoints it reads from global memory and a leaf's current origin.deriv[index].
+template <typename T>
+__global__ void __launch_bounds__(32) k_scalar_reverse_bundles(const VRevP P) {
+    __shared__ __align__(16) T ring[kVRing * 32];
+    __shared__ int4 srec[kVRecSlots][2][32];
+    __shared__ __align__(16) T sop[kVOpSlots][5][32];
+    const int lane = threadIdx.x;
+    const int64_t R = P.R, r = blockIdx.x;
+    T *der = reinterpret_cast<T *>(P.der);
+    const T *epart = reinterpret_cast<const T *>(P.epart);
+    const int64_t T_ = P.n_bundles;
+    auto leaf_ptr = [&](const int4 &Bq) -> T * {
+        const int64_t elem = (int64_t)(unsigned)Bq.z | ((int64_t)Bq.w << 32);
+        return reinterpret_cast<T *>(P.ext_der[Bq.y]) + elem + r * P.ext_size[Bq.y];              // origin.deriv[index]
+    };
+    for (int64_t t = -kVRecAhead; t < T_; ++t) {
+        cp_async_wait_keep<kVOpAhead - 1>();
+        int4 A0 = make_int4(kVEmpty, 0, 0, 0), B0 = A0;
+        if (t >= 0) { A0 = srec[t & (kVRecSlots - 1)][0][lane]; B0 = srec[t & (kVRecSlots - 1)][1][lane]; }
+        {
+            const int64_t tr = t + kVRecAhead, q = tr * 32 + lane;
+            const int sl = (int)(tr & (kVRecSlots - 1));
+            cp_async16(&srec[sl][0][lane], P.recA + q); cp_async16(&srec[sl][1][lane], P.recB + q);
+        }
+        const int64_t to = t + kVOpAhead;
+        if (to >= 0 && to < T_) {
+            const int4 A = srec[to & (kVRecSlots - 1)][0][lane], Bq = srec[to & (kVRecSlots - 1)][1][lane];
+            if (A.x != kVEmpty) {
+                T(*o)[32] = sop[to & (kVOpSlots - 1)];
+                const int ne = A.w & 0xffffff;
+                if (ne > 0) {
+                    cp_async_small<sizeof(T)>(&o[0][lane], epart + Bq.x);
+                    if (((unsigned)A.y >> 30) == kVGlobal) cp_async_small<sizeof(T)>(&o[2][lane], der + (int64_t)(A.y & 0x3fffffff) * R + r);
+                }
+                if (ne > 1) {
+                    cp_async_small<sizeof(T)>(&o[1][lane], epart + Bq.x + 1);
+                    if (((unsigned)A.z >> 30) == kVGlobal) cp_async_small<sizeof(T)>(&o[3][lane], der + (int64_t)(A.z & 0x3fffffff) * R + r);
+                }
+                if (A.x < 0 && !P.leaves_zero) cp_async_small<sizeof(T)>(&o[4][lane], leaf_ptr(Bq));   // pull_deriv!
+            }
+        }
+        cp_async_commit();
+        if (A0.x != kVEmpty) {
+            T(*o)[32] = sop[t & (kVOpSlots - 1)];
+            const int ne = A0.w & 0xffffff;
+            T acc = (A0.x < 0 && !P.leaves_zero) ? o[4][lane] : (T)0;
+            if (A0.x >= 0 && (A0.w >> 24)) {
+                // adjoints that instructions AFTER the block pushed into an exported slot (one TrackedReal, one deriv field)
+                for (int64_t x = P.xoff[A0.x]; x < P.xoff[A0.x + 1]; ++x) {
+                    const int oo = P.xord[x];
+                    T *p = reinterpret_cast<T *>(P.ext_der[oo]) + P.xelem[x] + r * P.ext_size[oo];
+                    acc = acc + *p; *p = (T)0;                                                      // ... and unseed!(output)
+                }
+            }
+            // increment_deriv!(slot, deriv(out_c) * partial) for every consumer c, in the reference's order
+            if (ne > 0) acc = acc + (((unsigned)A0.y >> 30) == kVRingSrc ? ring[A0.y & 0x3fffffff] : o[2][lane]) * o[0][lane];
+            if (ne > 1) acc = acc + (((unsigned)A0.z >> 30) == kVRingSrc ? ring[A0.z & 0x3fffffff] : o[3][lane]) * o[1][lane];
+            for (int e = 2; e < ne; ++e) {
+                const int c = P.vsrc[B0.x + e];
+                const T a = ((unsigned)c >> 30) == kVRingSrc ? ring[c & 0x3fffffff] : der[(int64_t)(c & 0x3fffffff) * R + r];
+                acc = acc + a * epart[B0.x + e];
+            }
+            ring[(int)(t & (kVRing - 1)) * 32 + lane] = acc;
+            if (A0.x >= 0) der[(int64_t)A0.x * R + r] = acc;                                        // the slot's final adjoint
+            else *leaf_ptr(B0) = acc;                                                               // push_deriv!
+        }
+        __syncwarp();
+    }
+    cp_async_wait_all();
+}
+
 // levels -> launches: a wide level alone on a full grid, runs of narrow levels on one CTA (block-level barrier between levels)
 std::vector<ScalarSeg> plan_segments(const std::vector<int64_t> &off) {
     std::vector<ScalarSeg> segs;
@@ -296,6 +495,38 @@ std::vector<ScalarSeg> plan_segments(const std::vector<int64_t> &off) {
         }
     }
     return segs;
+}
+
+// List scheduling into bundles of <= 32 nodes: a node runs in a LATER bundle than every predecessor; among the ready nodes the
+// one with the longest path to a sink goes first (ties: lower id).  succ = CSR successor lists, indeg = predecessor edge counts.
+struct BundlePlan { int64_t n_bundles = 0; std::vector<int32_t> bundle, lane; };
+BundlePlan schedule_bundles(int64_t N, const std::vector<int64_t> &succ_off, const std::vector<int32_t> &succ, std::vector<int32_t> indeg,
+                            const std::vector<int32_t> &height) {
+    BundlePlan bp;
+    bp.bundle.assign(N, -1); bp.lane.assign(N, -1);
+    typedef std::pair<int32_t, int32_t> Key;                     // (height, -id): max-heap
+    std::vector<Key> heap, pending;
+    for (int64_t v = 0; v < N; ++v) if (indeg[v] == 0) heap.push_back(Key(height[v], -(int32_t)v));
+    std::make_heap(heap.begin(), heap.end());
+    int64_t done = 0, t = 0;
+    while (done < N) {
+        if (heap.empty()) break;                                  // cannot happen on a DAG
+        int k = 0;
+        pending.clear();
+        while (k < 32 && !heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end());
+            const int32_t v = -heap.back().second;
+            heap.pop_back();
+            bp.bundle[v] = (int32_t)t; bp.lane[v] = k++;
+            ++done;
+            for (int64_t e = succ_off[v]; e < succ_off[v + 1]; ++e)
+                if (--indeg[succ[e]] == 0) pending.push_back(Key(height[succ[e]], -succ[e]));
+        }
+        for (const Key &x : pending) { heap.push_back(x); std::push_heap(heap.begin(), heap.end()); }
+        ++t;
+    }
+    bp.n_bundles = done == N ? t : -1;
+    return bp;
 }
 
 template <typename U>
@@ -539,6 +770,108 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
             fprintf(stderr, "[rdb scalar] n=%lld leaves=%lld edges=%lld blocks=%lld global_rows=%lld near=%lld staged=%lld direct=%lld\n", (long long)n,
                     (long long)nl, (long long)ne, (long long)nblk, (long long)B.n_grow, (long long)B.n_near, (long long)B.n_staged, (long long)B.n_direct);
     }
+    // bundle plans (k_scalar_forward_bundles / k_scalar_reverse_bundles) for deep graphs ------------------------------------------
+    std::vector<int4> vfA, vfB, vfC, vrA, vrB;
+    std::vector<int32_t> vsrc(ne, 0);
+    B.n_fbundles = B.n_rbundles = 0;
+    B.fwd_bundles = B.rev_bundles = false;
+    {
+        static const int force = [] { const char *e = getenv("RDB_SCALAR_BUNDLES"); return e ? atoi(e) : -1; }();   // 0 = never, 1 = always
+        const bool deep_f = force >= 0 ? force == 1 : nfl > 48, deep_r = force >= 0 ? force == 1 : nrl > 48;
+        if (deep_f && n > 0 && (uint64_t)(nl + n) + n_fconst < (1u << 30)) {
+            // forward DAG: instruction -> the later instructions that read its slot
+            std::vector<int64_t> soff(n + 1, 0);
+            std::vector<int32_t> indeg(n, 0), height(n, 1);
+            for (int64_t i = 0; i < n; ++i) {
+                if (kind_a[i] == 1) { soff[code_a[i] + 1]++; indeg[i]++; }
+                if (kind_b[i] == 1) { soff[code_b[i] + 1]++; indeg[i]++; }
+            }
+            for (int64_t i = 0; i < n; ++i) soff[i + 1] += soff[i];
+            std::vector<int32_t> succ(soff[n]);
+            {
+                std::vector<int64_t> fill(soff.begin(), soff.end() - 1);
+                for (int64_t i = 0; i < n; ++i) {
+                    if (kind_a[i] == 1) succ[fill[code_a[i]]++] = (int32_t)i;
+                    if (kind_b[i] == 1) succ[fill[code_b[i]]++] = (int32_t)i;
+                }
+            }
+            for (int64_t i = n - 1; i >= 0; --i)
+                for (int64_t e = soff[i]; e < soff[i + 1]; ++e) height[i] = std::max(height[i], height[succ[e]] + 1);
+            BundlePlan bp = schedule_bundles(n, soff, succ, indeg, height);
+            if (bp.n_bundles > 0) {
+                const int64_t T = bp.n_bundles;
+                vfA.assign((T + kVRecAhead + 1) * 32, make_int4(kVEmpty, 0, 0, 0)); vfB.assign((T + kVRecAhead + 1) * 32, make_int4(-1, -1, 0, 0)); vfC.assign((T + kVRecAhead + 1) * 32, make_int4(0, 0, 0, 0));
+                for (int64_t i = 0; i < n; ++i) {
+                    auto src = [&](int kind, int code) -> int {
+                        if (kind == 0) return (int)(kVNone << 30);
+                        if (kind == 2) return (int)((kVGlobal << 30) | (unsigned)code);                    // leaf: val[code]
+                        if (kind == 3) return (int)((kVGlobal << 30) | (unsigned)(nl + n + code));             // literal pool appended to val[]
+                        if (bp.bundle[i] - bp.bundle[code] < kVRing)                                        // still in the ring
+                            return (int)((kVRingSrc << 30) | (unsigned)((bp.bundle[code] & (kVRing - 1)) * 32 + bp.lane[code]));
+                        return (int)((kVGlobal << 30) | (unsigned)(nl + code));
+                    };
+                    const int64_t q = (int64_t)bp.bundle[i] * 32 + bp.lane[i];
+                    const int4 E = h_exprs[body[5 * i]];
+                    vfA[q] = make_int4((int)i, src(kind_a[i], code_a[i]), src(kind_b[i], code_b[i]), 0);
+                    vfB[q] = make_int4(epos[2 * i], epos[2 * i + 1], E.x, E.y | (E.z << 16));
+                    vfC[q] = h_ops[E.x];
+                }
+                B.n_fbundles = T; B.fwd_bundles = true;
+            }
+        }
+        if (deep_r && ns > 0) {
+            // pull DAG: consumer instruction c -> its operand slots (they accumulate deriv(out_c))
+            std::vector<int64_t> soff(ns + 1, 0);
+            std::vector<int32_t> indeg(ns, 0), height(ns, 1);
+            for (int64_t i = 0; i < n; ++i)
+                for (int k = 0; k < 2; ++k) {
+                    const int64_t sl = slot_of(k == 0 ? kind_a[i] : kind_b[i], k == 0 ? code_a[i] : code_b[i]);
+                    if (sl >= 0) { soff[i + 1]++; indeg[sl]++; }
+                }
+            for (int64_t v = 0; v < ns; ++v) soff[v + 1] += soff[v];
+            std::vector<int32_t> succ(soff[ns]);
+            {
+                std::vector<int64_t> fill(soff.begin(), soff.end() - 1);
+                for (int64_t i = 0; i < n; ++i)
+                    for (int k = 0; k < 2; ++k) {
+                        const int64_t sl = slot_of(k == 0 ? kind_a[i] : kind_b[i], k == 0 ? code_a[i] : code_b[i]);
+                        if (sl >= 0) succ[fill[i]++] = (int32_t)sl;
+                    }
+            }
+            // operands have lower instruction ids (or are leaves, which have no successors): ascending order is reverse-topological
+            for (int64_t i = 0; i < n; ++i)
+                for (int64_t e = soff[i]; e < soff[i + 1]; ++e) height[i] = std::max(height[i], height[succ[e]] + 1);
+            BundlePlan bp = schedule_bundles(ns, soff, succ, indeg, height);
+            if (bp.n_bundles > 0) {
+                const int64_t T = bp.n_bundles;
+                vrA.assign((T + kVRecAhead + 1) * 32, make_int4(kVEmpty, 0, 0, 0)); vrB.assign((T + kVRecAhead + 1) * 32, make_int4(0, 0, 0, 0));
+                for (int64_t sl = 0; sl < ns; ++sl) {
+                    const int64_t e0 = reoff[rpos[sl]], cnt = ecount[sl];
+                    if (cnt > 0xffffff) { vrA.clear(); break; }
+                    int s01[2] = {(int)(kVNone << 30), (int)(kVNone << 30)};
+                    for (int64_t k = 0; k < cnt; ++k) {
+                        const int c = esrc[e0 + k];
+                        const int code = bp.bundle[sl] - bp.bundle[c] < kVRing
+                                             ? (int)((kVRingSrc << 30) | (unsigned)((bp.bundle[c] & (kVRing - 1)) * 32 + bp.lane[c]))
+                                             : (int)((kVGlobal << 30) | (unsigned)c);
+                        vsrc[e0 + k] = code;
+                        if (k < 2) s01[k] = code;
+                    }
+                    const int64_t q = (int64_t)bp.bundle[sl] * 32 + bp.lane[sl];
+                    const int flags = (sl < n && xoff[sl + 1] > xoff[sl]) ? 1 : 0;
+                    vrA[q] = make_int4(sl < n ? (int)sl : ~(int)(sl - n), s01[0], s01[1], (int)cnt | (flags << 24));
+                    if (sl < n) vrB[q] = make_int4((int)e0, 0, 0, 0);
+                    else {
+                        const int64_t l = sl - n;
+                        vrB[q] = make_int4((int)e0, leaf_ord[l], (int)(uint32_t)(leaf_elem[l] & 0xffffffffLL), (int)(leaf_elem[l] >> 32));
+                    }
+                }
+                if (!vrA.empty()) { B.n_rbundles = T; B.rev_bundles = true; }
+            }
+        }
+        if (getenv("RDB_SCALAR_DEBUG"))
+            fprintf(stderr, "[rdb scalar] levels fwd=%d rev=%d bundles fwd=%lld rev=%lld\n", nfl, nrl, (long long)B.n_fbundles, (long long)B.n_rbundles);
+    }
     // forward instruction table, level-sorted ------------------------------------------------------------------------------------
     std::vector<int4> finstr(n);
     {
@@ -559,7 +892,7 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
     auto pad = [](size_t b) { return (b + 15) & ~size_t(15); };
     size_t bytes = pad(n * 16) + pad((nfl + 1) * 8) + pad(h_ops.size() * 16) + pad(nex * 16) + pad(2 * n * 4) + pad(nl * 4) + pad(nl * 8) +
                    pad(nexp * 4) * 2 + pad(nexp * 8) + pad(ns * 4) + pad((ns + 1) * 8) + pad(ne * 4) + pad((nrl + 1) * 8) + pad((n + 1) * 8) +
-                   pad(nexp * 4) + pad(nexp * 8) + pad(nref * 8) * 3 + pad(npos * 16) * 4 + pad(nblk * kStageF * 8) + pad(ne * 4) + 512;
+                   pad(nexp * 4) + pad(nexp * 8) + pad(nref * 8) * 3 + pad(npos * 16) * 4 + pad(nblk * kStageF * 8) + pad(ne * 4) * 2 + pad(vfA.size() * 16) * 3 + pad(vrA.size() * 16) * 2 + 1024;
     std::vector<uint8_t> host(bytes, 0);
     if (cudaMalloc(&B.d_tables, bytes) != cudaSuccess) { cudaGetLastError(); return "scalar block: out of device memory (tables)"; }
     uint8_t *hp = host.data();
@@ -577,13 +910,15 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
     put(B.d_rslot, rslot); put(B.d_reoff, reoff); put(B.d_esrc, esrc); put(B.d_rlevel_off, rlevel_off);
     put(B.d_xoff, xoff); put(B.d_xord, xord); put(B.d_xelem, xelem);
     put(B.d_recA, recA); put(B.d_recB, recB); put(B.d_recC, recC); put(B.d_recD, recD); put(B.d_pf, pf); put(B.d_tsrc, tsrc);
+    put(B.d_vfA, vfA); put(B.d_vfB, vfB); put(B.d_vfC, vfC); put(B.d_vrA, vrA); put(B.d_vrB, vrB); put(B.d_vsrc, vsrc);
     std::vector<void *> nulls(nref, nullptr); std::vector<int64_t> zeros(nref, 0);
     put(B.d_ext_val, nulls); put(B.d_ext_der, nulls); put(B.d_ext_size, zeros);
     if ((size_t)(hp - host.data()) > bytes) return "scalar block: internal table overflow";
     if (cudaMemcpyAsync(B.d_tables, host.data(), bytes, cudaMemcpyHostToDevice, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
         cudaGetLastError(); return "scalar block: table upload failed";
     }
-    if (cudaMalloc(&B.d_val, std::max<size_t>((size_t)(nl + n) * es, 16)) != cudaSuccess ||
+    B.n_lit = B.fwd_bundles ? (int64_t)n_fconst : 0;
+    if (cudaMalloc(&B.d_val, std::max<size_t>((size_t)(nl + n + B.n_lit) * es, 16)) != cudaSuccess ||
         cudaMalloc(&B.d_epart, std::max<size_t>((size_t)ne * es, 16)) != cudaSuccess) { cudaGetLastError(); return "scalar block: out of device memory (pools)"; }
     B.h_ext_val.assign(nref, nullptr); B.h_ext_der.assign(nref, nullptr); B.h_ext_size.assign(nref, 0);
     return "";
@@ -622,15 +957,23 @@ cudaError_t scalar_block_ensure_R(ScalarBlock &B, int64_t R, size_t es) {
 template <typename T>
 cudaError_t scalar_block_forward(cudaStream_t s, ScalarBlock &B, const double *fconst, int *launches) {
     int nl = 0;
-    if (B.n_leaf > 0) {
-        k_scalar_pull<T><<<(unsigned)((B.n_leaf + 255) / 256), 256, 0, s>>>((T *)B.d_val, B.d_leaf_ord, B.d_leaf_elem, B.d_ext_val, B.n_leaf);
+    const int64_t n_lit = B.fwd_bundles ? B.n_lit : 0;
+    if (B.n_leaf + n_lit > 0) {
+        k_scalar_pull<T><<<(unsigned)((B.n_leaf + n_lit + 255) / 256), 256, 0, s>>>((T *)B.d_val, B.d_leaf_ord, B.d_leaf_elem, B.d_ext_val, B.n_leaf,
+                                                                                   B.n, fconst, n_lit);
         ++nl;
     }
-    FwdP P{B.d_finstr, B.d_flevel_off, B.d_ops, B.d_exprs, B.d_epos, fconst, B.d_val, B.d_epart, B.n_leaf, 0, 0};
-    for (const ScalarSeg &g : B.fsegs) {
-        P.lv0 = g.lv0; P.lv1 = g.lv1;
-        k_scalar_forward<T><<<g.grid, kFwdThreads, 0, s>>>(P);
+    if (B.fwd_bundles) {
+        VFwdP V{B.d_vfA, B.d_vfB, B.d_vfC, B.d_ops, fconst, B.d_val, B.d_epart, B.n_leaf, B.n_fbundles};
+        k_scalar_forward_bundles<T><<<1, 32, 0, s>>>(V);
         ++nl;
+    } else {
+        FwdP P{B.d_finstr, B.d_flevel_off, B.d_ops, B.d_exprs, B.d_epos, fconst, B.d_val, B.d_epart, B.n_leaf, 0, 0};
+        for (const ScalarSeg &g : B.fsegs) {
+            P.lv0 = g.lv0; P.lv1 = g.lv1;
+            k_scalar_forward<T><<<g.grid, kFwdThreads, 0, s>>>(P);
+            ++nl;
+        }
     }
     if (B.n_exports > 0) {
         k_scalar_export<T><<<(unsigned)((B.n_exports + 255) / 256), 256, 0, s>>>((const T *)B.d_val, B.d_exp_slot, B.d_exp_ord, B.d_exp_elem,
@@ -648,6 +991,11 @@ cudaError_t scalar_block_reverse(cudaStream_t s, ScalarBlock &B, int64_t R, bool
         StreamP P{B.d_recA, B.d_recB, B.d_recC, B.d_recD, B.d_pf, B.d_tsrc, B.d_epart, B.d_xoff, B.d_xord, B.d_xelem,
                   B.d_ext_der, B.d_ext_size, B.d_der, R, B.n_sblocks, leaves_zero ? 1 : 0};
         k_scalar_reverse_stream<T><<<(unsigned)((R + 31) / 32), 32, 0, s>>>(P);
+        ++nl;
+    } else if (B.rev_bundles) {
+        VRevP V{B.d_vrA, B.d_vrB, B.d_vsrc, B.d_epart, B.d_xoff, B.d_xord, B.d_xelem, B.d_ext_der, B.d_ext_size, B.d_der, R, B.n_rbundles,
+                leaves_zero ? 1 : 0};
+        k_scalar_reverse_bundles<T><<<(unsigned)R, 32, 0, s>>>(V);
         ++nl;
     } else {
         RevP P{B.d_rslot, B.d_reoff, B.d_esrc, B.d_epart, B.d_rlevel_off, B.d_xoff, B.d_xord, B.d_xelem, B.d_leaf_ord, B.d_leaf_elem,
