@@ -396,14 +396,16 @@ __global__ void __launch_bounds__(256) k_row_exponent(const unsigned long long *
 template <bool KMAJOR>
 __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, const double *__restrict__ src, int64_t ld, int rows, int K,
                                                   int Kp, int nslices, int bits, const int *__restrict__ e_in) {
-    __shared__ double tile[KMAJOR ? 1 : 128][KMAJOR ? 1 : 33];
+    // [k % 4][k / 4][r]: a thread later reads 4 consecutive k of one row, i.e. one element of each k%4 plane at row k/4 = lane -
+    // 33-double rows make both the write (lanes along r) and that read (lanes along k/4) bank-conflict free
+    __shared__ double tile[KMAJOR ? 1 : 4][KMAJOR ? 1 : 32][KMAJOR ? 1 : 33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 128;
     if (!KMAJOR) {
         // tile[k][r] <- src[(r0+r) + (k0+k)*ld], lanes along r (coalesced)
         for (int k = w; k < 128; k += 8) {
             int r = r0 + lane, kk = k0 + k;
-            tile[k][lane] = (r < rows && kk < K) ? src[r + (int64_t)kk * ld] : 0.0;
+            tile[k & 3][k >> 2][lane] = (r < rows && kk < K) ? src[r + (int64_t)kk * ld] : 0.0;
         }
         __syncthreads();
     }
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, cons
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = tile[4 * lane + j][rl];
+                for (int j = 0; j < 4; ++j) v[j] = tile[j][lane][rl];
             }
         }
 #pragma unroll
