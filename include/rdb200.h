@@ -69,7 +69,9 @@ int rdb_ctx_set_gemm_f64_mode(rdb_ctx *, int mode, int slices);
 rdb_tape *rdb_tape_load(rdb_ctx *, const void *program, size_t nbytes, const rdb_options *opts);
 void rdb_tape_destroy(rdb_tape *);
 
-/* value!(input_hook(tape)[slot], x) (src/api/tape.jl:40-44 -> src/tracked.jl:156-163). */
+/* value!(input_hook(tape)[slot], x) (src/api/tape.jl:40-44 -> src/tracked.jl:156-163).  The copy is only ENQUEUED (large host
+ * matrices upload in column panels on a separate stream and the sweep consumes them panel by panel): `data` must stay alive and
+ * unmodified until the next rdb_forward / rdb_gradient / rdb_jacobian / rdb_hessian on this tape has returned. */
 int rdb_tape_set_input(rdb_tape *, int input_slot, const void *data, int is_device);
 
 /* forward_pass!(::CompiledTape) (src/api/tape.jl:122-127; src/tape.jl:75-80). */
