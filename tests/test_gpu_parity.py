@@ -401,6 +401,47 @@ def test_input_shape_errors(rd):
         rd.gradient_(np.zeros(3), ct, np.ones(4))
 
 
+# ------------------------------------------------------------------------------------------ host-array paths at panel sizes
+PANEL_CASES = {
+    # gradient! with HOST inputs/results takes extra routes once a matrix reaches 32 MB and 2048 columns: inputs upload in column
+    # panels (the first `*` that reads the last-uploaded input as its plain right operand starts per panel), and the last one or
+    # two `*` accumulations into an input run as (interleaved) column panels with early D2H copies.  Each case pins one route.
+    "a'*b + a*b'": lambda rd: lambda a, b: rd.sum(a.T @ b + a @ b.T),          # folded/plain pairs on both inputs (cfg 2)
+    "a*b + b*a": lambda rd: lambda a, b: rd.sum(a @ b + b @ a),                  # plain/plain pairs
+    "a*a": lambda rd: lambda a, b: rd.sum(a @ a + b),                            # both accumulations in ONE instruction: no partner
+    "(a*b)*a": lambda rd: lambda a, b: rd.sum((a @ b) @ a),                      # partner's output adjoint not final yet: no hoist
+    "tanh.(a)*b": lambda rd: lambda a, b: rd.sum(rd.bcast(lambda u: rd.tanh(u), a) @ b),   # streamed b; a's first reader is not a `*`
+    "b*a (b uploaded last, left operand)": lambda rd: lambda a, b: rd.sum(b @ a),           # last upload is a LEFT operand: settle
+}
+
+
+@pytest.mark.parametrize("name", sorted(PANEL_CASES))
+def test_host_arrays_at_panel_sizes(rd, orc, name):
+    n = 2048                                                    # 2048 x 2048 FP64 = 32 MiB: the smallest size that takes the routes
+    rng = np.random.default_rng(5)
+    rec = (rng.random((n, n)), rng.random((n, n)))
+    ins = (np.asfortranarray(rng.random((n, n)) / n), np.asfortranarray(rng.random((n, n))))
+    f = PANEL_CASES[name](rd)
+    ct = run_gradient(rd, orc, f, rec, ins, check_buffers=False)
+    # the same compiled tape with DEVICE arrays takes none of the routes: results must agree to the last bit (the int8-slice
+    # GEMM is exact integer accumulation per element, so cutting it into panels cannot change a single result)
+    import torch
+    dev_in = tuple(torch.from_numpy(np.ascontiguousarray(x.T)).cuda() for x in ins)
+    dev_out = tuple(torch.empty(n * n, dtype=torch.float64, device="cuda") for _ in ins)
+    rd.gradient_(dev_out, ct, dev_in)
+    host_out = tuple(np.zeros((n, n), order="F") for _ in ins)
+    rd.gradient_(host_out, ct, ins)
+    for h, d in zip(host_out, dev_out):
+        assert np.array_equal(h, d.cpu().numpy().reshape(n, n, order="F"))
+    # and again with fresh inputs on the same tape (events, panel state and slice caches must not leak between calls)
+    ins2 = (np.asfortranarray(rng.random((n, n)) / n), np.asfortranarray(rng.random((n, n))))
+    res2 = tuple(np.zeros((n, n), order="F") for _ in ins2)
+    rd.gradient_(res2, ct, ins2)
+    _, g2 = orc.OracleTape(rd.GradientTape(f, rec).program_bytes()).gradient(list(ins2))
+    for r, g in zip(res2, g2):
+        assert relerr(r, g) < 1e-12
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_cfg2_full_size_closed_form(rd):
     """4096x4096 FP64: the oracle needs ~3 s of DGEMM per eval, so the full-size check uses the size-independent
