@@ -454,17 +454,21 @@ def sharded_legs(args, torch, dist, rd, ctx, rank, world):
             out[key] = {"skipped": f"needs {need / 2**30:.1f} GiB result + tangent workspace, {free / 2**30:.1f} GiB free"}
             continue
         tape = rd.HessianTape(rd.workloads.f_rosenbrock, rd.workloads.inputs_rosenbrock(n, seed=1))
-        ct = rd.compile(tape, ctx=ctx)
+        # a context with a stream of its own: the launch-bound sweep replays as one CUDA graph (the legacy default stream cannot
+        # be captured); every call is synchronous, so the events on torch's stream still bracket the work
+        hctx = rd.engine.Context(torch.cuda.current_device())
+        ct = rd.compile(tape, ctx=hctx)
         x_d = torch.from_numpy(rd.workloads.inputs_rosenbrock(n, seed=2)).cuda()
+        torch.cuda.synchronize()
         H_d = torch.empty(n * (ce - cb), dtype=torch.float64, device="cuda")
 
         def hstep():
             rd.hessian_(H_d, ct, x_d, cols=(cb, ce))
-        ms = timed_steps(torch, dist, world, hstep, 3, 2)
+        ms = timed_steps(torch, dist, world, hstep, 3, 3)
         out[key] = {"metric": "hessian! rows/s", "value": n * 3 / (ms * 1e-3), "unit": "rows/s", "n": n, "ms_per_hessian": ms / 3,
                     "cols_per_rank": cols, "result": "left sharded in device memory",
                     "result_write_GBps_per_gpu": n * (ce - cb) * 8 / (ms / 3 * 1e-3) / 1e9}
-        del ct, H_d, x_d
+        del ct, H_d, x_d, hctx
         torch.cuda.empty_cache()
     return out
 

@@ -140,7 +140,14 @@ if "5" in which:   # cfg 5: hessian! extended Rosenbrock n = 16384
     Hcf[2 * idx + 1, 2 * idx + 1] = 200
     err = float((Hm - Hcf).abs().max() / Hcf.abs().max())
     zeros_exact = bool((Hm[Hcf == 0] == 0).all())
+    Hs = torch.empty(n * (n // 8), dtype=torch.float64, device="cuda")
+    hctx = rd.engine.Context(0)                                                    # own stream: the sweep replays as a CUDA graph
+    cth = rd.compile(tape, ctx=hctx)
+    torch.cuda.synchronize()
+    ms_graph = timeit(lambda: rd.hessian_(H, cth, xd), 10, 3)
+    ms_shard = timeit(lambda: rd.hessian_(Hs, cth, xd, cols=(0, n // 8)), 20, 3)     # what ONE rank does at 8 GPUs
     out.append({"cfg": 5, "what": "hessian! extended Rosenbrock n=16384 f64 (forward-over-reverse)", "ms_per_hessian": ms, "rows_per_s": n / ms * 1e3,
+                "ms_per_hessian_graph": ms_graph, "ms_one_eighth_column_shard_graph": ms_shard, "speedup_if_8_ranks": ms_graph / ms_shard,
                 "result_bytes": n * n * 8, "result_write_GBps": n * n * 8 / ms / 1e6, "max_rel_err_vs_closed_form": err,
                 "structural_zeros_exact": zeros_exact, "steps": stats_of(tape, lambda c: rd.hessian_(H, c, xd))})
 

@@ -141,6 +141,9 @@ struct rdb_tape {
     std::vector<StepStat> stats;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool forward_valid = false;
+    // hessian! with a device result and no gradient/value request, launch-bound tapes: the whole sweep as one graph, keyed by its arguments
+    struct HessGraph { cudaGraphExec_t exec = nullptr; int state = 0; int64_t cb = 0, ce = 0, ld = 0; void *result = nullptr; } hgraph;
+    bool capturing = false;        // hessian_impl is being captured: no synchronisation, no host copies
     int last_upload = -1;          // buffer of the most recent panelled upload (the one worth consuming panel by panel)
     // deriv zero-state, per ROOT buffer: dz[b] != 0 means deriv(b) is LOGICALLY zero while its storage may hold anything.
     // unseed! (every reverse exec ends with one, tracked.jl:207-213) only sets the flag; the next accumulation into the buffer
@@ -1657,6 +1660,53 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
     if (grad_out) CU(cudaMemcpyAsync(grad_out, x.der, (size_t)n * t->es, cudaMemcpyDeviceToHost, S(t)));
     if (!on_device && cols > 0)
         CU(cudaMemcpy2DAsync(result, (size_t)ld * t->es, t->stage, (size_t)n * t->es, (size_t)n * t->es, (size_t)cols, cudaMemcpyDeviceToHost, S(t)));
+    if (!t->capturing) CU(cudaStreamSynchronize(S(t)));
+    return RDB_OK;
+}
+
+// hessian! entry: launch-bound tapes with a device result replay the whole sweep (forward with second partials, first- and
+// second-order reverse, result block written in place) as ONE captured graph.  First call with a given (columns, result, ld)
+// runs eagerly and warms every lazy allocation, the second captures, later ones only launch.
+template <typename T>
+static int hessian_entry(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64_t ld, int on_device, void *grad_out, void *value_out) {
+    auto &G = t->hgraph;
+    const bool want = graph_eligible(t) && on_device && !grad_out && !value_out && ce > cb && t->inputs.size() == 1;
+    const bool same = want && G.cb == cb && G.ce == ce && G.ld == ld && G.result == result;
+    if (!want || !same) {
+        if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+        G.state = want ? 1 : 0; G.cb = cb; G.ce = ce; G.ld = ld; G.result = result;
+        return hessian_impl<T>(t, cb, ce, result, ld, on_device, grad_out, value_out);
+    }
+    if (G.state == 1) {
+        OK(settle_uploads(t, -1));
+        G.state = -1;
+        if (cudaStreamBeginCapture(S(t), cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            return hessian_impl<T>(t, cb, ce, result, ld, on_device, grad_out, value_out);
+        }
+        t->capturing = true;
+        const int rc = hessian_impl<T>(t, cb, ce, result, ld, on_device, grad_out, value_out);
+        t->capturing = false;
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(S(t), &g);
+        if (rc != RDB_OK || e != cudaSuccess || !g) {
+            cudaGetLastError();
+            if (g) cudaGraphDestroy(g);
+            return hessian_impl<T>(t, cb, ce, result, ld, on_device, grad_out, value_out);      // eager from now on (state -1)
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&G.exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ei != cudaSuccess) { cudaGetLastError(); G.exec = nullptr; return hessian_impl<T>(t, cb, ce, result, ld, on_device, grad_out, value_out); }
+        G.state = 2;
+    }
+    if (G.state != 2) return hessian_impl<T>(t, cb, ce, result, ld, on_device, grad_out, value_out);
+    OK(settle_uploads(t, -1));
+    CU(cudaGraphLaunch(G.exec, S(t)));
+    t->launches += 1;
+    // host-side state the sweep leaves behind (tail of hessian_impl)
+    for (size_t b = 0; b < t->bufs.size(); ++b) t->dz[droot(t, (int)b)] = 1;
+    t->dz[droot(t, t->inputs[0])] = 0;
+    t->forward_valid = true;
     CU(cudaStreamSynchronize(S(t)));
     return RDB_OK;
 }
@@ -1732,6 +1782,7 @@ void rdb_tape_destroy(rdb_tape *t) {
     if (t->ev0) cudaEventDestroy(t->ev0);
     if (t->ev1) cudaEventDestroy(t->ev1);
     if (t->gexec) cudaGraphExecDestroy(t->gexec);
+    if (t->hgraph.exec) cudaGraphExecDestroy(t->hgraph.exec);
     for (auto &e : t->early.ev) if (e) cudaEventDestroy(e);
     if (t->ctx && t->ctx->upload_stream) cudaStreamSynchronize(t->ctx->upload_stream);
     for (auto &b : t->bufs) for (auto &e : b.up_ev) if (e) cudaEventDestroy(e);
@@ -1795,7 +1846,7 @@ int rdb_jacobian(rdb_tape *t, int slot, int64_t rb, int64_t re, void *result, in
 }
 int rdb_hessian(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64_t ld, int on_device, void *grad_out, void *value_out) {
     if (!t || (!result && ce > cb)) return fail(RDB_EINVAL, "null argument");
-    return DISPATCH(t, hessian_impl, t, cb, ce, result, ld, on_device, grad_out, value_out);
+    return DISPATCH(t, hessian_entry, t, cb, ce, result, ld, on_device, grad_out, value_out);
 }
 int64_t rdb_buffer_size(rdb_tape *t, int b) {
     if (!t || b < 0 || (size_t)b >= t->bufs.size()) return -1;

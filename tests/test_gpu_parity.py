@@ -223,6 +223,48 @@ def test_cfg5_hessian(rd, orc, n, block):
         assert np.array_equal(part, H[:, 3:7])
 
 
+@pytest.mark.parametrize("n,block", [(64, 0), (64, 16), (1000, 0), (4096, 0)])
+def test_cfg5_hessian_graph_replay(rd, n, block):
+    """Device results without gradient/value: the second call with the same arguments captures the sweep as a CUDA graph, later
+    calls replay it.  New inputs every call, a different column shard in between (the key changes: eager again), then the
+    Hessian through a general tape (tangent sweeps instead of the sparse kernel)."""
+    import torch
+    def closed(x):
+        o, e = x[0::2], x[1::2]
+        Hcf = np.zeros((n, n)); idx = np.arange(n // 2)
+        Hcf[2 * idx, 2 * idx] = 1200 * o ** 2 - 400 * e + 2
+        Hcf[2 * idx, 2 * idx + 1] = Hcf[2 * idx + 1, 2 * idx] = -400 * o
+        Hcf[2 * idx + 1, 2 * idx + 1] = 200
+        return Hcf
+    tape = rd.HessianTape(rd.workloads.f_rosenbrock, rd.workloads.inputs_rosenbrock(n, seed=1))
+    ct = rd.compile(tape, seed_block=block)
+    H = torch.full((n * n,), float("nan"), dtype=torch.float64, device="cuda")
+    Hs = torch.full((n * (n // 4),), float("nan"), dtype=torch.float64, device="cuda")
+    for call in range(5):
+        x = rd.workloads.inputs_rosenbrock(n, seed=10 + call)
+        xd = torch.from_numpy(x).cuda()
+        if call == 3:                                            # a shard: other key, runs eagerly, resets the capture
+            Hs.fill_(float("nan"))
+            rd.hessian_(Hs, ct, xd, cols=(n // 2, n // 2 + n // 4))
+            assert np.array_equal(Hs.cpu().numpy().reshape(n, n // 4, order="F"), closed(x)[:, n // 2:n // 2 + n // 4]) or \
+                relerr(Hs.cpu().numpy().reshape(n, n // 4, order="F"), closed(x)[:, n // 2:n // 2 + n // 4]) < 1e-12
+            continue
+        H.fill_(float("nan"))
+        rd.hessian_(H, ct, xd)
+        Hh = H.cpu().numpy().reshape(n, n, order="F")
+        Hcf = closed(x)
+        assert relerr(Hh, Hcf) < 1e-12, f"call {call}"
+        assert np.all(Hh[Hcf == 0] == 0.0), f"call {call}"
+    # the gradient path on the same tape still sees consistent state after graph replays
+    g = np.zeros(n); Hn = np.zeros((n, n), order="F")
+    x = rd.workloads.inputs_rosenbrock(n, seed=99)
+    res = rd.DiffResult(0.0, g, Hn)
+    rd.hessian_(res, ct, x)
+    o, e = x[0::2], x[1::2]
+    gref = np.zeros(n); gref[0::2] = -400 * o * (e - o * o) - 2 * (1 - o); gref[1::2] = 200 * (e - o * o)
+    assert relerr(g, gref) < 1e-12 and relerr(Hn, closed(x)) < 1e-12
+
+
 def test_hessian_vs_reference_algorithm(rd):
     """Forward-over-reverse on the array tape (engine) against the reference's reverse-over-reverse on a scalar tape
     (oracle/scalar_tape.py, literal restatement of api/tape.jl:285-293): same Hessian to 1e-12."""
