@@ -136,7 +136,7 @@ struct ScalarBlock {
     int64_t n_sblocks = 0, n_grow = 0, n_near = 0, n_staged = 0, n_direct = 0;
     size_t der_bytes = 0;
     // bundle ("VLIW") plans for deep graphs: forward, and reverse with R < 16 seeds (scalar.cu)
-    int64_t n_fbundles = 0, n_rbundles = 0, n_lit = 0;
+    int64_t n_fbundles = 0, n_rbundles = 0, n_lit = 0, n_brow = 0;
     bool fwd_bundles = false, rev_bundles = false;
     std::vector<int32_t> refbufs;               // tape buffer ids referenced (leaf origins and export targets)
     std::vector<char> ref_has_leaf, ref_has_export;
@@ -176,6 +176,7 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *payload, int64_t l
 void scalar_block_free(ScalarBlock &B);
 cudaError_t scalar_block_upload_ext(ScalarBlock &B, cudaStream_t s);
 cudaError_t scalar_block_ensure_R(ScalarBlock &B, int64_t R, size_t es);
+bool scalar_reverse_streams(const ScalarBlock &B, int64_t R, size_t es);   // R >= 16 seeds: streaming kernel (true) or one bundle warp per seed
 // forward: pull leaf values, evaluate level by level, mirror exports; returns the number of kernel launches in *launches
 template <typename T> cudaError_t scalar_block_forward(cudaStream_t, ScalarBlock &B, const double *fconst, int *launches);
 // reverse for R seeds (deriv layout of tape buffers: [elem + r*size])

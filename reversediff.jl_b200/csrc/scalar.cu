@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -404,10 +405,14 @@ struct VRevP {
     void *der; int64_t R; int64_t n_bundles; int leaves_zero;
 };
 
-// grid.x = seeds (R < 16): one warp per seed, the seeds share nothing.  Same pipeline as the forward kernel; the staged operands
-// of a bundle are its two partials, the adjoints it reads from global memory and a leaf's current origin.deriv[index].
+// grid.x = seeds: one warp per seed, the seeds share nothing.  Same pipeline as the forward kernel with a shallower ring and
+// shorter distances (13 KB of shared memory: 13+ CTAs per SM when many seeds run at once); the staged operands of a bundle are
+// its two partials, the adjoints it reads from global memory and a leaf's current origin.deriv[index].  Only adjoints with a
+// reader more than kVRingR bundles away get a row in global memory (B.y).
+constexpr int kVRingR = 16, kVRecAheadR = 6, kVRecSlotsR = 8, kVOpAheadR = 3, kVOpSlotsR = 4;
 template <typename T>
 __global__ void __launch_bounds__(32) k_scalar_reverse_bundles(const VRevP P) {
+    constexpr int kVRing = kVRingR, kVRecAhead = kVRecAheadR, kVRecSlots = kVRecSlotsR, kVOpAhead = kVOpAheadR, kVOpSlots = kVOpSlotsR;
     __shared__ __align__(16) T ring[kVRing * 32];
     __shared__ int4 srec[kVRecSlots][2][32];
     __shared__ __align__(16) T sop[kVOpSlots][5][32];
@@ -468,8 +473,8 @@ __global__ void __launch_bounds__(32) k_scalar_reverse_bundles(const VRevP P) {
                 acc = acc + a * epart[B0.x + e];
             }
             ring[(int)(t & (kVRing - 1)) * 32 + lane] = acc;
-            if (A0.x >= 0) der[(int64_t)A0.x * R + r] = acc;                                        // the slot's final adjoint
-            else *leaf_ptr(B0) = acc;                                                               // push_deriv!
+            if (A0.x < 0) *leaf_ptr(B0) = acc;                                                      // push_deriv!
+            else if (B0.y >= 0) der[(int64_t)B0.y * R + r] = acc;                                   // a reader beyond the ring wants it
         }
         __syncwarp();
     }
@@ -844,23 +849,32 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
             BundlePlan bp = schedule_bundles(ns, soff, succ, indeg, height);
             if (bp.n_bundles > 0) {
                 const int64_t T = bp.n_bundles;
-                vrA.assign((T + kVRecAhead + 1) * 32, make_int4(kVEmpty, 0, 0, 0)); vrB.assign((T + kVRecAhead + 1) * 32, make_int4(0, 0, 0, 0));
+                vrA.assign((T + kVRecAhead + 1) * 32, make_int4(kVEmpty, 0, 0, 0)); vrB.assign((T + kVRecAhead + 1) * 32, make_int4(0, -1, 0, 0));
+                std::vector<int32_t> brow(n, -1);                 // global row of an instruction output read from beyond the ring
+                B.n_brow = 0;
+                for (int64_t sl = 0; sl < ns; ++sl) {
+                    const int64_t e0 = reoff[rpos[sl]];
+                    for (int64_t k = 0; k < ecount[sl]; ++k) {
+                        const int c = esrc[e0 + k];
+                        if (bp.bundle[sl] - bp.bundle[c] >= kVRingR && brow[c] < 0) brow[c] = (int32_t)B.n_brow++;
+                    }
+                }
                 for (int64_t sl = 0; sl < ns; ++sl) {
                     const int64_t e0 = reoff[rpos[sl]], cnt = ecount[sl];
                     if (cnt > 0xffffff) { vrA.clear(); break; }
                     int s01[2] = {(int)(kVNone << 30), (int)(kVNone << 30)};
                     for (int64_t k = 0; k < cnt; ++k) {
                         const int c = esrc[e0 + k];
-                        const int code = bp.bundle[sl] - bp.bundle[c] < kVRing
-                                             ? (int)((kVRingSrc << 30) | (unsigned)((bp.bundle[c] & (kVRing - 1)) * 32 + bp.lane[c]))
-                                             : (int)((kVGlobal << 30) | (unsigned)c);
+                        const int code = bp.bundle[sl] - bp.bundle[c] < kVRingR
+                                             ? (int)((kVRingSrc << 30) | (unsigned)((bp.bundle[c] & (kVRingR - 1)) * 32 + bp.lane[c]))
+                                             : (int)((kVGlobal << 30) | (unsigned)brow[c]);
                         vsrc[e0 + k] = code;
                         if (k < 2) s01[k] = code;
                     }
                     const int64_t q = (int64_t)bp.bundle[sl] * 32 + bp.lane[sl];
                     const int flags = (sl < n && xoff[sl + 1] > xoff[sl]) ? 1 : 0;
                     vrA[q] = make_int4(sl < n ? (int)sl : ~(int)(sl - n), s01[0], s01[1], (int)cnt | (flags << 24));
-                    if (sl < n) vrB[q] = make_int4((int)e0, 0, 0, 0);
+                    if (sl < n) vrB[q] = make_int4((int)e0, brow[sl], 0, 0);
                     else {
                         const int64_t l = sl - n;
                         vrB[q] = make_int4((int)e0, leaf_ord[l], (int)(uint32_t)(leaf_elem[l] & 0xffffffffLL), (int)(leaf_elem[l] >> 32));
@@ -938,11 +952,30 @@ cudaError_t scalar_block_upload_ext(ScalarBlock &B, cudaStream_t s) {
     return e;
 }
 
+// Which kernel takes a reverse sweep of R >= 16 seeds.  Fitted on B200 (profiles/README.md): the streaming kernel costs ~290 clk
+// per schedule position whatever R is (one warp per 32 seeds); one bundle warp per seed costs ~(1100 + 170 W) clk per bundle
+// with W warps resident on an SM (<= 13), so it wins while the seeds fit one or two rounds of a short schedule (n <~ 2048 for
+// the literal Hessian tape).  Its global adjoint rows must also stay small.
+bool scalar_reverse_streams(const ScalarBlock &B, int64_t R, size_t es) {
+    if (R < 16) return false;
+    if (!B.rev_bundles) return true;
+    static const int force = [] { const char *e = getenv("RDB_SCALAR_MANYSEED"); return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'b' ? 2 : 0)); }();
+    if (force) return force == 1;
+    if ((double)B.n_brow * (double)R * (double)es > 4.0 * (1 << 30)) return true;
+    const double W = std::min(13.0, std::ceil((double)R / 148.0)), rounds = std::ceil((double)R / (148.0 * 13.0));
+    const double t_stream = 290.0 * (double)B.n_sblocks * 32.0, t_bundles = (1100.0 + 170.0 * W) * (double)B.n_rbundles * rounds;
+    return t_stream <= t_bundles;
+}
+
 cudaError_t scalar_block_ensure_R(ScalarBlock &B, int64_t R, size_t es) {
-    // R < 16: the slot-lane kernel indexes adjoints by instruction ([i*R + r]); R >= 16: the streaming kernel only keeps the rows
-    // that are read from global memory ([row*R + r])
+    // adjoint rows in global memory, [row*R + r]: the level kernel (R < 16, shallow graphs) indexes them by instruction; the
+    // bundle and streaming kernels only keep the rows that are read from beyond their shared-memory rings
     const int64_t few = std::min<int64_t>(R, 15);
-    const size_t need = std::max<size_t>(std::max<size_t>((size_t)B.n * few, R >= 16 ? (size_t)B.n_grow * R : 0) * es, 16);
+    size_t elems = 16;
+    if (!B.rev_bundles) elems = std::max<size_t>(elems, (size_t)B.n * few);
+    else elems = std::max<size_t>(elems, (size_t)B.n_brow * few);
+    if (R >= 16) elems = std::max<size_t>(elems, (size_t)(scalar_reverse_streams(B, R, es) ? B.n_grow : B.n_brow) * R);
+    const size_t need = elems * es;
     if (need > B.der_bytes) {
         cudaFree(B.d_der);
         B.d_der = nullptr; B.der_bytes = 0;
@@ -987,7 +1020,8 @@ cudaError_t scalar_block_forward(cudaStream_t s, ScalarBlock &B, const double *f
 template <typename T>
 cudaError_t scalar_block_reverse(cudaStream_t s, ScalarBlock &B, int64_t R, bool leaves_zero, int *launches) {
     int nl = 0;
-    if (R >= 16) {
+    const bool stream = scalar_reverse_streams(B, R, sizeof(T));
+    if (stream) {
         StreamP P{B.d_recA, B.d_recB, B.d_recC, B.d_recD, B.d_pf, B.d_tsrc, B.d_epart, B.d_xoff, B.d_xord, B.d_xelem,
                   B.d_ext_der, B.d_ext_size, B.d_der, R, B.n_sblocks, leaves_zero ? 1 : 0};
         k_scalar_reverse_stream<T><<<(unsigned)((R + 31) / 32), 32, 0, s>>>(P);
