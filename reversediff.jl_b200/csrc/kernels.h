@@ -164,7 +164,9 @@ struct ScalarBlock {
     void *d_epart = nullptr;                    // T[n_edges] partials in reverse edge order
     int4 *d_recA = nullptr, *d_recB = nullptr, *d_recC = nullptr, *d_recD = nullptr;   // per schedule position (scalar.cu, "streaming plan")
     int2 *d_pf = nullptr;                       // per schedule block: what to prefetch into the staging buffer
-    int4 *d_vfA = nullptr, *d_vfB = nullptr, *d_vfC = nullptr, *d_vrA = nullptr, *d_vrB = nullptr;   // bundle records
+    int4 *d_vfA = nullptr, *d_vfB = nullptr, *d_vfC = nullptr, *d_vfD = nullptr, *d_vrA = nullptr, *d_vrB = nullptr;
+    int32_t *d_bpos = nullptr;                  // 2n: where forward stores partial (i, a|b) in the bundle-ordered copy, or -1
+    void *d_bpart = nullptr;                    // T[2 x 32 x bundles]: partials of edges 0/1 in reverse-bundle order   // bundle records
     int32_t *d_vsrc = nullptr;                  // bundle reverse: operand sources of every edge (same order as d_esrc)
     int32_t *d_tsrc = nullptr;                  // operand codes of every edge for the streaming kernel (same order as d_esrc)
     void *d_der = nullptr;                      // adjoints of instruction outputs: T[n x R] at [i*R + r] (R < 16), T[n_grow x R] (R >= 16)

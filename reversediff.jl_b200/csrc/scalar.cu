@@ -40,7 +40,7 @@ constexpr int kWideLevel = 8192;      // a level at least this wide gets a grid 
 constexpr int kNone = INT_MIN;
 
 struct FwdP {
-    const int4 *finstr; const int64_t *level_off; const int4 *ops; const int4 *exprs; const int32_t *epos;
+    const int4 *finstr; const int64_t *level_off; const int4 *ops; const int4 *exprs; const int32_t *epos; const int32_t *bpos; void *bpart;
     const double *fconst; void *val; void *epart; int64_t n_leaf; int lv0, lv1;
 };
 
@@ -63,6 +63,12 @@ __global__ void __launch_bounds__(kFwdThreads) k_scalar_forward(const FwdP P) {
             const int ea = P.epos[2 * (int64_t)I.x], eb = P.epos[2 * (int64_t)I.x + 1];
             if (ea >= 0) epart[ea] = d[0];                                                  // cache[] = partials
             if (eb >= 0) epart[eb] = d[1];
+            if (P.bpos) {                                                                   // ... and in bundle order (k_scalar_reverse_bundles)
+                T *bpart = reinterpret_cast<T *>(P.bpart);
+                const int ba = P.bpos[2 * (int64_t)I.x], bb = P.bpos[2 * (int64_t)I.x + 1];
+                if (ba >= 0) bpart[ba] = d[0];
+                if (bb >= 0) bpart[bb] = d[1];
+            }
         }
         if (lv + 1 < P.lv1) __syncthreads();      // multi-level launches run on ONE CTA
     }
@@ -338,12 +344,13 @@ __device__ __forceinline__ void eval_scalar(const int4 *__restrict__ ops, int e_
 //   kVGlobal: index into val[] (a leaf, a literal - the pool is appended to val[] - or an instruction output older than the
 //   ring), kVRingSrc: ring entry
 //   B = (where partial a goes in epart or -1, same for b, bytecode offset, n_ops | n_args << 16)     C = the first bytecode operation
+//   D = (where partial a goes in bpart - the bundle-ordered copy read by k_scalar_reverse_bundles - or -1, same for b, 0, 0)
 // Software pipeline, one cp.async group per bundle: records travel kVRecAhead bundles ahead into a shared-memory ring of
 // kVRecSlots, the global operands of a bundle kVOpAhead bundles ahead (their addresses come from the record, which has landed by
 // then); wait_group keeps the last kVOpAhead - 1 groups in flight.
-constexpr int kVRecAhead = 12, kVRecSlots = 16, kVOpAhead = 6, kVOpSlots = 8;
+constexpr int kVRecAhead = 6, kVRecSlots = 8, kVOpAhead = 3, kVOpSlots = 4;
 struct VFwdP {
-    const int4 *recA, *recB, *recC; const int4 *ops; const double *fconst; void *val; void *epart; int64_t n_leaf; int64_t n_bundles;
+    const int4 *recA, *recB, *recC, *recD; const int4 *ops; const double *fconst; void *val; void *epart; void *bpart; int64_t n_leaf; int64_t n_bundles;
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -355,20 +362,22 @@ __device__ __forceinline__ void cp_async_wait_keep() { asm volatile("cp.async.wa
 template <typename T>
 __global__ void __launch_bounds__(32) k_scalar_forward_bundles(const VFwdP P) {
     __shared__ __align__(16) T ring[kVRing * 32];
-    __shared__ int4 srec[kVRecSlots][3][32];
+    __shared__ int4 srec[kVRecSlots][4][32];
     __shared__ __align__(16) T sop[kVOpSlots][2][32];
     const int lane = threadIdx.x;
     T *val = reinterpret_cast<T *>(P.val);
     T *epart = reinterpret_cast<T *>(P.epart);
+    T *bpart = reinterpret_cast<T *>(P.bpart);
     const int64_t T_ = P.n_bundles;
     for (int64_t t = -kVRecAhead; t < T_; ++t) {
         cp_async_wait_keep<kVOpAhead - 1>();                       // groups of iterations <= t - kVOpAhead have landed
-        int4 A0 = make_int4(kVEmpty, 0, 0, 0), B0 = A0, C0 = A0;
-        if (t >= 0) { A0 = srec[t & (kVRecSlots - 1)][0][lane]; B0 = srec[t & (kVRecSlots - 1)][1][lane]; C0 = srec[t & (kVRecSlots - 1)][2][lane]; }
+        int4 A0 = make_int4(kVEmpty, 0, 0, 0), B0 = A0, C0 = A0, D0 = A0;
+        if (t >= 0) { A0 = srec[t & (kVRecSlots - 1)][0][lane]; B0 = srec[t & (kVRecSlots - 1)][1][lane]; C0 = srec[t & (kVRecSlots - 1)][2][lane]; D0 = srec[t & (kVRecSlots - 1)][3][lane]; }
         {                                                          // records of bundle t + kVRecAhead (tables are padded)
             const int64_t tr = t + kVRecAhead, q = tr * 32 + lane;
             const int sl = (int)(tr & (kVRecSlots - 1));
             cp_async16(&srec[sl][0][lane], P.recA + q); cp_async16(&srec[sl][1][lane], P.recB + q); cp_async16(&srec[sl][2][lane], P.recC + q);
+            cp_async16(&srec[sl][3][lane], P.recD + q);
         }
         const int64_t to = t + kVOpAhead;
         if (to >= 0 && to < T_) {                                  // pull_value! of bundle t + kVOpAhead: leaves, literals, old slots
@@ -389,6 +398,8 @@ __global__ void __launch_bounds__(32) k_scalar_forward_bundles(const VFwdP P) {
             ring[(int)(t & (kVRing - 1)) * 32 + lane] = v;
             if (B0.x >= 0) epart[B0.x] = d[0];                              // cache[] = partials, where the reverse sweep reads them
             if (B0.y >= 0) epart[B0.y] = d[1];
+            if (D0.x >= 0) bpart[D0.x] = d[0];
+            if (D0.y >= 0) bpart[D0.y] = d[1];
         }
         __syncwarp();
     }
@@ -399,7 +410,7 @@ __global__ void __launch_bounds__(32) k_scalar_forward_bundles(const VFwdP P) {
 //   number of edges | has-exports << 24)   sources: kVGlobal: consumer instruction (adjoint at der[c*R + r]), kVRingSrc: ring entry
 //   B = (first edge in vsrc/epart; leaf: ordinal of the origin buffer; leaf: element, low word; high word)
 struct VRevP {
-    const int4 *recA, *recB; const int32_t *vsrc; const void *epart;
+    const int4 *recA, *recB; const int32_t *vsrc; const void *epart; const void *bpart;
     const int64_t *xoff; const int32_t *xord; const int64_t *xelem;
     void *const *ext_der; const int64_t *ext_size;
     void *der; int64_t R; int64_t n_bundles; int leaves_zero;
@@ -415,11 +426,13 @@ __global__ void __launch_bounds__(32) k_scalar_reverse_bundles(const VRevP P) {
     constexpr int kVRing = kVRingR, kVRecAhead = kVRecAheadR, kVRecSlots = kVRecSlotsR, kVOpAhead = kVOpAheadR, kVOpSlots = kVOpSlotsR;
     __shared__ __align__(16) T ring[kVRing * 32];
     __shared__ int4 srec[kVRecSlots][2][32];
-    __shared__ __align__(16) T sop[kVOpSlots][5][32];
+    __shared__ __align__(16) T sop[kVOpSlots][3][32];             // [0], [1]: adjoints read from global memory, [2]: a leaf's origin.deriv
+    __shared__ __align__(16) T spp[kVOpSlots][32][2];             // the partials of edges 0 and 1: ONE coalesced copy per lane (bpart is bundle-ordered)
     const int lane = threadIdx.x;
     const int64_t R = P.R, r = blockIdx.x;
     T *der = reinterpret_cast<T *>(P.der);
     const T *epart = reinterpret_cast<const T *>(P.epart);
+    const T *bpart = reinterpret_cast<const T *>(P.bpart);
     const int64_t T_ = P.n_bundles;
     auto leaf_ptr = [&](const int4 &Bq) -> T * {
         const int64_t elem = (int64_t)(unsigned)Bq.z | ((int64_t)Bq.w << 32);
@@ -441,22 +454,25 @@ __global__ void __launch_bounds__(32) k_scalar_reverse_bundles(const VRevP P) {
                 T(*o)[32] = sop[to & (kVOpSlots - 1)];
                 const int ne = A.w & 0xffffff;
                 if (ne > 0) {
-                    cp_async_small<sizeof(T)>(&o[0][lane], epart + Bq.x);
-                    if (((unsigned)A.y >> 30) == kVGlobal) cp_async_small<sizeof(T)>(&o[2][lane], der + (int64_t)(A.y & 0x3fffffff) * R + r);
+                    cp_async_small<2 * sizeof(T)>(&spp[to & (kVOpSlots - 1)][lane][0], bpart + 2 * (to * 32 + lane));
+                    if (((unsigned)A.y >> 30) == kVGlobal) cp_async_small<sizeof(T)>(&o[0][lane], der + (int64_t)(A.y & 0x3fffffff) * R + r);
                 }
-                if (ne > 1) {
-                    cp_async_small<sizeof(T)>(&o[1][lane], epart + Bq.x + 1);
-                    if (((unsigned)A.z >> 30) == kVGlobal) cp_async_small<sizeof(T)>(&o[3][lane], der + (int64_t)(A.z & 0x3fffffff) * R + r);
-                }
-                if (A.x < 0 && !P.leaves_zero) cp_async_small<sizeof(T)>(&o[4][lane], leaf_ptr(Bq));   // pull_deriv!
+                if (ne > 1 && ((unsigned)A.z >> 30) == kVGlobal) cp_async_small<sizeof(T)>(&o[1][lane], der + (int64_t)(A.z & 0x3fffffff) * R + r);
+                if (A.x < 0 && !P.leaves_zero) cp_async_small<sizeof(T)>(&o[2][lane], leaf_ptr(Bq));   // pull_deriv!
+                if (A.x >= 0 && ((A.w >> 24) & 2))                                                       // what later instructions pushed into an exported slot
+                    cp_async_small<sizeof(T)>(&o[2][lane], reinterpret_cast<const T *>(P.ext_der[Bq.w]) + Bq.z + r * P.ext_size[Bq.w]);
             }
         }
         cp_async_commit();
         if (A0.x != kVEmpty) {
             T(*o)[32] = sop[t & (kVOpSlots - 1)];
             const int ne = A0.w & 0xffffff;
-            T acc = (A0.x < 0 && !P.leaves_zero) ? o[4][lane] : (T)0;
-            if (A0.x >= 0 && (A0.w >> 24)) {
+            T acc = (A0.x < 0 && !P.leaves_zero) ? o[2][lane] : (T)0;
+            const T p0 = spp[t & (kVOpSlots - 1)][lane][0], p1 = spp[t & (kVOpSlots - 1)][lane][1];
+            if (A0.x >= 0 && ((A0.w >> 24) & 2)) {
+                acc = acc + o[2][lane];
+                (reinterpret_cast<T *>(P.ext_der[B0.w]) + B0.z)[r * P.ext_size[B0.w]] = (T)0;               // unseed!(output)
+            } else if (A0.x >= 0 && (A0.w >> 24)) {
                 // adjoints that instructions AFTER the block pushed into an exported slot (one TrackedReal, one deriv field)
                 for (int64_t x = P.xoff[A0.x]; x < P.xoff[A0.x + 1]; ++x) {
                     const int oo = P.xord[x];
@@ -465,8 +481,8 @@ __global__ void __launch_bounds__(32) k_scalar_reverse_bundles(const VRevP P) {
                 }
             }
             // increment_deriv!(slot, deriv(out_c) * partial) for every consumer c, in the reference's order
-            if (ne > 0) acc = acc + (((unsigned)A0.y >> 30) == kVRingSrc ? ring[A0.y & 0x3fffffff] : o[2][lane]) * o[0][lane];
-            if (ne > 1) acc = acc + (((unsigned)A0.z >> 30) == kVRingSrc ? ring[A0.z & 0x3fffffff] : o[3][lane]) * o[1][lane];
+            if (ne > 0) acc = acc + (((unsigned)A0.y >> 30) == kVRingSrc ? ring[A0.y & 0x3fffffff] : o[0][lane]) * p0;
+            if (ne > 1) acc = acc + (((unsigned)A0.z >> 30) == kVRingSrc ? ring[A0.z & 0x3fffffff] : o[1][lane]) * p1;
             for (int e = 2; e < ne; ++e) {
                 const int c = P.vsrc[B0.x + e];
                 const T a = ((unsigned)c >> 30) == kVRingSrc ? ring[c & 0x3fffffff] : der[(int64_t)(c & 0x3fffffff) * R + r];
@@ -776,7 +792,10 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
                     (long long)nl, (long long)ne, (long long)nblk, (long long)B.n_grow, (long long)B.n_near, (long long)B.n_staged, (long long)B.n_direct);
     }
     // bundle plans (k_scalar_forward_bundles / k_scalar_reverse_bundles) for deep graphs ------------------------------------------
-    std::vector<int4> vfA, vfB, vfC, vrA, vrB;
+    std::vector<int4> vfA, vfB, vfC, vfD, vrA, vrB;
+    std::vector<int32_t> bpos(2 * n, -1);         // where partial (i, a|b) goes in the bundle-ordered copy, or -1
+    std::vector<int64_t> fq;                       // forward bundle position of instruction i
+    int64_t n_bpart = 0;
     std::vector<int32_t> vsrc(ne, 0);
     B.n_fbundles = B.n_rbundles = 0;
     B.fwd_bundles = B.rev_bundles = false;
@@ -805,6 +824,7 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
             BundlePlan bp = schedule_bundles(n, soff, succ, indeg, height);
             if (bp.n_bundles > 0) {
                 const int64_t T = bp.n_bundles;
+                fq.assign(n, 0);
                 vfA.assign((T + kVRecAhead + 1) * 32, make_int4(kVEmpty, 0, 0, 0)); vfB.assign((T + kVRecAhead + 1) * 32, make_int4(-1, -1, 0, 0)); vfC.assign((T + kVRecAhead + 1) * 32, make_int4(0, 0, 0, 0));
                 for (int64_t i = 0; i < n; ++i) {
                     auto src = [&](int kind, int code) -> int {
@@ -820,6 +840,7 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
                     vfA[q] = make_int4((int)i, src(kind_a[i], code_a[i]), src(kind_b[i], code_b[i]), 0);
                     vfB[q] = make_int4(epos[2 * i], epos[2 * i + 1], E.x, E.y | (E.z << 16));
                     vfC[q] = h_ops[E.x];
+                    fq[i] = q;
                 }
                 B.n_fbundles = T; B.fwd_bundles = true;
             }
@@ -872,16 +893,34 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
                         if (k < 2) s01[k] = code;
                     }
                     const int64_t q = (int64_t)bp.bundle[sl] * 32 + bp.lane[sl];
-                    const int flags = (sl < n && xoff[sl + 1] > xoff[sl]) ? 1 : 0;
+                    int flags = (sl < n && xoff[sl + 1] > xoff[sl]) ? 1 : 0;
+                    const bool one_export = flags && xoff[sl + 1] - xoff[sl] == 1 && xelem[xoff[sl]] < INT_MAX;
+                    if (one_export) flags |= 2;                    // its adjoint-so-far is staged like a leaf's (B.z = element, B.w = buffer)
                     vrA[q] = make_int4(sl < n ? (int)sl : ~(int)(sl - n), s01[0], s01[1], (int)cnt | (flags << 24));
-                    if (sl < n) vrB[q] = make_int4((int)e0, brow[sl], 0, 0);
+                    if (sl < n) vrB[q] = make_int4((int)e0, brow[sl], one_export ? (int)xelem[xoff[sl]] : 0, one_export ? xord[xoff[sl]] : 0);
                     else {
                         const int64_t l = sl - n;
                         vrB[q] = make_int4((int)e0, leaf_ord[l], (int)(uint32_t)(leaf_elem[l] & 0xffffffffLL), (int)(leaf_elem[l] >> 32));
                     }
                 }
-                if (!vrA.empty()) { B.n_rbundles = T; B.rev_bundles = true; }
+                if (!vrA.empty()) {
+                    B.n_rbundles = T; B.rev_bundles = true;
+                    n_bpart = (T + kVRecAhead + 1) * 64;
+                    // partial of (instruction i, operand k) = edge e of the operand's slot: edges 0 and 1 of the slot at bundle
+                    // position q live at bpart[2q], bpart[2q + 1]
+                    for (int64_t i = 0; i < n; ++i)
+                        for (int k = 0; k < 2; ++k) {
+                            const int64_t sl = slot_of(k == 0 ? kind_a[i] : kind_b[i], k == 0 ? code_a[i] : code_b[i]);
+                            if (sl < 0 || epos[2 * i + k] < 0) continue;
+                            const int64_t j = epos[2 * i + k] - reoff[rpos[sl]];
+                            if (j < 2) bpos[2 * i + k] = (int32_t)(2 * ((int64_t)bp.bundle[sl] * 32 + bp.lane[sl]) + j);
+                        }
+                }
             }
+        }
+        if (B.fwd_bundles) {
+            vfD.assign(vfA.size(), make_int4(-1, -1, 0, 0));
+            for (int64_t i = 0; i < n; ++i) vfD[fq[i]] = make_int4(bpos[2 * i], bpos[2 * i + 1], 0, 0);
         }
         if (getenv("RDB_SCALAR_DEBUG"))
             fprintf(stderr, "[rdb scalar] levels fwd=%d rev=%d bundles fwd=%lld rev=%lld\n", nfl, nrl, (long long)B.n_fbundles, (long long)B.n_rbundles);
@@ -906,7 +945,7 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
     auto pad = [](size_t b) { return (b + 15) & ~size_t(15); };
     size_t bytes = pad(n * 16) + pad((nfl + 1) * 8) + pad(h_ops.size() * 16) + pad(nex * 16) + pad(2 * n * 4) + pad(nl * 4) + pad(nl * 8) +
                    pad(nexp * 4) * 2 + pad(nexp * 8) + pad(ns * 4) + pad((ns + 1) * 8) + pad(ne * 4) + pad((nrl + 1) * 8) + pad((n + 1) * 8) +
-                   pad(nexp * 4) + pad(nexp * 8) + pad(nref * 8) * 3 + pad(npos * 16) * 4 + pad(nblk * kStageF * 8) + pad(ne * 4) * 2 + pad(vfA.size() * 16) * 3 + pad(vrA.size() * 16) * 2 + 1024;
+                   pad(nexp * 4) + pad(nexp * 8) + pad(nref * 8) * 3 + pad(npos * 16) * 4 + pad(nblk * kStageF * 8) + pad(ne * 4) * 2 + pad(vfA.size() * 16) * 4 + pad(vrA.size() * 16) * 2 + pad(2 * n * 4) + 1024;
     std::vector<uint8_t> host(bytes, 0);
     if (cudaMalloc(&B.d_tables, bytes) != cudaSuccess) { cudaGetLastError(); return "scalar block: out of device memory (tables)"; }
     uint8_t *hp = host.data();
@@ -924,7 +963,7 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
     put(B.d_rslot, rslot); put(B.d_reoff, reoff); put(B.d_esrc, esrc); put(B.d_rlevel_off, rlevel_off);
     put(B.d_xoff, xoff); put(B.d_xord, xord); put(B.d_xelem, xelem);
     put(B.d_recA, recA); put(B.d_recB, recB); put(B.d_recC, recC); put(B.d_recD, recD); put(B.d_pf, pf); put(B.d_tsrc, tsrc);
-    put(B.d_vfA, vfA); put(B.d_vfB, vfB); put(B.d_vfC, vfC); put(B.d_vrA, vrA); put(B.d_vrB, vrB); put(B.d_vsrc, vsrc);
+    put(B.d_vfA, vfA); put(B.d_vfB, vfB); put(B.d_vfC, vfC); put(B.d_vfD, vfD); put(B.d_bpos, bpos); put(B.d_vrA, vrA); put(B.d_vrB, vrB); put(B.d_vsrc, vsrc);
     std::vector<void *> nulls(nref, nullptr); std::vector<int64_t> zeros(nref, 0);
     put(B.d_ext_val, nulls); put(B.d_ext_der, nulls); put(B.d_ext_size, zeros);
     if ((size_t)(hp - host.data()) > bytes) return "scalar block: internal table overflow";
@@ -933,14 +972,15 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
     }
     B.n_lit = B.fwd_bundles ? (int64_t)n_fconst : 0;
     if (cudaMalloc(&B.d_val, std::max<size_t>((size_t)(nl + n + B.n_lit) * es, 16)) != cudaSuccess ||
-        cudaMalloc(&B.d_epart, std::max<size_t>((size_t)ne * es, 16)) != cudaSuccess) { cudaGetLastError(); return "scalar block: out of device memory (pools)"; }
+        cudaMalloc(&B.d_epart, std::max<size_t>((size_t)ne * es, 16)) != cudaSuccess ||
+        cudaMalloc(&B.d_bpart, std::max<size_t>((size_t)n_bpart * es, 16)) != cudaSuccess) { cudaGetLastError(); return "scalar block: out of device memory (pools)"; }
     B.h_ext_val.assign(nref, nullptr); B.h_ext_der.assign(nref, nullptr); B.h_ext_size.assign(nref, 0);
     return "";
 }
 
 void scalar_block_free(ScalarBlock &B) {
-    cudaFree(B.d_tables); cudaFree(B.d_val); cudaFree(B.d_epart); cudaFree(B.d_der);
-    B.d_tables = B.d_val = B.d_epart = B.d_der = nullptr;
+    cudaFree(B.d_tables); cudaFree(B.d_val); cudaFree(B.d_epart); cudaFree(B.d_bpart); cudaFree(B.d_der);
+    B.d_tables = B.d_val = B.d_epart = B.d_bpart = B.d_der = nullptr;
     B.der_bytes = 0;
 }
 
@@ -953,9 +993,9 @@ cudaError_t scalar_block_upload_ext(ScalarBlock &B, cudaStream_t s) {
 }
 
 // Which kernel takes a reverse sweep of R >= 16 seeds.  Fitted on B200 (profiles/README.md): the streaming kernel costs ~290 clk
-// per schedule position whatever R is (one warp per 32 seeds); one bundle warp per seed costs ~(1100 + 170 W) clk per bundle
-// with W warps resident on an SM (<= 13), so it wins while the seeds fit one or two rounds of a short schedule (n <~ 2048 for
-// the literal Hessian tape).  Its global adjoint rows must also stay small.
+// per schedule position whatever R is (one warp per 32 seeds); one bundle warp per seed costs ~(1100 + 100 W) clk per bundle
+// with W warps resident on an SM (<= 13), so it wins while the seeds fit a few rounds of a short schedule (n <= 4096 for the
+// literal Hessian tape).  Its global adjoint rows must also stay small.
 bool scalar_reverse_streams(const ScalarBlock &B, int64_t R, size_t es) {
     if (R < 16) return false;
     if (!B.rev_bundles) return true;
@@ -963,7 +1003,7 @@ bool scalar_reverse_streams(const ScalarBlock &B, int64_t R, size_t es) {
     if (force) return force == 1;
     if ((double)B.n_brow * (double)R * (double)es > 4.0 * (1 << 30)) return true;
     const double W = std::min(13.0, std::ceil((double)R / 148.0)), rounds = std::ceil((double)R / (148.0 * 13.0));
-    const double t_stream = 290.0 * (double)B.n_sblocks * 32.0, t_bundles = (1100.0 + 170.0 * W) * (double)B.n_rbundles * rounds;
+    const double t_stream = 290.0 * (double)B.n_sblocks * 32.0, t_bundles = (1100.0 + 100.0 * W) * (double)B.n_rbundles * rounds;
     return t_stream <= t_bundles;
 }
 
@@ -997,11 +1037,11 @@ cudaError_t scalar_block_forward(cudaStream_t s, ScalarBlock &B, const double *f
         ++nl;
     }
     if (B.fwd_bundles) {
-        VFwdP V{B.d_vfA, B.d_vfB, B.d_vfC, B.d_ops, fconst, B.d_val, B.d_epart, B.n_leaf, B.n_fbundles};
+        VFwdP V{B.d_vfA, B.d_vfB, B.d_vfC, B.d_vfD, B.d_ops, fconst, B.d_val, B.d_epart, B.d_bpart, B.n_leaf, B.n_fbundles};
         k_scalar_forward_bundles<T><<<1, 32, 0, s>>>(V);
         ++nl;
     } else {
-        FwdP P{B.d_finstr, B.d_flevel_off, B.d_ops, B.d_exprs, B.d_epos, fconst, B.d_val, B.d_epart, B.n_leaf, 0, 0};
+        FwdP P{B.d_finstr, B.d_flevel_off, B.d_ops, B.d_exprs, B.d_epos, B.rev_bundles ? B.d_bpos : nullptr, B.d_bpart, fconst, B.d_val, B.d_epart, B.n_leaf, 0, 0};
         for (const ScalarSeg &g : B.fsegs) {
             P.lv0 = g.lv0; P.lv1 = g.lv1;
             k_scalar_forward<T><<<g.grid, kFwdThreads, 0, s>>>(P);
@@ -1027,7 +1067,7 @@ cudaError_t scalar_block_reverse(cudaStream_t s, ScalarBlock &B, int64_t R, bool
         k_scalar_reverse_stream<T><<<(unsigned)((R + 31) / 32), 32, 0, s>>>(P);
         ++nl;
     } else if (B.rev_bundles) {
-        VRevP V{B.d_vrA, B.d_vrB, B.d_vsrc, B.d_epart, B.d_xoff, B.d_xord, B.d_xelem, B.d_ext_der, B.d_ext_size, B.d_der, R, B.n_rbundles,
+        VRevP V{B.d_vrA, B.d_vrB, B.d_vsrc, B.d_epart, B.d_bpart, B.d_xoff, B.d_xord, B.d_xelem, B.d_ext_der, B.d_ext_size, B.d_der, R, B.n_rbundles,
                 leaves_zero ? 1 : 0};
         k_scalar_reverse_bundles<T><<<(unsigned)R, 32, 0, s>>>(V);
         ++nl;
