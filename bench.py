@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -76,14 +76,25 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def pause(self):
+        """stop sampling (the lines so far are kept); start() resumes"""
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            try:
+                self.thread.join(timeout=2)
+            except Exception:
+                pass
+            self.proc = None
+            self.ran = True
+
     def stop(self):
-        if not self.proc:
+        self.pause()
+        if not getattr(self, "ran", False):
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
@@ -249,7 +260,8 @@ def main():
     if rank == 0:
         sampler.start()
     ms = timed_steps(torch, dist, world, step_dev, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        sampler.pause()                                       # the host-side parity check below is not part of any timed region
     value = world * args.steps / (ms * 1e-3)
 
     # parity of what was just timed: closed form, O(n^2)
@@ -275,9 +287,12 @@ def main():
     def step_e2e():
         rd.gradient_(res_h, ct, (a_h, b_h))
 
+    if rank == 0:
+        sampler.start()
     ms_e2e = timed_steps(torch, dist, world, step_e2e, max(3, args.steps // 2), 3)
     e2e_steps = max(3, args.steps // 2)
     e2e_val = world * e2e_steps / (ms_e2e * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None           # sampled every 20 ms during both timed regions (device-resident, end-to-end)
     assert np.max(np.abs(ga_h - ga)) <= tol * np.max(np.abs(ga))
     gb_ref = a64.sum(1)[:, None] + a64.sum(0)[None, :]
     assert np.max(np.abs(gb_h - gb_ref)) <= tol * np.max(np.abs(gb_ref))

@@ -462,6 +462,60 @@ __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, cons
     }
 }
 
+// Column-major source (rows strided by ld... i.e. consecutive ROWS are contiguous, k strided): tile of 128 rows x 32 k, so every
+// column read is 1 KB contiguous (the 32-row x 128-k tile of the generic kernel reads 256-byte pieces 32 KB apart: every piece a
+// different DRAM page).  Transposed through shared memory ([k % 4][k / 4][row]); a thread then owns 4 rows x 4 consecutive k and
+// stores one packed 32-bit word per slice and row - a warp writes full 32-byte sectors of 4 rows.
+__global__ void __launch_bounds__(256) k_slice_i8_cm(int8_t *__restrict__ dst, const double *__restrict__ src, int64_t ld, int rows, int K,
+                                                     int Kp, int nslices, int bits, const int *__restrict__ e_in) {
+    __shared__ double tile[4][8][132];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int r0 = blockIdx.y * 128, k0 = blockIdx.x * 32;
+    {
+        const int rr = tid & 127, kb = tid >> 7;                 // 128 threads along the rows, two columns per pass
+        const int r = r0 + rr;
+#pragma unroll 4
+        for (int k = kb; k < 32; k += 2) {
+            const int kk = k0 + k;
+            tile[k & 3][k >> 2][rr] = (r < rows && kk < K) ? src[r + (int64_t)kk * ld] : 0.0;
+        }
+    }
+    __syncthreads();
+    const int64_t plane = (int64_t)rows * Kp;
+    const int kg = lane & 7, k = k0 + 4 * kg;
+    const int radix = 1 << bits, half = radix >> 1;
+    long long X[4][4];
+    bool ok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rl = w * 4 + (lane >> 3) + 32 * i, r = r0 + rl;
+        ok[i] = r < rows && k < Kp;
+        const int e = ok[i] ? e_in[r] : 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double v = tile[j][kg][rl];
+            X[i][j] = (ok[i] && isfinite(v)) ? __double2ll_rn(scalbn(v, bits * nslices - e)) : 0LL;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (!ok[i]) continue;
+        const int r = r0 + w * 4 + (lane >> 3) + 32 * i;
+        for (int sidx = nslices - 1; sidx >= 0; --sidx) {
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int d = (int)(X[i][j] & (long long)(radix - 1));
+                X[i][j] >>= bits;
+                if (sidx > 0 && d >= half) { d -= radix; X[i][j] += 1; }
+                if (sidx == 0) d = (int)((X[i][j] << bits) | d);
+                packed |= ((uint32_t)(uint8_t)(int8_t)d) << (8 * j);
+            }
+            *reinterpret_cast<uint32_t *>(dst + sidx * plane + (int64_t)r * Kp + k) = packed;
+        }
+    }
+}
+
 struct OzParams {
     double *C;
     int64_t ldc;
@@ -1007,7 +1061,11 @@ static void slice_operand(cudaStream_t st, const double *src, int64_t ld, int64_
     k_row_exponent<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(mx, (int)rows, bits, e, sc);
     dim3 g((unsigned)((Kp + 127) / 128), (unsigned)((rows + 31) / 32));
     if (kmajor) k_slice_i8<true><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e);
-    else k_slice_i8<false><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e);
+    else {
+        dim3 gc((unsigned)((Kp + 31) / 32), (unsigned)((rows + 127) / 128));
+        if (gc.y <= 65535) k_slice_i8_cm<<<gc, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e);
+        else k_slice_i8<false><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e);
+    }
 }
 
 // returns the slices/scales of one operand; launches = kernels issued (0 on a cache hit)
