@@ -14,11 +14,17 @@
 //     in DESCENDING tape order (operand a before b), of deriv(out_c)*partial_c — exactly the sequence of increments the
 //     reference applies to s.deriv, so every sum is built in the reference's order, but each adjoint is written ONCE, by one
 //     thread, with no read-modify-write, no atomics and no unseed! traffic (a slot is final before anyone reads it);
-//   * levelises that pull graph too.  With R >= 16 seeds a warp's lanes are 32 seeds (adjoints laid out [slot][seed]: every
-//     load/store is one coalesced 256-byte line), a CTA's warps take the slots of a level, and a CTA only ever needs
-//     __syncthreads between levels because seeds never interact.  Algorithmic traffic per (instruction, seed): one 8-byte
-//     write + one 8-byte read per operand edge (~24 B for a binary instruction) against 48 B for the push form.
-//   * partials are stored by the forward sweep directly in reverse-edge order, so the reverse sweep streams them.
+//   * executes both graphs with the kernel that fits their shape (all of them produce the same sums in the same order):
+//       - shallow, wide graphs: one launch per dataflow level (k_scalar_forward, k_scalar_reverse_slots);
+//       - deep graphs (long `acc += term` chains), forward and reverse with few seeds: the dataflow list-scheduled into bundles
+//         of <= 32 independent slots executed by ONE warp (k_scalar_forward_bundles, k_scalar_reverse_bundles);
+//       - 16 or more seeds: the streaming kernel (lanes = seeds, one warp walks the whole schedule for its 32 seeds without any
+//         synchronisation, k_scalar_reverse_stream) or one bundle warp per seed, whichever a fitted cost model prefers
+//         (scalar_reverse_streams).
+//     In every kernel the adjoints that are still "near" live in a shared-memory ring and only the ones with a far reader are
+//     ever stored to global memory; records, partials and far operands are staged ahead of their use by cp.async.
+//   * partials are stored by the forward sweep directly where the reverse kernels read them (reverse-edge order, plus a
+//     bundle-ordered copy for the bundle kernel).
 // Compiled with -fmad=false (parity of deriv*partial + accumulate with the uncontracted CPU arithmetic).
 #include <cuda_runtime.h>
 #include <algorithm>
