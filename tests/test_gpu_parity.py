@@ -484,6 +484,23 @@ def test_host_arrays_at_panel_sizes(rd, orc, name):
         assert relerr(r, g) < 1e-12
 
 
+def test_host_arrays_at_panel_sizes_f32(rd, orc):
+    """FP32 takes the same host-array routes (3xTF32 tcgen05 GEMMs cut into column panels, panelled uploads) from 32 MiB on."""
+    import torch
+    n = 3072                                                    # 3072 x 3072 FP32 = 36 MiB
+    rng = np.random.default_rng(6)
+    rec = (rng.random((n, n)).astype(np.float32), rng.random((n, n)).astype(np.float32))
+    ins = (np.asfortranarray((rng.random((n, n)) / n).astype(np.float32)), np.asfortranarray(rng.random((n, n)).astype(np.float32)))
+    ct = run_gradient(rd, orc, rd.workloads.f_gradient_example, rec, ins, dtype=np.float32, check_buffers=False)
+    dev_in = tuple(torch.from_numpy(np.ascontiguousarray(x.T)).cuda() for x in ins)
+    dev_out = tuple(torch.empty(n * n, dtype=torch.float32, device="cuda") for _ in ins)
+    rd.gradient_(dev_out, ct, dev_in)
+    host_out = tuple(np.zeros((n, n), np.float32, order="F") for _ in ins)
+    rd.gradient_(host_out, ct, ins)
+    for h, d in zip(host_out, dev_out):
+        assert relerr(h, d.cpu().numpy().reshape(n, n, order="F")) < 1e-6
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_cfg2_full_size_closed_form(rd):
     """4096x4096 FP64: the oracle needs ~3 s of DGEMM per eval, so the full-size check uses the size-independent
