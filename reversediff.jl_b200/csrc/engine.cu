@@ -58,11 +58,15 @@ struct rdb_ctx {
     int gemm_f64_mode = 0, ozaki_slices = 0;   // for rdb_gemm on this context
     cudaStream_t copy_stream = nullptr;        // device->host result copies that overlap the tail of the reverse sweep
     cudaStream_t upload_stream = nullptr;      // host->device input copies in column panels (rdb_tape_set_input), see settle_uploads
+    cudaStream_t side_stream = nullptr;        // operand slicing for the NEXT `*` GEMM while the current one runs (preslice_*)
+    cudaEvent_t side_ev = nullptr;
 };
 static void ctx_release(rdb_ctx *c) {
     if (!c || --c->refs > 0) return;
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->upload_stream) cudaStreamDestroy(c->upload_stream);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->side_ev) cudaEventDestroy(c->side_ev);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -108,6 +112,7 @@ struct InstrPlan {
     void *jit_fn[2] = {nullptr, nullptr};   // [reduce]
     bool jit_tried[2] = {false, false};
     bool rev_done[2] = {false, false};   // `*`: this operand's adjoint was already accumulated in this sweep (paired panels, mul_reverse)
+    uint64_t dtag = 0;                   // `*`: identity of deriv(output) for the sliced-operand cache, fixed when first needed in a sweep
 };
 
 struct StepStat {
@@ -271,6 +276,10 @@ static int operand_value(rdb_tape *t, OperandPlan &o, MatRef<T> &m) {
 
 // ------------------------------------------------------------------------------------------ forward
 static void plan_col_panels(int64_t rows, int64_t cols, int64_t width[4]);
+template <typename T> struct MatRef;
+template <typename T> static void mul_operand_ref(rdb_tape *t, OperandPlan &o, MatRef<T> &m);
+static bool preslice_on(rdb_tape *t);
+static int preslice_begin(rdb_tape *t);
 static int settle_uploads(rdb_tape *t, int keep);
 static int droot(rdb_tape *t, int b);
 template <typename T>
@@ -370,6 +379,30 @@ static int forward_pass(rdb_tape *t, int order = 1) {
                     }
                     bi.up_n = 0;
                     break;
+                }
+                if (order == 1 && preslice_on(t) && M >= 256 && N >= 256 && K >= 256) {
+                    // while this GEMM runs: slice the operands of the next `*` whose operands exist already (tape inputs,
+                    // constants, outputs of earlier instructions)
+                    for (size_t j = i + 1; j < n; ++j) {
+                        InstrPlan &J = t->instrs[j];
+                        if (J.blk || J.rec.opcode != OP_MUL) continue;
+                        bool ready = J.in[0].mode != OPM_GATHER && J.in[1].mode != OPM_GATHER && J.in[0].rows >= 256 && J.in[1].cols >= 256 &&
+                                     J.in[0].cols >= 256;
+                        for (size_t x = i; x < j && ready; ++x)
+                            for (int b = 0; b < 2; ++b)
+                                if (droot(t, t->instrs[x].rec.out) == droot(t, J.in[b].rec.buffer)) ready = false;
+                        if (ready) {
+                            OK(preslice_begin(t));
+                            MatRef<T> A2, B2;
+                            mul_operand_ref<T>(t, J.in[0], A2);
+                            mul_operand_ref<T>(t, J.in[1], B2);
+                            ozaki_preslice(t->ctx->side_stream, (const double *)A2.ptr, A2.ld, J.in[0].rows, J.in[0].cols, A2.stored_t,
+                                           t->opts.ozaki_slices, operand_tag(t, J.in[0]));
+                            ozaki_preslice(t->ctx->side_stream, (const double *)B2.ptr, B2.ld, J.in[1].cols, J.in[0].cols, !B2.stored_t,
+                                           t->opts.ozaki_slices, operand_tag(t, J.in[1]));
+                        }
+                        break;
+                    }
                 }
                 g_tag_a = operand_tag(t, I.in[0]); g_tag_b = operand_tag(t, I.in[1]);
                 KL(t, gemm_t<T>(S(t), A.stored_t, B.stored_t, M, N, K, (T)1, A.ptr, A.ld, B.ptr, B.ld, (T)0, (T *)out.val, M));
@@ -629,6 +662,30 @@ static int find_mul_partner(rdb_tape *t, int k, int root, int64_t rows, int64_t 
     return -1;
 }
 
+// ---- slicing ahead (FP64 int8-slice GEMMs): the absmax/digit passes of the NEXT `*` GEMM's operands run on a side stream while
+// the current GEMM computes; the GEMM then finds them in the sliced-operand cache (umma.cu, ozaki_preslice).
+static bool preslice_on(rdb_tape *t) {
+    static const bool on = [] { const char *e = getenv("RDB_PRESLICE"); return !(e && e[0] == '0'); }();
+    return on && t->dtype == RDB_F64 && t->opts.gemm_f64_mode != 1 && !t->capturing;
+}
+// the side stream may read everything the main stream has produced so far
+static int preslice_begin(rdb_tape *t) {
+    rdb_ctx *c = t->ctx;
+    if (!c->side_stream) CU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    if (!c->side_ev) CU(cudaEventCreateWithFlags(&c->side_ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->side_ev, S(t)));
+    CU(cudaStreamWaitEvent(c->side_stream, c->side_ev, 0));
+    return RDB_OK;
+}
+// deriv(output) of a `*` as the adjoint GEMM of operand `side` reads it: side a -> rows m, k = n strided; side b -> rows n, k = m contiguous
+static void preslice_delta(rdb_tape *t, InstrPlan &J, int side) {
+    const int64_t M = J.in[0].rows, N = J.in[1].cols;
+    if (!J.dtag) J.dtag = new_delta_tag();
+    const double *d = (const double *)t->bufs[J.rec.out].der;
+    if (side == 0) ozaki_preslice(t->ctx->side_stream, d, M, M, N, false, t->opts.ozaki_slices, J.dtag);
+    else ozaki_preslice(t->ctx->side_stream, d, M, N, M, true, t->opts.ozaki_slices, J.dtag);
+}
+
 // a.deriv += delta * value(b)'   and   b.deriv += value(a)' * delta     (arithmetic.jl:272-285), R seed columns
 template <typename T>
 static int mul_reverse(rdb_tape *t, int k, int64_t R) {
@@ -645,7 +702,30 @@ static int mul_reverse(rdb_tape *t, int k, int64_t R) {
     // the other one can run now (find_mul_partner), both are cut into the same panels and interleaved, so the input's adjoint
     // is final - and on its way to the host - panel by panel while the rest of the sweep still computes.
     auto &E = t->early;
-    const uint64_t dtag = new_delta_tag();
+    if (!I.dtag) I.dtag = new_delta_tag();
+    const uint64_t dtag = I.dtag;
+    if (R == 1 && preslice_on(t) && !E.enabled && M >= 256 && N >= 256 && K >= 256) {      // (panelled GEMMs read delta PANELS: nothing to share)
+        // while this instruction's first adjoint GEMM runs: slice deriv(output) the way its second one reads it, and both views
+        // of the next `*` instruction's deriv(output) if that adjoint is already final
+        OK(preslice_begin(t));
+        if (oa.rec.tracked && ob.rec.tracked && !I.rev_done[0] && !I.rev_done[1]) preslice_delta(t, I, 1);
+        for (int j = k - 1; j >= 0; --j) {
+            InstrPlan &J = t->instrs[j];
+            if (J.blk || J.rec.opcode != OP_MUL) continue;
+            const int oj = droot(t, J.rec.out);
+            bool final_ = !t->dz[oj] && J.in[0].rows >= 256 && J.in[1].cols >= 256 && J.in[0].cols >= 256;
+            for (int i = j + 1; i <= k && final_; ++i) {
+                InstrPlan &X = t->instrs[i];
+                if (X.blk) { final_ = false; break; }
+                for (int b = 0; b < X.rec.n_in; ++b) if (droot(t, X.in[b].rec.buffer) == oj) final_ = false;
+            }
+            if (final_) {
+                if (J.in[0].rec.tracked && !J.rev_done[0]) preslice_delta(t, J, 0);
+                if (J.in[1].rec.tracked && !J.rev_done[1]) preslice_delta(t, J, 1);
+            }
+            break;                                                   // one instruction of lookahead
+        }
+    }
     auto panel_count = [&](int buffer, int64_t rows, int64_t cols, int remaining) -> int {
         const int rb = droot(t, buffer);
         if (E.enabled && R == 1 && E.dst[rb] && !E.issued[rb] && E.remaining[rb] == remaining && cols >= 2048 &&
@@ -676,7 +756,8 @@ static int mul_reverse(rdb_tape *t, int k, int64_t R) {
         if (panel_count(o.rec.buffer, rows, cols, 2) > 1) {
             pj = find_mul_partner(t, k, root, rows, cols, ps);
             if (pj < 0) return 0;
-            ptag = new_delta_tag();
+            if (!t->instrs[pj].dtag) t->instrs[pj].dtag = new_delta_tag();
+            ptag = t->instrs[pj].dtag;
         } else if (panel_count(o.rec.buffer, rows, cols, 1) == 1) return 0;
         int64_t width[4];
         plan_col_panels(rows, cols, width);
@@ -708,10 +789,12 @@ static int mul_reverse(rdb_tape *t, int k, int64_t R) {
             if (oa.mode == OPM_PLAIN) {
                 // a.deriv(MxK) += delta(MxN) * Bmat'(NxK)
                 g_tag_b = operand_tag(t, ob);
+                if (R == 1) g_tag_a = dtag;
                 KL(t, gemm_t<T>(S(t), false, !B.stored_t, M, K, N, (T)1, d, M, B.ptr, B.ld, beta_a, (T *)ba.der + r * ba.size, M));
             } else if (oa.mode == OPM_FOLDED_T) {
                 // scatter-add through the transpose map == origin.deriv(KxM) += Bmat(KxN) * delta'(NxM)
                 g_tag_a = operand_tag(t, ob);
+                if (R == 1) g_tag_b = dtag;
                 KL(t, gemm_t<T>(S(t), B.stored_t, true, K, M, N, (T)1, B.ptr, B.ld, d, M, beta_a, (T *)ba.der + r * ba.size, K));
             } else {
                 g_tag_b = operand_tag(t, ob);
@@ -733,6 +816,7 @@ static int mul_reverse(rdb_tape *t, int k, int64_t R) {
         } else if (ob.mode == OPM_PLAIN) {
             // b.deriv(K x N*R) += Amat'(KxM) * delta(M x N*R): the R seed columns ride along as extra GEMM columns
             g_tag_a = operand_tag(t, oa);
+            if (R == 1) g_tag_b = dtag;
             KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, N * R, M, (T)1, A.ptr, A.ld, delta, M, beta_b, (T *)bb.der, K));
         } else {
             for (int64_t r = 0; r < R; ++r) {
@@ -740,6 +824,7 @@ static int mul_reverse(rdb_tape *t, int k, int64_t R) {
                 if (ob.mode == OPM_FOLDED_T) {
                     // origin.deriv(NxK) += delta'(NxM) * Amat(MxK)
                     g_tag_b = operand_tag(t, oa);
+                    if (R == 1) g_tag_a = dtag;
                     KL(t, gemm_t<T>(S(t), true, A.stored_t, N, K, M, (T)1, d, M, A.ptr, A.ld, beta_b, (T *)bb.der + r * bb.size, N));
                 } else {
                     KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, N, M, (T)1, A.ptr, A.ld, d, M, (T)0, (T *)ob.dense_der, K));
@@ -832,7 +917,7 @@ static int scalar_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
 
 template <typename T>
 static int reverse_pass(rdb_tape *t, int64_t R) {
-    for (auto &I : t->instrs) I.rev_done[0] = I.rev_done[1] = false;
+    for (auto &I : t->instrs) { I.rev_done[0] = I.rev_done[1] = false; I.dtag = 0; }
     for (size_t k = t->instrs.size(); k-- > 0;) {
         InstrPlan &I = t->instrs[k];
         if (I.rec.opcode == OP_SCALAR_BLOCK) { OK(scalar_reverse<T>(t, I, R)); continue; }
@@ -1226,8 +1311,10 @@ static int graph_sweep(rdb_tape *t) {
     if (t->graph_state != 1) return 0;
     t->graph_state = -1;
     if (cudaStreamBeginCapture(S(t), cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return 0; }
+    t->capturing = true;                                   // no side-stream work inside the capture
     int rc = forward_pass<T>(t);
     if (rc == RDB_OK) rc = seed_scalar_and_reverse<T>(t);
+    t->capturing = false;
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(S(t), &g);
     if (rc != RDB_OK || e != cudaSuccess || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); return 0; }
@@ -1715,6 +1802,9 @@ static int hessian_entry(rdb_tape *t, int64_t cb, int64_t ce, void *result, int6
 static int fold_launches(rdb_tape *t, int rc) {
     t->launches += g_extra_launches;
     g_extra_launches = 0;
+    // slicing that ran ahead on the side stream and was not consumed must not outlive the call (the next call may refill the
+    // same cache entries from the main stream)
+    if (t->ctx && t->ctx->side_stream) cudaStreamSynchronize(t->ctx->side_stream);
     return rc;
 }
 #define DISPATCH(t, fn, ...) \

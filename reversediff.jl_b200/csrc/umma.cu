@@ -1033,6 +1033,8 @@ struct SliceEntry {
     int64_t ld, rows, K;
     bool kmajor;
     int ns, bits;
+    cudaEvent_t ready;          // recorded on the stream that (re)filled the entry; readers on another stream wait for it
+    cudaStream_t filled_on;
     int8_t *q;
     double *sc;
     size_t bytes;
@@ -1081,6 +1083,7 @@ static cudaError_t prepare_operand(cudaStream_t st, uint64_t tag, const double *
         if (en.ptr == src && en.ld == ld && en.rows == rows && en.K == K && en.kmajor == kmajor && en.ns == ns && en.bits == ozaki_bits()) { slot = &en; break; }
     if (slot && slot->tag == tag) {
         slot->last_use = ++g_use;
+        if (slot->filled_on != st && slot->ready) cudaStreamWaitEvent(st, slot->ready, 0);   // sliced ahead of time on the side stream
         *q = slot->q; *sc = slot->sc; *launches = 0;
         return cudaSuccess;
     }
@@ -1090,16 +1093,23 @@ static cudaError_t prepare_operand(cudaStream_t st, uint64_t tag, const double *
             size_t lru = 0;
             for (size_t i = 1; i < g_cache.size(); ++i) if (g_cache[i].last_use < g_cache[lru].last_use) lru = i;
             cudaFree(g_cache[lru].q);
+            if (g_cache[lru].ready) cudaEventDestroy(g_cache[lru].ready);
             g_cache_bytes -= g_cache[lru].bytes;
             g_cache.erase(g_cache.begin() + lru);
         }
         if (bytes > cache_cap()) {                                                  // too big to cache
+            if (!ws_q) { *q = nullptr; *sc = nullptr; *launches = 0; return cudaSuccess; }     // slicing ahead: nothing to do
             slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc);
             *q = ws_q; *sc = ws_sc; *launches = 3;
             return cudaSuccess;
         }
         SliceEntry en{};
-        if (cudaMalloc((void **)&en.q, bytes) != cudaSuccess) { cudaGetLastError(); slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc); *q = ws_q; *sc = ws_sc; *launches = 3; return cudaSuccess; }
+        if (cudaMalloc((void **)&en.q, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            if (!ws_q) { *q = nullptr; *sc = nullptr; *launches = 0; return cudaSuccess; }
+            slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc); *q = ws_q; *sc = ws_sc; *launches = 3; return cudaSuccess;
+        }
+        cudaEventCreateWithFlags(&en.ready, cudaEventDisableTiming);
         en.sc = (double *)(en.q + (((size_t)ns * rows * Kp + 255) & ~(size_t)255));
         en.ptr = src; en.ld = ld; en.rows = rows; en.K = K; en.kmajor = kmajor; en.ns = ns; en.bits = ozaki_bits(); en.bytes = bytes;
         g_cache_bytes += bytes;
@@ -1107,10 +1117,34 @@ static cudaError_t prepare_operand(cudaStream_t st, uint64_t tag, const double *
         slot = &g_cache.back();
     }
     slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, slot->q, ws_e, slot->sc);    // (re)fill in place: same buffers, new version
+    if (slot->ready) cudaEventRecord(slot->ready, st);
+    slot->filled_on = st;
     slot->tag = tag;
     slot->last_use = ++g_use;
     *q = slot->q; *sc = slot->sc; *launches = 3;
     return cudaSuccess;
+}
+
+// Slice an operand AHEAD of the GEMM that will read it, on another stream (the slicing passes are HBM-bound, the GEMM kernels
+// tensor-bound and 1 CTA/SM: the two overlap).  The entry lands in the cache under `tag`; the GEMM's own prepare_operand then
+// finds it and makes its stream wait for the entry's event.  kmajor: the operand's k index is the contiguous one
+// (A with ta, B without tb).  Only what gemm_f64_ozaki would run as ONE exact-int32 chunk is sliced ahead.
+cudaError_t ozaki_preslice(cudaStream_t side, const double *src, int64_t ld, int64_t rows, int64_t K, bool kmajor, int nslices, uint64_t tag) {
+    if (!tag || !src || rows < 256 || K < 256 || !umma_available()) return cudaSuccess;
+    if (nslices <= 0) nslices = ozaki_default_slices();
+    const int64_t kmax = (((1 << (33 - 2 * ozaki_bits())) - 1) / nslices) & ~127LL;
+    if (K > kmax) return cudaSuccess;
+    static int *side_e = nullptr;
+    static int64_t side_e_n = 0;
+    if (rows > side_e_n) {
+        if (side_e) cudaFree(side_e);
+        side_e = nullptr; side_e_n = 0;
+        if (cudaMalloc((void **)&side_e, (size_t)rows * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return cudaSuccess; }
+        side_e_n = rows;
+    }
+    const int64_t Kp = (K + 15) & ~15LL;
+    int8_t *q; double *sc; int launches = 0;
+    return prepare_operand(side, tag, src, ld, rows, K, Kp, kmajor, nslices, nullptr, side_e, nullptr, &q, &sc, &launches);
 }
 
 static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
