@@ -319,6 +319,21 @@ __device__ __forceinline__ void eval_scalar(const int4 *__restrict__ ops, int e_
     const T xa = x[a], xb = x[b];
     const T da0 = a == 0 ? (T)1 : (T)0, da1 = a == 1 ? (T)1 : (T)0, db0 = b == 0 ? (T)1 : (T)0, db1 = b == 1 ? (T)1 : (T)0;
     T f0 = (T)0, f1 = (T)0;
+    // + - * (unary -) ^2 make up most of any scalar tape and the lanes of a bundle hold all of them at once: evaluate the five
+    // together, branch-free, and select (same formulas, same operation order as the cases below), so a bundle of basic
+    // operations does not serialise into one pass per operation kind
+    if (code == E_ADD || code == E_SUB || code == E_MUL || code == E_NEG || (code == E_POWI && imm == 2)) {
+        const T sgn = code == E_SUB ? (T)-1 : (T)1;
+        const T v_as = code == E_SUB ? xa - xb : xa + xb, d_as0 = da0 + sgn * db0, d_as1 = da1 + sgn * db1;
+        const T v_m = xa * xb, d_m0 = da0 * xb + xa * db0, d_m1 = da1 * xb + xa * db1;
+        const T u1 = code == E_NEG ? (T)-1 : (T)2 * xa;                      // f1 of the unary ones
+        const T v_u = code == E_NEG ? -xa : xa * xa, d_u0 = u1 * da0, d_u1 = u1 * da1;
+        const bool as = code == E_ADD || code == E_SUB, mu = code == E_MUL;
+        v = as ? v_as : (mu ? v_m : v_u);
+        d[0] = as ? d_as0 : (mu ? d_m0 : d_u0);
+        d[1] = as ? d_as1 : (mu ? d_m1 : d_u1);
+        return;
+    }
     switch (code) {
         case E_CONST: v = (T)fc[imm]; d[0] = d[1] = (T)0; return;
         case E_ARG: v = x[imm & 1]; d[0] = (imm & 1) == 0 ? (T)1 : (T)0; d[1] = (imm & 1) == 1 ? (T)1 : (T)0; return;
