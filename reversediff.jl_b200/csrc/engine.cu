@@ -396,10 +396,12 @@ static int forward_pass(rdb_tape *t, int order = 1) {
                             MatRef<T> A2, B2;
                             mul_operand_ref<T>(t, J.in[0], A2);
                             mul_operand_ref<T>(t, J.in[1], B2);
+                            int nla = 0, nlb = 0;
                             ozaki_preslice(t->ctx->side_stream, (const double *)A2.ptr, A2.ld, J.in[0].rows, J.in[0].cols, A2.stored_t,
-                                           t->opts.ozaki_slices, operand_tag(t, J.in[0]));
+                                           t->opts.ozaki_slices, operand_tag(t, J.in[0]), &nla);
                             ozaki_preslice(t->ctx->side_stream, (const double *)B2.ptr, B2.ld, J.in[1].cols, J.in[0].cols, !B2.stored_t,
-                                           t->opts.ozaki_slices, operand_tag(t, J.in[1]));
+                                           t->opts.ozaki_slices, operand_tag(t, J.in[1]), &nlb);
+                            t->launches += nla + nlb;
                         }
                         break;
                     }
@@ -682,8 +684,10 @@ static void preslice_delta(rdb_tape *t, InstrPlan &J, int side) {
     const int64_t M = J.in[0].rows, N = J.in[1].cols;
     if (!J.dtag) J.dtag = new_delta_tag();
     const double *d = (const double *)t->bufs[J.rec.out].der;
-    if (side == 0) ozaki_preslice(t->ctx->side_stream, d, M, M, N, false, t->opts.ozaki_slices, J.dtag);
-    else ozaki_preslice(t->ctx->side_stream, d, M, N, M, true, t->opts.ozaki_slices, J.dtag);
+    int nl = 0;
+    if (side == 0) ozaki_preslice(t->ctx->side_stream, d, M, M, N, false, t->opts.ozaki_slices, J.dtag, &nl);
+    else ozaki_preslice(t->ctx->side_stream, d, M, N, M, true, t->opts.ozaki_slices, J.dtag, &nl);
+    t->launches += nl;
 }
 
 // a.deriv += delta * value(b)'   and   b.deriv += value(a)' * delta     (arithmetic.jl:272-285), R seed columns

@@ -33,7 +33,8 @@ cudaError_t gemm_f64_ozaki(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N,
                            uint64_t tag_a = 0, uint64_t tag_b = 0);
 
 // slice an operand ahead of its GEMM on another stream (umma.cu); a no-op when the operand is not eligible
-cudaError_t ozaki_preslice(cudaStream_t side, const double *src, int64_t ld, int64_t rows, int64_t K, bool kmajor, int nslices, uint64_t tag);
+cudaError_t ozaki_preslice(cudaStream_t side, const double *src, int64_t ld, int64_t rows, int64_t K, bool kmajor, int nslices, uint64_t tag,
+                           int *launched = nullptr);
 
 // ---- (a)/(b) elementwise sweeps ---------------------------------------------------------------------
 constexpr int kReduceBlocks = 1184;   // 148 SMs x 8 resident CTAs: partial-sum slots of the two-pass reductions

@@ -1129,7 +1129,9 @@ static cudaError_t prepare_operand(cudaStream_t st, uint64_t tag, const double *
 // tensor-bound and 1 CTA/SM: the two overlap).  The entry lands in the cache under `tag`; the GEMM's own prepare_operand then
 // finds it and makes its stream wait for the entry's event.  kmajor: the operand's k index is the contiguous one
 // (A with ta, B without tb).  Only what gemm_f64_ozaki would run as ONE exact-int32 chunk is sliced ahead.
-cudaError_t ozaki_preslice(cudaStream_t side, const double *src, int64_t ld, int64_t rows, int64_t K, bool kmajor, int nslices, uint64_t tag) {
+cudaError_t ozaki_preslice(cudaStream_t side, const double *src, int64_t ld, int64_t rows, int64_t K, bool kmajor, int nslices, uint64_t tag,
+                           int *launched) {
+    if (launched) *launched = 0;
     if (!tag || !src || rows < 256 || K < 256 || !umma_available()) return cudaSuccess;
     if (nslices <= 0) nslices = ozaki_default_slices();
     const int64_t kmax = (((1 << (33 - 2 * ozaki_bits())) - 1) / nslices) & ~127LL;
@@ -1144,7 +1146,9 @@ cudaError_t ozaki_preslice(cudaStream_t side, const double *src, int64_t ld, int
     }
     const int64_t Kp = (K + 15) & ~15LL;
     int8_t *q; double *sc; int launches = 0;
-    return prepare_operand(side, tag, src, ld, rows, K, Kp, kmajor, nslices, nullptr, side_e, nullptr, &q, &sc, &launches);
+    const cudaError_t e = prepare_operand(side, tag, src, ld, rows, K, Kp, kmajor, nslices, nullptr, side_e, nullptr, &q, &sc, &launches);
+    if (launched) *launched = launches;
+    return e;
 }
 
 static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
