@@ -413,3 +413,21 @@ def test_gpu_forward_mode_hessian_rejects_scalar_tapes(rd):
     ct = rd.compile(tape)
     with pytest.raises(Exception, match="scalar instructions"):
         rd.hessian_(np.zeros((4, 4), order="F"), ct, np.ones(4))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"RDB_SCALAR_BUNDLES": "1", "RDB_SCALAR_MANYSEED": "b"},      # bundle kernels everywhere
+                                 {"RDB_SCALAR_BUNDLES": "0", "RDB_SCALAR_MANYSEED": "s"}])     # level kernels + streaming kernel
+def test_gpu_every_scalar_kernel_variant(env):
+    """The planner picks a kernel per graph shape and seed count (depth > 48 levels -> bundles; 16+ seeds -> streaming kernel or
+    one bundle warp per seed by a cost model), so at default settings a small test graph only ever meets some of them.  The
+    choices are process-wide (read once from the environment): rerun the GPU tests of this file in a child process with each
+    kernel family forced on."""
+    import os, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    e = dict(os.environ); e.update(env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_scalar_tape.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "not every_scalar_kernel_variant", "-p", "no:cacheprovider"],
+                       cwd=os.path.dirname(here), env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
