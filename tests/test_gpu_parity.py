@@ -521,3 +521,18 @@ def test_cfg2_full_size_closed_form(rd):
     assert abs(res[0].value - val) < 1e-12 * abs(val)
     assert relerr(ga, b.sum(1)[:, None] + b.sum(0)[None, :]) < 1e-12
     assert relerr(gb, a.sum(1)[:, None] + a.sum(0)[None, :]) < 1e-12
+
+
+@pytest.mark.parametrize("env", [{"RDB_OZAKI_BITS": "7"},                                   # first-generation digits: 8 slices of 7 bits
+                                 {"RDB_PRESLICE": "0", "RDB_STREAM_INPUTS": "0"},              # no side stream, no panelled uploads
+                                 {"RDB_OZAKI_CLUSTER": "1"}])                                  # single-CTA tcgen05 kernel
+def test_gemm_path_variants_in_child_process(env):
+    """The GEMM-path knobs are read once per process: rerun the cfg 2 and panel-size tests with each alternative forced on."""
+    import subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    e = dict(os.environ); e.update(env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "(cfg2 or panel_sizes) and not child_process", "-p", "no:cacheprovider"],
+                       cwd=os.path.dirname(here), env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
