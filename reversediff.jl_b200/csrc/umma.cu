@@ -1009,7 +1009,9 @@ cudaError_t gemm_f64_ozaki(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t
     const int64_t kmax = (((1 << (33 - 2 * ozaki_bits())) - 1) / nslices) & ~127LL;      // int32 exactness, see ozaki_chunk
     int64_t chunks = (K + kmax - 1) / kmax;
     const int64_t tiles = ((M + 127) / 128) * ((N + 63) / 64);
-    while (tiles < 592 && K / (chunks * 2) >= 8192) chunks *= 2;        // want >= 4 waves of 148 tiles; chunks are serialised
+    (void)tiles;
+    static const int split_more = [] { const char *e = getenv("RDB_OZAKI_SPLITK"); return e ? atoi(e) : 0; }();
+    if (split_more) while (tiles < 592 && K / (chunks * 2) >= 8192) chunks *= 2;   // (experiment: more, shorter chunks; they run one after the other)
     chunks = 1 > chunks ? 1 : chunks;
     const int64_t kc = (((K + chunks - 1) / chunks) + 127) & ~127LL;
     int launches = 0;
