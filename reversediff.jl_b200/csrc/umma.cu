@@ -474,11 +474,14 @@ __global__ void __launch_bounds__(256) k_slice_i8_cm(int8_t *__restrict__ dst, c
     {
         const int rr = tid & 127, kb = tid >> 7;                 // 128 threads along the rows, two columns per pass
         const int r = r0 + rr;
-#pragma unroll 4
-        for (int k = kb; k < 32; k += 2) {
-            const int kk = k0 + k;
-            tile[k & 3][k >> 2][rr] = (r < rows && kk < K) ? src[r + (int64_t)kk * ld] : 0.0;
+        double v[16];                                                // all sixteen column reads in flight before the first store
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int kk = k0 + kb + 2 * i;
+            v[i] = (r < rows && kk < K) ? src[r + (int64_t)kk * ld] : 0.0;
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const int k = kb + 2 * i; tile[k & 3][k >> 2][rr] = v[i]; }
     }
     __syncthreads();
     const int64_t plane = (int64_t)rows * Kp;
