@@ -462,6 +462,58 @@ __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, cons
     }
 }
 
+// k-contiguous source, ONE pass: a warp owns a row, brings it into shared memory with cp.async (16-byte pieces), takes the row
+// maximum there, derives the exponent and cuts the digits from the same copy - the row is read from HBM once instead of twice
+// (k_row_absmax + k_row_exponent + k_slice_i8<true>).  blockDim = 32 x rows per CTA; dynamic shared memory = rows x Kp doubles.
+__global__ void __launch_bounds__(128) k_slice_fused_kmajor(int8_t *__restrict__ dst, const double *__restrict__ src, int64_t ld, int rows, int K,
+                                                            int Kp, int nslices, int bits, double *__restrict__ scale_out) {
+    extern __shared__ __align__(16) double srows[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int r = blockIdx.x * wpc + w;
+    if (r >= rows) return;
+    double *row = srows + (size_t)w * Kp;
+    const double *p = src + (int64_t)r * ld;
+    for (int c = lane; c < K / 2; c += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(row + 2 * c)), "l"(p + 2 * c) : "memory");
+    for (int k = K + lane; k < Kp; k += 32) row[k] = 0.0;                       // (K is even here) zero padding up to Kp
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    double mx = 0.0;
+    for (int k = 2 * lane; k < K; k += 64) {
+        const double2 v = *reinterpret_cast<const double2 *>(row + k);
+        const double a0 = fabs(v.x), a1 = fabs(v.y);
+        // NaN/Inf anywhere in the row poisons the row (fmax would drop a NaN): non-finite elements count as +Inf
+        mx = fmax(mx, a0 <= 1.7976931348623157e308 ? a0 : __longlong_as_double(0x7FF0000000000000LL));
+        mx = fmax(mx, a1 <= 1.7976931348623157e308 ? a1 : __longlong_as_double(0x7FF0000000000000LL));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const bool finite = isfinite(mx);
+    const int e = (mx > 0.0 && finite) ? ilogb(mx) + (bits == 8 ? 3 : 2) : 0;
+    if (lane == 0) scale_out[r] = finite ? scalbn(1.0, e) : __longlong_as_double(0x7FF8000000000000LL);
+    const int64_t plane = (int64_t)rows * Kp;
+    const int radix = 1 << bits, half = radix >> 1;
+    for (int k = 4 * lane; k < Kp; k += 128) {
+        const double2 lo = *reinterpret_cast<const double2 *>(row + k), hi = *reinterpret_cast<const double2 *>(row + k + 2);
+        const double v[4] = {lo.x, lo.y, hi.x, hi.y};
+        long long X[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) X[j] = isfinite(v[j]) ? __double2ll_rn(scalbn(v[j], bits * nslices - e)) : 0LL;
+        for (int sidx = nslices - 1; sidx >= 0; --sidx) {
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int d = (int)(X[j] & (long long)(radix - 1));
+                X[j] >>= bits;
+                if (sidx > 0 && d >= half) { d -= radix; X[j] += 1; }
+                if (sidx == 0) d = (int)((X[j] << bits) | d);
+                packed |= ((uint32_t)(uint8_t)(int8_t)d) << (8 * j);
+            }
+            *reinterpret_cast<uint32_t *>(dst + sidx * plane + (int64_t)r * Kp + k) = packed;
+        }
+    }
+}
+
 // Column-major source (rows strided by ld... i.e. consecutive ROWS are contiguous, k strided): tile of 128 rows x 32 k, so every
 // column read is 1 KB contiguous (the 32-row x 128-k tile of the generic kernel reads 256-byte pieces 32 KB apart: every piece a
 // different DRAM page).  Transposed through shared memory ([k % 4][k / 4][row]); a thread then owns 4 rows x 4 consecutive k and
@@ -1055,10 +1107,26 @@ static size_t cache_cap() {
 }
 
 int ozaki_bits();
-static void slice_operand(cudaStream_t st, const double *src, int64_t ld, int64_t rows, int64_t K, int64_t Kp, bool kmajor, int ns,
-                          int8_t *q, int *e, double *sc) {
+static int slice_operand(cudaStream_t st, const double *src, int64_t ld, int64_t rows, int64_t K, int64_t Kp, bool kmajor, int ns,
+                         int8_t *q, int *e, double *sc) {      // returns the number of kernels launched
     const int bits = ozaki_bits();
     using namespace umma;
+    // k-contiguous rows that fit shared memory and are 16-byte aligned: the one-pass kernel
+    static const bool fused_on = [] { const char *e = getenv("RDB_SLICE_FUSED"); return !(e && e[0] == '0'); }();
+    // (measured: a win while four rows fit 64 KB so several CTAs share an SM - the MLP config's K = 1024 operands, 12.04 -> 11.85 ms;
+    // at K = 4096, one 128 KB CTA per SM, it loses to the two-pass kernels)
+    if (kmajor && fused_on && K % 2 == 0 && ld % 2 == 0 && (((uintptr_t)src) & 15) == 0 && Kp <= 2048) {
+        int wpc = 4;
+        const size_t smem = (size_t)wpc * Kp * 8;
+        static size_t attr_smem = 0;
+        if (smem > attr_smem) {
+            if (cudaFuncSetAttribute(k_slice_fused_kmajor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) == cudaSuccess) attr_smem = 200 * 1024;
+        }
+        if (smem <= attr_smem || smem <= 48 * 1024) {
+            k_slice_fused_kmajor<<<(unsigned)((rows + wpc - 1) / wpc), 32 * wpc, smem, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, sc);
+            return 1;
+        }
+    }
     unsigned long long *mx = (unsigned long long *)sc;                  // scale array doubles as max scratch
     if (kmajor) k_row_absmax<true><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(src, ld, (int)rows, (int)K, mx);
     else {
@@ -1073,14 +1141,15 @@ static void slice_operand(cudaStream_t st, const double *src, int64_t ld, int64_
         if (gc.y <= 65535) k_slice_i8_cm<<<gc, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e);
         else k_slice_i8<false><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e);
     }
+    return 3;
 }
 
 // returns the slices/scales of one operand; launches = kernels issued (0 on a cache hit)
 static cudaError_t prepare_operand(cudaStream_t st, uint64_t tag, const double *src, int64_t ld, int64_t rows, int64_t K, int64_t Kp,
                                    bool kmajor, int ns, int8_t *ws_q, int *ws_e, double *ws_sc, int8_t **q, double **sc, int *launches) {
     if (!tag) {
-        slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc);
-        *q = ws_q; *sc = ws_sc; *launches = 3;
+        *launches = slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc);
+        *q = ws_q; *sc = ws_sc;
         return cudaSuccess;
     }
     SliceEntry *slot = nullptr;
@@ -1104,15 +1173,15 @@ static cudaError_t prepare_operand(cudaStream_t st, uint64_t tag, const double *
         }
         if (bytes > cache_cap()) {                                                  // too big to cache
             if (!ws_q) { *q = nullptr; *sc = nullptr; *launches = 0; return cudaSuccess; }     // slicing ahead: nothing to do
-            slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc);
-            *q = ws_q; *sc = ws_sc; *launches = 3;
+            *launches = slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc);
+            *q = ws_q; *sc = ws_sc;
             return cudaSuccess;
         }
         SliceEntry en{};
         if (cudaMalloc((void **)&en.q, bytes) != cudaSuccess) {
             cudaGetLastError();
             if (!ws_q) { *q = nullptr; *sc = nullptr; *launches = 0; return cudaSuccess; }
-            slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc); *q = ws_q; *sc = ws_sc; *launches = 3; return cudaSuccess;
+            *launches = slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc); *q = ws_q; *sc = ws_sc; return cudaSuccess;
         }
         cudaEventCreateWithFlags(&en.ready, cudaEventDisableTiming);
         en.sc = (double *)(en.q + (((size_t)ns * rows * Kp + 255) & ~(size_t)255));
@@ -1121,12 +1190,12 @@ static cudaError_t prepare_operand(cudaStream_t st, uint64_t tag, const double *
         g_cache.push_back(en);
         slot = &g_cache.back();
     }
-    slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, slot->q, ws_e, slot->sc);    // (re)fill in place: same buffers, new version
+    const int nl_fill = slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, slot->q, ws_e, slot->sc);    // (re)fill in place: same buffers, new version
     if (slot->ready) cudaEventRecord(slot->ready, st);
     slot->filled_on = st;
     slot->tag = tag;
     slot->last_use = ++g_use;
-    *q = slot->q; *sc = slot->sc; *launches = 3;
+    *q = slot->q; *sc = slot->sc; *launches = nl_fill;
     return cudaSuccess;
 }
 
