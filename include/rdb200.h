@@ -123,6 +123,12 @@ int rdb_gemm(rdb_ctx *, int dtype, int trans_a, int trans_b, int64_t m, int64_t 
  * reductions.jl:23-27); sum_out is a device scalar. */
 int rdb_add_sum(rdb_ctx *, int dtype, int64_t n, const void *a, const void *b, double sign, void *out, void *sum_out);
 
+/* ---- host-only planning helper (no device needed; unit-tested on the CPU) --------------------------- */
+/* Column panels used for large host arrays (panelled uploads in rdb_tape_set_input, panelled last accumulations with early D2H
+ * copies in rdb_gradient): widths[0..3] = columns per panel (0 = unused), chosen so each panel's 128x64 GEMM tiles fill whole
+ * waves of the 148 SMs.  Returns the number of panels. */
+int rdb_plan_col_panels(int64_t rows, int64_t cols, int64_t widths[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2006,4 +2006,12 @@ int rdb_add_sum(rdb_ctx *c, int dtype, int64_t n, const void *a, const void *b, 
     return RDB_OK;
 }
 
+int rdb_plan_col_panels(int64_t rows, int64_t cols, int64_t widths[4]) {
+    if (!widths || rows <= 0 || cols <= 0) return 0;
+    plan_col_panels(rows, cols, widths);
+    int n = 0;
+    for (int i = 0; i < 4; ++i) n += widths[i] > 0;
+    return n;
+}
+
 }  // extern "C"

@@ -37,3 +37,24 @@ def test_oracle_is_not_imported_by_the_product(rd):
             if f.endswith((".py", ".cu", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_col_panel_planner(rd):
+    """Host-only planner behind the panelled uploads / panelled last accumulations (engine.cu plan_col_panels): the panels tile
+    the columns exactly, every panel but the last is a whole number of 64-column tiles, and the 128x64-tile waves they cost on
+    148 SMs stay within one wave of the unsplit GEMM (four equal panels of a 4096^2 result would cost 16 against 13.8)."""
+    import ctypes as C
+    lib = rd.engine.lib()
+    for rows, cols in [(4096, 4096), (2048, 2048), (8192, 8192), (4096, 2048), (1024, 65536), (3000, 5000), (2048, 16384)]:        # sizes that reach the panel routes (>= 32 MB, >= 2048 columns)
+        w = (C.c_int64 * 4)()
+        n = lib.rdb_plan_col_panels(rows, cols, w)
+        widths = [int(x) for x in w if x > 0]
+        assert n == len(widths) and 1 <= n <= 4
+        assert sum(widths) == cols
+        assert all(x % 64 == 0 for x in widths[:-1])
+        rt = -(-rows // 128)
+        waves = sum(-(-(rt * -(-x // 64)) // 148) for x in widths)
+        ideal = rt * -(-cols // 64) / 148.0
+        assert waves <= -(-ideal // 1) + 1 or waves <= ideal * 1.12, (rows, cols, widths, waves, ideal)      # within one wave of the unsplit GEMM
+    w = (C.c_int64 * 4)()
+    assert lib.rdb_plan_col_panels(4096, 4096, w) == 3 and list(w)[:3] == [1472, 1472, 1152]
