@@ -599,18 +599,26 @@ static int mul_acc_cols(rdb_tape *t, InstrPlan &I, int side, int64_t c0, int64_t
     mul_operand_ref<T>(t, oa, A);
     mul_operand_ref<T>(t, ob, B);
     const T *delta = (const T *)t->bufs[I.rec.out].der;
+    // A panel reads row windows of operands the full GEMM would read whole: name the whole operand (tag + window) so the int8
+    // path slices it once for all panels - and finds it in the cache when the forward sweep or the slicing ahead left it there.
+    auto window = [](OperandWindow &w, const void *full, int64_t rows_full, int64_t row0, int64_t rows) {
+        w = OperandWindow();
+        if (rows != rows_full) { w.full = full; w.rows_full = rows_full; w.row0 = row0; }
+    };
     if (side == 0) {
         T *dst = (T *)t->bufs[oa.rec.buffer].der;
         if (oa.mode == OPM_PLAIN) {
             // a.deriv(MxK)[:, c0:] = delta(MxN) * Bmat'(N x k-panel)
             const T *bp = B.stored_t ? B.ptr + c0 * B.ld : B.ptr + c0;
             g_tag_a = dtag;
-            if (c0 == 0 && nc == K) g_tag_b = operand_tag(t, ob);
+            g_tag_b = operand_tag(t, ob);
+            window(g_win_b, B.ptr, K, c0, nc);
             KL(t, gemm_t<T>(S(t), false, !B.stored_t, M, nc, N, (T)1, delta, M, bp, B.ld, beta, dst + c0 * M, M));
         } else {
             // origin.deriv(KxM)[:, c0:] = Bmat(KxN) * delta'(N x m-panel)
             g_tag_a = operand_tag(t, ob);
-            if (c0 == 0 && nc == M) g_tag_b = dtag;
+            g_tag_b = dtag;
+            window(g_win_b, delta, M, c0, nc);
             KL(t, gemm_t<T>(S(t), B.stored_t, true, K, nc, N, (T)1, B.ptr, B.ld, delta + c0, M, beta, dst + c0 * K, K));
         }
     } else {
@@ -618,13 +626,15 @@ static int mul_acc_cols(rdb_tape *t, InstrPlan &I, int side, int64_t c0, int64_t
         if (ob.mode == OPM_PLAIN) {
             // b.deriv(KxN)[:, c0:] = Amat'(KxM) * delta(M x n-panel)
             g_tag_a = operand_tag(t, oa);
-            if (c0 == 0 && nc == N) g_tag_b = dtag;
+            g_tag_b = dtag;
+            window(g_win_b, delta, N, c0, nc);
             KL(t, gemm_t<T>(S(t), !A.stored_t, false, K, nc, M, (T)1, A.ptr, A.ld, delta + c0 * M, M, beta, dst + c0 * K, K));
         } else {
             // origin.deriv(NxK)[:, c0:] = delta'(NxM) * Amat(M x k-panel)
             const T *ap = A.stored_t ? A.ptr + c0 : A.ptr + c0 * A.ld;
             g_tag_a = dtag;
-            if (c0 == 0 && nc == K) g_tag_b = operand_tag(t, oa);
+            g_tag_b = operand_tag(t, oa);
+            window(g_win_b, A.ptr, K, c0, nc);
             KL(t, gemm_t<T>(S(t), true, A.stored_t, N, nc, M, (T)1, delta, M, ap, A.ld, beta, dst + c0 * N, N));
         }
     }
@@ -708,7 +718,7 @@ static int mul_reverse(rdb_tape *t, int k, int64_t R) {
     auto &E = t->early;
     if (!I.dtag) I.dtag = new_delta_tag();
     const uint64_t dtag = I.dtag;
-    if (R == 1 && preslice_on(t) && !E.enabled && M >= 256 && N >= 256 && K >= 256) {      // (panelled GEMMs read delta PANELS: nothing to share)
+    if (R == 1 && preslice_on(t) && M >= 256 && N >= 256 && K >= 256) {
         // while this instruction's first adjoint GEMM runs: slice deriv(output) the way its second one reads it, and both views
         // of the next `*` instruction's deriv(output) if that adjoint is already final
         OK(preslice_begin(t));

@@ -482,7 +482,9 @@ cudaError_t gemm_f64(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, in
                      int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int mode, int slices) {
     g_gemm_launches = 0;
     const uint64_t tag_a = g_tag_a, tag_b = g_tag_b;      // operand identity hints are valid for exactly one call
+    const OperandWindow win_a = g_win_a, win_b = g_win_b;
     g_tag_a = g_tag_b = 0;
+    g_win_a = g_win_b = OperandWindow();
     if (M <= 0 || N <= 0) return cudaSuccess;
     if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return cudaErrorInvalidValue;
     g_gemm_launches = 1;
@@ -495,7 +497,7 @@ cudaError_t gemm_f64(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, in
     if (env_mode) mode = env_mode;
     if (mode != 1) {
         cudaError_t e = gemm_f64_ozaki(st, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, slices > 0 ? slices : ozaki_default_slices(),
-                                       tag_a, tag_b);
+                                       tag_a, tag_b, win_a, win_b);
         if (e != cudaErrorNotSupported) return e;
     }
     if (!ta && !tb) return d64::launch<false, false>(st, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
@@ -645,6 +647,7 @@ cudaError_t gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, in
                      int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc) {
     g_gemm_launches = 0;
     g_tag_a = g_tag_b = 0;
+    g_win_a = g_win_b = OperandWindow();
     if (M <= 0 || N <= 0) return cudaSuccess;
     if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX) return cudaErrorInvalidValue;
     g_gemm_launches = 1;

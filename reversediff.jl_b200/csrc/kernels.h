@@ -25,12 +25,17 @@ cudaError_t gemm_f32_umma(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N, 
 // (tag, pointer, shape)"; the engine derives it from (tape uid, buffer id, value version).  0 = do not cache (adjoints).
 // Consumed (reset to 0) by the next gemm_f64 call on this thread.
 extern thread_local uint64_t g_tag_a, g_tag_b;
+// "The operand handed to the next gemm_f64 is rows [row0, row0 + rows) of a larger operand that starts at `full` (same leading
+// dimension, same contraction length), and the tag names that larger operand": the int8 path then slices the whole operand once
+// and serves every panel of a panelled GEMM from it.  rows = the m (A) or n (B) index.  Consumed like the tags.
+struct OperandWindow { const void *full = nullptr; int64_t rows_full = 0, row0 = 0; };
+extern thread_local OperandWindow g_win_a, g_win_b;
 
 // FP64 through exact int8 slices on the tcgen05 INT8 pipe (Ozaki scheme); cudaErrorNotSupported when not applicable
 int ozaki_default_slices();
 cudaError_t gemm_f64_ozaki(cudaStream_t, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
                            int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices,
-                           uint64_t tag_a = 0, uint64_t tag_b = 0);
+                           uint64_t tag_a = 0, uint64_t tag_b = 0, OperandWindow wa = OperandWindow(), OperandWindow wb = OperandWindow());
 
 // slice an operand ahead of its GEMM on another stream (umma.cu); a no-op when the operand is not eligible
 cudaError_t ozaki_preslice(cudaStream_t side, const double *src, int64_t ld, int64_t rows, int64_t K, bool kmajor, int nslices, uint64_t tag,

@@ -22,6 +22,7 @@
 
 namespace rdb {
 thread_local uint64_t g_tag_a = 0, g_tag_b = 0;
+thread_local OperandWindow g_win_a, g_win_b;
 namespace umma {
 
 constexpr int BM = 128, BN = 256, BKB = 128;          // tile rows / cols / K-bytes per stage (= one 128B swizzle atom)
@@ -267,11 +268,12 @@ static EncodeTiledFn encode_fn() {
 }
 // [slices][rows][Kp] K-major operand, element size es; box = (BKB/es, box_rows, 1), 128B swizzle
 static bool make_map(CUtensorMap *map, CUtensorMapDataType dt, int es, void *base, int64_t Kp, int64_t rows, int slices, int box_rows,
-                     int box_k_bytes = BKB, int box_slices = 1) {
+                     int box_k_bytes = BKB, int box_slices = 1, int64_t rows_stride = 0) {      // rows_stride: rows between slices (a window into a larger operand)
+    if (rows_stride <= 0) rows_stride = rows;
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)slices};
-    cuuint64_t strides[2] = {(cuuint64_t)Kp * es, (cuuint64_t)Kp * es * rows};
+    cuuint64_t strides[2] = {(cuuint64_t)Kp * es, (cuuint64_t)Kp * es * rows_stride};
     cuuint32_t box[3] = {(cuuint32_t)(box_k_bytes / es), (cuuint32_t)box_rows, (cuuint32_t)box_slices};
     cuuint32_t estr[3] = {1, 1, 1};
     return fn(map, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1051,7 +1053,7 @@ int ozaki_default_slices() {
 // One K-chunk of the sliced product (K*nslices < 2^19 keeps every int32 accumulation chain exact).
 static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
                                int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices,
-                               uint64_t tag_a, uint64_t tag_b);
+                               uint64_t tag_a, uint64_t tag_b, OperandWindow wa, OperandWindow wb);
 static thread_local int g_chunk_launches = 0;
 
 // C(MxN) <- alpha*op(A)*op(B) + beta*C in FP64 through exact int8 slices on tcgen05 (see the comment block above).
@@ -1059,7 +1061,7 @@ static thread_local int g_chunk_launches = 0;
 // keeps int32 exact and gives small-MxN / huge-K adjoints (dW = dZ * X', K = 65536 in the MLP config) enough tiles per wave.
 cudaError_t gemm_f64_ozaki(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
                            int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices,
-                           uint64_t tag_a, uint64_t tag_b) {
+                           uint64_t tag_a, uint64_t tag_b, OperandWindow wa, OperandWindow wb) {
     if (M < 256 || N < 256 || K < 256 || !umma_available()) return cudaErrorNotSupported;
     const int64_t kmax = (((1 << (33 - 2 * ozaki_bits())) - 1) / nslices) & ~127LL;      // int32 exactness, see ozaki_chunk
     int64_t chunks = (K + kmax - 1) / kmax;
@@ -1074,7 +1076,11 @@ cudaError_t gemm_f64_ozaki(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t
         const int64_t kk = K - k0 < kc ? K - k0 : kc;
         const double *Ac = ta ? A + k0 : A + k0 * lda;                   // op(A)(:, k0:) : stored KxM (ta) or MxK
         const double *Bc = tb ? B + k0 * ldb : B + k0;                   // op(B)(k0:, :) : stored NxK (tb) or KxN
-        cudaError_t e = ozaki_chunk(st, ta, tb, M, N, kk, alpha, Ac, lda, Bc, ldb, c == 0 ? beta : 1.0, C, ldc, nslices, tag_a, tag_b);
+        // (windows are honoured for single-chunk products only; with several K-chunks a windowed operand is sliced per panel,
+        //  untagged, because its tag names the whole operand)
+        const bool one = chunks == 1;
+        cudaError_t e = ozaki_chunk(st, ta, tb, M, N, kk, alpha, Ac, lda, Bc, ldb, c == 0 ? beta : 1.0, C, ldc, nslices,
+                                    (!one && wa.full) ? 0 : tag_a, (!one && wb.full) ? 0 : tag_b, one ? wa : OperandWindow(), one ? wb : OperandWindow());
         if (e != cudaSuccess) return e;
         launches += g_chunk_launches;      // per uncached operand: absmax, exponent, slice; + 1 tcgen05 kernel
     }
@@ -1227,14 +1233,18 @@ cudaError_t ozaki_preslice(cudaStream_t side, const double *src, int64_t ld, int
 
 static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
                                int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int nslices,
-                               uint64_t tag_a, uint64_t tag_b) {
+                               uint64_t tag_a, uint64_t tag_b, OperandWindow wa, OperandWindow wb) {
     using namespace umma;
     // int32 exactness: (d+1)*K*2^(2(bits-1)) < 2^31 for d <= nslices-1
     if (K * (int64_t)nslices > (1 << (33 - 2 * ozaki_bits())) - 1) return cudaErrorInvalidValue;
     const int64_t Kp = (K + 15) & ~15LL;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t a_bytes = tag_a ? 0 : al((size_t)nslices * M * Kp), b_bytes = tag_b ? 0 : al((size_t)nslices * N * Kp);
-    const size_t ea_bytes = al(M * 4), eb_bytes = al(N * 4), sa_bytes = al(M * 8), sb_bytes = al(N * 8);
+    if (!tag_a) wa = OperandWindow();
+    if (!tag_b) wb = OperandWindow();
+    // an operand that is a row window of a larger, tagged operand: slice (or find) the WHOLE operand in the cache and point the
+    // tensor map at the window - the panels of a panelled GEMM share one slicing
+    const size_t a_bytes = (tag_a && !wa.full) ? 0 : al((size_t)nslices * M * Kp), b_bytes = (tag_b && !wb.full) ? 0 : al((size_t)nslices * N * Kp);
+    const size_t ea_bytes = al(std::max<int64_t>(M, wa.rows_full) * 4), eb_bytes = al(std::max<int64_t>(N, wb.rows_full) * 4), sa_bytes = al(M * 8), sb_bytes = al(N * 8);
     uint8_t *ws = (uint8_t *)workspace(a_bytes + b_bytes + ea_bytes + eb_bytes + sa_bytes + sb_bytes);
     if (!ws) return cudaErrorMemoryAllocation;
     int8_t *ws_a = (int8_t *)ws, *ws_b = (int8_t *)(ws + a_bytes);
@@ -1245,10 +1255,27 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     int8_t *As, *Bs;
     double *sa, *sb;
     int la = 0, lb = 0;
-    cudaError_t pe = prepare_operand(st, tag_a, A, lda, M, K, Kp, ta, nslices, ws_a, ea, ws_sa, &As, &sa, &la);
-    if (pe != cudaSuccess) return pe;
-    pe = prepare_operand(st, tag_b, B, ldb, N, K, Kp, !tb, nslices, ws_b, eb, ws_sb, &Bs, &sb, &lb);
-    if (pe != cudaSuccess) return pe;
+    int64_t a_stride = 0, b_stride = 0;                 // rows between slice planes when the operand is a window
+    cudaError_t pe = cudaSuccess;
+    As = nullptr; Bs = nullptr;
+    if (wa.full) {
+        pe = prepare_operand(st, tag_a, (const double *)wa.full, lda, wa.rows_full, K, Kp, ta, nslices, nullptr, ea, nullptr, &As, &sa, &la);
+        if (pe != cudaSuccess) return pe;
+        if (As) { As += wa.row0 * Kp; sa += wa.row0; a_stride = wa.rows_full; }
+    }
+    if (!As) {                                         // no window, or the whole operand could not be cached: this panel on its own
+        pe = prepare_operand(st, wa.full ? 0 : tag_a, A, lda, M, K, Kp, ta, nslices, ws_a, ea, ws_sa, &As, &sa, &la);
+        if (pe != cudaSuccess) return pe;
+    }
+    if (wb.full) {
+        pe = prepare_operand(st, tag_b, (const double *)wb.full, ldb, wb.rows_full, K, Kp, !tb, nslices, nullptr, eb, nullptr, &Bs, &sb, &lb);
+        if (pe != cudaSuccess) return pe;
+        if (Bs) { Bs += wb.row0 * Kp; sb += wb.row0; b_stride = wb.rows_full; }
+    }
+    if (!Bs) {
+        pe = prepare_operand(st, wb.full ? 0 : tag_b, B, ldb, N, K, Kp, !tb, nslices, ws_b, eb, ws_sb, &Bs, &sb, &lb);
+        if (pe != cudaSuccess) return pe;
+    }
     g_chunk_launches = la + lb + 1;
     CUtensorMap mA, mB;
     static int group_m = -1;
@@ -1260,8 +1287,8 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
         using namespace oz2;
         static int kbytes = -1;
         if (kbytes < 0) { const char *e = getenv("RDB_OZAKI_KB"); kbytes = (e && atoi(e) == 32) ? 32 : 64; }
-        if (!make_map(&mA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, kbytes, nslices) ||
-            !make_map(&mB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2, kbytes, nslices))
+        if (!make_map(&mA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, kbytes, nslices, a_stride) ||
+            !make_map(&mB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2, kbytes, nslices, b_stride))
             return cudaErrorInvalidValue;
         dim3 grid2((unsigned)((M + BM2 - 1) / BM2), (unsigned)((N + BN2 - 1) / BN2));
         static int cl = -1;
@@ -1269,7 +1296,7 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
         if ((nslices == 8 || nslices == 7) && kbytes == 64 && cl > 1 && grid2.y % cl == 0) {
             // cluster of `cl` CTAs along n sharing the A stage through TMA multicast
             CUtensorMap mAmc;
-            if (!make_map(&mAmc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, kbytes, (nslices + cl - 1) / cl)) return cudaErrorInvalidValue;
+            if (!make_map(&mAmc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, kbytes, (nslices + cl - 1) / cl, a_stride)) return cudaErrorInvalidValue;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = grid2; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes_cluster(nslices, cl); cfg.stream = st;
             cudaLaunchAttribute at[1];
@@ -1309,8 +1336,8 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
 #undef RDB_OZ2
         return cudaGetLastError();
     }
-    if (!make_map(&mA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM) ||
-        !make_map(&mB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN))
+    if (!make_map(&mA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM, BKB, 1, a_stride) ||
+        !make_map(&mB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN, BKB, 1, b_stride))
         return cudaErrorInvalidValue;
     static bool attr = false;
     if (!attr) {
