@@ -484,6 +484,25 @@ def test_host_arrays_at_panel_sizes(rd, orc, name):
         assert relerr(r, g) < 1e-12
 
 
+def test_host_arrays_panels_with_k_chunks(rd, orc):
+    """Panelled adjoint GEMMs whose contraction is longer than one exact-int32 K-chunk (K = 20032 > 18688): the operand windows
+    are dropped for the chunked product (its tag names the whole operand) and every chunk slices its own panel."""
+    import torch
+    m, k, n = 20032, 2048, 2048
+    rng = np.random.default_rng(7)
+    rec = (rng.random((m, k)), rng.random((k, n)))
+    ins = (np.asfortranarray(rng.random((m, k)) / k), np.asfortranarray(rng.random((k, n))))
+    f = lambda a, b: rd.sum(a @ b)
+    ct = run_gradient(rd, orc, f, rec, ins, check_buffers=False)
+    dev_in = tuple(torch.from_numpy(np.ascontiguousarray(x.T)).cuda() for x in ins)
+    dev_out = tuple(torch.empty(x.size, dtype=torch.float64, device="cuda") for x in ins)
+    rd.gradient_(dev_out, ct, dev_in)
+    host_out = tuple(np.zeros(x.shape, order="F") for x in ins)
+    rd.gradient_(host_out, ct, ins)
+    for h, d in zip(host_out, dev_out):
+        assert relerr(h, d.cpu().numpy().reshape(h.shape, order="F")) < 1e-13
+
+
 def test_host_arrays_at_panel_sizes_f32(rd, orc):
     """FP32 takes the same host-array routes (3xTF32 tcgen05 GEMMs cut into column panels, panelled uploads) from 32 MiB on."""
     import torch
