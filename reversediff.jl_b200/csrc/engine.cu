@@ -371,6 +371,29 @@ static int forward_pass(rdb_tape *t, int order = 1) {
                 StepTimer tm(t, "gemm_forward", (double)(M * K + K * N + M * N) * t->es, 2.0 * M * N * K);
                 if (streamed >= 0 && (int)i == streamed_at) {
                     Buf &bi = t->bufs[streamed];
+                    if (preslice_on(t) && M >= 256 && N >= 256 && K >= 256) {
+                        // while the panels arrive: slice what the next `*` reads of the inputs that are already complete
+                        for (size_t j = i + 1; j < n; ++j) {
+                            InstrPlan &J = t->instrs[j];
+                            if (J.blk || J.rec.opcode != OP_MUL) continue;
+                            if (J.in[0].rows >= 256 && J.in[1].cols >= 256 && J.in[0].cols >= 256) {
+                                OK(preslice_begin(t));
+                                for (int b = 0; b < 2; ++b) {
+                                    OperandPlan &o = J.in[b];
+                                    bool ready = o.mode != OPM_GATHER && droot(t, o.rec.buffer) != droot(t, streamed);
+                                    for (size_t x = i; x < j && ready; ++x) if (droot(t, t->instrs[x].rec.out) == droot(t, o.rec.buffer)) ready = false;
+                                    if (!ready) continue;
+                                    MatRef<T> R2;
+                                    mul_operand_ref<T>(t, o, R2);
+                                    int nl2 = 0;
+                                    if (b == 0) ozaki_preslice(t->ctx->side_stream, (const double *)R2.ptr, R2.ld, o.rows, o.cols, R2.stored_t, t->opts.ozaki_slices, operand_tag(t, o), &nl2);
+                                    else ozaki_preslice(t->ctx->side_stream, (const double *)R2.ptr, R2.ld, o.cols, J.in[0].cols, !R2.stored_t, t->opts.ozaki_slices, operand_tag(t, o), &nl2);
+                                    t->launches += nl2;
+                                }
+                            }
+                            break;
+                        }
+                    }
                     for (int p = 0; p < bi.up_n; ++p) {
                         const int64_t c0 = bi.up_c0[p], nc = bi.up_c0[p + 1] - c0;
                         CU(cudaStreamWaitEvent(S(t), bi.up_ev[p], 0));
@@ -378,6 +401,14 @@ static int forward_pass(rdb_tape *t, int order = 1) {
                         KL(t, gemm_t<T>(S(t), A.stored_t, false, M, nc, K, (T)1, A.ptr, A.ld, B.ptr + c0 * B.ld, B.ld, (T)0, (T *)out.val + c0 * M, M));
                     }
                     bi.up_n = 0;
+                    if (preslice_on(t) && M >= 256 && N >= 256 && K >= 256) {
+                        // the panels were sliced one by one: slice the whole operand once more, off the critical path, so the
+                        // reverse sweep finds it in the cache like after an unstreamed forward GEMM
+                        OK(preslice_begin(t));
+                        int nl2 = 0;
+                        ozaki_preslice(t->ctx->side_stream, (const double *)B.ptr, B.ld, N, K, true, t->opts.ozaki_slices, operand_tag(t, I.in[1]), &nl2);
+                        t->launches += nl2;
+                    }
                     break;
                 }
                 if (order == 1 && preslice_on(t) && M >= 256 && N >= 256 && K >= 256) {
