@@ -393,6 +393,28 @@ __global__ void __launch_bounds__(256) k_row_exponent(const unsigned long long *
     scale_out[r] = finite ? scalbn(1.0, e) : __longlong_as_double(0x7FF8000000000000LL);
 }
 
+// Balanced base-256 digits of four fixed-point values at once (bits == 8).  Adding 0x80 at every digit position below the
+// leading one turns "d >= 128 ? d - 256, carry" into plain byte extraction: byte p of Y = X + 0x80..80 is digit_p + 128, i.e. the
+// digit's int8 bit pattern is that byte with its top bit flipped; the leading digit is the (signed) rest.  Bit-identical to the
+// digit loop.  Stores plane s (s = 0 leading) of the four consecutive k of one row as one packed 32-bit word.
+__device__ __forceinline__ void store_digits8(int8_t *__restrict__ dst_row_k, int64_t plane, int nslices, const long long X[4]) {
+    const unsigned long long bias = nslices > 1 ? (0x8080808080808080ULL >> (8 * (9 - nslices))) : 0ULL;
+    unsigned lo[4], hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned long long y = (unsigned long long)X[j] + bias;
+        lo[j] = (unsigned)y; hi[j] = (unsigned)(y >> 32);
+    }
+    for (int p = 0; p < nslices; ++p) {                          // byte position p <-> slice index nslices - 1 - p
+        const unsigned *w = p < 4 ? lo : hi;
+        const unsigned q = (unsigned)(p & 3), sel = q | ((4u + q) << 4);
+        const unsigned h01 = __byte_perm(w[0], w[1], sel), h23 = __byte_perm(w[2], w[3], sel);
+        unsigned packed = __byte_perm(h01, h23, 0x5410);
+        if (p != nslices - 1) packed ^= 0x80808080u;
+        *reinterpret_cast<uint32_t *>(dst_row_k + (int64_t)(nslices - 1 - p) * plane) = packed;
+    }
+}
+
 // ---- pass 2: slices.  dst is [s][rows][Kp] int8, k contiguous.  Block = 32 rows x 128 k; thread = 1 row x 4 consecutive k per
 // iteration, so every slice store is one packed 32-bit word and a warp writes 128 contiguous bytes of one row.
 template <bool KMAJOR>
@@ -449,6 +471,7 @@ __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, cons
     for (int i = 0; i < 4; ++i) {
         if (!ok[i]) continue;
         const int r = r0 + w + 8 * i;
+        if (bits == 8) { store_digits8(dst + (int64_t)r * Kp + k, plane, nslices, X[i]); continue; }
         for (int sidx = nslices - 1; sidx >= 0; --sidx) {
             uint32_t packed = 0;
 #pragma unroll
@@ -501,6 +524,7 @@ __global__ void __launch_bounds__(128) k_slice_fused_kmajor(int8_t *__restrict__
         long long X[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) X[j] = isfinite(v[j]) ? __double2ll_rn(scalbn(v[j], bits * nslices - e)) : 0LL;
+        if (bits == 8) { store_digits8(dst + (int64_t)r * Kp + k, plane, nslices, X); continue; }
         for (int sidx = nslices - 1; sidx >= 0; --sidx) {
             uint32_t packed = 0;
 #pragma unroll
@@ -558,6 +582,7 @@ __global__ void __launch_bounds__(256) k_slice_i8_cm(int8_t *__restrict__ dst, c
     for (int i = 0; i < 4; ++i) {
         if (!ok[i]) continue;
         const int r = r0 + w * 4 + (lane >> 3) + 32 * i;
+        if (bits == 8) { store_digits8(dst + (int64_t)r * Kp + k, plane, nslices, X[i]); continue; }
         for (int sidx = nslices - 1; sidx >= 0; --sidx) {
             uint32_t packed = 0;
 #pragma unroll
