@@ -128,6 +128,10 @@ int rdb_add_sum(rdb_ctx *, int dtype, int64_t n, const void *a, const void *b, d
  * copies in rdb_gradient): widths[0..3] = columns per panel (0 = unused), chosen so each panel's 128x64 GEMM tiles fill whole
  * waves of the 148 SMs.  Returns the number of panels. */
 int rdb_plan_col_panels(int64_t rows, int64_t cols, int64_t widths[4]);
+/* The list scheduler behind the scalar-block bundle kernels (reversediff.jl_b200/csrc/scalar.cu): a DAG given as CSR successor
+ * lists is packed into bundles of <= 32 mutually independent nodes, every node in a later bundle than all its predecessors, longest
+ * path to a sink first.  Fills bundle[v] and lane[v]; returns the number of bundles, -1 for a cyclic or malformed graph. */
+int64_t rdb_schedule_bundles(int64_t n_nodes, const int64_t *succ_off, const int32_t *succ, int32_t *bundle, int32_t *lane);
 
 #ifdef __cplusplus
 }

@@ -2047,6 +2047,10 @@ int rdb_add_sum(rdb_ctx *c, int dtype, int64_t n, const void *a, const void *b, 
     return RDB_OK;
 }
 
+int64_t rdb_schedule_bundles(int64_t n_nodes, const int64_t *succ_off, const int32_t *succ, int32_t *bundle, int32_t *lane) {
+    return scalar_schedule_bundles_host(n_nodes, succ_off, succ, bundle, lane);
+}
+
 int rdb_plan_col_panels(int64_t rows, int64_t cols, int64_t widths[4]) {
     if (!widths || rows <= 0 || cols <= 0) return 0;
     plan_col_panels(rows, cols, widths);

@@ -187,7 +187,8 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *payload, int64_t l
 void scalar_block_free(ScalarBlock &B);
 cudaError_t scalar_block_upload_ext(ScalarBlock &B, cudaStream_t s);
 cudaError_t scalar_block_ensure_R(ScalarBlock &B, int64_t R, size_t es);
-bool scalar_reverse_streams(const ScalarBlock &B, int64_t R, size_t es);   // R >= 16 seeds: streaming kernel (true) or one bundle warp per seed
+bool scalar_reverse_streams(const ScalarBlock &B, int64_t R, size_t es);
+int64_t scalar_schedule_bundles_host(int64_t n_nodes, const int64_t *succ_off, const int32_t *succ, int32_t *bundle, int32_t *lane);   // R >= 16 seeds: streaming kernel (true) or one bundle warp per seed
 // forward: pull leaf values, evaluate level by level, mirror exports; returns the number of kernel launches in *launches
 template <typename T> cudaError_t scalar_block_forward(cudaStream_t, ScalarBlock &B, const double *fconst, int *launches);
 // reverse for R seeds (deriv layout of tape buffers: [elem + r*size])

@@ -1105,6 +1105,32 @@ cudaError_t scalar_block_reverse(cudaStream_t s, ScalarBlock &B, int64_t R, bool
     return cudaGetLastError();
 }
 
+// host-only entry for unit tests of the bundle scheduler (no device needed): a DAG as CSR successor lists; returns the number of
+// bundles (or -1 on a cycle) and fills bundle[v], lane[v]
+int64_t scalar_schedule_bundles_host(int64_t n_nodes, const int64_t *succ_off, const int32_t *succ, int32_t *bundle, int32_t *lane) {
+    if (n_nodes < 0 || !succ_off || (!succ && succ_off[n_nodes] > 0) || !bundle || !lane) return -1;
+    std::vector<int64_t> off(succ_off, succ_off + n_nodes + 1);
+    std::vector<int32_t> su(succ, succ + off[n_nodes]), indeg(n_nodes, 0), height(n_nodes, 1);
+    for (int32_t x : su) { if (x < 0 || x >= n_nodes) return -1; indeg[x]++; }
+    // heights by reverse topological order (Kahn on the reversed problem is not needed: relax until stable along a topological order)
+    std::vector<int32_t> order; order.reserve(n_nodes);
+    {
+        std::vector<int32_t> deg(indeg);
+        for (int64_t v = 0; v < n_nodes; ++v) if (deg[v] == 0) order.push_back((int32_t)v);
+        for (size_t i = 0; i < order.size(); ++i)
+            for (int64_t e = off[order[i]]; e < off[order[i] + 1]; ++e) if (--deg[su[e]] == 0) order.push_back(su[e]);
+        if ((int64_t)order.size() != n_nodes) return -1;
+    }
+    for (size_t i = order.size(); i-- > 0;) {
+        const int32_t v = order[i];
+        for (int64_t e = off[v]; e < off[v + 1]; ++e) height[v] = std::max(height[v], height[su[e]] + 1);
+    }
+    BundlePlan bp = schedule_bundles(n_nodes, off, su, indeg, height);
+    if (bp.n_bundles < 0) return -1;
+    for (int64_t v = 0; v < n_nodes; ++v) { bundle[v] = bp.bundle[v]; lane[v] = bp.lane[v]; }
+    return bp.n_bundles;
+}
+
 template cudaError_t scalar_block_forward<double>(cudaStream_t, ScalarBlock &, const double *, int *);
 template cudaError_t scalar_block_forward<float>(cudaStream_t, ScalarBlock &, const double *, int *);
 template cudaError_t scalar_block_reverse<double>(cudaStream_t, ScalarBlock &, int64_t, bool, int *);

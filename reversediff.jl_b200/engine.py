@@ -62,6 +62,7 @@ def lib():
         "rdb_gemm": (i32, [vp, i32, i32, i32, i64, i64, i64, f64, vp, i64, vp, i64, f64, vp, i64]),
         "rdb_add_sum": (i32, [vp, i32, i64, vp, vp, f64, vp, vp]),
         "rdb_plan_col_panels": (i32, [i64, i64, C.POINTER(i64)]),
+        "rdb_schedule_bundles": (i64, [i64, C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError if the library lacks a declared symbol
@@ -74,7 +75,7 @@ EXPORTED_SYMBOLS = [
     "rdb_version", "rdb_last_error", "rdb_ctx_create", "rdb_ctx_destroy", "rdb_ctx_set_stream",
     "rdb_ctx_synchronize", "rdb_ctx_set_gemm_f64_mode", "rdb_tape_load", "rdb_tape_destroy", "rdb_tape_set_input", "rdb_forward",
     "rdb_reverse_scalar_seed", "rdb_gradient", "rdb_jacobian", "rdb_hessian", "rdb_get_value", "rdb_get_deriv",
-    "rdb_buffer_size", "rdb_tape_stats", "rdb_tape_launch_count", "rdb_gemm", "rdb_add_sum", "rdb_plan_col_panels",
+    "rdb_buffer_size", "rdb_tape_stats", "rdb_tape_launch_count", "rdb_gemm", "rdb_add_sum", "rdb_plan_col_panels", "rdb_schedule_bundles",
 ]
 
 

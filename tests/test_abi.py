@@ -58,3 +58,60 @@ def test_col_panel_planner(rd):
         assert waves <= -(-ideal // 1) + 1 or waves <= ideal * 1.12, (rows, cols, widths, waves, ideal)      # within one wave of the unsplit GEMM
     w = (C.c_int64 * 4)()
     assert lib.rdb_plan_col_panels(4096, 4096, w) == 3 and list(w)[:3] == [1472, 1472, 1152]
+
+
+def test_bundle_scheduler(rd):
+    """Host-only list scheduler of the scalar-block bundle kernels: every node lands in exactly one (bundle, lane) slot, at most 32
+    per bundle, strictly after all its predecessors; a chain with independent side work needs exactly as many bundles as the chain
+    is long (critical path first), a wide layer of independent nodes ceil(n/32); cycles are refused."""
+    import ctypes as C
+    import numpy as np
+    lib = rd.engine.lib()
+
+    def run(n, edges):
+        off = [0] * (n + 1)
+        for u, _ in edges:
+            off[u + 1] += 1
+        for i in range(n):
+            off[i + 1] += off[i]
+        fill = off[:-1].copy(); succ = [0] * len(edges)
+        for u, v in edges:
+            succ[fill[u]] = v; fill[u] += 1
+        o = (C.c_int64 * (n + 1))(*off); s_ = (C.c_int32 * max(len(edges), 1))(*succ)
+        b = (C.c_int32 * max(n, 1))(); l = (C.c_int32 * max(n, 1))()
+        nb = lib.rdb_schedule_bundles(n, o, s_, b, l)
+        return nb, list(b)[:n], list(l)[:n]
+
+    def check(n, edges, nb, b, l):
+        assert nb >= 0 and all(0 <= x < nb for x in b) and all(0 <= x < 32 for x in l)
+        assert len({(x, y) for x, y in zip(b, l)}) == n                       # one slot per node
+        for u, v in edges:
+            assert b[u] < b[v]                                                # strictly after every predecessor
+
+    # rosenbrock-like: a chain acc_k -> acc_{k+1} of length m, each link also fed by an independent 5-node term
+    m = 300
+    edges, n = [], 0
+    chain = []
+    for k in range(m):
+        term = list(range(n, n + 5)); n += 5
+        edges += [(term[i], term[i + 1]) for i in range(4)]
+        acc = n; n += 1
+        edges.append((term[-1], acc))
+        if chain:
+            edges.append((chain[-1], acc))
+        chain.append(acc)
+    nb, b, l = run(n, edges)
+    check(n, edges, nb, b, l)
+    assert nb == m + 5                                                        # the critical path: first term (5) + m chain links
+    # a wide independent layer
+    nb, b, l = run(1000, [])
+    check(1000, [], nb, b, l)
+    assert nb == 32 and max(b.count(x) for x in set(b)) == 32                # ceil(1000 / 32) bundles, full ones first
+    # random DAG
+    rng = np.random.default_rng(0)
+    n = 2000
+    edges = sorted({(int(u), int(v)) for u, v in zip(rng.integers(0, n, 6000), rng.integers(0, n, 6000)) if u < v})
+    nb, b, l = run(n, edges)
+    check(n, edges, nb, b, l)
+    # a cycle
+    assert run(3, [(0, 1), (1, 2), (2, 0)])[0] == -1
