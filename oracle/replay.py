@@ -140,13 +140,60 @@ def dual_eval(ops, fconst, args, dtype, order=1):
             f2 = imm * (imm - 1) * _powi(x, imm - 2) if imm not in (0, 1) else zero * x
             unary(a, _powi(x, imm), f1, f2)
         elif code == E_POW:
-            # (a^b)' = (b a^(b-1), a^b log a)
-            y = V[a] ** V[b]
-            fa = V[b] * V[a] ** (V[b] - one)
-            fb = y * np.log(V[a])
-            V.append(y); D.append([fa * D[a][p] + fb * D[b][p] for p in range(n)])
-            if order == 2:
-                raise NotImplementedError("second-order pow")
+            # ForwardDiff dual.jl, "exponentiation" (compat "0.10, 1"): three methods, selected by which operands are Duals.
+            # imm (recorded by the host: expr.py pow_imm): bits 0-1 flavor, bit 2 base is a plain Real, bit 3 exponent is.
+            #   flavor 0: one Dual{N} evaluation (∇broadcast broadcast.jl:147-153; @forward closures elementwise.jl:234-301;
+            #             scalar instructions macros.jl:87-124): isconstant(y) / iszero(partials(x)) look at the whole vector
+            #   flavor 1: tracker_∇broadcast, one Dual{1} evaluation per argument (broadcast.jl:218-224): per component
+            #   flavor 2: (broadcast,^) caches e*b^(e-1) and log(b)*b^e directly (elementwise.jl:633-643)
+            vx, vy = V[a], V[b]
+            flavor, x_real, y_real = imm & 3, bool(imm & 4), bool(imm & 8)
+            with np.errstate(all="ignore"):
+                expv = vx ** vy
+                if x_real and y_real:
+                    d = [zero * expv for _ in range(n)]
+                elif flavor == 2:
+                    bs = vy * vx ** (vy - one)                 # base_partials_kernel
+                    ex = np.log(vx) * expv                     # exp_partials_kernel
+                    d = [np.where(D[a][p] != 0, bs * D[a][p], zero) + np.where(D[b][p] != 0, ex * D[b][p], zero) for p in range(n)]
+                elif y_real:
+                    # x::Dual ^ y::Real:  (y == 0 || iszero(partials(x))) ? zero : partials(x) * y * x^(y-1)
+                    pw = vx ** (vy - one)
+                    allz = np.logical_and.reduce([np.asarray(D[a][p] == 0) for p in range(n)])
+                    d = [np.where((vy == 0) | (np.asarray(D[a][p] == 0) if flavor == 1 else allz), zero, D[a][p] * vy * pw)
+                         for p in range(n)]
+                elif x_real:
+                    # x::Real ^ y::Dual:  deriv = (iszero(x) && v > 0) ? zero(expv) : expv*log(x)
+                    deriv = np.where((vx == 0) & (vy > 0), zero, expv * np.log(vx))
+                    d = [deriv * D[b][p] for p in range(n)]
+                else:
+                    powval = vy * vx ** (vy - one)
+                    lg = np.where((vx == 0) & (vy > 0), zero, expv * np.log(vx))
+                    cst = np.logical_and.reduce([np.asarray(D[b][p] == 0) for p in range(n)])
+                    d = [D[a][p] * powval + D[b][p] * np.where(np.asarray(D[b][p] == 0) if flavor == 1 else cst, one, lg)
+                         for p in range(n)]
+                V.append(expv); D.append(d)
+                if order == 2:
+                    # second partials of x^y (not ForwardDiff's code path - the reference nests tapes for Hessians; this is
+                    # calculus): f_xx = y(y-1)x^(y-2), f_xy = x^(y-1)(1 + y log x), f_yy = x^y log(x)^2
+                    a_off = x_real | (y_real & np.asarray(vy == 0))
+                    lx = np.log(vx)
+                    fa, fb = vy * vx ** (vy - one), np.where((vx == 0) & (vy > 0), zero, expv * lx)
+                    faa, fab, fbb = vy * (vy - one) * vx ** (vy - 2 * one), vx ** (vy - one) * (one + vy * lx), fb * lx
+                    Hn = []
+                    for p in range(n):
+                        row = []
+                        for q in range(n):
+                            h = zero * expv
+                            if not x_real:
+                                h = np.where(a_off, h, fa * H[a][p][q] + faa * D[a][p] * D[a][q])
+                            if not y_real:
+                                h = h + fb * H[b][p][q] + fbb * D[b][p] * D[b][q]
+                            if not x_real and not y_real:
+                                h = h + fab * (D[a][p] * D[b][q] + D[a][q] * D[b][p])
+                            row.append(h)
+                        Hn.append(row)
+                    H.append(Hn)
         elif code == E_TANH:
             t = np.tanh(V[a]); f1 = one - t * t
             unary(a, t, f1, -2 * t * f1)
@@ -163,7 +210,8 @@ def dual_eval(ops, fconst, args, dtype, order=1):
         elif code == E_ABS2:
             unary(a, V[a] * V[a], 2 * V[a], 2 * one)
         elif code == E_ABS:
-            unary(a, np.abs(V[a]), np.sign(V[a]), zero)
+            # ForwardDiff: abs(d::Dual) = signbit(d) ? -d : d   (derivative +1 at +0.0, -1 at -0.0)
+            unary(a, np.abs(V[a]), np.where(np.signbit(V[a]), -one, one), zero)
         elif code in (E_MAX, E_MIN):
             pick_a = (V[a] > V[b]) if code == E_MAX else (V[a] < V[b])
             V.append(np.where(pick_a, V[a], V[b]))

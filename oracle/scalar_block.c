@@ -50,8 +50,26 @@ static int dual2(const int32_t *ops, int64_t n_ops, const double *fc, const doub
             case E_MUL: { double va = V[a], vb = V[b]; V[r] = va * vb; D0[r] = D0[a] * vb + va * D0[b]; D1[r] = D1[a] * vb + va * D1[b]; unary = 0; } break;
             case E_DIV: { double q = V[a] / V[b], ib = 1.0 / V[b]; double t0 = (D0[a] - q * D0[b]) * ib, t1 = (D1[a] - q * D1[b]) * ib;
                           V[r] = q; D0[r] = t0; D1[r] = t1; unary = 0; } break;
-            case E_POW: { double y = pow(V[a], V[b]), fa = V[b] * pow(V[a], V[b] - 1.0), fb = y * log(V[a]);
-                          double t0 = fa * D0[a] + fb * D0[b], t1 = fa * D1[a] + fb * D1[b]; V[r] = y; D0[r] = t0; D1[r] = t1; unary = 0; } break;
+            case E_POW: {
+                /* ForwardDiff dual.jl "exponentiation": scalar instructions dualise TrackedReal arguments only (macros.jl:101-124);
+                   imm bit 2 / bit 3 = base / exponent is a plain Real (flavor bits 0-1 are always 0 on a scalar tape) */
+                double vx = V[a], vy = V[b], expv = pow(vx, vy), t0, t1;
+                int x_real = (imm & 4) != 0, y_real = (imm & 8) != 0;
+                if (x_real && y_real) { t0 = t1 = 0.0; }
+                else if (y_real) {                       /* Dual^Real */
+                    if (vy == 0.0 || (D0[a] == 0.0 && D1[a] == 0.0)) t0 = t1 = 0.0;
+                    else { double pw = pow(vx, vy - 1.0); t0 = D0[a] * vy * pw; t1 = D1[a] * vy * pw; }
+                } else if (x_real) {                     /* Real^Dual */
+                    double deriv = (vx == 0.0 && vy > 0.0) ? 0.0 : expv * log(vx);
+                    t0 = deriv * D0[b]; t1 = deriv * D1[b];
+                } else {                                 /* Dual^Dual */
+                    double powval = vy * pow(vx, vy - 1.0), logval;
+                    if (D0[b] == 0.0 && D1[b] == 0.0) logval = 1.0;
+                    else if (vx == 0.0 && vy > 0.0) logval = 0.0;
+                    else logval = expv * log(vx);
+                    t0 = D0[a] * powval + D0[b] * logval; t1 = D1[a] * powval + D1[b] * logval;
+                }
+                V[r] = expv; D0[r] = t0; D1[r] = t1; unary = 0; } break;
             case E_MAX: case E_MIN: { int pick_a = code == E_MAX ? (V[a] > V[b]) : (V[a] < V[b]); int s = pick_a ? a : b;
                           V[r] = V[s]; D0[r] = D0[s]; D1[r] = D1[s]; unary = 0; } break;
             case E_NEG: f0 = -V[a]; f1 = -1.0; break;
@@ -63,7 +81,7 @@ static int dual2(const int32_t *ops, int64_t n_ops, const double *fc, const doub
             case E_SIN: f0 = sin(V[a]); f1 = cos(V[a]); break;
             case E_COS: f0 = cos(V[a]); f1 = -sin(V[a]); break;
             case E_ABS2: f0 = V[a] * V[a]; f1 = 2.0 * V[a]; break;
-            case E_ABS: f0 = fabs(V[a]); f1 = V[a] > 0 ? 1.0 : (V[a] < 0 ? -1.0 : 0.0); break;
+            case E_ABS: f0 = fabs(V[a]); f1 = signbit(V[a]) ? -1.0 : 1.0; break;   /* abs(d::Dual) = signbit(d) ? -d : d */
             case E_INV: { double rr = 1.0 / V[a]; f0 = rr; f1 = -rr * rr; } break;
             case E_SIGMOID: { double s = 1.0 / (1.0 + exp(-V[a])); f0 = s; f1 = s * (1.0 - s); } break;
             default: return code ? code : -1;

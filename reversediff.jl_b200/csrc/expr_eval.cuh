@@ -45,6 +45,59 @@ __device__ __forceinline__ int tri(int p, int q, int N) {   // p <= q packed ind
     return p * N - p * (p - 1) / 2 + (q - p);
 }
 
+// `^` with Dual operands.  imm (expr.py pow_imm): bits 0-1 flavor, bit 2 base is a plain Real, bit 3 exponent is a plain Real.
+// Flavors 0/1 are ForwardDiff's three methods (dual.jl, "exponentiation"):
+//   Dual^Real  : (y == 0 || iszero(partials(x))) ? 0 : partials(x) * y * x^(y-1)          -- log(x) is never formed
+//   Real^Dual  : ((x == 0 && y > 0) ? 0 : x^y * log(x)) * partials(y)
+//   Dual^Dual  : partials(x) * (y x^(y-1)) + partials(y) * logval,  logval = isconstant(y) ? 1 : ((x == 0 && y > 0) ? 0 : x^y log(x))
+// flavor 0 tests isconstant / iszero on the whole partials vector (one Dual{N} evaluation: ∇broadcast, @forward closures, scalar
+// instructions), flavor 1 per component (tracker_∇broadcast evaluates one Dual{1} per argument, broadcast.jl:221-224); flavor 2
+// is (broadcast,^): base partial e*b^(e-1) and exponent partial log(b)*b^e, cached separately (elementwise.jl:633-643).
+template <typename T, int N>
+__device__ __forceinline__ void pow_dual(T va, T vb, int imm, const T *Da, const T *Db, T &y, T *Dr) {
+    const int flavor = imm & 3;
+    const bool a_plain = (imm & 4) != 0, b_plain = (imm & 8) != 0;
+    y = M<T>::pow_(va, vb);
+    if (a_plain && b_plain) {
+#pragma unroll
+        for (int p = 0; p < N; ++p) Dr[p] = (T)0;
+        return;
+    }
+    const T pw1 = M<T>::pow_(va, vb - (T)1);
+    if (flavor == 2) {
+        const T fa = vb * pw1, fb = M<T>::log_(va) * y;
+#pragma unroll
+        for (int p = 0; p < N; ++p) Dr[p] = (Da[p] != (T)0 ? fa * Da[p] : (T)0) + (Db[p] != (T)0 ? fb * Db[p] : (T)0);
+        return;
+    }
+    if (b_plain) {
+        bool all0 = true;
+#pragma unroll
+        for (int p = 0; p < N; ++p) all0 = all0 && Da[p] == (T)0;
+#pragma unroll
+        for (int p = 0; p < N; ++p) {
+            const bool z = vb == (T)0 || (flavor == 1 ? Da[p] == (T)0 : all0);
+            Dr[p] = z ? (T)0 : (Da[p] * vb) * pw1;
+        }
+        return;
+    }
+    const T lg = (va == (T)0 && vb > (T)0) ? (T)0 : y * M<T>::log_(va);
+    if (a_plain) {
+#pragma unroll
+        for (int p = 0; p < N; ++p) Dr[p] = lg * Db[p];
+        return;
+    }
+    const T powval = vb * pw1;
+    bool cst = true;
+#pragma unroll
+    for (int p = 0; p < N; ++p) cst = cst && Db[p] == (T)0;
+#pragma unroll
+    for (int p = 0; p < N; ++p) {
+        const T logval = (flavor == 1 ? Db[p] == (T)0 : cst) ? (T)1 : lg;
+        Dr[p] = Da[p] * powval + Db[p] * logval;
+    }
+}
+
 template <typename T, int N, int ORDER>
 __device__ __forceinline__ void eval_expr(const int4 *__restrict__ ops, int n_ops, const double *__restrict__ fc,
                                           const T *x, T &val, T *dout, T *hout, int r0 = N) {
@@ -135,15 +188,28 @@ __device__ __forceinline__ void eval_expr(const int4 *__restrict__ ops, int n_op
                 unary = false;
             } break;
             case E_POW: {
-                const T y = M<T>::pow_(V[a], V[b]);
-                const T fa = V[b] * M<T>::pow_(V[a], V[b] - (T)1);
-                const T fb = y * M<T>::log_(V[a]);
+                const T va = V[a], vb = V[b];
+                T y;
+                pow_dual<T, N>(va, vb, imm, D[a], D[b], y, D[r]);
                 V[r] = y;
+                if (ORDER == 2) {
+                    // y_pq = fa a_pq + fb b_pq + faa a_p a_q + fab (a_p b_q + a_q b_p) + fbb b_p b_q; a plain Real operand has no
+                    // tangents, and its coefficients (log of a non-positive base...) must not touch the result
+                    const bool b_off = (imm & 8) != 0;
+                    const bool a_off = (imm & 4) != 0 || (b_off && vb == (T)0);          // Dual^Real with y == 0: constant
+                    const T pw1 = M<T>::pow_(va, vb - (T)1), la = M<T>::log_(va);
+                    const T fa = vb * pw1, fb = (va == (T)0 && vb > (T)0) ? (T)0 : y * la;
+                    const T faa = vb * (vb - (T)1) * M<T>::pow_(va, vb - (T)2), fab = pw1 * ((T)1 + vb * la), fbb = fb * la;
 #pragma unroll
-                for (int p = 0; p < N; ++p) D[r][p] = fa * D[a][p] + fb * D[b][p];
-                if (ORDER == 2) {   // second-order pow is rejected at load time
+                    for (int p = 0; p < N; ++p)
 #pragma unroll
-                    for (int h = 0; h < NH; ++h) H[r][h] = (T)0;
+                        for (int q = p; q < N; ++q) {
+                            T h = (T)0;
+                            if (!a_off) h = fa * H[a][tri(p, q, N)] + faa * D[a][p] * D[a][q];
+                            if (!b_off) h = h + fb * H[b][tri(p, q, N)] + fbb * D[b][p] * D[b][q];
+                            if (!a_off && !b_off) h = h + fab * (D[a][p] * D[b][q] + D[a][q] * D[b][p]);
+                            H[r][tri(p, q, N)] = h;
+                        }
                 }
                 unary = false;
             } break;
@@ -174,7 +240,7 @@ __device__ __forceinline__ void eval_expr(const int4 *__restrict__ ops, int n_op
             case E_SIN: { f0 = M<T>::sin_(V[a]); f1 = M<T>::cos_(V[a]); f2 = -f0; } break;
             case E_COS: { f0 = M<T>::cos_(V[a]); f1 = -M<T>::sin_(V[a]); f2 = -f0; } break;
             case E_ABS2: { f0 = V[a] * V[a]; f1 = (T)2 * V[a]; f2 = (T)2; } break;
-            case E_ABS: { f0 = M<T>::abs_(V[a]); f1 = V[a] > (T)0 ? (T)1 : (V[a] < (T)0 ? (T)-1 : (T)0); f2 = (T)0; } break;
+            case E_ABS: { f0 = M<T>::abs_(V[a]); f1 = signbit(V[a]) ? (T)-1 : (T)1; f2 = (T)0; } break;   // abs(d::Dual) = signbit(d) ? -d : d
             case E_INV: { const T rr = (T)1 / V[a]; f0 = rr; f1 = -rr * rr; f2 = (T)2 * rr * rr * rr; } break;
             case E_SIGMOID: { const T s = (T)1 / ((T)1 + M<T>::exp_(-V[a])); f0 = s; f1 = s * ((T)1 - s); f2 = f1 * ((T)1 - (T)2 * s); } break;
             default: f0 = (T)0; break;

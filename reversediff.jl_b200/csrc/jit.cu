@@ -176,13 +176,48 @@ static std::string generate(const ExprParams &P, const int32_t *ops, const doubl
                 for (int p = 0; p < N; ++p)
                     o << "    const T " << g.D(r, p) << " = (" << g.D(a, p) << " - " << g.V(r) << " * " << g.D(b, p) << ") * ib_" << r << ";\n";
                 break;
-            case E_POW:
+            case E_POW: {
+                // the three ForwardDiff `^` methods / the (broadcast,^) formulas, chosen statically from imm (expr_eval.cuh pow_dual)
+                const int flavor = imm & 3;
+                const bool a_plain = (imm & 4) != 0, b_plain = (imm & 8) != 0;
+                const std::string R = std::to_string(r), z = g.zero();
                 o << "    const T " << g.V(r) << " = " << g.fn("pow") << "(" << g.V(a) << ", " << g.V(b) << ");\n";
-                o << "    const T fa_" << r << " = " << g.V(b) << " * " << g.fn("pow") << "(" << g.V(a) << ", " << g.V(b) << " - " << g.one() << ");\n";
-                o << "    const T fb_" << r << " = " << g.V(r) << " * " << g.fn("log") << "(" << g.V(a) << ");\n";
+                if (a_plain && b_plain) {
+                    for (int p = 0; p < N; ++p) o << "    const T " << g.D(r, p) << " = " << z << ";\n";
+                    break;
+                }
+                o << "    const T pw_" << R << " = " << g.fn("pow") << "(" << g.V(a) << ", " << g.V(b) << " - " << g.one() << ");\n";
+                if (flavor == 2) {
+                    o << "    const T fa_" << R << " = " << g.V(b) << " * pw_" << R << ";\n";
+                    o << "    const T fb_" << R << " = " << g.fn("log") << "(" << g.V(a) << ") * " << g.V(r) << ";\n";
+                    for (int p = 0; p < N; ++p)
+                        o << "    const T " << g.D(r, p) << " = (" << g.D(a, p) << " != " << z << " ? fa_" << R << " * " << g.D(a, p) << " : " << z
+                          << ") + (" << g.D(b, p) << " != " << z << " ? fb_" << R << " * " << g.D(b, p) << " : " << z << ");\n";
+                    break;
+                }
+                if (b_plain) {
+                    o << "    const bool az_" << R << " = true";
+                    for (int p = 0; p < N; ++p) o << " && " << g.D(a, p) << " == " << z;
+                    o << ";\n";
+                    for (int p = 0; p < N; ++p)
+                        o << "    const T " << g.D(r, p) << " = (" << g.V(b) << " == " << z << " || "
+                          << (flavor == 1 ? g.D(a, p) + " == " + z : "az_" + R) << ") ? " << z << " : (" << g.D(a, p) << " * " << g.V(b) << ") * pw_" << R << ";\n";
+                    break;
+                }
+                o << "    const T lg_" << R << " = (" << g.V(a) << " == " << z << " && " << g.V(b) << " > " << z << ") ? " << z << " : "
+                  << g.V(r) << " * " << g.fn("log") << "(" << g.V(a) << ");\n";
+                if (a_plain) {
+                    for (int p = 0; p < N; ++p) o << "    const T " << g.D(r, p) << " = lg_" << R << " * " << g.D(b, p) << ";\n";
+                    break;
+                }
+                o << "    const T pv_" << R << " = " << g.V(b) << " * pw_" << R << ";\n";
+                o << "    const bool cs_" << R << " = true";
+                for (int p = 0; p < N; ++p) o << " && " << g.D(b, p) << " == " << z;
+                o << ";\n";
                 for (int p = 0; p < N; ++p)
-                    o << "    const T " << g.D(r, p) << " = fa_" << r << " * " << g.D(a, p) << " + fb_" << r << " * " << g.D(b, p) << ";\n";
-                break;
+                    o << "    const T " << g.D(r, p) << " = " << g.D(a, p) << " * pv_" << R << " + " << g.D(b, p) << " * (("
+                      << (flavor == 1 ? g.D(b, p) + " == " + z : "cs_" + R) << ") ? " << g.one() << " : lg_" << R << ");\n";
+            } break;
             case E_MAX: case E_MIN:
                 o << "    const bool pk_" << r << " = " << g.V(a) << (code == E_MAX ? " > " : " < ") << g.V(b) << ";\n";
                 o << "    const T " << g.V(r) << " = pk_" << r << " ? " << g.V(a) << " : " << g.V(b) << ";\n";
@@ -211,8 +246,7 @@ static std::string generate(const ExprParams &P, const int32_t *ops, const doubl
             case E_COS: g.unary(r, a, g.fn("cos") + "(" + g.V(a) + ")", "-" + g.fn("sin") + "(" + g.V(a) + ")"); break;
             case E_ABS2: g.unary(r, a, g.V(a) + " * " + g.V(a), "(T)2 * " + g.V(a)); break;
             case E_ABS:
-                g.unary(r, a, g.fn("fabs") + "(" + g.V(a) + ")",
-                        g.V(a) + " > " + g.zero() + " ? " + g.one() + " : (" + g.V(a) + " < " + g.zero() + " ? -" + g.one() + " : " + g.zero() + ")");
+                g.unary(r, a, g.fn("fabs") + "(" + g.V(a) + ")", "signbit(" + g.V(a) + ") ? -" + g.one() + " : " + g.one());
                 break;
             case E_INV:
                 o << "    const T t_" << r << " = " << g.one() << " / " << g.V(a) << ";\n";

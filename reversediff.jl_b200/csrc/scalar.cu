@@ -341,8 +341,7 @@ __device__ __forceinline__ void eval_scalar(const int4 *__restrict__ ops, int e_
         case E_SUB: v = xa - xb; d[0] = da0 + (T)-1 * db0; d[1] = da1 + (T)-1 * db1; return;
         case E_MUL: v = xa * xb; d[0] = da0 * xb + xa * db0; d[1] = da1 * xb + xa * db1; return;
         case E_DIV: { const T q = xa / xb, ib = (T)1 / xb; v = q; d[0] = (da0 - q * db0) * ib; d[1] = (da1 - q * db1) * ib; } return;
-        case E_POW: { const T y = M<T>::pow_(xa, xb), fa = xb * M<T>::pow_(xa, xb - (T)1), fb = y * M<T>::log_(xa);
-                      v = y; d[0] = fa * da0 + fb * db0; d[1] = fa * da1 + fb * db1; } return;
+        case E_POW: { const T Da[2] = {da0, da1}, Db[2] = {db0, db1}; pow_dual<T, 2>(xa, xb, imm, Da, Db, v, d); } return;
         case E_MAX: case E_MIN: { const bool pa = code == E_MAX ? (xa > xb) : (xa < xb); v = pa ? xa : xb; d[0] = pa ? da0 : db0; d[1] = pa ? da1 : db1; } return;
         case E_NEG: f0 = -xa; f1 = (T)-1; break;
         case E_POWI: f0 = powi(xa, imm); f1 = imm != 0 ? (T)imm * powi(xa, imm - 1) : (T)0; break;

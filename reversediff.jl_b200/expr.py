@@ -18,23 +18,30 @@ from . import program as P
 
 
 class Tracer:
-    def __init__(self, n_args: int):
+    """``dual[i]`` says whether argument ``i`` reaches the closure as a ForwardDiff ``Dual`` (tracked arguments of
+    ``map``/``broadcast``/scalar instructions, EVERY argument of ``∇broadcast``, ``broadcast.jl:142-153``) or as the plain
+    ``Real`` it is (untracked arguments of ``@forward`` closures, ``elementwise.jl:107-167,234-301``; literals).  Only ``^``
+    cares: ``Dual^Real``, ``Real^Dual`` and ``Dual^Dual`` are three different ForwardDiff methods (see ``pow_imm``)."""
+
+    def __init__(self, n_args: int, dual=None, pow_flavor: int = 0):
         if n_args > P.MAX_ARGS:
             raise ValueError(f"elementwise closures with more than {P.MAX_ARGS} array arguments are not supported")
         self.n_args = n_args
+        self.dual = [True] * n_args if dual is None else [bool(d) for d in dual]
+        self.pow_flavor = int(pow_flavor)
         self.ops: list[tuple[int, int, int, int]] = []
         self.fconsts: list[float] = []
 
-    def emit(self, code, a=0, b=0, imm=0) -> "Sym":
+    def emit(self, code, a=0, b=0, imm=0, dual=True) -> "Sym":
         self.ops.append((code, a, b, imm))
         reg = self.n_args + len(self.ops) - 1
         if reg >= P.MAX_EXPR_REGS:
             raise ValueError(f"scalar closure too large (> {P.MAX_EXPR_REGS} SSA values)")
-        return Sym(self, reg)
+        return Sym(self, reg, dual)
 
     def const(self, c) -> "Sym":
         self.fconsts.append(float(c))
-        return self.emit(P.E_CONST, 0, 0, len(self.fconsts) - 1)
+        return self.emit(P.E_CONST, 0, 0, len(self.fconsts) - 1, dual=False)
 
     def lift(self, x) -> "Sym":
         if isinstance(x, Sym):
@@ -49,16 +56,17 @@ class Tracer:
 class Sym:
     """Symbolic ``Real`` used to run a closure once at compile time."""
 
-    __slots__ = ("tr", "reg")
+    __slots__ = ("tr", "reg", "dual")
     __array_priority__ = 1000
 
-    def __init__(self, tr: Tracer, reg: int):
-        self.tr, self.reg = tr, reg
+    def __init__(self, tr: Tracer, reg: int, dual: bool = True):
+        self.tr, self.reg, self.dual = tr, reg, dual
 
     def _bin(self, code, other, swap=False):
         o = self.tr.lift(other)
         a, b = (o, self) if swap else (self, o)
-        return self.tr.emit(code, a.reg, b.reg)
+        imm = pow_imm(self.tr.pow_flavor, a.dual, b.dual) if code == P.E_POW else 0
+        return self.tr.emit(code, a.reg, b.reg, imm, dual=a.dual or b.dual)
 
     def __add__(self, o): return self._bin(P.E_ADD, o)
     def __radd__(self, o): return self._bin(P.E_ADD, o, True)
@@ -68,12 +76,12 @@ class Sym:
     def __rmul__(self, o): return self._bin(P.E_MUL, o, True)
     def __truediv__(self, o): return self._bin(P.E_DIV, o)
     def __rtruediv__(self, o): return self._bin(P.E_DIV, o, True)
-    def __neg__(self): return self.tr.emit(P.E_NEG, self.reg)
+    def __neg__(self): return self.tr.emit(P.E_NEG, self.reg, dual=self.dual)
     def __pos__(self): return self
 
     def __pow__(self, o):
         if isinstance(o, (int, np.integer)) and not isinstance(o, bool):
-            return self.tr.emit(P.E_POWI, self.reg, 0, int(o))   # Base.literal_pow
+            return self.tr.emit(P.E_POWI, self.reg, 0, int(o), dual=self.dual)   # Base.literal_pow
         return self._bin(P.E_POW, o)
 
     def __rpow__(self, o): return self._bin(P.E_POW, o, True)
@@ -85,10 +93,20 @@ class Sym:
     __bool__ = __lt__ = __le__ = __gt__ = __ge__ = _nobranch
 
 
+def pow_imm(flavor: int, a_dual: bool, b_dual: bool) -> int:
+    """``imm`` of an ``E_POW`` op: bits 0-1 = flavor, bit 2 = base is a plain Real, bit 3 = exponent is a plain Real.
+
+    flavor 0: ForwardDiff ``^`` (``Dual^Dual`` checks ``isconstant(y)`` on the whole partials vector; one ``Dual{N}`` evaluation
+    for all partials — ``∇broadcast``, ``@forward`` closures, scalar instructions); flavor 1: the same, but every partial comes
+    from its own ``Dual{1}`` evaluation (``tracker_∇broadcast``'s ``_deriv``, ``broadcast.jl:221-224``), i.e. ``isconstant`` per
+    component; flavor 2: the uncached formulas of ``(broadcast,^)`` (``elementwise.jl:633-643``: ``e*b^(e-1)``, ``log(b)*b^e``)."""
+    return (int(flavor) & 3) | (0 if a_dual else 4) | (0 if b_dual else 8)
+
+
 def _unary(code, npf):
     def f(x):
         if isinstance(x, Sym):
-            return x.tr.emit(code, x.reg)
+            return x.tr.emit(code, x.reg, dual=x.dual)
         if hasattr(x, "_scalar_unary"):          # TrackedReal: DiffRules unary function -> one ScalarInstruction (scalars.jl:11-12)
             return x._scalar_unary(code)
         return npf(x)
@@ -124,15 +142,16 @@ max_ = _binary(P.E_MAX, np.maximum)
 min_ = _binary(P.E_MIN, np.minimum)
 
 
-def trace(f, n_args: int):
-    """Run ``f`` on ``n_args`` symbolic reals; return ``(ops int32[n,4], fconsts float64[])``."""
-    tr = Tracer(n_args)
-    out = f(*[Sym(tr, i) for i in range(n_args)])
+def trace(f, n_args: int, dual=None, pow_flavor: int = 0):
+    """Run ``f`` on ``n_args`` symbolic reals; return ``(ops int32[n,4], fconsts float64[])``.  ``dual``/``pow_flavor``: see
+    ``Tracer`` / ``pow_imm``."""
+    tr = Tracer(n_args, dual, pow_flavor)
+    out = f(*[Sym(tr, i, tr.dual[i]) for i in range(n_args)])
     out = tr.lift(out)
     if out.reg < n_args:                       # closure returned one of its arguments
-        out = tr.emit(P.E_ARG, 0, 0, out.reg)
+        out = tr.emit(P.E_ARG, 0, 0, out.reg, dual=out.dual)
     elif out.reg != n_args + len(tr.ops) - 1:  # result must be the last SSA value
-        out = tr.emit(P.E_ADD, out.reg, tr.const(0.0).reg)
+        out = tr.emit(P.E_ADD, out.reg, tr.const(0.0).reg, dual=out.dual)
     return np.asarray(tr.ops, np.int32).reshape(-1, 4), np.asarray(tr.fconsts, np.float64)
 
 

@@ -71,7 +71,8 @@ class ForwardOptimize:
         # (self::ForwardOptimize)(t::TrackedReal) / (a, b) with at least one TrackedReal (macros.jl:84-131): ONE instruction
         if len(a) in (1, 2) and any(isinstance(x, TrackedReal) for x in a) and \
                 all(isinstance(x, TrackedReal) or np.ndim(x) == 0 for x in a):
-            return record_scalar(E.trace(self.f, len(a)), *a)
+            # only TrackedReal arguments are dualised; plain Reals stay Reals (macros.jl:101-124)
+            return record_scalar(E.trace(self.f, len(a), dual=[isinstance(x, TrackedReal) for x in a]), *a)
         return self.f(*a)
 
 
@@ -297,7 +298,9 @@ def record_scalar(expr, a, b=None):
 
 
 def _scalar_binary(code, a, b):
-    return record_scalar((np.asarray([(code, 0, 1, 0)], np.int32), np.zeros(0)), a, b)
+    # ^ is three ForwardDiff methods (Dual^Dual, Dual^Real, Real^Dual): which one ran is part of the instruction (expr.pow_imm)
+    imm = E.pow_imm(0, isinstance(a, TrackedReal), isinstance(b, TrackedReal)) if code == P.E_POW else 0
+    return record_scalar((np.asarray([(code, 0, 1, imm)], np.int32), np.zeros(0)), a, b)
 
 
 def _scalar_const(tp, c):
@@ -533,7 +536,15 @@ def _record_elementwise(opcode, f, args, require_same_shape=False):
         for i in range(nd):
             if p[i] not in (1, oshape[i]):
                 raise ValueError(f"arrays could not be broadcast to a common size: {shapes}")
-    ex = E.trace(f, len(args))
+    # which arguments the closure sees as Duals: every Real/array argument of ∇broadcast (broadcast.jl:142-153) and of
+    # tracker_∇broadcast (dual(x::Real, p), broadcast.jl:218-224); only the tracked ones for @forward closures
+    # (elementwise.jl:234-301); (broadcast,^) uses its own cached formulas (elementwise.jl:633-643)
+    if opcode in (P.OP_MAP, P.OP_BCAST):
+        dual = [istracked(a) for a in args]
+    else:
+        dual = [True] * len(args)
+    flavor = 1 if opcode == P.OP_TRACKER_BCAST else (2 if opcode == P.OP_BCAST_POW else 0)
+    ex = E.trace(f, len(args), dual=dual, pow_flavor=flavor)
     vals = [np.asarray(value(a), tp.dtype).reshape(p, order="F") for a, p in zip(args, padded)]
     out = _track_new(np.broadcast_to(E.eval_value(ex, vals, tp.dtype), oshape), tp)
     ops = [_capture(a, tp, bound_to=oshape) for a in args]
