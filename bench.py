@@ -247,7 +247,7 @@ def main():
     a, b = rd.workloads.inputs_gradient_example(n, npdt)
 
     # ---- device-resident leg ---------------------------------------------------------------------
-    a_d = torch.from_numpy(np.ascontiguousarray(a.T)).cuda(); b_d = torch.from_numpy(np.ascontiguousarray(b.T)).cuda()
+    a_d = rd.engine.device_array(a); b_d = rd.engine.device_array(b)    # column-major images of a, b
     ga_d = torch.empty(n * n, dtype=tdt, device="cuda"); gb_d = torch.empty(n * n, dtype=tdt, device="cuda")
 
     def step_dev():

@@ -42,8 +42,9 @@ typedef struct rdb_options {
     int32_t seed_block;       /* R: seed rows / Hessian columns processed per batched sweep (0=auto) */
     int32_t use_graph;        /* 1 = replay gradient! through a captured CUDA graph (default 1)      */
     int32_t profile;          /* 1 = record per-step CUDA-event timings for rdb_tape_stats           */
-    int32_t gemm_f64_mode;    /* FP64 `*` kernels: 0 = auto (exact int8 slices on tcgen05 when eligible,
-                                 DMMA otherwise), 1 = DMMA only                                        */
+    int32_t gemm_f64_mode;    /* FP64 `*` kernels: 0 = auto (exact int8 slices on tcgen05 when eligible and certified
+                                 accurate, DMMA otherwise - see rdb_tape_guard_stats), 1 = DMMA only,
+                                 2 = int8 slices without the DMMA replay (measurement)                 */
     int32_t ozaki_slices;     /* int8 slices per FP64 operand for the tcgen05 path (0 = default: 7 of 8 bits) */
     int32_t reserved[2];
 } rdb_options;
@@ -51,7 +52,8 @@ typedef struct rdb_options {
 /* ---- library / context --------------------------------------------------------------------------- */
 const char *rdb_version(void);
 const char *rdb_last_error(void);
-/* One context per process and device (one process per GPU). */
+/* One context per device and stream; all state of the kernels (workspaces, sliced-operand cache) belongs to the context, so
+ * several contexts - on one device or on several, from one host thread each - can be live in a process. */
 rdb_ctx *rdb_ctx_create(int device_id);
 void rdb_ctx_destroy(rdb_ctx *);
 /* Adopt a caller stream (e.g. torch's current stream) instead of the context's own. */
@@ -60,6 +62,13 @@ int rdb_ctx_synchronize(rdb_ctx *);
 /* FP64 kernel selection for rdb_gemm on this context (tapes carry their own in rdb_options): mode 0 = auto,
  * 1 = DMMA only; slices = int8 slices per operand of the tcgen05 int8 path (0 = default: 7 slices of 8 bits, at most 8). */
 int rdb_ctx_set_gemm_f64_mode(rdb_ctx *, int mode, int slices);
+
+/* Accuracy certificate of the int8-slice FP64 GEMM (the default `*` kernel for m, n, k >= 256).  Its error is norm-wise
+ * (relative to the row / column maxima of the operands), not component-wise like DGEMM's, so every launch records
+ * max |alpha op(A) op(B)| and a rigorous bound of its own error; a launch is FLAGGED when bound > 2^-40 * max |product|
+ * (9.1e-13, inside the 1e-12 contract).  Tapes act on it themselves (rdb_tape_guard_stats); for rdb_gemm the caller reads the
+ * counters here: launches checked / flagged since the last call and the worst bound/|product| ratio.  Synchronises. */
+int rdb_ctx_gemm_guard(rdb_ctx *, int64_t *checked, int64_t *flagged, double *worst_ratio);
 
 /* ---- tape life cycle ----------------------------------------------------------------------------- */
 /* Replaces ReverseDiff.compile(t::AbstractTape) (src/api/tape.jl:146-149) and the CompiledTape it builds
@@ -101,7 +110,7 @@ int rdb_jacobian(rdb_tape *, int input_slot, int64_t row_begin, int64_t row_end,
  * array tape of f is replayed forward-over-reverse with `seed_block` tangent directions per sweep.
  * `result` addresses element (0, col_begin) of the column-major n x n matrix, leading dimension `ld`.
  * grad_out / value_out (may be NULL) receive the gradient and primal as the DiffResult method does
- * (src/api/hessians.jl:92-97). */
+ * (src/api/hessians.jl:92-97); grad_out may be a host or a device pointer, value_out is a host pointer. */
 int rdb_hessian(rdb_tape *, int64_t col_begin, int64_t col_end, void *result, int64_t ld, int result_on_device,
                 void *grad_out, void *value_out);
 
@@ -111,6 +120,10 @@ int rdb_get_deriv(rdb_tape *, int buffer_id, void *dst_host);
 int64_t rdb_buffer_size(rdb_tape *, int buffer_id);
 /* Per-step report (kernel name, time, algorithmic bytes / flops) as JSON; needs opts.profile = 1. */
 int rdb_tape_stats(rdb_tape *, char *json, size_t cap);
+/* Totals since load of the int8-slice GEMM's accuracy certificate on this tape (see rdb_ctx_gemm_guard): launches checked,
+ * launches flagged, and how many API calls were therefore replayed with the DMMA kernels before returning (gemm_f64_mode 0;
+ * mul!, src/derivatives/linalg/arithmetic.jl:245-285, is DGEMM in the reference).  Any pointer may be NULL. */
+int rdb_tape_guard_stats(rdb_tape *, int64_t *checked, int64_t *flagged, int64_t *fallbacks, double *worst_ratio);
 /* Number of kernel launches issued by the engine on this tape since load (bench "gpu_launches"). */
 int64_t rdb_tape_launch_count(rdb_tape *);
 

@@ -40,7 +40,7 @@ def stats_of(tape, run, **opts):
 
 
 def dev(x):
-    return torch.from_numpy(np.ascontiguousarray(np.asarray(x).T if np.ndim(x) == 2 else x)).cuda()
+    return rd.engine.device_array(x)      # same shape, column-major memory
 
 
 out = []

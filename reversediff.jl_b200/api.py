@@ -142,6 +142,8 @@ class HessianTape(AbstractTape):
         self.input = [TrackedArray(v, self.tape, b)]             # jcfg.input
         y, grad = record_gradient_program(func, self.input[0])   # GradientTape(f, ht.input, gcfg) + seeded_reverse_pass!
         self.primal = y.value                                    # f(x) as an outer-tape scalar
+        # value!(result, ...) of the DiffResult method (hessians.jl:92-97) reads it back from the engine
+        self.primal_buffer = scalar_buffer(self.primal) if isinstance(self.primal, TrackedReal) else -1
         self.output = collect(grad, self.tape)                   # ht.output: the gradient, an array of outer-tape scalars
         prog.output_buffer = self.output.buffer
 
@@ -280,10 +282,14 @@ def hessian_(result, ct: CompiledTape, input_, cols=None, rows=None):
         b, e = (0, n) if rows is None else rows
         if isinstance(result, DiffResult):
             # seeded_reverse_pass!(DiffResult(gradient(result), hessian(result)), tape); value!(result, f(input))  (hessians.jl:92-97)
+            if _is_device(result.derivs[1]) or _is_device(result.derivs[0]):
+                raise TypeError("hessian! of a reverse-mode HessianTape into a DiffResult needs host arrays (the gradient is the "
+                                "tape's output value, extracted on the host); pass a plain device matrix for the Hessian alone")
             g = ct.handle.jacobian(0, b, e, result.derivs[1], (e - b, n), want_value=True, out_shape=(n,))
-            if not _is_device(result.derivs[0]):
-                np.copyto(result.derivs[0].reshape(-1, order="F"), np.asarray(g).reshape(-1, order="F"))
-            result.value = ct.tape.func(np.asarray(input_))
+            _store(result.derivs[0], g)
+            # the reference re-evaluates f(input) on the CPU here; the primal is already on the tape (recorded by
+            # record_gradient_program), so it is read back from the engine instead - no host evaluation of f
+            result.value = ct.handle.get_value(ct.tape.primal_buffer)[0]
         else:
             ct.handle.jacobian(0, b, e, result, (e - b, n), want_value=False, out_shape=(n,))
         return result
@@ -291,12 +297,20 @@ def hessian_(result, ct: CompiledTape, input_, cols=None, rows=None):
         raise ValueError("a forward-mode HessianTape shards by columns: pass cols=(b, e)")
     b, e = (0, n) if cols is None else cols
     if isinstance(result, DiffResult):
-        g, val = ct.handle.hessian(b, e, result.derivs[1], (n, e - b), want_grad=True)
-        np.copyto(result.derivs[0].reshape(-1, order="F"), g) if not _is_device(result.derivs[0]) else None
+        dev_g = result.derivs[0] if _is_device(result.derivs[0]) else None
+        g, val = ct.handle.hessian(b, e, result.derivs[1], (n, e - b), want_grad=True, grad_out=dev_g)
+        if dev_g is None:
+            _store(result.derivs[0], g)
         result.value = val
     else:
         ct.handle.hessian(b, e, result, (n, e - b), want_grad=False)
     return result
+
+
+def _store(dst, flat):
+    """Write a flat column-major vector into a host result array of any layout (a reshape of a C-ordered array is a copy, so
+    the assignment goes through the array itself)."""
+    dst[...] = np.asarray(flat).reshape(dst.shape, order="F")
 
 
 def shard_range(n: int, world: int, rank: int):

@@ -60,9 +60,20 @@ struct rdb_ctx {
     cudaStream_t upload_stream = nullptr;      // host->device input copies in column panels (rdb_tape_set_input), see settle_uploads
     cudaStream_t side_stream = nullptr;        // operand slicing for the NEXT `*` GEMM while the current one runs (preslice_*)
     cudaEvent_t side_ev = nullptr;
+    GemmState gemm;                            // workspace, sliced-operand cache, accuracy-certificate slots of the `*` kernels
 };
+// every C-ABI entry: the calling thread works on this context's device with this context's GEMM state
+static void ctx_enter(rdb_ctx *c) {
+    cudaSetDevice(c->device);
+    g_gemm = &c->gemm;
+}
 static void ctx_release(rdb_ctx *c) {
     if (!c || --c->refs > 0) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->side_stream) cudaStreamSynchronize(c->side_stream);
+    c->gemm.release();
+    if (g_gemm == &c->gemm) g_gemm = nullptr;
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->upload_stream) cudaStreamDestroy(c->upload_stream);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
@@ -149,6 +160,13 @@ struct rdb_tape {
     // hessian! with a device result and no gradient/value request, launch-bound tapes: the whole sweep as one graph, keyed by its arguments
     struct HessGraph { cudaGraphExec_t exec = nullptr; int state = 0; int64_t cb = 0, ce = 0, ld = 0; void *result = nullptr; } hgraph;
     bool capturing = false;        // hessian_impl is being captured: no synchronisation, no host copies
+    // accuracy certificate of the int8-slice `*` kernels (umma.cu guard): totals since load, and the fallback state
+    int64_t guard_checked = 0, guard_flagged = 0, guard_fallbacks = 0;
+    double guard_worst = 0;
+    int guard_streak = 0;          // consecutive calls whose certificate failed; 3 make the tape DMMA-only for good
+    bool dmma_now = false;         // this call is the DMMA replay of a call whose certificate failed
+    uint64_t graph_gen = 0, hgraph_gen = 0;   // GemmState::alloc_gen when the graphs were captured
+    int graph_guard_n = 0, hgraph_guard_n = 0; // certificate slots the captured kernels write
     int last_upload = -1;          // buffer of the most recent panelled upload (the one worth consuming panel by panel)
     // deriv zero-state, per ROOT buffer: dz[b] != 0 means deriv(b) is LOGICALLY zero while its storage may hold anything.
     // unseed! (every reverse exec ends with one, tracked.jl:207-213) only sets the flag; the next accumulation into the buffer
@@ -709,7 +727,7 @@ static int find_mul_partner(rdb_tape *t, int k, int root, int64_t rows, int64_t 
 // the current GEMM computes; the GEMM then finds them in the sliced-operand cache (umma.cu, ozaki_preslice).
 static bool preslice_on(rdb_tape *t) {
     static const bool on = [] { const char *e = getenv("RDB_PRESLICE"); return !(e && e[0] == '0'); }();
-    return on && t->dtype == RDB_F64 && t->opts.gemm_f64_mode != 1 && !t->capturing;
+    return on && t->dtype == RDB_F64 && t->opts.gemm_f64_mode != 1 && !t->dmma_now && !t->capturing && !t->ctx->gemm.no_cache;
 }
 // the side stream may read everything the main stream has produced so far
 static int preslice_begin(rdb_tape *t) {
@@ -1337,8 +1355,14 @@ static int seed_scalar_and_reverse(rdb_tape *t) {
     return reverse_pass<T>(t, 1);
 }
 
+struct NoCacheScope {
+    GemmState &G;
+    bool prev;
+    NoCacheScope(GemmState &g, bool on) : G(g), prev(g.no_cache) { G.no_cache = on; }
+    ~NoCacheScope() { G.no_cache = prev; }
+};
 static bool graph_eligible(rdb_tape *t) {
-    if (!t->opts.use_graph || t->opts.profile || S(t) == nullptr) return false;     // the legacy default stream cannot be captured
+    if (!t->opts.use_graph || t->opts.profile || S(t) == nullptr || t->dmma_now) return false;     // the legacy default stream cannot be captured
     int64_t elems = 0;
     for (auto &b : t->bufs) elems += b.size;
     return elems <= (1 << 20);                                                       // launch-bound tapes only
@@ -1347,14 +1371,25 @@ static bool graph_eligible(rdb_tape *t) {
 // forward sweep + seeded reverse sweep as ONE graph launch; returns 1 if the graph ran, 0 if the caller must run eagerly
 template <typename T>
 static int graph_sweep(rdb_tape *t) {
+    GemmState &G = t->ctx->gemm;
+    if (t->graph_state == 2 && t->graph_gen != G.alloc_gen) {
+        // the context's GEMM workspace moved since the capture (another tape grew it): the graph holds dead pointers
+        cudaGraphExecDestroy(t->gexec);
+        t->gexec = nullptr;
+        t->graph_state = 1;
+    }
     if (t->graph_state == 2) {
+        if (G.guard_used != 0) CU(guard_fold(S(t), G));   // the graph writes certificate slots [0, n)
         CU(cudaGraphLaunch(t->gexec, S(t)));
+        G.guard_used = t->graph_guard_n;
         t->launches += 1;
         return 1;
     }
     if (t->graph_state == 0) { t->graph_state = 1; return 0; }
     if (t->graph_state != 1) return 0;
     t->graph_state = -1;
+    CU(guard_fold(S(t), G));                               // the captured kernels take certificate slots 0, 1, ...
+    const uint64_t gen0 = G.alloc_gen;
     if (cudaStreamBeginCapture(S(t), cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return 0; }
     t->capturing = true;                                   // no side-stream work inside the capture
     int rc = forward_pass<T>(t);
@@ -1362,18 +1397,26 @@ static int graph_sweep(rdb_tape *t) {
     t->capturing = false;
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(S(t), &g);
+    t->graph_guard_n = G.guard_used;
+    G.guard_used = 0;                                      // nothing ran yet
     if (rc != RDB_OK || e != cudaSuccess || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); return 0; }
+    if (G.alloc_gen != gen0) { cudaGraphDestroy(g); t->graph_state = 1; return 0; }   // the workspace grew inside the capture: run eagerly, capture next time
     e = cudaGraphInstantiate(&t->gexec, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) { cudaGetLastError(); t->gexec = nullptr; return 0; }
     t->graph_state = 2;
+    t->graph_gen = G.alloc_gen;
     CU(cudaGraphLaunch(t->gexec, S(t)));
+    G.guard_used = t->graph_guard_n;
     t->launches += 1;
     return 1;
 }
 
 template <typename T>
 static int gradient_impl(rdb_tape *t, void *const *result_ptrs, int on_device, void *value_out) {
+    // graph tapes slice every operand into the context workspace on every replay (GemmState::no_cache), also in the eager warm-up
+    // call, so that the workspace already has its final size when the capture starts
+    NoCacheScope nc(t->ctx->gemm, graph_eligible(t));
     if (graph_eligible(t)) {
         int ran = graph_sweep<T>(t);
         if (ran < 0) return ran;
@@ -1789,7 +1832,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
     for (auto &b : t->bufs) if (b.alias_of >= 0) b.td = t->bufs[b.alias_of].td;
     for (size_t b = 0; b < t->bufs.size(); ++b) t->dz[droot(t, (int)b)] = 1;   // intermediates were physically unseeded
     t->dz[droot(t, xid)] = 0;                                                   // deriv(x) holds the gradient
-    if (grad_out) CU(cudaMemcpyAsync(grad_out, x.der, (size_t)n * t->es, cudaMemcpyDeviceToHost, S(t)));
+    if (grad_out) CU(cudaMemcpyAsync(grad_out, x.der, (size_t)n * t->es, cudaMemcpyDefault, S(t)));
     if (!on_device && cols > 0)
         CU(cudaMemcpy2DAsync(result, (size_t)ld * t->es, t->stage, (size_t)n * t->es, (size_t)n * t->es, (size_t)cols, cudaMemcpyDeviceToHost, S(t)));
     if (!t->capturing) CU(cudaStreamSynchronize(S(t)));
@@ -1802,7 +1845,12 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
 template <typename T>
 static int hessian_entry(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64_t ld, int on_device, void *grad_out, void *value_out) {
     auto &G = t->hgraph;
+    GemmState &GS = t->ctx->gemm;
     const bool want = graph_eligible(t) && on_device && !grad_out && !value_out && ce > cb && t->inputs.size() == 1;
+    NoCacheScope nc(GS, want);
+    if (G.state == 2 && t->hgraph_gen != GS.alloc_gen) {     // the context's GEMM workspace moved since the capture
+        cudaGraphExecDestroy(G.exec); G.exec = nullptr; G.state = 1;
+    }
     const bool same = want && G.cb == cb && G.ce == ce && G.ld == ld && G.result == result;
     if (!want || !same) {
         if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
@@ -1812,6 +1860,8 @@ static int hessian_entry(rdb_tape *t, int64_t cb, int64_t ce, void *result, int6
     if (G.state == 1) {
         OK(settle_uploads(t, -1));
         G.state = -1;
+        CU(guard_fold(S(t), GS));
+        const uint64_t gen0 = GS.alloc_gen;
         if (cudaStreamBeginCapture(S(t), cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
             cudaGetLastError();
             return hessian_impl<T>(t, cb, ce, result, ld, on_device, grad_out, value_out);
@@ -1821,19 +1871,29 @@ static int hessian_entry(rdb_tape *t, int64_t cb, int64_t ce, void *result, int6
         t->capturing = false;
         cudaGraph_t g = nullptr;
         const cudaError_t e = cudaStreamEndCapture(S(t), &g);
+        t->hgraph_guard_n = GS.guard_used;
+        GS.guard_used = 0;
         if (rc != RDB_OK || e != cudaSuccess || !g) {
             cudaGetLastError();
             if (g) cudaGraphDestroy(g);
             return hessian_impl<T>(t, cb, ce, result, ld, on_device, grad_out, value_out);      // eager from now on (state -1)
         }
+        if (GS.alloc_gen != gen0) {                      // the workspace grew inside the capture: eager now, capture next time
+            cudaGraphDestroy(g);
+            G.state = 1;
+            return hessian_impl<T>(t, cb, ce, result, ld, on_device, grad_out, value_out);
+        }
         const cudaError_t ei = cudaGraphInstantiate(&G.exec, g, 0);
         cudaGraphDestroy(g);
         if (ei != cudaSuccess) { cudaGetLastError(); G.exec = nullptr; return hessian_impl<T>(t, cb, ce, result, ld, on_device, grad_out, value_out); }
         G.state = 2;
+        t->hgraph_gen = GS.alloc_gen;
     }
     if (G.state != 2) return hessian_impl<T>(t, cb, ce, result, ld, on_device, grad_out, value_out);
     OK(settle_uploads(t, -1));
+    if (GS.guard_used != 0) CU(guard_fold(S(t), GS));
     CU(cudaGraphLaunch(G.exec, S(t)));
+    GS.guard_used = t->hgraph_guard_n;
     t->launches += 1;
     // host-side state the sweep leaves behind (tail of hessian_impl)
     for (size_t b = 0; b < t->bufs.size(); ++b) t->dz[droot(t, (int)b)] = 1;
@@ -1852,9 +1912,39 @@ static int fold_launches(rdb_tape *t, int rc) {
     if (t->ctx && t->ctx->side_stream) cudaStreamSynchronize(t->ctx->side_stream);
     return rc;
 }
+// Run one API call on a tape.  FP64 `*` instructions of eligible shapes go through exact int8 slices on tcgen05, whose error is
+// norm-wise (2^-56 of the row/column maxima), not component-wise like DGEMM's.  Every such launch therefore leaves a rigorous
+// a-posteriori certificate (umma.cu: max error bound <= 2^-40 * max |product|); when any launch of the call fails it, the call
+// is replayed with the DMMA kernels (plain FP64 FMA arithmetic, what the reference's BLAS does) before it returns.  Three failing
+// calls in a row make the tape DMMA-only.  gemm_f64_mode: 0 = this, 1 = DMMA only, 2 = int8 slices without the replay.
+template <typename F>
+static int run_call(rdb_tape *t, F &&run) {
+    rdb_ctx *c = t->ctx;
+    ctx_enter(c);
+    g_f64_mode = t->opts.gemm_f64_mode;
+    g_f64_slices = t->opts.ozaki_slices;
+    g_extra_launches = 0;
+    int rc = fold_launches(t, run());
+    if (rc != RDB_OK || t->dtype != RDB_F64 || t->opts.gemm_f64_mode == 1 || !c->gemm.guard) return rc;
+    if (c->gemm.guard_used == 0 && !c->gemm.guard_pending) return rc;   // no int8-slice launch in this call
+    GuardSummary gs;
+    CU(guard_read(S(t), c->gemm, &gs));
+    t->guard_checked += (int64_t)gs.checked;
+    t->guard_flagged += (int64_t)gs.flagged;
+    if (gs.worst_ratio > t->guard_worst) t->guard_worst = gs.worst_ratio;
+    if (gs.flagged == 0) { t->guard_streak = 0; return rc; }
+    if (t->opts.gemm_f64_mode != 0) return rc;
+    t->guard_fallbacks++;
+    t->dmma_now = true;
+    g_f64_mode = 1;
+    g_extra_launches = 0;
+    rc = fold_launches(t, run());
+    t->dmma_now = false;
+    if (++t->guard_streak >= 3) t->opts.gemm_f64_mode = 1;
+    return rc;
+}
 #define DISPATCH(t, fn, ...) \
-    (g_f64_mode = (t)->opts.gemm_f64_mode, g_f64_slices = (t)->opts.ozaki_slices, g_extra_launches = 0, \
-     fold_launches((t), (t)->dtype == RDB_F64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__)))
+    run_call((t), [&]() -> int { return (t)->dtype == RDB_F64 ? fn<double>(__VA_ARGS__) : fn<float>(__VA_ARGS__); })
 
 extern "C" {
 
@@ -1892,13 +1982,32 @@ int rdb_ctx_set_gemm_f64_mode(rdb_ctx *c, int mode, int slices) {
 }
 int rdb_ctx_synchronize(rdb_ctx *c) {
     if (!c) return fail(RDB_EINVAL, "null context");
+    ctx_enter(c);
     CU(cudaStreamSynchronize(c->stream));
+    return RDB_OK;
+}
+int rdb_ctx_gemm_guard(rdb_ctx *c, int64_t *checked, int64_t *flagged, double *worst_ratio) {
+    if (!c) return fail(RDB_EINVAL, "null context");
+    ctx_enter(c);
+    GuardSummary gs;
+    CU(guard_read(c->stream, c->gemm, &gs));
+    if (checked) *checked = (int64_t)gs.checked;
+    if (flagged) *flagged = (int64_t)gs.flagged;
+    if (worst_ratio) *worst_ratio = gs.worst_ratio;
+    return RDB_OK;
+}
+int rdb_tape_guard_stats(rdb_tape *t, int64_t *checked, int64_t *flagged, int64_t *fallbacks, double *worst_ratio) {
+    if (!t) return fail(RDB_EINVAL, "null tape");
+    if (checked) *checked = t->guard_checked;
+    if (flagged) *flagged = t->guard_flagged;
+    if (fallbacks) *fallbacks = t->guard_fallbacks;
+    if (worst_ratio) *worst_ratio = t->guard_worst;
     return RDB_OK;
 }
 
 rdb_tape *rdb_tape_load(rdb_ctx *c, const void *program, size_t nbytes, const rdb_options *opts) {
     if (!c || !program) { fail(RDB_EINVAL, "null argument"); return nullptr; }
-    cudaSetDevice(c->device);
+    ctx_enter(c);
     auto *t = new rdb_tape();
     t->ctx = c;
     c->refs++;
@@ -1911,7 +2020,7 @@ rdb_tape *rdb_tape_load(rdb_ctx *c, const void *program, size_t nbytes, const rd
 }
 void rdb_tape_destroy(rdb_tape *t) {
     if (!t) return;
-    if (t->ctx) cudaStreamSynchronize(t->ctx->stream);
+    if (t->ctx) { ctx_enter(t->ctx); cudaStreamSynchronize(t->ctx->stream); }
     for (void *p : t->allocs) cudaFree(p);
     for (auto &I : t->instrs) if (I.blk) scalar_block_free(*I.blk);
     if (t->ev0) cudaEventDestroy(t->ev0);
@@ -1928,6 +2037,7 @@ void rdb_tape_destroy(rdb_tape *t) {
 int rdb_tape_set_input(rdb_tape *t, int slot, const void *data, int is_device) {
     if (!t || !data) return fail(RDB_EINVAL, "null argument");
     if (slot < 0 || (size_t)slot >= t->inputs.size()) return fail(RDB_EINVAL, "input slot %d out of range", slot);
+    ctx_enter(t->ctx);
     Buf &b = t->bufs[t->inputs[slot]];
     static const bool stream_inputs = [] { const char *e = getenv("RDB_STREAM_INPUTS"); return !(e && e[0] == '0'); }();
     const bool matrix = b.nd == 2 && b.dims[0] * b.dims[1] == b.size && b.alias_of < 0;
@@ -1966,6 +2076,7 @@ int rdb_forward(rdb_tape *t) {
 }
 int rdb_reverse_scalar_seed(rdb_tape *t) {
     if (!t) return fail(RDB_EINVAL, "null tape");
+    ctx_enter(t->ctx);
     OK(settle_uploads(t, -1));
     OK(DISPATCH(t, seed_scalar_and_reverse, t));
     CU(cudaStreamSynchronize(S(t)));
@@ -1989,6 +2100,7 @@ int64_t rdb_buffer_size(rdb_tape *t, int b) {
 }
 int rdb_get_value(rdb_tape *t, int b, void *dst) {
     if (!t || !dst || b < 0 || (size_t)b >= t->bufs.size()) return fail(RDB_EINVAL, "bad buffer id");
+    ctx_enter(t->ctx);
     OK(settle_uploads(t, -1));
     CU(cudaMemcpyAsync(dst, t->bufs[b].val, (size_t)t->bufs[b].size * t->es, cudaMemcpyDeviceToHost, S(t)));
     CU(cudaStreamSynchronize(S(t)));
@@ -1997,6 +2109,7 @@ int rdb_get_value(rdb_tape *t, int b, void *dst) {
 int rdb_get_deriv(rdb_tape *t, int b, void *dst) {
     if (!t || !dst || b < 0 || (size_t)b >= t->bufs.size()) return fail(RDB_EINVAL, "bad buffer id");
     if (!t->bufs[b].der) return fail(RDB_EINVAL, "buffer %d has no deriv (CONST)", b);
+    ctx_enter(t->ctx);
     OK(dmaterialize(t, b, std::max<int64_t>(t->R_alloc, 1), false));
     CU(cudaMemcpyAsync(dst, t->bufs[b].der, (size_t)t->bufs[b].size * t->es, cudaMemcpyDeviceToHost, S(t)));
     CU(cudaStreamSynchronize(S(t)));
@@ -2023,6 +2136,7 @@ int64_t rdb_tape_launch_count(rdb_tape *t) { return t ? t->launches : -1; }
 int rdb_gemm(rdb_ctx *c, int dtype, int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const void *A, int64_t lda,
              const void *B, int64_t ldb, double beta, void *C, int64_t ldc) {
     if (!c) return fail(RDB_EINVAL, "null context");
+    ctx_enter(c);
     cudaError_t e = dtype == RDB_F64
                         ? gemm_f64(c->stream, ta != 0, tb != 0, m, n, k, alpha, (const double *)A, lda, (const double *)B, ldb, beta, (double *)C, ldc,
                                    c->gemm_f64_mode, c->ozaki_slices)
@@ -2033,6 +2147,7 @@ int rdb_gemm(rdb_ctx *c, int dtype, int ta, int tb, int64_t m, int64_t n, int64_
 
 int rdb_add_sum(rdb_ctx *c, int dtype, int64_t n, const void *a, const void *b, double sign, void *out, void *sum_out) {
     if (!c) return fail(RDB_EINVAL, "null context");
+    ctx_enter(c);
     static void *scratch = nullptr;
     if (!scratch && cudaMalloc(&scratch, kReduceBlocks * 8) != cudaSuccess) return fail(RDB_ENOMEM, "scratch alloc failed");
     cudaError_t e;

@@ -424,8 +424,6 @@ __global__ void __launch_bounds__(256) gemv_n_finish(int rows, int chunks, doubl
     if (beta != 0.0) v += beta * (double)y[(int64_t)r * incy];
     y[(int64_t)r * incy] = (T)v;
 }
-static double *g_scratch = nullptr;
-static size_t g_scratch_elems = 0;
 template <typename T>
 static cudaError_t gemv(cudaStream_t st, bool trans, int64_t rows, int64_t cols, double alpha, const T *A, int64_t lda, const T *x,
                         int64_t incx, double beta, T *y, int64_t incy) {
@@ -442,11 +440,14 @@ static cudaError_t gemv(cudaStream_t st, bool trans, int64_t rows, int64_t cols,
     int kchunk = (int)((cols + chunks - 1) / chunks);
     chunks = (cols + kchunk - 1) / kchunk;
     size_t need = (size_t)chunks * rows;
-    if (need > g_scratch_elems) {
+    GemmState &G = gemm_state();                    // per-context scratch (kernels.h)
+    double *&g_scratch = G.gemv_scratch;
+    if (need > G.gemv_scratch_elems) {
         if (g_scratch) cudaFree(g_scratch);
-        g_scratch = nullptr; g_scratch_elems = 0;
+        g_scratch = nullptr; G.gemv_scratch_elems = 0;
+        G.alloc_gen++;
         if (cudaMalloc(&g_scratch, need * sizeof(double)) != cudaSuccess) return cudaErrorMemoryAllocation;
-        g_scratch_elems = need;
+        G.gemv_scratch_elems = need;
     }
     gemv_n_partial<T><<<dim3((unsigned)bx, (unsigned)chunks), 256, 0, st>>>((int)rows, (int)cols, A, lda, x, incx, g_scratch, kchunk);
     gemv_n_finish<T><<<(unsigned)bx, 256, 0, st>>>((int)rows, (int)chunks, alpha, g_scratch, beta, y, incy);

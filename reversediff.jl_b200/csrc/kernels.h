@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <vector>
 #include "program.h"
 
 namespace rdb {
@@ -30,6 +31,54 @@ extern thread_local uint64_t g_tag_a, g_tag_b;
 // and serves every panel of a panelled GEMM from it.  rows = the m (A) or n (B) index.  Consumed like the tags.
 struct OperandWindow { const void *full = nullptr; int64_t rows_full = 0, row0 = 0; };
 extern thread_local OperandWindow g_win_a, g_win_b;
+
+// ---- per-context state of the GEMM layer ---------------------------------------------------------------
+// Everything the `*` kernels keep between calls lives here (one per rdb_ctx, i.e. per device + stream), not in process globals:
+// two contexts - two streams, two devices, two host threads - never share a workspace or a cache entry.  The engine points
+// g_gemm at the context's state at every C-ABI entry; code that runs without a context (none in the product) gets a
+// process-wide default instance.
+struct SliceEntry {              // one operand of the int8 path, sliced: [slice][rows][Kp] int8 + per-row scales
+    uint64_t tag;
+    const void *ptr;
+    int64_t ld, rows, K;
+    bool kmajor;
+    int ns, bits;
+    cudaEvent_t ready;           // recorded on the stream that (re)filled the entry; readers on another stream wait for it
+    cudaStream_t filled_on;
+    int8_t *q;
+    double *sc;
+    size_t bytes;
+    uint64_t last_use;
+};
+constexpr int kGuardSlots = 2048;
+struct GuardSummary { unsigned long long checked, flagged; double worst_ratio; double pad; };
+struct GemmState {
+    void *ws = nullptr;          // grow-only workspace of the tcgen05 paths (slices of uncached operands, scales)
+    size_t ws_bytes = 0;
+    double *gemv_scratch = nullptr;
+    size_t gemv_scratch_elems = 0;
+    uint64_t alloc_gen = 0;      // bumped whenever ws / gemv_scratch move: a CUDA graph captured before is stale
+    int *side_e = nullptr;       // exponent scratch of the slicing-ahead stream
+    int64_t side_e_n = 0;
+    std::vector<SliceEntry> cache;
+    uint64_t use = 0;
+    size_t cache_bytes = 0;
+    bool no_cache = false;       // CUDA-graph tapes: every operand is sliced into the workspace on every replay (a cache hit
+                                 // at capture time would freeze stale slices into the graph)
+    // accuracy certificate of the int8-slice path (umma.cu, "guard"): per launch (max |alpha op(A) op(B)|, max error bound)
+    unsigned long long *guard = nullptr;      // device, kGuardSlots x 2 bit patterns of non-negative doubles
+    GuardSummary *guard_sum = nullptr;        // device: accumulated by guard_fold
+    GuardSummary *guard_host = nullptr;       // pinned host copy
+    int guard_used = 0;
+    bool guard_pending = false;               // folded results wait in guard_sum
+    void release();
+};
+extern thread_local GemmState *g_gemm;
+GemmState &gemm_state();                      // *g_gemm, or the process-wide default
+// fold the slots used so far into the summary and reset them (stream-ordered); guard_read copies the summary to the host,
+// synchronises the stream and clears it
+cudaError_t guard_fold(cudaStream_t st, GemmState &G);
+cudaError_t guard_read(cudaStream_t st, GemmState &G, GuardSummary *out);
 
 // FP64 through exact int8 slices on the tcgen05 INT8 pipe (Ozaki scheme); cudaErrorNotSupported when not applicable
 int ozaki_default_slices();

@@ -23,6 +23,23 @@
 namespace rdb {
 thread_local uint64_t g_tag_a = 0, g_tag_b = 0;
 thread_local OperandWindow g_win_a, g_win_b;
+thread_local GemmState *g_gemm = nullptr;
+GemmState &gemm_state() {
+    static GemmState fallback;               // only reached by code that runs outside any context
+    return g_gemm ? *g_gemm : fallback;
+}
+void GemmState::release() {
+    if (ws) cudaFree(ws);
+    if (gemv_scratch) cudaFree(gemv_scratch);
+    if (side_e) cudaFree(side_e);
+    for (auto &en : cache) { if (en.q) cudaFree(en.q); if (en.ready) cudaEventDestroy(en.ready); }
+    cache.clear();
+    if (guard) cudaFree(guard);
+    if (guard_sum) cudaFree(guard_sum);
+    if (guard_host) cudaFreeHost(guard_host);
+    ws = nullptr; gemv_scratch = nullptr; side_e = nullptr; guard = nullptr; guard_sum = nullptr; guard_host = nullptr;
+    ws_bytes = gemv_scratch_elems = 0; side_e_n = 0; cache_bytes = 0; guard_used = 0;
+}
 namespace umma {
 
 constexpr int BM = 128, BN = 256, BKB = 128;          // tile rows / cols / K-bytes per stage (= one 128B swizzle atom)
@@ -282,18 +299,18 @@ static bool make_map(CUtensorMap *map, CUtensorMapDataType dt, int es, void *bas
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// grow-only device workspace (one device per process)
-static void *g_ws = nullptr;
-static size_t g_ws_bytes = 0;
+// grow-only device workspace of the current context (GemmState, kernels.h)
 static void *workspace(size_t bytes) {
-    if (bytes > g_ws_bytes) {
-        if (g_ws) cudaFree(g_ws);
-        g_ws = nullptr;
-        g_ws_bytes = 0;
-        if (cudaMalloc(&g_ws, bytes) != cudaSuccess) return nullptr;
-        g_ws_bytes = bytes;
+    GemmState &G = gemm_state();
+    if (bytes > G.ws_bytes) {
+        if (G.ws) cudaFree(G.ws);
+        G.ws = nullptr;
+        G.ws_bytes = 0;
+        G.alloc_gen++;
+        if (cudaMalloc(&G.ws, bytes) != cudaSuccess) return nullptr;
+        G.ws_bytes = bytes;
     }
-    return g_ws;
+    return G.ws;
 }
 
 // ------------------------------------------------------------------------------------------ 3xTF32 operand split
@@ -390,7 +407,8 @@ __global__ void __launch_bounds__(256) k_row_exponent(const unsigned long long *
     int e = (mx > 0.0 && finite) ? ilogb(mx) + (bits == 8 ? 3 : 2) : 0;
     e_out[r] = e;
     // a row/column holding NaN or Inf gets a NaN scale: every output it touches becomes NaN, as DGEMM would propagate it
-    scale_out[r] = finite ? scalbn(1.0, e) : __longlong_as_double(0x7FF8000000000000LL);
+    // an all-zero row gets scale 0 (its digits are all zero anyway): it then adds nothing to the guard's error bound
+    scale_out[r] = finite ? (mx > 0.0 ? scalbn(1.0, e) : 0.0) : __longlong_as_double(0x7FF8000000000000LL);
 }
 
 // Balanced base-256 digits of four fixed-point values at once (bits == 8).  Adding 0x80 at every digit position below the
@@ -515,7 +533,7 @@ __global__ void __launch_bounds__(128) k_slice_fused_kmajor(int8_t *__restrict__
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     const bool finite = isfinite(mx);
     const int e = (mx > 0.0 && finite) ? ilogb(mx) + (bits == 8 ? 3 : 2) : 0;
-    if (lane == 0) scale_out[r] = finite ? scalbn(1.0, e) : __longlong_as_double(0x7FF8000000000000LL);
+    if (lane == 0) scale_out[r] = finite ? (mx > 0.0 ? scalbn(1.0, e) : 0.0) : __longlong_as_double(0x7FF8000000000000LL);
     const int64_t plane = (int64_t)rows * Kp;
     const int radix = 1 << bits, half = radix >> 1;
     for (int k = 4 * lane; k < Kp; k += 128) {
@@ -606,7 +624,45 @@ struct OzParams {
     int nslices;
     int group_m;                // tile rasterisation group (see raster())
     int bits;                   // bits per digit: slice pair (p, q) weighs 2^(-bits (p + q + 2))
+    // accuracy certificate ("guard"): slot[0] <- max |alpha * (op(A) op(B))(i,j)| as computed, slot[1] <- max over (i,j) of the
+    // rigorous error bound gscale * |alpha| * 2^ea[i] * 2^eb[j], gscale = K * c(bits, S) (guard_coeff); NULL = not recorded
+    unsigned long long *guard;
+    double gscale;
 };
+
+// |x - x~| <= 2^(e - bS - 1) per element (rint), |x| <= 2^e / 4 (b = 8) or 2^e / 2 (b = 7), and the slice pairs with p + q >= S
+// that the kernels drop weigh at most (S-1)/4 * 2^(-bS) per k (digits <= 2^(b-1)); 1 % covers the second-order terms:
+// |(A B)(i,j) - computed| <= K * c * 2^ea[i] * 2^eb[j] + (a few ulps of the computed value, added in guard_fold).
+static double guard_coeff(int bits, int S) {
+    const double rep = (bits == 8 ? 0.5 : 1.0) * ldexp(1.0, -bits * S - 1), drop = 0.25 * (S - 1) * ldexp(1.0, -bits * S);
+    return 1.01 * (rep + drop);
+}
+__device__ __forceinline__ void guard_record(unsigned long long *slot, double gmax, double bmax, double gscale, int lane) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        bmax = fmax(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+    }
+    if (lane == 0) {
+        // bit patterns of non-negative doubles order like unsigned integers; the plain read is only a filter (monotone slot)
+        const unsigned long long g = (unsigned long long)__double_as_longlong(gmax), b = (unsigned long long)__double_as_longlong(bmax * gscale);
+        if (g > *(volatile unsigned long long *)&slot[0]) atomicMax(&slot[0], g);
+        if (b > *(volatile unsigned long long *)&slot[1]) atomicMax(&slot[1], b);
+    }
+}
+// one thread per used slot: flagged when bound + 16 ulp of the value exceeds tau * value, tau = 2^-40 (9.1e-13 < the 1e-12 contract)
+__global__ void k_guard_fold(unsigned long long *slots, int n, GuardSummary *sum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double prod = __longlong_as_double((long long)slots[2 * i]), bnd0 = __longlong_as_double((long long)slots[2 * i + 1]);
+    slots[2 * i] = 0ull; slots[2 * i + 1] = 0ull;
+    atomicAdd(&sum->checked, 1ull);
+    if (!(bnd0 > 0.0)) return;                                  // all-zero operand (scale 0): the product is exactly zero
+    const double bnd = bnd0 + 16.0 * 1.1102230246251565e-16 * prod;
+    const double ratio = prod > 0.0 ? bnd / prod : __longlong_as_double(0x7FF0000000000000LL);
+    if (ratio > 9.094947017729282e-13) atomicAdd(&sum->flagged, 1ull);
+    atomicMax((unsigned long long *)&sum->worst_ratio, (unsigned long long)__double_as_longlong(ratio));
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -756,6 +812,48 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_i8(int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
 }
 
+// Epilogue shared by the gen-2 kernels: the S int32 accumulators of a 128 x 64 tile (TMEM columns d*64 .. d*64+63) are assembled
+// into FP64 in registers, smallest weight first, scaled by alpha * 2^(ea[row] + eb[col]) and written once; the guard's two maxima
+// (OzParams) ride along.  Warp q4 owns TMEM lanes [32 q4, 32 q4 + 32) = tile rows.
+template <int S>
+__device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int lane, int m0, int n0, int M, int N, const OzParams &P) {
+    const int row = m0 + q4 * 32 + lane;
+    const double rs = row < M ? P.alpha * P.sa[row] : 0.0;
+    double gmax = 0.0, bmax = 0.0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN2; c0 += 32) {
+        double sum[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum[j] = 0.0;
+#pragma unroll 1
+        for (int d = S - 1; d >= 0; --d) {                          // smallest terms first
+            uint32_t v[32];
+            tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(d * BN2 + c0), v);
+            const double w = scalbn(1.0, -P.bits * (d + 2));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[j] += (double)(int)v[j] * w;      // exact products, FP64 adds
+        }
+        if (row < M) {
+            double prev[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = n0 + c0 + j;
+                prev[j] = (col < N && P.beta != 0.0) ? P.C[row + (int64_t)col * P.ldc] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = n0 + c0 + j;
+                if (col < N) {
+                    const double w = rs * P.sb[col], term = sum[j] * w;
+                    gmax = fmax(gmax, fabs(term)); bmax = fmax(bmax, fabs(w));
+                    P.C[row + (int64_t)col * P.ldc] = P.beta * prev[j] + term;
+                }
+            }
+        }
+    }
+    if (P.guard) guard_record(P.guard, gmax, bmax, P.gscale, lane);
+}
+
 template <int S, int KB>
 __global__ void __launch_bounds__(THREADS, 1)
 umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, OzParams P) {
@@ -830,38 +928,9 @@ umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             tc_commit(tmem_full);
         }
     } else {
-        const int q4 = warp & 3;
-        const int row = m0 + q4 * 32 + lane;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        const double rs = row < M ? P.alpha * P.sa[row] : 0.0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN2; c0 += 32) {
-            double sum[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sum[j] = 0.0;
-#pragma unroll 1
-            for (int d = S - 1; d >= 0; --d) {                          // smallest terms first
-                uint32_t v[32];
-                tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(d * BN2 + c0), v);
-                const double w = scalbn(1.0, -P.bits * (d + 2));
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sum[j] += (double)(int)v[j] * w;      // exact products, FP64 adds
-            }
-            if (row < M) {
-                double prev[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = n0 + c0 + j;
-                    prev[j] = (col < N && P.beta != 0.0) ? P.C[row + (int64_t)col * P.ldc] : 0.0;
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = n0 + c0 + j;
-                    if (col < N) P.C[row + (int64_t)col * P.ldc] = P.beta * prev[j] + sum[j] * (rs * P.sb[col]);
-                }
-            }
-        }
+        oz2_epilogue<S>(tmem_base, warp & 3, lane, m0, n0, M, N, P);
     }
     tc_fence_before();
     __syncthreads();
@@ -971,38 +1040,9 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
             tc_commit(tmem_full);
         }
     } else {
-        const int q4 = warp & 3;
-        const int row = m0 + q4 * 32 + lane;
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        const double rs = row < M ? P.alpha * P.sa[row] : 0.0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN2; c0 += 32) {
-            double sum[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sum[j] = 0.0;
-#pragma unroll 1
-            for (int d = S - 1; d >= 0; --d) {
-                uint32_t v[32];
-                tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(d * BN2 + c0), v);
-                const double w = scalbn(1.0, -P.bits * (d + 2));
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sum[j] += (double)(int)v[j] * w;
-            }
-            if (row < M) {
-                double prev[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = n0 + c0 + j;
-                    prev[j] = (col < N && P.beta != 0.0) ? P.C[row + (int64_t)col * P.ldc] : 0.0;
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = n0 + c0 + j;
-                    if (col < N) P.C[row + (int64_t)col * P.ldc] = P.beta * prev[j] + sum[j] * (rs * P.sb[col]);
-                }
-            }
-        }
+        oz2_epilogue<S>(tmem_base, warp & 3, lane, m0, n0, M, N, P);
     }
     tc_fence_before();
     __syncthreads();
@@ -1113,24 +1153,28 @@ cudaError_t gemm_f64_ozaki(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t
     return cudaSuccess;
 }
 
+cudaError_t guard_fold(cudaStream_t st, GemmState &G) {
+    if (!G.guard || G.guard_used == 0) return cudaSuccess;
+    umma::k_guard_fold<<<(G.guard_used + 255) / 256, 256, 0, st>>>(G.guard, G.guard_used, G.guard_sum);
+    G.guard_used = 0;
+    G.guard_pending = true;
+    return cudaGetLastError();
+}
+cudaError_t guard_read(cudaStream_t st, GemmState &G, GuardSummary *out) {
+    *out = GuardSummary{0, 0, 0.0, 0.0};
+    if (!G.guard) return cudaSuccess;
+    cudaError_t e = guard_fold(st, G);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(G.guard_host, G.guard_sum, sizeof(GuardSummary), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(G.guard_sum, 0, sizeof(GuardSummary), st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    *out = *G.guard_host;
+    G.guard_pending = false;
+    return cudaSuccess;
+}
+
 // ---- sliced-operand cache: CONST matrices (frozen by `capture`) and value buffers are sliced once per content version and
 // reused by every `*` instruction / adjoint / seed block that reads them (the jacobian! config re-reads A and B for every block).
-struct SliceEntry {
-    uint64_t tag;
-    const void *ptr;
-    int64_t ld, rows, K;
-    bool kmajor;
-    int ns, bits;
-    cudaEvent_t ready;          // recorded on the stream that (re)filled the entry; readers on another stream wait for it
-    cudaStream_t filled_on;
-    int8_t *q;
-    double *sc;
-    size_t bytes;
-    uint64_t last_use;
-};
-static std::vector<SliceEntry> g_cache;
-static uint64_t g_use = 0;
-static size_t g_cache_bytes = 0;
 static size_t cache_cap() {
     static size_t cap = 0;
     if (!cap) { const char *e = getenv("RDB_SLICE_CACHE_MB"); cap = (size_t)(e ? atoll(e) : 8192) << 20; }
@@ -1178,7 +1222,12 @@ static int slice_operand(cudaStream_t st, const double *src, int64_t ld, int64_t
 // returns the slices/scales of one operand; launches = kernels issued (0 on a cache hit)
 static cudaError_t prepare_operand(cudaStream_t st, uint64_t tag, const double *src, int64_t ld, int64_t rows, int64_t K, int64_t Kp,
                                    bool kmajor, int ns, int8_t *ws_q, int *ws_e, double *ws_sc, int8_t **q, double **sc, int *launches) {
-    if (!tag) {
+    GemmState &G = gemm_state();
+    auto &g_cache = G.cache;
+    uint64_t &g_use = G.use;
+    size_t &g_cache_bytes = G.cache_bytes;
+    if (!tag || G.no_cache) {
+        if (!ws_q) { *q = nullptr; *sc = nullptr; *launches = 0; return cudaSuccess; }     // slicing ahead: nothing to do
         *launches = slice_operand(st, src, ld, rows, K, Kp, kmajor, ns, ws_q, ws_e, ws_sc);
         *q = ws_q; *sc = ws_sc;
         return cudaSuccess;
@@ -1241,8 +1290,10 @@ cudaError_t ozaki_preslice(cudaStream_t side, const double *src, int64_t ld, int
     if (nslices <= 0) nslices = ozaki_default_slices();
     const int64_t kmax = (((1 << (33 - 2 * ozaki_bits())) - 1) / nslices) & ~127LL;
     if (K > kmax) return cudaSuccess;
-    static int *side_e = nullptr;
-    static int64_t side_e_n = 0;
+    GemmState &G = gemm_state();
+    if (G.no_cache) return cudaSuccess;
+    int *&side_e = G.side_e;
+    int64_t &side_e_n = G.side_e_n;
     if (rows > side_e_n) {
         if (side_e) cudaFree(side_e);
         side_e = nullptr; side_e_n = 0;
@@ -1264,6 +1315,8 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     if (K * (int64_t)nslices > (1 << (33 - 2 * ozaki_bits())) - 1) return cudaErrorInvalidValue;
     const int64_t Kp = (K + 15) & ~15LL;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    GemmState &G = gemm_state();
+    if (G.no_cache) tag_a = tag_b = 0;         // CUDA-graph tapes: slices always land in the workspace, inside the graph
     if (!tag_a) wa = OperandWindow();
     if (!tag_b) wb = OperandWindow();
     // an operand that is a row window of a larger, tagged operand: slice (or find) the WHOLE operand in the cache and point the
@@ -1305,7 +1358,18 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     CUtensorMap mA, mB;
     static int group_m = -1;
     if (group_m < 0) { const char *e = getenv("RDB_OZAKI_GROUP_M"); group_m = e ? atoi(e) : 8; if (group_m < 1) group_m = 1 << 20; }
-    OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m, ozaki_bits()};
+    // accuracy certificate: one slot per launch; a full table is folded (stream-ordered) and reused
+    if (!G.guard) {
+        if (cudaMalloc((void **)&G.guard, kGuardSlots * 2 * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMalloc((void **)&G.guard_sum, sizeof(GuardSummary)) != cudaSuccess ||
+            cudaMallocHost((void **)&G.guard_host, sizeof(GuardSummary)) != cudaSuccess) return cudaErrorMemoryAllocation;
+        cudaMemsetAsync(G.guard, 0, kGuardSlots * 2 * sizeof(unsigned long long), st);
+        cudaMemsetAsync(G.guard_sum, 0, sizeof(GuardSummary), st);
+        G.guard_used = 0;
+    }
+    if (G.guard_used >= kGuardSlots) { cudaError_t ge = guard_fold(st, G); if (ge != cudaSuccess) return ge; }
+    unsigned long long *gslot = G.guard + 2 * (G.guard_used++);
+    OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m, ozaki_bits(), gslot, (double)K * guard_coeff(ozaki_bits(), nslices)};
     static int gen = -1;
     if (gen < 0) { const char *e = getenv("RDB_OZAKI_GEN"); gen = e ? atoi(e) : 2; }
     if (gen == 2 && nslices <= 8) {

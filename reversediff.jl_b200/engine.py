@@ -46,6 +46,8 @@ def lib():
         "rdb_ctx_set_stream": (i32, [vp, vp]),
         "rdb_ctx_synchronize": (i32, [vp]),
         "rdb_ctx_set_gemm_f64_mode": (i32, [vp, i32, i32]),
+        "rdb_ctx_gemm_guard": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(f64)]),
+        "rdb_tape_guard_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(f64)]),
         "rdb_tape_load": (vp, [vp, vp, C.c_size_t, C.POINTER(_Options)]),
         "rdb_tape_destroy": (None, [vp]),
         "rdb_tape_set_input": (i32, [vp, i32, vp, i32]),
@@ -73,7 +75,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "rdb_version", "rdb_last_error", "rdb_ctx_create", "rdb_ctx_destroy", "rdb_ctx_set_stream",
-    "rdb_ctx_synchronize", "rdb_ctx_set_gemm_f64_mode", "rdb_tape_load", "rdb_tape_destroy", "rdb_tape_set_input", "rdb_forward",
+    "rdb_ctx_synchronize", "rdb_ctx_set_gemm_f64_mode", "rdb_ctx_gemm_guard", "rdb_tape_guard_stats", "rdb_tape_load", "rdb_tape_destroy", "rdb_tape_set_input", "rdb_forward",
     "rdb_reverse_scalar_seed", "rdb_gradient", "rdb_jacobian", "rdb_hessian", "rdb_get_value", "rdb_get_deriv",
     "rdb_buffer_size", "rdb_tape_stats", "rdb_tape_launch_count", "rdb_gemm", "rdb_add_sum", "rdb_plan_col_panels", "rdb_schedule_bundles",
 ]
@@ -87,6 +89,23 @@ def _check(rc):
 
 def _is_device(x):
     return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+def device_array(x, device="cuda"):
+    """numpy array -> CUDA tensor of the SAME shape whose memory is column-major (what the engine reads and writes; the
+    reference's arrays are column-major, src/tracked.jl:77).  A C-contiguous 2-D torch tensor is the TRANSPOSE of that."""
+    import torch
+    a = np.asarray(x)
+    t = torch.from_numpy(np.ascontiguousarray(a.T)).to(device)
+    return t.permute(*reversed(range(t.ndim))) if t.ndim >= 2 else t
+
+
+def _colmajor_strides(shape):
+    st, acc = [], 1
+    for d in shape:
+        st.append(acc)
+        acc *= int(d)
+    return tuple(st)
 
 
 class Context:
@@ -105,6 +124,12 @@ class Context:
 
     def set_gemm_f64_mode(self, mode: int, slices: int = 0):
         _check(lib().rdb_ctx_set_gemm_f64_mode(self.ptr, mode, slices))
+
+    def gemm_guard(self):
+        """(launches checked, launches flagged, worst bound/|product| ratio) of the int8-slice GEMM since the last call."""
+        a, b, w = C.c_int64(0), C.c_int64(0), C.c_double(0.0)
+        _check(lib().rdb_ctx_gemm_guard(self.ptr, C.byref(a), C.byref(b), C.byref(w)))
+        return int(a.value), int(b.value), float(w.value)
 
     def gemm(self, dtype, ta, tb, m, n, k, alpha, A, lda, Bp, ldb, beta, Cp, ldc):
         _check(lib().rdb_gemm(self.ptr, dtype, int(ta), int(tb), m, n, k, alpha, A, lda, Bp, ldb, beta, Cp, ldc))
@@ -156,10 +181,33 @@ class EngineTape:
             raise ValueError(f"input of shape {a.shape} does not match the recorded shape {tuple(shape)}")
         return np.asfortranarray(a)
 
+    def _check_device(self, x, shape, what):
+        """A device tensor crosses the C ABI as a bare pointer: everything the engine assumes about it is checked here.
+        Accepted: a 1-D contiguous tensor holding the column-major linearisation, or an N-D tensor of exactly the recorded
+        shape with column-major strides (``device_array`` makes one; ``t.T`` of a C-contiguous transposed tensor)."""
+        shape = tuple(int(d) for d in shape)
+        n = int(np.prod(shape)) if shape else 1
+        if not x.is_floating_point() or x.element_size() != self.np_dtype.itemsize:
+            raise TypeError(f"{what}: device tensor of dtype {x.dtype} on a {self.np_dtype} tape")
+        if x.device.index is not None and x.device.index != self.ctx.device_id:
+            raise ValueError(f"{what}: tensor lives on cuda:{x.device.index}, the tape's context on cuda:{self.ctx.device_id}")
+        if x.numel() != n:
+            raise ValueError(f"{what}: {x.numel()} elements, expected {n} (shape {shape})")
+        if x.ndim <= 1:
+            if x.ndim == 1 and n > 1 and x.stride(0) != 1:
+                raise ValueError(f"{what}: 1-D device tensors must be contiguous")
+            return
+        want = _colmajor_strides(shape)
+        ok = tuple(x.shape) == shape and all(d == 1 or s == w for d, s, w in zip(shape, x.stride(), want))
+        if not ok:
+            raise ValueError(f"{what}: N-D device tensors must have the recorded shape {shape} and COLUMN-MAJOR strides {want} "
+                             f"(got shape {tuple(x.shape)}, strides {tuple(x.stride())}); a C-contiguous torch matrix is the "
+                             "transpose of what the engine would read - pass engine.device_array(a), m.T of the transposed "
+                             "matrix, or a flat 1-D tensor holding the column-major data")
+
     def set_input(self, slot, x, shape):
         if _is_device(x):
-            if x.numel() != int(np.prod(shape)):
-                raise ValueError("device input has the wrong number of elements")
+            self._check_device(x, shape, f"input {slot}")
             _check(lib().rdb_tape_set_input(self.ptr, slot, C.c_void_p(x.data_ptr()), 1))
         else:
             a = self._host_in(x, shape)
@@ -171,11 +219,19 @@ class EngineTape:
     def reverse_scalar_seed(self):
         _check(lib().rdb_reverse_scalar_seed(self.ptr))
 
-    def _out_array(self, arr, shape):
-        """Return (pointer, is_device, staging) for a result array."""
+    def _out_array(self, arr, shape, ld=None):
+        """Return (pointer, is_device, staging) for a result array.  ``ld`` > rows: ``arr`` is a window into a larger column-major
+        matrix (a rank's row block of the full Jacobian): a flat device tensor that reaches at least to the block's last element."""
         if arr is None:
             return None, 0, None
         if _is_device(arr):
+            if ld is not None and len(shape) == 2 and ld != shape[0]:
+                need = ld * (shape[1] - 1) + shape[0]
+                if arr.ndim != 1 or (arr.numel() > 1 and arr.stride(0) != 1) or arr.numel() < need:
+                    raise ValueError(f"result: a strided block (ld = {ld}) needs a flat contiguous device tensor of >= {need} elements")
+                self._check_device(arr[:1], (1,), "result")
+                return arr.data_ptr(), 1, None
+            self._check_device(arr, shape, "result")
             return arr.data_ptr(), 1, None
         if not isinstance(arr, np.ndarray) or arr.dtype != self.np_dtype:
             raise TypeError(f"result arrays must be numpy arrays of dtype {self.np_dtype}")
@@ -207,7 +263,7 @@ class EngineTape:
         return val[0] if want_value else None
 
     def jacobian(self, slot, row_begin, row_end, result, shape, want_value=False, out_shape=None, ld=None):
-        p, d, st = self._out_array(result, shape)
+        p, d, st = self._out_array(result, shape, ld)
         ld = (row_end - row_begin) if ld is None else ld
         val = None
         vp = None
@@ -219,15 +275,21 @@ class EngineTape:
             result[...] = st.reshape(result.shape, order="F")
         return val
 
-    def hessian(self, col_begin, col_end, result, shape, want_grad=False, ld=None):
+    def hessian(self, col_begin, col_end, result, shape, want_grad=False, ld=None, grad_out=None):
         p, d, st = self._out_array(result, shape)
         n = shape[0]
         ld = n if ld is None else ld
         g = val = None
         gp = vp = None
         if want_grad:
-            g = np.zeros(n, self.np_dtype); val = np.zeros(1, self.np_dtype)
-            gp, vp = g.ctypes.data_as(C.c_void_p), val.ctypes.data_as(C.c_void_p)
+            val = np.zeros(1, self.np_dtype)
+            vp = val.ctypes.data_as(C.c_void_p)
+            if _is_device(grad_out):                      # the gradient goes straight into the caller's device tensor
+                self._check_device(grad_out, (n,), "gradient result")
+                g, gp = grad_out, C.c_void_p(grad_out.data_ptr())
+            else:
+                g = np.zeros(n, self.np_dtype)
+                gp = g.ctypes.data_as(C.c_void_p)
         _check(lib().rdb_hessian(self.ptr, col_begin, col_end, C.c_void_p(p), ld, d, gp, vp))
         if st is not None:
             result[...] = st.reshape(result.shape, order="F")
@@ -253,6 +315,12 @@ class EngineTape:
         buf = C.create_string_buffer(1 << 20)
         _check(lib().rdb_tape_stats(self.ptr, buf, len(buf)))
         return buf.value.decode()
+
+    def guard_stats(self):
+        """dict(checked, flagged, fallbacks, worst_ratio): the int8-slice GEMM's accuracy certificate on this tape since load."""
+        a, b, f, w = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_double(0.0)
+        _check(lib().rdb_tape_guard_stats(self.ptr, C.byref(a), C.byref(b), C.byref(f), C.byref(w)))
+        return {"checked": int(a.value), "flagged": int(b.value), "fallbacks": int(f.value), "worst_ratio": float(w.value)}
 
     def launch_count(self) -> int:
         return int(lib().rdb_tape_launch_count(self.ptr))

@@ -468,7 +468,7 @@ def test_host_arrays_at_panel_sizes(rd, orc, name):
     # the same compiled tape with DEVICE arrays takes none of the routes: results must agree to the last bit (the int8-slice
     # GEMM is exact integer accumulation per element, so cutting it into panels cannot change a single result)
     import torch
-    dev_in = tuple(torch.from_numpy(np.ascontiguousarray(x.T)).cuda() for x in ins)
+    dev_in = tuple(rd.engine.device_array(x) for x in ins)
     dev_out = tuple(torch.empty(n * n, dtype=torch.float64, device="cuda") for _ in ins)
     rd.gradient_(dev_out, ct, dev_in)
     host_out = tuple(np.zeros((n, n), order="F") for _ in ins)
@@ -494,7 +494,7 @@ def test_host_arrays_panels_with_k_chunks(rd, orc):
     ins = (np.asfortranarray(rng.random((m, k)) / k), np.asfortranarray(rng.random((k, n))))
     f = lambda a, b: rd.sum(a @ b)
     ct = run_gradient(rd, orc, f, rec, ins, check_buffers=False)
-    dev_in = tuple(torch.from_numpy(np.ascontiguousarray(x.T)).cuda() for x in ins)
+    dev_in = tuple(rd.engine.device_array(x) for x in ins)
     dev_out = tuple(torch.empty(x.size, dtype=torch.float64, device="cuda") for x in ins)
     rd.gradient_(dev_out, ct, dev_in)
     host_out = tuple(np.zeros(x.shape, order="F") for x in ins)
@@ -511,7 +511,7 @@ def test_host_arrays_at_panel_sizes_f32(rd, orc):
     rec = (rng.random((n, n)).astype(np.float32), rng.random((n, n)).astype(np.float32))
     ins = (np.asfortranarray((rng.random((n, n)) / n).astype(np.float32)), np.asfortranarray(rng.random((n, n)).astype(np.float32)))
     ct = run_gradient(rd, orc, rd.workloads.f_gradient_example, rec, ins, dtype=np.float32, check_buffers=False)
-    dev_in = tuple(torch.from_numpy(np.ascontiguousarray(x.T)).cuda() for x in ins)
+    dev_in = tuple(rd.engine.device_array(x) for x in ins)
     dev_out = tuple(torch.empty(n * n, dtype=torch.float32, device="cuda") for _ in ins)
     rd.gradient_(dev_out, ct, dev_in)
     host_out = tuple(np.zeros((n, n), np.float32, order="F") for _ in ins)
