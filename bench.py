@@ -166,6 +166,26 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms set their BLAS pool to all usable cores themselves so that
+    the reference number does not depend on how the script was launched.  Returns the thread count in effect."""
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except Exception:
+        ncores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=ncores)
+    except Exception:
+        pass
+    return blas_threads()
+
+
+def workload_config(n, dtype):
+    """`config` is identical on both arms (the driver compares them); descriptive extras live in `config_detail`."""
+    return {"workload": f"compiled-tape gradient! of sum(a'*b + a*b') at {n}x{n} {dtype} (BASELINE configs[1])", "n": n}
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -173,21 +193,31 @@ def run_reference(args):
     rd = graft.load_package(); orc = graft.load_oracle()
     npdt = np.float64 if args.dtype == "f64" else np.float32
     n = args.n
+    cores = use_all_host_cores()
     times = cpu_replay(rd, orc, n, npdt, args.warmup + args.steps)[args.warmup:]
     total = float(np.sum(times))
     val = args.steps / total
-    cores = blas_threads()
     line = {
         "impl": "reference", "metric": "gradient! evals/s", "value": val, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"compiled-tape gradient! of sum(a'*b + a*b') at {n}x{n} {args.dtype} (BASELINE configs[1])", "n": n},
+        "config": workload_config(n, args.dtype),
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} full-size evals of the numpy/OpenBLAS oracle (reference-equivalent CPU replay; "
                                    f"Julia is not installed so ReverseDiff.jl itself cannot run), {cores} BLAS threads"},
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def committed_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
+    (profiles/traffic.json names the capture file, the command and the commit it was taken at) - never a literal in this file."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+        return float(rec["dram_bytes_per_launch"]), f"{rec['source']} @ {rec['commit']}"
+    except Exception as e:
+        return None, f"profiles/traffic.json unavailable ({e})"
 
 
 def measure_blas_peak(torch, n, tdt):
@@ -341,13 +371,13 @@ def main():
         peak_src = (f"2 x {peak_tag} (kind::i8 issues at twice the bf16 rate; nominal dense 4500); cuBLASLt int8 GEMM 8192^3 "
                     f"(torch._int_mm) measured in this run = {i8:.0f}" if i8 else
                     f"2 x {peak_tag} (kind::i8 issues at twice the bf16 rate; nominal dense 4500); torch._int_mm unavailable")
-        traffic = 1.0387e9 + 0.1262e9   # dram__bytes_read+write per 4096^3 launch, ncu --set full (profiles/prof_ozaki2c_r1c.txt)
+        traffic, traffic_src = committed_traffic("int8")
     elif args.dtype == "f64":
         ops_per_flop = 1.0
         kernel = "d64::dgemm_dmma_kernel (mma.sync m8n8k4 f64 = SASS DMMA.8x8x4)"
         unit, pipe_peak = "TFLOP/s (fp64)", blas_peak
         peak_src = "cuBLAS DGEMM measured in this run (MEASURED_PEAKS.json holds no FP64 figure)"
-        traffic = 1.084e9 + 0.121e9     # profiles/prof_dgemm_r1.txt
+        traffic, traffic_src = committed_traffic("dmma")
     else:
         ops_per_flop = 3.0
         kernel = "umma::umma_gemm_kernel<tf32> (TMA + tcgen05.mma kind::tf32, 3xTF32 split) + k_split_tf32"
@@ -365,11 +395,11 @@ def main():
         else:
             pipe_peak = 0.5 * bf16_peak
             peak_src = f"0.5 x {peak_tag} (tf32 issues at half the bf16 rate)"
-        traffic = None
+        traffic, traffic_src = None, None
     achieved = fp_equiv * ops_per_flop
     roofline = {
         "bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": pipe_peak, "unit": unit, "frac": achieved / pipe_peak,
-        "traffic": traffic, "peak_source": peak_src,
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "note": "achieved = tensor-pipe operations actually issued (algorithmic 2mnk x ops_per_flop) / CUDA-event time of the `*` "
                 "steps INCLUDING their operand slicing passes",
         "ops_per_algorithmic_flop": ops_per_flop,
@@ -396,8 +426,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         orc = graft.load_oracle()
+        cores = use_all_host_cores()
         times = cpu_replay(rd, orc, n, npdt, 2)
-        cores = blas_threads()
         cpu = {"value": 1.0 / min(times), "unit": "evals/s", "cores": cores, "kind": "port",
                "sample": f"2 full-size evals ({n}x{n} {args.dtype}) of the numpy/OpenBLAS oracle, best taken; "
                          f"{cores} BLAS threads of {os.cpu_count()} host cores"}
@@ -405,21 +435,24 @@ def main():
     extra = {}
     if not args.skip_extra:
         extra = sharded_legs(args, torch, dist, rd, ctx, rank, world)
+        if rank == 0 and world == 1:
+            extra["other_configs"] = other_configs(args, torch, rd, ctx)
 
     if rank == 0:
         line = {
             "metric": "gradient! evals/s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"compiled-tape gradient! of sum(a'*b + a*b') at {n}x{n} {args.dtype} (BASELINE configs[1])",
-                       "n": n, "tape": "*(IDX a', b) ; *(a, IDX b') ; + ; sum", "flops_per_eval": 12.0 * n ** 3, "gemm_kernels": args.gemm,
-                       "l2": "working set (8 x %d MB) larger than the 126 MB L2" % (n * n * es // 2 ** 20),
-                       "multi_gpu": "replicas only (a scalar function's gradient does not shard)" if world > 1 else "single GPU"},
+            "config": workload_config(n, args.dtype),
+            "config_detail": {"tape": "*(IDX a', b) ; *(a, IDX b') ; + ; sum", "flops_per_eval": 12.0 * n ** 3, "gemm_kernels": args.gemm,
+                              "l2": "working set (8 x %d MB) larger than the 126 MB L2" % (n * n * es // 2 ** 20),
+                              "multi_gpu": "replicas only (a scalar function's gradient does not shard)" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": 2 * n * n * es, "d2h_bytes_per_step": 2 * n * n * es + es,
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": int(l_per_step * args.steps),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "parity": {"max_rel_err_vs_closed_form": float(err), "tol": tol},
+            "gemm_guard": ct.handle.guard_stats(),
         }
         line.update(extra)
         print(json.dumps(line), flush=True)
@@ -429,10 +462,60 @@ def main():
     _ = keep
 
 
+def adaptive_steps(torch, step, min_steps=10, min_seconds=0.25, cap=2000):
+    """enough timed steps for >= min_seconds of device time (the hessian! shard of one rank is tens of microseconds)"""
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); step(); e1.record(); torch.cuda.synchronize()
+    est = max(e0.elapsed_time(e1), 1e-3)
+    return int(min(cap, max(min_steps, np.ceil(min_seconds * 1e3 / est))))
+
+
+def agree_steps(torch, dist, world, k):
+    if world > 1:
+        t = torch.tensor([k], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        k = int(t.item())
+    return k
+
+
+def timed_once(torch, dist, world, fn, reps=3):
+    """best of `reps` single calls, CUDA events, max over ranks (ms) - for the collectives"""
+    best = 1e30
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        best = min(best, ms)
+    return best
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
 def sharded_legs(args, torch, dist, rd, ctx, rank, world):
-    """jacobian! rows and hessian! columns sharded over the ranks, results left sharded in device memory
-    (SURVEY.md §8e); the all-gather of the result blocks is timed separately."""
+    """jacobian! rows and hessian! columns sharded over the ranks: every rank replays its own tape copy over
+    its shard, no collective on the data path; results are left sharded in device memory for the timed region, and the product's
+    own gather (rdb_gather_result: NCCL inside librdb200.so, blocks placed into the reference's column-major result) is timed
+    separately."""
     out = {}
+    peaks = load_peaks()
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    bf16_peak = peaks.get("bf16_tflops", 1590.0)
+    comm = rd.make_comm(ctx) if world > 1 else None
     # ---- jacobian!: f(x) = (A*x + x) .* tanh.(B*x), output-seed rows [rank*m/G, (rank+1)*m/G)
     n = args.jac_n
     A, B, x0 = rd.workloads.inputs_jacobian(n, seed=1)
@@ -440,28 +523,42 @@ def sharded_legs(args, torch, dist, rd, ctx, rank, world):
     ct = rd.compile(tape, ctx=ctx)
     _, _, x = rd.workloads.inputs_jacobian(n, seed=2)
     x_d = torch.from_numpy(x).cuda()
-    rows = n // world
     rb, re = rd.shard_range(n, world, rank)
     J_d = torch.empty((re - rb) * n, dtype=torch.float64, device="cuda")
 
     def step():
         rd.jacobian_(J_d, ct, x_d, rows=(rb, re))
-    ms = timed_steps(torch, dist, world, step, 3, 2)
-    full = torch.empty(world * rows * n, dtype=torch.float64, device="cuda") if (n % world == 0 and world > 1) else None
+    k = agree_steps(torch, dist, world, adaptive_steps(torch, step))
+    ms = timed_steps(torch, dist, world, step, k, 3)
+    per = ms / k
     gather_ms = None
-    if full is not None:
-        torch.cuda.synchronize(); dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); dist.all_gather_into_tensor(full, J_d); e1.record(); torch.cuda.synchronize()
-        gather_ms = e0.elapsed_time(e1)
-    out["jacobian"] = {"metric": "jacobian! rows/s", "value": n * 3 / (ms * 1e-3), "unit": "rows/s", "n": n, "ms_per_jacobian": ms / 3,
-                       "rows_per_rank": rows, "result": "left sharded in device memory", "allgather_ms": gather_ms}
-    del ct, J_d, full
+    if comm is not None:
+        full = torch.empty(n * n, dtype=torch.float64, device="cuda")
+        gather_ms = timed_once(torch, dist, world, lambda: rd.gather_jacobian_(full, J_d, ct, comm))
+        # the gathered matrix IS the reference's result layout: spot-check rank 0's copy against the closed form
+        if rank == 0:
+            s_ = A @ x + x; t_ = np.tanh(B @ x)
+            rows_chk = np.array([0, n // 3, n - 1])
+            Jrows = full.reshape(n, n).T[torch.from_numpy(rows_chk).cuda()].cpu().numpy()
+            Jcf = t_[rows_chk, None] * (A[rows_chk] + np.eye(n)[rows_chk]) + (s_ * (1 - t_ ** 2))[rows_chk, None] * B[rows_chk]
+            assert np.max(np.abs(Jrows - Jcf)) < 1e-12 * np.max(np.abs(Jcf)), "gathered Jacobian does not match the closed form"
+        del full
+    flops_row = 4.0 * n * n                                     # two adjoint GEMV-columns per seed row
+    tf_equiv = flops_row * n / (per * 1e-3) / 1e12              # whole job: all n rows per `per` ms
+    out["jacobian"] = {"metric": "jacobian! rows/s", "value": n / (per * 1e-3), "unit": "rows/s", "n": n, "ms_per_jacobian": per,
+                       "timed_steps": k, "rows_per_rank": re - rb, "result": "left sharded in device memory for the timed region",
+                       "gather_ms": gather_ms, "gather": "rdb_gather_result (NCCL broadcasts + block placement into the column-major m x n result)",
+                       "roofline": {"bound": "tensor", "algorithmic_flops_per_row": flops_row, "achieved_fp64_equiv_tflops_per_gpu": tf_equiv / world,
+                                    "achieved": tf_equiv / world * 28.0, "peak": 2.0 * bf16_peak, "unit": "TOP/s (int8)",
+                                    "frac": tf_equiv / world * 28.0 / (2.0 * bf16_peak),
+                                    "note": "28 int8 slice products per FP64 product (7 slices of 8 bits); includes the replicated forward "
+                                            "sweep, seeding, elementwise adjoints and row extraction of every block"},
+                       "gemm_guard": ct.handle.guard_stats()}
+    del ct, J_d
     # ---- hessian!: extended Rosenbrock, column chunks
     for key, n in (("hessian", args.hess_n), ("hessian_large", args.hess_large_n)):
         if n <= 0:
             continue
-        cols = n // world
         cb, ce = rd.shard_range(n, world, rank)
         need = n * (ce - cb) * 8
         free, _total = torch.cuda.mem_get_info()
@@ -479,12 +576,94 @@ def sharded_legs(args, torch, dist, rd, ctx, rank, world):
 
         def hstep():
             rd.hessian_(H_d, ct, x_d, cols=(cb, ce))
-        ms = timed_steps(torch, dist, world, hstep, 3, 3)
-        out[key] = {"metric": "hessian! rows/s", "value": n * 3 / (ms * 1e-3), "unit": "rows/s", "n": n, "ms_per_hessian": ms / 3,
-                    "cols_per_rank": cols, "result": "left sharded in device memory",
-                    "result_write_GBps_per_gpu": n * (ce - cb) * 8 / (ms / 3 * 1e-3) / 1e9}
+        k = agree_steps(torch, dist, world, adaptive_steps(torch, hstep))
+        ms = timed_steps(torch, dist, world, hstep, k, 3)
+        per = ms / k
+        gather_ms = None
+        if comm is not None and key == "hessian":
+            full = torch.empty(n * n, dtype=torch.float64, device="cuda")
+            gather_ms = timed_once(torch, dist, world, lambda: rd.gather_hessian_(full, H_d, ct, comm))
+            del full
+        gbps = n * (ce - cb) * 8 / (per * 1e-3) / 1e9
+        out[key] = {"metric": "hessian! rows/s", "value": n / (per * 1e-3), "unit": "rows/s", "n": n, "ms_per_hessian": per,
+                    "timed_steps": k, "cols_per_rank": ce - cb, "result": "left sharded in device memory for the timed region",
+                    "gather_ms": gather_ms,
+                    "roofline": {"bound": "hbm", "algorithmic_bytes_per_row": n * 8, "achieved": gbps, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": gbps / hbm_peak, "note": "per GPU: the dense n x cols result block is the traffic (SURVEY section 8d)"}}
         del ct, H_d, x_d, hctx
         torch.cuda.empty_cache()
+    if comm is not None:
+        comm.close()
+    return out
+
+
+def other_configs(args, torch, rd, ctx):
+    """The BASELINE configs that are not the headline, one short measurement each (rank 0, N = 1), so the driver's record holds
+    them: cfg 1 (100 x 100, the only size the reference publishes a number for), cfg 2 in FP32, cfg 3 (MLP)."""
+    out = {}
+
+    def timeit(step, steps, warm=3):
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+    # cfg 1: 100 x 100 FP64, host arrays through the public call (wall clock, synchronous calls): README reports 429.65 us
+    n = 100
+    rng = np.random.default_rng(1)
+    c1ctx = rd.engine.Context(torch.cuda.current_device())        # own stream: the sweep replays as one CUDA graph
+    ct = rd.compile(rd.GradientTape(rd.workloads.f_gradient_example, (rng.random((n, n)), rng.random((n, n)))), ctx=c1ctx)
+    a, b = rd.workloads.inputs_gradient_example(n)
+    res = (np.zeros((n, n), order="F"), np.zeros((n, n), order="F"))
+    for _ in range(20):
+        rd.gradient_(res, ct, (a, b))
+    t0 = time.perf_counter()
+    for _ in range(500):
+        rd.gradient_(res, ct, (a, b))
+    us = (time.perf_counter() - t0) / 500 * 1e6
+    ok = np.max(np.abs(res[0] - (b.sum(1)[:, None] + b.sum(0)[None, :]))) < 1e-12 * np.max(np.abs(res[0]))
+    out["cfg1_100x100_f64"] = {"us_per_gradient_host_arrays_wall_clock": us, "evals_per_s": 1e6 / us, "reference_readme_us": 429.65,
+                               "vs_readme": 429.65 / us, "parity_ok": bool(ok),
+                               "note": "README.md timing is of unknown CPU hardware (BASELINE.md); includes the Python binding"}
+    del ct, c1ctx
+    # cfg 2 in FP32 (3xTF32 on tcgen05)
+    n = args.n
+    a0 = np.asfortranarray(rng.random((n, n)).astype(np.float32)); b0 = np.asfortranarray(rng.random((n, n)).astype(np.float32))
+    ct = rd.compile(rd.GradientTape(rd.workloads.f_gradient_example, (a0, b0), dtype=np.float32), ctx=ctx)
+    a, b = rd.workloads.inputs_gradient_example(n, np.float32)
+    ad, bd = rd.engine.device_array(a), rd.engine.device_array(b)
+    ga = torch.empty(n * n, dtype=torch.float32, device="cuda"); gb = torch.empty_like(ga)
+    ms = timeit(lambda: rd.gradient_((ga, gb), ct, (ad, bd)), 10)
+    b64 = b.astype(np.float64)
+    ref = b64.sum(1)[:, None] + b64.sum(0)[None, :]
+    err = float(np.max(np.abs(ga.cpu().numpy().reshape(n, n, order="F") - ref)) / np.max(np.abs(ref)))
+    out["cfg2_f32"] = {"evals_per_s": 1e3 / ms, "ms_per_eval": ms, "fp32_equiv_tflops": 12.0 * n ** 3 / ms / 1e9, "max_rel_err_vs_closed_form": err, "tol": 1e-5}
+    del ct, ga, gb, ad, bd
+    # cfg 3: MLP, X 1024 x 65536 frozen in the tape
+    d = h = o = 1024; N = 65536
+    X, rec = rd.workloads.inputs_mlp(d, h, o, N, seed=1)
+    tape = rd.GradientTape(rd.workloads.make_f_mlp(X), rec)
+    ct = rd.compile(tape, ctx=ctx)
+    _, ws = rd.workloads.inputs_mlp(d, h, o, N, seed=2)
+    wd = [rd.engine.device_array(w) for w in ws]
+    gs = [torch.empty(w.size, dtype=torch.float64, device="cuda") for w in ws]
+    ms = timeit(lambda: rd.gradient_(tuple(gs), ct, tuple(wd)), 5)
+    Xd = torch.from_numpy(X).cuda(); W1, b1, W2, b2 = [torch.from_numpy(np.ascontiguousarray(w)).cuda() for w in ws]
+    Hh = torch.tanh(W1 @ Xd + b1[:, None]); Y = torch.tanh(W2 @ Hh + b2[:, None])
+    dZ2 = 1 - Y * Y; dZ1 = (W2.T @ dZ2) * (1 - Hh * Hh)
+    refs = [dZ1 @ Xd.T, dZ1.sum(1), dZ2 @ Hh.T, dZ2.sum(1)]
+    errs = []
+    for g, r, w in zip(gs, refs, ws):
+        gg = g.reshape(w.shape[::-1]).T if w.ndim == 2 else g
+        errs.append(float((gg - r).abs().max() / r.abs().max()))
+    S = h * N
+    out["cfg3_mlp_f64"] = {"evals_per_s": 1e3 / ms, "ms_per_eval": ms, "gemm_flops_per_eval": 10.0 * 1024 ** 2 * N,
+                           "elementwise_bytes_algorithmic": 14 * S * 8, "max_rel_err_vs_torch_fp64_backprop": max(errs), "tol": 1e-12,
+                           "gemm_guard": ct.handle.guard_stats()}
     return out
 
 

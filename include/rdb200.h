@@ -36,6 +36,7 @@ extern "C" {
 
 typedef struct rdb_ctx rdb_ctx;
 typedef struct rdb_tape rdb_tape;
+typedef struct rdb_comm rdb_comm;
 
 typedef struct rdb_options {
     int32_t fuse_elementwise; /* 1 = fuse runs of adjacent elementwise instructions (default 1)     */
@@ -126,6 +127,31 @@ int rdb_tape_stats(rdb_tape *, char *json, size_t cap);
 int rdb_tape_guard_stats(rdb_tape *, int64_t *checked, int64_t *flagged, int64_t *fallbacks, double *worst_ratio);
 /* Number of kernel launches issued by the engine on this tape since load (bench "gpu_launches"). */
 int64_t rdb_tape_launch_count(rdb_tape *);
+
+/* ---- multi-GPU result assembly (one process per GPU) -------------------------------- */
+/* jacobian! shards by output-seed rows and hessian! by columns; every rank replays its own tape copy and calls
+ * rdb_jacobian(row_begin, row_end) / rdb_hessian(col_begin, col_end) into a device block of its own - no collective on the data
+ * path.  The only exchange is the gather of those blocks into the reference's result: the column-major
+ * length(output) x length(input) matrix `result_matrix` of seeded_reverse_pass! (src/api/utils.jl:44-58), resp. the n x n Hessian
+ * (src/api/hessians.jl:86-90).  Blocks travel over NCCL (NVLink / NVSwitch), reached through dlopen("libnccl.so.2").
+ *
+ * rdb_comm_unique_id: rank 0 obtains RDB_COMM_ID_BYTES bytes (ncclGetUniqueId) and the HOST distributes them to the other ranks
+ * (MPI.jl, torch.distributed, a shared file - the engine has no bootstrap of its own); then every rank calls rdb_comm_create. */
+#define RDB_COMM_ID_BYTES 128
+int rdb_comm_unique_id(void *id);
+rdb_comm *rdb_comm_create(rdb_ctx *, int world, int rank, const void *id);
+void rdb_comm_destroy(rdb_comm *);
+/* kind 0: rank r holds rows [bounds[r], bounds[r+1]) of a column-major (bounds[world] x other_dim) matrix as a contiguous
+ *         (rows_r x other_dim) device block (what rdb_jacobian writes with ld = rows_r); result has leading dimension bounds[world].
+ * kind 1: rank r holds columns [bounds[r], bounds[r+1]) of a column-major (other_dim x bounds[world]) matrix (what rdb_hessian
+ *         writes with ld = other_dim).
+ * bounds (world + 1 entries, the same on every rank) need not be even.  root = -1: every rank receives the full matrix in `result`
+ * (device memory); root >= 0: only that rank does (`result` may be NULL elsewhere).  Collective; synchronous on return. */
+int rdb_gather_result(rdb_comm *, int dtype, int kind, const void *block, const int64_t *bounds, int64_t other_dim, void *result,
+                      int root);
+/* The same placement for ONE block in HOST memory (no device, no communicator): for callers that moved the blocks with a
+ * transport of their own, and for the CPU test of the N > 1 host logic.  result is the full m x n column-major matrix. */
+int rdb_place_block(int dtype, int kind, const void *block, int64_t begin, int64_t end, int64_t m, int64_t n, void *result);
 
 /* ---- single-kernel entry points (kernel tests and per-kernel roofline measurement) ----------------- */
 /* C <- alpha*op(A)*op(B) + beta*C, column-major device pointers; the kernel behind every `*` instruction

@@ -324,4 +324,39 @@ def hessian(ct: CompiledTape, input_):
     return hessian_(np.zeros((n, n), ct.dtype, order="F"), ct, input_)
 
 
+# --------------------------------------------------------------------------------------------- multi-GPU
+def shard_bounds(n: int, world: int):
+    """``world + 1`` offsets of the partition ``shard_range`` induces (identical on every rank)."""
+    return [shard_range(n, world, r)[0] for r in range(world)] + [n]
+
+
+def make_comm(ctx=None):
+    """One ``rdb_comm`` per process.  The engine has no bootstrap of its own: rank 0's NCCL id travels through the host's
+    ``torch.distributed`` group (any backend; Julia would use MPI.jl), after that all traffic is NCCL inside librdb200."""
+    import torch.distributed as dist
+    ctx = ctx if ctx is not None else _engine.default_context()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    box = [_engine.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return _engine.Comm(ctx, world, rank, box[0])
+
+
+def gather_jacobian_(result, block, ct: CompiledTape, comm, slot=0, root=-1):
+    """Place every rank's ``jacobian_(block, ct, x, rows=shard_range(m, world, rank))`` block into the reference's result: the
+    column-major ``length(output) x length(input)`` matrix (``result_matrix``, ``api/utils.jl:44-58``), on every rank
+    (``root=-1``) or on ``root``.  ``block`` and ``result`` are flat device tensors."""
+    m, n = ct.tape.output.size, ct.tape.input[slot].size
+    comm.gather(ct.dtype, 0, block, shard_bounds(m, comm.world), n, result, root)
+    return result
+
+
+def gather_hessian_(result, block, ct: CompiledTape, comm, root=-1):
+    """Same for ``hessian_(block, ct, x, cols=shard_range(n, world, rank))`` column blocks (contiguous in the column-major
+    Hessian, ``api/hessians.jl:86-90``); a reverse-mode (reference-style) tape shards by rows like ``jacobian!``."""
+    n = ct.tape.input[0].size
+    kind = 0 if getattr(ct.tape, "mode", "forward") == "reverse" else 1
+    comm.gather(ct.dtype, kind, block, shard_bounds(n, comm.world), n, result, root)
+    return result
+
+
 _ = value

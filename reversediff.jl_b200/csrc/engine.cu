@@ -35,6 +35,14 @@ static int fail(int code, const char *fmt, ...) {
     va_end(ap);
     return code;
 }
+// for the other translation units of the library (comm.cu)
+int rdb_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
 #define CU(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e__ = (call);                                                                        \
@@ -62,6 +70,8 @@ struct rdb_ctx {
     cudaEvent_t side_ev = nullptr;
     GemmState gemm;                            // workspace, sliced-operand cache, accuracy-certificate slots of the `*` kernels
 };
+cudaStream_t rdb_ctx_stream(rdb_ctx *c) { return c->stream; }
+int rdb_ctx_device(rdb_ctx *c) { return c->device; }
 // every C-ABI entry: the calling thread works on this context's device with this context's GEMM state
 static void ctx_enter(rdb_ctx *c) {
     cudaSetDevice(c->device);

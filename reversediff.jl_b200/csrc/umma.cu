@@ -146,6 +146,11 @@ struct EpiF32 {           // C = alpha*acc + beta*C   (FP32, column-major)
     __device__ __forceinline__ void store(int row, int col, uint32_t raw, float prev) const {
         C[row + (int64_t)col * ldc] = alpha * __uint_as_float(raw) + beta * prev;
     }
+    // later K-chunks of the same tile: C += alpha*acc (round-to-nearest FP32 adds, see umma_gemm_kernel)
+    __device__ __forceinline__ float reload(int row, int col) const { return C[row + (int64_t)col * ldc]; }
+    __device__ __forceinline__ void accumulate(int row, int col, uint32_t raw, float prev) const {
+        C[row + (int64_t)col * ldc] = prev + alpha * __uint_as_float(raw);
+    }
 };
 // ------------------------------------------------------------------------------------------ the kernel
 // Tile rasterisation: CTAs are dispatched in linear block order (x fastest).  With x = m-tile a wave of 148 CTAs touched every
@@ -161,6 +166,19 @@ __device__ __forceinline__ void raster(int cid, int tiles_m, int tiles_n, int GR
     n_tile = in_group / gsz;
 }
 
+__device__ __forceinline__ void mbar_arrive1(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// The tensor core ACCUMULATES with truncation, not round-to-nearest: every tcgen05.mma step shrinks |accumulator| by up to an
+// ulp, a BIAS that grows linearly with the number of steps chained into one accumulator (measured on B200, all-positive data:
+// -2.7e-6 relative at K = 1024, -1.3e-5 at 4096, -5.4e-5 at 16384 - profiles/README.md; the FP32 contract is 1e-5).  So a chain
+// is never longer than one K-CHUNK of KCHUNK_BLOCKS stages (512 elements x 3 segments = 192 steps): the two TMEM accumulators
+// take alternate chunks, and the epilogue warps drain a finished chunk into C with round-to-nearest FP32 adds
+// (C = alpha*acc + beta*C for the first chunk, C += alpha*acc afterwards; the tile stays in L2 between its chunks) while the
+// MMA warp is already filling the other accumulator.  The error then no longer depends on K (~3e-6 worst case).
+constexpr int KCHUNK_BLOCKS = 16;
+
 template <int KIND, typename Epi>
 __global__ void __launch_bounds__(THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
@@ -171,8 +189,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t *sB = smem + STAGES * A_STAGE;
     uint64_t *full = (uint64_t *)(smem + STAGES * (A_STAGE + B_STAGE));
     uint64_t *empty = full + STAGES;
-    uint64_t *tmem_full = empty + STAGES;
-    uint32_t *tmem_ptr = (uint32_t *)(tmem_full + 1);
+    uint64_t *tmem_full = empty + STAGES;      // [2]
+    uint64_t *tmem_empty = tmem_full + 2;      // [2]
+    uint32_t *tmem_ptr = (uint32_t *)(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int m_tile, n_tile;
@@ -181,16 +200,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int ELEMS = KIND == KIND_TF32 ? BKB / 4 : BKB;      // K elements per stage
     constexpr int KSTEP = KIND == KIND_TF32 ? 8 : 32;              // K elements per tcgen05.mma (32 bytes)
     const int kblocks = (K + ELEMS - 1) / ELEMS;
-    const int total = segs.n * kblocks;
+    const int chunks = (kblocks + KCHUNK_BLOCKS - 1) / KCHUNK_BLOCKS;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // two accumulators (2 x 256 TMEM columns): K-blocks alternate between them and the epilogue adds the halves in FP32 RN.
-    // The tensor core's FP32 accumulation truncates; halving the length of each sequential chain halves that bias
-    // (4096-term all-positive dot products: 5.4e-6 -> 2.7e-6 relative, against the 1e-5 bound).
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(2 * TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -202,64 +218,78 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int it = 0; it < total; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], A_STAGE + B_STAGE);
-                const int seg = it / kblocks, kb = it - seg * kblocks;
-                tma_load_3d(sA + s * A_STAGE, &tmA, &full[s], kb * ELEMS, m0, segs.sa[seg]);
-                tma_load_3d(sB + s * B_STAGE, &tmB, &full[s], kb * ELEMS, n0, segs.sb[seg]);
+            int it = 0;
+            for (int c = 0; c < chunks; ++c) {
+                const int kb0 = c * KCHUNK_BLOCKS, kb1 = min(kblocks, kb0 + KCHUNK_BLOCKS);
+                for (int seg = 0; seg < segs.n; ++seg)
+                    for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_expect_tx(&full[s], A_STAGE + B_STAGE);
+                        tma_load_3d(sA + s * A_STAGE, &tmA, &full[s], kb * ELEMS, m0, segs.sa[seg]);
+                        tma_load_3d(sB + s * B_STAGE, &tmB, &full[s], kb * ELEMS, n0, segs.sb[seg]);
+                    }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc<KIND>();
-            for (int it = 0; it < total; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&full[s], ph);
+            int it = 0;
+            for (int c = 0; c < chunks; ++c) {
+                const int buf = c & 1;
+                mbar_wait(&tmem_empty[buf], ((c >> 1) & 1) ^ 1);          // the epilogue drained this accumulator
                 tc_fence_after();
-                const uint64_t ad = make_smem_desc(smem_u32(sA + s * A_STAGE));
-                const uint64_t bd = make_smem_desc(smem_u32(sB + s * B_STAGE));
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                const int kb0 = c * KCHUNK_BLOCKS, kb1 = min(kblocks, kb0 + KCHUNK_BLOCKS);
+                const int iters = segs.n * (kb1 - kb0);
+                for (int j = 0; j < iters; ++j, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint64_t ad = make_smem_desc(smem_u32(sA + s * A_STAGE));
+                    const uint64_t bd = make_smem_desc(smem_u32(sB + s * B_STAGE));
 #pragma unroll
-                for (int k = 0; k < ELEMS / KSTEP; ++k) {
-                    // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                    tc_mma<KIND>(tmem_base + (uint32_t)((it & 1) * BN), ad + 2 * k, bd + 2 * k, idesc, (it > 1 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < ELEMS / KSTEP; ++k) {
+                        // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                        tc_mma<KIND>(acc, ad + 2 * k, bd + 2 * k, idesc, (j > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty[s]);            // frees the smem stage when these MMAs retire
                 }
-                tc_commit(&empty[s]);            // frees the smem stage when these MMAs retire
+                tc_commit(&tmem_full[buf]);          // this chunk's accumulator is complete
             }
-            tc_commit(tmem_full);                // accumulator complete
         }
     } else {
         // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
         const int q = warp & 3;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
         const int row = m0 + q * 32 + lane;
+        for (int c = 0; c < chunks; ++c) {
+            const int buf = c & 1;
+            mbar_wait(&tmem_full[buf], (c >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32], v1[32];
-            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (total > 1) {
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c0), v1);
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+                if (row < M) {
+                    // all 32 loads of the old C are issued before the first store (a load->store->load chain cost ~0.4 ms per GEMM)
+                    typename Epi::prev_t prev[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v1[j]));
-            }
-            if (row < M) {
-                // all 32 loads of the old C are issued before the first store (a load->store->load chain cost ~0.4 ms per GEMM)
-                typename Epi::prev_t prev[32];
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = n0 + c0 + j;
+                        if (col < N) prev[j] = c == 0 ? epi.load(row, col) : epi.reload(row, col);
+                    }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = n0 + c0 + j;
-                    if (col < N) prev[j] = epi.load(row, col);
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = n0 + c0 + j;
-                    if (col < N) epi.store(row, col, v[j], prev[j]);
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = n0 + c0 + j;
+                        if (col < N) { if (c == 0) epi.store(row, col, v[j], prev[j]); else epi.accumulate(row, col, v[j], prev[j]); }
+                    }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(&tmem_empty[buf]);
         }
     }
     tc_fence_before();
@@ -373,27 +403,43 @@ constexpr int OZ_MAX_SLICES = 8;    // 7*8 = 56 fixed-point bits fit an int64 wi
 
 // ---- pass 1: per-row max |x| (bit pattern of a non-negative double orders like an unsigned integer), then the binary
 // exponent e = ilogb(max) + 2 (so |x| 2^-e <= 0.5) and the scale 2^e
+// The same pass also takes the row's 1-norm and its number of non-zero elements: the accuracy certificate (guard) bounds the
+// error of element (i,j) through them instead of through K * max, which keeps it sharp for sparse operands (the one-hot seed
+// matrices of jacobian!) and for rows dominated by a few large elements.  stats = [max bits | 1-norm | nnz], `rows` apart.
 template <bool KMAJOR>
 __global__ void __launch_bounds__(256) k_row_absmax(const double *__restrict__ src, int64_t ld, int rows, int K,
                                                     unsigned long long *__restrict__ mx_bits) {
+    double *l1 = reinterpret_cast<double *>(mx_bits) + rows, *nz = l1 + rows;
     if (KMAJOR) {                               // one warp per row, k contiguous
         int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
         if (r >= rows) return;
         const double *p = src + (int64_t)r * ld;
-        double mx = 0.0;
+        double mx = 0.0, s1 = 0.0, cnt = 0.0;
         // NaN/Inf anywhere in the row poisons the row: fmax() would silently drop a NaN, so non-finite elements count as +Inf
-        for (int k = lane; k < K; k += 32) { double v = fabs(p[k]); mx = fmax(mx, v <= 1.7976931348623157e308 ? v : __longlong_as_double(0x7FF0000000000000LL)); }
+        for (int k = lane; k < K; k += 32) {
+            double v = fabs(p[k]);
+            mx = fmax(mx, v <= 1.7976931348623157e308 ? v : __longlong_as_double(0x7FF0000000000000LL));
+            s1 += v; cnt += v != 0.0 ? 1.0 : 0.0;
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) mx_bits[r] = (unsigned long long)__double_as_longlong(mx);
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if (lane == 0) { mx_bits[r] = (unsigned long long)__double_as_longlong(mx); l1[r] = s1; nz[r] = cnt; }
     } else {                                    // threads along rows (coalesced), blockIdx.y splits K into chunks of 64
         int r = blockIdx.x * 256 + threadIdx.x;
         if (r >= rows) return;
         int k0 = blockIdx.y * 64, k1 = min(K, k0 + 64);
-        double mx = 0.0;
+        double mx = 0.0, s1 = 0.0, cnt = 0.0;
 #pragma unroll 8
-        for (int k = k0; k < k1; ++k) { double v = fabs(src[r + (int64_t)k * ld]); mx = fmax(mx, v <= 1.7976931348623157e308 ? v : __longlong_as_double(0x7FF0000000000000LL)); }
+        for (int k = k0; k < k1; ++k) {
+            double v = fabs(src[r + (int64_t)k * ld]);
+            mx = fmax(mx, v <= 1.7976931348623157e308 ? v : __longlong_as_double(0x7FF0000000000000LL));
+            s1 += v; cnt += v != 0.0 ? 1.0 : 0.0;
+        }
         atomicMax(mx_bits + r, (unsigned long long)__double_as_longlong(mx));
+        if (cnt != 0.0) { atomicAdd(l1 + r, s1); atomicAdd(nz + r, cnt); }
     }
 }
 __global__ void __launch_bounds__(256) k_row_exponent(const unsigned long long *__restrict__ mx_bits, int rows, int bits, int *__restrict__ e_out,
@@ -409,6 +455,9 @@ __global__ void __launch_bounds__(256) k_row_exponent(const unsigned long long *
     // a row/column holding NaN or Inf gets a NaN scale: every output it touches becomes NaN, as DGEMM would propagate it
     // an all-zero row gets scale 0 (its digits are all zero anyway): it then adds nothing to the guard's error bound
     scale_out[r] = finite ? (mx > 0.0 ? scalbn(1.0, e) : 0.0) : __longlong_as_double(0x7FF8000000000000LL);
+    // 1-norm in units of the scale (<= nnz / 4); 1 % covers the rounding of the running sums
+    double *l1 = scale_out + rows;
+    l1[r] = (finite && mx > 0.0) ? 1.01 * scalbn(l1[r], -e) : 0.0;
 }
 
 // Balanced base-256 digits of four fixed-point values at once (bits == 8).  Adding 0x80 at every digit position below the
@@ -521,19 +570,27 @@ __global__ void __launch_bounds__(128) k_slice_fused_kmajor(int8_t *__restrict__
     for (int k = K + lane; k < Kp; k += 32) row[k] = 0.0;                       // (K is even here) zero padding up to Kp
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    double mx = 0.0;
+    double mx = 0.0, s1 = 0.0, cnt = 0.0;
     for (int k = 2 * lane; k < K; k += 64) {
         const double2 v = *reinterpret_cast<const double2 *>(row + k);
         const double a0 = fabs(v.x), a1 = fabs(v.y);
         // NaN/Inf anywhere in the row poisons the row (fmax would drop a NaN): non-finite elements count as +Inf
         mx = fmax(mx, a0 <= 1.7976931348623157e308 ? a0 : __longlong_as_double(0x7FF0000000000000LL));
         mx = fmax(mx, a1 <= 1.7976931348623157e308 ? a1 : __longlong_as_double(0x7FF0000000000000LL));
+        s1 += a0 + a1; cnt += (a0 != 0.0 ? 1.0 : 0.0) + (a1 != 0.0 ? 1.0 : 0.0);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
     const bool finite = isfinite(mx);
     const int e = (mx > 0.0 && finite) ? ilogb(mx) + (bits == 8 ? 3 : 2) : 0;
-    if (lane == 0) scale_out[r] = finite ? (mx > 0.0 ? scalbn(1.0, e) : 0.0) : __longlong_as_double(0x7FF8000000000000LL);
+    if (lane == 0) {
+        scale_out[r] = finite ? (mx > 0.0 ? scalbn(1.0, e) : 0.0) : __longlong_as_double(0x7FF8000000000000LL);
+        scale_out[rows + r] = (finite && mx > 0.0) ? 1.01 * scalbn(s1, -e) : 0.0;       // guard statistics, see k_row_absmax
+        scale_out[2 * rows + r] = cnt;
+    }
     const int64_t plane = (int64_t)rows * Kp;
     const int radix = 1 << bits, half = radix >> 1;
     for (int k = 4 * lane; k < Kp; k += 128) {
@@ -627,17 +684,23 @@ struct OzParams {
     // accuracy certificate ("guard"): slot[0] <- max |alpha * (op(A) op(B))(i,j)| as computed, slot[1] <- max over (i,j) of the
     // rigorous error bound gscale * |alpha| * 2^ea[i] * 2^eb[j], gscale = K * c(bits, S) (guard_coeff); NULL = not recorded
     unsigned long long *guard;
-    double gscale;
+    const double *la, *na, *lb, *nb;   // per row of op(A) / column of op(B): 1-norm in units of the scale, number of non-zeros
+    double g_rho, g_h, g_drop;         // guard_coeffs()
 };
 
 // |x - x~| <= 2^(e - bS - 1) per element (rint), |x| <= 2^e / 4 (b = 8) or 2^e / 2 (b = 7), and the slice pairs with p + q >= S
 // that the kernels drop weigh at most (S-1)/4 * 2^(-bS) per k (digits <= 2^(b-1)); 1 % covers the second-order terms:
 // |(A B)(i,j) - computed| <= K * c * 2^ea[i] * 2^eb[j] + (a few ulps of the computed value, added in guard_fold).
-static double guard_coeff(int bits, int S) {
-    const double rep = (bits == 8 ? 0.5 : 1.0) * ldexp(1.0, -bits * S - 1), drop = 0.25 * (S - 1) * ldexp(1.0, -bits * S);
-    return 1.01 * (rep + drop);
+// Per element, with s_a = 2^ea[i], s_b = 2^eb[j], abar = |a_i|_1 / s_a, bbar = |b_j|_1 / s_b, na / nb = non-zeros of the row / column
+// (zeros are represented exactly and meet no dropped pair), h = 1/4 (b = 8) or 1/2 (b = 7) = max |x| / scale:
+//   |(A B)(i,j) - computed| <= s_a s_b [ rho (min(abar, h nb) + min(bbar, h na)) + drop min(na, nb) ] + a few ulps of the value
+// rho = 1.01 * 2^(-bS-1), drop = 1.01 (S-1)/4 2^(-bS).  Dense operands give the familiar K c s_a s_b.
+static void guard_coeffs(int bits, int S, double &rho, double &h, double &drop) {
+    rho = 1.01 * ldexp(1.0, -bits * S - 1);
+    h = bits == 8 ? 0.25 : 0.5;
+    drop = 1.01 * 0.25 * (S - 1) * ldexp(1.0, -bits * S);
 }
-__device__ __forceinline__ void guard_record(unsigned long long *slot, double gmax, double bmax, double gscale, int lane) {
+__device__ __forceinline__ void guard_record(unsigned long long *slot, double gmax, double bmax, int lane) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
@@ -645,7 +708,7 @@ __device__ __forceinline__ void guard_record(unsigned long long *slot, double gm
     }
     if (lane == 0) {
         // bit patterns of non-negative doubles order like unsigned integers; the plain read is only a filter (monotone slot)
-        const unsigned long long g = (unsigned long long)__double_as_longlong(gmax), b = (unsigned long long)__double_as_longlong(bmax * gscale);
+        const unsigned long long g = (unsigned long long)__double_as_longlong(gmax), b = (unsigned long long)__double_as_longlong(bmax);
         if (g > *(volatile unsigned long long *)&slot[0]) atomicMax(&slot[0], g);
         if (b > *(volatile unsigned long long *)&slot[1]) atomicMax(&slot[1], b);
     }
@@ -819,6 +882,7 @@ template <int S>
 __device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int lane, int m0, int n0, int M, int N, const OzParams &P) {
     const int row = m0 + q4 * 32 + lane;
     const double rs = row < M ? P.alpha * P.sa[row] : 0.0;
+    const double la = (P.guard && row < M) ? P.la[row] : 0.0, hna = (P.guard && row < M) ? P.g_h * P.na[row] : 0.0;
     double gmax = 0.0, bmax = 0.0;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN2; c0 += 32) {
@@ -845,13 +909,17 @@ __device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int lan
                 const int col = n0 + c0 + j;
                 if (col < N) {
                     const double w = rs * P.sb[col], term = sum[j] * w;
-                    gmax = fmax(gmax, fabs(term)); bmax = fmax(bmax, fabs(w));
+                    if (P.guard) {
+                        const double hnb = P.g_h * P.nb[col];
+                        const double G = P.g_rho * (fmin(la, hnb) + fmin(P.lb[col], hna)) + P.g_drop * fmin(hna, hnb) / P.g_h;
+                        gmax = fmax(gmax, fabs(term)); bmax = fmax(bmax, fabs(w) * G);
+                    }
                     P.C[row + (int64_t)col * P.ldc] = P.beta * prev[j] + term;
                 }
             }
         }
     }
-    if (P.guard) guard_record(P.guard, gmax, bmax, P.gscale, lane);
+    if (P.guard) guard_record(P.guard, gmax, bmax, lane);
 }
 
 template <int S, int KB>
@@ -1205,7 +1273,7 @@ static int slice_operand(cudaStream_t st, const double *src, int64_t ld, int64_t
     unsigned long long *mx = (unsigned long long *)sc;                  // scale array doubles as max scratch
     if (kmajor) k_row_absmax<true><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(src, ld, (int)rows, (int)K, mx);
     else {
-        cudaMemsetAsync(mx, 0, rows * 8, st);
+        cudaMemsetAsync(mx, 0, rows * 24, st);                           // max | 1-norm | nnz
         k_row_absmax<false><<<dim3((unsigned)((rows + 255) / 256), (unsigned)((K + 63) / 64)), 256, 0, st>>>(src, ld, (int)rows, (int)K, mx);
     }
     k_row_exponent<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(mx, (int)rows, bits, e, sc);
@@ -1242,7 +1310,7 @@ static cudaError_t prepare_operand(cudaStream_t st, uint64_t tag, const double *
         return cudaSuccess;
     }
     if (!slot) {
-        const size_t bytes = (size_t)ns * rows * Kp + (size_t)rows * 8 + 512;
+        const size_t bytes = (size_t)ns * rows * Kp + (size_t)rows * 24 + 512;     // slices + (scale | 1-norm | nnz) per row
         while (!g_cache.empty() && g_cache_bytes + bytes > cache_cap()) {          // evict least recently used
             size_t lru = 0;
             for (size_t i = 1; i < g_cache.size(); ++i) if (g_cache[i].last_use < g_cache[lru].last_use) lru = i;
@@ -1322,7 +1390,7 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     // an operand that is a row window of a larger, tagged operand: slice (or find) the WHOLE operand in the cache and point the
     // tensor map at the window - the panels of a panelled GEMM share one slicing
     const size_t a_bytes = (tag_a && !wa.full) ? 0 : al((size_t)nslices * M * Kp), b_bytes = (tag_b && !wb.full) ? 0 : al((size_t)nslices * N * Kp);
-    const size_t ea_bytes = al(std::max<int64_t>(M, wa.rows_full) * 4), eb_bytes = al(std::max<int64_t>(N, wb.rows_full) * 4), sa_bytes = al(M * 8), sb_bytes = al(N * 8);
+    const size_t ea_bytes = al(std::max<int64_t>(M, wa.rows_full) * 4), eb_bytes = al(std::max<int64_t>(N, wb.rows_full) * 4), sa_bytes = al(M * 24), sb_bytes = al(N * 24);
     uint8_t *ws = (uint8_t *)workspace(a_bytes + b_bytes + ea_bytes + eb_bytes + sa_bytes + sb_bytes);
     if (!ws) return cudaErrorMemoryAllocation;
     int8_t *ws_a = (int8_t *)ws, *ws_b = (int8_t *)(ws + a_bytes);
@@ -1369,7 +1437,11 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     }
     if (G.guard_used >= kGuardSlots) { cudaError_t ge = guard_fold(st, G); if (ge != cudaSuccess) return ge; }
     unsigned long long *gslot = G.guard + 2 * (G.guard_used++);
-    OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m, ozaki_bits(), gslot, (double)K * guard_coeff(ozaki_bits(), nslices)};
+    double g_rho, g_h, g_drop;
+    guard_coeffs(ozaki_bits(), nslices, g_rho, g_h, g_drop);
+    // the row statistics sit `rows` apart behind the scales (the rows of the whole operand when this is a window of it)
+    const int64_t ra = a_stride ? a_stride : M, rb = b_stride ? b_stride : N;
+    OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m, ozaki_bits(), gslot, sa + ra, sa + 2 * ra, sb + rb, sb + 2 * rb, g_rho, g_h, g_drop};
     static int gen = -1;
     if (gen < 0) { const char *e = getenv("RDB_OZAKI_GEN"); gen = e ? atoi(e) : 2; }
     if (gen == 2 && nslices <= 8) {

@@ -48,6 +48,11 @@ def lib():
         "rdb_ctx_set_gemm_f64_mode": (i32, [vp, i32, i32]),
         "rdb_ctx_gemm_guard": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(f64)]),
         "rdb_tape_guard_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(f64)]),
+        "rdb_comm_unique_id": (i32, [vp]),
+        "rdb_comm_create": (vp, [vp, i32, i32, vp]),
+        "rdb_comm_destroy": (None, [vp]),
+        "rdb_gather_result": (i32, [vp, i32, i32, vp, C.POINTER(i64), i64, vp, i32]),
+        "rdb_place_block": (i32, [i32, i32, vp, i64, i64, i64, i64, vp]),
         "rdb_tape_load": (vp, [vp, vp, C.c_size_t, C.POINTER(_Options)]),
         "rdb_tape_destroy": (None, [vp]),
         "rdb_tape_set_input": (i32, [vp, i32, vp, i32]),
@@ -75,7 +80,8 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "rdb_version", "rdb_last_error", "rdb_ctx_create", "rdb_ctx_destroy", "rdb_ctx_set_stream",
-    "rdb_ctx_synchronize", "rdb_ctx_set_gemm_f64_mode", "rdb_ctx_gemm_guard", "rdb_tape_guard_stats", "rdb_tape_load", "rdb_tape_destroy", "rdb_tape_set_input", "rdb_forward",
+    "rdb_ctx_synchronize", "rdb_ctx_set_gemm_f64_mode", "rdb_ctx_gemm_guard", "rdb_tape_guard_stats", "rdb_comm_unique_id",
+    "rdb_comm_create", "rdb_comm_destroy", "rdb_gather_result", "rdb_place_block", "rdb_tape_load", "rdb_tape_destroy", "rdb_tape_set_input", "rdb_forward",
     "rdb_reverse_scalar_seed", "rdb_gradient", "rdb_jacobian", "rdb_hessian", "rdb_get_value", "rdb_get_deriv",
     "rdb_buffer_size", "rdb_tape_stats", "rdb_tape_launch_count", "rdb_gemm", "rdb_add_sum", "rdb_plan_col_panels", "rdb_schedule_bundles",
 ]
@@ -147,6 +153,59 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class Comm:
+    """``rdb_comm``: the NCCL communicator behind ``rdb_gather_result`` (one process per GPU).  ``id_bytes`` comes from
+    ``Comm.unique_id()`` on rank 0 and reaches the other ranks through the host (``api.make_comm`` uses torch.distributed)."""
+    ID_BYTES = 128
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(Comm.ID_BYTES)
+        _check(lib().rdb_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, ctx: Context, world: int, rank: int, id_bytes: bytes):
+        self.ctx, self.world, self.rank = ctx, int(world), int(rank)
+        buf = C.create_string_buffer(bytes(id_bytes), Comm.ID_BYTES)
+        self.ptr = lib().rdb_comm_create(ctx.ptr, self.world, self.rank, buf)
+        if not self.ptr:
+            msg = lib().rdb_last_error()
+            raise EngineError(f"rdb_comm_create failed: {msg.decode() if msg else '?'}")
+
+    def gather(self, np_dtype, kind, block, bounds, other_dim, result, root=-1):
+        """``rdb_gather_result``: ``block``/``result`` are device tensors (flat, column-major); ``bounds`` the partition."""
+        b = (C.c_int64 * len(bounds))(*[int(x) for x in bounds])
+        dt = RDB_F64 if np.dtype(np_dtype) == np.float64 else RDB_F32
+        bp = C.c_void_p(block.data_ptr()) if block is not None and block.numel() else None
+        rp = C.c_void_p(result.data_ptr()) if result is not None else None
+        _check(lib().rdb_gather_result(self.ptr, dt, int(kind), bp, b, int(other_dim), rp, int(root)))
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            lib().rdb_comm_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def place_block(kind, block, begin, end, result):
+    """``rdb_place_block`` on host arrays: ``result`` is the full column-major matrix (F-contiguous numpy array)."""
+    if not (isinstance(result, np.ndarray) and result.flags.f_contiguous and result.ndim == 2):
+        raise TypeError("result must be a 2-D F-contiguous numpy array")
+    blk = np.asfortranarray(block, dtype=result.dtype)
+    m, n = result.shape
+    want = (end - begin, n) if kind == 0 else (m, end - begin)
+    if blk.shape != want:
+        raise ValueError(f"block of shape {blk.shape}, expected {want}")
+    dt = RDB_F64 if result.dtype == np.float64 else RDB_F32
+    _check(lib().rdb_place_block(dt, int(kind), blk.ctypes.data_as(C.c_void_p), int(begin), int(end), m, n, result.ctypes.data_as(C.c_void_p)))
+    return result
 
 
 _default_ctx = None

@@ -124,6 +124,8 @@ def test_cfg4_baseline_size(rd):
     s = Ad @ xt + xt; t = torch.tanh(Bd @ xt)
     Jcf = t[:, None] * (Ad + torch.eye(n, dtype=torch.float64, device="cuda")) + (s * (1 - t * t))[:, None] * Bd
     assert _rel(J.reshape(n, n).T, Jcf) < 1e-12            # column-major (m x n) result viewed row-major
+    gs = ct.handle.guard_stats()
+    assert gs["checked"] >= 2 and gs["fallbacks"] == 0, gs     # the two 8192^3 adjoint products ran on int8 slices, certified
     # a shard of seed rows written into its place of the full column-major matrix (ld = m): what a rank of the multi-GPU run does
     J2 = torch.zeros(n * n, dtype=torch.float64, device="cuda")
     rb, re = 3 * n // 8, 4 * n // 8

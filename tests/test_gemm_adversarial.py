@@ -79,8 +79,9 @@ def test_k65536_gaussian_like_51bit_operands(rd, ctx):
 
 def test_in_row_magnitude_spread(rd, ctx):
     """Elements spread over 2^-46..1 (1e-14..1) inside every row / column.  Norm-wise the sliced product is as good as ever (small
-    elements lose bits but weigh little); component-wise it is not DGEMM - both are reported; the certificate passes because
-    max|P| is carried by the large elements."""
+    elements lose bits but weigh little); component-wise it is not DGEMM - both are reported.  The rigorous bound cannot know that
+    the dropped slice pairs of 1024 tiny-but-non-zero elements cancel statistically, so the certificate is allowed to fail here
+    (conservative: a tape would replay with DMMA); what must hold is the bound itself and the 1e-12 norm-wise accuracy."""
     rng = np.random.default_rng(12)
     m = n = 384; k = 1024
     A = np.asfortranarray(rng.standard_normal((m, k)) * np.ldexp(1.0, -rng.integers(0, 47, (m, k))))
@@ -89,8 +90,22 @@ def test_in_row_magnitude_spread(rd, ctx):
     C, (chk, flg, worst) = _gemm(rd, ctx, A, B, 2)
     Cd, _ = _gemm(rd, ctx, A, B, 1)
     e8, ed, pmax = _report("in-row spread 2^-46..1", C, Cd, P, A, B)
-    assert chk == 1 and flg == 0
+    print(f"[gemm-adversarial] in-row spread: certificate ratio {worst:.3e} (tau {TAU:.3e}), flagged {flg}")
+    assert chk == 1
     assert e8 <= worst * pmax and e8 < 1e-12 * pmax
+
+
+def test_one_hot_seed_operand_is_certified(rd, ctx):
+    """jacobian!'s adjoint products have a one-hot seed matrix as one operand.  A bound of the form K * max|row| * max|col| would
+    fail them (K = 2048 here, one non-zero per column); the certificate counts non-zeros and 1-norms per row, so they pass."""
+    rng = np.random.default_rng(16)
+    m = k = 2048; n = 512
+    A = np.asfortranarray(rng.random((m, k)) / k)
+    D = np.zeros((k, n), order="F")
+    D[rng.permutation(k)[:n], np.arange(n)] = rng.random(n) + 0.5          # one scaled unit vector per column
+    C, (chk, flg, worst) = _gemm(rd, ctx, A, D, 2)
+    assert chk == 1 and flg == 0 and worst < 1e-14, (chk, flg, worst)
+    assert np.max(np.abs(C - A @ D)) < 1e-15 * np.max(np.abs(C))
 
 
 def test_certificate_fails_on_misaligned_magnitudes_and_tape_replays_with_dmma(rd, orc, ctx):

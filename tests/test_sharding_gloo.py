@@ -27,12 +27,23 @@ def _worker(rank, world, port, q):
     _, _, x = rd.workloads.inputs_jacobian(n, seed=2)
     rb, re = shard(n, world, rank)
     _, Jblk = orc.OracleTape(tape.program_bytes()).jacobian([x], rows=range(rb, re))     # rows x n, this rank's seeds
-    blocks = [torch.zeros(n // world, n, dtype=torch.float64) for _ in range(world)]
-    dist.all_gather(blocks, torch.from_numpy(np.ascontiguousarray(Jblk)))
-    J = torch.cat(blocks, 0).numpy()
+    # what a rank's rdb_jacobian(row_begin, row_end, ld = rows) leaves behind: a contiguous column-major (rows x n) block
+    mine = torch.from_numpy(np.ascontiguousarray(np.asfortranarray(Jblk).reshape(-1, order="F")))
+    bounds = rd.shard_bounds(n, world)
+    blocks = [torch.zeros((bounds[r + 1] - bounds[r]) * n, dtype=torch.float64) for r in range(world)]
+    dist.all_gather(blocks, mine)                                    # gloo stands in for NCCL; the PLACEMENT is the product's
+    J = np.full((n, n), np.nan, order="F")
+    for r in range(world):                                           # rdb_place_block: the host twin of rdb_gather_result
+        rows = bounds[r + 1] - bounds[r]
+        rd.engine.place_block(0, blocks[r].numpy().reshape(rows, n, order="F"), bounds[r], bounds[r + 1], J)
+    # column blocks (hessian! shards): contiguous in the column-major result
+    Hfull = np.arange(float(n * n)).reshape(n, n, order="F")
+    H = np.full((n, n), np.nan, order="F")
+    for r in range(world):
+        rd.engine.place_block(1, Hfull[:, bounds[r]:bounds[r + 1]], bounds[r], bounds[r + 1], H)
     if rank == 0:
         _, Jfull = orc.OracleTape(tape.program_bytes()).jacobian([x])
-        q.put(float(np.max(np.abs(J - Jfull))))
+        q.put(max(float(np.max(np.abs(J - Jfull))), float(np.max(np.abs(H - Hfull)))))
     dist.barrier()
     dist.destroy_process_group()
 
