@@ -121,6 +121,11 @@ int rdb_get_deriv(rdb_tape *, int buffer_id, void *dst_host);
 int64_t rdb_buffer_size(rdb_tape *, int buffer_id);
 /* Per-step report (kernel name, time, algorithmic bytes / flops) as JSON; needs opts.profile = 1. */
 int rdb_tape_stats(rdb_tape *, char *json, size_t cap);
+/* on != 0: rdb_hessian calls whose result is a device array and that return nothing to the host (no grad_out / value_out) are
+ * only ENQUEUED on the context's stream; the caller orders later work after them on that stream or calls rdb_ctx_synchronize.
+ * Inputs passed by device pointer must stay alive until then.  (A sharded hessian! call is tens of microseconds of device work;
+ * returning without a host round trip lets consecutive calls overlap their launch latency.) */
+int rdb_tape_set_async(rdb_tape *, int on);
 /* Totals since load of the int8-slice GEMM's accuracy certificate on this tape (see rdb_ctx_gemm_guard): launches checked,
  * launches flagged, and how many API calls were therefore replayed with the DMMA kernels before returning (gemm_f64_mode 0;
  * mul!, src/derivatives/linalg/arithmetic.jl:245-285, is DGEMM in the reference).  Any pointer may be NULL. */

@@ -173,6 +173,9 @@ struct rdb_tape {
     // accuracy certificate of the int8-slice `*` kernels (umma.cu guard): totals since load, and the fallback state
     int64_t guard_checked = 0, guard_flagged = 0, guard_fallbacks = 0;
     double guard_worst = 0;
+    bool async = false;            // rdb_tape_set_async: calls with device results and no host outputs return without synchronising
+    int hess_prefill = 0;          // hessian!: the result block's zero-fill runs on a side stream next to the small kernels (1), not (-1), unknown (0)
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     int guard_streak = 0;          // consecutive calls whose certificate failed; 3 make the tape DMMA-only for good
     bool dmma_now = false;         // this call is the DMMA replay of a call whose certificate failed
     uint64_t graph_gen = 0, hgraph_gen = 0;   // GemmState::alloc_gen when the graphs were captured
@@ -1657,6 +1660,29 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                 need_x_tv = true;
     }
 
+    // first-order adjoints: with no gradient requested, only the adjoints that some second-order term multiplies are needed -
+    // deriv(output of a nonlinear instruction) and everything between it and the tape output.  need_der[b]: the sub-DAG that
+    // produces b contains a nonlinear instruction.
+    const bool lean = !grad_out && on_device && cols > 0;
+    std::vector<char> need_der(nb, 1);
+    if (lean) {
+        std::fill(need_der.begin(), need_der.end(), 0);
+        for (size_t ii = 0; ii < ni; ++ii) {
+            InstrPlan &I = t->instrs[ii];
+            bool nl = is_elementwise(I.rec.opcode);
+            for (int a = 0; a < I.rec.n_in && !nl; ++a) nl = need_der[root(I.in[a].rec.buffer)] != 0;
+            if (nl) need_der[root(I.rec.out)] = 1;
+        }
+        need_der[root(t->output)] = 1;                       // seeded below, so it must be unseeded again
+    }
+    if (!t->capturing) {                                     // (nothing is created inside a stream capture)
+        rdb_ctx *c = t->ctx;
+        if (!c->side_stream) CU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+        if (!t->fork_ev) CU(cudaEventCreateWithFlags(&t->fork_ev, cudaEventDisableTiming));
+        if (!t->join_ev) CU(cudaEventCreateWithFlags(&t->join_ev, cudaEventDisableTiming));
+    }
+    auto want_der = [&](int b) { return need_der[root(b)] != 0; };
+
     void *const x_td_own = x.td;
     bool first = true;
     for (int64_t c0 = cb; c0 < ce || first; c0 += K) {
@@ -1665,6 +1691,33 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
         const bool in_place = cols > 0 && dld == n;
         if (in_place) x.td = dres + (c0 - cb) * dld;
         for (auto &b : t->bufs) if (b.alias_of >= 0) b.td = t->bufs[b.alias_of].td;
+        // The zero-fill of the block (n x Kb: the bulk of the call's HBM traffic when the second-order terms are sparse) does not
+        // depend on the forward sweep or on the small first-order kernels: fork it onto the side stream, join before the first
+        // scatter into the block.  Whether the first writer wants zeros is learnt on the first (eager) sweep.
+        bool prefilled = false;
+        if (t->hess_prefill == 1 && cols > 0) {
+            rdb_ctx *c = t->ctx;
+            CU(cudaEventRecord(t->fork_ev, S(t)));
+            CU(cudaStreamWaitEvent(c->side_stream, t->fork_ev, 0));
+            CU(cudaMemsetAsync(x.td, 0, (size_t)(n * Kb) * t->es, c->side_stream));
+            CU(cudaEventRecord(t->join_ev, c->side_stream));
+            prefilled = true;
+        }
+        // make the block's storage really zero before a scatter / atomic accumulation: join the forked fill, or fill now
+        auto zero_x_td = [&]() -> int {
+            if (prefilled) { CU(cudaStreamWaitEvent(S(t), t->join_ev, 0)); prefilled = false; }
+            else {
+                CU(cudaMemsetAsync(x.td, 0, (size_t)(n * Kb) * t->es, S(t)));
+                if (t->hess_prefill == 0) t->hess_prefill = 1;
+            }
+            return RDB_OK;
+        };
+        // a full-coverage first write into the block: nothing to fill, and no point forking a fill next time
+        auto overwrite_x_td = [&]() -> int {
+            if (prefilled) { CU(cudaStreamWaitEvent(S(t), t->join_ev, 0)); prefilled = false; }
+            if (t->hess_prefill == 0) t->hess_prefill = -1;
+            return RDB_OK;
+        };
 
         // ---- tangent-forward sweep
         if (need_x_tv) KL(t, launch_seed_tangent<T>(S(t), (T *)x.tv, n, Kb, c0));
@@ -1725,7 +1778,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
         }
         // ---- reverse sweep carrying (adjoint, adjoint tangent); first-order adjoints are recomputed per chunk (size n, cheap)
         std::vector<char> td_zero(nb, 1);               // per ROOT buffer: adjoint tangent is (logically) zero
-        for (int b : t->inputs) OK(unseed<T>(t, t->bufs[b], 1));
+        for (int b : t->inputs) if (want_der(b)) OK(unseed<T>(t, t->bufs[b], 1));
         KL(t, launch_fill<T>(S(t), (T *)out.der, 1, (T)1));
         for (size_t ii = t->instrs.size(); ii-- > 0;) {
             InstrPlan &I = t->instrs[ii];
@@ -1737,9 +1790,12 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                 case OP_GETINDEX: case OP_GETINDEX_GENERIC: {
                     const int rb = root(I.in[0].rec.buffer);
                     Buf &b = t->bufs[I.in[0].rec.buffer];
-                    KL(t, launch_scatter_add<T>(S(t), (T *)b.der, b.size, I.in[0].d_map, delta, o.size, 1));
+                    if (want_der(I.in[0].rec.buffer)) KL(t, launch_scatter_add<T>(S(t), (T *)b.der, b.size, I.in[0].d_map, delta, o.size, 1));
                     if (!dt_zero) {
-                        if (td_zero[rb]) { CU(cudaMemsetAsync(b.td, 0, (size_t)(b.size * Kb) * t->es, S(t))); td_zero[rb] = 0; }
+                        if (td_zero[rb]) {
+                            if (rb == root(xid)) OK(zero_x_td()); else CU(cudaMemsetAsync(b.td, 0, (size_t)(b.size * Kb) * t->es, S(t)));
+                            td_zero[rb] = 0;
+                        }
                         StepTimer tm(t, "tangent_getindex_reverse", 3.0 * o.size * Kb * t->es, 0);
                         KL(t, launch_scatter_add<T>(S(t), (T *)b.td, b.size, I.in[0].d_map, dt, o.size, Kb));
                     }
@@ -1750,22 +1806,31 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                         const int rb = root(I.in[a].rec.buffer);
                         Buf &b = t->bufs[I.in[a].rec.buffer];
                         T sign = (a == 1 && I.rec.opcode == OP_SUB) ? (T)-1 : (T)1;
-                        KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, sign, o.size, false));
-                        if (!dt_zero) { KL(t, launch_axpy<T>(S(t), (T *)b.td, dt, sign, o.size * Kb, td_zero[rb] != 0)); td_zero[rb] = 0; }
+                        if (want_der(I.in[a].rec.buffer)) KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, sign, o.size, false));
+                        if (!dt_zero) {
+                            if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
+                            KL(t, launch_axpy<T>(S(t), (T *)b.td, dt, sign, o.size * Kb, td_zero[rb] != 0)); td_zero[rb] = 0;
+                        }
                     }
                     break;
                 case OP_NEG: {
                     const int rb = root(I.in[0].rec.buffer);
                     Buf &b = t->bufs[I.in[0].rec.buffer];
-                    KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, (T)-1, o.size, false));
-                    if (!dt_zero) { KL(t, launch_axpy<T>(S(t), (T *)b.td, dt, (T)-1, o.size * Kb, td_zero[rb] != 0)); td_zero[rb] = 0; }
+                    if (want_der(I.in[0].rec.buffer)) KL(t, launch_axpy<T>(S(t), (T *)b.der, delta, (T)-1, o.size, false));
+                    if (!dt_zero) {
+                        if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
+                        KL(t, launch_axpy<T>(S(t), (T *)b.td, dt, (T)-1, o.size * Kb, td_zero[rb] != 0)); td_zero[rb] = 0;
+                    }
                 } break;
                 case OP_SUM: case OP_MEAN: {
                     const int rb = root(I.in[0].rec.buffer);
                     Buf &b = t->bufs[I.in[0].rec.buffer];
                     T scale = I.rec.opcode == OP_MEAN ? (T)1 / (T)I.in[0].size : (T)1;
-                    KL(t, launch_acc_scalar<T>(S(t), (T *)b.der, b.size, 1, delta, scale, false));
-                    if (!dt_zero) { KL(t, launch_acc_scalar<T>(S(t), (T *)b.td, b.size, Kb, dt, scale, td_zero[rb] != 0)); td_zero[rb] = 0; }
+                    if (want_der(I.in[0].rec.buffer)) KL(t, launch_acc_scalar<T>(S(t), (T *)b.der, b.size, 1, delta, scale, false));
+                    if (!dt_zero) {
+                        if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
+                        KL(t, launch_acc_scalar<T>(S(t), (T *)b.td, b.size, Kb, dt, scale, td_zero[rb] != 0)); td_zero[rb] = 0;
+                    }
                 } break;
                 case OP_MUL: {
                     OperandPlan &oa = I.in[0], &ob = I.in[1];
@@ -1774,8 +1839,9 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                         const int rb = root(ob.rec.buffer);
                         Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
                         bool st = oa.mode == OPM_FOLDED_T;
-                        KL(t, gemm_t<T>(S(t), !st, false, Kd, N, M, (T)1, (const T *)a.val, st ? oa.cols : oa.rows, delta, M, (T)1, (T *)b.der, Kd));
+                        if (want_der(ob.rec.buffer)) KL(t, gemm_t<T>(S(t), !st, false, Kd, N, M, (T)1, (const T *)a.val, st ? oa.cols : oa.rows, delta, M, (T)1, (T *)b.der, Kd));
                         if (!dt_zero) {
+                            if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
                             KL(t, gemm_t<T>(S(t), !st, false, Kd, N * Kb, M, (T)1, (const T *)a.val, st ? oa.cols : oa.rows, dt, M, td_zero[rb] ? (T)0 : (T)1, (T *)b.td, Kd));
                             td_zero[rb] = 0;
                         }
@@ -1783,8 +1849,9 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                         const int rb = root(oa.rec.buffer);
                         Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
                         bool st = ob.mode == OPM_FOLDED_T;
-                        KL(t, gemm_t<T>(S(t), false, !st, M, Kd, N, (T)1, delta, M, (const T *)b.val, st ? ob.cols : ob.rows, (T)1, (T *)a.der, M));
+                        if (want_der(oa.rec.buffer)) KL(t, gemm_t<T>(S(t), false, !st, M, Kd, N, (T)1, delta, M, (const T *)b.val, st ? ob.cols : ob.rows, (T)1, (T *)a.der, M));
                         if (!dt_zero) {
+                            if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
                             for (int64_t k = 0; k < Kb; ++k)
                                 KL(t, gemm_t<T>(S(t), false, !st, M, Kd, N, (T)1, dt + k * o.size, M, (const T *)b.val, st ? ob.cols : ob.rows, td_zero[rb] ? (T)0 : (T)1, (T *)a.td + k * a.size, M));
                             td_zero[rb] = 0;
@@ -1796,7 +1863,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                     if (sparse_ok[ii]) {
                         // every argument is a getindex view of the seeded input and no adjoint tangent flows in
                         const int rx = root(xid);
-                        if (td_zero[rx]) { CU(cudaMemsetAsync(x.td, 0, (size_t)(n * Kb) * t->es, S(t))); td_zero[rx] = 0; }
+                        if (td_zero[rx]) { OK(zero_x_td()); td_zero[rx] = 0; }
                         const int64_t *maps[kMaxArgs];
                         const T *sec[kMaxArgs * kMaxArgs];
                         for (int p = 0; p < N; ++p) {
@@ -1806,7 +1873,8 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                         StepTimer tm(t, "tangent_reverse_sparse", (double)n * Kb * t->es, 0);
                         KL(t, launch_tangent_reverse_sparse<T>(S(t), (T *)x.td, n, Kb, c0, delta, N, maps, sec, o.size));
                         for (int p = 0; p < N; ++p)
-                            KL(t, launch_mul_acc<T>(S(t), (T *)t->bufs[I.in[p].rec.buffer].der, delta, (const T *)I.partial[p], o.size, 1, false));
+                            if (want_der(I.in[p].rec.buffer))
+                                KL(t, launch_mul_acc<T>(S(t), (T *)t->bufs[I.in[p].rec.buffer].der, delta, (const T *)I.partial[p], o.size, 1, false));
                         break;
                     }
                     const T *tvs[kMaxArgs];
@@ -1817,19 +1885,21 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                         const T *sec[kMaxArgs];
                         for (int q = 0; q < N; ++q) sec[q] = (const T *)I.second[tri_index(p, q, N)];
                         StepTimer tm(t, "tangent_reverse", (double)(N + (dt ? 2 : 1) + (td_zero[rb] ? 0 : 1)) * o.size * Kb * t->es, 0);
+                        if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
                         KL(t, launch_tangent_reverse<T>(S(t), (T *)b.td, dt, delta, (const T *)I.partial[p], N, sec, tvs, o.size, Kb, td_zero[rb] != 0));
                         td_zero[rb] = 0;
-                        KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[p], o.size, 1, false));
+                        if (want_der(I.in[p].rec.buffer)) KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[p], o.size, 1, false));
                     }
                 }
             }
-            OK(unseed<T>(t, o, 1));
+            if (want_der(I.rec.out)) OK(unseed<T>(t, o, 1));
         }
         if (cols > 0) {
             if (td_zero[root(xid)]) {          // f does not depend on x through any second-order path: exact zeros
-                if (in_place) CU(cudaMemsetAsync(x.td, 0, (size_t)(n * Kb) * t->es, S(t)));
-                else CU(cudaMemsetAsync(x_td_own, 0, (size_t)(n * Kb) * t->es, S(t)));
+                if (prefilled) { CU(cudaStreamWaitEvent(S(t), t->join_ev, 0)); prefilled = false; }
+                else CU(cudaMemsetAsync(x.td, 0, (size_t)(n * Kb) * t->es, S(t)));
             }
+            if (prefilled) { CU(cudaStreamWaitEvent(S(t), t->join_ev, 0)); prefilled = false; }   // never leave the fork unjoined
             if (!in_place) {
                 StepTimer tm(t, "hessian_cols_out", 2.0 * n * Kb * t->es, 0);
                 KL(t, launch_copy2d<T>(S(t), dres + (c0 - cb) * dld, dld, (const T *)x.td, n, n, Kb));   // H[:, c0:c0+Kb] = tangent of deriv(x)
@@ -1841,11 +1911,11 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
     x.td = x_td_own;
     for (auto &b : t->bufs) if (b.alias_of >= 0) b.td = t->bufs[b.alias_of].td;
     for (size_t b = 0; b < t->bufs.size(); ++b) t->dz[droot(t, (int)b)] = 1;   // intermediates were physically unseeded
-    t->dz[droot(t, xid)] = 0;                                                   // deriv(x) holds the gradient
+    t->dz[droot(t, xid)] = 0;                                                   // deriv(x) holds the gradient (zeros in a lean sweep)
     if (grad_out) CU(cudaMemcpyAsync(grad_out, x.der, (size_t)n * t->es, cudaMemcpyDefault, S(t)));
     if (!on_device && cols > 0)
         CU(cudaMemcpy2DAsync(result, (size_t)ld * t->es, t->stage, (size_t)n * t->es, (size_t)n * t->es, (size_t)cols, cudaMemcpyDeviceToHost, S(t)));
-    if (!t->capturing) CU(cudaStreamSynchronize(S(t)));
+    if (!t->capturing && !(t->async && on_device && !grad_out && !value_out)) CU(cudaStreamSynchronize(S(t)));
     return RDB_OK;
 }
 
@@ -1909,7 +1979,7 @@ static int hessian_entry(rdb_tape *t, int64_t cb, int64_t ce, void *result, int6
     for (size_t b = 0; b < t->bufs.size(); ++b) t->dz[droot(t, (int)b)] = 1;
     t->dz[droot(t, t->inputs[0])] = 0;
     t->forward_valid = true;
-    CU(cudaStreamSynchronize(S(t)));
+    if (!t->async) CU(cudaStreamSynchronize(S(t)));
     return RDB_OK;
 }
 
@@ -1919,7 +1989,7 @@ static int fold_launches(rdb_tape *t, int rc) {
     g_extra_launches = 0;
     // slicing that ran ahead on the side stream and was not consumed must not outlive the call (the next call may refill the
     // same cache entries from the main stream)
-    if (t->ctx && t->ctx->side_stream) cudaStreamSynchronize(t->ctx->side_stream);
+    if (t->ctx && t->ctx->side_stream && !t->async) cudaStreamSynchronize(t->ctx->side_stream);
     return rc;
 }
 // Run one API call on a tape.  FP64 `*` instructions of eligible shapes go through exact int8 slices on tcgen05, whose error is
@@ -2006,6 +2076,11 @@ int rdb_ctx_gemm_guard(rdb_ctx *c, int64_t *checked, int64_t *flagged, double *w
     if (worst_ratio) *worst_ratio = gs.worst_ratio;
     return RDB_OK;
 }
+int rdb_tape_set_async(rdb_tape *t, int on) {
+    if (!t) return fail(RDB_EINVAL, "null tape");
+    t->async = on != 0;
+    return RDB_OK;
+}
 int rdb_tape_guard_stats(rdb_tape *t, int64_t *checked, int64_t *flagged, int64_t *fallbacks, double *worst_ratio) {
     if (!t) return fail(RDB_EINVAL, "null tape");
     if (checked) *checked = t->guard_checked;
@@ -2037,6 +2112,8 @@ void rdb_tape_destroy(rdb_tape *t) {
     if (t->ev1) cudaEventDestroy(t->ev1);
     if (t->gexec) cudaGraphExecDestroy(t->gexec);
     if (t->hgraph.exec) cudaGraphExecDestroy(t->hgraph.exec);
+    if (t->fork_ev) cudaEventDestroy(t->fork_ev);
+    if (t->join_ev) cudaEventDestroy(t->join_ev);
     for (auto &e : t->early.ev) if (e) cudaEventDestroy(e);
     if (t->ctx && t->ctx->upload_stream) cudaStreamSynchronize(t->ctx->upload_stream);
     for (auto &b : t->bufs) for (auto &e : b.up_ev) if (e) cudaEventDestroy(e);

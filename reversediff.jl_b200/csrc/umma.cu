@@ -118,6 +118,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms of 1024 B (SBO), LBO unused.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     uint64_t d = 0;
@@ -146,11 +156,6 @@ struct EpiF32 {           // C = alpha*acc + beta*C   (FP32, column-major)
     __device__ __forceinline__ void store(int row, int col, uint32_t raw, float prev) const {
         C[row + (int64_t)col * ldc] = alpha * __uint_as_float(raw) + beta * prev;
     }
-    // later K-chunks of the same tile: C += alpha*acc (round-to-nearest FP32 adds, see umma_gemm_kernel)
-    __device__ __forceinline__ float reload(int row, int col) const { return C[row + (int64_t)col * ldc]; }
-    __device__ __forceinline__ void accumulate(int row, int col, uint32_t raw, float prev) const {
-        C[row + (int64_t)col * ldc] = prev + alpha * __uint_as_float(raw);
-    }
 };
 // ------------------------------------------------------------------------------------------ the kernel
 // Tile rasterisation: CTAs are dispatched in linear block order (x fastest).  With x = m-tile a wave of 148 CTAs touched every
@@ -174,13 +179,14 @@ __device__ __forceinline__ void mbar_arrive1(uint64_t *bar) {
 // ulp, a BIAS that grows linearly with the number of steps chained into one accumulator (measured on B200, all-positive data:
 // -2.7e-6 relative at K = 1024, -1.3e-5 at 4096, -5.4e-5 at 16384 - profiles/README.md; the FP32 contract is 1e-5).  So a chain
 // is never longer than one K-CHUNK of KCHUNK_BLOCKS stages (512 elements x 3 segments = 192 steps): the two TMEM accumulators
-// take alternate chunks, and the epilogue warps drain a finished chunk into C with round-to-nearest FP32 adds
-// (C = alpha*acc + beta*C for the first chunk, C += alpha*acc afterwards; the tile stays in L2 between its chunks) while the
-// MMA warp is already filling the other accumulator.  The error then no longer depends on K (~3e-6 worst case).
+// take alternate chunks, and EIGHT epilogue warps (two per TMEM lane quarter, 128 columns each) drain a finished chunk into
+// running sums held in registers with round-to-nearest FP32 adds while the MMA warp is already filling the other accumulator;
+// C is read and written once, at the end.  The error then no longer depends on K (~3e-6 worst case, measured).
 constexpr int KCHUNK_BLOCKS = 16;
+constexpr int THREADS_F32 = 64 + 8 * 32;     // TMA warp, MMA warp, 8 epilogue warps
 
 template <int KIND, typename Epi>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __maxnreg__(200)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  Segs segs, Epi epi) {
     extern __shared__ uint8_t smem_raw[];
@@ -204,7 +210,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -261,35 +267,44 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-        const int q = warp & 3;
+        // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); warps 2-5 take columns [0,128), warps 6-9 [128,256)
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const int row = m0 + q * 32 + lane;
+        constexpr int HC = BN / 2;
+        float run[HC];
+#pragma unroll
+        for (int j = 0; j < HC; ++j) run[j] = 0.f;
         for (int c = 0; c < chunks; ++c) {
             const int buf = c & 1;
             mbar_wait(&tmem_full[buf], (c >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), v);
-                if (row < M) {
-                    // all 32 loads of the old C are issued before the first store (a load->store->load chain cost ~0.4 ms per GEMM)
-                    typename Epi::prev_t prev[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = n0 + c0 + j;
-                        if (col < N) prev[j] = c == 0 ? epi.load(row, col) : epi.reload(row, col);
-                    }
+            for (int c0 = 0; c0 < HC; c0 += 16) {
+                uint32_t v[16];
+                tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * HC + c0), v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = n0 + c0 + j;
-                        if (col < N) { if (c == 0) epi.store(row, col, v[j], prev[j]); else epi.accumulate(row, col, v[j], prev[j]); }
-                    }
-                }
+                for (int j = 0; j < 16; ++j) run[c0 + j] += __uint_as_float(v[j]);        // FP32 round-to-nearest
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive1(&tmem_empty[buf]);
+        }
+        if (row < M) {
+#pragma unroll
+            for (int c0 = 0; c0 < HC; c0 += 16) {
+                // the loads of the old C are issued in batches before the stores (a load->store->load chain cost ~0.4 ms per GEMM)
+                typename Epi::prev_t prev[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = n0 + half * HC + c0 + j;
+                    if (col < N) prev[j] = epi.load(row, col);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = n0 + half * HC + c0 + j;
+                    if (col < N) epi.store(row, col, __float_as_uint(run[c0 + j]), prev[j]);
+                }
+            }
         }
     }
     tc_fence_before();
@@ -1159,7 +1174,7 @@ cudaError_t gemm_f32_umma(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t 
         attr = true;
     }
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
-    umma_gemm_kernel<KIND_TF32, EpiF32><<<grid, THREADS, SMEM_BYTES, st>>>(mA, mB, (int)M, (int)N, (int)Kp, segs, epi);
+    umma_gemm_kernel<KIND_TF32, EpiF32><<<grid, THREADS_F32, SMEM_BYTES, st>>>(mA, mB, (int)M, (int)N, (int)Kp, segs, epi);
     g_gemm_launches = 3;
     return cudaGetLastError();
 }

@@ -47,6 +47,7 @@ def lib():
         "rdb_ctx_synchronize": (i32, [vp]),
         "rdb_ctx_set_gemm_f64_mode": (i32, [vp, i32, i32]),
         "rdb_ctx_gemm_guard": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(f64)]),
+        "rdb_tape_set_async": (i32, [vp, i32]),
         "rdb_tape_guard_stats": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(f64)]),
         "rdb_comm_unique_id": (i32, [vp]),
         "rdb_comm_create": (vp, [vp, i32, i32, vp]),
@@ -80,7 +81,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "rdb_version", "rdb_last_error", "rdb_ctx_create", "rdb_ctx_destroy", "rdb_ctx_set_stream",
-    "rdb_ctx_synchronize", "rdb_ctx_set_gemm_f64_mode", "rdb_ctx_gemm_guard", "rdb_tape_guard_stats", "rdb_comm_unique_id",
+    "rdb_ctx_synchronize", "rdb_ctx_set_gemm_f64_mode", "rdb_ctx_gemm_guard", "rdb_tape_guard_stats", "rdb_tape_set_async", "rdb_comm_unique_id",
     "rdb_comm_create", "rdb_comm_destroy", "rdb_gather_result", "rdb_place_block", "rdb_tape_load", "rdb_tape_destroy", "rdb_tape_set_input", "rdb_forward",
     "rdb_reverse_scalar_seed", "rdb_gradient", "rdb_jacobian", "rdb_hessian", "rdb_get_value", "rdb_get_deriv",
     "rdb_buffer_size", "rdb_tape_stats", "rdb_tape_launch_count", "rdb_gemm", "rdb_add_sum", "rdb_plan_col_panels", "rdb_schedule_bundles",
@@ -374,6 +375,10 @@ class EngineTape:
         buf = C.create_string_buffer(1 << 20)
         _check(lib().rdb_tape_stats(self.ptr, buf, len(buf)))
         return buf.value.decode()
+
+    def set_async(self, on=True):
+        """``rdb_tape_set_async``: device-result ``hessian!`` calls return without synchronising (``ctx.synchronize()`` waits)."""
+        _check(lib().rdb_tape_set_async(self.ptr, 1 if on else 0))
 
     def guard_stats(self):
         """dict(checked, flagged, fallbacks, worst_ratio): the int8-slice GEMM's accuracy certificate on this tape since load."""
