@@ -185,8 +185,9 @@ __device__ __forceinline__ void mbar_arrive1(uint64_t *bar) {
 constexpr int KCHUNK_BLOCKS = 16;
 constexpr int THREADS_F32 = 64 + 8 * 32;     // TMA warp, MMA warp, 8 epilogue warps
 
+// (10 warps are allocated as 12 - warp allocation granularity 4 - so the budget is 65536 / (12 * 32) = 170 registers per thread)
 template <int KIND, typename Epi>
-__global__ void __maxnreg__(200)
+__global__ void __launch_bounds__(THREADS_F32, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                  Segs segs, Epi epi) {
     extern __shared__ uint8_t smem_raw[];
@@ -890,51 +891,91 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_i8(int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
 }
 
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {      // no wait: batch several, then tc_wait_ld()
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // Epilogue shared by the gen-2 kernels: the S int32 accumulators of a 128 x 64 tile (TMEM columns d*64 .. d*64+63) are assembled
-// into FP64 in registers, smallest weight first, scaled by alpha * 2^(ea[row] + eb[col]) and written once; the guard's two maxima
-// (OzParams) ride along.  Warp q4 owns TMEM lanes [32 q4, 32 q4 + 32) = tile rows.
+// into FP64, scaled by alpha * 2^(ea[row] + eb[col]) and written once.  Warp q4 owns TMEM lanes [32 q4, 32 q4 + 32) = tile rows.
+//  * the S tcgen05.ld of a 16-column block are issued back to back and waited for once (7 round trips per block were serialised);
+//  * accumulators are first combined EXACTLY three at a time in 64-bit integers (D_d carries weight 2^(-b(d+2)), so
+//    D_{3g} 2^(2b) + D_{3g+1} 2^b + D_{3g+2} < 2^(31+2b) <= 2^47 shares the weight 2^(-b(3g+4))): ceil(S/3) int->double
+//    conversions and FP64 adds per element instead of S of each, and fewer roundings (smallest group first);
+//  * the guard's two maxima ride along: max |term| through the high word of the double (integer max; an underestimate by at most
+//    2^-20, i.e. on the safe side), the error bound once per thread from the tile's column maxima (G is monotone in them).
 template <int S>
 __device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int lane, int m0, int n0, int M, int N, const OzParams &P) {
     const int row = m0 + q4 * 32 + lane;
-    const double rs = row < M ? P.alpha * P.sa[row] : 0.0;
-    const double la = (P.guard && row < M) ? P.la[row] : 0.0, hna = (P.guard && row < M) ? P.g_h * P.na[row] : 0.0;
-    double gmax = 0.0, bmax = 0.0;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN2; c0 += 32) {
-        double sum[32];
+    const bool live = row < M;
+    const double rs = live ? P.alpha * P.sa[row] : 0.0;
+    constexpr int NG = (S + 2) / 3;
+    double wg[NG];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum[j] = 0.0;
+    for (int g = 0; g < NG; ++g) {
+        const int last = (3 * g + 2 < S) ? 3 * g + 2 : S - 1;                       // weight of the group's LAST member
+        wg[g] = scalbn(1.0, -P.bits * (last + 2));
+    }
+    int gmax_hi = 0;
 #pragma unroll 1
-        for (int d = S - 1; d >= 0; --d) {                          // smallest terms first
-            uint32_t v[32];
-            tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(d * BN2 + c0), v);
-            const double w = scalbn(1.0, -P.bits * (d + 2));
+    for (int c0 = 0; c0 < BN2; c0 += 16) {
+        uint32_t v[S][16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum[j] += (double)(int)v[j] * w;      // exact products, FP64 adds
+        for (int d = 0; d < S; ++d) tc_ld16_issue(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(d * BN2 + c0), v[d]);
+        tc_wait_ld();
+        if (!live) continue;
+        double prev[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int col = n0 + c0 + j;
+            prev[j] = (col < N && P.beta != 0.0) ? P.C[row + (int64_t)col * P.ldc] : 0.0;
         }
-        if (row < M) {
-            double prev[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int col = n0 + c0 + j;
-                prev[j] = (col < N && P.beta != 0.0) ? P.C[row + (int64_t)col * P.ldc] : 0.0;
-            }
+        for (int j = 0; j < 16; ++j) {
+            const int col = n0 + c0 + j;
+            if (col >= N) continue;
+            double sum = 0.0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int col = n0 + c0 + j;
-                if (col < N) {
-                    const double w = rs * P.sb[col], term = sum[j] * w;
-                    if (P.guard) {
-                        const double hnb = P.g_h * P.nb[col];
-                        const double G = P.g_rho * (fmin(la, hnb) + fmin(P.lb[col], hna)) + P.g_drop * fmin(hna, hnb) / P.g_h;
-                        gmax = fmax(gmax, fabs(term)); bmax = fmax(bmax, fabs(w) * G);
-                    }
-                    P.C[row + (int64_t)col * P.ldc] = P.beta * prev[j] + term;
-                }
+            for (int g = NG - 1; g >= 0; --g) {                                        // smallest weight first
+                const int last = (3 * g + 2 < S) ? 3 * g + 2 : S - 1;
+                long long acc = 0;
+#pragma unroll
+                for (int d = 3 * g; d <= last; ++d) acc += (long long)(int)v[d][j] << (P.bits * (last - d));
+                sum += (double)acc * wg[g];
             }
+            const double term = sum * (rs * P.sb[col]);
+            gmax_hi = max(gmax_hi, __double2hiint(term) & 0x7fffffff);
+            P.C[row + (int64_t)col * P.ldc] = P.beta * prev[j] + term;
         }
     }
-    if (P.guard) guard_record(P.guard, gmax, bmax, lane);
+    if (P.guard) {
+        // column maxima of (scale, 1-norm, nnz) over the tile's 64 columns, then ONE bound per thread (row)
+        double sbm = 0.0, lbm = 0.0, nbm = 0.0;
+#pragma unroll
+        for (int h = 0; h < BN2; h += 32) {
+            const int col = n0 + h + lane;
+            if (col < N) { sbm = fmax(sbm, fabs(P.sb[col])); lbm = fmax(lbm, P.lb[col]); nbm = fmax(nbm, P.nb[col]); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sbm = fmax(sbm, __shfl_xor_sync(0xffffffffu, sbm, o));
+            lbm = fmax(lbm, __shfl_xor_sync(0xffffffffu, lbm, o));
+            nbm = fmax(nbm, __shfl_xor_sync(0xffffffffu, nbm, o));
+        }
+        double bnd = 0.0;
+        if (live) {
+            const double la = P.la[row], na = P.na[row];
+            const double G = P.g_rho * (fmin(la, P.g_h * nbm) + fmin(lbm, P.g_h * na)) + P.g_drop * fmin(na, nbm);
+            bnd = fabs(rs) * sbm * G;
+        }
+        gmax_hi = __reduce_max_sync(0xffffffffu, gmax_hi);
+        guard_record(P.guard, __hiloint2double(gmax_hi, 0), bnd, lane);
+    }
 }
 
 template <int S, int KB>
