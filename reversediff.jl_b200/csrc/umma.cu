@@ -1175,6 +1175,153 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
     }
 }
+
+// --------------------------------------------------------------------------------------------------
+// CTA-PAIR variant (cta_group::2).  The cluster kernel above runs its main loop at ~79 % of the int8 pipe: per 64-byte K-block
+// the MMAs read 192 KB of operands from shared memory and TMA writes 92 KB into it - 2.27 k clk of a 128 B/clk port against
+// 1.79 k clk of tensor work (K-sweep in profiles/README.md: 0.27 ms per 1024 of K at 4096 x 4096).  Here two CTAs with ADJACENT
+// m-blocks issue ONE tcgen05.mma with M = 256: each CTA keeps its own 128 rows of every A slice (no multicast, no zero slot) and
+// supplies only HALF of the N rows of every B operand, which halves the B reads (112 -> 56 KB) and needs no duplicate of A.
+//
+// The two halves of a B operand must sit at the SAME shared-memory offset in both CTAs (one descriptor serves the pair), the
+// leader's rows first in D.  With the merged-N trick (one MMA covers the B slices q0 .. q0+nq-1 of one A slice p, accumulators
+// d = p+q contiguous in TMEM) that fixes what each CTA holds per group:
+//      group            leader (rank 0)      peer (rank 1)        used for (p)            D
+//      {0,1,2,3} N=256  s0 s1                s2 s3                0 1 2 3                 acc p   .. p+3
+//      {4,5}     N=128  s4                   s5                   0 1                     acc p+4 .. p+5
+//      {0,1}     N=128  s0 (second copy)     s1                   4 5                     acc p   .. p+1
+//      {6} {4} {2} {0}  N=64: rows 0..31     rows 32..63          0 2 4 6 respectively    acc 6
+// i.e. 6 slice-equivalents of B per CTA and stage (24 KB, 28 before) and 12 MMAs per 32-byte k-step (10 before):
+// A reads 96 KB + B reads 56 KB + TMA writes 80 KB = 232 KB = 1.81 k clk per K-block - level with the 1.79 k clk of tensor work.
+// Every one of the 28 slice pairs with p + q <= 6 is issued exactly once: nothing is wasted, no scratch accumulator is needed.
+// TMA: both CTAs load with .cta_group::2 and signal the LEADER's full barrier (peer bit of the barrier address cleared); the
+// leader's tcgen05.commit arrives on the empty barrier of both CTAs.  Only S = 7 x 8-bit digits (the default) is built this way.
+__device__ __forceinline__ void tma_load_3d_2sm(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ constexpr uint32_t make_idesc_i8_pair(int n) {          // M = 256 across the pair
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+constexpr int PAIR_A_SLICE = BM2 * 64, PAIR_B_SLICE = BN2 * 64;                     // 8 KB, 4 KB
+constexpr int PAIR_STAGE = 7 * PAIR_A_SLICE + 6 * PAIR_B_SLICE;                     // 56 KB + 24 KB
+__host__ __device__ constexpr int smem_bytes_pair() { return 2 * PAIR_STAGE + 1024 + 256; }
+
+__global__ void __launch_bounds__(THREADS, 1)
+umma_ozaki2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmB1,
+                    const __grid_constant__ CUtensorMap tmBh, int M, int N, int K, OzParams P) {
+    constexpr int S = 7, KB = 64, STAGES2 = 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + STAGES2 * PAIR_STAGE);
+    uint64_t *empty = full + STAGES2;
+    uint64_t *tmem_full = empty + STAGES2;
+    uint32_t *tmem_ptr = (uint32_t *)(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();                     // 0 = leader: issues every MMA of the pair
+    int pair_m, n_tile;
+    raster((int)(blockIdx.x / 2 + (gridDim.x / 2) * blockIdx.y), (int)(gridDim.x / 2), (int)gridDim.y, P.group_m > 1 ? P.group_m / 2 : 1, pair_m, n_tile);
+    const int m0 = (pair_m * 2 + (int)crank) * BM2, n0 = n_tile * BN2;
+    const int kblocks = (K + KB - 1) / KB;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                              // one warp of EACH CTA, same smem slot for the address
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                           // both CTAs' barriers exist before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % STAGES2;
+                const uint32_t ph = (kb / STAGES2) & 1;
+                mbar_wait(&empty[s], ph ^ 1);                     // the leader's commit released this stage in both CTAs
+                if (crank == 0) mbar_expect_tx(&full[s], 2 * PAIR_STAGE);     // the bytes of BOTH CTAs land on the leader's barrier
+                uint8_t *st = smem + s * PAIR_STAGE, *b = st + 7 * PAIR_A_SLICE;
+                const int k0 = kb * KB;
+                tma_load_3d_2sm(st, &tmA, &full[s], k0, m0, 0);                                    // my 128 rows of all 7 A slices
+                const int r = (int)crank;
+                tma_load_3d_2sm(b, &tmB2, &full[s], k0, n0, 2 * r);                                // {0,1,2,3}: s0 s1 | s2 s3
+                tma_load_3d_2sm(b + 2 * PAIR_B_SLICE, &tmB1, &full[s], k0, n0, 4 + r);             // {4,5}:     s4    | s5
+                tma_load_3d_2sm(b + 3 * PAIR_B_SLICE, &tmB1, &full[s], k0, n0, r);                 // {0,1}:     s0    | s1
+#pragma unroll
+                for (int h = 0; h < 4; ++h)                                                          // {6} {4} {2} {0}: rows 0..31 | 32..63
+                    tma_load_3d_2sm(b + 4 * PAIR_B_SLICE + h * (PAIR_B_SLICE / 2), &tmBh, &full[s], k0, n0 + 32 * r, 6 - 2 * h);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && crank == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % STAGES2;
+                const uint32_t ph = (kb / STAGES2) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(smem + s * PAIR_STAGE), b0 = a0 + 7 * PAIR_A_SLICE;
+                const uint32_t bG4 = b0, bG45 = b0 + 2 * PAIR_B_SLICE, bG01 = b0 + 3 * PAIR_B_SLICE, bH = b0 + 4 * PAIR_B_SLICE;
+                auto acc = [&](int d) { return tmem_base + (uint32_t)(d * BN2); };
+#pragma unroll
+                for (int k = 0; k < KB / 32; ++k) {
+                    const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;           // p = 0 touches every accumulator first
+                    auto A = [&](int p) { return make_desc_kb<KB>(a0 + p * PAIR_A_SLICE) + 2 * k; };
+                    auto B = [&](uint32_t addr) { return make_desc_kb<KB>(addr) + 2 * k; };
+                    // p = 0
+                    tc_mma_i8_2sm(acc(0), A(0), B(bG4), make_idesc_i8_pair(256), first);
+                    tc_mma_i8_2sm(acc(4), A(0), B(bG45), make_idesc_i8_pair(128), first);
+                    tc_mma_i8_2sm(acc(6), A(0), B(bH), make_idesc_i8_pair(64), first);
+                    // p = 1
+                    tc_mma_i8_2sm(acc(1), A(1), B(bG4), make_idesc_i8_pair(256), 1u);
+                    tc_mma_i8_2sm(acc(5), A(1), B(bG45), make_idesc_i8_pair(128), 1u);
+                    // p = 2
+                    tc_mma_i8_2sm(acc(2), A(2), B(bG4), make_idesc_i8_pair(256), 1u);
+                    tc_mma_i8_2sm(acc(6), A(2), B(bH + PAIR_B_SLICE / 2), make_idesc_i8_pair(64), 1u);
+                    // p = 3
+                    tc_mma_i8_2sm(acc(3), A(3), B(bG4), make_idesc_i8_pair(256), 1u);
+                    // p = 4
+                    tc_mma_i8_2sm(acc(4), A(4), B(bG01), make_idesc_i8_pair(128), 1u);
+                    tc_mma_i8_2sm(acc(6), A(4), B(bH + 2 * (PAIR_B_SLICE / 2)), make_idesc_i8_pair(64), 1u);
+                    // p = 5
+                    tc_mma_i8_2sm(acc(5), A(5), B(bG01), make_idesc_i8_pair(128), 1u);
+                    // p = 6
+                    tc_mma_i8_2sm(acc(6), A(6), B(bH + 3 * (PAIR_B_SLICE / 2)), make_idesc_i8_pair(64), 1u);
+                }
+                tc_commit_2sm_mc(&empty[s], 0b11);                // frees the stage in both CTAs when these MMAs retire
+            }
+            tc_commit_2sm_mc(tmem_full, 0b11);                    // accumulators complete in both CTAs
+        }
+    } else {
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        oz2_epilogue<S>(tmem_base, warp & 3, lane, m0, n0, M, N, P);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                           // neither CTA frees TMEM / exits while the pair is still at work
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
 }  // namespace oz2
 
 }  // namespace umma
@@ -1508,6 +1655,32 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
             !make_map(&mB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2, kbytes, nslices, b_stride))
             return cudaErrorInvalidValue;
         dim3 grid2((unsigned)((M + BM2 - 1) / BM2), (unsigned)((N + BN2 - 1) / BN2));
+        static int pair = -1;
+        if (pair < 0) { const char *e = getenv("RDB_OZAKI_PAIR"); pair = e ? atoi(e) : 1; }
+        if (pair && nslices == 7 && ozaki_bits() == 8 && kbytes == 64 && !getenv("RDB_OZAKI_CLUSTER")) {
+            // CTA pairs along m (cta_group::2): see umma_ozaki2p_kernel
+            CUtensorMap mAp, mB2, mB1, mBh;
+            if (!make_map(&mAp, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, 64, nslices, a_stride) ||
+                !make_map(&mB2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2, 64, 2, b_stride) ||
+                !make_map(&mB1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2, 64, 1, b_stride) ||
+                !make_map(&mBh, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2 / 2, 64, 1, b_stride))
+                return cudaErrorInvalidValue;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2u * (unsigned)((M + 2 * BM2 - 1) / (2 * BM2)), (unsigned)((N + BN2 - 1) / BN2));
+            cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes_pair(); cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            static bool attrp = false;
+            if (!attrp) {
+                cudaError_t e = cudaFuncSetAttribute(umma_ozaki2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_pair());
+                if (e != cudaSuccess) return e;
+                attrp = true;
+            }
+            int Mi = (int)M, Ni = (int)N, Ki = (int)Kp;
+            return cudaLaunchKernelEx(&cfg, umma_ozaki2p_kernel, mAp, mB2, mB1, mBh, Mi, Ni, Ki, P);
+        }
         static int cl = -1;
         if (cl < 0) { const char *e = getenv("RDB_OZAKI_CLUSTER"); cl = e ? atoi(e) : 2; if (cl != 1 && cl != 2 && cl != 4) cl = 1; }
         if ((nslices == 8 || nslices == 7) && kbytes == 64 && cl > 1 && grid2.y % cl == 0) {
