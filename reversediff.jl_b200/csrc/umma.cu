@@ -702,6 +702,7 @@ struct OzParams {
     unsigned long long *guard;
     const double *la, *na, *lb, *nb;   // per row of op(A) / column of op(B): 1-norm in units of the scale, number of non-zeros
     double g_rho, g_h, g_drop;         // guard_coeffs()
+    int dbg;                           // timing experiments only (RDB_OZAKI_DBG): 1 = no TMA loads, 2 = no epilogue; results are garbage
 };
 
 // |x - x~| <= 2^(e - bS - 1) per element (rint), |x| <= 2^e / 4 (b = 8) or 2^e / 2 (b = 7), and the slice pairs with p + q >= S
@@ -891,26 +892,32 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_i8(int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM2 >> 4) << 24);
 }
 
-__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {      // no wait: batch several, then tc_wait_ld()
+__device__ __forceinline__ void tc_ld8_issue(uint32_t taddr, uint32_t (&v)[8]) {        // no wait: batch several, then tc_wait_ld()
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
         : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Epilogue warps of the gen-2 kernels: EPI_CB column blocks x 4 TMEM lane quarters.  With 4 warps (one per scheduler) the epilogue
+// was a single dependent instruction stream per scheduler and cost 0.15 ms of a 1.30 ms 4096^3 launch (timing experiment with the
+// epilogue switched off, profiles/README.md); 16 warps hide that latency.
+constexpr int EPI_CB = 4;
+constexpr int OZ_THREADS = 64 + 128 * EPI_CB;
+
 // Epilogue shared by the gen-2 kernels: the S int32 accumulators of a 128 x 64 tile (TMEM columns d*64 .. d*64+63) are assembled
-// into FP64, scaled by alpha * 2^(ea[row] + eb[col]) and written once.  Warp q4 owns TMEM lanes [32 q4, 32 q4 + 32) = tile rows.
-//  * the S tcgen05.ld of a 16-column block are issued back to back and waited for once (7 round trips per block were serialised);
+// into FP64, scaled by alpha * 2^(ea[row] + eb[col]) and written once.  Warp (q4, cb) owns TMEM lanes [32 q4, 32 q4 + 32) = tile rows
+// and the columns [cb CW, cb CW + CW), CW = 64 / EPI_CB.
+//  * the S tcgen05.ld of an 8-column block are issued back to back and waited for once;
 //  * accumulators are first combined EXACTLY three at a time in 64-bit integers (D_d carries weight 2^(-b(d+2)), so
 //    D_{3g} 2^(2b) + D_{3g+1} 2^b + D_{3g+2} < 2^(31+2b) <= 2^47 shares the weight 2^(-b(3g+4))): ceil(S/3) int->double
 //    conversions and FP64 adds per element instead of S of each, and fewer roundings (smallest group first);
 //  * the guard's two maxima ride along: max |term| through the high word of the double (integer max; an underestimate by at most
-//    2^-20, i.e. on the safe side), the error bound once per thread from the tile's column maxima (G is monotone in them).
+//    2^-20, i.e. on the safe side), the error bound once per thread from the column maxima of the warp's block (G is monotone in them).
 template <int S>
-__device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int lane, int m0, int n0, int M, int N, const OzParams &P) {
+__device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int cb, int lane, int m0, int n0, int M, int N, const OzParams &P) {
+    constexpr int CW = BN2 / EPI_CB;
     const int row = m0 + q4 * 32 + lane;
     const bool live = row < M;
     const double rs = live ? P.alpha * P.sa[row] : 0.0;
@@ -923,20 +930,20 @@ __device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int lan
     }
     int gmax_hi = 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN2; c0 += 16) {
-        uint32_t v[S][16];
+    for (int c0 = cb * CW; c0 < (cb + 1) * CW; c0 += 8) {
+        uint32_t v[S][8];
 #pragma unroll
-        for (int d = 0; d < S; ++d) tc_ld16_issue(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(d * BN2 + c0), v[d]);
+        for (int d = 0; d < S; ++d) tc_ld8_issue(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(d * BN2 + c0), v[d]);
+        double prev[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                                                  // the old C (beta != 0) travels under the TMEM loads
+            const int col = n0 + c0 + j;
+            prev[j] = (live && col < N && P.beta != 0.0) ? P.C[row + (int64_t)col * P.ldc] : 0.0;
+        }
         tc_wait_ld();
         if (!live) continue;
-        double prev[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int col = n0 + c0 + j;
-            prev[j] = (col < N && P.beta != 0.0) ? P.C[row + (int64_t)col * P.ldc] : 0.0;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const int col = n0 + c0 + j;
             if (col >= N) continue;
             double sum = 0.0;
@@ -954,12 +961,11 @@ __device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int lan
         }
     }
     if (P.guard) {
-        // column maxima of (scale, 1-norm, nnz) over the tile's 64 columns, then ONE bound per thread (row)
+        // column maxima of (scale, 1-norm, nnz) over the warp's CW columns, then ONE bound per thread (row)
         double sbm = 0.0, lbm = 0.0, nbm = 0.0;
-#pragma unroll
-        for (int h = 0; h < BN2; h += 32) {
-            const int col = n0 + h + lane;
-            if (col < N) { sbm = fmax(sbm, fabs(P.sb[col])); lbm = fmax(lbm, P.lb[col]); nbm = fmax(nbm, P.nb[col]); }
+        {
+            const int col = n0 + cb * CW + lane;
+            if (lane < CW && col < N) { sbm = fabs(P.sb[col]); lbm = P.lb[col]; nbm = P.nb[col]; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -979,7 +985,7 @@ __device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int lan
 }
 
 template <int S, int KB>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(OZ_THREADS, 1)
 umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, OzParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1054,7 +1060,7 @@ umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else {
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        oz2_epilogue<S>(tmem_base, warp & 3, lane, m0, n0, M, N, P);
+        oz2_epilogue<S>(tmem_base, warp & 3, (warp - 2) >> 2, lane, m0, n0, M, N, P);
     }
     tc_fence_before();
     __syncthreads();
@@ -1089,7 +1095,7 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask) {
 }
 
 template <int S, int CL>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(OZ_THREADS, 1)
 umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, OzParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1132,6 +1138,7 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
                 const int s = kb % STAGES2;
                 const uint32_t ph = (kb / STAGES2) & 1;
                 mbar_wait(&empty[s], ph ^ 1);                     // all CL consumers released this stage (in every CTA)
+                if (P.dbg & 1) { mbar_expect_tx(&full[s], 0); continue; }
                 mbar_expect_tx(&full[s], STAGE);                  // bytes landing in MY smem: S A-slices (CL multicasts) + my B slices
                 tma_load_3d_mc(smem + s * STAGE + crank * SL * A_SLICE, &tmAmc, &full[s], kb * KB, m0, crank * SL, MASK);
                 tma_load_3d(smem + s * STAGE + SA * A_SLICE, &tmB, &full[s], kb * KB, n0, 0);
@@ -1166,7 +1173,7 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
     } else {
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        oz2_epilogue<S>(tmem_base, warp & 3, lane, m0, n0, M, N, P);
+        if (!(P.dbg & 2)) oz2_epilogue<S>(tmem_base, warp & 3, (warp - 2) >> 2, lane, m0, n0, M, N, P);
     }
     tc_fence_before();
     __syncthreads();
@@ -1219,7 +1226,7 @@ constexpr int PAIR_A_SLICE = BM2 * 64, PAIR_B_SLICE = BN2 * 64;                 
 constexpr int PAIR_STAGE = 7 * PAIR_A_SLICE + 6 * PAIR_B_SLICE;                     // 56 KB + 24 KB
 __host__ __device__ constexpr int smem_bytes_pair() { return 2 * PAIR_STAGE + 1024 + 256; }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(OZ_THREADS, 1)
 umma_ozaki2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmB1,
                     const __grid_constant__ CUtensorMap tmBh, int M, int N, int K, OzParams P) {
     constexpr int S = 7, KB = 64, STAGES2 = 2;
@@ -1258,6 +1265,7 @@ umma_ozaki2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int s = kb % STAGES2;
                 const uint32_t ph = (kb / STAGES2) & 1;
                 mbar_wait(&empty[s], ph ^ 1);                     // the leader's commit released this stage in both CTAs
+                if (P.dbg & 1) { if (crank == 0) mbar_expect_tx(&full[s], 0); continue; }
                 if (crank == 0) mbar_expect_tx(&full[s], 2 * PAIR_STAGE);     // the bytes of BOTH CTAs land on the leader's barrier
                 uint8_t *st = smem + s * PAIR_STAGE, *b = st + 7 * PAIR_A_SLICE;
                 const int k0 = kb * KB;
@@ -1313,7 +1321,7 @@ umma_ozaki2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        oz2_epilogue<S>(tmem_base, warp & 3, lane, m0, n0, M, N, P);
+        if (!(P.dbg & 2)) oz2_epilogue<S>(tmem_base, warp & 3, (warp - 2) >> 2, lane, m0, n0, M, N, P);
     }
     tc_fence_before();
     __syncthreads();
@@ -1644,7 +1652,8 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     guard_coeffs(ozaki_bits(), nslices, g_rho, g_h, g_drop);
     // the row statistics sit `rows` apart behind the scales (the rows of the whole operand when this is a window of it)
     const int64_t ra = a_stride ? a_stride : M, rb = b_stride ? b_stride : N;
-    OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m, ozaki_bits(), gslot, sa + ra, sa + 2 * ra, sb + rb, sb + 2 * rb, g_rho, g_h, g_drop};
+    static const int dbg = [] { const char *e = getenv("RDB_OZAKI_DBG"); return e ? atoi(e) : 0; }();
+    OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m, ozaki_bits(), gslot, sa + ra, sa + 2 * ra, sb + rb, sb + 2 * rb, g_rho, g_h, g_drop, dbg};
     static int gen = -1;
     if (gen < 0) { const char *e = getenv("RDB_OZAKI_GEN"); gen = e ? atoi(e) : 2; }
     if (gen == 2 && nslices <= 8) {
@@ -1667,7 +1676,7 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
                 return cudaErrorInvalidValue;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(2u * (unsigned)((M + 2 * BM2 - 1) / (2 * BM2)), (unsigned)((N + BN2 - 1) / BN2));
-            cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes_pair(); cfg.stream = st;
+            cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = smem_bytes_pair(); cfg.stream = st;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1688,7 +1697,7 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
             CUtensorMap mAmc;
             if (!make_map(&mAmc, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, kbytes, (nslices + cl - 1) / cl, a_stride)) return cudaErrorInvalidValue;
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = grid2; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem_bytes_cluster(nslices, cl); cfg.stream = st;
+            cfg.gridDim = grid2; cfg.blockDim = dim3(OZ_THREADS); cfg.dynamicSmemBytes = smem_bytes_cluster(nslices, cl); cfg.stream = st;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = (unsigned)cl; at[0].val.clusterDim.z = 1;
@@ -1719,8 +1728,8 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
             if (e != cudaSuccess) return e;                                                                                \
             attr2 = true;                                                                                                  \
         }                                                                                                                  \
-        if (kbytes == 64) umma_ozaki2_kernel<SS, 64><<<grid2, THREADS, smem_bytes(SS, 64), st>>>(mA, mB, (int)M, (int)N, (int)Kp, P); \
-        else umma_ozaki2_kernel<SS, 32><<<grid2, THREADS, smem_bytes(SS, 32), st>>>(mA, mB, (int)M, (int)N, (int)Kp, P);   \
+        if (kbytes == 64) umma_ozaki2_kernel<SS, 64><<<grid2, OZ_THREADS, smem_bytes(SS, 64), st>>>(mA, mB, (int)M, (int)N, (int)Kp, P); \
+        else umma_ozaki2_kernel<SS, 32><<<grid2, OZ_THREADS, smem_bytes(SS, 32), st>>>(mA, mB, (int)M, (int)N, (int)Kp, P);   \
     } break;
         switch (nslices) { RDB_OZ2(2) RDB_OZ2(3) RDB_OZ2(4) RDB_OZ2(5) RDB_OZ2(6) RDB_OZ2(7) RDB_OZ2(8) default: return cudaErrorInvalidValue; }
 #undef RDB_OZ2
