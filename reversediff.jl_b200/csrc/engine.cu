@@ -174,6 +174,10 @@ struct rdb_tape {
     int64_t guard_checked = 0, guard_flagged = 0, guard_fallbacks = 0;
     double guard_worst = 0;
     bool async = false;            // rdb_tape_set_async: calls with device results and no host outputs return without synchronising
+    // hessian! of sum|mean(g.(views of x)) with a device result and nothing else requested: one fused kernel (kernels.cu
+    // k_hessian_separable); state 0 = not examined yet, 1 = planned, -1 = the tape does not have that shape
+    struct SepHess { int state = 0; int ew = -1; double delta = 1.0; const int64_t *map[kMaxArgs] = {nullptr}; int64_t *d_inv_off = nullptr, *d_inv = nullptr;
+                     const void *lazy_x = nullptr; bool x_consumed = false; } sep;
     int hess_prefill = 0;          // hessian!: the result block's zero-fill runs on a side stream next to the small kernels (1), not (-1), unknown (0)
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     int guard_streak = 0;          // consecutive calls whose certificate failed; 3 make the tape DMMA-only for good
@@ -624,6 +628,14 @@ static void plan_col_panels(int64_t rows, int64_t cols, int64_t width[4]) {
 // Inputs uploaded in panels (rdb_tape_set_input): make the main stream wait for them.  `keep` is left pending (its consumer
 // waits panel by panel).
 static int settle_uploads(rdb_tape *t, int keep) {
+    if (t->sep.lazy_x) {                        // a device input that the one-kernel hessian! would have read in place: copy it now
+        Buf &x = t->bufs[t->inputs[0]];
+        CU(cudaMemcpyAsync(x.val, t->sep.lazy_x, (size_t)x.size * t->es, cudaMemcpyDeviceToDevice, S(t)));
+        t->sep.lazy_x = nullptr;
+    } else if (t->sep.x_consumed) {
+        return fail(RDB_EINVAL, "the device input was read in place by an asynchronous hessian! call and never copied into the tape: "
+                                "call rdb_tape_set_input again before this entry point");
+    }
     for (size_t b = 0; b < t->bufs.size(); ++b) {
         Buf &B = t->bufs[b];
         if (B.up_n == 0 || (int)b == keep) continue;
@@ -1922,8 +1934,90 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
 // hessian! entry: launch-bound tapes with a device result replay the whole sweep (forward with second partials, first- and
 // second-order reverse, result block written in place) as ONE captured graph.  First call with a given (columns, result, ld)
 // runs eagerly and warms every lazy allocation, the second captures, later ones only launch.
+// ---- hessian! fast path: the tape is  v_1 = x[idx_1], ..., v_k = x[idx_k];  y = g.(v...) (or of x itself);  out = sum|mean(y).
+// Then H = sum_i delta * d2g(x[maps(i)]) scattered at (map_p(i), map_q(i)): every column holds a handful of entries, and the call is
+// the zero-fill of the block plus those entries - one kernel, no forward sweep, no tangents (src/api/hessians.jl:86-90 asks for
+// the matrix only).  Values of the intermediates are NOT refreshed (forward_valid stays false).
+template <typename T>
+static int sep_hess_plan(rdb_tape *t) {
+    auto &P = t->sep;
+    P.state = -1;
+    static const bool on = [] { const char *e = getenv("RDB_HESS_FUSED"); return !(e && e[0] == '0'); }();
+    const size_t ni = t->instrs.size();
+    if (!on || t->inputs.size() != 1 || ni < 2) return RDB_OK;
+    auto root = [&](int b) { while (t->bufs[b].alias_of >= 0) b = t->bufs[b].alias_of; return b; };
+    const int rx = root(t->inputs[0]);
+    const int64_t n = t->bufs[rx].size;
+    InstrPlan &R = t->instrs[ni - 1], &E = t->instrs[ni - 2];
+    if ((R.rec.opcode != OP_SUM && R.rec.opcode != OP_MEAN) || root(R.rec.out) != root(t->output) || root(R.in[0].rec.buffer) != root(E.rec.out)) return RDB_OK;
+    if (!is_elementwise(E.rec.opcode) || E.rec.opcode == OP_TRACKER_BCAST || E.rec.expr_len <= 0 || !E.d_ops) return RDB_OK;
+    const int N = E.rec.n_in;
+    const int64_t m = t->bufs[E.rec.out].size;
+    std::vector<int> producer(t->bufs.size(), -1);
+    for (size_t ii = 0; ii + 2 < ni; ++ii) {
+        InstrPlan &G = t->instrs[ii];
+        if (!is_getindex(G.rec.opcode) || root(G.in[0].rec.buffer) != rx || !G.in[0].d_map) return RDB_OK;
+        producer[root(G.rec.out)] = (int)ii;
+    }
+    std::vector<std::vector<int64_t>> maps(N);
+    for (int a = 0; a < N; ++a) {
+        OperandPlan &op = E.in[a];
+        if (!op.rec.tracked || op.rec.cls != CLS_TA || t->bufs[op.rec.buffer].size != m) return RDB_OK;
+        const int rb = root(op.rec.buffer);
+        if (rb == rx) { P.map[a] = nullptr; continue; }            // the argument is x itself (m == n checked above)
+        const int pr = producer[rb];
+        if (pr < 0 || t->instrs[pr].in[0].rec.idx_len != m) return RDB_OK;
+        P.map[a] = t->instrs[pr].in[0].d_map;
+        maps[a].resize(m);
+        CU(cudaMemcpyAsync(maps[a].data(), P.map[a], (size_t)m * 8, cudaMemcpyDeviceToHost, S(t)));
+    }
+    CU(cudaStreamSynchronize(S(t)));
+    std::vector<int64_t> off(n + 1, 0);
+    auto col_of = [&](int a, int64_t i) { return P.map[a] ? maps[a][i] : i; };
+    for (int a = 0; a < N; ++a) for (int64_t i = 0; i < m; ++i) ++off[col_of(a, i) + 1];
+    for (int64_t j = 0; j < n; ++j) { if (off[j + 1] > kSepHessMaxEntries) return RDB_OK; off[j + 1] += off[j]; }
+    std::vector<int64_t> inv(off[n]), fill(off.begin(), off.end() - 1);
+    for (int64_t i = 0; i < m; ++i) for (int a = 0; a < N; ++a) inv[fill[col_of(a, i)]++] = i * N + a;     // ascending (element, argument)
+    OK(dev_alloc(t, (void **)&P.d_inv_off, (n + 1) * 8));
+    OK(dev_alloc(t, (void **)&P.d_inv, std::max<int64_t>(1, off[n]) * 8));
+    CU(cudaMemcpyAsync(P.d_inv_off, off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, S(t)));
+    if (off[n]) CU(cudaMemcpyAsync(P.d_inv, inv.data(), (size_t)off[n] * 8, cudaMemcpyHostToDevice, S(t)));
+    CU(cudaStreamSynchronize(S(t)));
+    P.ew = (int)ni - 2;
+    P.delta = R.rec.opcode == OP_MEAN ? (double)((T)1 / (T)m) : 1.0;
+    P.state = 1;
+    return RDB_OK;
+}
+template <typename T>
+static int sep_hess_run(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64_t ld) {
+    auto &P = t->sep;
+    InstrPlan &E = t->instrs[P.ew];
+    Buf &x = t->bufs[t->inputs[0]];
+    const void *xin = x.val;
+    if (P.lazy_x) { xin = P.lazy_x; P.lazy_x = nullptr; P.x_consumed = true; }     // read in place; the tape's copy is not refreshed
+    else OK(settle_uploads(t, -1));
+    SepHessParams K{};
+    K.n_args = E.rec.n_in; K.n_ops = (int)E.rec.expr_len;
+    for (int a = 0; a < K.n_args; ++a) K.map[a] = P.map[a];
+    K.inv_off = P.d_inv_off; K.inv = P.d_inv; K.ops = E.d_ops; K.fconst = t->d_fconst;
+    K.x = xin; K.n_x = x.size; K.H = result; K.ld = ld; K.c0 = cb; K.K = ce - cb; K.delta = P.delta;
+    {
+        StepTimer tm(t, "hessian_separable", (double)x.size * K.K * t->es, 0);
+        KL(t, launch_hessian_separable<T>(S(t), K));
+    }
+    t->launches += 1;                                       // (KL counted one: the call is a fill kernel + its dependent patch kernel)
+    t->forward_valid = false;
+    if (!t->async) CU(cudaStreamSynchronize(S(t)));
+    return RDB_OK;
+}
+
 template <typename T>
 static int hessian_entry(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64_t ld, int on_device, void *grad_out, void *value_out) {
+    if (on_device && !grad_out && !value_out && ce > cb && t->inputs.size() == 1 && cb >= 0 && ce <= t->bufs[t->inputs[0]].size &&
+        ld >= t->bufs[t->inputs[0]].size && t->bufs[t->output].size == 1) {
+        if (t->sep.state == 0) OK(sep_hess_plan<T>(t));
+        if (t->sep.state == 1) return sep_hess_run<T>(t, cb, ce, result, ld);
+    }
     auto &G = t->hgraph;
     GemmState &GS = t->ctx->gemm;
     const bool want = graph_eligible(t) && on_device && !grad_out && !value_out && ce > cb && t->inputs.size() == 1;
@@ -2147,9 +2241,15 @@ int rdb_tape_set_input(rdb_tape *t, int slot, const void *data, int is_device) {
             b.up_c0[++b.up_n] = c0;
         }
         t->last_upload = t->inputs[slot];
+    } else if (is_device && t->async && t->sep.state == 1 && slot == 0) {
+        // asynchronous mode + the one-kernel hessian!: the kernel reads the caller's array in place (the header already asks for
+        // device inputs to stay alive until the stream is synchronised); any other entry point copies it first (settle_uploads)
+        t->sep.lazy_x = data;
+        t->sep.x_consumed = false;
     } else {
         if (b.up_n > 0) { CU(cudaStreamWaitEvent(S(t), b.up_ev[b.up_n - 1], 0)); b.up_n = 0; }
         CU(cudaMemcpyAsync(b.val, data, (size_t)b.size * t->es, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, S(t)));
+        t->sep.lazy_x = nullptr; t->sep.x_consumed = false;
     }
     bump_version(t, t->inputs[slot]);
     t->forward_valid = false;

@@ -9,6 +9,8 @@
 // normally run the NVRTC-specialised kernels of jit.cu.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
+#include <algorithm>
 #include "kernels.h"
 #include "expr_eval.cuh"
 
@@ -728,6 +730,119 @@ cudaError_t launch_tangent_reverse_sparse(cudaStream_t s, T *td_x, int64_t n_x, 
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------- hessian! of a separable objective, one kernel
+// Two kernels chained by programmatic dependent launch.  The call's HBM traffic is a device fill of the block (7.5 TB/s for a plain
+// fill kernel; a fused kernel whose CTAs also evaluated entries reached 5.3-5.7), so the fill stays a plain fill: many small CTAs
+// in address order, nothing else in them.  It triggers the launch of its dependent at once; the patch kernel - one lane per column -
+// evaluates the second partials of the elements that read x[column] while the fill is still running, waits for the fill to be
+// complete and visible (griddepcontrol.wait), and adds its few values in tape order.  No atomics: a column belongs to one lane.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_fill_block_pdl(T *__restrict__ H, int64_t n, int64_t K, int64_t ld) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    using VT = typename Vec<T>::type;
+    constexpr int V = Vec<T>::N;
+    T zz[V] = {};
+    const VT z = vec_pack<T>(zz);
+    if (ld == n && ((((uintptr_t)H) & 15) == 0)) {                           // the block is one contiguous range
+        VT *dst = reinterpret_cast<VT *>(H);
+        const int64_t tot = K * n, nv = tot / V;
+        const int64_t base = (int64_t)blockIdx.x * (4 * kThreads) + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const int64_t i = base + j * kThreads; if (i < nv) dst[i] = z; }
+        if (blockIdx.x == 0) for (int64_t j = nv * V + threadIdx.x; j < tot; j += kThreads) H[j] = (T)0;
+    } else {
+        const int64_t per_col = (n + 4 * kThreads - 1) / (4 * kThreads);    // CTAs per column
+        const int64_t k = blockIdx.x / per_col, r0 = (blockIdx.x % per_col) * (4 * kThreads);
+        if (k < K) for (int j = 0; j < 4; ++j) { const int64_t i = r0 + j * kThreads + threadIdx.x; if (i < n) H[k * ld + i] = (T)0; }
+    }
+}
+template <typename T, int N>
+__global__ void __launch_bounds__(128) k_hessian_patch(const SepHessParams P) {
+    __shared__ int4 s_ops[kMaxExprRegs];
+    for (int i = threadIdx.x; i < P.n_ops; i += blockDim.x) s_ops[i] = reinterpret_cast<const int4 *>(P.ops)[i];
+    __syncthreads();
+    T *H = reinterpret_cast<T *>(P.H);
+    const T *x = reinterpret_cast<const T *>(P.x);
+    constexpr int kMaxHeld = 4;                      // entries a lane keeps in registers; longer lists are evaluated after the wait
+    int64_t h_row[kMaxHeld * N];
+    T h_val[kMaxHeld * N];
+    int held = 0;
+    auto eval_entry = [&](int64_t e, int64_t *rows, T *vals) {
+        // the element that reads x[c] as its argument q: row map[p][i] of this column gets delta * d2g / dx_p dx_q
+        const int64_t iq = P.inv[e], i = iq / N;
+        const int q = (int)(iq - i * N);
+        T xs[N], val, dd[N], hh[Tri<N>::NH];
+#pragma unroll
+        for (int p = 0; p < N; ++p) { rows[p] = P.map[p] ? P.map[p][i] : i; xs[p] = x[rows[p]]; }
+        eval_expr<T, N, 2>(s_ops, P.n_ops, P.fconst, xs, val, dd, hh);
+#pragma unroll
+        for (int p = 0; p < N; ++p) vals[p] = (T)P.delta * hh[p <= q ? tri(p, q, N) : tri(q, p, N)];
+    };
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t e0 = 0, e1 = 0;
+    if (k < P.K) {
+        e0 = P.inv_off[P.c0 + k]; e1 = P.inv_off[P.c0 + k + 1];
+        if (e1 - e0 <= kMaxHeld)
+            for (int64_t e = e0; e < e1; ++e) { eval_entry(e, h_row + held * N, h_val + held * N); ++held; }
+        else held = -1;
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");                       // the fill is complete and its zeros are visible
+    if (k >= P.K) return;
+    T *col = H + k * P.ld;
+    if (held >= 0) {
+        // the column was zero-filled and belongs to this lane: values that share a row are summed in registers (tape order) and
+        // every touched row is stored once - no read-modify-write round trip after the wait
+#pragma unroll
+        for (int e = 0; e < kMaxHeld * N; ++e) {
+            if (e >= held * N) break;
+            bool first = true;
+#pragma unroll
+            for (int f = 0; f < kMaxHeld * N; ++f) if (f < e && h_row[f] == h_row[e]) first = false;
+            if (!first) continue;
+            T acc = h_val[e];
+#pragma unroll
+            for (int f = 0; f < kMaxHeld * N; ++f) if (f > e && f < held * N && h_row[f] == h_row[e]) acc += h_val[f];
+            col[h_row[e]] = acc;
+        }
+        return;
+    }
+    for (int64_t e = e0; e < e1; ++e) {
+        int64_t rows[N]; T vals[N];
+        eval_entry(e, rows, vals);
+#pragma unroll
+        for (int p = 0; p < N; ++p) col[rows[p]] += vals[p];
+    }
+}
+template <typename T, int N>
+static cudaError_t launch_patch_n(cudaStream_t s, const SepHessParams &P) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((P.K + 127) / 128)); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_hessian_patch<T, N>, P);
+}
+template <typename T>
+cudaError_t launch_hessian_separable(cudaStream_t s, const SepHessParams &P) {
+    if (P.K <= 0) return cudaSuccess;
+    T *H = reinterpret_cast<T *>(P.H);
+    const bool contiguous = P.ld == P.n_x && ((((uintptr_t)H) & 15) == 0);
+    const int64_t per_cta = 4 * kThreads * (contiguous ? Vec<T>::N : 1);
+    const int64_t ctas = contiguous ? (P.K * P.n_x + per_cta - 1) / per_cta : P.K * ((P.n_x + per_cta - 1) / per_cta);
+    if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
+    k_fill_block_pdl<T><<<(unsigned)ctas, kThreads, 0, s>>>(H, P.n_x, P.K, P.ld);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    switch (P.n_args) {
+        case 1: return launch_patch_n<T, 1>(s, P);
+        case 2: return launch_patch_n<T, 2>(s, P);
+        case 3: return launch_patch_n<T, 3>(s, P);
+        case 4: return launch_patch_n<T, 4>(s, P);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_colsum(T *__restrict__ out, const T *__restrict__ x, int64_t n, int64_t K, double scale) {
     int64_t k = blockIdx.x;
@@ -784,6 +899,7 @@ cudaError_t launch_copy2d(cudaStream_t s, T *dst, int64_t ldd, const T *src, int
     template cudaError_t launch_tangent_reverse<T>(cudaStream_t, T *, const T *, const T *, const T *, int, const T *const *, const T *const *, int64_t, int64_t, bool); \
     template cudaError_t launch_gather_cols<T>(cudaStream_t, T *, const T *, int64_t, const int64_t *, int64_t, int64_t); \
     template cudaError_t launch_tangent_reverse_sparse<T>(cudaStream_t, T *, int64_t, int64_t, int64_t, const T *, int, const int64_t *const *, const T *const *, int64_t); \
+    template cudaError_t launch_hessian_separable<T>(cudaStream_t, const SepHessParams &);                               \
     template cudaError_t launch_seed_tangent<T>(cudaStream_t, T *, int64_t, int64_t, int64_t);                            \
     template cudaError_t launch_seed_gather<T>(cudaStream_t, T *, const int64_t *, int64_t, int64_t, int64_t);            \
     template cudaError_t launch_colsum<T>(cudaStream_t, T *, const T *, int64_t, int64_t, T);                             \

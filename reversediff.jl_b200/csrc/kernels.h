@@ -163,6 +163,24 @@ template <typename T> cudaError_t launch_tangent_forward(cudaStream_t, T *tv_out
 // td_p[i+k*n] (+)= dt[i+k*n]*partial_p[i] + delta[i]*sum_q second_pq[i]*tv_q[i+k*n]   (dt may be NULL = known zero)
 template <typename T> cudaError_t launch_tangent_reverse(cudaStream_t, T *td_p, const T *dt, const T *delta, const T *partial_p, int n_args, const T *const *second_pq, const T *const *tv_in, int64_t n, int64_t K, bool overwrite);
 // all arguments are getindex views of the seeded input: td_x[map_p[i] + k*n_x] += delta[i]*second_pq[i] at k = map_q[i] - c0
+// hessian! of f(x) = sum|mean(g.(views of x...)) in ONE kernel (engine.cu: SepHess): column c of the block is zero-filled and the few
+// second partials that land in it are evaluated from x on the spot (inverse index: which (element, argument) pairs read x[c]);
+// one thread applies a column's contributions in tape order, so the result does not depend on scheduling
+struct SepHessParams {
+    int n_args, n_ops;
+    const int64_t *map[kMaxArgs];   // device; NULL = the argument is x itself
+    const int64_t *inv_off;         // n_x + 1
+    const int64_t *inv;             // packed element * n_args + argument, ascending per column
+    const int32_t *ops;             // device, 4 x int32 per op
+    const double *fconst;
+    const void *x;
+    int64_t n_x;
+    void *H;
+    int64_t ld, c0, K;
+    double delta;                   // adjoint of every element of g's output: 1 (sum) or 1 / length (mean)
+};
+constexpr int kSepHessMaxEntries = 32;
+template <typename T> cudaError_t launch_hessian_separable(cudaStream_t, const SepHessParams &);
 template <typename T> cudaError_t launch_tangent_reverse_sparse(cudaStream_t, T *td_x, int64_t n_x, int64_t K, int64_t c0, const T *delta, int n_args, const int64_t *const *maps, const T *const *second_pq /* [p*n_args+q] */, int64_t n);
 // rows gather/scatter for getindex under tangents: out[k + c*n] = src[map[k] + c*src_n]
 template <typename T> cudaError_t launch_gather_cols(cudaStream_t, T *out, const T *src, int64_t src_n, const int64_t *map, int64_t n, int64_t K);

@@ -555,3 +555,81 @@ def test_gemm_path_variants_in_child_process(env):
                        cwd=os.path.dirname(here), env=e, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+@pytest.mark.parametrize("env,select", [({"RDB_HESS_FUSED": "0"}, "cfg5_hessian"),          # hessian!: the general graph-replayed sweep
+                                        ({"RDB_OZAKI_PAIR": "1"}, "cfg2 or panel_sizes")])    # cta_group::2 CTA-pair int8-slice kernel
+def test_alternative_paths_in_child_process(env, select):
+    import subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    e = dict(os.environ); e.update(env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                        "-k", f"({select}) and not child_process", "-p", "no:cacheprovider"],
+                       cwd=os.path.dirname(here), env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+def test_hessian_separable_fast_path_shapes(rd, orc):
+    """The one-kernel hessian! (device result, nothing else requested) against the general sweep (host result) on the shapes the
+    planner accepts: views with a repeated index (two contributions into one entry), `mean`, and a closure of x itself."""
+    import torch
+    E, T = rd.expr, rd.tracked
+    n = 64
+    x0 = np.random.default_rng(3).random(n) + 0.5
+    x = np.random.default_rng(4).random(n) + 0.5
+    ia = [0, 5, 5, 9, 63, 2]; ib = [1, 5, 7, 9, 0, 2]
+
+    def f_views(v):
+        g = T.forward(lambda a, b: a * a * b + E.exp(a * b))
+        return T.mean(T.map_(g, v[ia], v[ib]))
+
+    def f_self(v):
+        return T.sum(T.bcast(lambda a: E.sin(a) * a ** 3, v))
+
+    for f in (f_views, f_self):
+        ct = rd.compile(rd.HessianTape(f, x0))
+        Hh = np.zeros((n, n), order="F")
+        rd.hessian_(Hh, ct, x)                                    # host result: general sweep
+        Hd = torch.full((n * n,), float("nan"), dtype=torch.float64, device="cuda")
+        rd.hessian_(Hd, ct, torch.from_numpy(x).cuda())          # device result: fused kernel
+        Hf = Hd.cpu().numpy().reshape(n, n, order="F")
+        assert relerr(Hf, Hh) < 1e-13
+        assert np.all(Hf[Hh == 0] == 0.0) and np.allclose(Hf, Hf.T, rtol=0, atol=1e-13 * np.max(np.abs(Hf)))
+        part = torch.full((n * 16,), float("nan"), dtype=torch.float64, device="cuda")
+        rd.hessian_(part, ct, torch.from_numpy(x).cuda(), cols=(40, 56))
+        assert np.array_equal(part.cpu().numpy().reshape(n, 16, order="F"), Hf[:, 40:56])
+
+
+def test_hessian_async_reads_device_input_in_place(rd):
+    """rdb_tape_set_async + the one-kernel hessian!: a device input is read in place (no copy into the tape), calls are only
+    enqueued, and an entry point that needs the tape's own copy of the input refuses to run on a stale one."""
+    import torch
+    n = 512
+    ctx = rd.engine.Context(0)
+    ct = rd.compile(rd.HessianTape(rd.workloads.f_rosenbrock, rd.workloads.inputs_rosenbrock(n, seed=1)), ctx=ctx)
+
+    def closed(x):
+        o, e = x[0::2], x[1::2]
+        Hcf = np.zeros((n, n)); idx = np.arange(n // 2)
+        Hcf[2 * idx, 2 * idx] = 1200 * o ** 2 - 400 * e + 2
+        Hcf[2 * idx, 2 * idx + 1] = Hcf[2 * idx + 1, 2 * idx] = -400 * o
+        Hcf[2 * idx + 1, 2 * idx + 1] = 200
+        return Hcf
+    xs = [rd.workloads.inputs_rosenbrock(n, seed=20 + k) for k in range(3)]
+    xd = [torch.from_numpy(x).cuda() for x in xs]
+    Hd = [torch.full((n * n,), float("nan"), dtype=torch.float64, device="cuda") for _ in xs]
+    rd.hessian_(Hd[0], ct, xd[0])                                # synchronous first call: plans the fast path
+    ct.handle.set_async(True)
+    for k in (1, 2):
+        rd.hessian_(Hd[k], ct, xd[k])                            # enqueued only
+    ctx.synchronize()
+    for k in range(3):
+        Hh = Hd[k].cpu().numpy().reshape(n, n, order="F")
+        assert relerr(Hh, closed(xs[k])) < 1e-12 and np.all(Hh[closed(xs[k]) == 0] == 0.0)
+    ct.handle.set_async(False)
+    with pytest.raises(Exception):                               # the tape never received a copy of xd[2]
+        ct.handle.forward()
+    g = np.zeros(n); res = rd.DiffResult(0.0, g, np.zeros((n, n), order="F"))
+    rd.hessian_(res, ct, xs[1])                                  # a fresh set_input: everything works again
+    assert relerr(res.hessian, closed(xs[1])) < 1e-12
