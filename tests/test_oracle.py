@@ -286,3 +286,16 @@ def test_scalar_tape_reverse_over_reverse_rosenbrock(rd, orc):
     tape = rd.HessianTape(rd.workloads.f_rosenbrock, x)
     oval, (og,) = orc.OracleTape(tape.program_bytes()).gradient([x])
     assert relerr(g, og) < 1e-14 and abs(val - oval) < 1e-13 * abs(oval)
+
+
+def test_golden_program_hashes_are_current():
+    """tests/golden/cfg*.program.sha256 is the byte-level contract the Julia lowering (julia/ReverseDiffB200.jl, checked by
+    julia/golden_roundtrip.jl) is held to: the Python recorder must still emit exactly those bytes, or the hashes must be
+    regenerated on purpose (tests/golden/make_program_hashes.py)."""
+    import hashlib, importlib.util, os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_program_hashes", os.path.join(here, "make_program_hashes.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    for name, raw in mod.programs().items():
+        want, size = open(os.path.join(here, f"{name}.program.sha256")).read().split()
+        assert hashlib.sha256(raw).hexdigest() == want and len(raw) == int(size), name
