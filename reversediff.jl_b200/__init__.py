@@ -9,7 +9,7 @@ tape, input)`` — see DESIGN.md.  Recording happens on the host (``tracked.py``
 ``csrc/librdb200.so`` (hand-written sm_100a CUDA) through the C ABI of ``include/rdb200.h``.
 """
 from .tracked import (TrackedArray, TrackedReal, InstructionTape, ForwardOptimize, SkipOptimize,  # noqa: F401
-                      forward, skip, value, istracked, sum, mean, dot, bcast, map_, broadcast, collect)
+                      forward, skip, value, istracked, sum, mean, dot, bcast, map_, broadcast, collect, convert)
 from .expr import (tanh, exp, log, sqrt, sin, cos, abs2, abs_, inv, logistic, max_, min_)          # noqa: F401
 from .api import (GradientTape, JacobianTape, HessianTape, CompiledTape, DiffResult, compile,      # noqa: F401
                   gradient_, jacobian_, hessian_, gradient, jacobian, hessian, seeded_forward_pass, shard_range, shard_bounds,

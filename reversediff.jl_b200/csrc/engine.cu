@@ -132,6 +132,9 @@ struct InstrPlan {
     std::vector<int32_t> h_ops;     // host copy of the scalar program (NVRTC specialisation)
     void *jit_fn[2] = {nullptr, nullptr};   // [reduce]
     bool jit_tried[2] = {false, false};
+    int run_end = -2;                    // elementwise run fusion: last instruction of the run that starts here (-2 = not planned, own index = none)
+    void *run_fn[2] = {nullptr, nullptr};  // [reduce]: the run's NVRTC kernel
+    bool run_tried[2] = {false, false};
     bool rev_done[2] = {false, false};   // `*`: this operand's adjoint was already accumulated in this sweep (paired panels, mul_reverse)
     uint64_t dtag = 0;                   // `*`: identity of deriv(output) for the sliced-operand cache, fixed when first needed in a sweep
 };
@@ -318,9 +321,9 @@ static int preslice_begin(rdb_tape *t);
 static int settle_uploads(rdb_tape *t, int keep);
 static int droot(rdb_tape *t, int b);
 template <typename T>
-static int expr_forward(rdb_tape *t, InstrPlan &I, bool reduce, int order) {
+static int expr_params(rdb_tape *t, InstrPlan &I, bool reduce, int order, ExprParams &p) {
     Buf &out = t->bufs[I.rec.out];
-    ExprParams p{};
+    p = ExprParams{};
     p.n_args = I.rec.n_in; p.n_ops = (int)I.rec.expr_len; p.order = order; p.reduce = reduce ? 1 : 0;
     p.n = out.size;
     for (int d = 0; d < kMaxDims; ++d) p.dims[d] = out.dims[d];
@@ -343,6 +346,81 @@ static int expr_forward(rdb_tape *t, InstrPlan &I, bool reduce, int order) {
     }
     for (int h = 0; h < kMaxArgs * (kMaxArgs + 1) / 2; ++h) p.second[h] = I.second[h];
     p.out = out.val; p.ops = I.d_ops; p.fconst = t->d_fconst; p.block_sums = t->scratch;
+    return RDB_OK;
+}
+
+// ---- north star (a): a run of adjacent elementwise instructions of one shape replays as ONE forward kernel that still stores every
+// instruction's value and partials.  An instruction joins the run that starts at `head` when its output has the head's shape and
+// every argument produced inside the run is a plain same-shape TrackedArray operand (it then travels in a register); arguments
+// from outside the run are loaded as usual (broadcast clamps included).  Needs the NVRTC path; without it the instructions launch
+// one by one.  Results are bit-identical either way (same arithmetic, same order).
+static int plan_run(rdb_tape *t, size_t head) {
+    InstrPlan &H = t->instrs[head];
+    if (H.run_end != -2) return H.run_end;
+    H.run_end = (int)head;
+    static const bool on = [] { const char *e = getenv("RDB_FUSE_RUNS"); return !(e && e[0] == '0'); }();
+    if (!on || !t->opts.fuse_elementwise) return H.run_end;
+    Buf &ho = t->bufs[H.rec.out];
+    auto root = [&](int b) { while (t->bufs[b].alias_of >= 0) b = t->bufs[b].alias_of; return b; };
+    auto joinable = [&](size_t k) {
+        InstrPlan &I = t->instrs[k];
+        if (I.blk || !is_elementwise(I.rec.opcode) || I.rec.expr_len <= 0) return false;
+        Buf &o = t->bufs[I.rec.out];
+        if (o.size != ho.size) return false;
+        for (int d = 0; d < kMaxDims; ++d) if (o.dims[d] != ho.dims[d]) return false;
+        for (int a = 0; a < I.rec.n_in; ++a) {
+            OperandPlan &op = I.in[a];
+            bool inside = false;
+            for (size_t j = head; j < k; ++j) inside |= root(t->instrs[j].rec.out) == root(op.rec.buffer);
+            if (!inside) { if (op.rec.cls == CLS_TR) return false; continue; }       // (scalar operands keep the one-by-one path)
+            if (op.rec.cls != CLS_TA || op.mode != OPM_PLAIN || t->bufs[op.rec.buffer].size != ho.size) return false;
+            for (int d = 0; d < kMaxDims; ++d) if ((d < op.rec.ndims ? op.rec.dims[d] : 1) != ho.dims[d]) return false;
+        }
+        return true;
+    };
+    if (!joinable(head)) return H.run_end;
+    size_t k = head + 1;
+    while (k < t->instrs.size() && k - head < 8 && joinable(k)) ++k;
+    H.run_end = (int)k - 1;
+    return H.run_end;
+}
+// 1 = launched as one kernel, 0 = not available (caller launches the instructions one by one)
+template <typename T>
+static int expr_forward_run(rdb_tape *t, size_t head, size_t last, bool reduce) {
+    InstrPlan &H = t->instrs[head];
+    const int ri = reduce ? 1 : 0;
+    if (H.run_tried[ri] && !H.run_fn[ri]) return 0;
+    const int n_items = (int)(last - head + 1);
+    std::vector<JitRunItem> items(n_items);
+    auto root = [&](int b) { while (t->bufs[b].alias_of >= 0) b = t->bufs[b].alias_of; return b; };
+    double bytes = 0;
+    for (int k = 0; k < n_items; ++k) {
+        InstrPlan &I = t->instrs[head + k];
+        OK(expr_params<T>(t, I, false, 1, items[k].p));
+        items[k].ops = I.h_ops.data();
+        bytes += (double)t->bufs[I.rec.out].size * t->es;
+        for (int a = 0; a < I.rec.n_in; ++a) {
+            items[k].from_item[a] = -1;
+            for (int j = 0; j < k; ++j) if (root(t->instrs[head + j].rec.out) == root(I.in[a].rec.buffer)) items[k].from_item[a] = j;
+            if (items[k].from_item[a] < 0) bytes += (double)t->bufs[I.in[a].rec.buffer].size * t->es;
+            if (I.partial[a]) bytes += (double)t->bufs[I.rec.out].size * t->es;
+        }
+    }
+    if (!H.run_tried[ri]) {
+        H.run_tried[ri] = true;
+        H.run_fn[ri] = jit_run_kernel(items.data(), n_items, t->h_fconst.data(), sizeof(T) == 4, reduce);
+        if (!H.run_fn[ri]) return 0;
+    }
+    StepTimer tm(t, reduce ? "expr_forward_run+sum" : "expr_forward_run", bytes, 0);
+    KL(t, jit_run_launch(S(t), H.run_fn[ri], items.data(), n_items, t->scratch, reduce));
+    return 1;
+}
+
+template <typename T>
+static int expr_forward(rdb_tape *t, InstrPlan &I, bool reduce, int order) {
+    Buf &out = t->bufs[I.rec.out];
+    ExprParams p{};
+    OK(expr_params<T>(t, I, reduce, order, p));
     int np = 0;
     for (int a = 0; a < I.rec.n_in; ++a) np += I.partial[a] ? 1 : 0;
     StepTimer tm(t, order == 2 ? "expr_forward2" : (reduce ? "expr_forward+sum" : "expr_forward"),
@@ -396,6 +474,25 @@ static int forward_pass(rdb_tape *t, int order = 1) {
                 Nx.in[0].mode == OPM_PLAIN &&
                 (I.rec.opcode == OP_ADD || I.rec.opcode == OP_SUB || is_elementwise(I.rec.opcode)))
                 fuse_next = true;
+        }
+        if (order == 1 && !I.blk && is_elementwise(I.rec.opcode)) {
+            const size_t last = (size_t)plan_run(t, i);
+            if (last > i) {
+                InstrPlan &L = t->instrs[last];
+                bool red = false;                                    // the `sum`/`mean` right behind the run rides along too
+                if (t->opts.fuse_elementwise && last + 1 < n) {
+                    InstrPlan &Nx = t->instrs[last + 1];
+                    red = (Nx.rec.opcode == OP_SUM || Nx.rec.opcode == OP_MEAN) && Nx.in[0].rec.buffer == L.rec.out && Nx.in[0].mode == OPM_PLAIN;
+                }
+                const int rc = expr_forward_run<T>(t, i, last, red);
+                if (rc < 0) return rc;
+                if (rc == 1) {
+                    for (size_t k = i + 1; k <= last; ++k) { bump_version(t, t->instrs[k].rec.out); t->instrs[k].fused_into_prev = false; }
+                    if (last + 1 < n) t->instrs[last + 1].fused_into_prev = red;
+                    i = last;
+                    continue;
+                }
+            }
         }
         switch (I.rec.opcode) {
             case OP_MUL: {
@@ -1038,6 +1135,30 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                 if (I.in[0].rec.tracked) {
                     Buf &b = t->bufs[I.in[0].rec.buffer];
                     T scale = I.rec.opcode == OP_MEAN ? (T)1 / (T)I.in[0].size : (T)1;
+                    // reverse {sum, +} in one step: the instruction right before is the array +/- that produced the summed buffer, and
+                    // nothing has accumulated into that buffer's deriv yet.  x.deriv += scale * delta goes straight into the
+                    // operands of the +/- (the same values in the same order as via deriv(a + b): 1 * (scale * delta)), deriv(a + b)
+                    // stays logically zero - it would be unseeded right after anyway (arithmetic.jl:45-53) - and the +/- itself is then
+                    // skipped by the "no adjoint reached this output" test.  cfg 2: 2 M E written instead of 5 M E moved.
+                    if (t->opts.fuse_elementwise && k > 0 && t->dz[droot(t, I.in[0].rec.buffer)] && I.in[0].rec.cls == CLS_TA && I.in[0].mode == OPM_PLAIN) {
+                        InstrPlan &A = t->instrs[k - 1];
+                        const bool pm = !A.blk && (A.rec.opcode == OP_ADD || A.rec.opcode == OP_SUB) && A.rec.out == I.in[0].rec.buffer;
+                        bool plain = pm;
+                        for (int a = 0; a < 2 && plain; ++a)
+                            if (A.in[a].rec.tracked && (A.in[a].rec.cls != CLS_TA || A.in[a].mode != OPM_PLAIN || t->bufs[A.in[a].rec.buffer].size != b.size)) plain = false;
+                        if (plain) {
+                            for (int a = 0; a < 2; ++a) {
+                                if (!A.in[a].rec.tracked) continue;
+                                Buf &ba = t->bufs[A.in[a].rec.buffer];
+                                const T sg = (a == 1 && A.rec.opcode == OP_SUB) ? -scale : scale;
+                                const bool ow = dtake(t, A.in[a].rec.buffer);
+                                StepTimer tm(t, "sum+add_reverse", (ow ? 1.0 : 2.0) * ba.size * R * t->es, 0);
+                                KL(t, launch_acc_scalar<T>(S(t), (T *)ba.der, ba.size, R, delta, sg, ow));
+                                OK(acc_done(t, A.in[a].rec.buffer));
+                            }
+                            break;
+                        }
+                    }
                     const bool ow = dtake(t, I.in[0].rec.buffer);
                     StepTimer tm(t, "sum_reverse", (ow ? 1.0 : 2.0) * b.size * R * t->es, 0);
                     KL(t, launch_acc_scalar<T>(S(t), (T *)b.der, b.size, R, delta, scale, ow));

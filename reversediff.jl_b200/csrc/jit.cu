@@ -111,26 +111,19 @@ struct Gen {
     }
 };
 
-// returns "" when the program cannot be specialised
-static std::string generate(const ExprParams &P, const int32_t *ops, const double *fconst, bool f32, bool reduce) {
-    Gen g;
-    g.N = P.n_args;
-    g.f32 = f32;
+// One elementwise instruction inside the element loop of a generated kernel.  `pfx` names its pointers (`<pfx>a0`, `<pfx>out`,
+// `<pfx>p0`); src[a] non-empty: the argument is the value an earlier instruction of the same fused run computed for this very element
+// (a register), not a load.  The instruction's value is left in `<pfx>y` (declared by the caller).  false: cannot be specialised.
+static bool emit_instruction(Gen &g, const ExprParams &P, const int32_t *ops, const double *fconst, bool f32, const std::string &pfx,
+                             const std::string *src) {
     const int N = P.n_args;
+    g.N = N;
     auto &o = g.o;
-    o << "typedef " << (f32 ? "float" : "double") << " T;\n";
-    o << "__device__ __forceinline__ T powi_(T x, int n) { if (n == 0) return (T)1; bool neg = n < 0; if (neg) n = -n; T r = x; "
-         "for (int i = 1; i < n; ++i) r = r * x; return neg ? (T)1 / r : r; }\n";
-    o << "extern \"C\" __global__ void __launch_bounds__(256) expr_k(";
-    for (int a = 0; a < N; ++a) o << "const T* __restrict__ a" << a << ", ";
-    o << "T* __restrict__ out";
-    for (int a = 0; a < N; ++a) if (P.partial[a]) o << ", T* __restrict__ p" << a;
-    o << ", double* __restrict__ bsums) {\n";
-    o << "  double local = 0.0;\n";
     const bool small = P.n <= 0x7fffffffLL;
-    o << "  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < " << P.n << "LL; i += gridDim.x * 256LL) {\n";
+    o << "    {\n";
     for (int a = 0; a < N; ++a) {
-        if (P.arg[a].same) { o << "    const T v" << a << " = a" << a << "[i];\n"; continue; }
+        if (src && !src[a].empty()) { o << "    const T v" << a << " = " << src[a] << ";\n"; continue; }
+        if (P.arg[a].same) { o << "    const T v" << a << " = " << pfx << "a" << a << "[i];\n"; continue; }
         // broadcast clamp (propagation.jl:25-27) as literal strides
         o << "    T v" << a << ";\n    {\n";
         if (small) o << "      unsigned rem = (unsigned)i; unsigned off = 0u;\n";
@@ -142,7 +135,7 @@ static std::string generate(const ExprParams &P, const int32_t *ops, const doubl
             if (st != 0) o << "      off += (rem % " << dim << sfx << ") * " << st << sfx << ";\n";
             o << "      rem /= " << dim << sfx << ";\n";
         }
-        o << "      v" << a << " = a" << a << "[off];\n    }\n";
+        o << "      v" << a << " = " << pfx << "a" << a << "[off];\n    }\n";
     }
     for (int a = 0; a < N; ++a)
         for (int p = 0; p < N; ++p) o << "    const T " << g.D(a, p) << " = " << (a == p ? g.one() : g.zero()) << ";\n";
@@ -152,7 +145,7 @@ static std::string generate(const ExprParams &P, const int32_t *ops, const doubl
         switch (code) {
             case E_CONST: {
                 std::string c = lit(fconst[imm], f32);
-                if (c.empty()) return "";
+                if (c.empty()) return false;
                 o << "    const T " << g.V(r) << " = (T)" << c << ";\n";
                 for (int p = 0; p < N; ++p) o << "    const T " << g.D(r, p) << " = " << g.zero() << ";\n";
             } break;
@@ -256,12 +249,29 @@ static std::string generate(const ExprParams &P, const int32_t *ops, const doubl
                 o << "    const T t_" << r << " = " << g.one() << " / (" << g.one() << " + " << g.fn("exp") << "(-" << g.V(a) << "));\n";
                 g.unary(r, a, "t_" + std::to_string(r), "t_" + std::to_string(r) + " * (" + g.one() + " - t_" + std::to_string(r) + ")");
                 break;
-            default: return "";
+            default: return false;
         }
     }
-    o << "    out[i] = " << g.V(r - 1) << ";\n";
-    for (int a = 0; a < N; ++a) if (P.partial[a]) o << "    p" << a << "[i] = " << g.D(r - 1, a) << ";\n";
-    if (reduce) o << "    local += (double)" << g.V(r - 1) << ";\n";
+    o << "    " << pfx << "out[i] = " << g.V(r - 1) << ";\n";
+    for (int a = 0; a < N; ++a) if (P.partial[a]) o << "    " << pfx << "p" << a << "[i] = " << g.D(r - 1, a) << ";\n";
+    o << "    " << pfx << "y = " << g.V(r - 1) << ";\n";
+    o << "    }\n";
+    return true;
+}
+
+static void emit_prologue(Gen &g, bool f32) {
+    g.o << "typedef " << (f32 ? "float" : "double") << " T;\n";
+    g.o << "__device__ __forceinline__ T powi_(T x, int n) { if (n == 0) return (T)1; bool neg = n < 0; if (neg) n = -n; T r = x; "
+           "for (int i = 1; i < n; ++i) r = r * x; return neg ? (T)1 / r : r; }\n";
+    g.o << "extern \"C\" __global__ void __launch_bounds__(256) expr_k(";
+}
+static void emit_params(Gen &g, const ExprParams &P, const std::string &pfx, const std::string *src) {
+    for (int a = 0; a < P.n_args; ++a) if (!src || src[a].empty()) g.o << "const T* __restrict__ " << pfx << "a" << a << ", ";
+    g.o << "T* __restrict__ " << pfx << "out, ";
+    for (int a = 0; a < P.n_args; ++a) if (P.partial[a]) g.o << "T* __restrict__ " << pfx << "p" << a << ", ";
+}
+static void emit_epilogue(Gen &g, bool reduce) {
+    auto &o = g.o;
     o << "  }\n";
     if (reduce) {
         o << "  __shared__ double ws[8];\n"
@@ -275,7 +285,44 @@ static std::string generate(const ExprParams &P, const int32_t *ops, const doubl
              "  }\n";
     }
     o << "}\n";
-    return o.str();
+}
+
+// returns "" when the program cannot be specialised
+static std::string generate(const ExprParams &P, const int32_t *ops, const double *fconst, bool f32, bool reduce) {
+    Gen g;
+    g.f32 = f32;
+    emit_prologue(g, f32);
+    emit_params(g, P, "", nullptr);
+    g.o << "double* __restrict__ bsums) {\n  double local = 0.0;\n";
+    g.o << "  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < " << P.n << "LL; i += gridDim.x * 256LL) {\n    T y;\n";
+    if (!emit_instruction(g, P, ops, fconst, f32, "", nullptr)) return "";
+    if (reduce) g.o << "    local += (double)y;\n";
+    emit_epilogue(g, reduce);
+    return g.o.str();
+}
+
+// A run of adjacent same-shape elementwise instructions as ONE kernel (north star (a)): every instruction still stores its value and
+// its partials - the reverse sweep and `value(x)` see exactly what the separate kernels would have left - but a value consumed by a
+// later instruction of the run travels in a register instead of through HBM, and the run is one launch.
+static std::string generate_run(const JitRunItem *items, int n_items, const double *fconst, bool f32, bool reduce) {
+    Gen g;
+    g.f32 = f32;
+    emit_prologue(g, f32);
+    std::vector<std::vector<std::string>> src(n_items, std::vector<std::string>(kMaxArgs));
+    for (int k = 0; k < n_items; ++k) {
+        for (int a = 0; a < items[k].p.n_args; ++a)
+            if (items[k].from_item[a] >= 0) src[k][a] = "s" + std::to_string(items[k].from_item[a]) + "_y";
+        emit_params(g, items[k].p, "s" + std::to_string(k) + "_", src[k].data());
+    }
+    g.o << "double* __restrict__ bsums) {\n  double local = 0.0;\n";
+    g.o << "  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < " << items[0].p.n << "LL; i += gridDim.x * 256LL) {\n";
+    for (int k = 0; k < n_items; ++k) {
+        g.o << "    T s" << k << "_y;\n";
+        if (!emit_instruction(g, items[k].p, items[k].ops, fconst, f32, "s" + std::to_string(k) + "_", src[k].data())) return "";
+    }
+    if (reduce) g.o << "    local += (double)s" << (n_items - 1) << "_y;\n";
+    emit_epilogue(g, reduce);
+    return g.o.str();
 }
 
 static std::map<std::string, CUfunction> g_cache;
@@ -325,6 +372,33 @@ void *jit_expr_kernel(const ExprParams &p, const int32_t *host_ops, const double
     std::string src = jit::generate(p, host_ops, host_fconst, f32, reduce);
     if (src.empty()) return nullptr;
     return (void *)jit::compile(src);
+}
+
+void *jit_run_kernel(const JitRunItem *items, int n_items, const double *host_fconst, bool f32, bool reduce) {
+    for (int k = 0; k < n_items; ++k) if (items[k].p.order != 1 || items[k].p.n != items[0].p.n) return nullptr;
+    std::string src = jit::generate_run(items, n_items, host_fconst, f32, reduce);
+    if (src.empty()) return nullptr;
+    return (void *)jit::compile(src);
+}
+
+cudaError_t jit_run_launch(cudaStream_t st, void *fn, const JitRunItem *items, int n_items, void *block_sums, bool reduce) {
+    std::vector<void *> args;
+    std::vector<const void *> ptrs;
+    ptrs.reserve((size_t)n_items * (2 * kMaxArgs + 1) + 1);
+    for (int k = 0; k < n_items; ++k) {
+        const ExprParams &p = items[k].p;
+        for (int i = 0; i < p.n_args; ++i) if (items[k].from_item[i] < 0) ptrs.push_back(p.arg[i].ptr);
+        ptrs.push_back(p.out);
+        for (int i = 0; i < p.n_args; ++i) if (p.partial[i]) ptrs.push_back(p.partial[i]);
+    }
+    ptrs.push_back(block_sums);
+    for (auto &q : ptrs) args.push_back((void *)&q);
+    const int64_t n = items[0].p.n;
+    int64_t blocks = reduce ? kReduceBlocks : (n + 511) / 512;
+    if (!reduce && blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    CUresult r = jit::drv().launchKernel((CUfunction)fn, (unsigned)blocks, 1, 1, 256, 1, 1, 0, (CUstream)st, args.data(), nullptr);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorLaunchFailure;
 }
 
 cudaError_t jit_expr_launch(cudaStream_t st, void *fn, const ExprParams &p, bool reduce) {

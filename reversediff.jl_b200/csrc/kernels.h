@@ -121,6 +121,11 @@ struct ExprParams {
 // program cannot be specialised (the interpreter launch_expr_forward is used then)
 void *jit_expr_kernel(const ExprParams &p, const int32_t *host_ops, const double *host_fconst, bool f32, bool reduce);
 cudaError_t jit_expr_launch(cudaStream_t, void *fn, const ExprParams &p, bool reduce);
+// a run of adjacent same-shape elementwise instructions as one NVRTC kernel; from_item[a] >= 0: argument a is the value that item
+// of the run computed for the same element (never re-read from memory)
+struct JitRunItem { ExprParams p; const int32_t *ops; int from_item[kMaxArgs]; };
+void *jit_run_kernel(const JitRunItem *items, int n_items, const double *host_fconst, bool f32, bool reduce);
+cudaError_t jit_run_launch(cudaStream_t, void *fn, const JitRunItem *items, int n_items, void *block_sums, bool reduce);
 
 template <typename T> cudaError_t launch_fill(cudaStream_t, T *p, int64_t n, T v);
 // out = a + sign*b   (array +/-: arithmetic.jl:7-12,69-79); if block_sums != NULL also writes per-block sums

@@ -315,6 +315,18 @@ def _scalar_identity(t: "TrackedReal"):
     return record_scalar((np.asarray([(P.E_ARG, 0, 0, 0)], np.int32), np.zeros(0)), t)
 
 
+def convert(t):
+    """``convert(::Type{T1<:TrackedReal}, t::TrackedReal)`` (``src/tracked.jl:237-257``): a new TrackedReal of another value /
+    deriv type that keeps the line of references back to the origin's deriv.  Forward: ``value!(output, value(input))``; reverse:
+    ``increment_deriv!(input, deriv(output)); unseed!(output)`` - i.e. the identity scalar instruction (partial 1), and that is how
+    it travels: a slot of the current scalar block with the one-op program ``E_ARG``.  (All values of one tape share the tape's
+    element type here, so the conversion of the value itself is a no-op.)  A plain Real converts to an origin-less TrackedReal
+    that no instruction refers to (``tracked.jl:259-265``): returned as is."""
+    if not isinstance(t, TrackedReal):
+        return t
+    return _scalar_identity(t)
+
+
 def scalar_buffer(t: "TrackedReal") -> int:
     """Size-1 buffer that carries ``t`` (operand class TR of array instructions; ``output_hook`` of a GradientTape)."""
     prog = t.tape.program

@@ -633,3 +633,46 @@ def test_hessian_async_reads_device_input_in_place(rd):
     g = np.zeros(n); res = rd.DiffResult(0.0, g, np.zeros((n, n), order="F"))
     rd.hessian_(res, ct, xs[1])                                  # a fresh set_input: everything works again
     assert relerr(res.hessian, closed(xs[1])) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_elementwise_run_fusion_is_bit_identical(rd, orc, dtype):
+    """North star (a): a run of adjacent same-shape elementwise instructions replays as ONE forward kernel, and the `sum` behind
+    the run and the reverse {sum, +} pair are fused too.  Every instruction's value and every deriv must be bit-identical to the
+    one-kernel-per-instruction replay (`fuse_elementwise=0`), and agree with the oracle."""
+    E, T = rd.expr, rd.tracked
+    rng = np.random.default_rng(5)
+    m, n = 96, 160
+    A0, B0 = rng.random((m, n)).astype(dtype), rng.random((m, n)).astype(dtype)
+    c0 = rng.random(m).astype(dtype)
+    A, B = (rng.random((m, n)) - 0.5).astype(dtype), (rng.random((m, n)) - 0.5).astype(dtype)
+    c = (rng.random(m) - 0.5).astype(dtype)
+
+    def f(a, b, bias):
+        t = T.broadcast(T.forward(E.tanh), b)                      # unfused spelling of cfg 4: broadcast(tanh) ...
+        y = T.broadcast("*", a, t)                                 # ... then (broadcast, *) on its output
+        z = T.bcast(lambda u, w: E.exp(u * 0.5) + w, y, bias)      # joins the run; `bias` broadcasts along columns (loaded, clamped)
+        q = T.broadcast("-", a, b)                                 # an independent instruction of the same shape joins as well
+        return T.sum(z + q)                                        # array + then sum: forward {+, sum} and reverse {sum, +}
+
+    tape = rd.GradientTape(f, (A0, B0, c0), dtype=dtype)
+    ot = orc.OracleTape(tape.program_bytes())
+    val, grads = ot.gradient([A, B, c])
+    got = {}
+    for fuse in (1, 0):
+        ct = rd.compile(tape, fuse_elementwise=fuse)
+        res = tuple(rd.DiffResult(0.0, np.zeros(np.shape(x), dtype, order="F")) for x in (A, B, c))
+        l0 = ct.handle.launch_count()
+        rd.gradient_(res, ct, (A, B, c))
+        launches = ct.handle.launch_count() - l0
+        nb = len(ot.value)
+        got[fuse] = ([np.asarray(r.gradient).copy() for r in res], float(res[0].value),
+                     [ct.handle.get_value(b).copy() for b in range(nb) if ot.kind[b] != orc.BUF_CONST], launches)
+        for r, g in zip(res, grads):
+            assert relerr(r.gradient, g) < TOL[dtype]
+    for x, y in zip(got[1][0], got[0][0]):
+        assert np.array_equal(x, y)
+    assert got[1][1] == got[0][1]
+    for x, y in zip(got[1][2], got[0][2]):
+        assert np.array_equal(x, y)
+    assert got[1][3] < got[0][3]                                  # and it really took fewer launches

@@ -166,6 +166,49 @@ def test_oracle_mixed_and_ackley_finite_differences(rd, orc):
     assert relerr(g, fd_grad(ackley_np, [x], 0)) < 1e-6
 
 
+def make_converted(rd):
+    def f(x, w):
+        """``convert`` (``src/tracked.jl:237-257``) between scalar and array instructions: of a scalar-getindex leaf, of a block
+        slot, of the TrackedReal an array instruction produced; the same source converted twice."""
+        a = rd.convert(x[2])                           # leaf -> slot
+        s = rd.convert(rd.sum(w))                      # output of an array instruction -> slot
+        y = rd.convert(a * s + x[0])                   # slot -> slot
+        z = rd.sum(rd.bcast(lambda v, c: v * c, w, rd.convert(y)))
+        return z * rd.convert(x[2]) + rd.exp(rd.convert(y))
+    return f
+
+
+def converted_np(x, w):
+    y = x[2] * np.sum(w) + x[0]
+    return np.sum(w * y) * x[2] + np.exp(y)
+
+
+def test_oracle_convert_instruction(rd, orc):
+    x0 = np.random.default_rng(1).random(6); w0 = np.random.default_rng(3).random(5)
+    x = np.random.default_rng(2).random(6); w = np.random.default_rng(4).random(5)
+    tape = rd.GradientTape(make_converted(rd), (x0, w0))
+    val, (gx, gw) = orc.OracleTape(tape.program_bytes()).gradient([x, w])
+    assert abs(val - converted_np(x, w)) < 1e-13 * abs(val)
+    assert relerr(gx, fd_grad(converted_np, [x, w], 0)) < 1e-6 and relerr(gw, fd_grad(converted_np, [x, w], 1)) < 1e-6
+    y = x[2] * np.sum(w) + x[0]
+    gx_cf = np.zeros(6); gx_cf[0] = np.sum(w) * x[2] + np.exp(y); gx_cf[2] = (np.sum(w) * x[2] + np.exp(y)) * np.sum(w) + np.sum(w * y)
+    assert relerr(gx, gx_cf) < 1e-13
+    assert rd.convert(3.5) == 3.5
+
+
+@pytest.mark.gpu
+def test_gpu_convert_instruction(rd, orc):
+    x0 = np.random.default_rng(1).random(6); w0 = np.random.default_rng(3).random(5)
+    x = np.random.default_rng(2).random(6); w = np.random.default_rng(4).random(5)
+    tape = rd.GradientTape(make_converted(rd), (x0, w0))
+    ct = rd.compile(tape)
+    res = (rd.DiffResult(0.0, np.zeros(6)), rd.DiffResult(0.0, np.zeros(5)))
+    rd.gradient_(res, ct, (x, w))
+    val, (gx, gw) = orc.OracleTape(tape.program_bytes()).gradient([x, w])
+    assert abs(res[0].value - val) <= 1e-12 * abs(val)
+    assert relerr(res[0].gradient, gx) < 1e-12 and relerr(res[1].gradient, gw) < 1e-12
+
+
 def test_oracle_jacobian_of_tracked_real_array(rd, orc):
     n = 12
     x0 = np.random.default_rng(1).random(n); x = np.random.default_rng(2).random(n)
