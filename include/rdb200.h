@@ -96,6 +96,16 @@ int rdb_reverse_scalar_seed(rdb_tape *);
  * NULL) receives value(output) as the DiffResult methods do (src/api/utils.jl:96-100). */
 int rdb_gradient(rdb_tape *, void *const *result_ptrs, int results_on_device, void *value_out);
 
+/* The same call, only ENQUEUED: it returns as soon as the sweeps and the copies into `result_ptrs` / `value_out` are on the
+ * context's streams (host arrays should be page-locked, or the copies block the caller).  rdb_tape_wait(tape) completes it: it waits
+ * for the device, runs the accuracy check of the call's int8-slice GEMMs and, if that fails, replays the call with the DMMA kernels
+ * before returning - so results are valid only after rdb_tape_wait.  Between the two calls the tape, its inputs (rdb_tape_set_input
+ * arrays) and its results must not be touched, and the tape's context must not run other tapes.  Two tapes of the same program on
+ * two contexts pipeline consecutive evaluations: the upload of evaluation k+1 and the download of k-1 overlap the sweeps of k
+ * (gradient! at 4096 x 4096 moves 268 MB each way per evaluation, more than half of its compute time over PCIe). */
+int rdb_gradient_async(rdb_tape *, void *const *result_ptrs, int results_on_device, void *value_out);
+int rdb_tape_wait(rdb_tape *);
+
 /* jacobian!(result, tape::CompiledJacobian, input) (src/api/jacobians.jl:120-124) restricted to the seed
  * rows [row_begin,row_end) of seeded_reverse_pass! (src/api/utils.jl:44-58): one forward sweep, then the
  * rows are replayed in blocks of `seed_block` one-hot seeds.  `result` addresses element (row_begin, 0) of

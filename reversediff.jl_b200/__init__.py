@@ -12,7 +12,7 @@ from .tracked import (TrackedArray, TrackedReal, InstructionTape, ForwardOptimiz
                       forward, skip, value, istracked, sum, mean, dot, bcast, map_, broadcast, collect, convert)
 from .expr import (tanh, exp, log, sqrt, sin, cos, abs2, abs_, inv, logistic, max_, min_)          # noqa: F401
 from .api import (GradientTape, JacobianTape, HessianTape, CompiledTape, DiffResult, compile,      # noqa: F401
-                  gradient_, jacobian_, hessian_, gradient, jacobian, hessian, seeded_forward_pass, shard_range, shard_bounds,
+                  gradient_, jacobian_, hessian_, gradient, jacobian, hessian, GradientPipeline, seeded_forward_pass, shard_range, shard_bounds,
                   make_comm, gather_jacobian_, gather_hessian_)
 from . import program, expr, engine, workloads                                                    # noqa: F401
 

@@ -236,6 +236,56 @@ def gradient_(result, ct: CompiledTape, input_):
     return result
 
 
+class GradientPipeline:
+    """Consecutive ``gradient!`` evaluations of one tape, pipelined over ``depth`` engine copies of it (each on a context = stream
+    set of its own): ``submit`` enqueues an evaluation (``rdb_tape_set_input`` + ``rdb_gradient_async``) and returns at once, so the
+    upload of evaluation k+1 and the download of k-1 run under the sweeps of k; ``submit`` on a busy slot and ``drain`` complete
+    the oldest call first (``rdb_tape_wait``).  Results land where ``gradient!`` would put them and are valid once the call has
+    been completed; inputs and results must stay untouched until then.  The reference has no counterpart (its replay is
+    synchronous CPU code); what is kept is the per-call contract of ``gradient!(result, tape, input)`` (``api/gradients.jl:78-82``)."""
+
+    def __init__(self, tape, depth=2, device=None, **options):
+        if isinstance(tape, CompiledTape):
+            device = tape.ctx.device_id if device is None else device
+            tape = tape.tape
+        dev = 0 if device is None else device
+        self.slots = [CompiledTape(tape, _engine.Context(dev), **options) for _ in range(depth)]
+        self._inflight = [None] * depth
+        self._next = 0
+
+    def submit(self, result, input_):
+        k = self._next
+        self._next = (k + 1) % len(self.slots)
+        self._complete(k)
+        ct = self.slots[k]
+        _need_compiled(ct, "gradient")
+        seeded_forward_pass(ct, input_)
+        arrs, drs = _result_arrays(result, len(ct.tape.input))
+        if len(arrs) != len(ct.tape.input):
+            raise ValueError("result does not match the tape's inputs")
+        ct.handle.gradient_async(arrs, [tuple(t.shape) for t in ct.tape.input], want_value=bool(drs))
+        self._inflight[k] = (drs, input_, result)
+        return result
+
+    def _complete(self, k):
+        if self._inflight[k] is None:
+            return
+        drs, _inp, _res = self._inflight[k]
+        self._inflight[k] = None
+        val = self.slots[k].handle.wait()
+        for d in drs:
+            d.value = val
+
+    def drain(self):
+        """Complete every evaluation in flight, oldest first."""
+        n = len(self.slots)
+        for j in range(n):
+            self._complete((self._next + j) % n)
+
+    def launch_count(self):
+        return sum(ct.handle.launch_count() for ct in self.slots)
+
+
 def gradient(ct: CompiledTape, input_):
     """``gradient!(tape, input)`` (``api/gradients.jl:61-65``): allocates via construct_result."""
     res = [np.zeros(t.shape, ct.dtype, order="F") for t in ct.tape.input]

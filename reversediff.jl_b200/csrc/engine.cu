@@ -176,6 +176,10 @@ struct rdb_tape {
     // accuracy certificate of the int8-slice `*` kernels (umma.cu guard): totals since load, and the fallback state
     int64_t guard_checked = 0, guard_flagged = 0, guard_fallbacks = 0;
     double guard_worst = 0;
+    // rdb_gradient_async: the call is only enqueued; rdb_tape_wait completes it (and runs the deferred accuracy check of the int8-slice GEMMs)
+    struct Pending { bool active = false; std::vector<void *> results; int on_device = 0; void *value_out = nullptr; bool guard = false; } pending;
+    bool async_call = false;       // inside rdb_gradient_async: gradient_impl records done_ev instead of synchronising
+    cudaEvent_t done_ev = nullptr;
     bool async = false;            // rdb_tape_set_async: calls with device results and no host outputs return without synchronising
     // hessian! of sum|mean(g.(views of x)) with a device result and nothing else requested: one fused kernel (kernels.cu
     // k_hessian_separable); state 0 = not examined yet, 1 = planned, -1 = the tape does not have that shape
@@ -1574,6 +1578,7 @@ static int gradient_impl(rdb_tape *t, void *const *result_ptrs, int on_device, v
                 CU(cudaMemcpyAsync(result_ptrs[i], b.der, (size_t)b.size * t->es, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, S(t)));
             }
             if (value_out) CU(cudaMemcpyAsync(value_out, t->bufs[t->output].val, t->es, cudaMemcpyDeviceToHost, S(t)));
+            if (t->async_call) { CU(cudaEventRecord(t->done_ev, S(t))); return RDB_OK; }
             CU(cudaStreamSynchronize(S(t)));
             return RDB_OK;
         }
@@ -1616,6 +1621,15 @@ static int gradient_impl(rdb_tape *t, void *const *result_ptrs, int on_device, v
         Buf &b = t->bufs[t->inputs[i]];
         OK(dmaterialize(t, t->inputs[i], 1, false));
         CU(cudaMemcpyAsync(result_ptrs[i], b.der, (size_t)b.size * t->es, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, S(t)));
+    }
+    if (t->async_call) {                                     // enqueue only: the early copies join the main stream, one event closes the call
+        if (t->ctx->copy_stream) {
+            if (!t->join_ev) CU(cudaEventCreateWithFlags(&t->join_ev, cudaEventDisableTiming));
+            CU(cudaEventRecord(t->join_ev, t->ctx->copy_stream));
+            CU(cudaStreamWaitEvent(S(t), t->join_ev, 0));
+        }
+        CU(cudaEventRecord(t->done_ev, S(t)));
+        return RDB_OK;
     }
     CU(cudaStreamSynchronize(S(t)));
     if (t->ctx->copy_stream) CU(cudaStreamSynchronize(t->ctx->copy_stream));
@@ -2204,7 +2218,7 @@ static int fold_launches(rdb_tape *t, int rc) {
     g_extra_launches = 0;
     // slicing that ran ahead on the side stream and was not consumed must not outlive the call (the next call may refill the
     // same cache entries from the main stream)
-    if (t->ctx && t->ctx->side_stream && !t->async) cudaStreamSynchronize(t->ctx->side_stream);
+    if (t->ctx && t->ctx->side_stream && !t->async && !t->async_call) cudaStreamSynchronize(t->ctx->side_stream);
     return rc;
 }
 // Run one API call on a tape.  FP64 `*` instructions of eligible shapes go through exact int8 slices on tcgen05, whose error is
@@ -2220,6 +2234,7 @@ static int run_call(rdb_tape *t, F &&run) {
     g_f64_slices = t->opts.ozaki_slices;
     g_extra_launches = 0;
     int rc = fold_launches(t, run());
+    if (t->async_call) { t->pending.guard = rc == RDB_OK && t->dtype == RDB_F64 && t->opts.gemm_f64_mode != 1; return rc; }   // rdb_tape_wait checks
     if (rc != RDB_OK || t->dtype != RDB_F64 || t->opts.gemm_f64_mode == 1 || !c->gemm.guard) return rc;
     if (c->gemm.guard_used == 0 && !c->gemm.guard_pending) return rc;   // no int8-slice launch in this call
     GuardSummary gs;
@@ -2329,6 +2344,7 @@ void rdb_tape_destroy(rdb_tape *t) {
     if (t->hgraph.exec) cudaGraphExecDestroy(t->hgraph.exec);
     if (t->fork_ev) cudaEventDestroy(t->fork_ev);
     if (t->join_ev) cudaEventDestroy(t->join_ev);
+    if (t->done_ev) cudaEventDestroy(t->done_ev);
     for (auto &e : t->early.ev) if (e) cudaEventDestroy(e);
     if (t->ctx && t->ctx->upload_stream) cudaStreamSynchronize(t->ctx->upload_stream);
     for (auto &b : t->bufs) for (auto &e : b.up_ev) if (e) cudaEventDestroy(e);
@@ -2393,6 +2409,50 @@ int rdb_reverse_scalar_seed(rdb_tape *t) {
 int rdb_gradient(rdb_tape *t, void *const *result_ptrs, int on_device, void *value_out) {
     if (!t) return fail(RDB_EINVAL, "null tape");
     return DISPATCH(t, gradient_impl, t, result_ptrs, on_device, value_out);
+}
+int rdb_gradient_async(rdb_tape *t, void *const *result_ptrs, int on_device, void *value_out) {
+    if (!t) return fail(RDB_EINVAL, "null tape");
+    if (t->pending.active) return fail(RDB_EINVAL, "this tape has an asynchronous call in flight: rdb_tape_wait first");
+    ctx_enter(t->ctx);
+    if (!t->done_ev) CU(cudaEventCreateWithFlags(&t->done_ev, cudaEventDisableTiming));
+    t->pending.results.assign(t->inputs.size(), nullptr);
+    if (result_ptrs) for (size_t i = 0; i < t->inputs.size(); ++i) t->pending.results[i] = result_ptrs[i];
+    t->pending.on_device = on_device; t->pending.value_out = value_out; t->pending.guard = false;
+    t->async_call = true;
+    const int rc = DISPATCH(t, gradient_impl, t, result_ptrs, on_device, value_out);
+    t->async_call = false;
+    t->pending.active = rc == RDB_OK;
+    return rc;
+}
+int rdb_tape_wait(rdb_tape *t) {
+    if (!t) return fail(RDB_EINVAL, "null tape");
+    if (!t->pending.active) return RDB_OK;
+    rdb_ctx *c = t->ctx;
+    ctx_enter(c);
+    t->pending.active = false;
+    CU(cudaEventSynchronize(t->done_ev));
+    if (c->side_stream) CU(cudaStreamSynchronize(c->side_stream));      // slicing that ran ahead and was not consumed
+    if (!t->pending.guard || !c->gemm.guard || (c->gemm.guard_used == 0 && !c->gemm.guard_pending)) return RDB_OK;
+    // the accuracy certificate of the call's int8-slice GEMMs, deferred from run_call
+    GuardSummary gs;
+    CU(guard_read(S(t), c->gemm, &gs));
+    t->guard_checked += (int64_t)gs.checked;
+    t->guard_flagged += (int64_t)gs.flagged;
+    if (gs.worst_ratio > t->guard_worst) t->guard_worst = gs.worst_ratio;
+    if (gs.flagged == 0) { t->guard_streak = 0; return RDB_OK; }
+    if (t->opts.gemm_f64_mode != 0) return RDB_OK;
+    // replay with the DMMA kernels, synchronously; the inputs are still in the tape's buffers
+    t->guard_fallbacks++;
+    const int mode0 = t->opts.gemm_f64_mode;
+    t->opts.gemm_f64_mode = 1;
+    t->dmma_now = true;
+    void *const *rp = t->pending.results.data();
+    const int on_device = t->pending.on_device;
+    void *value_out = t->pending.value_out;
+    const int rc = DISPATCH(t, gradient_impl, t, rp, on_device, value_out);
+    t->dmma_now = false;
+    t->opts.gemm_f64_mode = (++t->guard_streak >= 3) ? 1 : mode0;
+    return rc;
 }
 int rdb_jacobian(rdb_tape *t, int slot, int64_t rb, int64_t re, void *result, int64_t ld, int on_device, void *value_out) {
     if (!t || (!result && re > rb)) return fail(RDB_EINVAL, "null argument");

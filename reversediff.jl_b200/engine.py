@@ -60,6 +60,8 @@ def lib():
         "rdb_forward": (i32, [vp]),
         "rdb_reverse_scalar_seed": (i32, [vp]),
         "rdb_gradient": (i32, [vp, C.POINTER(vp), i32, vp]),
+        "rdb_gradient_async": (i32, [vp, C.POINTER(vp), i32, vp]),
+        "rdb_tape_wait": (i32, [vp]),
         "rdb_jacobian": (i32, [vp, i32, i64, i64, vp, i64, i32, vp]),
         "rdb_hessian": (i32, [vp, i64, i64, vp, i64, i32, vp, vp]),
         "rdb_get_value": (i32, [vp, i32, vp]),
@@ -83,7 +85,7 @@ EXPORTED_SYMBOLS = [
     "rdb_version", "rdb_last_error", "rdb_ctx_create", "rdb_ctx_destroy", "rdb_ctx_set_stream",
     "rdb_ctx_synchronize", "rdb_ctx_set_gemm_f64_mode", "rdb_ctx_gemm_guard", "rdb_tape_guard_stats", "rdb_tape_set_async", "rdb_comm_unique_id",
     "rdb_comm_create", "rdb_comm_destroy", "rdb_gather_result", "rdb_place_block", "rdb_tape_load", "rdb_tape_destroy", "rdb_tape_set_input", "rdb_forward",
-    "rdb_reverse_scalar_seed", "rdb_gradient", "rdb_jacobian", "rdb_hessian", "rdb_get_value", "rdb_get_deriv",
+    "rdb_reverse_scalar_seed", "rdb_gradient", "rdb_gradient_async", "rdb_tape_wait", "rdb_jacobian", "rdb_hessian", "rdb_get_value", "rdb_get_deriv",
     "rdb_buffer_size", "rdb_tape_stats", "rdb_tape_launch_count", "rdb_gemm", "rdb_add_sum", "rdb_plan_col_panels", "rdb_schedule_bundles",
 ]
 
@@ -321,6 +323,40 @@ class EngineTape:
             if st is not None:
                 r[...] = st.reshape(r.shape, order="F")
         return val[0] if want_value else None
+
+    def gradient_async(self, results, shapes, want_value=True):
+        """``rdb_gradient_async``: enqueue only.  Host results must be Fortran-contiguous arrays of the tape's dtype (page-locked
+        ones keep the copies off the caller's thread); ``wait()`` completes the call and returns the primal."""
+        n = len(results)
+        ptrs = (C.c_void_p * n)()
+        dev = None
+        for i, (r, s) in enumerate(zip(results, shapes)):
+            p, d, st = self._out_array(r, s)
+            if st is not None:
+                raise ValueError("asynchronous calls write straight into the result arrays: pass Fortran-contiguous arrays of the tape's dtype")
+            if p is not None:
+                dev = d if dev is None else dev
+                if d != dev:
+                    raise ValueError("results must be all host or all device arrays")
+            ptrs[i] = p
+        val = None
+        if want_value:
+            try:                                          # a page-locked scalar, or the tiny D2H copy blocks the caller until the forward sweep is done
+                import torch
+                self._pending_val_t = torch.zeros(1, dtype=torch.float64 if self.np_dtype == np.float64 else torch.float32).pin_memory()
+                val = self._pending_val_t.numpy()
+            except Exception:
+                val = np.zeros(1, self.np_dtype)
+        self._pending = (ptrs, results, val)              # keep everything the device writes to alive until wait()
+        _check(lib().rdb_gradient_async(self.ptr, ptrs, dev or 0, val.ctypes.data_as(C.c_void_p) if want_value else None))
+
+    def wait(self):
+        """``rdb_tape_wait``: results of the pending asynchronous call are valid after this returns; returns its primal (or None)."""
+        _check(lib().rdb_tape_wait(self.ptr))
+        pend, self._pending = getattr(self, "_pending", None), None
+        if pend is None or pend[2] is None:
+            return None
+        return pend[2][0].copy()
 
     def jacobian(self, slot, row_begin, row_end, result, shape, want_value=False, out_shape=None, ld=None):
         p, d, st = self._out_array(result, shape, ld)

@@ -676,3 +676,41 @@ def test_elementwise_run_fusion_is_bit_identical(rd, orc, dtype):
     for x, y in zip(got[1][2], got[0][2]):
         assert np.array_equal(x, y)
     assert got[1][3] < got[0][3]                                  # and it really took fewer launches
+
+
+def test_gradient_pipeline_matches_synchronous_calls(rd):
+    """rdb_gradient_async / rdb_tape_wait through rd.GradientPipeline: six consecutive evaluations with different inputs over two
+    engine copies of the tape, page-locked host arrays; every result must be bit-identical to the synchronous gradient! of the
+    same input (same kernels, same order), values included."""
+    import torch
+    n = 512                                                   # the tcgen05 int8-slice GEMMs and the panel logic are in play
+    rng = np.random.default_rng(7)
+    tape = rd.GradientTape(rd.workloads.f_gradient_example, (rng.random((n, n)), rng.random((n, n))))
+    ct = rd.compile(tape)
+
+    def pinned(shape):
+        t = torch.empty(int(np.prod(shape)), dtype=torch.float64).pin_memory()
+        return t, t.numpy().reshape(shape, order="F")
+    keep, ins, outs = [], [], []
+    for k in range(6):
+        (ta, a), (tb, b) = pinned((n, n)), pinned((n, n))
+        a[...] = rng.random((n, n)); b[...] = rng.random((n, n))
+        (tga, ga), (tgb, gb) = pinned((n, n)), pinned((n, n))
+        keep += [ta, tb, tga, tgb]
+        ins.append((a, b)); outs.append((rd.DiffResult(0.0, ga), rd.DiffResult(0.0, gb)))
+    pipe = rd.GradientPipeline(tape, depth=2)
+    for k in range(6):
+        pipe.submit(outs[k], ins[k])
+    pipe.drain()
+    for k in range(6):
+        ref = (rd.DiffResult(0.0, np.zeros((n, n), order="F")), rd.DiffResult(0.0, np.zeros((n, n), order="F")))
+        rd.gradient_(ref, ct, ins[k])
+        assert np.array_equal(outs[k][0].gradient, ref[0].gradient) and np.array_equal(outs[k][1].gradient, ref[1].gradient), k
+        assert outs[k][0].value == ref[0].value and outs[k][1].value == ref[1].value
+    # a slot refuses a second asynchronous call before its first one was completed
+    h = pipe.slots[0].handle
+    rd.seeded_forward_pass(pipe.slots[0], ins[0])
+    h.gradient_async([outs[0][0].gradient, outs[0][1].gradient], [(n, n), (n, n)])
+    with pytest.raises(Exception):
+        h.gradient_async([outs[0][0].gradient, outs[0][1].gradient], [(n, n), (n, n)])
+    h.wait()
