@@ -41,7 +41,8 @@ SP_POOL, SP_LITERAL, SP_NONE = -1, -2, -3
 ELEMENTWISE = (OP_NBCAST, OP_MAP, OP_BCAST, OP_BCAST_ADD, OP_BCAST_SUB, OP_BCAST_MUL, OP_BCAST_DIV, OP_BCAST_LDIV, OP_BCAST_POW,
                OP_TRACKER_BCAST)
 (E_CONST, E_ADD, E_SUB, E_MUL, E_DIV, E_NEG, E_POWI, E_POW, E_TANH, E_EXP, E_LOG, E_SQRT,
- E_SIN, E_COS, E_ABS2, E_ABS, E_MAX, E_MIN, E_INV, E_SIGMOID, E_ARG) = range(1, 22)
+ E_SIN, E_COS, E_ABS2, E_ABS, E_MAX, E_MIN, E_INV, E_SIGMOID, E_ARG,
+ E_LOG1P, E_EXPM1, E_ASIN, E_ACOS, E_ATAN, E_SINH, E_COSH, E_TAN, E_ATAN2, E_HYPOT) = range(1, 32)
 
 _HEADER = np.dtype([
     ("magic", "<u8"), ("version", "<u4"), ("dtype", "<u4"),
@@ -223,6 +224,39 @@ def dual_eval(ops, fconst, args, dtype, order=1):
         elif code == E_SIGMOID:
             s = one / (one + np.exp(-V[a])); f1 = s * (one - s)
             unary(a, s, f1, f1 * (one - 2 * s))
+        # DiffRules (v1.x, `@define_diffrule`): log1p' = inv(x + 1); expm1' = exp(x); asin' = inv(sqrt(1 - x^2)); acos' = -inv(sqrt(1 - x^2));
+        # atan' = inv(1 + x^2); sinh' = cosh(x); cosh' = sinh(x); tan' = 1 + tan(x)^2  (second derivatives: calculus)
+        elif code == E_LOG1P:
+            u = one / (V[a] + one); unary(a, np.log1p(V[a]), u, -u * u)
+        elif code == E_EXPM1:
+            e = np.exp(V[a]); unary(a, np.expm1(V[a]), e, e)
+        elif code == E_ASIN:
+            w = one - V[a] * V[a]; u = one / np.sqrt(w); unary(a, np.arcsin(V[a]), u, V[a] * u / w)
+        elif code == E_ACOS:
+            w = one - V[a] * V[a]; u = one / np.sqrt(w); unary(a, np.arccos(V[a]), -u, -(V[a] * u / w))
+        elif code == E_ATAN:
+            u = one / (one + V[a] * V[a]); unary(a, np.arctan(V[a]), u, -2 * V[a] * u * u)
+        elif code == E_SINH:
+            unary(a, np.sinh(V[a]), np.cosh(V[a]), np.sinh(V[a]))
+        elif code == E_COSH:
+            unary(a, np.cosh(V[a]), np.sinh(V[a]), np.cosh(V[a]))
+        elif code == E_TAN:
+            tt = np.tan(V[a]); f1 = one + tt * tt; unary(a, tt, f1, 2 * tt * f1)
+        elif code in (E_ATAN2, E_HYPOT):
+            # atan(y, x): (x / (y^2 + x^2), -y / (y^2 + x^2)); hypot(x, y): (x / hypot(x, y), y / hypot(x, y))
+            va, vb = V[a], V[b]
+            if code == E_ATAN2:
+                r2 = va * va + vb * vb
+                y = np.arctan2(va, vb); ga, gb = vb / r2, -va / r2
+                i4 = one / (r2 * r2); gaa, gbb, gab = -2 * va * vb * i4, 2 * va * vb * i4, (va * va - vb * vb) * i4
+            else:
+                y = np.hypot(va, vb); ga, gb = va / y, vb / y
+                i3 = one / (y * y * y); gaa, gbb, gab = vb * vb * i3, va * va * i3, -(va * vb) * i3
+            V.append(y)
+            D.append([ga * D[a][p] + gb * D[b][p] for p in range(n)])
+            if order == 2:
+                H.append([[ga * H[a][p][q] + gb * H[b][p][q] + gaa * D[a][p] * D[a][q] + gab * (D[a][p] * D[b][q] + D[a][q] * D[b][p])
+                           + gbb * D[b][p] * D[b][q] for q in range(n)] for p in range(n)])
         else:
             raise ValueError(f"unknown scalar opcode {code}")
     shape = np.broadcast_shapes(*[np.shape(v) for v in V[:n]], np.shape(V[-1]))

@@ -20,7 +20,8 @@
 #include <stdint.h>
 
 enum { E_CONST = 1, E_ADD, E_SUB, E_MUL, E_DIV, E_NEG, E_POWI, E_POW, E_TANH, E_EXP, E_LOG, E_SQRT, E_SIN, E_COS,
-       E_ABS2, E_ABS, E_MAX, E_MIN, E_INV, E_SIGMOID, E_ARG };
+       E_ABS2, E_ABS, E_MAX, E_MIN, E_INV, E_SIGMOID, E_ARG,
+       E_LOG1P, E_EXPM1, E_ASIN, E_ACOS, E_ATAN, E_SINH, E_COSH, E_TAN, E_ATAN2, E_HYPOT };
 enum { SP_POOL = -1, SP_LITERAL = -2, SP_NONE = -3 };
 #define MAX_REGS 34
 
@@ -84,6 +85,20 @@ static int dual2(const int32_t *ops, int64_t n_ops, const double *fc, const doub
             case E_ABS: f0 = fabs(V[a]); f1 = signbit(V[a]) ? -1.0 : 1.0; break;   /* abs(d::Dual) = signbit(d) ? -d : d */
             case E_INV: { double rr = 1.0 / V[a]; f0 = rr; f1 = -rr * rr; } break;
             case E_SIGMOID: { double s = 1.0 / (1.0 + exp(-V[a])); f0 = s; f1 = s * (1.0 - s); } break;
+            case E_LOG1P: f0 = log1p(V[a]); f1 = 1.0 / (V[a] + 1.0); break;
+            case E_EXPM1: f0 = expm1(V[a]); f1 = exp(V[a]); break;
+            case E_ASIN: f0 = asin(V[a]); f1 = 1.0 / sqrt(1.0 - V[a] * V[a]); break;
+            case E_ACOS: f0 = acos(V[a]); f1 = -(1.0 / sqrt(1.0 - V[a] * V[a])); break;
+            case E_ATAN: f0 = atan(V[a]); f1 = 1.0 / (1.0 + V[a] * V[a]); break;
+            case E_SINH: f0 = sinh(V[a]); f1 = cosh(V[a]); break;
+            case E_COSH: f0 = cosh(V[a]); f1 = sinh(V[a]); break;
+            case E_TAN: { double tt = tan(V[a]); f0 = tt; f1 = 1.0 + tt * tt; } break;
+            case E_ATAN2: { double va = V[a], vb = V[b], r2 = va * va + vb * vb, ga = vb / r2, gb = -va / r2;
+                            double t0 = ga * D0[a] + gb * D0[b], t1 = ga * D1[a] + gb * D1[b];
+                            V[r] = atan2(va, vb); D0[r] = t0; D1[r] = t1; unary = 0; } break;
+            case E_HYPOT: { double va = V[a], vb = V[b], y = hypot(va, vb), ga = va / y, gb = vb / y;
+                            double t0 = ga * D0[a] + gb * D0[b], t1 = ga * D1[a] + gb * D1[b];
+                            V[r] = y; D0[r] = t0; D1[r] = t1; unary = 0; } break;
             default: return code ? code : -1;
         }
         if (unary) { V[r] = f0; D0[r] = f1 * D0[a]; D1[r] = f1 * D1[a]; }

@@ -1437,7 +1437,7 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
             for (int64_t k = 0; k < I.rec.expr_len; ++k) {
                 int code = ops[4 * k], ra = ops[4 * k + 1], rb = ops[4 * k + 2], imm = ops[4 * k + 3];
                 int reg = I.rec.n_in + (int)k;
-                if (code < E_CONST || code > E_ARG) return fail(RDB_EUNSUPPORTED, "instruction %u: scalar function %d is not on the whitelist", i, code);
+                if (code < E_CONST || code > E_LAST) return fail(RDB_EUNSUPPORTED, "instruction %u: scalar function %d is not on the whitelist", i, code);
                 if (code == E_CONST) { if (imm < 0 || (uint64_t)imm >= h.n_fconst) return fail(RDB_EINVAL, "instruction %u: bad literal", i); }
                 else if (code == E_ARG) { if (imm < 0 || imm >= I.rec.n_in) return fail(RDB_EINVAL, "instruction %u: bad arg ref", i); }
                 else {

@@ -18,6 +18,16 @@ template <> struct M<double> {
     static __device__ __forceinline__ double cos_(double x) { return cos(x); }
     static __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
     static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+    static __device__ __forceinline__ double log1p_(double x) { return log1p(x); }
+    static __device__ __forceinline__ double expm1_(double x) { return expm1(x); }
+    static __device__ __forceinline__ double asin_(double x) { return asin(x); }
+    static __device__ __forceinline__ double acos_(double x) { return acos(x); }
+    static __device__ __forceinline__ double atan_(double x) { return atan(x); }
+    static __device__ __forceinline__ double sinh_(double x) { return sinh(x); }
+    static __device__ __forceinline__ double cosh_(double x) { return cosh(x); }
+    static __device__ __forceinline__ double tan_(double x) { return tan(x); }
+    static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+    static __device__ __forceinline__ double hypot_(double x, double y) { return hypot(x, y); }
 };
 template <> struct M<float> {
     static __device__ __forceinline__ float tanh_(float x) { return tanhf(x); }
@@ -28,6 +38,16 @@ template <> struct M<float> {
     static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
     static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
     static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float log1p_(float x) { return log1pf(x); }
+    static __device__ __forceinline__ float expm1_(float x) { return expm1f(x); }
+    static __device__ __forceinline__ float asin_(float x) { return asinf(x); }
+    static __device__ __forceinline__ float acos_(float x) { return acosf(x); }
+    static __device__ __forceinline__ float atan_(float x) { return atanf(x); }
+    static __device__ __forceinline__ float sinh_(float x) { return sinhf(x); }
+    static __device__ __forceinline__ float cosh_(float x) { return coshf(x); }
+    static __device__ __forceinline__ float tan_(float x) { return tanf(x); }
+    static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+    static __device__ __forceinline__ float hypot_(float x, float y) { return hypotf(x, y); }
 };
 
 template <typename T>
@@ -243,6 +263,47 @@ __device__ __forceinline__ void eval_expr(const int4 *__restrict__ ops, int n_op
             case E_ABS: { f0 = M<T>::abs_(V[a]); f1 = signbit(V[a]) ? (T)-1 : (T)1; f2 = (T)0; } break;   // abs(d::Dual) = signbit(d) ? -d : d
             case E_INV: { const T rr = (T)1 / V[a]; f0 = rr; f1 = -rr * rr; f2 = (T)2 * rr * rr * rr; } break;
             case E_SIGMOID: { const T s = (T)1 / ((T)1 + M<T>::exp_(-V[a])); f0 = s; f1 = s * ((T)1 - s); f2 = f1 * ((T)1 - (T)2 * s); } break;
+            // DiffRules: log1p' = inv(x + 1), expm1' = exp(x), asin' = inv(sqrt(1 - x^2)), acos' = -inv(sqrt(1 - x^2)),
+            // atan' = inv(1 + x^2), sinh' = cosh(x), cosh' = sinh(x), tan' = 1 + tan(x)^2
+            case E_LOG1P: { const T u = (T)1 / (V[a] + (T)1); f0 = M<T>::log1p_(V[a]); f1 = u; f2 = -u * u; } break;
+            case E_EXPM1: { const T e = M<T>::exp_(V[a]); f0 = M<T>::expm1_(V[a]); f1 = e; f2 = e; } break;
+            case E_ASIN: { const T w = (T)1 - V[a] * V[a], u = (T)1 / M<T>::sqrt_(w); f0 = M<T>::asin_(V[a]); f1 = u; f2 = V[a] * u / w; } break;
+            case E_ACOS: { const T w = (T)1 - V[a] * V[a], u = (T)1 / M<T>::sqrt_(w); f0 = M<T>::acos_(V[a]); f1 = -u; f2 = -(V[a] * u / w); } break;
+            case E_ATAN: { const T u = (T)1 / ((T)1 + V[a] * V[a]); f0 = M<T>::atan_(V[a]); f1 = u; f2 = (T)-2 * V[a] * u * u; } break;
+            case E_SINH: { f0 = M<T>::sinh_(V[a]); f1 = M<T>::cosh_(V[a]); f2 = f0; } break;
+            case E_COSH: { f0 = M<T>::cosh_(V[a]); f1 = M<T>::sinh_(V[a]); f2 = f0; } break;
+            case E_TAN: { const T tt = M<T>::tan_(V[a]); f0 = tt; f1 = (T)1 + tt * tt; f2 = (T)2 * tt * f1; } break;
+            case E_ATAN2:
+            case E_HYPOT: {
+                // y = g(a, b) with partials (ga, gb) and second partials (gaa, gab, gbb):
+                //   atan(y, x): (x / (y^2 + x^2), -y / (y^2 + x^2))   [DiffRules atan(x, y) with the roles of its names]
+                //   hypot(x, y): (x / hypot, y / hypot)
+                const T va = V[a], vb = V[b];
+                T y, ga, gb, gaa = (T)0, gab = (T)0, gbb = (T)0;
+                if (code == E_ATAN2) {
+                    const T r2 = va * va + vb * vb;
+                    y = M<T>::atan2_(va, vb); ga = vb / r2; gb = -va / r2;
+                    if (ORDER == 2) { const T i4 = (T)1 / (r2 * r2); gaa = (T)-2 * va * vb * i4; gbb = (T)2 * va * vb * i4; gab = (va * va - vb * vb) * i4; }
+                } else {
+                    y = M<T>::hypot_(va, vb); ga = va / y; gb = vb / y;
+                    if (ORDER == 2) { const T i3 = (T)1 / (y * y * y); gaa = vb * vb * i3; gbb = va * va * i3; gab = -(va * vb) * i3; }
+                }
+                if (ORDER == 2) {
+#pragma unroll
+                    for (int p = 0; p < N; ++p)
+#pragma unroll
+                        for (int q = p; q < N; ++q)
+                            H[r][tri(p, q, N)] = ga * H[a][tri(p, q, N)] + gb * H[b][tri(p, q, N)] + gaa * D[a][p] * D[a][q] +
+                                                 gab * (D[a][p] * D[b][q] + D[a][q] * D[b][p]) + gbb * D[b][p] * D[b][q];
+                }
+                T dn[N];
+#pragma unroll
+                for (int p = 0; p < N; ++p) dn[p] = ga * D[a][p] + gb * D[b][p];
+                V[r] = y;
+#pragma unroll
+                for (int p = 0; p < N; ++p) D[r][p] = dn[p];
+                unary = false;
+            } break;
             default: f0 = (T)0; break;
         }
         if (unary) {

@@ -249,6 +249,30 @@ static bool emit_instruction(Gen &g, const ExprParams &P, const int32_t *ops, co
                 o << "    const T t_" << r << " = " << g.one() << " / (" << g.one() << " + " << g.fn("exp") << "(-" << g.V(a) << "));\n";
                 g.unary(r, a, "t_" + std::to_string(r), "t_" + std::to_string(r) + " * (" + g.one() + " - t_" + std::to_string(r) + ")");
                 break;
+            case E_LOG1P: g.unary(r, a, g.fn("log1p") + "(" + g.V(a) + ")", g.one() + " / (" + g.V(a) + " + " + g.one() + ")"); break;
+            case E_EXPM1: g.unary(r, a, g.fn("expm1") + "(" + g.V(a) + ")", g.fn("exp") + "(" + g.V(a) + ")"); break;
+            case E_ASIN: g.unary(r, a, g.fn("asin") + "(" + g.V(a) + ")", g.one() + " / " + g.fn("sqrt") + "(" + g.one() + " - " + g.V(a) + " * " + g.V(a) + ")"); break;
+            case E_ACOS: g.unary(r, a, g.fn("acos") + "(" + g.V(a) + ")", "-(" + g.one() + " / " + g.fn("sqrt") + "(" + g.one() + " - " + g.V(a) + " * " + g.V(a) + "))"); break;
+            case E_ATAN: g.unary(r, a, g.fn("atan") + "(" + g.V(a) + ")", g.one() + " / (" + g.one() + " + " + g.V(a) + " * " + g.V(a) + ")"); break;
+            case E_SINH: g.unary(r, a, g.fn("sinh") + "(" + g.V(a) + ")", g.fn("cosh") + "(" + g.V(a) + ")"); break;
+            case E_COSH: g.unary(r, a, g.fn("cosh") + "(" + g.V(a) + ")", g.fn("sinh") + "(" + g.V(a) + ")"); break;
+            case E_TAN:
+                o << "    const T t_" << r << " = " << g.fn("tan") << "(" << g.V(a) << ");\n";
+                g.unary(r, a, "t_" + std::to_string(r), g.one() + " + t_" + std::to_string(r) + " * t_" + std::to_string(r));
+                break;
+            case E_ATAN2: case E_HYPOT: {
+                const std::string R = std::to_string(r);
+                if (code == E_ATAN2) {
+                    o << "    const T r2_" << R << " = " << g.V(a) << " * " << g.V(a) << " + " << g.V(b) << " * " << g.V(b) << ";\n";
+                    o << "    const T " << g.V(r) << " = " << g.fn("atan2") << "(" << g.V(a) << ", " << g.V(b) << ");\n";
+                    o << "    const T ga_" << R << " = " << g.V(b) << " / r2_" << R << ";\n    const T gb_" << R << " = -" << g.V(a) << " / r2_" << R << ";\n";
+                } else {
+                    o << "    const T " << g.V(r) << " = " << g.fn("hypot") << "(" << g.V(a) << ", " << g.V(b) << ");\n";
+                    o << "    const T ga_" << R << " = " << g.V(a) << " / " << g.V(r) << ";\n    const T gb_" << R << " = " << g.V(b) << " / " << g.V(r) << ";\n";
+                }
+                for (int p = 0; p < N; ++p)
+                    o << "    const T " << g.D(r, p) << " = ga_" << R << " * " << g.D(a, p) << " + gb_" << R << " * " << g.D(b, p) << ";\n";
+            } break;
             default: return false;
         }
     }

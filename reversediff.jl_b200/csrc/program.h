@@ -25,6 +25,8 @@ enum Opcode : int32_t {
 enum ExprOp : int32_t {
     E_CONST = 1, E_ADD, E_SUB, E_MUL, E_DIV, E_NEG, E_POWI, E_POW, E_TANH, E_EXP, E_LOG, E_SQRT, E_SIN, E_COS,
     E_ABS2, E_ABS, E_MAX, E_MIN, E_INV, E_SIGMOID, E_ARG,
+    E_LOG1P, E_EXPM1, E_ASIN, E_ACOS, E_ATAN, E_SINH, E_COSH, E_TAN, E_ATAN2, E_HYPOT,
+    E_LAST = E_HYPOT,
 };
 
 #pragma pack(push, 1)

@@ -601,7 +601,7 @@ std::string scalar_block_build(ScalarBlock &B, const int64_t *w, int64_t len, co
         for (int64_t o = 0; o < el; ++o) {
             const int32_t *q = expr + eo + 4 * o;
             const int code = q[0], ra = q[1], rb = q[2], imm = q[3], reg = (int)(na + o);
-            if (code < E_CONST || code > E_ARG) return "scalar block: scalar function is not on the whitelist";
+            if (code < E_CONST || code > E_LAST) return "scalar block: scalar function is not on the whitelist";
             if (code == E_CONST) { if (imm < 0 || (uint64_t)imm >= n_fconst) return "scalar block: bad literal"; }
             else if (code == E_ARG) { if (imm < 0 || imm >= na) return "scalar block: bad arg ref"; }
             else {

@@ -123,6 +123,14 @@ abs2 = _unary(P.E_ABS2, lambda v: v * v)
 abs_ = _unary(P.E_ABS, np.abs)
 inv = _unary(P.E_INV, lambda v: 1.0 / v)
 logistic = _unary(P.E_SIGMOID, lambda v: 1.0 / (1.0 + np.exp(-v)))
+log1p = _unary(P.E_LOG1P, np.log1p)
+expm1 = _unary(P.E_EXPM1, np.expm1)
+asin = _unary(P.E_ASIN, np.arcsin)
+acos = _unary(P.E_ACOS, np.arccos)
+sinh = _unary(P.E_SINH, np.sinh)
+cosh = _unary(P.E_COSH, np.cosh)
+tan = _unary(P.E_TAN, np.tan)
+_atan1 = _unary(P.E_ATAN, np.arctan)
 
 
 def _binary(code, npf):
@@ -140,6 +148,13 @@ def _binary(code, npf):
 
 max_ = _binary(P.E_MAX, np.maximum)
 min_ = _binary(P.E_MIN, np.minimum)
+hypot = _binary(P.E_HYPOT, np.hypot)
+_atan2 = _binary(P.E_ATAN2, np.arctan2)
+
+
+def atan(y, x=None):
+    """``atan(x)`` and the two-argument ``atan(y, x)`` (both in ``DiffRules.diffrules()``)."""
+    return _atan1(y) if x is None else _atan2(y, x)
 
 
 def trace(f, n_args: int, dual=None, pow_flavor: int = 0):
@@ -185,6 +200,16 @@ def eval_value(expr, args, dtype):
         elif code == P.E_MIN: r = np.minimum(regs[a], regs[b])
         elif code == P.E_INV: r = 1.0 / regs[a]
         elif code == P.E_SIGMOID: r = 1.0 / (1.0 + np.exp(-regs[a]))
+        elif code == P.E_LOG1P: r = np.log1p(regs[a])
+        elif code == P.E_EXPM1: r = np.expm1(regs[a])
+        elif code == P.E_ASIN: r = np.arcsin(regs[a])
+        elif code == P.E_ACOS: r = np.arccos(regs[a])
+        elif code == P.E_ATAN: r = np.arctan(regs[a])
+        elif code == P.E_SINH: r = np.sinh(regs[a])
+        elif code == P.E_COSH: r = np.cosh(regs[a])
+        elif code == P.E_TAN: r = np.tan(regs[a])
+        elif code == P.E_ATAN2: r = np.arctan2(regs[a], regs[b])
+        elif code == P.E_HYPOT: r = np.hypot(regs[a], regs[b])
         else:
             raise ValueError(f"unknown scalar opcode {code}")
         regs.append(r)

@@ -39,6 +39,14 @@ _UNARY = {
     P.E_ABS2: (E.abs2, lambda v, y: 2.0 * v),
     P.E_INV: (E.inv, lambda v, y: -(y * y)),                               # -abs2(inv(x))
     P.E_SIGMOID: (E.logistic, lambda v, y: y * (1.0 - y)),
+    P.E_LOG1P: (E.log1p, lambda v, y: 1.0 / (v + 1.0)),                    # inv(x + 1)
+    P.E_EXPM1: (E.expm1, lambda v, y: E.exp(v)),
+    P.E_ASIN: (E.asin, lambda v, y: 1.0 / E.sqrt(1.0 - v * v)),
+    P.E_ACOS: (E.acos, lambda v, y: -(1.0 / E.sqrt(1.0 - v * v))),
+    P.E_ATAN: (E.atan, lambda v, y: 1.0 / (1.0 + v * v)),
+    P.E_SINH: (E.sinh, lambda v, y: E.cosh(v)),
+    P.E_COSH: (E.cosh, lambda v, y: E.sinh(v)),
+    P.E_TAN: (E.tan, lambda v, y: 1.0 + y * y),
 }
 _BINARY = {
     P.E_ADD: (lambda a, b: a + b, lambda a, b, y: 1.0, lambda a, b, y: 1.0),
@@ -46,6 +54,8 @@ _BINARY = {
     P.E_MUL: (lambda a, b: a * b, lambda a, b, y: b, lambda a, b, y: a),
     P.E_DIV: (lambda a, b: a / b, lambda a, b, y: 1.0 / b, lambda a, b, y: -(a / b / b)),   # (one(x)/y, -(x/y/y))
     P.E_POW: (lambda a, b: a ** b, lambda a, b, y: b * a ** (b - 1.0), lambda a, b, y: y * E.log(a)),
+    P.E_ATAN2: (lambda a, b: E.atan(a, b), lambda a, b, y: b / (a * a + b * b), lambda a, b, y: -a / (a * a + b * b)),
+    P.E_HYPOT: (E.hypot, lambda a, b, y: a / y, lambda a, b, y: b / y),
 }
 
 

@@ -93,11 +93,18 @@ E_MAX, E_MIN = 17, 18
 E_INV = 19
 E_SIGMOID = 20  # logistic (LogExpFunctions.logistic)
 E_ARG = 21      # r = arg[imm] (identity; used when the closure returns an argument)
+# second tranche of DiffRules.diffrules() functions (src/derivatives/scalars.jl:5-22, elementwise.jl:70-76)
+E_LOG1P, E_EXPM1, E_ASIN, E_ACOS, E_ATAN, E_SINH, E_COSH, E_TAN = 22, 23, 24, 25, 26, 27, 28, 29
+E_ATAN2 = 30    # atan(y, x)
+E_HYPOT = 31
+E_LAST = E_HYPOT
 E_NAMES = {
     E_CONST: "const", E_ADD: "add", E_SUB: "sub", E_MUL: "mul", E_DIV: "div", E_NEG: "neg",
     E_POWI: "powi", E_POW: "pow", E_TANH: "tanh", E_EXP: "exp", E_LOG: "log", E_SQRT: "sqrt",
     E_SIN: "sin", E_COS: "cos", E_ABS2: "abs2", E_ABS: "abs", E_MAX: "max", E_MIN: "min",
     E_INV: "inv", E_SIGMOID: "logistic", E_ARG: "arg",
+    E_LOG1P: "log1p", E_EXPM1: "expm1", E_ASIN: "asin", E_ACOS: "acos", E_ATAN: "atan", E_SINH: "sinh", E_COSH: "cosh",
+    E_TAN: "tan", E_ATAN2: "atan2", E_HYPOT: "hypot",
 }
 MAX_ARGS = 4
 MAX_DIMS = 4
