@@ -738,7 +738,12 @@ cudaError_t launch_tangent_reverse_sparse(cudaStream_t s, T *td_x, int64_t n_x, 
 // complete and visible (griddepcontrol.wait), and adds its few values in tape order.  No atomics: a column belongs to one lane.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_fill_block_pdl(T *__restrict__ H, int64_t n, int64_t K, int64_t ld) {
+    // its own dependent (the patch kernel) may start at once: it only reads x until its griddepcontrol.wait.  This kernel is itself
+    // launched as a programmatic dependent of whatever kernel precedes it on the stream (back-to-back hessian! calls: the previous
+    // call's patch kernel, which triggers at its start): the CTAs become resident early and wait here, so no launch latency sits
+    // between two calls, and nothing is written before the previous kernel is complete
     asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     using VT = typename Vec<T>::type;
     constexpr int V = Vec<T>::N;
     T zz[V] = {};
@@ -758,6 +763,7 @@ __global__ void __launch_bounds__(kThreads) k_fill_block_pdl(T *__restrict__ H, 
 }
 template <typename T, int N>
 __global__ void __launch_bounds__(128) k_hessian_patch(const SepHessParams P) {
+    asm volatile("griddepcontrol.launch_dependents;");                       // (the next call's fill kernel waits for this grid to complete)
     __shared__ int4 s_ops[kMaxExprRegs];
     for (int i = threadIdx.x; i < P.n_ops; i += blockDim.x) s_ops[i] = reinterpret_cast<const int4 *>(P.ops)[i];
     __syncthreads();
@@ -831,9 +837,16 @@ cudaError_t launch_hessian_separable(cudaStream_t s, const SepHessParams &P) {
     const int64_t per_cta = 4 * kThreads * (contiguous ? Vec<T>::N : 1);
     const int64_t ctas = contiguous ? (P.K * P.n_x + per_cta - 1) / per_cta : P.K * ((P.n_x + per_cta - 1) / per_cta);
     if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
-    k_fill_block_pdl<T><<<(unsigned)ctas, kThreads, 0, s>>>(H, P.n_x, P.K, P.ld);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_fill_block_pdl<T>, H, P.n_x, P.K, P.ld);
+        if (e != cudaSuccess) return e;
+    }
     switch (P.n_args) {
         case 1: return launch_patch_n<T, 1>(s, P);
         case 2: return launch_patch_n<T, 2>(s, P);
