@@ -181,6 +181,61 @@ def use_all_host_cores():
     return blas_threads()
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE any page-locked buffer is
+    allocated, so that first touch places the staging memory on the GPU's own NUMA node.  Returns what was found."""
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0"
+        info["numa_node"] = int(open(path + "/numa_node").read().strip())
+        cl = open(path + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cl.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        info["cpus"] = cl
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+    except Exception as e:
+        info["error"] = str(e)[:80]
+    return info
+
+
+def pcie_probe(torch, dist, world, nbytes=256 << 20, reps=4):
+    """Host<->device copy bandwidth of page-locked buffers with ALL ranks copying at once, both directions concurrently: the
+    platform ceiling of the end-to-end leg (every evaluation moves 268 MB each way per GPU)."""
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory(); h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device="cuda"); d_out = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    def go():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+    go(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        go()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    gbps = reps * nbytes / dt / 1e9
+    return {"GBps_each_way_per_gpu_all_ranks_copying": gbps, "evals_per_s_bound_per_gpu": gbps * 1e9 / (2 * 4096 * 4096 * 8),
+            "note": "concurrent H2D + D2H of 256 MiB page-locked buffers on every rank, max over ranks"}
+
+
 def workload_config(n, dtype):
     """`config` is identical on both arms (the driver compares them); descriptive extras live in `config_detail`."""
     return {"workload": f"compiled-tape gradient! of sum(a'*b + a*b') at {n}x{n} {dtype} (BASELINE configs[1])", "n": n}
@@ -261,6 +316,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     rd = graft.load_package()
     ctx = rd.engine.Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)     # engine launches on torch's stream: events see it
@@ -355,6 +411,7 @@ def main():
         ms_e2e = float(tt.item())
         dist.barrier()
     e2e_val = world * e2e_steps / (ms_e2e * 1e-3)
+    pcie = pcie_probe(torch, dist, world)
     clocks = sampler.stop() if rank == 0 else None           # sampled every 20 ms during the timed regions (device-resident, end-to-end)
     gb_ref = a64.sum(1)[:, None] + a64.sum(0)[None, :]
     for ga_x, gb_x, rr in ((ga_h, gb_h, res_h), (ga_h2, gb_h2, res_h2)):
@@ -487,7 +544,8 @@ def main():
                     "how": "rd.GradientPipeline(depth=2): rdb_tape_set_input + rdb_gradient_async per step, rdb_tape_wait before a slot is "
                            "reused; pinned host inputs and results; host clock from the first submit to the last result byte in host memory",
                     "synchronous_calls": {"value": world * e2e_sync_steps / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync / e2e_sync_steps,
-                                          "how": "one rdb_gradient per step, returning when its results are in host memory"}},
+                                          "how": "one rdb_gradient per step, returning when its results are in host memory"},
+                    "host_link": pcie, "rank0_numa": numa},
             "gpu_launches": int(l_per_step * args.steps),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "parity": {"max_rel_err_vs_closed_form": float(err), "tol": tol},
