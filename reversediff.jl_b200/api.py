@@ -53,6 +53,11 @@ class AbstractTape:
         self.func = func
         self.is_tuple = isinstance(input_, (tuple, list))
         xs = list(input_) if self.is_tuple else [input_]
+        # record-time inputs that already live on the device (torch CUDA tensors, same shape conventions as at replay: an N-D
+        # tensor of the recorded shape, column-major strides or not - only values and shape matter here): recording is host work in
+        # the reference too (operator overloading on TrackedArray), so their values come over once, now; replays then take and
+        # return device arrays without any host copy (`is_device`)
+        xs = [x.detach().cpu().numpy() if _engine._is_device(x) else x for x in xs]
         if dtype is None:
             dtype = np.result_type(*[np.asarray(x).dtype for x in xs])
             if dtype not in (np.float32, np.float64):

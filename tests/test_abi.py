@@ -31,12 +31,39 @@ def test_no_cpu_fallback(rd):
 
 
 def test_oracle_is_not_imported_by_the_product(rd):
+    """The oracle is test infrastructure: no product source may import it, dlopen it, spawn it or even name a path under oracle/
+    in code (prose in comments / docstrings is fine), and importing the product must leave no oracle module or oracle-built library
+    in the process."""
+    import io, sys, tokenize
     root = os.path.join(os.path.dirname(__file__), "..", "reversediff.jl_b200")
     for dirpath, _, files in os.walk(root):
         for f in files:
-            if f.endswith((".py", ".cu", ".h")):
-                src = open(os.path.join(dirpath, f)).read()
+            path = os.path.join(dirpath, f)
+            if f.endswith(".py"):
+                src = open(path).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                # every token that is code or a string literal other than a docstring-position string
+                toks = list(tokenize.generate_tokens(io.StringIO(src).readline))
+                for i, t in enumerate(toks):
+                    if t.type == tokenize.NAME and t.string == "oracle":
+                        raise AssertionError(f"{f}:{t.start[0]} names `oracle` in code")
+                    if t.type == tokenize.STRING and re.search(r"oracle[/\\.]|libscalar_block|scalar_block\.c", t.string):
+                        prev = next((p_ for p_ in reversed(toks[:i]) if p_.type not in (tokenize.NL, tokenize.NEWLINE, tokenize.INDENT,
+                                                                                         tokenize.DEDENT, tokenize.COMMENT)), None)
+                        is_doc = prev is None or prev.string in (":",) or prev.type == tokenize.ENCODING
+                        assert is_doc, f"{f}:{t.start[0]} has a string literal naming the oracle outside a docstring"
+            elif f.endswith((".cu", ".h", ".cuh", ".cpp")):
+                code = re.sub(r"//[^\n]*|/\*.*?\*/", "", open(path).read(), flags=re.S)
+                assert "oracle" not in code and "scalar_block.so" not in code, f"{f} names the oracle in code"
+    assert not [m for m in sys.modules if m == "oracle" or m.startswith("oracle.")] or "oracle.replay" in sys.modules   # (the test session itself may have it)
+    import subprocess
+    probe = ("import sys, os; sys.path.insert(0, %r); import __graft_entry__ as g; g.load_package(); "
+             "bad = [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]; "
+             "maps = open('/proc/self/maps').read(); "
+             "assert not bad and 'libscalar_block' not in maps and '/oracle/' not in maps, (bad,); print('clean')"
+             % os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+    r = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stdout + r.stderr
 
 
 def test_col_panel_planner(rd):

@@ -714,3 +714,21 @@ def test_gradient_pipeline_matches_synchronous_calls(rd):
     with pytest.raises(Exception):
         h.gradient_async([outs[0][0].gradient, outs[0][1].gradient], [(n, n), (n, n)])
     h.wait()
+
+
+def test_record_and_replay_with_device_arrays(rd):
+    """a tape recorded from device arrays replays with device inputs and device results - no host array is
+    ever handed to the engine (values come to the host once, at record time, for the operator-overloading pass)."""
+    import torch
+    n = 300
+    rng = np.random.default_rng(9)
+    a0, b0 = rng.random((n, n)), rng.random((n, n))
+    a, b = rng.random((n, n)), rng.random((n, n))
+    tape = rd.GradientTape(rd.workloads.f_gradient_example, (rd.engine.device_array(a0), rd.engine.device_array(b0)))
+    ref = rd.GradientTape(rd.workloads.f_gradient_example, (a0, b0))
+    assert tape.program_bytes() == ref.program_bytes()
+    ct = rd.compile(tape)
+    ga = torch.empty(n * n, dtype=torch.float64, device="cuda"); gb = torch.empty_like(ga)
+    rd.gradient_((ga, gb), ct, (rd.engine.device_array(a), rd.engine.device_array(b)))
+    assert relerr(ga.cpu().numpy().reshape(n, n, order="F"), b.sum(1)[:, None] + b.sum(0)[None, :]) < 1e-12
+    assert relerr(gb.cpu().numpy().reshape(n, n, order="F"), a.sum(1)[:, None] + a.sum(0)[None, :]) < 1e-12
