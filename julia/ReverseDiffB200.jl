@@ -47,7 +47,8 @@ const SP_POOL, SP_LITERAL, SP_NONE = Int64(-1), Int64(-2), Int64(-3)
 const E_CONST, E_ADD, E_SUB, E_MUL, E_DIV, E_NEG, E_POWI, E_POW = Int32.((1, 2, 3, 4, 5, 6, 7, 8))
 const E_TANH, E_EXP, E_LOG, E_SQRT, E_SIN, E_COS, E_ABS2, E_ABS = Int32.((9, 10, 11, 12, 13, 14, 15, 16))
 const E_MAX, E_MIN, E_INV, E_SIGMOID, E_ARG = Int32.((17, 18, 19, 20, 21))
-const MAX_ARGS, MAX_DIMS, MAX_EXPR_REGS = 4, 4, 32
+const WIRE_ARGS, MAX_ARGS, MAX_DIMS, MAX_EXPR_REGS = 4, 8, 4, 32     # 4 operand slots per record; operands 5.. in OP_MORE_OPERANDS records
+const OP_MORE_OPERANDS = Int32(22)
 const COMPACT_TRANSPOSE_THRESHOLD = 1 << 20
 
 # ------------------------------------------------------------------------------------------------ symbolic reals (expr.py)
@@ -262,6 +263,7 @@ function to_bytes(p::TapeProgram)
         write(bufs, b.alias_of, Int32(0), off)
     end
     ins = IOBuffer(); idx = IOBuffer(); ex = IOBuffer(); fc = IOBuffer()
+    n_records = 0
     n_idx() = position(idx) ÷ 8; n_ex() = position(ex) ÷ 4; n_fc() = position(fc) ÷ 8
     function put_expr(ops, fconsts)                                      # literal indices become absolute in the program-wide pool
         base = n_fc(); start = n_ex()
@@ -299,7 +301,12 @@ function to_bytes(p::TapeProgram)
             eoff, elen = put_expr(it.expr[1], it.expr[2])
         end
         write(ins, it.opcode, Int32(length(inputs)), it.out, it.n_expr_args, Int64(eoff), Int64(elen))
-        for j in 1:MAX_ARGS
+        nrec = 1 + (max(length(inputs), 1) - 1) ÷ WIRE_ARGS
+        n_records += nrec
+        for j in 1:(nrec * WIRE_ARGS)
+            if j > WIRE_ARGS && (j - 1) % WIRE_ARGS == 0             # continuation record: operands j .. j+3 of this instruction
+                write(ins, OP_MORE_OPERANDS, Int32(min(WIRE_ARGS, length(inputs) - (j - 1))), Int32(-1), Int32(0), Int64(0), Int64(0))
+            end
             if j > length(inputs)
                 write(ins, zeros(UInt8, 104)); continue
             end
@@ -315,7 +322,7 @@ function to_bytes(p::TapeProgram)
         end
     end
     sections = (take!(bufs), reinterpret(UInt8, p.inputs) |> collect, take!(ins), take!(idx), take!(ex), take!(fc), take!(consts))
-    counts = (length(p.buffers), length(p.inputs), length(p.instrs))
+    counts = (length(p.buffers), length(p.inputs), n_records)
     offs = Int[]; off = 128
     for s in sections
         push!(offs, off); off += align8(length(s))

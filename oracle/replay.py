@@ -28,7 +28,8 @@ import numpy as np
 
 MAGIC = 0x3030324244525052
 VERSION = 2
-MAX_ARGS, MAX_DIMS = 4, 4
+MAX_ARGS, MAX_DIMS = 4, 4          # (MAX_ARGS: operand slots per record; longer operand lists continue in OP_MORE_OPERANDS records)
+OP_MORE_OPERANDS = 22
 
 BUF_TA, BUF_TR, BUF_CONST = 0, 1, 2
 CLS_TA, CLS_IDX, CLS_CONST, CLS_TR = 0, 1, 2, 3
@@ -308,13 +309,15 @@ class OracleTape:
                 self.value.append(np.zeros(dims, self.dtype, order="F"))
                 self.deriv.append(np.zeros(dims, self.dtype, order="F"))
         self.instrs = []
-        for rec in ins:
+        for r_, rec in enumerate(ins):
+            if int(rec["opcode"]) == OP_MORE_OPERANDS:       # operands 5.. of the record before it (broadcast.jl:142-146 is N-ary)
+                continue
             it = _Instr()
             it.opcode, it.out = int(rec["opcode"]), int(rec["out"])
             it.n_expr_args = int(rec["n_expr_args"])
             it.inputs = []
             for j in range(int(rec["n_in"])):
-                o = rec["in"][j]
+                o = ins[r_ + j // MAX_ARGS]["in"][j % MAX_ARGS]
                 op = _Operand()
                 op.buffer, op.cls, op.tracked = int(o["buffer"]), int(o["cls"]), bool(o["tracked"])
                 nd = int(o["ndims"])

@@ -1354,12 +1354,27 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
     }
 
     // instructions ---------------------------------------------------------------------------------------
-    t->instrs.resize(h.n_instr);
-    for (uint32_t i = 0; i < h.n_instr; ++i) {
+    // a record with more than kWireArgs operands is followed by OP_MORE_OPERANDS records holding the rest
+    std::vector<uint32_t> heads;
+    for (uint32_t r = 0; r < h.n_instr;) {
+        const InstrRec &R = irec[r];
+        if (R.opcode == OP_MORE_OPERANDS) return fail(RDB_EINVAL, "record %u: operand continuation without an instruction", r);
+        if (R.n_in < 1 || R.n_in > kMaxArgs) return fail(RDB_EINVAL, "record %u: bad input count", r);
+        heads.push_back(r);
+        uint32_t extra = R.n_in > kWireArgs ? (uint32_t)((R.n_in - 1) / kWireArgs) : 0;
+        for (uint32_t e = 1; e <= extra; ++e) {
+            const int want = std::min(kWireArgs, R.n_in - (int)e * kWireArgs);
+            if (r + e >= h.n_instr || irec[r + e].opcode != OP_MORE_OPERANDS || irec[r + e].n_in != want)
+                return fail(RDB_EINVAL, "record %u: missing or malformed operand continuation", r);
+        }
+        r += 1 + extra;
+    }
+    t->instrs.resize(heads.size());
+    for (uint32_t i = 0; i < (uint32_t)heads.size(); ++i) {
         InstrPlan &I = t->instrs[i];
-        I.rec = irec[i];
+        const uint32_t r0 = heads[i];
+        I.rec = irec[r0];
         const int op = I.rec.opcode;
-        if (I.rec.n_in < 1 || I.rec.n_in > kMaxArgs) return fail(RDB_EINVAL, "instruction %u: bad input count", i);
         if (I.rec.out < 0 || (uint32_t)I.rec.out >= h.n_buffers || t->bufs[I.rec.out].kind == BUF_CONST) return fail(RDB_EINVAL, "instruction %u: bad output", i);
         switch (op) {
             case OP_MUL: case OP_ADD: case OP_SUB: case OP_DOT: if (I.rec.n_in != 2) return fail(RDB_EINVAL, "instruction %u: needs 2 inputs", i); break;
@@ -1376,7 +1391,7 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
         Buf &out = t->bufs[I.rec.out];
         for (int a = 0; a < I.rec.n_in; ++a) {
             OperandPlan &o = I.in[a];
-            o.rec = I.rec.in[a];
+            o.rec = irec[r0 + a / kWireArgs].in[a % kWireArgs];
             if (o.rec.buffer < 0 || (uint32_t)o.rec.buffer >= h.n_buffers) return fail(RDB_EINVAL, "instruction %u: bad operand buffer", i);
             if (o.rec.ndims < 0 || o.rec.ndims > kMaxDims) return fail(RDB_EINVAL, "instruction %u: bad operand ndims", i);
             Buf &b = t->bufs[o.rec.buffer];
@@ -1708,6 +1723,7 @@ static int ensure_second_order(rdb_tape *t) {
         if (!is_elementwise(op)) continue;
         Buf &out = t->bufs[I.rec.out];
         const int N = I.rec.n_in;
+        if (N > 4) return fail(RDB_EUNSUPPORTED, "hessian!: elementwise closures of more than four arguments have no second-order kernel yet");
         for (int a = 0; a < N; ++a) {
             if (I.in[a].size != out.size) return fail(RDB_EUNSUPPORTED, "hessian!: broadcasting elementwise instructions are not lowered yet");
             if (!I.partial[a]) OK(dev_alloc(t, &I.partial[a], out.size * (int64_t)t->es));
@@ -2087,6 +2103,7 @@ static int sep_hess_plan(rdb_tape *t) {
     if ((R.rec.opcode != OP_SUM && R.rec.opcode != OP_MEAN) || root(R.rec.out) != root(t->output) || root(R.in[0].rec.buffer) != root(E.rec.out)) return RDB_OK;
     if (!is_elementwise(E.rec.opcode) || E.rec.opcode == OP_TRACKER_BCAST || E.rec.expr_len <= 0 || !E.d_ops) return RDB_OK;
     const int N = E.rec.n_in;
+    if (N > 4) return RDB_OK;
     const int64_t m = t->bufs[E.rec.out].size;
     std::vector<int> producer(t->bufs.size(), -1);
     for (size_t ii = 0; ii + 2 < ni; ++ii) {

@@ -372,8 +372,12 @@ static cudaError_t expr_forward_n(cudaStream_t s, const ExprParams &p) {
     d.block_sums = reinterpret_cast<double *>(p.block_sums); d.n_ops = p.n_ops;
     int grid = p.reduce ? kReduceBlocks : grid_for(p.n, 2);
     if (p.order == 2) {
-        if (p.reduce) k_expr_forward<T, N, 2, true><<<grid, kThreads, 0, s>>>(d);
-        else k_expr_forward<T, N, 2, false><<<grid, kThreads, 0, s>>>(d);
+        if constexpr (N <= 4) {                 // second partials (hessian!) are built for closures of up to four arguments
+            if (p.reduce) k_expr_forward<T, N, 2, true><<<grid, kThreads, 0, s>>>(d);
+            else k_expr_forward<T, N, 2, false><<<grid, kThreads, 0, s>>>(d);
+        } else {
+            return cudaErrorInvalidValue;
+        }
     } else {
         if (p.reduce) k_expr_forward<T, N, 1, true><<<grid, kThreads, 0, s>>>(d);
         else k_expr_forward<T, N, 1, false><<<grid, kThreads, 0, s>>>(d);
@@ -388,6 +392,10 @@ cudaError_t launch_expr_forward(cudaStream_t s, const ExprParams &p) {
         case 2: return expr_forward_n<T, 2>(s, p);
         case 3: return expr_forward_n<T, 3>(s, p);
         case 4: return expr_forward_n<T, 4>(s, p);
+        case 5: return expr_forward_n<T, 5>(s, p);
+        case 6: return expr_forward_n<T, 6>(s, p);
+        case 7: return expr_forward_n<T, 7>(s, p);
+        case 8: return expr_forward_n<T, 8>(s, p);
     }
     return cudaErrorInvalidValue;
 }

@@ -7,7 +7,8 @@ namespace rdb {
 
 constexpr uint64_t kMagic = 0x3030324244525052ull;
 constexpr uint32_t kVersion = 2;
-constexpr int kMaxArgs = 4;
+constexpr int kWireArgs = 4;   // operand slots of one instruction record on the wire
+constexpr int kMaxArgs = 8;    // operands of one instruction (records with more than kWireArgs continue in OP_MORE_OPERANDS records)
 constexpr int kMaxDims = 4;
 constexpr int kMaxExprRegs = 32;
 
@@ -20,6 +21,7 @@ enum Opcode : int32_t {
     OP_BCAST = 9, OP_BCAST_ADD = 10, OP_BCAST_SUB = 11, OP_BCAST_MUL = 12, OP_BCAST_DIV = 13, OP_BCAST_LDIV = 14, OP_BCAST_POW = 15,
     OP_GETINDEX = 16, OP_DOT = 17, OP_SUMDIMS = 18, OP_TRACKER_BCAST = 19, OP_GETINDEX_GENERIC = 20,
     OP_SCALAR_BLOCK = 21,   // a run of ScalarInstructions; payload layout in program.py (ScalarBlock)
+    OP_MORE_OPERANDS = 22,  // not an instruction: operands 5.. of the record before it (∇broadcast is N-ary, broadcast.jl:142-146)
 };
 
 enum ExprOp : int32_t {
@@ -64,7 +66,7 @@ static_assert(sizeof(OperandRec) == 104, "OperandRec layout");
 struct InstrRec {
     int32_t opcode, n_in, out, n_expr_args;
     int64_t expr_offset, expr_len;
-    OperandRec in[kMaxArgs];
+    OperandRec in[kWireArgs];
 };
 static_assert(sizeof(InstrRec) == 32 + 4 * 104, "InstrRec layout");
 #pragma pack(pop)

@@ -63,6 +63,7 @@ OP_SUMDIMS = 18   # sum!/sum(x,dims) linalg/reductions.jl:32-46
 OP_TRACKER_BCAST = 19  # tracker_∇broadcast (a plain Real or TrackedReal among the args)  broadcast.jl:229-238
 OP_GETINDEX_GENERIC = 20  # (getindex, Val(:generic)): integer-vector indices  tracked.jl:352-362
 OP_SCALAR_BLOCK = 21  # a run of consecutive ScalarInstructions (tape.jl:30-45; derivatives/scalars.jl:52-123), see ScalarBlock
+OP_MORE_OPERANDS = 22  # not an instruction: operands 5.. of the record before it (`∇broadcast` is N-ary, broadcast.jl:142-146)
 OP_NAMES = {
     OP_MUL: "*", OP_ADD: "+", OP_SUB: "-", OP_NEG: "neg", OP_SUM: "sum", OP_MEAN: "mean",
     OP_NBCAST: "∇broadcast", OP_MAP: "map", OP_BCAST: "broadcast",
@@ -106,7 +107,8 @@ E_NAMES = {
     E_LOG1P: "log1p", E_EXPM1: "expm1", E_ASIN: "asin", E_ACOS: "acos", E_ATAN: "atan", E_SINH: "sinh", E_COSH: "cosh",
     E_TAN: "tan", E_ATAN2: "atan2", E_HYPOT: "hypot",
 }
-MAX_ARGS = 4
+WIRE_ARGS = 4     # operand slots of one instruction record
+MAX_ARGS = 8      # operands of one instruction; records 5.. travel in OP_MORE_OPERANDS records right behind it
 MAX_DIMS = 4
 MAX_EXPR_REGS = 32
 
@@ -139,7 +141,7 @@ assert OPERAND_DTYPE.itemsize == 104
 INSTR_DTYPE = np.dtype([
     ("opcode", "<i4"), ("n_in", "<i4"), ("out", "<i4"), ("n_expr_args", "<i4"),
     ("expr_offset", "<i8"), ("expr_len", "<i8"),
-    ("in", OPERAND_DTYPE, (MAX_ARGS,)),
+    ("in", OPERAND_DTYPE, (WIRE_ARGS,)),
 ])
 assert INSTR_DTYPE.itemsize == 32 + 4 * 104
 
@@ -339,12 +341,16 @@ class TapeProgram:
                 if pad:
                     const_chunks.append(b"\0" * pad)
                 const_off += len(raw) + pad
-        ins = np.zeros(ni, INSTR_DTYPE)
+        n_rec = sum(1 + (max(len(it.inputs), 1) - 1) // WIRE_ARGS for it in self.instrs)
+        ins = np.zeros(n_rec, INSTR_DTYPE)
         idx_chunks, idx_off = [], 0
         expr_chunks, expr_off = [], 0
         fconst_chunks, fconst_off = [], 0
-        for i, it in enumerate(self.instrs):
-            rec = ins[i]
+        r = 0
+        for it in self.instrs:
+            rec = ins[r]
+            r0 = r
+            r += 1 + (max(len(it.inputs), 1) - 1) // WIRE_ARGS
             rec["opcode"] = it.opcode
             rec["n_in"] = len(it.inputs)
             rec["out"] = it.out
@@ -395,7 +401,11 @@ class TapeProgram:
                 fconst_chunks.append(np.asarray(fc, np.float64))
                 fconst_off += len(fc)
             for j, op in enumerate(it.inputs):
-                o = rec["in"][j]
+                if j >= WIRE_ARGS and j % WIRE_ARGS == 0:            # continuation record
+                    more = ins[r0 + j // WIRE_ARGS]
+                    more["opcode"], more["out"] = OP_MORE_OPERANDS, -1
+                    more["n_in"] = min(WIRE_ARGS, len(it.inputs) - j)
+                o = ins[r0 + j // WIRE_ARGS]["in"][j % WIRE_ARGS]
                 o["buffer"], o["cls"], o["tracked"] = op.buffer, op.cls, int(op.tracked)
                 o["idx_kind"] = op.idx_kind
                 o["ndims"] = len(op.dims)
@@ -435,7 +445,7 @@ class TapeProgram:
 
         h = hdr[0]
         h["magic"], h["version"], h["dtype"] = MAGIC, VERSION, self.dtype
-        h["n_buffers"], h["n_instr"], h["n_inputs"] = nb, ni, nin
+        h["n_buffers"], h["n_instr"], h["n_inputs"] = nb, n_rec, nin
         h["output_buffer"] = self.output_buffer
         h["off_buffers"] = place(bufs.tobytes())
         h["off_inputs"] = place(inputs.tobytes())
@@ -479,10 +489,12 @@ class TapeProgram:
             p.buffers.append(Buffer(int(b["kind"]), dims, int(b["alias_of"]), data))
         p.inputs = [int(i) for i in inputs]
         p.output_buffer = int(h["output_buffer"])
-        for rec in ins:
+        for r, rec in enumerate(ins):
+            if int(rec["opcode"]) == OP_MORE_OPERANDS:
+                continue
             ops_in = []
             for j in range(int(rec["n_in"])):
-                o = rec["in"][j]
+                o = ins[r + j // WIRE_ARGS]["in"][j % WIRE_ARGS]
                 nd = int(o["ndims"])
                 m = None
                 if int(o["idx_kind"]) == IDX_EXPLICIT:

@@ -732,3 +732,42 @@ def test_record_and_replay_with_device_arrays(rd):
     rd.gradient_((ga, gb), ct, (rd.engine.device_array(a), rd.engine.device_array(b)))
     assert relerr(ga.cpu().numpy().reshape(n, n, order="F"), b.sum(1)[:, None] + b.sum(0)[None, :]) < 1e-12
     assert relerr(gb.cpu().numpy().reshape(n, n, order="F"), a.sum(1)[:, None] + a.sum(0)[None, :]) < 1e-12
+
+
+def _f_many_args(rd, k):
+    E, T = rd.expr, rd.tracked
+
+    def f(*xs):
+        # one fused dot-broadcast of k array arguments (broadcast.jl:142-146 is N-ary): matrices, a column vector and a row vector
+        def g(*v):
+            acc = v[0] * v[1]
+            for i in range(2, len(v)):
+                acc = acc + (E.tanh(v[i]) * v[i - 1] if i % 2 else v[i] * v[i] * 0.5)
+            return acc
+        return T.sum(T.bcast(g, *xs))
+    return f
+
+
+def _many_args_inputs(k, seed, m=24, n=40):
+    rng = np.random.default_rng(seed)
+    shapes = [(m, n)] * k
+    shapes[2] = (m,)                 # broadcasts along columns
+    shapes[-1] = (1, n)              # broadcasts along rows
+    return [np.asfortranarray(rng.random(s) - 0.3) for s in shapes]
+
+
+@pytest.mark.parametrize("k", [5, 6, 8])
+def test_nbcast_more_than_four_arguments(rd, orc, k):
+    """`∇broadcast` with more than four array arguments: operands 5.. travel in OP_MORE_OPERANDS records; NVRTC kernel on the
+    device (the interpreter in a child process with RDB_JIT=0), oracle on the host."""
+    run_gradient(rd, orc, _f_many_args(rd, k), _many_args_inputs(k, 1), _many_args_inputs(k, 2), np.float64)
+
+
+def test_nbcast_many_arguments_interpreter_in_child_process():
+    import subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    e = dict(os.environ); e["RDB_JIT"] = "0"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "more_than_four or run_fusion", "-p", "no:cacheprovider"],
+                       cwd=os.path.dirname(here), env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
