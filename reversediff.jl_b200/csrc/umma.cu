@@ -1184,6 +1184,122 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
 }
 
 // --------------------------------------------------------------------------------------------------
+// PERSISTENT cluster variant: one 2-CTA cluster per SM pair for the whole launch, tiles dealt round-robin over the clusters in raster
+// order.  TMEM, barriers and tensor-map fetches are set up once; the stage ring runs on across tile boundaries, so while the 16
+// epilogue warps drain tile t the producer already fills both stages of tile t+1 (the accumulators - 448 of the 512 TMEM columns -
+// cannot be double-buffered, so the MMA thread itself waits for `tmem_empty`).  Per tile this removes TMEM allocation, barrier
+// initialisation, two cluster barriers and the exposed latency of the first loads: ~3 us of the ~87 us a 4096-deep tile takes, ~3 us
+// of the ~30 us of the MLP config's 1024-deep tiles.
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+umma_ozaki2cp_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, OzParams P,
+                     int m_tiles, int n_groups) {
+    constexpr int CL = 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int KB = 64, STAGES2 = stages_for(KB), A_SLICE = BM2 * KB, B_SLICE = BN2 * KB;
+    constexpr int SL = (S + CL - 1) / CL, SA = SL * CL;
+    constexpr int STAGE = SA * A_SLICE + S * B_SLICE;
+    constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
+    uint64_t *full = (uint64_t *)(smem + STAGES2 * STAGE);
+    uint64_t *empty = full + STAGES2;
+    uint64_t *tmem_full = empty + STAGES2;
+    uint64_t *tmem_empty = tmem_full + 1;
+    uint32_t *tmem_ptr = (uint32_t *)(tmem_empty + 1);
+    constexpr int TCOLS = 512;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const int cid = (int)(blockIdx.x / CL), nclusters = (int)(gridDim.x / CL);
+    const int items = m_tiles * n_groups;
+    const int kblocks = (K + KB - 1) / KB;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, EPI_CB * 4);                        // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t kc = 0;                                       // k-blocks issued so far, over all tiles: the ring never restarts
+            for (int it = cid; it < items; it += nclusters) {
+                int m_tile, n_group;
+                raster(it, m_tiles, n_groups, P.group_m, m_tile, n_group);
+                const int m0 = m_tile * BM2, n0 = (n_group * CL + (int)crank) * BN2;
+                for (int kb = 0; kb < kblocks; ++kb, ++kc) {
+                    const int s = (int)(kc % STAGES2);
+                    const uint32_t ph = (kc / STAGES2) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], STAGE);
+                    tma_load_3d_mc(smem + s * STAGE + crank * SL * A_SLICE, &tmAmc, &full[s], kb * KB, m0, crank * SL, MASK);
+                    tma_load_3d(smem + s * STAGE + SA * A_SLICE, &tmB, &full[s], kb * KB, n0, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t kc = 0, tile = 0;
+            for (int it = cid; it < items; it += nclusters, ++tile) {
+                if (tile > 0) { mbar_wait(tmem_empty, (tile - 1) & 1); tc_fence_after(); }   // the epilogue has read the previous tile out of TMEM
+                for (int kb = 0; kb < kblocks; ++kb, ++kc) {
+                    const int s = (int)(kc % STAGES2);
+                    const uint32_t ph = (kc / STAGES2) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(smem + s * STAGE), b0 = a0 + SA * A_SLICE;
+#pragma unroll
+                    for (int p = 0; p < S; ++p) {
+                        const uint64_t ad = make_desc_kb<KB>(a0 + p * A_SLICE);
+#pragma unroll
+                        for (int q0 = 0; q0 < S - p; q0 += 4) {
+                            const int nq = (S - p - q0) < 4 ? (S - p - q0) : 4;
+                            const uint64_t bd = make_desc_kb<KB>(b0 + q0 * B_SLICE);
+                            const uint32_t acc = tmem_base + (uint32_t)((p + q0) * BN2);
+                            const uint32_t idesc = make_idesc_i8(nq * BN2);
+#pragma unroll
+                            for (int k = 0; k < KB / 32; ++k)
+                                tc_mma<KIND_I8>(acc, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || p > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit_mc(&empty[s], MASK);
+                }
+                tc_commit(tmem_full);
+            }
+        }
+    } else {
+        uint32_t tile = 0;
+        for (int it = cid; it < items; it += nclusters, ++tile) {
+            int m_tile, n_group;
+            raster(it, m_tiles, n_groups, P.group_m, m_tile, n_group);
+            const int m0 = m_tile * BM2, n0 = (n_group * CL + (int)crank) * BN2;
+            mbar_wait(tmem_full, tile & 1);
+            tc_fence_after();
+            oz2_epilogue<S>(tmem_base, warp & 3, (warp - 2) >> 2, lane, m0, n0, M, N, P);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(tmem_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS));
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
 // CTA-PAIR variant (cta_group::2).  The cluster kernel above runs its main loop at ~79 % of the int8 pipe: per 64-byte K-block
 // the MMAs read 192 KB of operands from shared memory and TMA writes 92 KB into it - 2.27 k clk of a 128 B/clk port against
 // 1.79 k clk of tensor work (K-sweep in profiles/README.md: 0.27 ms per 1024 of K at 4096 x 4096).  Here two CTAs with ADJACENT
@@ -1712,6 +1828,41 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
                 attrc = true;
             }
             int Mi = (int)M, Ni = (int)N, Ki = (int)Kp;
+            static int persistent = -1;
+            if (persistent < 0) { const char *e = getenv("RDB_OZAKI_PERSISTENT"); persistent = e ? atoi(e) : 1; }
+            // measured (4096 x 4096 outputs): +4 % at K = 1024, nothing at K = 4096, -0.5 % at K = 8192 (the static deal over the resident
+            // clusters loses what the hardware's dynamic CTA scheduling evens out) => short contractions only; 2 = always (tests)
+            if ((persistent == 2 || (persistent == 1 && K <= 2048)) && nslices == 7 && cl == 2) {
+                static int max_clusters = -1;
+                static bool attrcp = false;
+                if (!attrcp) {
+                    cudaError_t e = cudaFuncSetAttribute(umma_ozaki2cp_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_cluster(7, 2));
+                    if (e != cudaSuccess) return e;
+                    attrcp = true;
+                }
+                if (max_clusters < 0) {
+                    cudaLaunchConfig_t q = {};
+                    q.gridDim = dim3(2 * 148); q.blockDim = dim3(OZ_THREADS); q.dynamicSmemBytes = smem_bytes_cluster(7, 2);
+                    cudaLaunchAttribute qa[1];
+                    qa[0].id = cudaLaunchAttributeClusterDimension;
+                    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                    q.attrs = qa; q.numAttrs = 1;
+                    int nc = 0;
+                    if (cudaOccupancyMaxActiveClusters(&nc, umma_ozaki2cp_kernel<7>, &q) != cudaSuccess || nc < 1) { cudaGetLastError(); nc = 0; }
+                    max_clusters = nc;
+                }
+                const int m_tiles = (int)grid2.x, n_groups = (int)(grid2.y / 2);
+                const int items = m_tiles * n_groups;
+                if (max_clusters > 0 && items >= max_clusters) {       // (fewer tiles than clusters: nothing to keep resident for)
+                    cudaLaunchConfig_t pc = {};
+                    pc.gridDim = dim3(2u * (unsigned)max_clusters); pc.blockDim = dim3(OZ_THREADS); pc.dynamicSmemBytes = smem_bytes_cluster(7, 2); pc.stream = st;
+                    cudaLaunchAttribute pa[1];
+                    pa[0].id = cudaLaunchAttributeClusterDimension;
+                    pa[0].val.clusterDim.x = 2; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
+                    pc.attrs = pa; pc.numAttrs = 1;
+                    return cudaLaunchKernelEx(&pc, umma_ozaki2cp_kernel<7>, mAmc, mB, Mi, Ni, Ki, P, m_tiles, n_groups);
+                }
+            }
             if (nslices == 8) {
                 if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 2>, mAmc, mB, Mi, Ni, Ki, P);
                 return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 4>, mAmc, mB, Mi, Ni, Ki, P);

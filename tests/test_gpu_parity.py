@@ -558,7 +558,8 @@ def test_gemm_path_variants_in_child_process(env):
 
 
 @pytest.mark.parametrize("env,select", [({"RDB_HESS_FUSED": "0"}, "cfg5_hessian"),          # hessian!: the general graph-replayed sweep
-                                        ({"RDB_OZAKI_PAIR": "1"}, "cfg2 or panel_sizes")])    # cta_group::2 CTA-pair int8-slice kernel
+                                        ({"RDB_OZAKI_PAIR": "1"}, "cfg2 or panel_sizes"),     # cta_group::2 CTA-pair int8-slice kernel
+                                        ({"RDB_OZAKI_PERSISTENT": "2"}, "cfg2 or panel_sizes or cfg3")])   # persistent cluster kernel for every K
 def test_alternative_paths_in_child_process(env, select):
     import subprocess, sys
     here = os.path.dirname(os.path.abspath(__file__))
