@@ -1714,8 +1714,8 @@ static int ensure_second_order(rdb_tape *t) {
         if (!(op == OP_MUL || op == OP_ADD || op == OP_SUB || op == OP_NEG || op == OP_SUM || op == OP_MEAN || is_getindex(op) || is_elementwise(op)))
             return fail(RDB_EUNSUPPORTED, "hessian!: opcode %d has no forward-over-reverse rule yet", op);
         if (op == OP_MUL) {
-            if (I.in[0].rec.tracked && I.in[1].rec.tracked)
-                return fail(RDB_EUNSUPPORTED, "hessian!: `*` of two tracked operands is not lowered yet");
+            if (I.in[0].rec.tracked && I.in[1].rec.tracked && (I.in[0].mode != OPM_PLAIN || I.in[1].mode != OPM_PLAIN))
+                return fail(RDB_EUNSUPPORTED, "hessian!: `*` of two tracked operands needs both of them untransposed");
             for (int a = 0; a < 2; ++a)
                 if (I.in[a].mode == OPM_GATHER) return fail(RDB_EUNSUPPORTED, "hessian!: gathered `*` operand");
             continue;
@@ -1801,13 +1801,17 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
             sparse_ok[ii] = views;
             if (views) td_nz[root(xid)] = 1;
             else for (int a = 0; a < I.rec.n_in; ++a) if (I.in[a].rec.tracked) td_nz[root(I.in[a].rec.buffer)] = 1;
+        } else if (I.rec.opcode == OP_MUL && I.in[0].rec.tracked && I.in[1].rec.tracked) {
+            // bilinear: the cross terms delta * tv(b)' and tv(a)' * delta exist even when no adjoint tangent flows in
+            for (int a = 0; a < 2; ++a) td_nz[root(I.in[a].rec.buffer)] = 1;
         } else if (!dtz) {
             for (int a = 0; a < I.rec.n_in; ++a) if (I.in[a].rec.tracked) td_nz[root(I.in[a].rec.buffer)] = 1;
         }
     }
     for (size_t ii = ni; ii-- > 0;) {
         InstrPlan &I = t->instrs[ii];
-        const bool nonlinear = is_elementwise(I.rec.opcode) && !sparse_ok[ii];
+        const bool bilinear = I.rec.opcode == OP_MUL && I.in[0].rec.tracked && I.in[1].rec.tracked;
+        const bool nonlinear = (is_elementwise(I.rec.opcode) && !sparse_ok[ii]) || bilinear;
         for (int a = 0; a < I.rec.n_in; ++a) {
             if (!I.in[a].rec.tracked) continue;
             if (nonlinear || (!is_elementwise(I.rec.opcode) && need_tv[root(I.rec.out)])) need_tv[root(I.in[a].rec.buffer)] = 1;
@@ -1819,7 +1823,8 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
         InstrPlan &I = t->instrs[ii];
         for (int a = 0; a < I.rec.n_in; ++a)
             if (root(I.in[a].rec.buffer) == root(xid) && !is_getindex(I.rec.opcode) &&
-                ((is_elementwise(I.rec.opcode) && !sparse_ok[ii]) || (!is_elementwise(I.rec.opcode) && need_tv[root(I.rec.out)])))
+                ((is_elementwise(I.rec.opcode) && !sparse_ok[ii]) || (!is_elementwise(I.rec.opcode) && need_tv[root(I.rec.out)]) ||
+                 (I.rec.opcode == OP_MUL && I.in[0].rec.tracked && I.in[1].rec.tracked)))
                 need_x_tv = true;
     }
 
@@ -1832,7 +1837,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
         std::fill(need_der.begin(), need_der.end(), 0);
         for (size_t ii = 0; ii < ni; ++ii) {
             InstrPlan &I = t->instrs[ii];
-            bool nl = is_elementwise(I.rec.opcode);
+            bool nl = is_elementwise(I.rec.opcode) || (I.rec.opcode == OP_MUL && I.in[0].rec.tracked && I.in[1].rec.tracked);
             for (int a = 0; a < I.rec.n_in && !nl; ++a) nl = need_der[root(I.in[a].rec.buffer)] != 0;
             if (nl) need_der[root(I.rec.out)] = 1;
         }
@@ -1914,7 +1919,13 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                     // exactly one tracked operand (checked): tangent is linear in it
                     OperandPlan &oa = I.in[0], &ob = I.in[1];
                     int64_t M = oa.rows, Kd = oa.cols, N = ob.cols;
-                    if (ob.rec.tracked) {
+                    if (oa.rec.tracked && ob.rec.tracked) {
+                        // d(a b) = da b + a db: a * [tv(b) for every direction] as one GEMM, then tv(a)_k * b per direction
+                        Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
+                        KL(t, gemm_t<T>(S(t), false, false, M, N * Kb, Kd, (T)1, (const T *)a.val, M, (const T *)b.tv, Kd, (T)0, (T *)o.tv, M));
+                        for (int64_t k = 0; k < Kb; ++k)
+                            KL(t, gemm_t<T>(S(t), false, false, M, N, Kd, (T)1, (const T *)a.tv + k * a.size, M, (const T *)b.val, Kd, (T)1, (T *)o.tv + k * o.size, M));
+                    } else if (ob.rec.tracked) {
                         if (ob.mode != OPM_PLAIN) return fail(RDB_EUNSUPPORTED, "hessian!: transposed tracked `*` operand");
                         Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
                         bool st = oa.mode == OPM_FOLDED_T;
@@ -1931,8 +1942,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                     const T *part[kMaxArgs], *tvs[kMaxArgs];
                     for (int a = 0; a < I.rec.n_in; ++a) {
                         part[a] = (const T *)I.partial[a];
-                        tvs[a] = (const T *)t->bufs[I.in[a].rec.buffer].tv;
-                        if (!I.in[a].rec.tracked) return fail(RDB_EUNSUPPORTED, "hessian!: untracked elementwise argument");
+                        tvs[a] = I.in[a].rec.tracked ? (const T *)t->bufs[I.in[a].rec.buffer].tv : nullptr;   // untracked: no tangent
                     }
                     StepTimer tm(t, "tangent_forward", (double)(I.rec.n_in + 1) * o.size * Kb * t->es, 0);
                     KL(t, launch_tangent_forward<T>(S(t), (T *)o.tv, I.rec.n_in, part, tvs, o.size, Kb));
@@ -1998,7 +2008,30 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                 case OP_MUL: {
                     OperandPlan &oa = I.in[0], &ob = I.in[1];
                     int64_t M = oa.rows, Kd = oa.cols, N = ob.cols;
-                    if (ob.rec.tracked) {
+                    if (oa.rec.tracked && ob.rec.tracked) {
+                        // out = a b with both tracked (untransposed).  First order: deriv(a) += delta b', deriv(b) += a' delta.
+                        // Second order, per direction k:   td(a)_k += dt_k b' + delta tv(b)_k'      td(b)_k += a' dt_k + tv(a)_k' delta
+                        Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
+                        const int ra = root(oa.rec.buffer), rb = root(ob.rec.buffer);
+                        if (want_der(oa.rec.buffer)) KL(t, gemm_t<T>(S(t), false, true, M, Kd, N, (T)1, delta, M, (const T *)b.val, Kd, (T)1, (T *)a.der, M));
+                        if (want_der(ob.rec.buffer)) KL(t, gemm_t<T>(S(t), true, false, Kd, N, M, (T)1, (const T *)a.val, M, delta, M, (T)1, (T *)b.der, Kd));
+                        // td(b): one GEMM over all directions for a' dt, then the cross term per direction
+                        if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
+                        bool bz = td_zero[rb] != 0;
+                        if (!dt_zero) { KL(t, gemm_t<T>(S(t), true, false, Kd, N * Kb, M, (T)1, (const T *)a.val, M, dt, M, bz ? (T)0 : (T)1, (T *)b.td, Kd)); bz = false; }
+                        for (int64_t k = 0; k < Kb; ++k)
+                            KL(t, gemm_t<T>(S(t), true, false, Kd, N, M, (T)1, (const T *)a.tv + k * a.size, M, delta, M, bz ? (T)0 : (T)1, (T *)b.td + k * b.size, Kd));
+                        td_zero[rb] = 0;
+                        // td(a) (a and b may be the same buffer: x * x accumulates both halves into one td)
+                        if (td_zero[ra] && ra == root(xid)) OK(overwrite_x_td());
+                        const bool az = td_zero[ra] != 0;
+                        for (int64_t k = 0; k < Kb; ++k) {
+                            bool z = az;
+                            if (!dt_zero) { KL(t, gemm_t<T>(S(t), false, true, M, Kd, N, (T)1, dt + k * o.size, M, (const T *)b.val, Kd, z ? (T)0 : (T)1, (T *)a.td + k * a.size, M)); z = false; }
+                            KL(t, gemm_t<T>(S(t), false, true, M, Kd, N, (T)1, delta, M, (const T *)b.tv + k * b.size, Kd, z ? (T)0 : (T)1, (T *)a.td + k * a.size, M));
+                        }
+                        td_zero[ra] = 0;
+                    } else if (ob.rec.tracked) {
                         const int rb = root(ob.rec.buffer);
                         Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
                         bool st = oa.mode == OPM_FOLDED_T;
@@ -2041,8 +2074,9 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                         break;
                     }
                     const T *tvs[kMaxArgs];
-                    for (int a = 0; a < N; ++a) tvs[a] = (const T *)t->bufs[I.in[a].rec.buffer].tv;
+                    for (int a = 0; a < N; ++a) tvs[a] = I.in[a].rec.tracked ? (const T *)t->bufs[I.in[a].rec.buffer].tv : nullptr;
                     for (int p = 0; p < N; ++p) {
+                        if (!I.in[p].rec.tracked) continue;                    // nothing flows into an untracked argument
                         const int rb = root(I.in[p].rec.buffer);
                         Buf &b = t->bufs[I.in[p].rec.buffer];
                         const T *sec[kMaxArgs];

@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(kThreads) k_tangent_forward(T *__restrict__ ou
         int64_t e = i % n;
         T acc = (T)0;
 #pragma unroll
-        for (int p = 0; p < N; ++p) acc += a.partial[p][e] * a.tv[p][i];
+        for (int p = 0; p < N; ++p) if (a.tv[p]) acc += a.partial[p][e] * a.tv[p][i];     // an untracked argument has no tangent
         out[i] = acc;
     }
 }
@@ -680,7 +680,7 @@ k_tangent_reverse(T *__restrict__ td, const T *__restrict__ dt, const T *__restr
         int64_t e = i % n;
         T acc = (T)0;
 #pragma unroll
-        for (int q = 0; q < N; ++q) acc += a.second[q][e] * a.tv[q][i];
+        for (int q = 0; q < N; ++q) if (a.tv[q]) acc += a.second[q][e] * a.tv[q][i];      // an untracked argument has no tangent
         T v = delta[e] * acc;
         if (dt) v += dt[i] * partial_p[e];          // dt == nullptr: the output's adjoint tangent is known to be zero
         td[i] = OVERWRITE ? v : td[i] + v;

@@ -772,3 +772,45 @@ def test_nbcast_many_arguments_interpreter_in_child_process():
                         "-k", "more_than_four or run_fusion", "-p", "no:cacheprovider"],
                        cwd=os.path.dirname(here), env=e, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("block", [0, 5])
+def test_hessian_bilinear_mul_of_two_tracked_operands(rd, orc, block):
+    """hessian! through `*` with BOTH operands tracked (d2(a b) carries the cross terms delta tv(b)' and tv(a)' delta): X*X with the
+    same buffer on both sides, X * g.(X), and a chain into a third product; against the closed form where there is one and
+    against finite differences of the oracle's gradient."""
+    rng = np.random.default_rng(6)
+    m = 4
+    C = rng.random((m, m))
+
+    def f_square(x):                                         # f = sum(C .* (X X)):  H[(i,k),(k',j)] = C[i,j] d(k,k') + C[k',k... ] (closed form below)
+        X = x.reshape(m, m)
+        return rd.sum(rd.bcast(lambda u, c: u * c, X @ X, C))
+
+    def f_mixed(x):
+        X = x.reshape(m, m)
+        Y = rd.bcast(lambda u: rd.exp(u * 0.5), X)
+        Z = X @ Y                                             # two different tracked buffers
+        return rd.sum(rd.bcast(rd.tanh, Z @ X + Y))            # and a product whose left operand carries tangents already
+
+    x0 = rng.random(m * m); x = rng.random(m * m) - 0.3
+    for f in (f_square, f_mixed):
+        tape = rd.HessianTape(f, x0)
+        ct = rd.compile(tape, seed_block=block)
+        g = np.zeros(m * m); Hn = np.zeros((m * m, m * m), order="F")
+        res = rd.DiffResult(0.0, g, Hn)
+        rd.hessian_(res, ct, x)
+        val, (go,) = orc.OracleTape(tape.program_bytes()).gradient([x])
+        assert abs(res.value - val) < 1e-12 * abs(val) and relerr(g, go) < 1e-12
+        Hfd = orc.hessian_dense(tape.program_bytes(), x)
+        assert np.max(np.abs(Hn - Hfd)) < 1e-6 * max(1.0, np.max(np.abs(Hfd)))
+        assert np.max(np.abs(Hn - Hn.T)) < 1e-12 * np.max(np.abs(Hn))
+        if f is f_square:
+            # f = sum_ijk C[i,j] X[i,k] X[k,j]  =>  d2f / dX[a,b] dX[c,d] = C[a,d] [b == c] + C[c,b] [d == a]   (column-major vec)
+            Hcf = np.zeros((m * m, m * m))
+            for a_ in range(m):
+                for b_ in range(m):
+                    for c_ in range(m):
+                        for d_ in range(m):
+                            Hcf[a_ + b_ * m, c_ + d_ * m] = C[a_, d_] * (b_ == c_) + C[c_, b_] * (d_ == a_)
+            assert relerr(Hn, Hcf) < 1e-13
