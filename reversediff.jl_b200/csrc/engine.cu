@@ -1725,13 +1725,26 @@ static int ensure_second_order(rdb_tape *t) {
         const int N = I.rec.n_in;
         if (N > 4) return fail(RDB_EUNSUPPORTED, "hessian!: elementwise closures of more than four arguments have no second-order kernel yet");
         for (int a = 0; a < N; ++a) {
-            if (I.in[a].size != out.size) return fail(RDB_EUNSUPPORTED, "hessian!: broadcasting elementwise instructions are not lowered yet");
             if (!I.partial[a]) OK(dev_alloc(t, &I.partial[a], out.size * (int64_t)t->es));
         }
         for (int h = 0; h < N * (N + 1) / 2; ++h) OK(dev_alloc(t, &I.second[h], out.size * (int64_t)t->es));
     }
     t->second_order = true;
     return RDB_OK;
+}
+
+// per-argument strides of an elementwise instruction against its output (0 along clamped dimensions, propagation.jl:25-27)
+static void bcast_strides(const InstrPlan &I, const Buf &out, int64_t (*strides)[kMaxDims], int64_t *sizes) {
+    for (int a = 0; a < I.rec.n_in; ++a) {
+        const OperandPlan &o = I.in[a];
+        int64_t st = 1;
+        for (int d = 0; d < kMaxDims; ++d) {
+            const int64_t od = d < o.rec.ndims ? o.rec.dims[d] : 1;
+            strides[a][d] = (od == 1 && out.dims[d] != 1) ? 0 : st;
+            st *= od;
+        }
+        sizes[a] = o.size;
+    }
 }
 
 static int tri_index(int p, int q, int N) {
@@ -1796,7 +1809,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
             for (int a = 0; a < I.rec.n_in && views; ++a) {
                 int pr = producer[root(I.in[a].rec.buffer)];
                 views = I.in[a].rec.tracked && pr >= 0 && is_getindex(t->instrs[pr].rec.opcode) &&
-                        root(t->instrs[pr].in[0].rec.buffer) == root(xid);
+                        root(t->instrs[pr].in[0].rec.buffer) == root(xid) && I.in[a].size == t->bufs[I.rec.out].size;
             }
             sparse_ok[ii] = views;
             if (views) td_nz[root(xid)] = 1;
@@ -1945,7 +1958,14 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                         tvs[a] = I.in[a].rec.tracked ? (const T *)t->bufs[I.in[a].rec.buffer].tv : nullptr;   // untracked: no tangent
                     }
                     StepTimer tm(t, "tangent_forward", (double)(I.rec.n_in + 1) * o.size * Kb * t->es, 0);
-                    KL(t, launch_tangent_forward<T>(S(t), (T *)o.tv, I.rec.n_in, part, tvs, o.size, Kb));
+                    bool same_shape = true;
+                    for (int a = 0; a < I.rec.n_in; ++a) same_shape &= I.in[a].size == o.size;
+                    if (same_shape) KL(t, launch_tangent_forward<T>(S(t), (T *)o.tv, I.rec.n_in, part, tvs, o.size, Kb));
+                    else {
+                        int64_t strides[kMaxArgs][kMaxDims], sizes[kMaxArgs];
+                        bcast_strides(I, o, strides, sizes);
+                        KL(t, launch_tangent_forward_g<T>(S(t), (T *)o.tv, I.rec.n_in, part, tvs, strides, sizes, o.dims, o.size, Kb));
+                    }
                 }
             }
         }
@@ -2082,10 +2102,29 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                         const T *sec[kMaxArgs];
                         for (int q = 0; q < N; ++q) sec[q] = (const T *)I.second[tri_index(p, q, N)];
                         StepTimer tm(t, "tangent_reverse", (double)(N + (dt ? 2 : 1) + (td_zero[rb] ? 0 : 1)) * o.size * Kb * t->es, 0);
-                        if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
-                        KL(t, launch_tangent_reverse<T>(S(t), (T *)b.td, dt, delta, (const T *)I.partial[p], N, sec, tvs, o.size, Kb, td_zero[rb] != 0));
+                        bool same_shape = true;
+                        for (int a = 0; a < N; ++a) same_shape &= I.in[a].size == o.size;
+                        if (same_shape) {
+                            if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
+                            KL(t, launch_tangent_reverse<T>(S(t), (T *)b.td, dt, delta, (const T *)I.partial[p], N, sec, tvs, o.size, Kb, td_zero[rb] != 0));
+                        } else {
+                            // broadcasting closure: the accumulating kernel needs real zeros (or the running sum) in td
+                            if (td_zero[rb]) {
+                                if (rb == root(xid)) OK(zero_x_td()); else CU(cudaMemsetAsync(b.td, 0, (size_t)(b.size * Kb) * t->es, S(t)));
+                            }
+                            int64_t strides[kMaxArgs][kMaxDims], sizes[kMaxArgs];
+                            bcast_strides(I, o, strides, sizes);
+                            KL(t, launch_tangent_reverse_g<T>(S(t), (T *)b.td, dt, delta, (const T *)I.partial[p], N, p, sec, tvs, strides, sizes, o.dims, o.size, Kb));
+                        }
                         td_zero[rb] = 0;
-                        if (want_der(I.in[p].rec.buffer)) KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[p], o.size, 1, false));
+                        if (want_der(I.in[p].rec.buffer)) {
+                            if (I.in[p].size == o.size) KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[p], o.size, 1, false));
+                            else {                         // clamped argument: deriv[g_p(e)] += delta[e] * partial[e]  (propagation.jl:117-188)
+                                int64_t strides[kMaxArgs][kMaxDims], sizes[kMaxArgs];
+                                bcast_strides(I, o, strides, sizes);
+                                KL(t, launch_mul_acc_generic<T>(S(t), (T *)b.der, b.size, strides[p], delta, (const T *)I.partial[p], o.dims, o.size, 1));
+                            }
+                        }
                     }
                 }
             }

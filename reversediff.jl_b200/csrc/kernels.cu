@@ -703,6 +703,90 @@ cudaError_t launch_tangent_reverse(cudaStream_t s, T *td_p, const T *dt, const T
     return cudaGetLastError();
 }
 
+// The same two sweeps for closures whose arguments BROADCAST against the output (propagation.jl:25-27 clamps: an argument
+// dimension of length 1 keeps index 0): argument q's element for output element e is g_q(e) = sum_d idx_d(e) * stride[q][d]
+// (stride 0 along clamped dimensions), its tangents live at g_q(e) + k * size[q].  Into a clamped argument many output elements
+// add: atomics (only this generality path uses them; same-shape closures keep the kernels above).
+template <typename T>
+struct TanArgsG {
+    const T *partial[kMaxArgs];
+    const T *tv[kMaxArgs];
+    const T *second[kMaxArgs];
+    int64_t stride[kMaxArgs][kMaxDims];
+    int64_t size[kMaxArgs];
+    int64_t dims[kMaxDims];
+    int n_args;
+};
+template <typename T>
+__device__ __forceinline__ int64_t g_index(const TanArgsG<T> &a, int q, int64_t e) {
+    int64_t off = 0, rem = e;
+#pragma unroll
+    for (int d = 0; d < kMaxDims; ++d) { off += (rem % a.dims[d]) * a.stride[q][d]; rem /= a.dims[d]; }
+    return off;
+}
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_tangent_forward_g(T *__restrict__ out, TanArgsG<T> a, int64_t n, int64_t K) {
+    int64_t tot = n * K;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) {
+        const int64_t e = i % n, k = i / n;
+        T acc = (T)0;
+        for (int p = 0; p < a.n_args; ++p)
+            if (a.tv[p]) acc += a.partial[p][e] * a.tv[p][g_index(a, p, e) + k * a.size[p]];
+        out[i] = acc;
+    }
+}
+template <typename T>
+cudaError_t launch_tangent_forward_g(cudaStream_t s, T *tv_out, int n_args, const T *const *partial, const T *const *tv_in,
+                                     const int64_t (*stride)[kMaxDims], const int64_t *sizes, const int64_t *dims, int64_t n, int64_t K) {
+    if (n * K <= 0) return cudaSuccess;
+    TanArgsG<T> a{};
+    a.n_args = n_args;
+    for (int d = 0; d < kMaxDims; ++d) a.dims[d] = dims[d];
+    for (int p = 0; p < n_args; ++p) {
+        a.partial[p] = partial[p]; a.tv[p] = tv_in[p]; a.second[p] = nullptr; a.size[p] = sizes[p];
+        for (int d = 0; d < kMaxDims; ++d) a.stride[p][d] = stride[p][d];
+    }
+    k_tangent_forward_g<T><<<grid_for(n * K, 2), kThreads, 0, s>>>(tv_out, a, n, K);
+    return cudaGetLastError();
+}
+// td_p[g_p(e), k] += delta[e] * sum_q second_pq[e] * tv_q[g_q(e), k] + dt[e, k] * partial_p[e]; `p_direct`: argument p has the
+// output's shape (one writer per element, plain read-modify-write), otherwise atomicAdd.  The destination must hold zeros or the
+// running sum already (the caller clears it when this is the first accumulation).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_tangent_reverse_g(T *__restrict__ td, const T *__restrict__ dt, const T *__restrict__ delta, const T *__restrict__ partial_p,
+                    TanArgsG<T> a, int p, int p_direct, int64_t n, int64_t K) {
+    int64_t tot = n * K;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) {
+        const int64_t e = i % n, k = i / n;
+        T acc = (T)0;
+        for (int q = 0; q < a.n_args; ++q)
+            if (a.tv[q]) acc += a.second[q][e] * a.tv[q][g_index(a, q, e) + k * a.size[q]];
+        T v = delta[e] * acc;
+        if (dt) v += dt[i] * partial_p[e];
+        const int64_t dst = g_index(a, p, e) + k * a.size[p];
+        if (p_direct) td[dst] += v;
+        else atomicAdd(td + dst, v);
+    }
+}
+template <typename T>
+cudaError_t launch_tangent_reverse_g(cudaStream_t s, T *td_p, const T *dt, const T *delta, const T *partial_p, int n_args, int p,
+                                     const T *const *second_pq, const T *const *tv_in, const int64_t (*stride)[kMaxDims],
+                                     const int64_t *sizes, const int64_t *dims, int64_t n, int64_t K) {
+    if (n * K <= 0) return cudaSuccess;
+    TanArgsG<T> a{};
+    a.n_args = n_args;
+    for (int d = 0; d < kMaxDims; ++d) a.dims[d] = dims[d];
+    for (int q = 0; q < n_args; ++q) {
+        a.partial[q] = nullptr; a.tv[q] = tv_in[q]; a.second[q] = second_pq[q]; a.size[q] = sizes[q];
+        for (int d = 0; d < kMaxDims; ++d) a.stride[q][d] = stride[q][d];
+    }
+    k_tangent_reverse_g<T><<<grid_for(n * K, 2), kThreads, 0, s>>>(td_p, dt, delta, partial_p, a, p, sizes[p] == n ? 1 : 0, n, K);
+    return cudaGetLastError();
+}
+
 // Sparse second-order term for an elementwise instruction whose arguments are all `getindex` views of the seeded input: the value
 // tangent of argument q is the one-hot selector (map_q[i] == c0 + k), so
 //   td_x[map_p[i] + k*n_x] += delta[i] * second_pq[i]   only at k = map_q[i] - c0.
@@ -918,6 +1002,8 @@ cudaError_t launch_copy2d(cudaStream_t s, T *dst, int64_t ldd, const T *src, int
     template cudaError_t launch_rows_out<T>(cudaStream_t, T *, int64_t, const T *, int64_t, int64_t);                     \
     template cudaError_t launch_tangent_forward<T>(cudaStream_t, T *, int, const T *const *, const T *const *, int64_t, int64_t); \
     template cudaError_t launch_tangent_reverse<T>(cudaStream_t, T *, const T *, const T *, const T *, int, const T *const *, const T *const *, int64_t, int64_t, bool); \
+    template cudaError_t launch_tangent_forward_g<T>(cudaStream_t, T *, int, const T *const *, const T *const *, const int64_t (*)[kMaxDims], const int64_t *, const int64_t *, int64_t, int64_t); \
+    template cudaError_t launch_tangent_reverse_g<T>(cudaStream_t, T *, const T *, const T *, const T *, int, int, const T *const *, const T *const *, const int64_t (*)[kMaxDims], const int64_t *, const int64_t *, int64_t, int64_t); \
     template cudaError_t launch_gather_cols<T>(cudaStream_t, T *, const T *, int64_t, const int64_t *, int64_t, int64_t); \
     template cudaError_t launch_tangent_reverse_sparse<T>(cudaStream_t, T *, int64_t, int64_t, int64_t, const T *, int, const int64_t *const *, const T *const *, int64_t); \
     template cudaError_t launch_hessian_separable<T>(cudaStream_t, const SepHessParams &);                               \

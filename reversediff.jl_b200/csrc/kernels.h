@@ -186,6 +186,9 @@ struct SepHessParams {
 };
 constexpr int kSepHessMaxEntries = 32;
 template <typename T> cudaError_t launch_hessian_separable(cudaStream_t, const SepHessParams &);
+// the same sweeps for closures whose arguments broadcast against the output (index maps from strides; atomics into clamped arguments)
+template <typename T> cudaError_t launch_tangent_forward_g(cudaStream_t, T *tv_out, int n_args, const T *const *partial, const T *const *tv_in, const int64_t (*stride)[kMaxDims], const int64_t *sizes, const int64_t *dims, int64_t n, int64_t K);
+template <typename T> cudaError_t launch_tangent_reverse_g(cudaStream_t, T *td_p, const T *dt, const T *delta, const T *partial_p, int n_args, int p, const T *const *second_pq, const T *const *tv_in, const int64_t (*stride)[kMaxDims], const int64_t *sizes, const int64_t *dims, int64_t n, int64_t K);
 template <typename T> cudaError_t launch_tangent_reverse_sparse(cudaStream_t, T *td_x, int64_t n_x, int64_t K, int64_t c0, const T *delta, int n_args, const int64_t *const *maps, const T *const *second_pq /* [p*n_args+q] */, int64_t n);
 // rows gather/scatter for getindex under tangents: out[k + c*n] = src[map[k] + c*src_n]
 template <typename T> cudaError_t launch_gather_cols(cudaStream_t, T *out, const T *src, int64_t src_n, const int64_t *map, int64_t n, int64_t K);

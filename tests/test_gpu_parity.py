@@ -814,3 +814,32 @@ def test_hessian_bilinear_mul_of_two_tracked_operands(rd, orc, block):
                         for d_ in range(m):
                             Hcf[a_ + b_ * m, c_ + d_ * m] = C[a_, d_] * (b_ == c_) + C[c_, b_] * (d_ == a_)
             assert relerr(Hn, Hcf) < 1e-13
+
+
+@pytest.mark.parametrize("block", [0, 3])
+def test_hessian_broadcasting_closures(rd, orc, block):
+    """hessian! through elementwise closures whose arguments broadcast against the output (column vector, row vector, an untracked
+    constant matrix): tangents gathered through the clamps, adjoint tangents reduced into the clamped arguments."""
+    rng = np.random.default_rng(8)
+    m, n = 4, 3
+    C = rng.random((m, n))
+
+    def f(x):
+        X = x[0:m * n].reshape(m, n)
+        b = x[m * n:m * n + m]                                   # length-m vector: broadcasts along columns
+        r = x[m * n + m:m * n + m + n].reshape(1, n)             # 1 x n row: broadcasts along rows
+        Y = rd.bcast(lambda u, v, w, c: rd.tanh(u * v + w) * c + v * v * w, X, b, r, C)
+        return rd.sum(rd.bcast(lambda y, v: y * y + rd.exp(v * 0.3), Y, b))
+
+    N = m * n + m + n
+    x0 = rng.random(N); x = rng.random(N) - 0.4
+    tape = rd.HessianTape(f, x0)
+    ct = rd.compile(tape, seed_block=block)
+    g = np.zeros(N); Hn = np.zeros((N, N), order="F")
+    res = rd.DiffResult(0.0, g, Hn)
+    rd.hessian_(res, ct, x)
+    val, (go,) = orc.OracleTape(tape.program_bytes()).gradient([x])
+    assert abs(res.value - val) < 1e-12 * abs(val) and relerr(g, go) < 1e-12
+    Hfd = orc.hessian_dense(tape.program_bytes(), x)
+    assert np.max(np.abs(Hn - Hfd)) < 1e-6 * max(1.0, np.max(np.abs(Hfd)))
+    assert np.max(np.abs(Hn - Hn.T)) < 1e-12 * np.max(np.abs(Hn))
