@@ -132,6 +132,7 @@ struct InstrPlan {
     std::vector<int32_t> h_ops;     // host copy of the scalar program (NVRTC specialisation)
     void *jit_fn[2] = {nullptr, nullptr};   // [reduce]
     bool jit_tried[2] = {false, false};
+    int partial_alias[kMaxArgs] = {-1, -1, -1, -1, -1, -1, -1, -1};   // >= 0: this argument's partial is provably the SAME value as that earlier argument's: stored once
     int run_end = -2;                    // elementwise run fusion: last instruction of the run that starts here (-2 = not planned, own index = none)
     void *run_fn[2] = {nullptr, nullptr};  // [reduce]: the run's NVRTC kernel
     bool run_tried[2] = {false, false};
@@ -346,7 +347,7 @@ static int expr_params(rdb_tape *t, InstrPlan &I, bool reduce, int order, ExprPa
             st *= od;
         }
         p.arg[a].same = same ? 1 : 0;
-        p.partial[a] = I.partial[a];
+        p.partial[a] = I.partial_alias[a] >= 0 ? nullptr : I.partial[a];     // an aliased partial is written once, by the argument it aliases
     }
     for (int h = 0; h < kMaxArgs * (kMaxArgs + 1) / 2; ++h) p.second[h] = I.second[h];
     p.out = out.val; p.ops = I.d_ops; p.fconst = t->d_fconst; p.block_sums = t->scratch;
@@ -358,6 +359,37 @@ static int expr_params(rdb_tape *t, InstrPlan &I, bool reduce, int order, ExprPa
 // every argument produced inside the run is a plain same-shape TrackedArray operand (it then travels in a register); arguments
 // from outside the run are loaded as usual (broadcast clamps included).  Needs the NVRTC path; without it the instructions launch
 // one by one.  Results are bit-identical either way (same arithmetic, same order).
+// Which arguments of a scalar program have IDENTICAL partials by construction?  The forward kernels evaluate one Dual{N}: register r
+// carries partials D[r][p].  This walks the same recursion symbolically, using only identities that are exact in floating point for
+// every input (x + 0 = x, 0 + x = x, f1 * 1 = f1); everything else stays an opaque term that names its register and its argument.
+// `tanh(x + y)` gives D[.][x] = D[.][y] = "f1_3": the reference stores partial_x and partial_y separately (broadcast.jl:155,182-191),
+// but they hold the same numbers, so one array serves both (25 % of the forward sweep's bytes at the MLP config).
+static void partial_signatures(const int32_t *ops, int64_t n_ops, int n_args, std::vector<std::string> &sig) {
+    std::vector<std::vector<std::string>> D((size_t)n_args + n_ops, std::vector<std::string>(n_args));
+    for (int a = 0; a < n_args; ++a) for (int p = 0; p < n_args; ++p) D[a][p] = a == p ? "1" : "0";
+    for (int64_t k = 0; k < n_ops; ++k) {
+        const int code = ops[4 * k], a = ops[4 * k + 1], b = ops[4 * k + 2], imm = ops[4 * k + 3];
+        const size_t r = (size_t)n_args + k;
+        for (int p = 0; p < n_args; ++p) {
+            std::string &d = D[r][p];
+            const std::string tag = std::to_string(r) + "_" + std::to_string(p);
+            switch (code) {
+                case E_CONST: d = "0"; break;
+                case E_ARG: d = D[imm][p]; break;
+                case E_ADD: d = D[a][p] == "0" ? D[b][p] : (D[b][p] == "0" ? D[a][p] : "(" + D[a][p] + "+" + D[b][p] + ")"); break;
+                case E_SUB: d = D[b][p] == "0" ? D[a][p] : "(" + D[a][p] + "-" + D[b][p] + ")"; break;
+                case E_NEG: case E_POWI: case E_TANH: case E_EXP: case E_LOG: case E_SQRT: case E_SIN: case E_COS: case E_ABS2: case E_ABS:
+                case E_INV: case E_SIGMOID: case E_LOG1P: case E_EXPM1: case E_ASIN: case E_ACOS: case E_ATAN: case E_SINH: case E_COSH: case E_TAN:
+                    // f1(v_a) * D[a][p]: the factor depends on the register only
+                    d = D[a][p] == "1" ? "f1_" + std::to_string(r) : "(f1_" + std::to_string(r) + "*" + D[a][p] + ")";
+                    break;
+                default: d = "op" + tag; break;               // products, quotients, powers, max/min, two-argument functions: opaque
+            }
+        }
+    }
+    sig = D.back();
+}
+
 static int plan_run(rdb_tape *t, size_t head) {
     InstrPlan &H = t->instrs[head];
     if (H.run_end != -2) return H.run_end;
@@ -407,7 +439,7 @@ static int expr_forward_run(rdb_tape *t, size_t head, size_t last, bool reduce) 
             items[k].from_item[a] = -1;
             for (int j = 0; j < k; ++j) if (root(t->instrs[head + j].rec.out) == root(I.in[a].rec.buffer)) items[k].from_item[a] = j;
             if (items[k].from_item[a] < 0) bytes += (double)t->bufs[I.in[a].rec.buffer].size * t->es;
-            if (I.partial[a]) bytes += (double)t->bufs[I.rec.out].size * t->es;
+            if (I.partial[a] && I.partial_alias[a] < 0) bytes += (double)t->bufs[I.rec.out].size * t->es;
         }
     }
     if (!H.run_tried[ri]) {
@@ -426,7 +458,7 @@ static int expr_forward(rdb_tape *t, InstrPlan &I, bool reduce, int order) {
     ExprParams p{};
     OK(expr_params<T>(t, I, reduce, order, p));
     int np = 0;
-    for (int a = 0; a < I.rec.n_in; ++a) np += I.partial[a] ? 1 : 0;
+    for (int a = 0; a < I.rec.n_in; ++a) np += (I.partial[a] && I.partial_alias[a] < 0) ? 1 : 0;
     StepTimer tm(t, order == 2 ? "expr_forward2" : (reduce ? "expr_forward+sum" : "expr_forward"),
                  (double)out.size * t->es * (1 + np + 1), 0);
     if (order == 1 && out.size > 0) {
@@ -1027,9 +1059,67 @@ static int mul_reverse(rdb_tape *t, int k, int64_t R) {
 }
 
 template <typename T>
-static int expr_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
+static int expr_reverse(rdb_tape *t, InstrPlan &I, int64_t R, const T *sdelta = nullptr, T sscale = (T)1, bool probe = false) {
+    // sdelta != nullptr: deriv(output)[e + r n] = sscale * sdelta[r] for every e - the `sum`/`mean` that consumes this instruction's
+    // output would have written exactly that (reverse {sum, elementwise} in one step); only the patterns below take it.
+    // probe: only report (1 / 0) whether the scalar-delta form is available for this instruction.
     Buf &out = t->bufs[I.rec.out];
     const T *delta = (const T *)out.der;
+    if (sdelta || probe) {
+        bool ok = t->opts.fuse_elementwise != 0;
+        int n_same = 0, n_col = 0, n_tracked = 0;
+        for (int a = 0; a < I.rec.n_in && ok; ++a) {
+            OperandPlan &o = I.in[a];
+            if (!o.rec.tracked) continue;
+            ++n_tracked;
+            if (o.mode != OPM_PLAIN) { ok = false; break; }
+            const int64_t d0 = o.rec.ndims >= 1 ? o.rec.dims[0] : 1;
+            bool same = true;
+            for (int d = 0; d < kMaxDims; ++d) same &= (d < o.rec.ndims ? o.rec.dims[d] : 1) == out.dims[d];
+            if (same) ++n_same;
+            else if (o.size == d0 && d0 == out.dims[0] && d0 > 1 && out.nd >= 2) ++n_col;
+            else ok = false;
+        }
+        // every tracked argument of the output's shape, or the {same shape, column vector} pair of two different buffers
+        ok = ok && n_tracked > 0 && (n_col == 0 || (n_col == 1 && n_same == 1 && n_tracked == 2));
+        if (ok && n_col == 1) {
+            int ia = -1, ib = -1;
+            for (int a = 0; a < I.rec.n_in; ++a) if (I.in[a].rec.tracked) { if (I.in[a].size == out.size) ia = a; else ib = a; }
+            ok = droot(t, I.in[ia].rec.buffer) != droot(t, I.in[ib].rec.buffer);
+        }
+        if (probe) return ok ? 1 : 0;
+        if (!ok) return fail(RDB_EINVAL, "internal: scalar-delta elementwise reverse on an unsupported pattern");
+    }
+    // {broadcast adjoint, bias column-reduce} in one pass: exactly one tracked argument of the output's shape and one tracked column
+    // vector clamped along the columns (`tanh.(W*X .+ b)`): delta is read once for both accumulations (5 S E -> 4 S E).  Two different
+    // buffers, so the order of accumulation into each of them is the reference's.
+    if (t->opts.fuse_elementwise && out.nd >= 2) {
+        int ia = -1, ib = -1, n_tracked = 0;
+        for (int a = 0; a < I.rec.n_in; ++a) {
+            OperandPlan &o = I.in[a];
+            if (!o.rec.tracked) continue;
+            ++n_tracked;
+            if (o.mode != OPM_PLAIN) { ia = ib = -2; break; }
+            const int64_t d0 = o.rec.ndims >= 1 ? o.rec.dims[0] : 1;
+            bool same = true;
+            for (int d = 0; d < kMaxDims; ++d) same &= (d < o.rec.ndims ? o.rec.dims[d] : 1) == out.dims[d];
+            if (same && ia == -1) ia = a;
+            else if (!same && o.size == d0 && d0 == out.dims[0] && d0 > 1 && ib == -1) ib = a;
+            else { ia = ib = -2; break; }
+        }
+        if (ia >= 0 && ib >= 0 && n_tracked == 2 && droot(t, I.in[ia].rec.buffer) != droot(t, I.in[ib].rec.buffer)) {
+            Buf &bs = t->bufs[I.in[ia].rec.buffer], &bc = t->bufs[I.in[ib].rec.buffer];
+            const int64_t d0 = out.dims[0];
+            const bool ow_same = dtake(t, I.in[ia].rec.buffer), ow_col = dtake(t, I.in[ib].rec.buffer);
+            StepTimer tm(t, sdelta ? "sum+expr_reverse+colreduce" : "expr_reverse+colreduce", ((ow_same ? 3.0 : 4.0) * R + (sdelta ? 0.0 : 1.0)) * out.size * t->es, 0);
+            KL(t, launch_mul_acc_colvec_fused<T>(S(t), (T *)bc.der, sdelta ? sdelta : delta, (const T *)I.partial[ib], d0, out.size / d0, R, (T *)t->scratch,
+                                                 t->scratch_bytes / 8, ow_col, (T *)bs.der, (const T *)I.partial[ia], ow_same, sdelta != nullptr, sscale));
+            t->launches++;
+            OK(acc_done(t, I.in[ia].rec.buffer));
+            OK(acc_done(t, I.in[ib].rec.buffer));
+            return RDB_OK;
+        }
+    }
     for (int a = 0; a < I.rec.n_in; ++a) {
         OperandPlan &o = I.in[a];
         if (!o.rec.tracked) continue;
@@ -1042,8 +1132,9 @@ static int expr_reverse(rdb_tape *t, InstrPlan &I, int64_t R) {
         }
         if (same) {
             const bool ow = dtake(t, o.rec.buffer);
-            StepTimer tm(t, "expr_reverse", ((ow ? 2.0 : 3.0) * R + 1.0) * out.size * t->es, 0);
-            KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[a], out.size, R, ow));
+            StepTimer tm(t, sdelta ? "sum+expr_reverse" : "expr_reverse", ((ow ? 2.0 : 3.0) * R + (sdelta ? 0.0 : 1.0)) * out.size * t->es, 0);
+            if (sdelta) KL(t, launch_mul_acc_sdelta<T>(S(t), (T *)b.der, sdelta, sscale, (const T *)I.partial[a], out.size, R, ow));
+            else KL(t, launch_mul_acc<T>(S(t), (T *)b.der, delta, (const T *)I.partial[a], out.size, R, ow));
         } else if (o.size == 1) {
             // scalar (TrackedReal) argument: input_deriv += sum_i x[i]*partial[i]   (propagation.jl:98-108; unbroadcast(::Number) = sum)
             StepTimer tm(t, "expr_reverse_scalar", 2.0 * out.size * R * t->es, 0);
@@ -1160,6 +1251,16 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                                 KL(t, launch_acc_scalar<T>(S(t), (T *)ba.der, ba.size, R, delta, sg, ow));
                                 OK(acc_done(t, A.in[a].rec.buffer));
                             }
+                            break;
+                        }
+                    }
+                    // reverse {sum, elementwise} in one step, same idea: the producer of the summed buffer is the elementwise instruction
+                    // right before, nothing else has accumulated into its output's deriv: its reverse exec takes the scalar adjoint
+                    // (scale * delta[r], the very value the fill would have stored) and deriv(output) stays logically zero
+                    if (t->opts.fuse_elementwise && k > 0 && t->dz[droot(t, I.in[0].rec.buffer)] && I.in[0].rec.cls == CLS_TA && I.in[0].mode == OPM_PLAIN) {
+                        InstrPlan &A = t->instrs[k - 1];
+                        if (!A.blk && is_elementwise(A.rec.opcode) && A.rec.out == I.in[0].rec.buffer && expr_reverse<T>(t, A, R, nullptr, (T)1, true) == 1) {
+                            OK(expr_reverse<T>(t, A, R, delta, scale, false));
                             break;
                         }
                     }
@@ -1470,8 +1571,17 @@ static int load_program(rdb_tape *t, const uint8_t *raw, size_t nbytes) {
                     int64_t od = d < I.in[a].rec.ndims ? I.in[a].rec.dims[d] : 1;
                     if (od != out.dims[d] && od != 1) return fail(RDB_EINVAL, "instruction %u: operand does not broadcast to the output", i);
                 }
+            }
+            static const bool dedup = [] { const char *e = getenv("RDB_PARTIAL_DEDUP"); return !(e && e[0] == '0'); }();
+            std::vector<std::string> sig;
+            if (dedup && t->opts.fuse_elementwise) partial_signatures(ops, I.rec.expr_len, I.rec.n_in, sig);
+            for (int a = 0; a < I.rec.n_in; ++a) {
                 // results[I].partial[p] (broadcast.jl:155; elementwise.jl:239): only tracked arguments are ever read back
-                if (I.in[a].rec.tracked) OK(dev_alloc(t, &I.partial[a], out.size * (int64_t)t->es));
+                if (!I.in[a].rec.tracked) continue;
+                for (int p = 0; p < a && !sig.empty() && I.partial_alias[a] < 0; ++p)
+                    if (I.in[p].rec.tracked && I.partial_alias[p] < 0 && sig[p] == sig[a] && sig[a] != "0" && sig[a].compare(0, 2, "op") != 0) I.partial_alias[a] = p;
+                if (I.partial_alias[a] >= 0) I.partial[a] = I.partial[I.partial_alias[a]];
+                else OK(dev_alloc(t, &I.partial[a], out.size * (int64_t)t->es));
             }
         } else if (is_getindex(op)) {
             if (I.in[0].mode != OPM_GATHER) return fail(RDB_EINVAL, "instruction %u: getindex without a map", i);

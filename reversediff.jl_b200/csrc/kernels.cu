@@ -418,6 +418,28 @@ k_mul_acc(T *__restrict__ dst, const T *__restrict__ delta, const T *__restrict_
         }
     }
 }
+// the same with delta[e + r n] = scale * dscalar[r] for every e: what `sum`/`mean` reverse would have written into deriv(output)
+// first (reductions.jl:15-21) - the fill and its re-read are skipped, the product is formed from the same two factors
+template <typename T, bool OVERWRITE>
+__global__ void __launch_bounds__(kThreads)
+k_mul_acc_sdelta(T *__restrict__ dst, const T *__restrict__ dscalar, T scale, const T *__restrict__ partial, int64_t n, int64_t R) {
+    int64_t tot = n * R;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < tot; i += st) {
+        const int64_t r = i / n, e = i - r * n;
+        const T d = scale * dscalar[r];
+        T v = d * partial[e];
+        dst[i] = OVERWRITE ? v : dst[i] + v;
+    }
+}
+template <typename T>
+cudaError_t launch_mul_acc_sdelta(cudaStream_t s, T *dst, const T *dscalar, T scale, const T *partial, int64_t n, int64_t R, bool overwrite) {
+    if (n * R <= 0) return cudaSuccess;
+    int grid = grid_for(n * R, 4);
+    if (overwrite) k_mul_acc_sdelta<T, true><<<grid, kThreads, 0, s>>>(dst, dscalar, scale, partial, n, R);
+    else k_mul_acc_sdelta<T, false><<<grid, kThreads, 0, s>>>(dst, dscalar, scale, partial, n, R);
+    return cudaGetLastError();
+}
 template <typename T>
 cudaError_t launch_mul_acc(cudaStream_t s, T *dst, const T *delta, const T *partial, int64_t n, int64_t R, bool overwrite) {
     if (n * R <= 0) return cudaSuccess;
@@ -442,6 +464,30 @@ k_colvec_partial(double *__restrict__ scratch, const T *__restrict__ delta, cons
 #pragma unroll 4
     if (partial) { for (int64_t j = j0; j < j1; ++j) acc += (double)(dl[i + j * d0] * partial[i + j * d0]); }
     else { for (int64_t j = j0; j < j1; ++j) acc += (double)dl[i + j * d0]; }
+    scratch[(c * R + r) * d0 + i] = acc;
+}
+// pass 1 fused with the same-shape argument's accumulation of the SAME instruction: delta is read once for both
+// (dx[e] (+)= delta[e] * px[e] exactly as k_mul_acc does it; the column sums exactly as k_colvec_partial)
+template <typename T, bool OVERWRITE, bool SDELTA>
+__global__ void __launch_bounds__(kThreads)
+k_colvec_partial_fused(double *__restrict__ scratch, const T *__restrict__ delta, const T *__restrict__ partial_col,
+                       T *__restrict__ dx, const T *__restrict__ partial_same, int64_t d0, int64_t d1, int64_t R, int64_t cols_per_chunk, T scale) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t c = blockIdx.y, r = blockIdx.z;
+    if (i >= d0) return;
+    int64_t j0 = c * cols_per_chunk, j1 = j0 + cols_per_chunk;
+    if (j1 > d1) j1 = d1;
+    const T *dl = SDELTA ? delta : delta + r * d0 * d1;       // SDELTA: delta holds R scalars (the adjoint of a `sum`/`mean` output)
+    const T ds = SDELTA ? scale * delta[r] : (T)0;
+    T *dxr = dx + r * d0 * d1;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int64_t j = j0; j < j1; ++j) {
+        const T d = SDELTA ? ds : dl[i + j * d0];
+        const T v = d * partial_same[i + j * d0];
+        dxr[i + j * d0] = OVERWRITE ? v : dxr[i + j * d0] + v;
+        acc += (double)(d * partial_col[i + j * d0]);
+    }
     scratch[(c * R + r) * d0 + i] = acc;
 }
 template <typename T>
@@ -475,6 +521,37 @@ cudaError_t launch_mul_acc_colvec(cudaStream_t s, T *dst, const T *delta, const 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     k_colvec_finish<T><<<(unsigned)((d0 * R + kThreads - 1) / kThreads), kThreads, 0, s>>>(dst, scratch, d0, R, chunks, overwrite ? 1 : 0);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_mul_acc_colvec_fused(cudaStream_t s, T *dst_col, const T *delta, const T *partial_col, int64_t d0, int64_t d1, int64_t R,
+                                        T *scratch_, int64_t scratch_elems, bool overwrite_col, T *dst_same, const T *partial_same,
+                                        bool overwrite_same, bool sdelta, T scale) {
+    if (d0 * d1 * R <= 0) return cudaSuccess;
+    double *scratch = reinterpret_cast<double *>(scratch_);
+    int64_t bx = (d0 + kThreads - 1) / kThreads;
+    int64_t want = (kSMs * 8 + bx * R - 1) / (bx * R);
+    if (want < 1) want = 1;
+    if (want > d1) want = d1;
+    int64_t maxc = scratch_elems / (d0 * R);
+    if (maxc < 1) return cudaErrorMemoryAllocation;
+    if (want > maxc) want = maxc;
+    if (want > 65535) want = 65535;
+    int64_t cols = (d1 + want - 1) / want;
+    int64_t chunks = (d1 + cols - 1) / cols;
+    if (R > 65535) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)bx, (unsigned)chunks, (unsigned)R);
+    if (sdelta) {
+        if (overwrite_same) k_colvec_partial_fused<T, true, true><<<grid, kThreads, 0, s>>>(scratch, delta, partial_col, dst_same, partial_same, d0, d1, R, cols, scale);
+        else k_colvec_partial_fused<T, false, true><<<grid, kThreads, 0, s>>>(scratch, delta, partial_col, dst_same, partial_same, d0, d1, R, cols, scale);
+    } else {
+        if (overwrite_same) k_colvec_partial_fused<T, true, false><<<grid, kThreads, 0, s>>>(scratch, delta, partial_col, dst_same, partial_same, d0, d1, R, cols, scale);
+        else k_colvec_partial_fused<T, false, false><<<grid, kThreads, 0, s>>>(scratch, delta, partial_col, dst_same, partial_same, d0, d1, R, cols, scale);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_colvec_finish<T><<<(unsigned)((d0 * R + kThreads - 1) / kThreads), kThreads, 0, s>>>(dst_col, scratch, d0, R, chunks, overwrite_col ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -995,6 +1072,8 @@ cudaError_t launch_copy2d(cudaStream_t s, T *dst, int64_t ldd, const T *src, int
     template cudaError_t launch_expr_forward<T>(cudaStream_t, const ExprParams &);                                        \
     template cudaError_t launch_mul_acc<T>(cudaStream_t, T *, const T *, const T *, int64_t, int64_t, bool);              \
     template cudaError_t launch_mul_acc_colvec<T>(cudaStream_t, T *, const T *, const T *, int64_t, int64_t, int64_t, T *, int64_t, bool); \
+    template cudaError_t launch_mul_acc_colvec_fused<T>(cudaStream_t, T *, const T *, const T *, int64_t, int64_t, int64_t, T *, int64_t, bool, T *, const T *, bool, bool, T); \
+    template cudaError_t launch_mul_acc_sdelta<T>(cudaStream_t, T *, const T *, T, const T *, int64_t, int64_t, bool); \
     template cudaError_t launch_mul_acc_generic<T>(cudaStream_t, T *, int64_t, const int64_t *, const T *, const T *, const int64_t *, int64_t, int64_t); \
     template cudaError_t launch_gather<T>(cudaStream_t, T *, const T *, const int64_t *, int64_t);                        \
     template cudaError_t launch_scatter_add<T>(cudaStream_t, T *, int64_t, const int64_t *, const T *, int64_t, int64_t); \

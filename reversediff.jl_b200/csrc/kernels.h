@@ -152,6 +152,10 @@ template <typename T> cudaError_t launch_mul_acc(cudaStream_t, T *dst, const T *
 // (propagation.jl:90-96 with bound (d0,1)); scratch holds d0*R*chunks partial sums
 template <typename T> cudaError_t launch_mul_acc_colvec(cudaStream_t, T *dst, const T *delta, const T *partial, int64_t d0, int64_t d1, int64_t R, T *scratch, int64_t scratch_elems, bool overwrite = false);
 // generic clamped accumulate (any broadcast pattern) with atomics
+// launch_mul_acc of the same-shape argument and launch_mul_acc_colvec of the column-vector argument of ONE instruction in one pass over delta
+template <typename T> cudaError_t launch_mul_acc_colvec_fused(cudaStream_t, T *dst_col, const T *delta, const T *partial_col, int64_t d0, int64_t d1, int64_t R, T *scratch, int64_t scratch_elems, bool overwrite_col, T *dst_same, const T *partial_same, bool overwrite_same, bool sdelta = false, T scale = (T)1);
+// launch_mul_acc with delta = scale * dscalar[r] for every element (the adjoint a `sum`/`mean` would have filled in)
+template <typename T> cudaError_t launch_mul_acc_sdelta(cudaStream_t, T *dst, const T *dscalar, T scale, const T *partial, int64_t n, int64_t R, bool overwrite);
 template <typename T> cudaError_t launch_mul_acc_generic(cudaStream_t, T *dst, int64_t dst_n, const int64_t *dst_stride, const T *delta, const T *partial, const int64_t *dims, int64_t n, int64_t R);
 // out[k] = src[map[k]]      (pull_value! of IDX operands, getindex forward: tracked.jl:178-181,331-340)
 template <typename T> cudaError_t launch_gather(cudaStream_t, T *out, const T *src, const int64_t *map, int64_t n);

@@ -656,6 +656,19 @@ def test_elementwise_run_fusion_is_bit_identical(rd, orc, dtype):
         q = T.broadcast("-", a, b)                                 # an independent instruction of the same shape joins as well
         return T.sum(z + q)                                        # array + then sum: forward {+, sum} and reverse {sum, +}
 
+    def f2(a, b, bias):
+        # `sum` right behind an elementwise instruction with a same-shape and a column-vector argument: forward {elementwise, sum},
+        # reverse {sum, elementwise adjoint, bias column-reduce} in one pass each
+        h = T.bcast(lambda u, w: E.tanh(u + w), a, bias)
+        return T.sum(T.bcast(lambda u, v, w: u * v + E.exp(w * 0.25), h, b, bias))
+
+    for fn in (f, f2):
+        _check_fused_against_unfused(rd, orc, fn, (A0, B0, c0), (A, B, c), dtype)
+
+
+def _check_fused_against_unfused(rd, orc, f, rec, ins, dtype):
+    A0, B0, c0 = rec
+    A, B, c = ins
     tape = rd.GradientTape(f, (A0, B0, c0), dtype=dtype)
     ot = orc.OracleTape(tape.program_bytes())
     val, grads = ot.gradient([A, B, c])
