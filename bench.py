@@ -7,13 +7,19 @@ Metric (BASELINE.json): compiled-tape ``gradient!`` evals/s of ``f(a,b) = sum(a'
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 4096] [--dtype f64|f32]
 
 * ``value``     device-resident inputs/results (D2D copies only), CUDA events, max over ranks.
-* ``e2e``       same call with pinned HOST inputs and HOST results: H2D + replay + D2H inside the timed region.
-* ``roofline``  dominant kernel (the DMMA GEMM): 12 n^3 flop per eval / summed CUDA-event time of the six GEMM
-                launches, against a cuBLAS DGEMM measured in the same run (MEASURED_PEAKS.json has no FP64 entry).
+* ``e2e``       page-locked HOST inputs and HOST results, every step uploads its inputs and downloads its results; consecutive steps
+                pipelined over two engine copies of the tape (rd.GradientPipeline = rdb_gradient_async + rdb_tape_wait); the
+                one-synchronous-call-per-step number rides along (``e2e.synchronous_calls``), and ``e2e.host_link`` is the measured
+                host<->device copy bandwidth with every rank copying (the platform ceiling of this leg).
+* ``roofline``  dominant kernel (the tcgen05 int8-slice GEMM behind every FP64 ``*``): tensor-pipe operations issued per launch
+                (28 int8 products of 2 n^3) / CUDA-event time of the launches including their slicing passes, against
+                2 x the driver-measured bf16 burst (MEASURED_PEAKS.json); FP64-equivalent TFLOP/s next to a cuBLAS DGEMM measured in
+                the same run; ``traffic`` from the committed ncu capture named in profiles/traffic.json.
 * ``cpu_baseline`` the oracle (reference-equivalent CPU replay, numpy/OpenBLAS) on the box's host cores.
-* N > 1: gradient! of one scalar function does not shard ("replicas only", SURVEY.md §8e): every rank replays its
-  own tape copy, value = N evals / max-over-ranks time.  The same run then measures the paths that DO shard —
-  jacobian! by output-seed rows and hessian! by column chunks — and reports them under "jacobian"/"hessian".
+* N > 1: gradient! of one scalar function does not shard ("replicas only", SURVEY.md section 8e): every rank replays its
+  own tape copy, value = N evals / max-over-ranks time.  The same run then measures the paths that DO shard -
+  jacobian! by output-seed rows and hessian! by column chunks (results left sharded; the product's NCCL gather timed apart) -
+  and reports them under "jacobian"/"hessian"; N = 1 also runs cfg 1, cfg 2 in FP32 and cfg 3 ("other_configs").
 * ``--impl reference``: the reference-equivalent CPU replay alone (rank 0 only), same metric/config.
 """
 from __future__ import annotations
