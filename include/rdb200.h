@@ -140,6 +140,11 @@ int rdb_tape_set_async(rdb_tape *, int on);
  * launches flagged, and how many API calls were therefore replayed with the DMMA kernels before returning (gemm_f64_mode 0;
  * mul!, src/derivatives/linalg/arithmetic.jl:245-285, is DGEMM in the reference).  Any pointer may be NULL. */
 int rdb_tape_guard_stats(rdb_tape *, int64_t *checked, int64_t *flagged, int64_t *fallbacks, double *worst_ratio);
+/* int8 slice products the tcgen05 `*` kernels of this tape issued since load, summed over launches (folded in with the certificate
+ * after every call).  A dense FP64 operand pair costs S(S+1)/2 = 28 of them per launch; operands whose low digit planes are
+ * identically zero (constant fills such as the adjoint of `sum`, one-hot seeds, Float32 data held in Float64) cost fewer - the
+ * kernels skip those planes, with bit-identical results.  launches checked (rdb_tape_guard_stats) is the number of launches. */
+int64_t rdb_tape_slice_pairs(rdb_tape *);
 /* Number of kernel launches issued by the engine on this tape since load (bench "gpu_launches"). */
 int64_t rdb_tape_launch_count(rdb_tape *);
 

@@ -175,7 +175,7 @@ struct rdb_tape {
     struct HessGraph { cudaGraphExec_t exec = nullptr; int state = 0; int64_t cb = 0, ce = 0, ld = 0; void *result = nullptr; } hgraph;
     bool capturing = false;        // hessian_impl is being captured: no synchronisation, no host copies
     // accuracy certificate of the int8-slice `*` kernels (umma.cu guard): totals since load, and the fallback state
-    int64_t guard_checked = 0, guard_flagged = 0, guard_fallbacks = 0;
+    int64_t guard_checked = 0, guard_flagged = 0, guard_fallbacks = 0, slice_pairs = 0;
     double guard_worst = 0;
     // rdb_gradient_async: the call is only enqueued; rdb_tape_wait completes it (and runs the deferred accuracy check of the int8-slice GEMMs)
     struct Pending { bool active = false; std::vector<void *> results; int on_device = 0; void *value_out = nullptr; bool guard = false; } pending;
@@ -2440,6 +2440,7 @@ static int run_call(rdb_tape *t, F &&run) {
     GuardSummary gs;
     CU(guard_read(S(t), c->gemm, &gs));
     t->guard_checked += (int64_t)gs.checked;
+    t->slice_pairs += (int64_t)gs.pairs;
     t->guard_flagged += (int64_t)gs.flagged;
     if (gs.worst_ratio > t->guard_worst) t->guard_worst = gs.worst_ratio;
     if (gs.flagged == 0) { t->guard_streak = 0; return rc; }
@@ -2511,6 +2512,7 @@ int rdb_tape_set_async(rdb_tape *t, int on) {
     t->async = on != 0;
     return RDB_OK;
 }
+int64_t rdb_tape_slice_pairs(rdb_tape *t) { return t ? t->slice_pairs : -1; }
 int rdb_tape_guard_stats(rdb_tape *t, int64_t *checked, int64_t *flagged, int64_t *fallbacks, double *worst_ratio) {
     if (!t) return fail(RDB_EINVAL, "null tape");
     if (checked) *checked = t->guard_checked;
@@ -2637,6 +2639,7 @@ int rdb_tape_wait(rdb_tape *t) {
     GuardSummary gs;
     CU(guard_read(S(t), c->gemm, &gs));
     t->guard_checked += (int64_t)gs.checked;
+    t->slice_pairs += (int64_t)gs.pairs;
     t->guard_flagged += (int64_t)gs.flagged;
     if (gs.worst_ratio > t->guard_worst) t->guard_worst = gs.worst_ratio;
     if (gs.flagged == 0) { t->guard_streak = 0; return RDB_OK; }

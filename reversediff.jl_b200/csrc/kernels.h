@@ -51,7 +51,7 @@ struct SliceEntry {              // one operand of the int8 path, sliced: [slice
     uint64_t last_use;
 };
 constexpr int kGuardSlots = 2048;
-struct GuardSummary { unsigned long long checked, flagged; double worst_ratio; double pad; };
+struct GuardSummary { unsigned long long checked, flagged; double worst_ratio; unsigned long long pairs; };   // pairs: slice products issued (after plane trimming), summed over launches
 struct GemmState {
     void *ws = nullptr;          // grow-only workspace of the tcgen05 paths (slices of uncached operands, scales)
     size_t ws_bytes = 0;

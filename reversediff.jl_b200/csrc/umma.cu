@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(256) k_row_absmax(const double *__restrict__ s
 __global__ void __launch_bounds__(256) k_row_exponent(const unsigned long long *__restrict__ mx_bits, int rows, int bits, int *__restrict__ e_out,
                                                       double *__restrict__ scale_out) {
     int r = blockIdx.x * 256 + threadIdx.x;
+    if (r == 0) reinterpret_cast<unsigned long long *>(scale_out)[3 * (int64_t)rows] = 0ull;     // plane word (planes_note), filled by the slice pass
     if (r >= rows) return;
     double mx = __longlong_as_double((long long)mx_bits[r]);
     const bool finite = isfinite(mx);
@@ -474,6 +475,39 @@ __global__ void __launch_bounds__(256) k_row_exponent(const unsigned long long *
     // 1-norm in units of the scale (<= nnz / 4); 1 % covers the rounding of the running sums
     double *l1 = scale_out + rows;
     l1[r] = (finite && mx > 0.0) ? 1.01 * scalbn(l1[r], -e) : 0.0;
+}
+
+// ---- significant planes ("plane word").  Every slicing pass also ORs the fixed-point values X of the whole operand into one
+// 64-bit word stored behind the row statistics (index 3 * rows of the scale array).  If the low 8 z bits of that word are zero,
+// the z least significant digit planes of the operand are identically zero (a zero low byte of X is digit 0 with no carry), so
+// every slice pair that touches them contributes exactly nothing: the GEMM kernels read the word and neither load nor multiply
+// those planes - bit-identical results with fewer products.  Operands of few significant bits have such planes: constant fills
+// (the adjoint of `sum`: one plane), one-hot / integer-valued seeds, Float32 data held in Float64 (24 bits: four planes).
+__device__ __forceinline__ void planes_publish_warp(unsigned long long *word, unsigned long long orv) {
+    unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)orv), hi = __reduce_or_sync(0xffffffffu, (unsigned)(orv >> 32));
+    if ((threadIdx.x & 31) == 0) {
+        const unsigned long long v = ((unsigned long long)hi << 32) | lo;
+        if (v & ~*(volatile unsigned long long *)word) atomicOr(word, v);      // the plain read is only a filter (bits are only ever set)
+    }
+}
+__device__ __forceinline__ void planes_publish_block(unsigned long long *word, unsigned long long orv, unsigned long long *sh) {
+    unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)orv), hi = __reduce_or_sync(0xffffffffu, (unsigned)(orv >> 32));
+    if (threadIdx.x == 0) *sh = 0ull;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && (lo | hi)) atomicOr(sh, ((unsigned long long)hi << 32) | lo);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long v = *sh;
+        if (v & ~*(volatile unsigned long long *)word) atomicOr(word, v);
+    }
+}
+// planes of an operand that can hold a non-zero digit, from its plane word (1 for an all-zero operand)
+__device__ __forceinline__ int planes_of(const unsigned long long *word, int nslices, int bits) {
+    if (!word) return nslices;
+    const unsigned long long v = *word;
+    if (!v) return 1;
+    const int z = (__ffsll((long long)v) - 1) / bits;
+    return z >= nslices ? 1 : nslices - z;
 }
 
 // Balanced base-256 digits of four fixed-point values at once (bits == 8).  Adding 0x80 at every digit position below the
@@ -502,7 +536,8 @@ __device__ __forceinline__ void store_digits8(int8_t *__restrict__ dst_row_k, in
 // iteration, so every slice store is one packed 32-bit word and a warp writes 128 contiguous bytes of one row.
 template <bool KMAJOR>
 __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, const double *__restrict__ src, int64_t ld, int rows, int K,
-                                                  int Kp, int nslices, int bits, const int *__restrict__ e_in) {
+                                                  int Kp, int nslices, int bits, const int *__restrict__ e_in, unsigned long long *plane_word) {
+    __shared__ unsigned long long sh_or;
     // [k % 4][k / 4][r]: a thread later reads 4 consecutive k of one row, i.e. one element of each k%4 plane at row k/4 = lane -
     // 33-double rows make both the write (lanes along r) and that read (lanes along k/4) bank-conflict free
     __shared__ double tile[KMAJOR ? 1 : 4][KMAJOR ? 1 : 32][KMAJOR ? 1 : 33];
@@ -550,6 +585,14 @@ __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, cons
 #pragma unroll
         for (int j = 0; j < 4; ++j) X[i][j] = isfinite(v[j]) ? __double2ll_rn(scalbn(v[j], bits * nslices - e)) : 0LL;
     }
+    {
+        unsigned long long orv = 0ull;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) orv |= (unsigned long long)X[i][j];
+        planes_publish_block(plane_word, orv, &sh_or);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         if (!ok[i]) continue;
@@ -575,6 +618,7 @@ __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, cons
 // (k_row_absmax + k_row_exponent + k_slice_i8<true>).  blockDim = 32 x rows per CTA; dynamic shared memory = rows x Kp doubles.
 __global__ void __launch_bounds__(128) k_slice_fused_kmajor(int8_t *__restrict__ dst, const double *__restrict__ src, int64_t ld, int rows, int K,
                                                             int Kp, int nslices, int bits, double *__restrict__ scale_out) {
+    // (the plane word at scale_out[3 * rows] is zeroed by the launcher: planes_publish_warp only ever sets bits)
     extern __shared__ __align__(16) double srows[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const int r = blockIdx.x * wpc + w;
@@ -609,12 +653,13 @@ __global__ void __launch_bounds__(128) k_slice_fused_kmajor(int8_t *__restrict__
     }
     const int64_t plane = (int64_t)rows * Kp;
     const int radix = 1 << bits, half = radix >> 1;
+    unsigned long long orv = 0ull;
     for (int k = 4 * lane; k < Kp; k += 128) {
         const double2 lo = *reinterpret_cast<const double2 *>(row + k), hi = *reinterpret_cast<const double2 *>(row + k + 2);
         const double v[4] = {lo.x, lo.y, hi.x, hi.y};
         long long X[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) X[j] = isfinite(v[j]) ? __double2ll_rn(scalbn(v[j], bits * nslices - e)) : 0LL;
+        for (int j = 0; j < 4; ++j) { X[j] = isfinite(v[j]) ? __double2ll_rn(scalbn(v[j], bits * nslices - e)) : 0LL; orv |= (unsigned long long)X[j]; }
         if (bits == 8) { store_digits8(dst + (int64_t)r * Kp + k, plane, nslices, X); continue; }
         for (int sidx = nslices - 1; sidx >= 0; --sidx) {
             uint32_t packed = 0;
@@ -629,6 +674,7 @@ __global__ void __launch_bounds__(128) k_slice_fused_kmajor(int8_t *__restrict__
             *reinterpret_cast<uint32_t *>(dst + sidx * plane + (int64_t)r * Kp + k) = packed;
         }
     }
+    planes_publish_warp(reinterpret_cast<unsigned long long *>(scale_out) + 3 * (int64_t)rows, orv);
 }
 
 // Column-major source (rows strided by ld... i.e. consecutive ROWS are contiguous, k strided): tile of 128 rows x 32 k, so every
@@ -636,8 +682,9 @@ __global__ void __launch_bounds__(128) k_slice_fused_kmajor(int8_t *__restrict__
 // different DRAM page).  Transposed through shared memory ([k % 4][k / 4][row]); a thread then owns 4 rows x 4 consecutive k and
 // stores one packed 32-bit word per slice and row - a warp writes full 32-byte sectors of 4 rows.
 __global__ void __launch_bounds__(256) k_slice_i8_cm(int8_t *__restrict__ dst, const double *__restrict__ src, int64_t ld, int rows, int K,
-                                                     int Kp, int nslices, int bits, const int *__restrict__ e_in) {
+                                                     int Kp, int nslices, int bits, const int *__restrict__ e_in, unsigned long long *plane_word) {
     __shared__ double tile[4][8][132];
+    __shared__ unsigned long long sh_or;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int r0 = blockIdx.y * 128, k0 = blockIdx.x * 32;
     {
@@ -668,6 +715,14 @@ __global__ void __launch_bounds__(256) k_slice_i8_cm(int8_t *__restrict__ dst, c
             const double v = tile[j][kg][rl];
             X[i][j] = (ok[i] && isfinite(v)) ? __double2ll_rn(scalbn(v, bits * nslices - e)) : 0LL;
         }
+    }
+    {
+        unsigned long long orv = 0ull;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) orv |= (unsigned long long)X[i][j];
+        planes_publish_block(plane_word, orv, &sh_or);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -703,6 +758,10 @@ struct OzParams {
     const double *la, *na, *lb, *nb;   // per row of op(A) / column of op(B): 1-norm in units of the scale, number of non-zeros
     double g_rho, g_h, g_drop;         // guard_coeffs()
     int dbg;                           // timing experiments only (RDB_OZAKI_DBG): 1 = no TMA loads, 2 = no epilogue; results are garbage
+    // plane words of op(A) / op(B) (planes_publish_*; NULL = every plane is live) and the running count of slice pairs issued
+    const unsigned long long *pa, *pb;
+    unsigned long long *pairs;
+    int allow_swap;                    // both tilings (C and C^T) have the same number of 2-CTA clusters: the kernel may swap the roles
 };
 
 // |x - x~| <= 2^(e - bS - 1) per element (rint), |x| <= 2^e / 4 (b = 8) or 2^e / 2 (b = 7), and the slice pairs with p + q >= S
@@ -915,12 +974,21 @@ constexpr int OZ_THREADS = 64 + 128 * EPI_CB;
 //    conversions and FP64 adds per element instead of S of each, and fewer roundings (smallest group first);
 //  * the guard's two maxima ride along: max |term| through the high word of the double (integer max; an underestimate by at most
 //    2^-20, i.e. on the safe side), the error bound once per thread from the column maxima of the warp's block (G is monotone in them).
-template <int S>
-__device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int cb, int lane, int m0, int n0, int M, int N, const OzParams &P) {
+// nd = number of accumulators the main loop wrote (S unless planes were trimmed: na + nb - 1); the others count as zero
+// EpiRole: which operand supplies the tile's rows.  The trimmed cluster path may compute the tile of C^T = op(B)^T op(A)^T instead
+// (rows = columns of C, the operand with fewer live planes in the A role, see oz2_trimmed_cluster): CT = true addresses C transposed.
+struct EpiRole { const double *srow, *scol, *lrow, *nrow, *lcol, *ncol; };
+__device__ __forceinline__ EpiRole epi_role(const OzParams &P, bool swapped = false) {
+    return swapped ? EpiRole{P.sb, P.sa, P.lb, P.nb, P.la, P.na} : EpiRole{P.sa, P.sb, P.la, P.na, P.lb, P.nb};
+}
+template <int S, bool CT = false>
+__device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int cb, int lane, int m0, int n0, int M, int N, const OzParams &P, int nd,
+                                             const EpiRole R) {
     constexpr int CW = BN2 / EPI_CB;
     const int row = m0 + q4 * 32 + lane;
     const bool live = row < M;
-    const double rs = live ? P.alpha * P.sa[row] : 0.0;
+    const double rs = live ? P.alpha * R.srow[row] : 0.0;
+    const int64_t rstride = CT ? P.ldc : 1, cstride = CT ? 1 : P.ldc;
     constexpr int NG = (S + 2) / 3;
     double wg[NG];
 #pragma unroll
@@ -938,7 +1006,7 @@ __device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int cb,
 #pragma unroll
         for (int j = 0; j < 8; ++j) {                                                  // the old C (beta != 0) travels under the TMEM loads
             const int col = n0 + c0 + j;
-            prev[j] = (live && col < N && P.beta != 0.0) ? P.C[row + (int64_t)col * P.ldc] : 0.0;
+            prev[j] = (live && col < N && P.beta != 0.0) ? P.C[row * rstride + col * cstride] : 0.0;
         }
         tc_wait_ld();
         if (!live) continue;
@@ -952,12 +1020,12 @@ __device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int cb,
                 const int last = (3 * g + 2 < S) ? 3 * g + 2 : S - 1;
                 long long acc = 0;
 #pragma unroll
-                for (int d = 3 * g; d <= last; ++d) acc += (long long)(int)v[d][j] << (P.bits * (last - d));
+                for (int d = 3 * g; d <= last; ++d) acc += (long long)(d < nd ? (int)v[d][j] : 0) << (P.bits * (last - d));   // (unwritten accumulators hold stale TMEM)
                 sum += (double)acc * wg[g];
             }
-            const double term = sum * (rs * P.sb[col]);
+            const double term = sum * (rs * R.scol[col]);
             gmax_hi = max(gmax_hi, __double2hiint(term) & 0x7fffffff);
-            P.C[row + (int64_t)col * P.ldc] = P.beta * prev[j] + term;
+            P.C[row * rstride + col * cstride] = P.beta * prev[j] + term;
         }
     }
     if (P.guard) {
@@ -965,7 +1033,7 @@ __device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int cb,
         double sbm = 0.0, lbm = 0.0, nbm = 0.0;
         {
             const int col = n0 + cb * CW + lane;
-            if (lane < CW && col < N) { sbm = fabs(P.sb[col]); lbm = P.lb[col]; nbm = P.nb[col]; }
+            if (lane < CW && col < N) { sbm = fabs(R.scol[col]); lbm = R.lcol[col]; nbm = R.ncol[col]; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -975,7 +1043,7 @@ __device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int cb,
         }
         double bnd = 0.0;
         if (live) {
-            const double la = P.la[row], na = P.na[row];
+            const double la = R.lrow[row], na = R.nrow[row];
             const double G = P.g_rho * (fmin(la, P.g_h * nbm) + fmin(lbm, P.g_h * na)) + P.g_drop * fmin(na, nbm);
             bnd = fabs(rs) * sbm * G;
         }
@@ -984,9 +1052,44 @@ __device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int cb,
     }
 }
 
+// ---- trimmed main loop: only na planes of op(A) and nb planes of op(B) can hold non-zero digits (plane words, see
+// planes_publish_*).  Pairs (p, q) with p < na, q < nb, p + q <= S-1 are issued, merged over q as in the dense loop; accumulator
+// d = p + q is first written (accumulate = 0) by the smallest p that reaches it.  Dynamic loops: this path trades the unrolled
+// issue sequence for up to 28x fewer products.
+template <int S, int KB>
+__device__ __forceinline__ void oz2_issue_trimmed(uint32_t a0, uint32_t b0, uint32_t tmem_base, int na, int nb, bool first_kblock) {
+    constexpr int A_SLICE = BM2 * KB, B_SLICE = BN2 * KB;
+    int init = 0;                                                  // accumulators written so far in this tile (first K-block only)
+    for (int p = 0; p < na; ++p) {
+        const int nqt = nb < S - p ? nb : S - p;
+        const uint64_t ad = make_desc_kb<KB>(a0 + p * A_SLICE);
+        for (int q = 0; q < nqt;) {
+            int nq = nqt - q < 4 ? nqt - q : 4;
+            uint32_t acc0 = 1u;
+            if (first_kblock) {
+                if (p + q >= init) acc0 = 0u;                      // d = p + q and everything above it in this chunk is new
+                else if (init - (p + q) < nq) nq = init - (p + q); // the already written accumulators first, the new one next round
+            }
+            const uint64_t bd = make_desc_kb<KB>(b0 + q * B_SLICE);
+            const uint32_t acc = tmem_base + (uint32_t)((p + q) * BN2);
+            const uint32_t idesc = make_idesc_i8(nq * BN2);
+#pragma unroll
+            for (int k = 0; k < KB / 32; ++k) tc_mma<KIND_I8>(acc, ad + 2 * k, bd + 2 * k, idesc, k > 0 ? 1u : acc0);
+            q += nq;
+        }
+        if (first_kblock && p + nqt > init) init = p + nqt;
+    }
+}
+__device__ __forceinline__ int oz2_pairs(int S, int na, int nb) {
+    int n = 0;
+    for (int p = 0; p < na; ++p) n += nb < S - p ? nb : S - p;
+    return n;
+}
+
 template <int S, int KB>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
-umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, OzParams P) {
+umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA1,
+                   const __grid_constant__ CUtensorMap tmB1, int M, int N, int K, OzParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int STAGE = stage_bytes(S, KB), STAGES2 = stages_for(KB), BKB2 = KB, A_SLICE = BM2 * KB, B_SLICE = BN2 * KB;
@@ -1001,6 +1104,8 @@ umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     raster((int)(blockIdx.x + gridDim.x * blockIdx.y), (int)gridDim.x, (int)gridDim.y, P.group_m, m_tile, n_tile);
     const int m0 = m_tile * BM2, n0 = n_tile * BN2;
     const int kblocks = (K + BKB2 - 1) / BKB2;
+    const int na = planes_of(P.pa, S, P.bits), nb = planes_of(P.pb, S, P.bits);     // live planes: tmA1 / tmB1 load them one by one
+    const bool dense = na == S && nb == S;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -1022,6 +1127,12 @@ umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const int s = kb % STAGES2;
                 const uint32_t ph = (kb / STAGES2) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
+                if (!dense) {
+                    mbar_expect_tx(&full[s], na * A_SLICE + nb * B_SLICE);
+                    for (int p = 0; p < na; ++p) tma_load_3d(smem + s * STAGE + p * A_SLICE, &tmA1, &full[s], kb * BKB2, m0, p);
+                    for (int q = 0; q < nb; ++q) tma_load_3d(smem + s * STAGE + S * A_SLICE + q * B_SLICE, &tmB1, &full[s], kb * BKB2, n0, q);
+                    continue;
+                }
                 mbar_expect_tx(&full[s], STAGE);
                 // one 3-D box per operand: (64 bytes of k) x rows x all S slices
                 tma_load_3d(smem + s * STAGE, &tmA, &full[s], kb * BKB2, m0, 0);
@@ -1036,6 +1147,7 @@ umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(smem + s * STAGE), b0 = a0 + S * A_SLICE;
+                if (!dense) { oz2_issue_trimmed<S, KB>(a0, b0, tmem_base, na, nb, kb == 0); tc_commit(&empty[s]); continue; }
                 // For a fixed A slice p the partner slices q = 0..S-1-p are CONTIGUOUS rows of the B stage ([slice][64 rows]) and
                 // their accumulators d = p+q are CONTIGUOUS TMEM column blocks, so up to four pairs go out as ONE MMA with
                 // N = 64*(#q) <= 256: A is read from shared memory once per four pairs (N=64 MMAs were smem-read bound).
@@ -1056,11 +1168,12 @@ umma_ozaki2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 tc_commit(&empty[s]);
             }
             tc_commit(tmem_full);
+            if (P.pairs && blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(P.pairs, (unsigned long long)oz2_pairs(S, na, nb));
         }
     } else {
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        oz2_epilogue<S>(tmem_base, warp & 3, (warp - 2) >> 2, lane, m0, n0, M, N, P);
+        oz2_epilogue<S>(tmem_base, warp & 3, (warp - 2) >> 2, lane, m0, n0, M, N, P, dense ? S : (na + nb - 1 < S ? na + nb - 1 : S), epi_role(P));
     }
     tc_fence_before();
     __syncthreads();
@@ -1096,7 +1209,9 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask) {
 
 template <int S, int CL>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
-umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, OzParams P) {
+umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmA1n, const __grid_constant__ CUtensorMap tmB1w,
+                    int M, int N, int K, OzParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int KB = 64, STAGES2 = stages_for(KB), A_SLICE = BM2 * KB, B_SLICE = BN2 * KB;
@@ -1104,9 +1219,10 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
     constexpr int SA = SL * CL;                                   // last box may reach past slice S-1 (TMA zero-fills, counts bytes)
     constexpr int STAGE = SA * A_SLICE + S * B_SLICE;
     constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
+    constexpr int MAXST = 8;                                      // barrier pairs: the trimmed path runs a deeper ring of smaller stages
     uint64_t *full = (uint64_t *)(smem + STAGES2 * STAGE);
-    uint64_t *empty = full + STAGES2;
-    uint64_t *tmem_full = empty + STAGES2;
+    uint64_t *empty = full + MAXST;
+    uint64_t *tmem_full = empty + MAXST;
     uint32_t *tmem_ptr = (uint32_t *)(tmem_full + 1);
     constexpr int TCOLS = S * BN2 <= 32 ? 32 : S * BN2 <= 64 ? 64 : S * BN2 <= 128 ? 128 : S * BN2 <= 256 ? 256 : 512;
 
@@ -1116,9 +1232,11 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
     raster((int)(blockIdx.x + gridDim.x * (blockIdx.y / CL)), (int)gridDim.x, (int)(gridDim.y / CL), P.group_m, m_tile, n_group);
     const int m0 = m_tile * BM2, n0 = (n_group * CL + (int)crank) * BN2;
     const int kblocks = (K + KB - 1) / KB;
+    const int na = planes_of(P.pa, S, P.bits), nb = planes_of(P.pb, S, P.bits);     // live planes: tmA1 / tmB1 load them one by one
+    const bool dense = na == S && nb == S;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
+        for (int s = 0; s < MAXST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1132,13 +1250,85 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 0) {
+    if (CL == 2 && !dense) {
+        // ---- trimmed operands (plane words): only `na` planes of op(A) and `nb` of op(B) are live.
+        //  * ROLES: the operand with fewer live planes takes the A role (128-row tiles): one MMA then covers up to four planes of
+        //    the other operand (merged N), where the opposite assignment would issue N = 64 MMAs at 2/3 of the pipe rate.  If that
+        //    is op(B) the CTA computes a tile of C^T = op(B)^T op(A)^T and its epilogue addresses C transposed (P.allow_swap: the
+        //    host checked that both tilings have the same number of clusters).
+        //  * SHARING: the two CTAs of the cluster multicast whichever role weighs more per K-block: the A role (same rows, adjacent
+        //    column tiles - the dense geometry) or the B role (adjacent row tiles, same columns).
+        //  * RING: a stage holds just the live planes, so the 184 KB of the two dense stages become up to 8 stages: the loads of a
+        //    short K-block (a handful of MMAs) need that depth to cover the TMA round trip.
+        const bool swap = P.allow_swap && nb < na;
+        const int nar = swap ? nb : na, nbr = swap ? na : nb;
+        const int Rr = swap ? N : M, Cr = swap ? M : N;
+        const CUtensorMap *mapA = swap ? &tmB1w : &tmA1, *mapB = swap ? &tmA1n : &tmB1;
+        const int RT = (Rr + BM2 - 1) / BM2, CT = (Cr + BN2 - 1) / BN2;
+        const bool share_b = nbr * B_SLICE > nar * A_SLICE && RT % 2 == 0;
+        const int cid = (int)(blockIdx.x + gridDim.x * (blockIdx.y / 2));
+        int r_tile, c_tile;
+        if (!share_b) { int rt, cg; raster(cid, RT, CT / 2, P.group_m, rt, cg); r_tile = rt; c_tile = cg * 2 + (int)crank; }
+        else { int rp, ct; raster(cid, RT / 2, CT, P.group_m, rp, ct); r_tile = rp * 2 + (int)crank; c_tile = ct; }
+        const int r0 = r_tile * BM2, c0 = c_tile * BN2;
+        const int stride = nar * A_SLICE + nbr * B_SLICE;
+        int nst = (STAGES2 * STAGE) / stride;
+        if (nst > MAXST) nst = MAXST;
+        if (warp == 0) {
+            if (lane == 0) {
+                // my half of the shared role's planes goes to both CTAs, the other role's planes are mine alone
+                const int nsh = share_b ? nbr : nar, half = (nsh + 1) / 2;
+                const int sh0 = (int)crank * half, sh1 = sh0 + half < nsh ? sh0 + half : nsh;
+                int st = 0; uint32_t ph = 0;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[st], ph ^ 1);
+                    uint8_t *base = smem + st * stride;
+                    mbar_expect_tx(&full[st], stride);
+                    if (!share_b) {
+                        for (int p = sh0; p < sh1; ++p) tma_load_3d_mc(base + p * A_SLICE, mapA, &full[st], kb * KB, r0, p, MASK);
+                        for (int q = 0; q < nbr; ++q) tma_load_3d(base + nar * A_SLICE + q * B_SLICE, mapB, &full[st], kb * KB, c0, q);
+                    } else {
+                        for (int p = 0; p < nar; ++p) tma_load_3d(base + p * A_SLICE, mapA, &full[st], kb * KB, r0, p);
+                        for (int q = sh0; q < sh1; ++q) tma_load_3d_mc(base + nar * A_SLICE + q * B_SLICE, mapB, &full[st], kb * KB, c0, q, MASK);
+                    }
+                    if (++st == nst) { st = 0; ph ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                int st = 0; uint32_t ph = 0;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[st], ph);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(smem + st * stride);
+                    oz2_issue_trimmed<S, KB>(a0, a0 + nar * A_SLICE, tmem_base, nar, nbr, kb == 0);
+                    tc_commit_mc(&empty[st], MASK);
+                    if (++st == nst) { st = 0; ph ^= 1; }
+                }
+                tc_commit(tmem_full);
+                if (P.pairs && blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(P.pairs, (unsigned long long)oz2_pairs(S, nar, nbr));
+            }
+        } else {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+            const int nd = nar + nbr - 1 < S ? nar + nbr - 1 : S;
+            if (swap) oz2_epilogue<S, true>(tmem_base, warp & 3, (warp - 2) >> 2, lane, r0, c0, Rr, Cr, P, nd, epi_role(P, true));
+            else oz2_epilogue<S, false>(tmem_base, warp & 3, (warp - 2) >> 2, lane, r0, c0, Rr, Cr, P, nd, epi_role(P, false));
+        }
+    } else if (warp == 0) {
         if (lane == 0) {
             for (int kb = 0; kb < kblocks; ++kb) {
                 const int s = kb % STAGES2;
                 const uint32_t ph = (kb / STAGES2) & 1;
                 mbar_wait(&empty[s], ph ^ 1);                     // all CL consumers released this stage (in every CTA)
                 if (P.dbg & 1) { mbar_expect_tx(&full[s], 0); continue; }
+                if (!dense) {                                     // my share of the live A planes (multicast), my live B planes
+                    mbar_expect_tx(&full[s], na * A_SLICE + nb * B_SLICE);
+                    const int p1 = ((int)crank + 1) * SL < na ? ((int)crank + 1) * SL : na;
+                    for (int p = (int)crank * SL; p < p1; ++p) tma_load_3d_mc(smem + s * STAGE + p * A_SLICE, &tmA1, &full[s], kb * KB, m0, p, MASK);
+                    for (int q = 0; q < nb; ++q) tma_load_3d(smem + s * STAGE + SA * A_SLICE + q * B_SLICE, &tmB1, &full[s], kb * KB, n0, q);
+                    continue;
+                }
                 mbar_expect_tx(&full[s], STAGE);                  // bytes landing in MY smem: S A-slices (CL multicasts) + my B slices
                 tma_load_3d_mc(smem + s * STAGE + crank * SL * A_SLICE, &tmAmc, &full[s], kb * KB, m0, crank * SL, MASK);
                 tma_load_3d(smem + s * STAGE + SA * A_SLICE, &tmB, &full[s], kb * KB, n0, 0);
@@ -1152,6 +1342,7 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(smem + s * STAGE), b0 = a0 + SA * A_SLICE;
+                if (!dense) { oz2_issue_trimmed<S, KB>(a0, b0, tmem_base, na, nb, kb == 0); tc_commit_mc(&empty[s], MASK); continue; }
 #pragma unroll
                 for (int p = 0; p < S; ++p) {
                     const uint64_t ad = make_desc_kb<KB>(a0 + p * A_SLICE);
@@ -1169,11 +1360,12 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
                 tc_commit_mc(&empty[s], MASK);                    // arrives on empty[s] of every CTA in the cluster
             }
             tc_commit(tmem_full);
+            if (P.pairs && blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(P.pairs, (unsigned long long)oz2_pairs(S, na, nb));
         }
     } else {
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        if (!(P.dbg & 2)) oz2_epilogue<S>(tmem_base, warp & 3, (warp - 2) >> 2, lane, m0, n0, M, N, P);
+        if (!(P.dbg & 2)) oz2_epilogue<S>(tmem_base, warp & 3, (warp - 2) >> 2, lane, m0, n0, M, N, P, dense ? S : (na + nb - 1 < S ? na + nb - 1 : S), epi_role(P));
     }
     tc_fence_before();
     __syncthreads();
@@ -1192,8 +1384,8 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
 // of the ~30 us of the MLP config's 1024-deep tiles.
 template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
-umma_ozaki2cp_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, OzParams P,
-                     int m_tiles, int n_groups) {
+umma_ozaki2cp_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA1,
+                     const __grid_constant__ CUtensorMap tmB1, int M, int N, int K, OzParams P, int m_tiles, int n_groups) {
     constexpr int CL = 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1213,6 +1405,8 @@ umma_ozaki2cp_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_con
     const int cid = (int)(blockIdx.x / CL), nclusters = (int)(gridDim.x / CL);
     const int items = m_tiles * n_groups;
     const int kblocks = (K + KB - 1) / KB;
+    const int na = planes_of(P.pa, S, P.bits), nb = planes_of(P.pb, S, P.bits);     // live planes: tmA1 / tmB1 load them one by one
+    const bool dense = na == S && nb == S;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
@@ -1241,6 +1435,13 @@ umma_ozaki2cp_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_con
                     const int s = (int)(kc % STAGES2);
                     const uint32_t ph = (kc / STAGES2) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
+                    if (!dense) {
+                        mbar_expect_tx(&full[s], na * A_SLICE + nb * B_SLICE);
+                        const int p1 = ((int)crank + 1) * SL < na ? ((int)crank + 1) * SL : na;
+                        for (int p = (int)crank * SL; p < p1; ++p) tma_load_3d_mc(smem + s * STAGE + p * A_SLICE, &tmA1, &full[s], kb * KB, m0, p, MASK);
+                        for (int q = 0; q < nb; ++q) tma_load_3d(smem + s * STAGE + SA * A_SLICE + q * B_SLICE, &tmB1, &full[s], kb * KB, n0, q);
+                        continue;
+                    }
                     mbar_expect_tx(&full[s], STAGE);
                     tma_load_3d_mc(smem + s * STAGE + crank * SL * A_SLICE, &tmAmc, &full[s], kb * KB, m0, crank * SL, MASK);
                     tma_load_3d(smem + s * STAGE + SA * A_SLICE, &tmB, &full[s], kb * KB, n0, 0);
@@ -1258,6 +1459,7 @@ umma_ozaki2cp_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_con
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(smem + s * STAGE), b0 = a0 + SA * A_SLICE;
+                    if (!dense) { oz2_issue_trimmed<S, KB>(a0, b0, tmem_base, na, nb, kb == 0); tc_commit_mc(&empty[s], MASK); continue; }
 #pragma unroll
                     for (int p = 0; p < S; ++p) {
                         const uint64_t ad = make_desc_kb<KB>(a0 + p * A_SLICE);
@@ -1276,6 +1478,7 @@ umma_ozaki2cp_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_con
                 }
                 tc_commit(tmem_full);
             }
+            if (P.pairs && blockIdx.x == 0) atomicAdd(P.pairs, (unsigned long long)oz2_pairs(S, na, nb));
         }
     } else {
         uint32_t tile = 0;
@@ -1285,7 +1488,7 @@ umma_ozaki2cp_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_con
             const int m0 = m_tile * BM2, n0 = (n_group * CL + (int)crank) * BN2;
             mbar_wait(tmem_full, tile & 1);
             tc_fence_after();
-            oz2_epilogue<S>(tmem_base, warp & 3, (warp - 2) >> 2, lane, m0, n0, M, N, P);
+            oz2_epilogue<S>(tmem_base, warp & 3, (warp - 2) >> 2, lane, m0, n0, M, N, P, dense ? S : (na + nb - 1 < S ? na + nb - 1 : S), epi_role(P));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive1(tmem_empty);
@@ -1437,7 +1640,7 @@ umma_ozaki2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        if (!(P.dbg & 2)) oz2_epilogue<S>(tmem_base, warp & 3, (warp - 2) >> 2, lane, m0, n0, M, N, P);
+        if (!(P.dbg & 2)) oz2_epilogue<S>(tmem_base, warp & 3, (warp - 2) >> 2, lane, m0, n0, M, N, P, S, epi_role(P));
     }
     tc_fence_before();
     __syncthreads();
@@ -1556,7 +1759,7 @@ cudaError_t guard_fold(cudaStream_t st, GemmState &G) {
     return cudaGetLastError();
 }
 cudaError_t guard_read(cudaStream_t st, GemmState &G, GuardSummary *out) {
-    *out = GuardSummary{0, 0, 0.0, 0.0};
+    *out = GuardSummary{0, 0, 0.0, 0ull};
     if (!G.guard) return cudaSuccess;
     cudaError_t e = guard_fold(st, G);
     if (e != cudaSuccess) return e;
@@ -1593,6 +1796,7 @@ static int slice_operand(cudaStream_t st, const double *src, int64_t ld, int64_t
             if (cudaFuncSetAttribute(k_slice_fused_kmajor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) == cudaSuccess) attr_smem = 200 * 1024;
         }
         if (smem <= attr_smem || smem <= 48 * 1024) {
+            cudaMemsetAsync(sc + 3 * rows, 0, 8, st);                        // plane word
             k_slice_fused_kmajor<<<(unsigned)((rows + wpc - 1) / wpc), 32 * wpc, smem, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, sc);
             return 1;
         }
@@ -1605,11 +1809,12 @@ static int slice_operand(cudaStream_t st, const double *src, int64_t ld, int64_t
     }
     k_row_exponent<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(mx, (int)rows, bits, e, sc);
     dim3 g((unsigned)((Kp + 127) / 128), (unsigned)((rows + 31) / 32));
-    if (kmajor) k_slice_i8<true><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e);
+    unsigned long long *pw = reinterpret_cast<unsigned long long *>(sc) + 3 * rows;    // zeroed by k_row_exponent
+    if (kmajor) k_slice_i8<true><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e, pw);
     else {
         dim3 gc((unsigned)((Kp + 31) / 32), (unsigned)((rows + 127) / 128));
-        if (gc.y <= 65535) k_slice_i8_cm<<<gc, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e);
-        else k_slice_i8<false><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e);
+        if (gc.y <= 65535) k_slice_i8_cm<<<gc, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e, pw);
+        else k_slice_i8<false><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e, pw);
     }
     return 3;
 }
@@ -1637,7 +1842,7 @@ static cudaError_t prepare_operand(cudaStream_t st, uint64_t tag, const double *
         return cudaSuccess;
     }
     if (!slot) {
-        const size_t bytes = (size_t)ns * rows * Kp + (size_t)rows * 24 + 512;     // slices + (scale | 1-norm | nnz) per row
+        const size_t bytes = (size_t)ns * rows * Kp + (size_t)rows * 24 + 8 + 512; // slices + (scale | 1-norm | nnz) per row + plane word
         while (!g_cache.empty() && g_cache_bytes + bytes > cache_cap()) {          // evict least recently used
             size_t lru = 0;
             for (size_t i = 1; i < g_cache.size(); ++i) if (g_cache[i].last_use < g_cache[lru].last_use) lru = i;
@@ -1717,7 +1922,7 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     // an operand that is a row window of a larger, tagged operand: slice (or find) the WHOLE operand in the cache and point the
     // tensor map at the window - the panels of a panelled GEMM share one slicing
     const size_t a_bytes = (tag_a && !wa.full) ? 0 : al((size_t)nslices * M * Kp), b_bytes = (tag_b && !wb.full) ? 0 : al((size_t)nslices * N * Kp);
-    const size_t ea_bytes = al(std::max<int64_t>(M, wa.rows_full) * 4), eb_bytes = al(std::max<int64_t>(N, wb.rows_full) * 4), sa_bytes = al(M * 24), sb_bytes = al(N * 24);
+    const size_t ea_bytes = al(std::max<int64_t>(M, wa.rows_full) * 4), eb_bytes = al(std::max<int64_t>(N, wb.rows_full) * 4), sa_bytes = al(M * 24 + 8), sb_bytes = al(N * 24 + 8);
     uint8_t *ws = (uint8_t *)workspace(a_bytes + b_bytes + ea_bytes + eb_bytes + sa_bytes + sb_bytes);
     if (!ws) return cudaErrorMemoryAllocation;
     int8_t *ws_a = (int8_t *)ws, *ws_b = (int8_t *)(ws + a_bytes);
@@ -1727,6 +1932,7 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     // rows of op(A) are m: ta => stored KxM, k contiguous per m => KMAJOR.  rows of op(B)^T are n: !tb => stored KxN => KMAJOR.
     int8_t *As, *Bs;
     double *sa, *sb;
+    const unsigned long long *pwa = nullptr, *pwb = nullptr;       // plane words: behind the statistics of the operand that was sliced
     int la = 0, lb = 0;
     int64_t a_stride = 0, b_stride = 0;                 // rows between slice planes when the operand is a window
     cudaError_t pe = cudaSuccess;
@@ -1734,20 +1940,22 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     if (wa.full) {
         pe = prepare_operand(st, tag_a, (const double *)wa.full, lda, wa.rows_full, K, Kp, ta, nslices, nullptr, ea, nullptr, &As, &sa, &la);
         if (pe != cudaSuccess) return pe;
-        if (As) { As += wa.row0 * Kp; sa += wa.row0; a_stride = wa.rows_full; }
+        if (As) { pwa = reinterpret_cast<const unsigned long long *>(sa) + 3 * wa.rows_full; As += wa.row0 * Kp; sa += wa.row0; a_stride = wa.rows_full; }
     }
     if (!As) {                                         // no window, or the whole operand could not be cached: this panel on its own
         pe = prepare_operand(st, wa.full ? 0 : tag_a, A, lda, M, K, Kp, ta, nslices, ws_a, ea, ws_sa, &As, &sa, &la);
         if (pe != cudaSuccess) return pe;
+        pwa = reinterpret_cast<const unsigned long long *>(sa) + 3 * M;
     }
     if (wb.full) {
         pe = prepare_operand(st, tag_b, (const double *)wb.full, ldb, wb.rows_full, K, Kp, !tb, nslices, nullptr, eb, nullptr, &Bs, &sb, &lb);
         if (pe != cudaSuccess) return pe;
-        if (Bs) { Bs += wb.row0 * Kp; sb += wb.row0; b_stride = wb.rows_full; }
+        if (Bs) { pwb = reinterpret_cast<const unsigned long long *>(sb) + 3 * wb.rows_full; Bs += wb.row0 * Kp; sb += wb.row0; b_stride = wb.rows_full; }
     }
     if (!Bs) {
         pe = prepare_operand(st, wb.full ? 0 : tag_b, B, ldb, N, K, Kp, !tb, nslices, ws_b, eb, ws_sb, &Bs, &sb, &lb);
         if (pe != cudaSuccess) return pe;
+        pwb = reinterpret_cast<const unsigned long long *>(sb) + 3 * N;
     }
     g_chunk_launches = la + lb + 1;
     CUtensorMap mA, mB;
@@ -1769,7 +1977,10 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     // the row statistics sit `rows` apart behind the scales (the rows of the whole operand when this is a window of it)
     const int64_t ra = a_stride ? a_stride : M, rb = b_stride ? b_stride : N;
     static const int dbg = [] { const char *e = getenv("RDB_OZAKI_DBG"); return e ? atoi(e) : 0; }();
-    OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m, ozaki_bits(), gslot, sa + ra, sa + 2 * ra, sb + rb, sb + 2 * rb, g_rho, g_h, g_drop, dbg};
+    static const bool trim = [] { const char *e = getenv("RDB_OZAKI_TRIM"); return !(e && e[0] == '0'); }();    // 0: every plane of every operand is multiplied
+    OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m, ozaki_bits(), gslot, sa + ra, sa + 2 * ra, sb + rb, sb + 2 * rb, g_rho, g_h, g_drop, dbg,
+               trim ? pwa : nullptr, trim ? pwb : nullptr, &G.guard_sum->pairs,
+               (((M + 63) / 64) % 2 == 0 && ((N + 63) / 64) % 2 == 0 && !getenv("RDB_OZAKI_NOSWAP")) ? 1 : 0};
     static int gen = -1;
     if (gen < 0) { const char *e = getenv("RDB_OZAKI_GEN"); gen = e ? atoi(e) : 2; }
     if (gen == 2 && nslices <= 8) {
@@ -1778,6 +1989,15 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
         if (kbytes < 0) { const char *e = getenv("RDB_OZAKI_KB"); kbytes = (e && atoi(e) == 32) ? 32 : 64; }
         if (!make_map(&mA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, kbytes, nslices, a_stride) ||
             !make_map(&mB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2, kbytes, nslices, b_stride))
+            return cudaErrorInvalidValue;
+        // one-plane boxes of the same operands: what the kernels load when the plane words say that only some planes are live
+        CUtensorMap mA1, mB1;
+        if (!make_map(&mA1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, kbytes, 1, a_stride) ||
+            !make_map(&mB1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2, kbytes, 1, b_stride))
+            return cudaErrorInvalidValue;
+        CUtensorMap mA1n, mB1w;       // the same planes with the box heights exchanged, for the role swap of the trimmed path
+        if (!make_map(&mA1n, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BN2, kbytes, 1, a_stride) ||
+            !make_map(&mB1w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BM2, kbytes, 1, b_stride))
             return cudaErrorInvalidValue;
         dim3 grid2((unsigned)((M + BM2 - 1) / BM2), (unsigned)((N + BN2 - 1) / BN2));
         static int pair = -1;
@@ -1860,15 +2080,15 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
                     pa[0].id = cudaLaunchAttributeClusterDimension;
                     pa[0].val.clusterDim.x = 2; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
                     pc.attrs = pa; pc.numAttrs = 1;
-                    return cudaLaunchKernelEx(&pc, umma_ozaki2cp_kernel<7>, mAmc, mB, Mi, Ni, Ki, P, m_tiles, n_groups);
+                    return cudaLaunchKernelEx(&pc, umma_ozaki2cp_kernel<7>, mAmc, mB, mA1, mB1, Mi, Ni, Ki, P, m_tiles, n_groups);
                 }
             }
             if (nslices == 8) {
-                if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 2>, mAmc, mB, Mi, Ni, Ki, P);
-                return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 4>, mAmc, mB, Mi, Ni, Ki, P);
+                if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 2>, mAmc, mB, mA1, mB1, mA1n, mB1w, Mi, Ni, Ki, P);
+                return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 4>, mAmc, mB, mA1, mB1, mA1n, mB1w, Mi, Ni, Ki, P);
             }
-            if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<7, 2>, mAmc, mB, Mi, Ni, Ki, P);
-            return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<7, 4>, mAmc, mB, Mi, Ni, Ki, P);
+            if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<7, 2>, mAmc, mB, mA1, mB1, mA1n, mB1w, Mi, Ni, Ki, P);
+            return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<7, 4>, mAmc, mB, mA1, mB1, mA1n, mB1w, Mi, Ni, Ki, P);
         }
 #define RDB_OZ2(SS)                                                                                                        \
     case SS: {                                                                                                             \
@@ -1879,8 +2099,8 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
             if (e != cudaSuccess) return e;                                                                                \
             attr2 = true;                                                                                                  \
         }                                                                                                                  \
-        if (kbytes == 64) umma_ozaki2_kernel<SS, 64><<<grid2, OZ_THREADS, smem_bytes(SS, 64), st>>>(mA, mB, (int)M, (int)N, (int)Kp, P); \
-        else umma_ozaki2_kernel<SS, 32><<<grid2, OZ_THREADS, smem_bytes(SS, 32), st>>>(mA, mB, (int)M, (int)N, (int)Kp, P);   \
+        if (kbytes == 64) umma_ozaki2_kernel<SS, 64><<<grid2, OZ_THREADS, smem_bytes(SS, 64), st>>>(mA, mB, mA1, mB1, (int)M, (int)N, (int)Kp, P); \
+        else umma_ozaki2_kernel<SS, 32><<<grid2, OZ_THREADS, smem_bytes(SS, 32), st>>>(mA, mB, mA1, mB1, (int)M, (int)N, (int)Kp, P);   \
     } break;
         switch (nslices) { RDB_OZ2(2) RDB_OZ2(3) RDB_OZ2(4) RDB_OZ2(5) RDB_OZ2(6) RDB_OZ2(7) RDB_OZ2(8) default: return cudaErrorInvalidValue; }
 #undef RDB_OZ2

@@ -69,6 +69,7 @@ def lib():
         "rdb_buffer_size": (i64, [vp, i32]),
         "rdb_tape_stats": (i32, [vp, C.c_char_p, C.c_size_t]),
         "rdb_tape_launch_count": (i64, [vp]),
+        "rdb_tape_slice_pairs": (i64, [vp]),
         "rdb_gemm": (i32, [vp, i32, i32, i32, i64, i64, i64, f64, vp, i64, vp, i64, f64, vp, i64]),
         "rdb_add_sum": (i32, [vp, i32, i64, vp, vp, f64, vp, vp]),
         "rdb_plan_col_panels": (i32, [i64, i64, C.POINTER(i64)]),
@@ -86,7 +87,7 @@ EXPORTED_SYMBOLS = [
     "rdb_ctx_synchronize", "rdb_ctx_set_gemm_f64_mode", "rdb_ctx_gemm_guard", "rdb_tape_guard_stats", "rdb_tape_set_async", "rdb_comm_unique_id",
     "rdb_comm_create", "rdb_comm_destroy", "rdb_gather_result", "rdb_place_block", "rdb_tape_load", "rdb_tape_destroy", "rdb_tape_set_input", "rdb_forward",
     "rdb_reverse_scalar_seed", "rdb_gradient", "rdb_gradient_async", "rdb_tape_wait", "rdb_jacobian", "rdb_hessian", "rdb_get_value", "rdb_get_deriv",
-    "rdb_buffer_size", "rdb_tape_stats", "rdb_tape_launch_count", "rdb_gemm", "rdb_add_sum", "rdb_plan_col_panels", "rdb_schedule_bundles",
+    "rdb_buffer_size", "rdb_tape_stats", "rdb_tape_launch_count", "rdb_tape_slice_pairs", "rdb_gemm", "rdb_add_sum", "rdb_plan_col_panels", "rdb_schedule_bundles",
 ]
 
 
@@ -420,7 +421,8 @@ class EngineTape:
         """dict(checked, flagged, fallbacks, worst_ratio): the int8-slice GEMM's accuracy certificate on this tape since load."""
         a, b, f, w = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_double(0.0)
         _check(lib().rdb_tape_guard_stats(self.ptr, C.byref(a), C.byref(b), C.byref(f), C.byref(w)))
-        return {"checked": int(a.value), "flagged": int(b.value), "fallbacks": int(f.value), "worst_ratio": float(w.value)}
+        return {"checked": int(a.value), "flagged": int(b.value), "fallbacks": int(f.value), "worst_ratio": float(w.value),
+                "slice_pairs": int(lib().rdb_tape_slice_pairs(self.ptr))}
 
     def launch_count(self) -> int:
         return int(lib().rdb_tape_launch_count(self.ptr))
