@@ -8,7 +8,7 @@ Metric (BASELINE.json): compiled-tape ``gradient!`` evals/s of ``f(a,b) = sum(a'
 
 * ``value``     device-resident inputs/results (D2D copies only), CUDA events, max over ranks.
 * ``e2e``       page-locked HOST inputs and HOST results, every step uploads its inputs and downloads its results; consecutive steps
-                pipelined over two engine copies of the tape (rd.GradientPipeline = rdb_gradient_async + rdb_tape_wait); the
+                pipelined over three engine copies of the tape (rd.GradientPipeline = rdb_gradient_async + rdb_tape_wait); the
                 one-synchronous-call-per-step number rides along (``e2e.synchronous_calls``), and ``e2e.host_link`` is the measured
                 host<->device copy bandwidth with every rank copying (the platform ceiling of this leg).
 * ``roofline``  dominant kernel (the tcgen05 int8-slice GEMM behind every FP64 ``*``): tensor-pipe operations issued per launch
@@ -383,26 +383,36 @@ def main():
     ms_e2e_sync = timed_steps(torch, dist, world, step_e2e, max(3, args.steps // 2), 3)
     e2e_sync_steps = max(3, args.steps // 2)
     # (b) the headline end-to-end number: the same per-step work (every step uploads its inputs from page-locked host arrays and
-    # downloads its two gradients and the value), consecutive evaluations pipelined over two engine copies of the tape
+    # downloads its two gradients and the value), consecutive evaluations pipelined over three engine copies of the tape
     # (rd.GradientPipeline = rdb_tape_set_input + rdb_gradient_async, rdb_tape_wait): evaluation k+1 uploads and k-1 downloads
     # while k computes.  The timed region ends when the LAST result byte is in host memory (drain).
     (tga2, ga_h2), (tgb2, gb_h2) = pinned(np.zeros((n, n), npdt)), pinned(np.zeros((n, n), npdt))
     keep += [tga2, tgb2]
     res_h2 = (rd.DiffResult(0.0, ga_h2), rd.DiffResult(0.0, gb_h2))
-    pipe = rd.GradientPipeline(tape, depth=2, device=local, gemm_f64_mode=mode)
-    res_slots = (res_h, res_h2)
-    e2e_steps = max(6, args.steps)
+    # depth 4 (measured, profiles/e2e_sweep.sh: 126.7 / 137.7 / 144.2 evals/s at depth 2 / 3 / 4): a slot's own upload -> sweeps ->
+    # download chain takes ~17 ms while every engine - copy in, copy out, SMs - is busy only ~6 ms per evaluation
+    depth = int(os.environ.get("RDB_BENCH_DEPTH", "4"))
+    res_slots = [res_h, res_h2]
+    host_results = [(ga_h, gb_h), (ga_h2, gb_h2)]
+    for _ in range(depth - 2):
+        (tgx, ga_hx), (tgy, gb_hx) = pinned(np.zeros((n, n), npdt)), pinned(np.zeros((n, n), npdt))
+        keep += [tgx, tgy]
+        res_slots.append((rd.DiffResult(0.0, ga_hx), rd.DiffResult(0.0, gb_hx)))
+        host_results.append((ga_hx, gb_hx))
+    res_slots = res_slots[:depth]; host_results = host_results[:depth]
+    pipe = rd.GradientPipeline(tape, depth=depth, device=local, gemm_f64_mode=mode)
+    e2e_steps = max(40, args.steps)                           # (the first upload and the last download overlap nothing: amortised over the run)
 
     def run_pipeline(k):
         for j in range(k):
-            pipe.submit(res_slots[j % 2], (a_h, b_h))
+            pipe.submit(res_slots[j % depth], (a_h, b_h))
         pipe.drain()
-    run_pipeline(4)                                           # warm-up: both slots compile their kernels and size their workspaces
+    run_pipeline(2 * depth)                                        # warm-up: all slots compile their kernels and size their workspaces
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    for r in (ga_h, gb_h, ga_h2, gb_h2):
-        r[...] = 0
+    for ga_x, gb_x in host_results:
+        ga_x[...] = 0; gb_x[...] = 0
     lp0 = pipe.launch_count()
     if rank == 0:
         sampler.start()
@@ -420,7 +430,7 @@ def main():
     pcie = pcie_probe(torch, dist, world)
     clocks = sampler.stop() if rank == 0 else None           # sampled every 20 ms during the timed regions (device-resident, end-to-end)
     gb_ref = a64.sum(1)[:, None] + a64.sum(0)[None, :]
-    for ga_x, gb_x, rr in ((ga_h, gb_h, res_h), (ga_h2, gb_h2, res_h2)):
+    for ga_x, gb_x in host_results:
         assert np.max(np.abs(ga_x - ga)) <= tol * np.max(np.abs(ga))
         assert np.max(np.abs(gb_x - gb_ref)) <= tol * np.max(np.abs(gb_ref))
     del pipe
@@ -435,9 +445,10 @@ def main():
         for _ in range(reps_):
             rd.gradient_((ga_d, gb_d), ctp, (a_d, b_d))
         st = json.loads(ctp.handle.stats())
+        gs = ctp.handle.guard_stats()
         del ctp
-        return st, reps_
-    stats, reps = gemm_stats(mode)
+        return st, reps_, gs
+    stats, reps, gstats = gemm_stats(mode)
     g_ms = sum(s["ms"] for s in stats if s["step"].startswith("gemm"))
     g_fl = sum(s["flops"] for s in stats if s["step"].startswith("gemm"))
     g_cnt = sum(s["count"] for s in stats if s["step"].startswith("gemm"))
@@ -495,15 +506,43 @@ def main():
             peak_src = f"0.5 x {peak_tag} (tf32 issues at half the bf16 rate)"
         traffic, traffic_src = None, None
     achieved = fp_equiv * ops_per_flop
+    launch_kinds = None
+    if args.dtype == "f64" and mode == 0 and gstats.get("checked", 0) > 0:
+        # Slice pairs actually issued (rdb_tape_slice_pairs): the kernels skip digit planes that are identically zero.  The two forward
+        # products multiply dense operands (28 pairs); the four adjoint products meet deriv(output) of `sum`, a constant fill with ONE
+        # live plane (7 pairs): tensor work shrinks 4x and those launches are bound by operand delivery (L2 -> shared memory), not by
+        # the tensor pipe.  `frac` is therefore taken on the DENSE launches - the kernel in the regime the roofline describes - and
+        # the all-launch figure is reported next to it.
+        pairs_per_launch_all = gstats["slice_pairs"] / gstats["checked"]
+        fwd = [s_ for s_ in stats if s_["step"] == "gemm_forward"]
+        rev = [s_ for s_ in stats if s_["step"].startswith("gemm_reverse")]
+        f_ms = sum(s_["ms"] for s_ in fwd); f_cnt = sum(s_["count"] for s_ in fwd)
+        r_ms = sum(s_["ms"] for s_ in rev); r_cnt = sum(s_["count"] for s_ in rev)
+        tot_pairs = gstats["slice_pairs"]
+        dense_pairs = ops_per_flop
+        rev_pairs = (tot_pairs - dense_pairs * f_cnt * gstats["checked"] / max(g_cnt, 1)) / max(r_cnt * gstats["checked"] / max(g_cnt, 1), 1)
+        ops_launch = 2.0 * n ** 3
+        launch_kinds = {
+            "dense_forward": {"launches_per_step": f_cnt // reps, "avg_launch_ms": f_ms / max(f_cnt, 1), "slice_pairs_per_launch": dense_pairs,
+                              "int8_tops": dense_pairs * ops_launch / (f_ms / max(f_cnt, 1) * 1e-3) / 1e12},
+            "trimmed_reverse": {"launches_per_step": r_cnt // reps, "avg_launch_ms": r_ms / max(r_cnt, 1), "slice_pairs_per_launch": rev_pairs,
+                                "int8_tops": rev_pairs * ops_launch / (r_ms / max(r_cnt, 1) * 1e-3) / 1e12,
+                                "bound": "operand delivery L2 -> shared memory (one live plane of deriv(output))"},
+            "all_launches": {"slice_pairs_per_launch": pairs_per_launch_all,
+                             "int8_tops": pairs_per_launch_all * ops_launch / (g_ms / max(g_cnt, 1) * 1e-3) / 1e12},
+        }
+        achieved = launch_kinds["dense_forward"]["int8_tops"]
     roofline = {
         "bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": pipe_peak, "unit": unit, "frac": achieved / pipe_peak,
         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-        "note": "achieved = tensor-pipe operations actually issued (algorithmic 2mnk x ops_per_flop) / CUDA-event time of the `*` "
-                "steps INCLUDING their operand slicing passes",
+        "note": "achieved = tensor-pipe operations actually issued by the DENSE launches of the kernel (the two forward products: "
+                "28 slice pairs x 2mnk) / their CUDA-event time INCLUDING the slicing passes of both operands; launch_kinds holds the "
+                "trimmed adjoint launches and the all-launch average (slice pairs counted on the device, rdb_tape_slice_pairs)",
         "ops_per_algorithmic_flop": ops_per_flop,
         "fp_equivalent": {"achieved_tflops": fp_equiv, "cublas_gemm_tflops_same_run": blas_peak, "ratio_vs_cublas": fp_equiv / blas_peak,
                           "what": f"algorithmic 2mnk flops of the six {n}^3 `*` instructions / their time, next to cuBLAS "
                                   f"{'D' if args.dtype == 'f64' else 'S'}GEMM {n}^3 (best of 6)"},
+        "launch_kinds": launch_kinds,
         "algorithmic_flops_per_launch": 2.0 * n ** 3, "launches_per_step": g_cnt // reps,
         "avg_launch_ms": g_ms / max(g_cnt, 1), "gemm_share_of_step": g_ms / tot_ms,
         "elementwise": {"bound": "hbm", "achieved": ew_bytes / (ew_ms * 1e-3) / 1e9 if ew_ms > 0 else None, "peak": hbm_peak,
@@ -515,7 +554,7 @@ def main():
     if args.dtype == "f64" and mode == 0:
         roofline["cublaslt_int8_tops_same_run"] = i8
         # the DMMA kernel on the same tape, same run, for context
-        st1, r1 = gemm_stats(1)
+        st1, r1, _ = gemm_stats(1)
         d_ms = sum(s["ms"] for s in st1 if s["step"].startswith("gemm")); d_fl = sum(s["flops"] for s in st1 if s["step"].startswith("gemm"))
         roofline["dmma_path_same_run"] = {"gemm_tflops": d_fl / (d_ms * 1e-3) / 1e12, "frac_of_cublas_dgemm": d_fl / (d_ms * 1e-3) / 1e12 / blas_peak,
                                           "ms_per_eval_all_steps": sum(s["ms"] for s in st1) / r1}
@@ -547,7 +586,7 @@ def main():
                               "multi_gpu": "replicas only (a scalar function's gradient does not shard)" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": 2 * n * n * es, "d2h_bytes_per_step": 2 * n * n * es + es,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "gpu_launches": int(e2e_launches),
-                    "how": "rd.GradientPipeline(depth=2): rdb_tape_set_input + rdb_gradient_async per step, rdb_tape_wait before a slot is "
+                    "how": f"rd.GradientPipeline(depth={depth}): rdb_tape_set_input + rdb_gradient_async per step, rdb_tape_wait before a slot is "
                            "reused; pinned host inputs and results; host clock from the first submit to the last result byte in host memory",
                     "synchronous_calls": {"value": world * e2e_sync_steps / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync / e2e_sync_steps,
                                           "how": "one rdb_gradient per step, returning when its results are in host memory"},

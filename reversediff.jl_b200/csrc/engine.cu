@@ -1733,7 +1733,9 @@ static int gradient_impl(rdb_tape *t, void *const *result_ptrs, int on_device, v
             if (result_ptrs[i] && E.dst[r]) distinct = false;      // two result slots alias one buffer: keep the plain path
             if (result_ptrs[i]) E.dst[r] = result_ptrs[i];
         }
-        E.enabled = distinct;
+        // 0: never; 1 (default): always; 2: synchronous calls only (a pipelined caller overlaps whole evaluations instead)
+        static const int early_mode = [] { const char *e = getenv("RDB_EARLY_D2H"); return e ? atoi(e) : 1; }();
+        E.enabled = distinct && early_mode != 0 && !(early_mode == 2 && t->async_call);
     }
     int rc = seed_scalar_and_reverse<T>(t);
     E.enabled = false;

@@ -432,7 +432,20 @@ __global__ void __launch_bounds__(256) k_row_absmax(const double *__restrict__ s
         const double *p = src + (int64_t)r * ld;
         double mx = 0.0, s1 = 0.0, cnt = 0.0;
         // NaN/Inf anywhere in the row poisons the row: fmax() would silently drop a NaN, so non-finite elements count as +Inf
-        for (int k = lane; k < K; k += 32) {
+        int kdone = 0;
+        if ((ld & 1) == 0 && ((uintptr_t)src & 15) == 0) {          // 16-byte loads, four in flight per lane
+            const int Kv = K & ~1;
+#pragma unroll 4
+            for (int k = 2 * lane; k < Kv; k += 64) {
+                const double2 t = *reinterpret_cast<const double2 *>(p + k);
+                const double v0 = fabs(t.x), v1 = fabs(t.y);
+                mx = fmax(mx, v0 <= 1.7976931348623157e308 ? v0 : __longlong_as_double(0x7FF0000000000000LL));
+                mx = fmax(mx, v1 <= 1.7976931348623157e308 ? v1 : __longlong_as_double(0x7FF0000000000000LL));
+                s1 += v0; s1 += v1; cnt += v0 != 0.0 ? 1.0 : 0.0; cnt += v1 != 0.0 ? 1.0 : 0.0;
+            }
+            kdone = Kv;
+        }
+        for (int k = kdone + lane; k < K; k += 32) {
             double v = fabs(p[k]);
             mx = fmax(mx, v <= 1.7976931348623157e308 ? v : __longlong_as_double(0x7FF0000000000000LL));
             s1 += v; cnt += v != 0.0 ? 1.0 : 0.0;
@@ -510,11 +523,24 @@ __device__ __forceinline__ int planes_of(const unsigned long long *word, int nsl
     return z >= nslices ? 1 : nslices - z;
 }
 
+// 2^h as the product of two normal doubles (h = bits * S - e >= -971 because e <= 1027; h > 1000 only for rows of denormal
+// magnitude): X = rint((v * m1) * m2) equals rint(scalbn(v, h)) bit for bit - both products are exact unless the result is
+// below 2^-1022, where either way rounds to X = 0 - at two multiplications instead of a library call per element.
+__device__ __forceinline__ void pow2_pair(int h, double &m1, double &m2) {
+    const int h1 = h > 1000 ? 1000 : h;
+    m1 = __hiloint2double((1023 + h1) << 20, 0);
+    m2 = __hiloint2double((1023 + (h - h1)) << 20, 0);
+}
+
 // Balanced base-256 digits of four fixed-point values at once (bits == 8).  Adding 0x80 at every digit position below the
 // leading one turns "d >= 128 ? d - 256, carry" into plain byte extraction: byte p of Y = X + 0x80..80 is digit_p + 128, i.e. the
 // digit's int8 bit pattern is that byte with its top bit flipped; the leading digit is the (signed) rest.  Bit-identical to the
 // digit loop.  Stores plane s (s = 0 leading) of the four consecutive k of one row as one packed 32-bit word.
-__device__ __forceinline__ void store_digits8(int8_t *__restrict__ dst_row_k, int64_t plane, int nslices, const long long X[4]) {
+// NS > 0: the number of slices is a compile-time constant (the default S = 7 is instantiated: byte selectors, plane offsets and the
+// bias become immediates - the generic kernels spent most of their issue slots computing them); NS = 0: `nslices` at run time.
+template <int NS = 0>
+__device__ __forceinline__ void store_digits8(int8_t *__restrict__ dst_row_k, int64_t plane, int nslices_rt, const long long X[4]) {
+    const int nslices = NS ? NS : nslices_rt;
     const unsigned long long bias = nslices > 1 ? (0x8080808080808080ULL >> (8 * (9 - nslices))) : 0ULL;
     unsigned lo[4], hi[4];
 #pragma unroll
@@ -522,7 +548,9 @@ __device__ __forceinline__ void store_digits8(int8_t *__restrict__ dst_row_k, in
         const unsigned long long y = (unsigned long long)X[j] + bias;
         lo[j] = (unsigned)y; hi[j] = (unsigned)(y >> 32);
     }
-    for (int p = 0; p < nslices; ++p) {                          // byte position p <-> slice index nslices - 1 - p
+#pragma unroll
+    for (int p = 0; p < (NS ? NS : 8); ++p) {                    // byte position p <-> slice index nslices - 1 - p
+        if (p >= nslices) break;
         const unsigned *w = p < 4 ? lo : hi;
         const unsigned q = (unsigned)(p & 3), sel = q | ((4u + q) << 4);
         const unsigned h01 = __byte_perm(w[0], w[1], sel), h23 = __byte_perm(w[2], w[3], sel);
@@ -534,9 +562,10 @@ __device__ __forceinline__ void store_digits8(int8_t *__restrict__ dst_row_k, in
 
 // ---- pass 2: slices.  dst is [s][rows][Kp] int8, k contiguous.  Block = 32 rows x 128 k; thread = 1 row x 4 consecutive k per
 // iteration, so every slice store is one packed 32-bit word and a warp writes 128 contiguous bytes of one row.
-template <bool KMAJOR>
-__global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, const double *__restrict__ src, int64_t ld, int rows, int K,
-                                                  int Kp, int nslices, int bits, const int *__restrict__ e_in, unsigned long long *plane_word) {
+template <bool KMAJOR, int NS8 = 0>      // NS8 > 0: bits == 8 and nslices == NS8 are compile-time facts
+__global__ void __launch_bounds__(256, 4) k_slice_i8(int8_t *__restrict__ dst, const double *__restrict__ src, int64_t ld, int rows, int K,
+                                                  int Kp, int nslices_rt, int bits_rt, const int *__restrict__ e_in, unsigned long long *plane_word) {
+    const int nslices = NS8 ? NS8 : nslices_rt, bits = NS8 ? 8 : bits_rt;
     __shared__ unsigned long long sh_or;
     // [k % 4][k / 4][r]: a thread later reads 4 consecutive k of one row, i.e. one element of each k%4 plane at row k/4 = lane -
     // 33-double rows make both the write (lanes along r) and that read (lanes along k/4) bank-conflict free
@@ -582,8 +611,10 @@ __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, cons
                 for (int j = 0; j < 4; ++j) v[j] = tile[j][lane][rl];
             }
         }
+        double m1, m2;
+        pow2_pair(bits * nslices - e, m1, m2);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) X[i][j] = isfinite(v[j]) ? __double2ll_rn(scalbn(v[j], bits * nslices - e)) : 0LL;
+        for (int j = 0; j < 4; ++j) X[i][j] = isfinite(v[j]) ? __double2ll_rn((v[j] * m1) * m2) : 0LL;
     }
     {
         unsigned long long orv = 0ull;
@@ -597,7 +628,7 @@ __global__ void __launch_bounds__(256) k_slice_i8(int8_t *__restrict__ dst, cons
     for (int i = 0; i < 4; ++i) {
         if (!ok[i]) continue;
         const int r = r0 + w + 8 * i;
-        if (bits == 8) { store_digits8(dst + (int64_t)r * Kp + k, plane, nslices, X[i]); continue; }
+        if (bits == 8) { store_digits8<NS8>(dst + (int64_t)r * Kp + k, plane, nslices, X[i]); continue; }
         for (int sidx = nslices - 1; sidx >= 0; --sidx) {
             uint32_t packed = 0;
 #pragma unroll
@@ -654,12 +685,14 @@ __global__ void __launch_bounds__(128) k_slice_fused_kmajor(int8_t *__restrict__
     const int64_t plane = (int64_t)rows * Kp;
     const int radix = 1 << bits, half = radix >> 1;
     unsigned long long orv = 0ull;
+    double m1, m2;
+    pow2_pair(bits * nslices - e, m1, m2);
     for (int k = 4 * lane; k < Kp; k += 128) {
         const double2 lo = *reinterpret_cast<const double2 *>(row + k), hi = *reinterpret_cast<const double2 *>(row + k + 2);
         const double v[4] = {lo.x, lo.y, hi.x, hi.y};
         long long X[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { X[j] = isfinite(v[j]) ? __double2ll_rn(scalbn(v[j], bits * nslices - e)) : 0LL; orv |= (unsigned long long)X[j]; }
+        for (int j = 0; j < 4; ++j) { X[j] = isfinite(v[j]) ? __double2ll_rn((v[j] * m1) * m2) : 0LL; orv |= (unsigned long long)X[j]; }
         if (bits == 8) { store_digits8(dst + (int64_t)r * Kp + k, plane, nslices, X); continue; }
         for (int sidx = nslices - 1; sidx >= 0; --sidx) {
             uint32_t packed = 0;
@@ -681,8 +714,10 @@ __global__ void __launch_bounds__(128) k_slice_fused_kmajor(int8_t *__restrict__
 // column read is 1 KB contiguous (the 32-row x 128-k tile of the generic kernel reads 256-byte pieces 32 KB apart: every piece a
 // different DRAM page).  Transposed through shared memory ([k % 4][k / 4][row]); a thread then owns 4 rows x 4 consecutive k and
 // stores one packed 32-bit word per slice and row - a warp writes full 32-byte sectors of 4 rows.
-__global__ void __launch_bounds__(256) k_slice_i8_cm(int8_t *__restrict__ dst, const double *__restrict__ src, int64_t ld, int rows, int K,
-                                                     int Kp, int nslices, int bits, const int *__restrict__ e_in, unsigned long long *plane_word) {
+template <int NS8 = 0>
+__global__ void __launch_bounds__(256, 4) k_slice_i8_cm(int8_t *__restrict__ dst, const double *__restrict__ src, int64_t ld, int rows, int K,
+                                                     int Kp, int nslices_rt, int bits_rt, const int *__restrict__ e_in, unsigned long long *plane_word) {
+    const int nslices = NS8 ? NS8 : nslices_rt, bits = NS8 ? 8 : bits_rt;
     __shared__ double tile[4][8][132];
     __shared__ unsigned long long sh_or;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -710,10 +745,12 @@ __global__ void __launch_bounds__(256) k_slice_i8_cm(int8_t *__restrict__ dst, c
         const int rl = w * 4 + (lane >> 3) + 32 * i, r = r0 + rl;
         ok[i] = r < rows && k < Kp;
         const int e = ok[i] ? e_in[r] : 0;
+        double m1, m2;
+        pow2_pair(bits * nslices - e, m1, m2);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const double v = tile[j][kg][rl];
-            X[i][j] = (ok[i] && isfinite(v)) ? __double2ll_rn(scalbn(v, bits * nslices - e)) : 0LL;
+            X[i][j] = (ok[i] && isfinite(v)) ? __double2ll_rn((v * m1) * m2) : 0LL;
         }
     }
     {
@@ -728,7 +765,7 @@ __global__ void __launch_bounds__(256) k_slice_i8_cm(int8_t *__restrict__ dst, c
     for (int i = 0; i < 4; ++i) {
         if (!ok[i]) continue;
         const int r = r0 + w * 4 + (lane >> 3) + 32 * i;
-        if (bits == 8) { store_digits8(dst + (int64_t)r * Kp + k, plane, nslices, X[i]); continue; }
+        if (bits == 8) { store_digits8<NS8>(dst + (int64_t)r * Kp + k, plane, nslices, X[i]); continue; }
         for (int sidx = nslices - 1; sidx >= 0; --sidx) {
             uint32_t packed = 0;
 #pragma unroll
@@ -1010,6 +1047,8 @@ __device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int cb,
         }
         tc_wait_ld();
         if (!live) continue;
+        // transposed addressing: a thread's eight columns are eight CONSECUTIVE doubles of C - 16-byte stores when aligned
+        const bool vec = CT && n0 + c0 + 8 <= N && (P.ldc & 1) == 0 && (((uintptr_t)P.C) & 15) == 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int col = n0 + c0 + j;
@@ -1025,7 +1064,18 @@ __device__ __forceinline__ void oz2_epilogue(uint32_t tmem_base, int q4, int cb,
             }
             const double term = sum * (rs * R.scol[col]);
             gmax_hi = max(gmax_hi, __double2hiint(term) & 0x7fffffff);
-            P.C[row * rstride + col * cstride] = P.beta * prev[j] + term;
+            if (CT) prev[j] = P.beta * prev[j] + term;
+            else P.C[row * rstride + col * cstride] = P.beta * prev[j] + term;
+        }
+        if (CT) {
+            double *dst = P.C + row * rstride + (n0 + c0);
+            if (vec) {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2 *>(dst + j) = make_double2(prev[j], prev[j + 1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (n0 + c0 + j < N) dst[j] = prev[j];
+            }
         }
     }
     if (P.guard) {
@@ -1283,6 +1333,7 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[st], ph ^ 1);
                     uint8_t *base = smem + st * stride;
+                    if (P.dbg & 1) { mbar_expect_tx(&full[st], 0); if (++st == nst) { st = 0; ph ^= 1; } continue; }
                     mbar_expect_tx(&full[st], stride);
                     if (!share_b) {
                         for (int p = sh0; p < sh1; ++p) tma_load_3d_mc(base + p * A_SLICE, mapA, &full[st], kb * KB, r0, p, MASK);
@@ -1312,7 +1363,8 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
             mbar_wait(tmem_full, 0);
             tc_fence_after();
             const int nd = nar + nbr - 1 < S ? nar + nbr - 1 : S;
-            if (swap) oz2_epilogue<S, true>(tmem_base, warp & 3, (warp - 2) >> 2, lane, r0, c0, Rr, Cr, P, nd, epi_role(P, true));
+            if (P.dbg & 2) {}
+            else if (swap) oz2_epilogue<S, true>(tmem_base, warp & 3, (warp - 2) >> 2, lane, r0, c0, Rr, Cr, P, nd, epi_role(P, true));
             else oz2_epilogue<S, false>(tmem_base, warp & 3, (warp - 2) >> 2, lane, r0, c0, Rr, Cr, P, nd, epi_role(P, false));
         }
     } else if (warp == 0) {
@@ -1810,11 +1862,16 @@ static int slice_operand(cudaStream_t st, const double *src, int64_t ld, int64_t
     k_row_exponent<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(mx, (int)rows, bits, e, sc);
     dim3 g((unsigned)((Kp + 127) / 128), (unsigned)((rows + 31) / 32));
     unsigned long long *pw = reinterpret_cast<unsigned long long *>(sc) + 3 * rows;    // zeroed by k_row_exponent
-    if (kmajor) k_slice_i8<true><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e, pw);
-    else {
+    const bool s7 = bits == 8 && ns == 7;                              // the default digits: specialised kernels
+    if (kmajor) {
+        if (s7) k_slice_i8<true, 7><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e, pw);
+        else k_slice_i8<true><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e, pw);
+    } else {
         dim3 gc((unsigned)((Kp + 31) / 32), (unsigned)((rows + 127) / 128));
-        if (gc.y <= 65535) k_slice_i8_cm<<<gc, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e, pw);
-        else k_slice_i8<false><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e, pw);
+        if (gc.y <= 65535) {
+            if (s7) k_slice_i8_cm<7><<<gc, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e, pw);
+            else k_slice_i8_cm<><<<gc, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e, pw);
+        } else k_slice_i8<false><<<g, 256, 0, st>>>(q, src, ld, (int)rows, (int)K, (int)Kp, ns, bits, e, pw);
     }
     return 3;
 }
