@@ -799,6 +799,7 @@ struct OzParams {
     const unsigned long long *pa, *pb;
     unsigned long long *pairs;
     int allow_swap;                    // both tilings (C and C^T) have the same number of 2-CTA clusters: the kernel may swap the roles
+    int pair_first;                    // umma_ozaki2tp_kernel was launched in front: one-plane products are its work, not the cluster kernel's
 };
 
 // |x - x~| <= 2^(e - bS - 1) per element (rint), |x| <= 2^e / 4 (b = 8) or 2^e / 2 (b = 7), and the slice pairs with p + q >= S
@@ -1284,6 +1285,7 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
     const int kblocks = (K + KB - 1) / KB;
     const int na = planes_of(P.pa, S, P.bits), nb = planes_of(P.pb, S, P.bits);     // live planes: tmA1 / tmB1 load them one by one
     const bool dense = na == S && nb == S;
+    if (P.pair_first && (na < nb ? na : nb) == 1) return;         // umma_ozaki2tp_kernel did this product (uniform over the grid)
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < MAXST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
@@ -1701,6 +1703,122 @@ umma_ozaki2p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
     }
 }
+
+// --------------------------------------------------------------------------------------------------
+// TRIMMED CTA-PAIR kernel (cta_group::2) for products in which one operand has ONE live digit plane (plane words: the adjoint of
+// `sum`, constant fills, one-hot seeds).  ncu on the trimmed cluster path (profiles/prof_ozaki2c_r2b.txt) shows those launches
+// bound by operand DELIVERY - 36 KB per 64-byte K-block arrive in every SM for 0.45 k clocks of tensor work, at the same
+// ~12 TB/s of crossbar -> shared memory the dense kernel runs at - so multicast cannot help (every SM still receives every byte).
+// A CTA pair can: the one-plane operand takes the A role (each CTA its own 128 rows, 8 KB), the other operand's planes are the
+// B rows of M = 256 MMAs and each CTA supplies only HALF of them (2 KB per plane instead of 4): 22 KB per K-block for (1, 7)
+// planes, and up to 8 stages of it in flight.  The B rows of one MMA are the 64-row planes of a chunk (planes 0..3 -> N = 256,
+// planes 4..6 -> N = 192) stacked in plane order, so the leader holds the first 32 c rows of a c-plane chunk and the peer the
+// rest: whole planes come as 64-row boxes, the odd half plane as a 32-row box.  Accumulator d = q sits at TMEM column 64 q in both
+// CTAs, so the epilogue is the trimmed cluster path's.  tcgen05 instructions of one kernel must agree on the cta_group, hence a
+// separate kernel; the host cannot know the plane counts (they are device data), so it launches this kernel in front of the
+// cluster kernel and each of the two returns at once when the product is the other's (P.pair_first).
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+umma_ozaki2tp_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmA32,
+                     const __grid_constant__ CUtensorMap tmB128, const __grid_constant__ CUtensorMap tmB64, const __grid_constant__ CUtensorMap tmB32,
+                     int M, int N, int K, OzParams P) {
+    const int na = planes_of(P.pa, S, P.bits), nb = planes_of(P.pb, S, P.bits);
+    if ((na < nb ? na : nb) != 1) return;                         // not a one-plane product: the cluster kernel behind this launch runs it
+    constexpr int KB = 64, A_SLICE = BM2 * KB, HALF = (BN2 / 2) * KB, MAXST = 8, RING = 2 * (8 * A_SLICE + S * BN2 * KB);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + RING);
+    uint64_t *empty = full + MAXST;
+    uint64_t *tmem_full = empty + MAXST;
+    uint32_t *tmem_ptr = (uint32_t *)(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();                     // 0 = leader: issues every MMA of the pair
+    const bool swap = na != 1;                                     // op(B) is the one-plane operand: compute the tile of C^T
+    const int nbr = swap ? na : nb;
+    const int Rr = swap ? N : M, Cr = swap ? M : N;
+    const CUtensorMap *mapA = swap ? &tmB128 : &tmA128, *mapB64 = swap ? &tmA64 : &tmB64, *mapB32 = swap ? &tmA32 : &tmB32;
+    int rp, ct;
+    raster((int)(blockIdx.x / 2), Rr / (2 * BM2), Cr / BN2, P.group_m > 1 ? P.group_m / 2 : 1, rp, ct);
+    const int r0 = (rp * 2 + (int)crank) * BM2, c0 = ct * BN2;
+    const int kblocks = (K + KB - 1) / KB;
+    const int c1 = nbr < 4 ? nbr : 4, c2 = nbr - c1;              // planes per chunk: N = 64 c1 and 64 c2
+    const int stride = A_SLICE + nbr * HALF;
+    int nst = RING / stride;
+    if (nst > MAXST) nst = MAXST;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < MAXST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty[st], ph ^ 1);                    // the leader's commit released this stage in both CTAs
+                if (crank == 0) mbar_expect_tx(&full[st], (P.dbg & 1) ? 0 : 2 * stride);      // the bytes of BOTH CTAs land on the leader's barrier
+                if (!(P.dbg & 1)) {
+                    uint8_t *base = smem + st * stride;
+                    const int k0 = kb * KB;
+                    tma_load_3d_2sm(base, mapA, &full[st], k0, r0, 0);
+                    uint8_t *dst = base + A_SLICE;
+                    for (int chunk = 0; chunk < 2; ++chunk) {      // my half of each chunk's rows, in units of 32-row half planes
+                        const int c = chunk ? c2 : c1, plane0 = chunk ? 4 : 0;
+                        for (int h = (int)crank * c, h1 = h + c; h < h1;) {
+                            if (!(h & 1) && h + 1 < h1) { tma_load_3d_2sm(dst, mapB64, &full[st], k0, c0, plane0 + (h >> 1)); dst += 2 * HALF; h += 2; }
+                            else { tma_load_3d_2sm(dst, mapB32, &full[st], k0, c0 + 32 * (h & 1), plane0 + (h >> 1)); dst += HALF; h += 1; }
+                        }
+                    }
+                }
+                if (++st == nst) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && crank == 0) {
+            int st = 0; uint32_t ph = 0;
+            const uint32_t id1 = make_idesc_i8_pair(c1 * BN2), id2 = make_idesc_i8_pair(c2 * BN2);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[st], ph);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(smem + st * stride);
+                const uint64_t ad = make_desc_kb<KB>(a0), b1 = make_desc_kb<KB>(a0 + A_SLICE), b2 = make_desc_kb<KB>(a0 + A_SLICE + c1 * HALF);
+#pragma unroll
+                for (int k = 0; k < KB / 32; ++k) {
+                    const uint32_t accf = (kb > 0 || k > 0) ? 1u : 0u;
+                    tc_mma_i8_2sm(tmem_base, ad + 2 * k, b1 + 2 * k, id1, accf);
+                    if (c2) tc_mma_i8_2sm(tmem_base + 4 * BN2, ad + 2 * k, b2 + 2 * k, id2, accf);
+                }
+                tc_commit_2sm_mc(&empty[st], 0b11);               // frees the stage in both CTAs when these MMAs retire
+                if (++st == nst) { st = 0; ph ^= 1; }
+            }
+            tc_commit_2sm_mc(tmem_full, 0b11);
+            if (P.pairs && blockIdx.x == 0) atomicAdd(P.pairs, (unsigned long long)nbr);
+        }
+    } else {
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        if (P.dbg & 2) {}
+        else if (swap) oz2_epilogue<S, true>(tmem_base, warp & 3, (warp - 2) >> 2, lane, r0, c0, Rr, Cr, P, nbr, epi_role(P, true));
+        else oz2_epilogue<S, false>(tmem_base, warp & 3, (warp - 2) >> 2, lane, r0, c0, Rr, Cr, P, nbr, epi_role(P, false));
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                           // neither CTA frees TMEM / exits while the pair is still at work
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
 }  // namespace oz2
 
 }  // namespace umma
@@ -2037,7 +2155,7 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     static const bool trim = [] { const char *e = getenv("RDB_OZAKI_TRIM"); return !(e && e[0] == '0'); }();    // 0: every plane of every operand is multiplied
     OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m, ozaki_bits(), gslot, sa + ra, sa + 2 * ra, sb + rb, sb + 2 * rb, g_rho, g_h, g_drop, dbg,
                trim ? pwa : nullptr, trim ? pwb : nullptr, &G.guard_sum->pairs,
-               (((M + 63) / 64) % 2 == 0 && ((N + 63) / 64) % 2 == 0 && !getenv("RDB_OZAKI_NOSWAP")) ? 1 : 0};
+               (((M + 63) / 64) % 2 == 0 && ((N + 63) / 64) % 2 == 0 && !getenv("RDB_OZAKI_NOSWAP")) ? 1 : 0, 0};
     static int gen = -1;
     if (gen < 0) { const char *e = getenv("RDB_OZAKI_GEN"); gen = e ? atoi(e) : 2; }
     if (gen == 2 && nslices <= 8) {
@@ -2139,6 +2257,34 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
                     pc.attrs = pa; pc.numAttrs = 1;
                     return cudaLaunchKernelEx(&pc, umma_ozaki2cp_kernel<7>, mAmc, mB, mA1, mB1, Mi, Ni, Ki, P, m_tiles, n_groups);
                 }
+            }
+            // one-plane products go to the trimmed CTA-pair kernel, launched in front (it returns at once for every other product)
+            // (measured, profiles/trim_dbg.sh at 4096^3, (1, 7) planes: 0.85 ms per call against 0.72 for the trimmed cluster path - its
+            //  MMA skeleton is 0.08 ms faster but the cta_group::2 loads that complete on the leader's barrier cost 0.27 ms instead
+            //  of 0.06 => OFF unless RDB_OZAKI_TPAIR=1; kept for the tests and the next attempt)
+            static const bool tpair = [] { const char *e = getenv("RDB_OZAKI_TPAIR"); return e && e[0] == '1'; }();
+            if (tpair && trim && nslices == 7 && ozaki_bits() == 8 && cl == 2 && M % 256 == 0 && N % 256 == 0) {
+                CUtensorMap mA32, mB32;
+                if (!make_map(&mA32, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BN2 / 2, kbytes, 1, a_stride) ||
+                    !make_map(&mB32, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2 / 2, kbytes, 1, b_stride))
+                    return cudaErrorInvalidValue;
+                static bool attrtp = false;
+                if (!attrtp) {
+                    cudaError_t e = cudaFuncSetAttribute(umma_ozaki2tp_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_cluster(7, 2));
+                    if (e != cudaSuccess) return e;
+                    attrtp = true;
+                }
+                cudaLaunchConfig_t tc = {};
+                tc.gridDim = dim3((unsigned)(2 * (M / 256) * (N / 64))); tc.blockDim = dim3(OZ_THREADS);
+                tc.dynamicSmemBytes = smem_bytes_cluster(7, 2); tc.stream = st;
+                cudaLaunchAttribute ta_[1];
+                ta_[0].id = cudaLaunchAttributeClusterDimension;
+                ta_[0].val.clusterDim.x = 2; ta_[0].val.clusterDim.y = 1; ta_[0].val.clusterDim.z = 1;
+                tc.attrs = ta_; tc.numAttrs = 1;
+                cudaError_t e = cudaLaunchKernelEx(&tc, umma_ozaki2tp_kernel<7>, mA1, mA1n, mA32, mB1w, mB1, mB32, Mi, Ni, Ki, P);
+                if (e != cudaSuccess) return e;
+                P.pair_first = 1;
+                g_chunk_launches += 1;
             }
             if (nslices == 8) {
                 if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 2>, mAmc, mB, mA1, mB1, mA1n, mB1w, Mi, Ni, Ki, P);

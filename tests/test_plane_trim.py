@@ -30,7 +30,8 @@ def _operand(rng, rows, cols, bits):
 
 
 # (m, n, k): which kernel the dispatcher picks is noted per shape
-SHAPES = [(512, 512, 4096),      # cluster kernel, role swap allowed, row tiles even (either multicast geometry)
+SHAPES = [(512, 512, 4096),      # cluster kernel, role swap allowed, row tiles even (either multicast geometry); one-plane operands: CTA-pair kernel
+          (1024, 768, 2304),     # the same, rectangular (the pair kernel's tile walk differs between C and C^T)
           (384, 512, 2304),      # cluster kernel, 3 row tiles: the B-role multicast needs an even count and is not taken unswapped
           (448, 512, 2304),      # cluster kernel, odd number of 64-wide row tiles: no role swap
           (640, 448, 512),       # odd number of column tiles: single-CTA kernel
@@ -97,3 +98,15 @@ def test_cfg2_adjoint_of_sum_is_one_plane_and_results_do_not_change(tmp_path, n,
     else:
         assert int(on["pairs"]) * 168 == int(off["pairs"]) * 84 and int(on["pairs"]) > 0
     assert np.array_equal(on["ga"], off["ga"]) and np.array_equal(on["gb"], off["gb"]) and float(on["value"]) == float(off["value"])
+
+
+def test_trimmed_cta_pair_kernel_in_child_process():
+    """umma_ozaki2tp_kernel (cta_group::2, one-plane products) is off by default (slower, see umma.cu): rerun the exactness tests of the
+    shapes it takes with RDB_OZAKI_TPAIR=1."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    e = dict(os.environ); e["RDB_OZAKI_TPAIR"] = "1"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_plane_trim.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "test_trimmed_gemm_is_exact and (512-512-4096 or 1024-768-2304)", "-p", "no:cacheprovider"],
+                       cwd=os.path.dirname(here), env=e, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
