@@ -8,13 +8,17 @@ Metric (BASELINE.json): compiled-tape ``gradient!`` evals/s of ``f(a,b) = sum(a'
 
 * ``value``     device-resident inputs/results (D2D copies only), CUDA events, max over ranks.
 * ``e2e``       page-locked HOST inputs and HOST results, every step uploads its inputs and downloads its results; consecutive steps
-                pipelined over three engine copies of the tape (rd.GradientPipeline = rdb_gradient_async + rdb_tape_wait); the
+                pipelined over four engine copies of the tape (rd.GradientPipeline = rdb_gradient_async + rdb_tape_wait); the
                 one-synchronous-call-per-step number rides along (``e2e.synchronous_calls``), and ``e2e.host_link`` is the measured
                 host<->device copy bandwidth with every rank copying (the platform ceiling of this leg).
-* ``roofline``  dominant kernel (the tcgen05 int8-slice GEMM behind every FP64 ``*``): tensor-pipe operations issued per launch
-                (28 int8 products of 2 n^3) / CUDA-event time of the launches including their slicing passes, against
-                2 x the driver-measured bf16 burst (MEASURED_PEAKS.json); FP64-equivalent TFLOP/s next to a cuBLAS DGEMM measured in
-                the same run; ``traffic`` from the committed ncu capture named in profiles/traffic.json.
+* ``roofline``  dominant kernel (the tcgen05 int8-slice GEMM behind every FP64 ``*``): tensor-pipe operations issued per DENSE launch
+                (28 int8 products of 2 n^3: the two forward products) / CUDA-event time of those launches including the slicing
+                passes of both operands, against 2 x the driver-measured bf16 burst (MEASURED_PEAKS.json).  The four adjoint
+                products meet deriv(output) of `sum` - a constant fill with one live digit plane - and issue 7 slice pairs
+                (counted on the device, rdb_tape_slice_pairs); they are bound by operand delivery and reported under
+                ``roofline.launch_kinds``; ``other_configs.cfg2_without_plane_trimming`` is the same leg with every plane
+                multiplied.  FP64-equivalent TFLOP/s next to a cuBLAS DGEMM measured in the same run; ``traffic`` from the committed
+                ncu capture named in profiles/traffic.json.
 * ``cpu_baseline`` the oracle (reference-equivalent CPU replay, numpy/OpenBLAS) on the box's host cores.
 * N > 1: gradient! of one scalar function does not shard ("replicas only"): every rank replays its
   own tape copy, value = N evals / max-over-ranks time.  The same run then measures the paths that DO shard -
@@ -56,6 +60,7 @@ def parse():
                     help="FP64 `*` kernels: auto = exact int8 slices on tcgen05 where eligible (default), dmma = DMMA only")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extra", action="store_true", help="skip the jacobian!/hessian! legs")
+    ap.add_argument("--only-value", action="store_true", help="device-resident leg only: print {value, ms_per_step, parity} and exit")
     return ap.parse_args()
 
 
@@ -363,6 +368,14 @@ def main():
     tol = 1e-12 if args.dtype == "f64" else 1e-5
     if not err < tol:
         raise SystemExit(f"parity check failed: {err}")
+
+    if args.only_value:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms / args.steps, "max_rel_err_vs_closed_form": float(err),
+                              "gemm_guard": ct.handle.guard_stats()}), flush=True)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
 
     # ---- end-to-end leg: pinned host inputs and results --------------------------------------------
     def pinned(arr):
@@ -765,6 +778,23 @@ def other_configs(args, torch, rd, ctx):
     """The BASELINE configs that are not the headline, one short measurement each (rank 0, N = 1), so the driver's record holds
     them: cfg 1 (100 x 100, the only size the reference publishes a number for), cfg 2 in FP32, cfg 3 (MLP)."""
     out = {}
+    # the headline leg once more in a child process with plane trimming switched off (the knob is read once per process): every
+    # digit plane of every operand is multiplied, which is what a tape whose `*` adjoints are dense (no constant-fill
+    # deriv(output)) pays - the same-run number to hold next to `value`
+    if args.dtype == "f64" and args.gemm == "auto":
+        try:
+            import subprocess
+            e = dict(os.environ); e["RDB_OZAKI_TRIM"] = "0"
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--only-value", "--steps", str(max(5, args.steps // 2)), "--warmup", "3",
+                                "--n", str(args.n)], env=e, capture_output=True, text=True, timeout=300)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+            d = json.loads(line)
+            out["cfg2_without_plane_trimming"] = {"evals_per_s": d["value"], "ms_per_eval": d["ms_per_step"],
+                                                  "max_rel_err_vs_closed_form": d["max_rel_err_vs_closed_form"],
+                                                  "slice_pairs_per_eval": d["gemm_guard"]["slice_pairs"] / max(d["gemm_guard"]["checked"], 1) * 6,
+                                                  "how": "child process, RDB_OZAKI_TRIM=0: all 28 slice pairs of all six products"}
+        except Exception as ex:  # noqa: BLE001 - a reporting extra must not sink the bench line
+            out["cfg2_without_plane_trimming"] = {"error": repr(ex)[:200]}
 
     def timeit(step, steps, warm=3):
         for _ in range(warm):

@@ -1350,11 +1350,24 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
         } else if (warp == 1) {
             if (lane == 0) {
                 int st = 0; uint32_t ph = 0;
+                // one live A-role plane (the common trimmed product): the whole K-block is two merged MMAs per k-step, planes 0..3
+                // and 4..6 of the B role - issued from precomputed descriptors (the general loop's index arithmetic, ~100 dependent
+                // instructions of this one thread per K-block, took longer than the MMAs themselves)
+                const int c1 = nbr < 4 ? nbr : 4, c2 = nbr - c1;
+                const uint32_t id1 = make_idesc_i8(c1 * BN2), id2 = make_idesc_i8(c2 * BN2);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full[st], ph);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(smem + st * stride);
-                    oz2_issue_trimmed<S, KB>(a0, a0 + nar * A_SLICE, tmem_base, nar, nbr, kb == 0);
+                    if (nar == 1) {
+                        const uint64_t ad = make_desc_kb<KB>(a0), b1 = make_desc_kb<KB>(a0 + A_SLICE), b2 = make_desc_kb<KB>(a0 + A_SLICE + c1 * B_SLICE);
+#pragma unroll
+                        for (int k = 0; k < KB / 32; ++k) {
+                            const uint32_t accf = (kb > 0 || k > 0) ? 1u : 0u;
+                            tc_mma<KIND_I8>(tmem_base, ad + 2 * k, b1 + 2 * k, id1, accf);
+                            if (c2) tc_mma<KIND_I8>(tmem_base + 4 * BN2, ad + 2 * k, b2 + 2 * k, id2, accf);
+                        }
+                    } else oz2_issue_trimmed<S, KB>(a0, a0 + nar * A_SLICE, tmem_base, nar, nbr, kb == 0);
                     tc_commit_mc(&empty[st], MASK);
                     if (++st == nst) { st = 0; ph ^= 1; }
                 }
