@@ -34,12 +34,14 @@ SHAPES = [(512, 512, 4096),      # cluster kernel, role swap allowed, row tiles 
           (1024, 768, 2304),     # the same, rectangular (the pair kernel's tile walk differs between C and C^T)
           (384, 512, 2304),      # cluster kernel, 3 row tiles: the B-role multicast needs an even count and is not taken unswapped
           (448, 512, 2304),      # cluster kernel, odd number of 64-wide row tiles: no role swap
+          (512, 384, 640),       # swapped roles with an odd number of row tiles (the A-role multicast geometry)
+          (256, 512, 40960),     # three exact-int32 K-chunks, each sliced (and trimmed) on its own
           (640, 448, 512),       # odd number of column tiles: single-CTA kernel
           (2560, 2048, 1024)]    # short contraction, more tiles than resident clusters: persistent cluster kernel
 
 
 @pytest.mark.parametrize("m,n,k", SHAPES)
-@pytest.mark.parametrize("bits_a,bits_b", [(0, 40), (40, 0), (0, 0), (16, 16), (24, 8), (8, 24), (1, 33)])
+@pytest.mark.parametrize("bits_a,bits_b", [(0, 36), (36, 0), (0, 0), (16, 16), (24, 8), (8, 24), (1, 33)])
 @pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1)])
 def test_trimmed_gemm_is_exact(rd, ctx, m, n, k, bits_a, bits_b, ta, tb):
     import torch
