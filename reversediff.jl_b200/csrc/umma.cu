@@ -800,6 +800,7 @@ struct OzParams {
     unsigned long long *pairs;
     int allow_swap;                    // both tilings (C and C^T) have the same number of 2-CTA clusters: the kernel may swap the roles
     int pair_first;                    // umma_ozaki2tp_kernel was launched in front: one-plane products are its work, not the cluster kernel's
+    int wide;                          // trimmed cluster path: 128-byte K-blocks when the A role has one live plane
 };
 
 // |x - x~| <= 2^(e - bS - 1) per element (rint), |x| <= 2^e / 4 (b = 8) or 2^e / 2 (b = 7), and the slice pairs with p + q >= S
@@ -1262,7 +1263,8 @@ template <int S, int CL>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmA1n, const __grid_constant__ CUtensorMap tmB1w,
-                    int M, int N, int K, OzParams P) {
+                    const __grid_constant__ CUtensorMap tmA1x, const __grid_constant__ CUtensorMap tmB1x, const __grid_constant__ CUtensorMap tmA1nx,
+                    const __grid_constant__ CUtensorMap tmB1wx, int M, int N, int K, OzParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int KB = 64, STAGES2 = stages_for(KB), A_SLICE = BM2 * KB, B_SLICE = BN2 * KB;
@@ -1312,10 +1314,15 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
         //    column tiles - the dense geometry) or the B role (adjacent row tiles, same columns).
         //  * RING: a stage holds just the live planes, so the 184 KB of the two dense stages become up to 8 stages: the loads of a
         //    short K-block (a handful of MMAs) need that depth to cover the TMA round trip.
+        //  * WIDE K-BLOCKS: a one-plane A role moves 128 bytes of K per stage (128-byte swizzle, the tm*x maps) - half as many
+        //    boxes, barrier rounds and commits per byte (P.wide: 0 switches it off, timing experiments).
         const bool swap = P.allow_swap && nb < na;
         const int nar = swap ? nb : na, nbr = swap ? na : nb;
         const int Rr = swap ? N : M, Cr = swap ? M : N;
-        const CUtensorMap *mapA = swap ? &tmB1w : &tmA1, *mapB = swap ? &tmA1n : &tmB1;
+        const bool wide = nar == 1 && P.wide;
+        const int kbw = wide ? 128 : KB, a_slice = BM2 * kbw, b_slice = BN2 * kbw, kblocks_t = (K + kbw - 1) / kbw;
+        const CUtensorMap *mapA = wide ? (swap ? &tmB1wx : &tmA1x) : (swap ? &tmB1w : &tmA1);
+        const CUtensorMap *mapB = wide ? (swap ? &tmA1nx : &tmB1x) : (swap ? &tmA1n : &tmB1);
         const int RT = (Rr + BM2 - 1) / BM2, CT = (Cr + BN2 - 1) / BN2;
         const bool share_b = nbr * B_SLICE > nar * A_SLICE && RT % 2 == 0;
         const int cid = (int)(blockIdx.x + gridDim.x * (blockIdx.y / 2));
@@ -1323,7 +1330,7 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
         if (!share_b) { int rt, cg; raster(cid, RT, CT / 2, P.group_m, rt, cg); r_tile = rt; c_tile = cg * 2 + (int)crank; }
         else { int rp, ct; raster(cid, RT / 2, CT, P.group_m, rp, ct); r_tile = rp * 2 + (int)crank; c_tile = ct; }
         const int r0 = r_tile * BM2, c0 = c_tile * BN2;
-        const int stride = nar * A_SLICE + nbr * B_SLICE;
+        const int stride = nar * a_slice + nbr * b_slice;
         int nst = (STAGES2 * STAGE) / stride;
         if (nst > MAXST) nst = MAXST;
         if (warp == 0) {
@@ -1332,17 +1339,17 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
                 const int nsh = share_b ? nbr : nar, half = (nsh + 1) / 2;
                 const int sh0 = (int)crank * half, sh1 = sh0 + half < nsh ? sh0 + half : nsh;
                 int st = 0; uint32_t ph = 0;
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int kb = 0; kb < kblocks_t; ++kb) {
                     mbar_wait(&empty[st], ph ^ 1);
                     uint8_t *base = smem + st * stride;
                     if (P.dbg & 1) { mbar_expect_tx(&full[st], 0); if (++st == nst) { st = 0; ph ^= 1; } continue; }
                     mbar_expect_tx(&full[st], stride);
                     if (!share_b) {
-                        for (int p = sh0; p < sh1; ++p) tma_load_3d_mc(base + p * A_SLICE, mapA, &full[st], kb * KB, r0, p, MASK);
-                        for (int q = 0; q < nbr; ++q) tma_load_3d(base + nar * A_SLICE + q * B_SLICE, mapB, &full[st], kb * KB, c0, q);
+                        for (int p = sh0; p < sh1; ++p) tma_load_3d_mc(base + p * a_slice, mapA, &full[st], kb * kbw, r0, p, MASK);
+                        for (int q = 0; q < nbr; ++q) tma_load_3d(base + nar * a_slice + q * b_slice, mapB, &full[st], kb * kbw, c0, q);
                     } else {
-                        for (int p = 0; p < nar; ++p) tma_load_3d(base + p * A_SLICE, mapA, &full[st], kb * KB, r0, p);
-                        for (int q = sh0; q < sh1; ++q) tma_load_3d_mc(base + nar * A_SLICE + q * B_SLICE, mapB, &full[st], kb * KB, c0, q, MASK);
+                        for (int p = 0; p < nar; ++p) tma_load_3d(base + p * a_slice, mapA, &full[st], kb * kbw, r0, p);
+                        for (int q = sh0; q < sh1; ++q) tma_load_3d_mc(base + nar * a_slice + q * b_slice, mapB, &full[st], kb * kbw, c0, q, MASK);
                     }
                     if (++st == nst) { st = 0; ph ^= 1; }
                 }
@@ -1355,11 +1362,19 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
                 // instructions of this one thread per K-block, took longer than the MMAs themselves)
                 const int c1 = nbr < 4 ? nbr : 4, c2 = nbr - c1;
                 const uint32_t id1 = make_idesc_i8(c1 * BN2), id2 = make_idesc_i8(c2 * BN2);
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int kb = 0; kb < kblocks_t; ++kb) {
                     mbar_wait(&full[st], ph);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(smem + st * stride);
-                    if (nar == 1) {
+                    if (wide) {
+                        const uint64_t ad = make_smem_desc(a0), b1 = make_smem_desc(a0 + a_slice), b2 = make_smem_desc(a0 + a_slice + c1 * b_slice);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t accf = (kb > 0 || k > 0) ? 1u : 0u;
+                            tc_mma<KIND_I8>(tmem_base, ad + 2 * k, b1 + 2 * k, id1, accf);
+                            if (c2) tc_mma<KIND_I8>(tmem_base + 4 * BN2, ad + 2 * k, b2 + 2 * k, id2, accf);
+                        }
+                    } else if (nar == 1) {
                         const uint64_t ad = make_desc_kb<KB>(a0), b1 = make_desc_kb<KB>(a0 + A_SLICE), b2 = make_desc_kb<KB>(a0 + A_SLICE + c1 * B_SLICE);
 #pragma unroll
                         for (int k = 0; k < KB / 32; ++k) {
@@ -2168,7 +2183,8 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     static const bool trim = [] { const char *e = getenv("RDB_OZAKI_TRIM"); return !(e && e[0] == '0'); }();    // 0: every plane of every operand is multiplied
     OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m, ozaki_bits(), gslot, sa + ra, sa + 2 * ra, sb + rb, sb + 2 * rb, g_rho, g_h, g_drop, dbg,
                trim ? pwa : nullptr, trim ? pwb : nullptr, &G.guard_sum->pairs,
-               (((M + 63) / 64) % 2 == 0 && ((N + 63) / 64) % 2 == 0 && !getenv("RDB_OZAKI_NOSWAP")) ? 1 : 0, 0};
+               (((M + 63) / 64) % 2 == 0 && ((N + 63) / 64) % 2 == 0 && !getenv("RDB_OZAKI_NOSWAP")) ? 1 : 0, 0,
+               getenv("RDB_OZAKI_WIDE") ? atoi(getenv("RDB_OZAKI_WIDE")) : 1};
     static int gen = -1;
     if (gen < 0) { const char *e = getenv("RDB_OZAKI_GEN"); gen = e ? atoi(e) : 2; }
     if (gen == 2 && nslices <= 8) {
@@ -2186,6 +2202,12 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
         CUtensorMap mA1n, mB1w;       // the same planes with the box heights exchanged, for the role swap of the trimmed path
         if (!make_map(&mA1n, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BN2, kbytes, 1, a_stride) ||
             !make_map(&mB1w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BM2, kbytes, 1, b_stride))
+            return cudaErrorInvalidValue;
+        CUtensorMap mA1x, mB1x, mA1nx, mB1wx;   // one-plane boxes of 128 bytes of K (128-byte swizzle): wide K-blocks of the trimmed path
+        if (!make_map(&mA1x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BM2, 128, 1, a_stride) ||
+            !make_map(&mB1x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BN2, 128, 1, b_stride) ||
+            !make_map(&mA1nx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, As, Kp, M, nslices, BN2, 128, 1, a_stride) ||
+            !make_map(&mB1wx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, Bs, Kp, N, nslices, BM2, 128, 1, b_stride))
             return cudaErrorInvalidValue;
         dim3 grid2((unsigned)((M + BM2 - 1) / BM2), (unsigned)((N + BN2 - 1) / BN2));
         static int pair = -1;
@@ -2300,11 +2322,11 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
                 g_chunk_launches += 1;
             }
             if (nslices == 8) {
-                if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 2>, mAmc, mB, mA1, mB1, mA1n, mB1w, Mi, Ni, Ki, P);
-                return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 4>, mAmc, mB, mA1, mB1, mA1n, mB1w, Mi, Ni, Ki, P);
+                if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 2>, mAmc, mB, mA1, mB1, mA1n, mB1w, mA1x, mB1x, mA1nx, mB1wx, Mi, Ni, Ki, P);
+                return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<8, 4>, mAmc, mB, mA1, mB1, mA1n, mB1w, mA1x, mB1x, mA1nx, mB1wx, Mi, Ni, Ki, P);
             }
-            if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<7, 2>, mAmc, mB, mA1, mB1, mA1n, mB1w, Mi, Ni, Ki, P);
-            return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<7, 4>, mAmc, mB, mA1, mB1, mA1n, mB1w, Mi, Ni, Ki, P);
+            if (cl == 2) return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<7, 2>, mAmc, mB, mA1, mB1, mA1n, mB1w, mA1x, mB1x, mA1nx, mB1wx, Mi, Ni, Ki, P);
+            return cudaLaunchKernelEx(&cfg, umma_ozaki2c_kernel<7, 4>, mAmc, mB, mA1, mB1, mA1n, mB1w, mA1x, mB1x, mA1nx, mB1wx, Mi, Ni, Ki, P);
         }
 #define RDB_OZ2(SS)                                                                                                        \
     case SS: {                                                                                                             \
