@@ -76,6 +76,8 @@ int rdb_ctx_device(rdb_ctx *c) { return c->device; }
 static void ctx_enter(rdb_ctx *c) {
     cudaSetDevice(c->device);
     g_gemm = &c->gemm;
+    c->gemm.uniform.clear();     // "this deriv buffer is a constant fill" is knowledge of ONE sweep inside ONE call: another call, another
+                                 // tape of the context, or a freed and reused address must never find it
 }
 static void ctx_release(rdb_ctx *c) {
     if (!c || --c->refs > 0) return;
@@ -721,7 +723,14 @@ static bool dtake(rdb_tape *t, int b) {
     const int r = droot(t, b);
     const bool ow = t->dz[r] != 0;
     t->dz[r] = 0;
+    if (t->ctx && t->bufs[r].der) t->ctx->gemm.uniform_clear(t->bufs[r].der);   // about to be written: no longer known to be a fill
     return ow;
+}
+// deriv(b) was just OVERWRITTEN with one value in every element (adjoint of sum / mean, one seed): the int8 slicer may write its
+// digit planes from element 0 (GemmState::uniform); any later accumulation goes through dtake / dmaterialize and withdraws this
+static void dmark_uniform(rdb_tape *t, int b, int64_t R) {
+    const int r = droot(t, b);
+    if (R == 1 && t->dtype == RDB_F64 && t->ctx && t->bufs[r].der) t->ctx->gemm.uniform_set(t->bufs[r].der);
 }
 // before a partial / atomic accumulation, or any read from outside the sweep: make the storage really zero
 static int dmaterialize(rdb_tape *t, int b, int64_t R, bool mark_live) {
@@ -730,6 +739,7 @@ static int dmaterialize(rdb_tape *t, int b, int64_t R, bool mark_live) {
         CU(cudaMemsetAsync(t->bufs[r].der, 0, (size_t)(t->bufs[r].size * R) * t->es, S(t)));
         if (mark_live) t->dz[r] = 0;
     }
+    if (mark_live && t->ctx && t->bufs[r].der) t->ctx->gemm.uniform_clear(t->bufs[r].der);
     return RDB_OK;
 }
 
@@ -1249,6 +1259,7 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                                 const bool ow = dtake(t, A.in[a].rec.buffer);
                                 StepTimer tm(t, "sum+add_reverse", (ow ? 1.0 : 2.0) * ba.size * R * t->es, 0);
                                 KL(t, launch_acc_scalar<T>(S(t), (T *)ba.der, ba.size, R, delta, sg, ow));
+                                if (ow) dmark_uniform(t, A.in[a].rec.buffer, R);
                                 OK(acc_done(t, A.in[a].rec.buffer));
                             }
                             break;
@@ -1267,6 +1278,7 @@ static int reverse_pass(rdb_tape *t, int64_t R) {
                     const bool ow = dtake(t, I.in[0].rec.buffer);
                     StepTimer tm(t, "sum_reverse", (ow ? 1.0 : 2.0) * b.size * R * t->es, 0);
                     KL(t, launch_acc_scalar<T>(S(t), (T *)b.der, b.size, R, delta, scale, ow));
+                    if (ow) dmark_uniform(t, I.in[0].rec.buffer, R);
                     OK(acc_done(t, I.in[0].rec.buffer));
                 }
                 break;
@@ -1625,6 +1637,7 @@ static int seed_scalar_and_reverse(rdb_tape *t) {
     Buf &out = t->bufs[t->output];
     if (out.size != 1) return fail(RDB_EINVAL, "gradient! needs a scalar tape output");
     for (size_t b = 0; b < t->bufs.size(); ++b) t->dz[droot(t, (int)b)] = 1;   // unseed!(input); intermediates are zero by invariant
+    if (t->ctx) t->ctx->gemm.uniform.clear();                                    // no deriv buffer is known to be a fill any more
     KL(t, launch_fill<T>(S(t), (T *)out.der, 1, (T)1));                     // seed!(output)
     t->dz[droot(t, t->output)] = 0;
     return reverse_pass<T>(t, 1);
@@ -1788,6 +1801,7 @@ static int jacobian_impl(rdb_tape *t, int slot, int64_t rb, int64_t re, void *re
     for (int64_t i0 = rb; i0 < re; i0 += R) {
         const int64_t Rb = std::min(R, re - i0);
         for (size_t b = 0; b < t->bufs.size(); ++b) t->dz[droot(t, (int)b)] = 1;       // unseed!(input)
+        if (t->ctx) t->ctx->gemm.uniform.clear();                                    // no deriv buffer is known to be a fill any more
         KL(t, launch_seed_onehot<T>(S(t), (T *)out.der, m, Rb, i0));                    // seed!(output, i) for Rb rows
         t->dz[droot(t, t->output)] = 0;
         OK(reverse_pass<T>(t, Rb));
@@ -2259,6 +2273,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
     x.td = x_td_own;
     for (auto &b : t->bufs) if (b.alias_of >= 0) b.td = t->bufs[b.alias_of].td;
     for (size_t b = 0; b < t->bufs.size(); ++b) t->dz[droot(t, (int)b)] = 1;   // intermediates were physically unseeded
+    if (t->ctx) t->ctx->gemm.uniform.clear();                                    // no deriv buffer is known to be a fill any more
     t->dz[droot(t, xid)] = 0;                                                   // deriv(x) holds the gradient (zeros in a lean sweep)
     if (grad_out) CU(cudaMemcpyAsync(grad_out, x.der, (size_t)n * t->es, cudaMemcpyDefault, S(t)));
     if (!on_device && cols > 0)
@@ -2408,6 +2423,7 @@ static int hessian_entry(rdb_tape *t, int64_t cb, int64_t ce, void *result, int6
     t->launches += 1;
     // host-side state the sweep leaves behind (tail of hessian_impl)
     for (size_t b = 0; b < t->bufs.size(); ++b) t->dz[droot(t, (int)b)] = 1;
+    if (t->ctx) t->ctx->gemm.uniform.clear();                                    // no deriv buffer is known to be a fill any more
     t->dz[droot(t, t->inputs[0])] = 0;
     t->forward_valid = true;
     if (!t->async) CU(cudaStreamSynchronize(S(t)));

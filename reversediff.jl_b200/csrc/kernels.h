@@ -66,6 +66,14 @@ struct GemmState {
     bool no_cache = false;       // CUDA-graph tapes: every operand is sliced into the workspace on every replay (a cache hit
                                  // at capture time would freeze stale slices into the graph)
     // accuracy certificate of the int8-slice path (umma.cu, "guard"): per launch (max |alpha op(A) op(B)|, max error bound)
+    // device buffers the engine KNOWS to hold one value in every element right now (deriv(x) after the adjoint of sum/mean
+    // overwrote it with a fill): the slicer writes their digit planes from element 0 instead of reading the matrix (umma.cu
+    // k_slice_uniform - the same digits, scales and plane word the generic passes produce).  The engine adds an entry when it
+    // issues the fill and removes it before anything else may write the buffer (engine.cu: dtake / dmaterialize / sweep start).
+    std::vector<const void *> uniform;
+    void uniform_set(const void *p) { for (auto q : uniform) if (q == p) return; uniform.push_back(p); }
+    void uniform_clear(const void *p) { for (size_t i = 0; i < uniform.size(); ++i) if (uniform[i] == p) { uniform[i] = uniform.back(); uniform.pop_back(); return; } }
+    bool uniform_has(const void *p) const { for (auto q : uniform) if (q == p) return true; return false; }
     unsigned long long *guard = nullptr;      // device, kGuardSlots x 2 bit patterns of non-negative doubles
     GuardSummary *guard_sum = nullptr;        // device: accumulated by guard_fold
     GuardSummary *guard_host = nullptr;       // pinned host copy

@@ -710,6 +710,53 @@ __global__ void __launch_bounds__(128) k_slice_fused_kmajor(int8_t *__restrict__
     planes_publish_warp(reinterpret_cast<unsigned long long *>(scale_out) + 3 * (int64_t)rows, orv);
 }
 
+// A UNIFORM operand (every element equals src[0]; GemmState::uniform): all rows share one exponent and one digit string, so the
+// planes are fills: 117 MB of stores for a 4096^2 operand instead of 2 x 134 MB read and 117 MB written.  Same e,
+// X, digits, scale and plane word as k_row_absmax + k_row_exponent + k_slice_i8 on the materialised matrix; the 1-norm statistic
+// is K |v| instead of a running sum (it only feeds the error bound, with 1 % of slack).  Grid-stride over rows x Kp / 16.
+__global__ void __launch_bounds__(256) k_slice_uniform(int8_t *__restrict__ dst, const double *__restrict__ src, int rows, int K, int Kp,
+                                                       int nslices, int bits, double *__restrict__ scale_out) {
+    const double v = src[0], av = fabs(v);
+    const bool finite = av <= 1.7976931348623157e308;
+    const int e = (av > 0.0 && finite) ? ilogb(av) + (bits == 8 ? 3 : 2) : 0;
+    double m1, m2;
+    pow2_pair(bits * nslices - e, m1, m2);
+    const long long X = finite ? __double2ll_rn((v * m1) * m2) : 0LL;
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = tid; r < rows; r += nth) {
+        scale_out[r] = finite ? (av > 0.0 ? scalbn(1.0, e) : 0.0) : __longlong_as_double(0x7FF8000000000000LL);
+        scale_out[rows + r] = (finite && av > 0.0) ? 1.01 * scalbn((double)K * av, -e) : 0.0;
+        scale_out[2 * (int64_t)rows + r] = av != 0.0 ? (double)K : 0.0;
+    }
+    if (tid == 0) reinterpret_cast<unsigned long long *>(scale_out)[3 * (int64_t)rows] = K > 0 ? (unsigned long long)X : 0ull;
+    // digit of plane p (p = 0 leading), as store_digits8 / the digit loop cut it
+    const int radix = 1 << bits, half = radix >> 1;
+    long long Y = X;
+    int digit[OZ_MAX_SLICES];
+    for (int sidx = nslices - 1; sidx >= 0; --sidx) {
+        int d = (int)(Y & (long long)(radix - 1));
+        Y >>= bits;
+        if (sidx > 0 && d >= half) { d -= radix; Y += 1; }
+        if (sidx == 0) d = (int)((Y << bits) | d);
+        digit[sidx] = d;
+    }
+    const int64_t plane = (int64_t)rows * Kp, words_per_row = Kp / 16, nwords = (int64_t)rows * words_per_row;
+    for (int p = 0; p < nslices; ++p) {                                  // every plane: not every GEMM kernel reads the plane word
+        const uint32_t b = (uint32_t)(uint8_t)(int8_t)digit[p], w = b * 0x01010101u;
+        uint4 *out = reinterpret_cast<uint4 *>(dst + p * plane);
+        for (int64_t i = tid; i < nwords; i += nth) {
+            const int k0 = (int)(i % words_per_row) * 16;
+            uint4 o = make_uint4(w, w, w, w);
+            if (k0 + 16 > K) {                                          // zero padding behind K
+                uint32_t t[4] = {w, w, w, w};
+                for (int j = 0; j < 16; ++j) if (k0 + j >= K) t[j >> 2] &= ~(0xFFu << (8 * (j & 3)));
+                o = make_uint4(t[0], t[1], t[2], t[3]);
+            }
+            out[i] = o;
+        }
+    }
+}
+
 // Column-major source (rows strided by ld... i.e. consecutive ROWS are contiguous, k strided): tile of 128 rows x 32 k, so every
 // column read is 1 KB contiguous (the 32-row x 128-k tile of the generic kernel reads 256-byte pieces 32 KB apart: every piece a
 // different DRAM page).  Transposed through shared memory ([k % 4][k / 4][row]); a thread then owns 4 rows x 4 consecutive k and
@@ -1982,6 +2029,12 @@ static int slice_operand(cudaStream_t st, const double *src, int64_t ld, int64_t
                          int8_t *q, int *e, double *sc) {      // returns the number of kernels launched
     const int bits = ozaki_bits();
     using namespace umma;
+    static const bool uniform_on = [] { const char *e = getenv("RDB_SLICE_UNIFORM"); return !(e && e[0] == '0'); }();
+    if (uniform_on && gemm_state().uniform_has(src) && Kp % 16 == 0 && ((uintptr_t)q & 15) == 0) {
+        // every element of this operand equals src[0] (the engine's word for it): planes as fills, no read of the matrix
+        k_slice_uniform<<<148 * 4, 256, 0, st>>>(q, src, (int)rows, (int)K, (int)Kp, ns, bits, sc);
+        return 1;
+    }
     // k-contiguous rows that fit shared memory and are 16-byte aligned: the one-pass kernel
     static const bool fused_on = [] { const char *e = getenv("RDB_SLICE_FUSED"); return !(e && e[0] == '0'); }();
     // (measured: a win while four rows fit 64 KB so several CTAs share an SM - the MLP config's K = 1024 operands, 12.04 -> 11.85 ms;

@@ -72,7 +72,8 @@ rd = graft.load_package()
 n = {n}
 rng = np.random.default_rng(5)
 a0, b0 = rng.random((n, n)), rng.random((n, n))
-tape = rd.GradientTape(rd.workloads.f_gradient_example, (a0, b0))
+f = rd.workloads.f_gradient_example if {objective!r} == "sum" else (lambda a, b: rd.mean(a.T @ b + a @ b.T))
+tape = rd.GradientTape(f, (a0, b0))
 ct = rd.compile(tape, use_graph={graph})
 a, b = rng.standard_normal((n, n)), rng.standard_normal((n, n))
 ga, gb = np.zeros((n, n), order="F"), np.zeros((n, n), order="F")
@@ -90,7 +91,7 @@ def test_cfg2_adjoint_of_sum_is_one_plane_and_results_do_not_change(tmp_path, n,
     for trim in ("1", "0"):
         out = str(tmp_path / f"trim{trim}.npz")
         e = dict(os.environ); e["RDB_OZAKI_TRIM"] = trim
-        r = subprocess.run([sys.executable, "-c", _CHILD.format(root=root, n=n, out=out, graph=graph, reps=3 if graph else 1)], env=e, capture_output=True, text=True, timeout=600)
+        r = subprocess.run([sys.executable, "-c", _CHILD.format(root=root, n=n, out=out, graph=graph, reps=3 if graph else 1, objective="sum")], env=e, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
         outs[trim] = np.load(out)
     on, off = outs["1"], outs["0"]
@@ -112,3 +113,23 @@ def test_trimmed_cta_pair_kernel_in_child_process():
                        cwd=os.path.dirname(here), env=e, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+@pytest.mark.parametrize("objective,n,graph", [("sum", 512, 0), ("mean", 512, 0), ("mean", 256, 1)])
+def test_uniform_adjoint_is_sliced_from_one_element_with_the_same_result(tmp_path, objective, n, graph):
+    """deriv(x) right after the adjoint of sum / mean is a constant fill and the engine knows it (GemmState::uniform): its digit planes
+    are written from element 0 (k_slice_uniform) instead of being cut from the matrix.  Same digits, same scales, same plane word -
+    the gradient must equal, bit for bit, the one of a process that always runs the generic slicing passes (RDB_SLICE_UNIFORM=0).
+    `mean` makes the fill value 1/n^2: a full-width mantissa, every plane live."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for uni in ("1", "0"):
+        out = str(tmp_path / f"uni{uni}.npz")
+        e = dict(os.environ); e["RDB_SLICE_UNIFORM"] = uni
+        r = subprocess.run([sys.executable, "-c", _CHILD.format(root=root, n=n, out=out, graph=graph, reps=3 if graph else 1, objective=objective)],
+                           env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        outs[uni] = np.load(out)
+    on, off = outs["1"], outs["0"]
+    assert int(on["pairs"]) == int(off["pairs"]) and int(on["pairs"]) > 0
+    assert np.array_equal(on["ga"], off["ga"]) and np.array_equal(on["gb"], off["gb"]) and float(on["value"]) == float(off["value"])
