@@ -845,7 +845,7 @@ struct OzParams {
     // plane words of op(A) / op(B) (planes_publish_*; NULL = every plane is live) and the running count of slice pairs issued
     const unsigned long long *pa, *pb;
     unsigned long long *pairs;
-    int allow_swap;                    // both tilings (C and C^T) have the same number of 2-CTA clusters: the kernel may swap the roles
+    int allow_swap;                    // the trimmed path may swap the roles (both tilings have the same number of 2-CTA clusters: column tiles are padded to pairs)
     int pair_first;                    // umma_ozaki2tp_kernel was launched in front: one-plane products are its work, not the cluster kernel's
     int wide;                          // trimmed cluster path: 128-byte K-blocks when the A role has one live plane
 };
@@ -1371,10 +1371,12 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
         const CUtensorMap *mapA = wide ? (swap ? &tmB1wx : &tmA1x) : (swap ? &tmB1w : &tmA1);
         const CUtensorMap *mapB = wide ? (swap ? &tmA1nx : &tmB1x) : (swap ? &tmA1n : &tmB1);
         const int RT = (Rr + BM2 - 1) / BM2, CT = (Cr + BN2 - 1) / BN2;
-        const bool share_b = nbr * B_SLICE > nar * A_SLICE && RT % 2 == 0;
+        const bool share_b = nbr * B_SLICE > nar * A_SLICE && RT % 2 == 0 && CT % 2 == 0;
         const int cid = (int)(blockIdx.x + gridDim.x * (blockIdx.y / 2));
         int r_tile, c_tile;
-        if (!share_b) { int rt, cg; raster(cid, RT, CT / 2, P.group_m, rt, cg); r_tile = rt; c_tile = cg * 2 + (int)crank; }
+        // (an odd number of column tiles is padded to whole clusters: the extra CTA loads zeros - TMA fills what lies outside the
+        //  tensor - and its epilogue stores nothing)
+        if (!share_b) { int rt, cg; raster(cid, RT, (CT + 1) / 2, P.group_m, rt, cg); r_tile = rt; c_tile = cg * 2 + (int)crank; }
         else { int rp, ct; raster(cid, RT / 2, CT, P.group_m, rp, ct); r_tile = rp * 2 + (int)crank; c_tile = ct; }
         const int r0 = r_tile * BM2, c0 = c_tile * BN2;
         const int stride = nar * a_slice + nbr * b_slice;
@@ -2236,7 +2238,7 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
     static const bool trim = [] { const char *e = getenv("RDB_OZAKI_TRIM"); return !(e && e[0] == '0'); }();    // 0: every plane of every operand is multiplied
     OzParams P{C, ldc, alpha, beta, sa, sb, nslices, group_m, ozaki_bits(), gslot, sa + ra, sa + 2 * ra, sb + rb, sb + 2 * rb, g_rho, g_h, g_drop, dbg,
                trim ? pwa : nullptr, trim ? pwb : nullptr, &G.guard_sum->pairs,
-               (((M + 63) / 64) % 2 == 0 && ((N + 63) / 64) % 2 == 0 && !getenv("RDB_OZAKI_NOSWAP")) ? 1 : 0, 0,
+               getenv("RDB_OZAKI_NOSWAP") ? 0 : 1, 0,
                getenv("RDB_OZAKI_WIDE") ? atoi(getenv("RDB_OZAKI_WIDE")) : 1};
     static int gen = -1;
     if (gen < 0) { const char *e = getenv("RDB_OZAKI_GEN"); gen = e ? atoi(e) : 2; }
@@ -2291,6 +2293,10 @@ static cudaError_t ozaki_chunk(cudaStream_t st, bool ta, bool tb, int64_t M, int
         }
         static int cl = -1;
         if (cl < 0) { const char *e = getenv("RDB_OZAKI_CLUSTER"); cl = e ? atoi(e) : 2; if (cl != 1 && cl != 2 && cl != 4) cl = 1; }
+        // 2-CTA clusters take any number of column tiles: an odd count is padded with one idle tile column (its loads lie outside the
+        // tensor and arrive as zeros, its stores are masked), so panels and ragged shapes run the cluster kernel - and its trimmed
+        // path - too
+        if (cl == 2 && (nslices == 8 || nslices == 7) && kbytes == 64 && (grid2.y & 1) && !getenv("RDB_OZAKI_NOPAD")) grid2.y += 1;
         if ((nslices == 8 || nslices == 7) && kbytes == 64 && cl > 1 && grid2.y % cl == 0) {
             // cluster of `cl` CTAs along n sharing the A stage through TMA multicast
             CUtensorMap mAmc;
