@@ -53,22 +53,34 @@ class AbstractTape:
         self.func = func
         self.is_tuple = isinstance(input_, (tuple, list))
         xs = list(input_) if self.is_tuple else [input_]
-        # record-time inputs that already live on the device (torch CUDA tensors, same shape conventions as at replay: an N-D
-        # tensor of the recorded shape, column-major strides or not - only values and shape matter here): recording is host work in
-        # the reference too (operator overloading on TrackedArray), so their values come over once, now; replays then take and
-        # return device arrays without any host copy (`is_device`)
-        xs = [x.detach().cpu().numpy() if _engine._is_device(x) else x for x in xs]
+        # Record-time inputs that already live on the device (torch CUDA tensors, same shape conventions as at replay: an N-D
+        # tensor of the recorded shape).  When EVERY input is a device array the tape is recorded SHAPES-ONLY (SURVEY section 8 f.4,
+        # TrackedArray{V,D,N,VA,DA} with device storage, src/tracked.jl:70-87): no element of any input crosses to the host, the
+        # operator-overloading pass runs on zero-stride placeholders and infers shapes (tracked.InstructionTape.shapes_only), and
+        # the values the reference's recording pass would have computed come out of the first forward sweep on the device.  The
+        # program is the same byte for byte (it never depended on values); a function whose control flow depends on values cannot
+        # be recorded this way and says so.  Mixed host/device inputs keep the old route: device values are copied over once.
+        shapes_only = len(xs) > 0 and all(_engine._is_device(x) for x in xs)
+        if shapes_only and dtype is None:
+            names = {str(x.dtype).replace("torch.", "") for x in xs}
+            dtype = np.float32 if names == {"float32"} else np.float64
+        if shapes_only:
+            from .tracked import placeholder
+            xs = [placeholder(tuple(x.shape), np.dtype(dtype)) for x in xs]
+        else:
+            xs = [x.detach().cpu().numpy() if _engine._is_device(x) else x for x in xs]
         if dtype is None:
             dtype = np.result_type(*[np.asarray(x).dtype for x in xs])
             if dtype not in (np.float32, np.float64):
                 dtype = np.float64
         self.tape = InstructionTape(dtype)
+        self.tape.shapes_only = shapes_only
         prog = self.tape.program
         # GradientConfig(input): track(similar(x), D, tp) then track!(cfg.input, input)
         # (api/Config.jl:37,45-47 ; tracked.jl:476-478)
         self.input = []
         for x in xs:
-            v = np.array(x, dtype=self.tape.dtype, order="F", copy=True)
+            v = x if shapes_only else np.array(x, dtype=self.tape.dtype, order="F", copy=True)
             if v.ndim == 0:
                 raise TypeError("tape inputs must be arrays")
             b = prog.add_buffer(P.BUF_TA, v.shape)

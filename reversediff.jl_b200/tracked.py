@@ -40,6 +40,11 @@ class InstructionTape:
             raise TypeError("only Float64 and Float32 tapes are supported")
         self.dtype = dtype
         self.program = P.TapeProgram(code)
+        # shapes_only: the tape is being recorded from DEVICE arrays (api.AbstractTape): no array element exists on the host, values
+        # are zero-stride placeholders of the right shape and every record_* below infers the output shape instead of computing the
+        # output (the program does not depend on values; the first forward sweep on the device produces them).  Anything that
+        # would need a value - comparisons of TrackedReals, i.e. value-dependent control flow - raises.
+        self.shapes_only = False
 
     def __len__(self):
         return len(self.program.instrs)
@@ -150,7 +155,7 @@ class TrackedArray:
 
     def __neg__(self):
         tp = self.tape
-        out = _track_new(-self.value, tp)
+        out = _track_new(lambda: -self.value, tp, shape=self.shape)
         tp.record(P.OP_NEG, [_capture(self, tp)], out.buffer)
         return out
 
@@ -227,12 +232,18 @@ class TrackedReal:
 
     # SkipOptimize'd predicates (derivatives/scalars.jl:24-46): evaluated on values, nothing recorded — which is why a
     # compiled tape freezes the branch taken at record time (docs/src/api.md:39-44)
-    def __lt__(self, o): return self.value < value(o)
-    def __le__(self, o): return self.value <= value(o)
-    def __gt__(self, o): return self.value > value(o)
-    def __ge__(self, o): return self.value >= value(o)
-    def __eq__(self, o): return self.value == value(o)
-    def __ne__(self, o): return self.value != value(o)
+    def _cmp_value(self):
+        if self.tape is not None and getattr(self.tape, "shapes_only", False):
+            raise TypeError("value-dependent control flow on a tape recorded from device arrays: no values exist on the host "
+                            "(record from host arrays instead)")
+        return self.value
+
+    def __lt__(self, o): return self._cmp_value() < value(o)
+    def __le__(self, o): return self._cmp_value() <= value(o)
+    def __gt__(self, o): return self._cmp_value() > value(o)
+    def __ge__(self, o): return self._cmp_value() >= value(o)
+    def __eq__(self, o): return self._cmp_value() == value(o)
+    def __ne__(self, o): return self._cmp_value() != value(o)
     __hash__ = object.__hash__
 
     def __float__(self):
@@ -292,7 +303,10 @@ def record_scalar(expr, a, b=None):
     eid = blk.expr(ops, fc, len(args))
     oa = _scalar_operand(blk, a, tp)
     ob = (P.SP_NONE, 0) if b is None else _scalar_operand(blk, b, tp)
-    v = E.eval_value((np.asarray(ops, np.int32).reshape(-1, 4), fc), [np.asarray(value(x), tp.dtype) for x in args], tp.dtype)
+    if tp.shapes_only:
+        v = np.zeros((), tp.dtype)                 # no values on the host (device recording): the block evaluates on the device
+    else:
+        v = E.eval_value((np.asarray(ops, np.int32).reshape(-1, 4), fc), [np.asarray(value(x), tp.dtype) for x in args], tp.dtype)
     slot = blk.push(eid, oa, ob)
     return TrackedReal(v[()], tp, -1, 0, blk, slot)
 
@@ -405,7 +419,24 @@ def _tape_of(*xs):
     raise TypeError("no tracked argument")
 
 
-def _track_new(v, tp: InstructionTape):
+def placeholder(shape, dtype):
+    """A read-only array of the given shape that owns ONE element (all strides zero): what a shapes-only tape holds as values."""
+    shape = tuple(int(d) for d in shape)
+    return np.lib.stride_tricks.as_strided(np.zeros(1, dtype), shape=shape, strides=(0,) * len(shape), writeable=False)
+
+
+def _track_new(v, tp: InstructionTape, shape=None):
+    """Track a freshly computed value.  ``v`` may be a thunk (called only when the tape records values); ``shape`` is the output
+    shape a shapes-only tape needs instead."""
+    if tp.shapes_only:
+        if shape is None:
+            raise TypeError("internal: this instruction has no shape rule for shapes-only recording")
+        shape = tuple(int(d) for d in shape)
+        if len(shape) == 0:
+            return TrackedReal(tp.dtype.type(0), tp, tp.program.add_buffer(P.BUF_TR, ()))
+        return TrackedArray(placeholder(shape, tp.dtype), tp, tp.program.add_buffer(P.BUF_TA, shape))
+    if callable(v):
+        v = v()
     v = np.asarray(v, tp.dtype)
     if v.ndim == 0:
         return TrackedReal(v[()], tp, tp.program.add_buffer(P.BUF_TR, ()))
@@ -453,7 +484,10 @@ def record_mul(x, y):
     vx, vy = np.asarray(value(x)), np.asarray(value(y))
     if vx.ndim not in (1, 2) or vy.ndim not in (1, 2):
         raise TypeError("`*` is defined for vectors and matrices")
-    out = _track_new(vx @ vy, tp)
+    if vx.shape[-1] != vy.shape[0]:
+        raise ValueError(f"`*`: inner dimensions do not match: {vx.shape} x {vy.shape}")
+    oshape = (vx.shape[:-1] if vx.ndim == 2 else ()) + (vy.shape[1:] if vy.ndim == 2 else ())
+    out = _track_new(lambda: vx @ vy, tp, shape=oshape)
     if isinstance(out, TrackedReal):
         raise TypeError("scalar-valued `*` (row vector times vector) is not lowered; use dot/sum")
     tp.record(P.OP_MUL, [_capture(x, tp), _capture(y, tp)], out.buffer)
@@ -469,7 +503,7 @@ def record_plusminus(opcode, x, y):
     vx, vy = np.asarray(value(x)), np.asarray(value(y))
     if vx.shape != vy.shape:
         raise ValueError("array +/- needs equal shapes (use broadcast('+', a, b) otherwise)")
-    out = _track_new(vx + vy if opcode == P.OP_ADD else vx - vy, tp)
+    out = _track_new(lambda: vx + vy if opcode == P.OP_ADD else vx - vy, tp, shape=vx.shape)
     tp.record(opcode, [_capture(x, tp), _capture(y, tp)], out.buffer)
     return out
 
@@ -485,7 +519,7 @@ def sum(x, dims=None):  # noqa: A001 - mirrors Base.sum
     if dims is not None:
         return record_sum_dims(x, dims)
     tp = x.tape
-    out = _track_new(np.sum(x.value), tp)
+    out = _track_new(lambda: np.sum(x.value), tp, shape=())
     tp.record(P.OP_SUM, [_capture(x, tp)], out.buffer)
     return out
 
@@ -495,7 +529,7 @@ def mean(x):
     if not isinstance(x, TrackedArray):
         return np.mean(x)
     tp = x.tape
-    out = _track_new(np.mean(x.value), tp)
+    out = _track_new(lambda: np.mean(x.value), tp, shape=())
     tp.record(P.OP_MEAN, [_capture(x, tp)], out.buffer)
     return out
 
@@ -505,7 +539,8 @@ def record_sum_dims(x, dims):
     if any(d < 1 or d > x.ndim for d in dims):
         raise ValueError("sum: dims out of range")
     tp = x.tape
-    out = _track_new(np.sum(x.value, axis=tuple(d - 1 for d in dims), keepdims=True), tp)
+    out = _track_new(lambda: np.sum(x.value, axis=tuple(d - 1 for d in dims), keepdims=True), tp,
+                     shape=tuple(1 if (i + 1) in dims else n for i, n in enumerate(x.shape)))
     # cache = index_bound(out, x)   (reductions.jl:43)
     tp.record(P.OP_SUMDIMS, [P.Operand(x.buffer, P.CLS_TA, True, x.shape, bound=out.shape)], out.buffer)
     return out
@@ -519,7 +554,7 @@ def dot(x, y):
     vx, vy = np.asarray(value(x)), np.asarray(value(y))
     if vx.size != vy.size:
         raise ValueError("dot needs equal lengths")
-    out = _track_new(np.dot(vx.reshape(-1, order="F"), vy.reshape(-1, order="F")), tp)
+    out = _track_new(lambda: np.dot(vx.reshape(-1, order="F"), vy.reshape(-1, order="F")), tp, shape=())
     tp.record(P.OP_DOT, [_capture(x, tp), _capture(y, tp)], out.buffer)
     return out
 
@@ -557,8 +592,10 @@ def _record_elementwise(opcode, f, args, require_same_shape=False):
         dual = [True] * len(args)
     flavor = 1 if opcode == P.OP_TRACKER_BCAST else (2 if opcode == P.OP_BCAST_POW else 0)
     ex = E.trace(f, len(args), dual=dual, pow_flavor=flavor)
-    vals = [np.asarray(value(a), tp.dtype).reshape(p, order="F") for a, p in zip(args, padded)]
-    out = _track_new(np.broadcast_to(E.eval_value(ex, vals, tp.dtype), oshape), tp)
+    def values():
+        vals = [np.asarray(value(a), tp.dtype).reshape(p, order="F") for a, p in zip(args, padded)]
+        return np.broadcast_to(E.eval_value(ex, vals, tp.dtype), oshape)
+    out = _track_new(values, tp, shape=oshape)
     ops = [_capture(a, tp, bound_to=oshape) for a in args]
     tp.record(opcode, ops, out.buffer, ex, len(args))
     return out
@@ -629,7 +666,7 @@ def record_getindex(t: TrackedArray, key):
         lin = np.arange(t.size, dtype=np.int64).reshape(t.shape, order="F")
         m = np.asarray([lin[k] for k in key], dtype=np.int64)
         tp = t.tape
-        out = _track_new(t.value.reshape(-1, order="F")[m], tp)
+        out = _track_new(lambda: t.value.reshape(-1, order="F")[m], tp, shape=m.shape)
         tp.record(P.OP_GETINDEX, [P.Operand(t.buffer, P.CLS_TA, True, t.shape, P.IDX_EXPLICIT, m)], out.buffer)
         return out
     if not isinstance(key, tuple):
@@ -644,7 +681,7 @@ def record_getindex(t: TrackedArray, key):
             if len(key) != t.ndim:
                 raise IndexError("wrong number of indices")
             lin = int(np.ravel_multi_index(tuple(int(k) % d for k, d in zip(key, t.shape)), t.shape, order="F"))
-        return TrackedReal(t.value.reshape(-1, order="F")[lin], t.tape, t.buffer, lin)
+        return TrackedReal(t.tape.dtype.type(0) if t.tape.shapes_only else t.value.reshape(-1, order="F")[lin], t.tape, t.buffer, lin)
     generic = not all(isinstance(k, slice) for k in key)
     if generic:
         # (getindex, Val(:generic)): Integer / Colon / integer-vector per dimension (tracked.jl:352-362)
@@ -664,7 +701,7 @@ def record_getindex(t: TrackedArray, key):
             sub = lin[key]
     m = np.ascontiguousarray(sub.reshape(-1, order="F"))
     tp = t.tape
-    out = _track_new(t.value.reshape(-1, order="F")[m].reshape(sub.shape, order="F"), tp)
+    out = _track_new(lambda: t.value.reshape(-1, order="F")[m].reshape(sub.shape, order="F"), tp, shape=sub.shape)
     op = P.Operand(t.buffer, P.CLS_TA, True, t.shape, P.IDX_EXPLICIT, m)
     tp.record(P.OP_GETINDEX_GENERIC if generic else P.OP_GETINDEX, [op], out.buffer)
     return out
