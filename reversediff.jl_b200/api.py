@@ -59,16 +59,16 @@ class AbstractTape:
         # operator-overloading pass runs on zero-stride placeholders and infers shapes (tracked.InstructionTape.shapes_only), and
         # the values the reference's recording pass would have computed come out of the first forward sweep on the device.  The
         # program is the same byte for byte (it never depended on values); a function whose control flow depends on values cannot
-        # be recorded this way and says so.  Mixed host/device inputs keep the old route: device values are copied over once.
-        shapes_only = len(xs) > 0 and all(_engine._is_device(x) for x in xs)
+        # be recorded this way and says so.
+        shapes_only = any(_engine._is_device(x) for x in xs)      # (host inputs of such a tape are not read either: replay supplies every value)
         if shapes_only and dtype is None:
             names = {str(x.dtype).replace("torch.", "") for x in xs}
-            dtype = np.float32 if names == {"float32"} else np.float64
+            dtype = np.float32 if names == {"float32"} else np.float64     # (np.result_type of the reference's promote rules: any Float64 wins)
         if shapes_only:
             from .tracked import placeholder
             xs = [placeholder(tuple(x.shape), np.dtype(dtype)) for x in xs]
         else:
-            xs = [x.detach().cpu().numpy() if _engine._is_device(x) else x for x in xs]
+            xs = [np.asarray(x) for x in xs]
         if dtype is None:
             dtype = np.result_type(*[np.asarray(x).dtype for x in xs])
             if dtype not in (np.float32, np.float64):
@@ -149,10 +149,16 @@ class HessianTape(AbstractTape):
         from .nested import record_gradient_program
         self.func = func
         self.is_tuple = False
-        v = np.array(input_, dtype=np.float64 if dtype is None else dtype, order="F", copy=True)
+        dev_in = _engine._is_device(input_)
+        if dev_in:                                               # device input: shapes-only, as in AbstractTape.__init__
+            dt = np.dtype(dtype) if dtype is not None else np.dtype(np.float32 if str(input_.dtype).endswith("float32") else np.float64)
+            v = np.zeros(tuple(input_.shape), dt, order="F")     # (the nested recorder indexes element by element: a real array of zeros)
+        else:
+            v = np.array(input_, dtype=np.float64 if dtype is None else dtype, order="F", copy=True)
         if v.dtype not in (np.float32, np.float64):
             v = v.astype(np.float64)
         self.tape = InstructionTape(v.dtype)                     # jtp: the tape that is kept (api/tape.jl:288)
+        self.tape.shapes_only = dev_in
         prog = self.tape.program
         b = prog.add_buffer(P.BUF_TA, v.shape)
         prog.inputs.append(b)

@@ -76,3 +76,19 @@ def test_value_dependent_control_flow_is_refused(rd):
     rd.GradientTape(f, x)                                 # from host arrays: fine (the branch taken is frozen into the tape, as in the reference)
     with pytest.raises(TypeError, match="value-dependent control flow"):
         rd.GradientTape(f, Dev(x))
+
+
+def test_mixed_host_and_device_inputs_record_shapes_only_too(rd):
+    rng = np.random.default_rng(1)
+    a0, b0 = rng.random((40, 40)), rng.random((40, 40))
+    host = rd.GradientTape(rd.workloads.f_gradient_example, (a0, b0))
+    mixed = rd.GradientTape(rd.workloads.f_gradient_example, (Dev(a0), b0))
+    assert mixed.tape.shapes_only and mixed.program_bytes() == host.program_bytes()
+
+
+def test_nested_hessian_recording_from_a_device_array(rd):
+    """`HessianTape(mode="reverse")` - the reference's own reverse-over-reverse scalar tape (nested.py) - from a device input."""
+    x = rd.workloads.inputs_rosenbrock(16)
+    host = rd.HessianTape(rd.workloads.f_rosenbrock_loop, x, mode="reverse")
+    dev = rd.HessianTape(rd.workloads.f_rosenbrock_loop, Dev(x), mode="reverse")
+    assert dev.tape.shapes_only and dev.program_bytes() == host.program_bytes()
