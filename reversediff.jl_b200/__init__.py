@@ -5,8 +5,9 @@ The directory name carries a dot (fixed by the repo layout contract), so it is i
 ``reversediff_jl_b200``.
 
 Scope: ONLY the compiled-tape replay path — ``compile`` + ``gradient!/jacobian!/hessian!(result,
-tape, input)`` — see DESIGN.md.  Recording happens on the host (``tracked.py``), replay happens in
-``csrc/librdb200.so`` (hand-written sm_100a CUDA) through the C ABI of ``include/rdb200.h``.
+tape, input)`` — see DESIGN.md.  Recording is the host's operator-overloading pass (``tracked.py``; shapes-only when the inputs
+are device arrays: no element of them is read), replay happens in ``csrc/librdb200.so`` (hand-written sm_100a CUDA) through the
+C ABI of ``include/rdb200.h``.
 """
 from .tracked import (TrackedArray, TrackedReal, InstructionTape, ForwardOptimize, SkipOptimize,  # noqa: F401
                       forward, skip, value, istracked, sum, mean, dot, bcast, map_, broadcast, collect, convert)
