@@ -47,6 +47,9 @@ const SP_POOL, SP_LITERAL, SP_NONE = Int64(-1), Int64(-2), Int64(-3)
 const E_CONST, E_ADD, E_SUB, E_MUL, E_DIV, E_NEG, E_POWI, E_POW = Int32.((1, 2, 3, 4, 5, 6, 7, 8))
 const E_TANH, E_EXP, E_LOG, E_SQRT, E_SIN, E_COS, E_ABS2, E_ABS = Int32.((9, 10, 11, 12, 13, 14, 15, 16))
 const E_MAX, E_MIN, E_INV, E_SIGMOID, E_ARG = Int32.((17, 18, 19, 20, 21))
+const E_LOG1P, E_EXPM1, E_ASIN, E_ACOS, E_ATAN, E_SINH, E_COSH, E_TAN, E_ATAN2, E_HYPOT = Int32.((22, 23, 24, 25, 26, 27, 28, 29, 30, 31))
+const E_EXP2, E_EXP10, E_LOG2, E_LOG10, E_CBRT, E_ASINH, E_ACOSH, E_ATANH = Int32.((32, 33, 34, 35, 36, 37, 38, 39))
+const E_SEC, E_CSC, E_COT, E_SECH, E_CSCH, E_COTH = Int32.((40, 41, 42, 43, 44, 45))
 const WIRE_ARGS, MAX_ARGS, MAX_DIMS, MAX_EXPR_REGS = 4, 8, 4, 32     # 4 operand slots per record; operands 5.. in OP_MORE_OPERANDS records
 const OP_MORE_OPERANDS = Int32(22)
 const COMPACT_TRANSPOSE_THRESHOLD = 1 << 20
@@ -114,8 +117,19 @@ end
 Base.:-(a::Sym) = unop(E_NEG, a)
 Base.:+(a::Sym) = a
 for (f, code) in ((:tanh, :E_TANH), (:exp, :E_EXP), (:log, :E_LOG), (:sqrt, :E_SQRT), (:sin, :E_SIN), (:cos, :E_COS),
-                  (:abs2, :E_ABS2), (:abs, :E_ABS), (:inv, :E_INV))
+                  (:abs2, :E_ABS2), (:abs, :E_ABS), (:inv, :E_INV),
+                  (:log1p, :E_LOG1P), (:expm1, :E_EXPM1), (:asin, :E_ASIN), (:acos, :E_ACOS), (:atan, :E_ATAN), (:sinh, :E_SINH),
+                  (:cosh, :E_COSH), (:tan, :E_TAN), (:exp2, :E_EXP2), (:exp10, :E_EXP10), (:log2, :E_LOG2), (:log10, :E_LOG10),
+                  (:cbrt, :E_CBRT), (:asinh, :E_ASINH), (:acosh, :E_ACOSH), (:atanh, :E_ATANH), (:sec, :E_SEC), (:csc, :E_CSC),
+                  (:cot, :E_COT), (:sech, :E_SECH), (:csch, :E_CSCH), (:coth, :E_COTH))
     @eval Base.$f(a::Sym) = unop($code, a)
+end
+for (f, code) in ((:atan, :E_ATAN2), (:hypot, :E_HYPOT))            # two-argument atan(y, x) and hypot
+    @eval Base.$f(a::Sym, b::Sym) = binop($code, a, b)
+    for R in REALS
+        @eval Base.$f(a::Sym, b::$R) = binop($code, a, b)
+        @eval Base.$f(a::$R, b::Sym) = binop($code, a, b)
+    end
 end
 if isdefined(ReverseDiff, :LogExpFunctions)
     @eval ReverseDiff.LogExpFunctions.logistic(a::Sym) = unop(E_SIGMOID, a)

@@ -41,9 +41,11 @@ OP_SCALAR_BLOCK = 21
 SP_POOL, SP_LITERAL, SP_NONE = -1, -2, -3
 ELEMENTWISE = (OP_NBCAST, OP_MAP, OP_BCAST, OP_BCAST_ADD, OP_BCAST_SUB, OP_BCAST_MUL, OP_BCAST_DIV, OP_BCAST_LDIV, OP_BCAST_POW,
                OP_TRACKER_BCAST)
+_LN2, _LN10 = 0.6931471805599453, 2.302585092994046      # Python floats: weak in NumPy's promotion, the tape's dtype is kept
 (E_CONST, E_ADD, E_SUB, E_MUL, E_DIV, E_NEG, E_POWI, E_POW, E_TANH, E_EXP, E_LOG, E_SQRT,
  E_SIN, E_COS, E_ABS2, E_ABS, E_MAX, E_MIN, E_INV, E_SIGMOID, E_ARG,
- E_LOG1P, E_EXPM1, E_ASIN, E_ACOS, E_ATAN, E_SINH, E_COSH, E_TAN, E_ATAN2, E_HYPOT) = range(1, 32)
+ E_LOG1P, E_EXPM1, E_ASIN, E_ACOS, E_ATAN, E_SINH, E_COSH, E_TAN, E_ATAN2, E_HYPOT,
+ E_EXP2, E_EXP10, E_LOG2, E_LOG10, E_CBRT, E_ASINH, E_ACOSH, E_ATANH, E_SEC, E_CSC, E_COT, E_SECH, E_CSCH, E_COTH) = range(1, 46)
 
 _HEADER = np.dtype([
     ("magic", "<u8"), ("version", "<u4"), ("dtype", "<u4"),
@@ -243,6 +245,38 @@ def dual_eval(ops, fconst, args, dtype, order=1):
             unary(a, np.cosh(V[a]), np.sinh(V[a]), np.cosh(V[a]))
         elif code == E_TAN:
             tt = np.tan(V[a]); f1 = one + tt * tt; unary(a, tt, f1, 2 * tt * f1)
+        # third tranche (DiffRules `@define_diffrule Base.*`): exp2' = exp2(x) * logtwo; exp10' = exp10(x) * logten; log2' = inv(x) / logtwo;
+        # log10' = inv(x) / logten; cbrt' = inv(3 * cbrt(x)^2); asinh' = inv(sqrt(x^2 + 1)); acosh' = inv(sqrt(x^2 - 1));
+        # atanh' = inv(1 - x^2); sec' = sec(x) * tan(x); csc' = -csc(x) * cot(x); cot' = -(1 + cot(x)^2); sech' = -tanh(x) * sech(x);
+        # csch' = -coth(x) * csch(x); coth' = -(csch(x)^2)   (second derivatives: calculus; sec = inv(cos) etc. as Base defines them)
+        elif code == E_EXP2:
+            f0 = np.exp2(V[a]); f1 = f0 * _LN2; unary(a, f0, f1, f1 * _LN2)
+        elif code == E_EXP10:
+            f0 = np.power(10.0, V[a]); f1 = f0 * _LN10; unary(a, f0, f1, f1 * _LN10)
+        elif code == E_LOG2:
+            u = one / V[a]; f1 = u / _LN2; unary(a, np.log2(V[a]), f1, -(f1 * u))
+        elif code == E_LOG10:
+            u = one / V[a]; f1 = u / _LN10; unary(a, np.log10(V[a]), f1, -(f1 * u))
+        elif code == E_CBRT:
+            c = np.cbrt(V[a]); f1 = one / (3 * (c * c)); unary(a, c, f1, -2 * f1 / (3 * V[a]))
+        elif code == E_ASINH:
+            u = one / np.sqrt(V[a] * V[a] + one); unary(a, np.arcsinh(V[a]), u, -(V[a] * u * u * u))
+        elif code == E_ACOSH:
+            u = one / np.sqrt(V[a] * V[a] - one); unary(a, np.arccosh(V[a]), u, -(V[a] * u * u * u))
+        elif code == E_ATANH:
+            u = one / (one - V[a] * V[a]); unary(a, np.arctanh(V[a]), u, 2 * V[a] * u * u)
+        elif code == E_SEC:
+            sc = one / np.cos(V[a]); tt = np.tan(V[a]); unary(a, sc, sc * tt, sc * (tt * tt + sc * sc))
+        elif code == E_CSC:
+            cs = one / np.sin(V[a]); ct = one / np.tan(V[a]); unary(a, cs, -(cs * ct), cs * (ct * ct + cs * cs))
+        elif code == E_COT:
+            ct = one / np.tan(V[a]); f1 = -(one + ct * ct); unary(a, ct, f1, -2 * ct * f1)
+        elif code == E_SECH:
+            sh = one / np.cosh(V[a]); th = np.tanh(V[a]); unary(a, sh, -(th * sh), sh * (th * th - sh * sh))
+        elif code == E_CSCH:
+            ch = one / np.sinh(V[a]); ct = one / np.tanh(V[a]); unary(a, ch, -(ct * ch), ch * (ct * ct + ch * ch))
+        elif code == E_COTH:
+            ct = one / np.tanh(V[a]); ch = one / np.sinh(V[a]); f1 = -(ch * ch); unary(a, ct, f1, -2 * ct * f1)
         elif code in (E_ATAN2, E_HYPOT):
             # atan(y, x): (x / (y^2 + x^2), -y / (y^2 + x^2)); hypot(x, y): (x / hypot(x, y), y / hypot(x, y))
             va, vb = V[a], V[b]

@@ -21,7 +21,8 @@
 
 enum { E_CONST = 1, E_ADD, E_SUB, E_MUL, E_DIV, E_NEG, E_POWI, E_POW, E_TANH, E_EXP, E_LOG, E_SQRT, E_SIN, E_COS,
        E_ABS2, E_ABS, E_MAX, E_MIN, E_INV, E_SIGMOID, E_ARG,
-       E_LOG1P, E_EXPM1, E_ASIN, E_ACOS, E_ATAN, E_SINH, E_COSH, E_TAN, E_ATAN2, E_HYPOT };
+       E_LOG1P, E_EXPM1, E_ASIN, E_ACOS, E_ATAN, E_SINH, E_COSH, E_TAN, E_ATAN2, E_HYPOT,
+       E_EXP2, E_EXP10, E_LOG2, E_LOG10, E_CBRT, E_ASINH, E_ACOSH, E_ATANH, E_SEC, E_CSC, E_COT, E_SECH, E_CSCH, E_COTH };
 enum { SP_POOL = -1, SP_LITERAL = -2, SP_NONE = -3 };
 #define MAX_REGS 34
 
@@ -93,6 +94,20 @@ static int dual2(const int32_t *ops, int64_t n_ops, const double *fc, const doub
             case E_SINH: f0 = sinh(V[a]); f1 = cosh(V[a]); break;
             case E_COSH: f0 = cosh(V[a]); f1 = sinh(V[a]); break;
             case E_TAN: { double tt = tan(V[a]); f0 = tt; f1 = 1.0 + tt * tt; } break;
+            case E_EXP2: f0 = exp2(V[a]); f1 = f0 * 0.69314718055994530942; break;
+            case E_EXP10: f0 = pow(10.0, V[a]); f1 = f0 * 2.30258509299404568402; break;
+            case E_LOG2: f0 = log2(V[a]); f1 = 1.0 / V[a] / 0.69314718055994530942; break;
+            case E_LOG10: f0 = log10(V[a]); f1 = 1.0 / V[a] / 2.30258509299404568402; break;
+            case E_CBRT: { double c = cbrt(V[a]); f0 = c; f1 = 1.0 / (3.0 * (c * c)); } break;
+            case E_ASINH: f0 = asinh(V[a]); f1 = 1.0 / sqrt(V[a] * V[a] + 1.0); break;
+            case E_ACOSH: f0 = acosh(V[a]); f1 = 1.0 / sqrt(V[a] * V[a] - 1.0); break;
+            case E_ATANH: f0 = atanh(V[a]); f1 = 1.0 / (1.0 - V[a] * V[a]); break;
+            case E_SEC: { double sc = 1.0 / cos(V[a]); f0 = sc; f1 = sc * tan(V[a]); } break;
+            case E_CSC: { double cs = 1.0 / sin(V[a]); f0 = cs; f1 = -(cs * (1.0 / tan(V[a]))); } break;
+            case E_COT: { double ct = 1.0 / tan(V[a]); f0 = ct; f1 = -(1.0 + ct * ct); } break;
+            case E_SECH: { double sh = 1.0 / cosh(V[a]); f0 = sh; f1 = -(tanh(V[a]) * sh); } break;
+            case E_CSCH: { double ch = 1.0 / sinh(V[a]); f0 = ch; f1 = -((1.0 / tanh(V[a])) * ch); } break;
+            case E_COTH: { double ch = 1.0 / sinh(V[a]); f0 = 1.0 / tanh(V[a]); f1 = -(ch * ch); } break;
             case E_ATAN2: { double va = V[a], vb = V[b], r2 = va * va + vb * vb, ga = vb / r2, gb = -va / r2;
                             double t0 = ga * D0[a] + gb * D0[b], t1 = ga * D1[a] + gb * D1[b];
                             V[r] = atan2(va, vb); D0[r] = t0; D1[r] = t1; unary = 0; } break;

@@ -12,7 +12,7 @@ C ABI of ``include/rdb200.h``.
 from .tracked import (TrackedArray, TrackedReal, InstructionTape, ForwardOptimize, SkipOptimize,  # noqa: F401
                       forward, skip, value, istracked, sum, mean, dot, bcast, map_, broadcast, collect, convert)
 from .expr import (tanh, exp, log, sqrt, sin, cos, abs2, abs_, inv, logistic, max_, min_, log1p, expm1, asin, acos, atan, sinh, cosh,
-                   tan, hypot)          # noqa: F401
+                   tan, hypot, exp2, exp10, log2, log10, cbrt, asinh, acosh, atanh, sec, csc, cot, sech, csch, coth)          # noqa: F401
 from .api import (GradientTape, JacobianTape, HessianTape, CompiledTape, DiffResult, compile,      # noqa: F401
                   gradient_, jacobian_, hessian_, gradient, jacobian, hessian, GradientPipeline, seeded_forward_pass, shard_range, shard_bounds,
                   make_comm, gather_jacobian_, gather_hessian_)

@@ -28,6 +28,14 @@ template <> struct M<double> {
     static __device__ __forceinline__ double tan_(double x) { return tan(x); }
     static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
     static __device__ __forceinline__ double hypot_(double x, double y) { return hypot(x, y); }
+    static __device__ __forceinline__ double exp2_(double x) { return exp2(x); }
+    static __device__ __forceinline__ double exp10_(double x) { return exp10(x); }
+    static __device__ __forceinline__ double log2_(double x) { return log2(x); }
+    static __device__ __forceinline__ double log10_(double x) { return log10(x); }
+    static __device__ __forceinline__ double cbrt_(double x) { return cbrt(x); }
+    static __device__ __forceinline__ double asinh_(double x) { return asinh(x); }
+    static __device__ __forceinline__ double acosh_(double x) { return acosh(x); }
+    static __device__ __forceinline__ double atanh_(double x) { return atanh(x); }
 };
 template <> struct M<float> {
     static __device__ __forceinline__ float tanh_(float x) { return tanhf(x); }
@@ -48,6 +56,14 @@ template <> struct M<float> {
     static __device__ __forceinline__ float tan_(float x) { return tanf(x); }
     static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
     static __device__ __forceinline__ float hypot_(float x, float y) { return hypotf(x, y); }
+    static __device__ __forceinline__ float exp2_(float x) { return exp2f(x); }
+    static __device__ __forceinline__ float exp10_(float x) { return exp10f(x); }
+    static __device__ __forceinline__ float log2_(float x) { return log2f(x); }
+    static __device__ __forceinline__ float log10_(float x) { return log10f(x); }
+    static __device__ __forceinline__ float cbrt_(float x) { return cbrtf(x); }
+    static __device__ __forceinline__ float asinh_(float x) { return asinhf(x); }
+    static __device__ __forceinline__ float acosh_(float x) { return acoshf(x); }
+    static __device__ __forceinline__ float atanh_(float x) { return atanhf(x); }
 };
 
 template <typename T>
@@ -273,6 +289,24 @@ __device__ __forceinline__ void eval_expr(const int4 *__restrict__ ops, int n_op
             case E_SINH: { f0 = M<T>::sinh_(V[a]); f1 = M<T>::cosh_(V[a]); f2 = f0; } break;
             case E_COSH: { f0 = M<T>::cosh_(V[a]); f1 = M<T>::sinh_(V[a]); f2 = f0; } break;
             case E_TAN: { const T tt = M<T>::tan_(V[a]); f0 = tt; f1 = (T)1 + tt * tt; f2 = (T)2 * tt * f1; } break;
+            // third tranche (DiffRules): exp2' = exp2(x) logtwo, exp10' = exp10(x) logten, log2' = inv(x) / logtwo, log10' = inv(x) / logten,
+            // cbrt' = inv(3 cbrt(x)^2), asinh' = inv(sqrt(x^2 + 1)), acosh' = inv(sqrt(x^2 - 1)), atanh' = inv(1 - x^2),
+            // sec' = sec(x) tan(x), csc' = -csc(x) cot(x), cot' = -(1 + cot(x)^2), sech' = -tanh(x) sech(x), csch' = -coth(x) csch(x),
+            // coth' = -(csch(x)^2); the reciprocal functions are evaluated as Julia defines them (inv(cos(x)), ...)
+            case E_EXP2: { const T l = (T)0.69314718055994530942; f0 = M<T>::exp2_(V[a]); f1 = f0 * l; f2 = f1 * l; } break;
+            case E_EXP10: { const T l = (T)2.30258509299404568402; f0 = M<T>::exp10_(V[a]); f1 = f0 * l; f2 = f1 * l; } break;
+            case E_LOG2: { const T l = (T)0.69314718055994530942, u = (T)1 / V[a]; f0 = M<T>::log2_(V[a]); f1 = u / l; f2 = -(f1 * u); } break;
+            case E_LOG10: { const T l = (T)2.30258509299404568402, u = (T)1 / V[a]; f0 = M<T>::log10_(V[a]); f1 = u / l; f2 = -(f1 * u); } break;
+            case E_CBRT: { const T c = M<T>::cbrt_(V[a]); f0 = c; f1 = (T)1 / ((T)3 * (c * c)); f2 = (T)-2 * f1 / ((T)3 * V[a]); } break;
+            case E_ASINH: { const T u = (T)1 / M<T>::sqrt_(V[a] * V[a] + (T)1); f0 = M<T>::asinh_(V[a]); f1 = u; f2 = -(V[a] * u * u * u); } break;
+            case E_ACOSH: { const T u = (T)1 / M<T>::sqrt_(V[a] * V[a] - (T)1); f0 = M<T>::acosh_(V[a]); f1 = u; f2 = -(V[a] * u * u * u); } break;
+            case E_ATANH: { const T u = (T)1 / ((T)1 - V[a] * V[a]); f0 = M<T>::atanh_(V[a]); f1 = u; f2 = (T)2 * V[a] * u * u; } break;
+            case E_SEC: { const T sc = (T)1 / M<T>::cos_(V[a]), tt = M<T>::tan_(V[a]); f0 = sc; f1 = sc * tt; f2 = sc * (tt * tt + sc * sc); } break;
+            case E_CSC: { const T cs = (T)1 / M<T>::sin_(V[a]), ct = (T)1 / M<T>::tan_(V[a]); f0 = cs; f1 = -(cs * ct); f2 = cs * (ct * ct + cs * cs); } break;
+            case E_COT: { const T ct = (T)1 / M<T>::tan_(V[a]); f0 = ct; f1 = -((T)1 + ct * ct); f2 = (T)-2 * ct * f1; } break;
+            case E_SECH: { const T sh = (T)1 / M<T>::cosh_(V[a]), th = M<T>::tanh_(V[a]); f0 = sh; f1 = -(th * sh); f2 = sh * (th * th - sh * sh); } break;
+            case E_CSCH: { const T ch = (T)1 / M<T>::sinh_(V[a]), ct = (T)1 / M<T>::tanh_(V[a]); f0 = ch; f1 = -(ct * ch); f2 = ch * (ct * ct + ch * ch); } break;
+            case E_COTH: { const T ct = (T)1 / M<T>::tanh_(V[a]), ch = (T)1 / M<T>::sinh_(V[a]); f0 = ct; f1 = -(ch * ch); f2 = (T)-2 * ct * f1; } break;
             case E_ATAN2:
             case E_HYPOT: {
                 // y = g(a, b) with partials (ga, gb) and second partials (gaa, gab, gbb):

@@ -260,6 +260,33 @@ static bool emit_instruction(Gen &g, const ExprParams &P, const int32_t *ops, co
                 o << "    const T t_" << r << " = " << g.fn("tan") << "(" << g.V(a) << ");\n";
                 g.unary(r, a, "t_" + std::to_string(r), g.one() + " + t_" + std::to_string(r) + " * t_" + std::to_string(r));
                 break;
+            case E_EXP2: case E_EXP10: {
+                const std::string R = std::to_string(r), l = code == E_EXP2 ? "(T)0.69314718055994530942" : "(T)2.30258509299404568402";
+                o << "    const T t_" << R << " = " << g.fn(code == E_EXP2 ? "exp2" : "exp10") << "(" << g.V(a) << ");\n";
+                g.unary(r, a, "t_" + R, "t_" + R + " * " + l);
+            } break;
+            case E_LOG2: g.unary(r, a, g.fn("log2") + "(" + g.V(a) + ")", g.one() + " / " + g.V(a) + " / (T)0.69314718055994530942"); break;
+            case E_LOG10: g.unary(r, a, g.fn("log10") + "(" + g.V(a) + ")", g.one() + " / " + g.V(a) + " / (T)2.30258509299404568402"); break;
+            case E_CBRT: {
+                const std::string R = std::to_string(r);
+                o << "    const T t_" << R << " = " << g.fn("cbrt") << "(" << g.V(a) << ");\n";
+                g.unary(r, a, "t_" + R, g.one() + " / ((T)3 * (t_" + R + " * t_" + R + "))");
+            } break;
+            case E_ASINH: g.unary(r, a, g.fn("asinh") + "(" + g.V(a) + ")", g.one() + " / " + g.fn("sqrt") + "(" + g.V(a) + " * " + g.V(a) + " + " + g.one() + ")"); break;
+            case E_ACOSH: g.unary(r, a, g.fn("acosh") + "(" + g.V(a) + ")", g.one() + " / " + g.fn("sqrt") + "(" + g.V(a) + " * " + g.V(a) + " - " + g.one() + ")"); break;
+            case E_ATANH: g.unary(r, a, g.fn("atanh") + "(" + g.V(a) + ")", g.one() + " / (" + g.one() + " - " + g.V(a) + " * " + g.V(a) + ")"); break;
+            case E_SEC: case E_CSC: case E_COT: case E_SECH: case E_CSCH: case E_COTH: {
+                // the reciprocal functions as Julia defines them: t = inv(cos | sin | tan | cosh | sinh | tanh)
+                const std::string R = std::to_string(r), t = "t_" + R, u = "u_" + R;
+                const char *inner = code == E_SEC ? "cos" : code == E_CSC ? "sin" : code == E_COT ? "tan" : code == E_SECH ? "cosh" : code == E_CSCH ? "sinh" : "tanh";
+                o << "    const T " << t << " = " << g.one() << " / " << g.fn(inner) << "(" << g.V(a) << ");\n";
+                if (code == E_SEC) { o << "    const T " << u << " = " << g.fn("tan") << "(" << g.V(a) << ");\n"; g.unary(r, a, t, t + " * " + u); }
+                else if (code == E_CSC) { o << "    const T " << u << " = " << g.one() << " / " << g.fn("tan") << "(" << g.V(a) << ");\n"; g.unary(r, a, t, "-(" + t + " * " + u + ")"); }
+                else if (code == E_COT) g.unary(r, a, t, "-(" + g.one() + " + " + t + " * " + t + ")");
+                else if (code == E_SECH) { o << "    const T " << u << " = " << g.fn("tanh") << "(" << g.V(a) << ");\n"; g.unary(r, a, t, "-(" + u + " * " + t + ")"); }
+                else if (code == E_CSCH) { o << "    const T " << u << " = " << g.one() << " / " << g.fn("tanh") << "(" << g.V(a) << ");\n"; g.unary(r, a, t, "-(" + u + " * " + t + ")"); }
+                else { o << "    const T " << u << " = " << g.one() << " / " << g.fn("sinh") << "(" << g.V(a) << ");\n"; g.unary(r, a, t, "-(" + u + " * " + u + ")"); }
+            } break;
             case E_ATAN2: case E_HYPOT: {
                 const std::string R = std::to_string(r);
                 if (code == E_ATAN2) {

@@ -131,6 +131,21 @@ sinh = _unary(P.E_SINH, np.sinh)
 cosh = _unary(P.E_COSH, np.cosh)
 tan = _unary(P.E_TAN, np.tan)
 _atan1 = _unary(P.E_ATAN, np.arctan)
+# third tranche; sec/csc/cot/sech/csch/coth are the reciprocals Julia defines them as (Base: sec(z) = inv(cos(z)), ...)
+exp2 = _unary(P.E_EXP2, np.exp2)
+exp10 = _unary(P.E_EXP10, lambda v: np.power(10.0, v))
+log2 = _unary(P.E_LOG2, np.log2)
+log10 = _unary(P.E_LOG10, np.log10)
+cbrt = _unary(P.E_CBRT, np.cbrt)
+asinh = _unary(P.E_ASINH, np.arcsinh)
+acosh = _unary(P.E_ACOSH, np.arccosh)
+atanh = _unary(P.E_ATANH, np.arctanh)
+sec = _unary(P.E_SEC, lambda v: 1.0 / np.cos(v))
+csc = _unary(P.E_CSC, lambda v: 1.0 / np.sin(v))
+cot = _unary(P.E_COT, lambda v: 1.0 / np.tan(v))
+sech = _unary(P.E_SECH, lambda v: 1.0 / np.cosh(v))
+csch = _unary(P.E_CSCH, lambda v: 1.0 / np.sinh(v))
+coth = _unary(P.E_COTH, lambda v: 1.0 / np.tanh(v))
 
 
 def _binary(code, npf):
@@ -210,6 +225,20 @@ def eval_value(expr, args, dtype):
         elif code == P.E_TAN: r = np.tan(regs[a])
         elif code == P.E_ATAN2: r = np.arctan2(regs[a], regs[b])
         elif code == P.E_HYPOT: r = np.hypot(regs[a], regs[b])
+        elif code == P.E_EXP2: r = np.exp2(regs[a])
+        elif code == P.E_EXP10: r = np.power(10.0, regs[a])
+        elif code == P.E_LOG2: r = np.log2(regs[a])
+        elif code == P.E_LOG10: r = np.log10(regs[a])
+        elif code == P.E_CBRT: r = np.cbrt(regs[a])
+        elif code == P.E_ASINH: r = np.arcsinh(regs[a])
+        elif code == P.E_ACOSH: r = np.arccosh(regs[a])
+        elif code == P.E_ATANH: r = np.arctanh(regs[a])
+        elif code == P.E_SEC: r = 1.0 / np.cos(regs[a])
+        elif code == P.E_CSC: r = 1.0 / np.sin(regs[a])
+        elif code == P.E_COT: r = 1.0 / np.tan(regs[a])
+        elif code == P.E_SECH: r = 1.0 / np.cosh(regs[a])
+        elif code == P.E_CSCH: r = 1.0 / np.sinh(regs[a])
+        elif code == P.E_COTH: r = 1.0 / np.tanh(regs[a])
         else:
             raise ValueError(f"unknown scalar opcode {code}")
         regs.append(r)

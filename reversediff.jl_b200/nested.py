@@ -28,6 +28,7 @@ def _one_minus_sq(t):
 
 
 # DiffRules: code -> (value, d/da[, d/db]) on wrapped values
+_LN2, _LN10 = float(np.log(2.0)), float(np.log(10.0))
 _UNARY = {
     P.E_NEG: (lambda v: -v, lambda v, y: -1.0),
     P.E_TANH: (E.tanh, lambda v, y: _one_minus_sq(y)),                    # 1 - tanh(x)^2
@@ -47,6 +48,20 @@ _UNARY = {
     P.E_SINH: (E.sinh, lambda v, y: E.cosh(v)),
     P.E_COSH: (E.cosh, lambda v, y: E.sinh(v)),
     P.E_TAN: (E.tan, lambda v, y: 1.0 + y * y),
+    P.E_EXP2: (E.exp2, lambda v, y: y * _LN2),                             # exp2(x) * logtwo
+    P.E_EXP10: (E.exp10, lambda v, y: y * _LN10),
+    P.E_LOG2: (E.log2, lambda v, y: 1.0 / v / _LN2),                       # inv(x) / logtwo
+    P.E_LOG10: (E.log10, lambda v, y: 1.0 / v / _LN10),
+    P.E_CBRT: (E.cbrt, lambda v, y: 1.0 / (3.0 * (y * y))),                # inv(3 * cbrt(x)^2)
+    P.E_ASINH: (E.asinh, lambda v, y: 1.0 / E.sqrt(v * v + 1.0)),
+    P.E_ACOSH: (E.acosh, lambda v, y: 1.0 / E.sqrt(v * v - 1.0)),
+    P.E_ATANH: (E.atanh, lambda v, y: 1.0 / (1.0 - v * v)),
+    P.E_SEC: (E.sec, lambda v, y: y * E.tan(v)),
+    P.E_CSC: (E.csc, lambda v, y: -(y * E.cot(v))),
+    P.E_COT: (E.cot, lambda v, y: -(1.0 + y * y)),
+    P.E_SECH: (E.sech, lambda v, y: -(E.tanh(v) * y)),
+    P.E_CSCH: (E.csch, lambda v, y: -(E.coth(v) * y)),
+    P.E_COTH: (E.coth, lambda v, y: -(E.csch(v) * E.csch(v))),
 }
 _BINARY = {
     P.E_ADD: (lambda a, b: a + b, lambda a, b, y: 1.0, lambda a, b, y: 1.0),

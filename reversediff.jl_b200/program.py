@@ -98,7 +98,9 @@ E_ARG = 21      # r = arg[imm] (identity; used when the closure returns an argum
 E_LOG1P, E_EXPM1, E_ASIN, E_ACOS, E_ATAN, E_SINH, E_COSH, E_TAN = 22, 23, 24, 25, 26, 27, 28, 29
 E_ATAN2 = 30    # atan(y, x)
 E_HYPOT = 31
-E_LAST = E_HYPOT
+# third tranche (exp2 exp10 log2 log10 cbrt asinh acosh atanh sec csc cot sech csch coth), all unary, all in DiffRules.diffrules()
+(E_EXP2, E_EXP10, E_LOG2, E_LOG10, E_CBRT, E_ASINH, E_ACOSH, E_ATANH, E_SEC, E_CSC, E_COT, E_SECH, E_CSCH, E_COTH) = range(32, 46)
+E_LAST = E_COTH
 E_NAMES = {
     E_CONST: "const", E_ADD: "add", E_SUB: "sub", E_MUL: "mul", E_DIV: "div", E_NEG: "neg",
     E_POWI: "powi", E_POW: "pow", E_TANH: "tanh", E_EXP: "exp", E_LOG: "log", E_SQRT: "sqrt",
@@ -106,6 +108,8 @@ E_NAMES = {
     E_INV: "inv", E_SIGMOID: "logistic", E_ARG: "arg",
     E_LOG1P: "log1p", E_EXPM1: "expm1", E_ASIN: "asin", E_ACOS: "acos", E_ATAN: "atan", E_SINH: "sinh", E_COSH: "cosh",
     E_TAN: "tan", E_ATAN2: "atan2", E_HYPOT: "hypot",
+    E_EXP2: "exp2", E_EXP10: "exp10", E_LOG2: "log2", E_LOG10: "log10", E_CBRT: "cbrt", E_ASINH: "asinh", E_ACOSH: "acosh",
+    E_ATANH: "atanh", E_SEC: "sec", E_CSC: "csc", E_COT: "cot", E_SECH: "sech", E_CSCH: "csch", E_COTH: "coth",
 }
 WIRE_ARGS = 4     # operand slots of one instruction record
 MAX_ARGS = 8      # operands of one instruction; records 5.. travel in OP_MORE_OPERANDS records right behind it

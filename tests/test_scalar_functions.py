@@ -1,4 +1,5 @@
-"""Second tranche of the DiffRules scalar-function whitelist (``log1p expm1 asin acos atan sinh cosh tan atan(y,x) hypot``;
+"""Second and third tranche of the DiffRules scalar-function whitelist (``log1p expm1 asin acos atan sinh cosh tan atan(y,x) hypot``,
+``exp2 exp10 log2 log10 cbrt asinh acosh atanh sec csc cot sech csch coth``;
 reference: ``src/derivatives/scalars.jl:5-22``, ``src/derivatives/elementwise.jl:70-76,186-230``), after the pattern of
 ``test/derivatives/ElementwiseTests.jl:22-66``: every function as ``map``/``broadcast`` of a ``@forward`` closure, as a fused
 dot-broadcast, and as a scalar instruction, value and derivative against closed forms (CPU: oracle) and oracle against device
@@ -16,6 +17,22 @@ UNARY = {
     "sinh": (np.sinh, np.cosh, np.sinh),
     "cosh": (np.cosh, np.sinh, np.cosh),
     "tan": (np.tan, lambda x: 1 + np.tan(x) ** 2, lambda x: 2 * np.tan(x) * (1 + np.tan(x) ** 2)),
+    # third tranche: exp2 exp10 log2 log10 cbrt asinh acosh atanh sec csc cot sech csch coth
+    "exp2": (np.exp2, lambda x: np.exp2(x) * np.log(2), lambda x: np.exp2(x) * np.log(2) ** 2),
+    "exp10": (lambda x: 10.0 ** x, lambda x: 10.0 ** x * np.log(10), lambda x: 10.0 ** x * np.log(10) ** 2),
+    "log2": (np.log2, lambda x: 1 / (x * np.log(2)), lambda x: -1 / (x * x * np.log(2))),
+    "log10": (np.log10, lambda x: 1 / (x * np.log(10)), lambda x: -1 / (x * x * np.log(10))),
+    "cbrt": (np.cbrt, lambda x: x ** (-2 / 3) / 3, lambda x: -2 * x ** (-5 / 3) / 9),
+    "asinh": (np.arcsinh, lambda x: 1 / np.sqrt(x * x + 1), lambda x: -x / (x * x + 1) ** 1.5),
+    # (acosh lives on x > 1 and the test data in [0.1, 0.9]: tested as x -> acosh(x + 1.5))
+    "acosh": (lambda x: np.arccosh(x + 1.5), lambda x: 1 / np.sqrt((x + 1.5) ** 2 - 1), lambda x: -(x + 1.5) / ((x + 1.5) ** 2 - 1) ** 1.5),
+    "atanh": (np.arctanh, lambda x: 1 / (1 - x * x), lambda x: 2 * x / (1 - x * x) ** 2),
+    "sec": (lambda x: 1 / np.cos(x), lambda x: np.tan(x) / np.cos(x), lambda x: (np.tan(x) ** 2 + 1 / np.cos(x) ** 2) / np.cos(x)),
+    "csc": (lambda x: 1 / np.sin(x), lambda x: -1 / (np.sin(x) * np.tan(x)), lambda x: (1 / np.tan(x) ** 2 + 1 / np.sin(x) ** 2) / np.sin(x)),
+    "cot": (lambda x: 1 / np.tan(x), lambda x: -1 / np.sin(x) ** 2, lambda x: 2 * np.cos(x) / np.sin(x) ** 3),
+    "sech": (lambda x: 1 / np.cosh(x), lambda x: -np.tanh(x) / np.cosh(x), lambda x: (np.tanh(x) ** 2 - 1 / np.cosh(x) ** 2) / np.cosh(x)),
+    "csch": (lambda x: 1 / np.sinh(x), lambda x: -1 / (np.sinh(x) * np.tanh(x)), lambda x: (1 / np.tanh(x) ** 2 + 1 / np.sinh(x) ** 2) / np.sinh(x)),
+    "coth": (lambda x: 1 / np.tanh(x), lambda x: -1 / np.sinh(x) ** 2, lambda x: 2 * np.cosh(x) / np.sinh(x) ** 3),
 }
 BINARY = {
     # name: (numpy value, d/da, d/db)
@@ -30,7 +47,7 @@ def relerr(a, b):
 
 
 def fn(rd, name):
-    return {"atan2": lambda a, b: rd.atan(a, b)}.get(name, getattr(rd, name, None))
+    return {"atan2": lambda a, b: rd.atan(a, b), "acosh": lambda x: rd.acosh(x + 1.5)}.get(name, getattr(rd, name, None))
 
 
 def data(seed, shape=(7, 5)):
@@ -60,6 +77,18 @@ def test_oracle_unary(rd, orc, name):
             v = xin
             ref = np.zeros_like(v); ref[3] = d1(v[3]) * v[0]; ref[0] = f(v[3]) + d1(v[0] * v[1]) * v[1]; ref[1] = d1(v[0] * v[1]) * v[0]
             assert relerr(grad, ref) < 1e-13
+
+
+@pytest.mark.parametrize("name", sorted(UNARY))
+def test_oracle_unary_second_order(rd, orc, name):
+    """The oracle's hyper-dual evaluation (what the device's second-order kernels are checked against): value, first and second
+    derivative of every unary function against the closed forms."""
+    f, d1, d2 = UNARY[name]
+    g = fn(rd, name)
+    x = np.random.default_rng(2).random(12) * 0.8 + 0.1
+    ops, fc = rd.expr.trace(lambda u: g(u), 1)
+    v, D, H = orc.dual_eval(np.asarray(ops, np.int32).reshape(-1, 4), fc, [x], np.float64, order=2)
+    assert relerr(v, f(x)) < 1e-14 and relerr(D[0], d1(x)) < 1e-14 and relerr(H[0][0], d2(x)) < 1e-13
 
 
 @pytest.mark.parametrize("name", sorted(BINARY))
