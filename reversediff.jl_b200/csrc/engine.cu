@@ -1837,8 +1837,13 @@ static int ensure_second_order(rdb_tape *t) {
     if (t->second_order) return RDB_OK;
     for (auto &I : t->instrs) {
         const int op = I.rec.opcode;
-        if (!(op == OP_MUL || op == OP_ADD || op == OP_SUB || op == OP_NEG || op == OP_SUM || op == OP_MEAN || is_getindex(op) || is_elementwise(op)))
+        if (!(op == OP_MUL || op == OP_ADD || op == OP_SUB || op == OP_NEG || op == OP_SUM || op == OP_MEAN || op == OP_DOT || is_getindex(op) || is_elementwise(op)))
             return fail(RDB_EUNSUPPORTED, "hessian!: opcode %d has no forward-over-reverse rule yet", op);
+        if (op == OP_DOT) {
+            for (int a = 0; a < 2; ++a)
+                if (I.in[a].mode != OPM_PLAIN) return fail(RDB_EUNSUPPORTED, "hessian!: index-mapped `dot` operand");
+            continue;
+        }
         if (op == OP_MUL) {
             if (I.in[0].rec.tracked && I.in[1].rec.tracked && (I.in[0].mode != OPM_PLAIN || I.in[1].mode != OPM_PLAIN))
                 return fail(RDB_EUNSUPPORTED, "hessian!: `*` of two tracked operands needs both of them untransposed");
@@ -1940,7 +1945,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
             sparse_ok[ii] = views;
             if (views) td_nz[root(xid)] = 1;
             else for (int a = 0; a < I.rec.n_in; ++a) if (I.in[a].rec.tracked) td_nz[root(I.in[a].rec.buffer)] = 1;
-        } else if (I.rec.opcode == OP_MUL && I.in[0].rec.tracked && I.in[1].rec.tracked) {
+        } else if ((I.rec.opcode == OP_MUL || I.rec.opcode == OP_DOT) && I.in[0].rec.tracked && I.in[1].rec.tracked) {
             // bilinear: the cross terms delta * tv(b)' and tv(a)' * delta exist even when no adjoint tangent flows in
             for (int a = 0; a < 2; ++a) td_nz[root(I.in[a].rec.buffer)] = 1;
         } else if (!dtz) {
@@ -1949,7 +1954,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
     }
     for (size_t ii = ni; ii-- > 0;) {
         InstrPlan &I = t->instrs[ii];
-        const bool bilinear = I.rec.opcode == OP_MUL && I.in[0].rec.tracked && I.in[1].rec.tracked;
+        const bool bilinear = (I.rec.opcode == OP_MUL || I.rec.opcode == OP_DOT) && I.in[0].rec.tracked && I.in[1].rec.tracked;
         const bool nonlinear = (is_elementwise(I.rec.opcode) && !sparse_ok[ii]) || bilinear;
         for (int a = 0; a < I.rec.n_in; ++a) {
             if (!I.in[a].rec.tracked) continue;
@@ -1963,7 +1968,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
         for (int a = 0; a < I.rec.n_in; ++a)
             if (root(I.in[a].rec.buffer) == root(xid) && !is_getindex(I.rec.opcode) &&
                 ((is_elementwise(I.rec.opcode) && !sparse_ok[ii]) || (!is_elementwise(I.rec.opcode) && need_tv[root(I.rec.out)]) ||
-                 (I.rec.opcode == OP_MUL && I.in[0].rec.tracked && I.in[1].rec.tracked)))
+                 ((I.rec.opcode == OP_MUL || I.rec.opcode == OP_DOT) && I.in[0].rec.tracked && I.in[1].rec.tracked)))
                 need_x_tv = true;
     }
 
@@ -1976,7 +1981,7 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
         std::fill(need_der.begin(), need_der.end(), 0);
         for (size_t ii = 0; ii < ni; ++ii) {
             InstrPlan &I = t->instrs[ii];
-            bool nl = is_elementwise(I.rec.opcode) || (I.rec.opcode == OP_MUL && I.in[0].rec.tracked && I.in[1].rec.tracked);
+            bool nl = is_elementwise(I.rec.opcode) || ((I.rec.opcode == OP_MUL || I.rec.opcode == OP_DOT) && I.in[0].rec.tracked && I.in[1].rec.tracked);
             for (int a = 0; a < I.rec.n_in && !nl; ++a) nl = need_der[root(I.in[a].rec.buffer)] != 0;
             if (nl) need_der[root(I.rec.out)] = 1;
         }
@@ -2053,6 +2058,15 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                 case OP_SUM: case OP_MEAN: {
                     T scale = I.rec.opcode == OP_MEAN ? (T)1 / (T)I.in[0].size : (T)1;
                     KL(t, launch_colsum<T>(S(t), (T *)o.tv, (const T *)t->bufs[I.in[0].rec.buffer].tv, I.in[0].size, Kb, scale));
+                } break;
+                case OP_DOT: {
+                    // d(x . y) = dx . y + x . dy (reductions.jl:91-104): per direction k a dot product, all directions as one
+                    // (1 x n) * (n x Kb) product per tracked operand
+                    Buf &a = t->bufs[I.in[0].rec.buffer], &b = t->bufs[I.in[1].rec.buffer];
+                    const int64_t nn = a.size;
+                    bool first_term = true;
+                    if (I.in[0].rec.tracked) { KL(t, gemm_t<T>(S(t), true, false, 1, Kb, nn, (T)1, (const T *)b.val, nn, (const T *)a.tv, nn, (T)0, (T *)o.tv, 1)); first_term = false; }
+                    if (I.in[1].rec.tracked) KL(t, gemm_t<T>(S(t), true, false, 1, Kb, nn, (T)1, (const T *)a.val, nn, (const T *)b.tv, nn, first_term ? (T)0 : (T)1, (T *)o.tv, 1));
                 } break;
                 case OP_MUL: {
                     // exactly one tracked operand (checked): tangent is linear in it
@@ -2151,6 +2165,21 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                         KL(t, launch_acc_scalar<T>(S(t), (T *)b.td, b.size, Kb, dt, scale, td_zero[rb] != 0)); td_zero[rb] = 0;
                     }
                 } break;
+                case OP_DOT:
+                    // out = x . y, delta and dt_k scalars.  First order: deriv(x) += delta y.  Second order, per direction k:
+                    // td(x)_k += dt_k y + delta tv(y)_k (the second term only when y is tracked too), and the same with x and y exchanged
+                    for (int a = 0; a < 2; ++a) {
+                        if (!I.in[a].rec.tracked) continue;
+                        const int rb = root(I.in[a].rec.buffer);
+                        Buf &b = t->bufs[I.in[a].rec.buffer], &other = t->bufs[I.in[1 - a].rec.buffer];
+                        if (want_der(I.in[a].rec.buffer)) KL(t, launch_scal_acc<T>(S(t), (T *)b.der, (const T *)other.val, delta, b.size, 1, false));
+                        const bool cross = I.in[1 - a].rec.tracked;
+                        if (dt_zero && !cross) continue;
+                        if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
+                        if (!dt_zero) { KL(t, launch_scal_acc<T>(S(t), (T *)b.td, (const T *)other.val, dt, b.size, Kb, td_zero[rb] != 0)); td_zero[rb] = 0; }
+                        if (cross) { KL(t, launch_scal_acc<T>(S(t), (T *)b.td, (const T *)other.tv, delta, b.size * Kb, 1, td_zero[rb] != 0)); td_zero[rb] = 0; }
+                    }
+                    break;
                 case OP_MUL: {
                     OperandPlan &oa = I.in[0], &ob = I.in[1];
                     int64_t M = oa.rows, Kd = oa.cols, N = ob.cols;

@@ -311,6 +311,49 @@ def test_hessian_general_tape_vs_fd(rd, orc):
     assert np.max(np.abs(H - H.T)) < 1e-12 * np.max(np.abs(H))
 
 
+@pytest.mark.parametrize("block", [0, 4])
+def test_hessian_through_dot(rd, orc, block):
+    """`dot` (reductions.jl:91-104) in the forward-over-reverse sweep: both operands tracked (bilinear: the cross terms
+    delta tv(y), delta tv(x)), one tracked against a constant, the same buffer twice (x . x), and a dot of nonlinear images -
+    against closed forms where there is one and finite differences of the oracle's gradient otherwise."""
+    rng = np.random.default_rng(11)
+    n = 10
+    c = rng.random(n)
+    A = rng.random((n, n))
+    x = rng.random(n) + 0.2
+    # 1. (x + c) . x  ->  H = 2 I
+    tape = rd.HessianTape(lambda v: rd.dot(v + c, v), rng.random(n))        # (a scalar `+` of two dots would be a scalar instruction)
+    H = rd.hessian(rd.compile(tape, seed_block=block), x)
+    assert np.max(np.abs(H - 2 * np.eye(n))) < 1e-13
+    # 2. (A x) . x  ->  H = A + A'
+    tape = rd.HessianTape(lambda v: rd.dot(A @ v, v), rng.random(n))
+    H = rd.hessian(rd.compile(tape, seed_block=block), x)
+    assert relerr(H, A + A.T) < 1e-13
+    # 3. tanh.(x) . exp.(x[perm] / 2): cross terms between nonlinear images
+    perm = [int(p) for p in rng.permutation(n)]
+    f = lambda v: rd.dot(rd.bcast(lambda u: rd.tanh(u), v), rd.bcast(lambda u: rd.exp(u * 0.5), v[perm]))
+    tape = rd.HessianTape(f, rng.random(n))
+    ct = rd.compile(tape, seed_block=block)
+    H = rd.hessian(ct, x)
+    Hfd = orc.hessian_dense(tape.program_bytes(), x)
+    assert np.max(np.abs(H - Hfd)) < 1e-6 * max(1.0, np.max(np.abs(Hfd)))
+    assert np.max(np.abs(H - H.T)) < 1e-12 * np.max(np.abs(H))
+    t, e = np.tanh(x), np.exp(0.5 * x)
+    Href = np.zeros((n, n))
+    for i in range(n):                      # sum_i tanh(x_i) exp(x_perm[i] / 2)
+        j = perm[i]
+        Href[i, i] += -2 * t[i] * (1 - t[i] ** 2) * e[j]
+        Href[j, j] += t[i] * 0.25 * e[j]
+        Href[i, j] += (1 - t[i] ** 2) * 0.5 * e[j]
+        Href[j, i] += (1 - t[i] ** 2) * 0.5 * e[j]
+    assert relerr(H, Href) < 1e-12
+    # the gradient that rides along
+    res = rd.DiffResult(0.0, np.zeros(n), np.zeros((n, n), order="F"))
+    rd.hessian_(res, ct, x)
+    _, (g,) = orc.OracleTape(tape.program_bytes()).gradient([x])
+    assert relerr(res.gradient, g) < 1e-12 and relerr(res.hessian, Href) < 1e-12
+
+
 # ------------------------------------------------------------------------------------------ per-instruction
 def _cases(rd):
     from test_oracle import CASES
