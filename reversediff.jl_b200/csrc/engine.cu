@@ -1837,7 +1837,7 @@ static int ensure_second_order(rdb_tape *t) {
     if (t->second_order) return RDB_OK;
     for (auto &I : t->instrs) {
         const int op = I.rec.opcode;
-        if (!(op == OP_MUL || op == OP_ADD || op == OP_SUB || op == OP_NEG || op == OP_SUM || op == OP_MEAN || op == OP_DOT || is_getindex(op) || is_elementwise(op)))
+        if (!(op == OP_MUL || op == OP_ADD || op == OP_SUB || op == OP_NEG || op == OP_SUM || op == OP_MEAN || op == OP_DOT || op == OP_SUMDIMS || is_getindex(op) || is_elementwise(op)))
             return fail(RDB_EUNSUPPORTED, "hessian!: opcode %d has no forward-over-reverse rule yet", op);
         if (op == OP_DOT) {
             for (int a = 0; a < 2; ++a)
@@ -2059,6 +2059,18 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                     T scale = I.rec.opcode == OP_MEAN ? (T)1 / (T)I.in[0].size : (T)1;
                     KL(t, launch_colsum<T>(S(t), (T *)o.tv, (const T *)t->bufs[I.in[0].rec.buffer].tv, I.in[0].size, Kb, scale));
                 } break;
+                case OP_SUMDIMS: {
+                    // linear: the same reduction of every direction's tangent (reductions.jl:39-46); the three shapes the forward sweep lowers
+                    Buf &src = t->bufs[I.in[0].rec.buffer];
+                    const int64_t d0 = src.dims[0], d1 = src.size / src.dims[0];
+                    if (o.size == 1) KL(t, launch_colsum<T>(S(t), (T *)o.tv, (const T *)src.tv, src.size, Kb, (T)1));
+                    else if (o.dims[0] == 1 && o.size == d1) KL(t, launch_colsum<T>(S(t), (T *)o.tv, (const T *)src.tv, d0, d1 * Kb, (T)1));
+                    else if (o.dims[0] == d0 && o.size == d0) {
+                        CU(cudaMemsetAsync(o.tv, 0, (size_t)(o.size * Kb) * t->es, S(t)));
+                        for (int64_t k = 0; k < Kb; ++k)
+                            KL(t, launch_mul_acc_colvec<T>(S(t), (T *)o.tv + k * o.size, (const T *)src.tv + k * src.size, (const T *)nullptr, d0, d1, 1, (T *)t->scratch, t->scratch_bytes / 8));
+                    } else return fail(RDB_EUNSUPPORTED, "sum over this combination of dimensions is not lowered");
+                } break;
                 case OP_DOT: {
                     // d(x . y) = dx . y + x . dy (reductions.jl:91-104): per direction k a dot product, all directions as one
                     // (1 x n) * (n x Kb) product per tracked operand
@@ -2163,6 +2175,18 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                     if (!dt_zero) {
                         if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
                         KL(t, launch_acc_scalar<T>(S(t), (T *)b.td, b.size, Kb, dt, scale, td_zero[rb] != 0)); td_zero[rb] = 0;
+                    }
+                } break;
+                case OP_SUMDIMS: {
+                    if (!I.in[0].rec.tracked) break;
+                    const int rb = root(I.in[0].rec.buffer);
+                    Buf &b = t->bufs[I.in[0].rec.buffer];
+                    int64_t dstride[kMaxDims], st = 1;
+                    for (int d = 0; d < kMaxDims; ++d) { dstride[d] = (o.dims[d] == 1 && b.dims[d] != 1) ? 0 : st; st *= o.dims[d]; }
+                    if (want_der(I.in[0].rec.buffer)) KL(t, launch_bcast_acc<T>(S(t), (T *)b.der, b.dims, dstride, delta, b.size, 1, o.size, false));
+                    if (!dt_zero) {
+                        if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
+                        KL(t, launch_bcast_acc<T>(S(t), (T *)b.td, b.dims, dstride, dt, b.size, Kb, o.size, td_zero[rb] != 0)); td_zero[rb] = 0;
                     }
                 } break;
                 case OP_DOT:

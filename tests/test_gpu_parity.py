@@ -354,6 +354,37 @@ def test_hessian_through_dot(rd, orc, block):
     assert relerr(res.gradient, g) < 1e-12 and relerr(res.hessian, Href) < 1e-12
 
 
+@pytest.mark.parametrize("dims", [1, 2, (1, 2)])
+@pytest.mark.parametrize("block", [0, 5])
+def test_hessian_through_sum_dims(rd, orc, dims, block):
+    """`sum(x, dims)` (reductions.jl:39-46) in the forward-over-reverse sweep: column sums, row sums and the full reduction of a
+    nonlinear image, a nonlinear closure on top - against the closed form f = sum_g tanh(s_g), s_g = sum of x^2 over group g."""
+    rng = np.random.default_rng(13)
+    r, c = 4, 3
+    n = r * c
+    f = lambda v: rd.sum(rd.bcast(lambda u: rd.tanh(u), rd.sum(rd.bcast(lambda u: u * u, v.reshape(r, c)), dims=dims)))
+    tape = rd.HessianTape(f, rng.random(n))
+    ct = rd.compile(tape, seed_block=block)
+    x = rng.random(n) * 0.8 + 0.1
+    H = rd.hessian(ct, x)
+    X = x.reshape(r, c, order="F")
+    grp = np.zeros((r, c), dtype=int)                    # group id of every element
+    if dims == 1: grp[:] = np.arange(c)[None, :]
+    elif dims == 2: grp[:] = np.arange(r)[:, None]
+    g = grp.reshape(-1, order="F")
+    s = np.array([np.sum(x[g == k] ** 2) for k in range(g.max() + 1)])
+    t = np.tanh(s)
+    Href = np.zeros((n, n))
+    for i in range(n):
+        for j in range(n):
+            if g[i] != g[j]: continue
+            k = g[i]
+            Href[i, j] = -2 * t[k] * (1 - t[k] ** 2) * 4 * x[i] * x[j] + (2 * (1 - t[k] ** 2) if i == j else 0.0)
+    assert relerr(H, Href) < 1e-12
+    assert np.max(np.abs(H - orc.hessian_dense(tape.program_bytes(), x))) < 1e-6
+    _ = X
+
+
 # ------------------------------------------------------------------------------------------ per-instruction
 def _cases(rd):
     from test_oracle import CASES
