@@ -2091,16 +2091,17 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                         for (int64_t k = 0; k < Kb; ++k)
                             KL(t, gemm_t<T>(S(t), false, false, M, N, Kd, (T)1, (const T *)a.tv + k * a.size, M, (const T *)b.val, Kd, (T)1, (T *)o.tv + k * o.size, M));
                     } else if (ob.rec.tracked) {
-                        if (ob.mode != OPM_PLAIN) return fail(RDB_EUNSUPPORTED, "hessian!: transposed tracked `*` operand");
                         Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
-                        bool st = oa.mode == OPM_FOLDED_T;
-                        KL(t, gemm_t<T>(S(t), st, false, M, N * Kb, Kd, (T)1, (const T *)a.val, st ? oa.cols : oa.rows, (const T *)b.tv, Kd, (T)0, (T *)o.tv, M));
+                        const bool st = oa.mode == OPM_FOLDED_T, sb = ob.mode == OPM_FOLDED_T;
+                        if (!sb) KL(t, gemm_t<T>(S(t), st, false, M, N * Kb, Kd, (T)1, (const T *)a.val, st ? oa.cols : oa.rows, (const T *)b.tv, Kd, (T)0, (T *)o.tv, M));
+                        else                                  // b is the transposed view of a tracked N x Kd buffer: its tangents are stored untransposed, one product per direction
+                            for (int64_t k = 0; k < Kb; ++k)
+                                KL(t, gemm_t<T>(S(t), st, true, M, N, Kd, (T)1, (const T *)a.val, st ? oa.cols : oa.rows, (const T *)b.tv + k * b.size, ob.cols, (T)0, (T *)o.tv + k * o.size, M));
                     } else {
-                        if (oa.mode != OPM_PLAIN) return fail(RDB_EUNSUPPORTED, "hessian!: transposed tracked `*` operand");
                         Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
-                        bool st = ob.mode == OPM_FOLDED_T;
+                        const bool sa = oa.mode == OPM_FOLDED_T, st = ob.mode == OPM_FOLDED_T;
                         for (int64_t k = 0; k < Kb; ++k)
-                            KL(t, gemm_t<T>(S(t), false, st, M, N, Kd, (T)1, (const T *)a.tv + k * a.size, M, (const T *)b.val, st ? ob.cols : ob.rows, (T)0, (T *)o.tv + k * o.size, M));
+                            KL(t, gemm_t<T>(S(t), sa, st, M, N, Kd, (T)1, (const T *)a.tv + k * a.size, sa ? oa.cols : oa.rows, (const T *)b.val, st ? ob.cols : ob.rows, (T)0, (T *)o.tv + k * o.size, M));
                     }
                 } break;
                 default: {   // elementwise closures
@@ -2230,6 +2231,19 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                             KL(t, gemm_t<T>(S(t), false, true, M, Kd, N, (T)1, delta, M, (const T *)b.tv + k * b.size, Kd, z ? (T)0 : (T)1, (T *)a.td + k * a.size, M));
                         }
                         td_zero[ra] = 0;
+                    } else if (ob.rec.tracked && ob.mode == OPM_FOLDED_T) {
+                        // b = B' with B (N x Kd) tracked: the adjoints are computed directly transposed (arithmetic.jl:272-285 on the
+                        // Adjoint): deriv(B) += delta' op(a), td(B)_k += dt_k' op(a)
+                        const int rb = root(ob.rec.buffer);
+                        Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
+                        const bool st = oa.mode == OPM_FOLDED_T;
+                        if (want_der(ob.rec.buffer)) KL(t, gemm_t<T>(S(t), true, st, N, Kd, M, (T)1, delta, M, (const T *)a.val, st ? oa.cols : oa.rows, (T)1, (T *)b.der, N));
+                        if (!dt_zero) {
+                            if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
+                            for (int64_t k = 0; k < Kb; ++k)
+                                KL(t, gemm_t<T>(S(t), true, st, N, Kd, M, (T)1, dt + k * o.size, M, (const T *)a.val, st ? oa.cols : oa.rows, td_zero[rb] ? (T)0 : (T)1, (T *)b.td + k * b.size, N));
+                            td_zero[rb] = 0;
+                        }
                     } else if (ob.rec.tracked) {
                         const int rb = root(ob.rec.buffer);
                         Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
@@ -2238,6 +2252,18 @@ static int hessian_impl(rdb_tape *t, int64_t cb, int64_t ce, void *result, int64
                         if (!dt_zero) {
                             if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
                             KL(t, gemm_t<T>(S(t), !st, false, Kd, N * Kb, M, (T)1, (const T *)a.val, st ? oa.cols : oa.rows, dt, M, td_zero[rb] ? (T)0 : (T)1, (T *)b.td, Kd));
+                            td_zero[rb] = 0;
+                        }
+                    } else if (oa.mode == OPM_FOLDED_T) {
+                        // a = A' with A (Kd x M) tracked: deriv(A) += op(b) delta', td(A)_k += op(b) dt_k'
+                        const int rb = root(oa.rec.buffer);
+                        Buf &a = t->bufs[oa.rec.buffer], &b = t->bufs[ob.rec.buffer];
+                        const bool st = ob.mode == OPM_FOLDED_T;
+                        if (want_der(oa.rec.buffer)) KL(t, gemm_t<T>(S(t), st, true, Kd, M, N, (T)1, (const T *)b.val, st ? ob.cols : ob.rows, delta, M, (T)1, (T *)a.der, Kd));
+                        if (!dt_zero) {
+                            if (td_zero[rb] && rb == root(xid)) OK(overwrite_x_td());
+                            for (int64_t k = 0; k < Kb; ++k)
+                                KL(t, gemm_t<T>(S(t), st, true, Kd, M, N, (T)1, (const T *)b.val, st ? ob.cols : ob.rows, dt + k * o.size, M, td_zero[rb] ? (T)0 : (T)1, (T *)a.td + k * a.size, Kd));
                             td_zero[rb] = 0;
                         }
                     } else {

@@ -385,6 +385,44 @@ def test_hessian_through_sum_dims(rd, orc, dims, block):
     _ = X
 
 
+@pytest.mark.parametrize("side", ["left", "right"])
+@pytest.mark.parametrize("block", [0, 5])
+def test_hessian_through_transposed_tracked_operand(rd, orc, side, block):
+    """`*` whose tracked operand is an Adjoint (X' * C and C * X'): tangents and adjoint tangents are stored untransposed and the
+    products read / write them through the transpose flags, as the first-order sweep does (arithmetic.jl:272-285)."""
+    rng = np.random.default_rng(17)
+    r, c, m = 4, 3, 5
+    n = r * c
+    if side == "left":
+        C = rng.random((r, m)) - 0.5
+        f = lambda v: rd.sum(rd.bcast(lambda u: rd.tanh(u), v.reshape(r, c).T @ C))          # Z = X' C  (c x m)
+    else:
+        C = rng.random((m, c)) - 0.5
+        f = lambda v: rd.sum(rd.bcast(lambda u: rd.tanh(u), C @ v.reshape(r, c).T))          # Z = C X'  (m x r)
+    tape = rd.HessianTape(f, rng.random(n))
+    ct = rd.compile(tape, seed_block=block)
+    x = rng.random(n) - 0.3
+    H = rd.hessian(ct, x)
+    X = x.reshape(r, c, order="F")
+    Z = X.T @ C if side == "left" else C @ X.T
+    t = np.tanh(Z); d2 = -2 * t * (1 - t * t)
+    Href = np.zeros((n, n))
+    lin = lambda i, j: i + j * r
+    for i in range(r):
+        for j in range(c):
+            for i2 in range(r):
+                for j2 in range(c):
+                    if side == "left":        # Z[j, k] = sum_i X[i, j] C[i, k]
+                        if j == j2: Href[lin(i, j), lin(i2, j2)] = np.sum(d2[j, :] * C[i, :] * C[i2, :])
+                    else:                     # Z[k, i] = sum_j C[k, j] X[i, j]
+                        if i == i2: Href[lin(i, j), lin(i2, j2)] = np.sum(d2[:, i] * C[:, j] * C[:, j2])
+    assert relerr(H, Href) < 1e-12
+    res = rd.DiffResult(0.0, np.zeros(n), np.zeros((n, n), order="F"))
+    rd.hessian_(res, ct, x)
+    _, (g,) = orc.OracleTape(tape.program_bytes()).gradient([x])
+    assert relerr(res.gradient, g) < 1e-12
+
+
 # ------------------------------------------------------------------------------------------ per-instruction
 def _cases(rd):
     from test_oracle import CASES
