@@ -50,3 +50,24 @@ def test_scalar_opcodes_agree_everywhere(rd, orc):
         assert len(names) == len(vals)
         jvals.update(zip(names, vals))
     assert jvals == {n: v for n, v in py.items() if n != "E_LAST"}
+
+
+def test_instruction_opcodes_agree_everywhere(rd, orc):
+    P = rd.program
+    py = {n: getattr(P, n) for n in dir(P) if re.fullmatch(r"OP_[A-Z0-9_]+", n) and isinstance(getattr(P, n), int)}
+    assert sorted(py.values()) == list(range(1, max(py.values()) + 1))
+    src = open(os.path.join(ROOT, "reversediff.jl_b200", "csrc", "program.h")).read()
+    m = re.search(r"enum Opcode[^{]*\{(.*?)\};", src, re.S)
+    body = re.sub(r"//[^\n]*", "", m.group(1))
+    eng = {n: int(v) for n, v in re.findall(r"(OP_[A-Z0-9_]+)\s*=\s*(\d+)", body)}
+    assert eng == py
+    porc = {n: getattr(orc, n) for n in dir(orc) if re.fullmatch(r"OP_[A-Z0-9_]+", n) and isinstance(getattr(orc, n), int)}
+    assert porc == py
+    jl = open(os.path.join(ROOT, "julia", "ReverseDiffB200.jl")).read()
+    jvals = {}
+    for m in re.finditer(r"const\s+((?:OP_[A-Z0-9_]+\s*,\s*)*OP_[A-Z0-9_]+)\s*=\s*Int32\.?\(\(?([^)]*)\)", jl):
+        names = [n.strip() for n in m.group(1).split(",")]
+        vals = [int(v) for v in m.group(2).split(",") if v.strip()]
+        assert len(names) == len(vals), m.group(0)
+        jvals.update(zip(names, vals))
+    assert jvals == py
