@@ -1355,8 +1355,8 @@ umma_ozaki2c_kernel(const __grid_constant__ CUtensorMap tmAmc, const __grid_cons
         // ---- trimmed operands (plane words): only `na` planes of op(A) and `nb` of op(B) are live.
         //  * ROLES: the operand with fewer live planes takes the A role (128-row tiles): one MMA then covers up to four planes of
         //    the other operand (merged N), where the opposite assignment would issue N = 64 MMAs at 2/3 of the pipe rate.  If that
-        //    is op(B) the CTA computes a tile of C^T = op(B)^T op(A)^T and its epilogue addresses C transposed (P.allow_swap: the
-        //    host checked that both tilings have the same number of clusters).
+        //    is op(B) the CTA computes a tile of C^T = op(B)^T op(A)^T and its epilogue addresses C transposed (both tilings have
+        //    the same number of clusters because column tiles are padded to pairs; P.allow_swap = 0 switches the swap off).
         //  * SHARING: the two CTAs of the cluster multicast whichever role weighs more per K-block: the A role (same rows, adjacent
         //    column tiles - the dense geometry) or the B role (adjacent row tiles, same columns).
         //  * RING: a stage holds just the live planes, so the 184 KB of the two dense stages become up to 8 stages: the loads of a
